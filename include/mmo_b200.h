@@ -1,0 +1,235 @@
+/* mmo_b200.h -- C ABI of libmmo_b200.so: the B200 (sm_100a) implementation of MMO's
+ * ligand-receptor scoring hot path.
+ *
+ * The reference (UnixJunkie/MMO) has no FFI on this path: the "operator API" is a set of OCaml
+ * functions in src/mol.ml, src/G3D.ml, src/grid.ml, src/SO3.ml and the drivers in src/lds.ml.
+ * Each entry point below names the reference function it replaces (file:line relative to
+ * /root/reference).  INTEGRATION.md shows the OCaml `external` + C stub a maintainer adds.
+ *
+ * Conventions
+ *  - every function returns 0 (MMO_OK) on success, a negative MMO_E* code otherwise; the message
+ *    is available from mmo_last_error() (thread local).  No C++ exception crosses the boundary.
+ *  - the caller owns all host buffers; the library owns device memory behind opaque handles.
+ *  - OCaml `float array` is a flat unboxed double[] and can be passed as is; OCaml `int array`
+ *    must be converted to int32_t by the stub.
+ *  - one device per process (mmo_init), created AFTER any fork() (CUDA contexts do not survive
+ *    fork; run lds with --par 1/1).  Handles are not thread-safe.
+ *  - there is NO CPU fallback: without a usable CUDA device every compute call fails.
+ */
+#ifndef MMO_B200_H
+#define MMO_B200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMO_OK 0
+#define MMO_EINVAL (-1)   /* bad argument */
+#define MMO_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, out of memory) */
+#define MMO_ESTATE (-3)   /* library not initialised / handle destroyed */
+#define MMO_ENCCL (-4)    /* NCCL not loadable or a collective failed */
+
+/* -ff BrG | BrL/Bst  (src/lds.ml:570-584) */
+#define MMO_VARIANT_GLOBAL 0   /* Mol.ene_inter_UFF_global_brute,  src/mol.ml:796-818 */
+#define MMO_VARIANT_SHIFTED 1  /* Mol.ene_inter_UFF_shifted_brute, src/mol.ml:822-849 (== _shifted_bst 928-960) */
+
+/* MMO_PREC_FP32: fp32 pair arithmetic, fp64 accumulation, close-contact pairs re-evaluated in fp64;
+ *                per-pose energy within max(1e-6*|E|, 1e-4 kcal/mol) of the reference arithmetic.
+ * MMO_PREC_FP64: every operation in IEEE double, no FMA contraction, summation order of
+ *                src/mol.ml:828-848 (receptor outer, ligand inner): bit-identical to the reference
+ *                arithmetic, hence identical argmin index and top-k order. */
+#define MMO_PREC_FP32 0
+#define MMO_PREC_FP64 1
+
+typedef struct mmo_receptor mmo_receptor;
+typedef struct mmo_ligand mmo_ligand;
+typedef struct mmo_grid mmo_grid;
+typedef struct mmo_mask mmo_mask;
+
+/* ---------------------------------------------------------------- runtime ---------------- */
+int mmo_init(int device);          /* select the CUDA device, create the library stream */
+int mmo_shutdown(void);
+const char *mmo_last_error(void);
+int mmo_device_count(int *n);
+const char *mmo_build_info(void);  /* "sm_100a, CUDA x.y, built <date>" */
+/* number of kernels this library has launched since mmo_init (bench.py's gpu_launches) */
+int64_t mmo_launch_count(void);
+/* per-kernel device time (CUDA events around every launch on the library stream); ids below */
+#define MMO_K_DIRECT_FP32 0
+#define MMO_K_HARD_FIX 1
+#define MMO_K_DIRECT_FP64 2
+#define MMO_K_INTRA 3
+#define MMO_K_GRID_BUILD 4
+#define MMO_K_INTERP 5
+#define MMO_K_PREFILTER 6
+#define MMO_K_REDUCE 7
+#define MMO_K_VDW_MASK 8
+#define MMO_K_MC 9
+int mmo_kernel_timing(int on);    /* switches collection on/off and zeroes the counters */
+int mmo_kernel_time_get(int kernel_id, double *ms, int64_t *launches);
+/* device-side timing on the library stream (CUDA events) and an L2 flush, for bench.py */
+int mmo_timer_start(void);
+int mmo_timer_stop(float *ms);
+int mmo_l2_flush(void);
+int mmo_sync(void);
+/* FP32 FMA-chain and HBM copy micro-benchmarks: the measured roofline denominators */
+int mmo_measure_fp32_peak(double *tflops);
+int mmo_measure_fp64_peak(double *tflops);
+int mmo_measure_hbm_copy(double *gbs);
+/* raw device buffers, so that a caller can keep pose batches resident in HBM */
+int mmo_dev_alloc(size_t bytes, void **dptr);
+int mmo_dev_free(void *dptr);
+int mmo_h2d(void *dptr, const void *host, size_t bytes);
+int mmo_d2h(void *host, const void *dptr, size_t bytes);
+/* page-locked host memory for the end-to-end path */
+int mmo_host_alloc(size_t bytes, void **hptr);
+int mmo_host_free(void *hptr);
+
+/* ---------------------------------------------------------------- molecules -------------- */
+/* Receptor atoms (Mol.t of the protein, src/mol.ml:17-35: xs, ys, zs, q_a, elt_a).
+ * Unsupported elements (not in src/UFF.ml:10-22) give NaN energies, like the reference. */
+int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const double *zs,
+                        const double *q, const int32_t *anum, mmo_receptor **out);
+int mmo_receptor_destroy(mmo_receptor *rec);
+
+/* Ligand (Mol.t of a ligand).  xs/ys/zs are the template conformer; for every *_poses entry point
+ * it must already be centred at the origin (lds.ml:44-52 preprocess_ligand).
+ *   r      vdW radii (mol.ml r_a), may be NULL when the centre-occupancy prefilter is not used
+ *   typ    FF atom types (mol.ml:456-462), may be NULL unless interpolated scoring is used
+ *   dists  N*N topological distances, (i,j) at i + j*N (mol.ml:151-152), may be NULL unless
+ *          intra-ligand energies are used; interacting pairs are those with dists >= 3
+ *   rotatable bonds (mol.ml:27-31): axis left[b] -> right[b], group atoms (tip excluded) in CSR form */
+int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const double *zs,
+                      const double *q, const double *r, const int32_t *anum, const int32_t *typ,
+                      const int32_t *dists,
+                      int32_t n_rbonds, const int32_t *rb_left, const int32_t *rb_right,
+                      const int32_t *rg_off, const int32_t *rg_idx, mmo_ligand **out);
+int mmo_ligand_destroy(mmo_ligand *lig);
+
+/* ---------------------------------------------------------------- direct pair path -------- */
+/* Mol.ene_inter_UFF_{global,shifted}_brute prot lig  (src/mol.ml:796-849), batched over n_poses
+ * ligand copies given by explicit coordinates: pose p, atom j at xs[p*L + j].
+ * n_poses = 1 is the literal `ene_inter : Mol.t -> float` closure of src/lds.ml:1952-1955. */
+int mmo_score_coords(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                     int64_t n_poses, const double *xs, const double *ys, const double *zs,
+                     double *out_E);
+/* same energies for poses given as (rotation, translation) of the centred template:
+ * Mol.rotate_then_translate_copy lig rot pos (src/mol.ml:669-672) then ene_inter.
+ * rot9: n_poses row-major 3x3 (Rot.t a..i, src/rot.ml:5-7); trans3: n_poses x 3. */
+int mmo_score_poses(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                    int64_t n_poses, const double *rot9, const double *trans3, double *out_E);
+/* device-resident variant (all three pointers are device memory from mmo_dev_alloc) */
+int mmo_score_poses_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                        int64_t n_poses, const double *d_rot9, const double *d_trans3, double *d_out_E);
+/* Mol.ene_inter_UFF_shifted_bst_components (src/mol.ml:928-956): EW*sum_elec and sum_vdW apart
+ * (fp64, ligand-outer order with receptor atoms in index order) */
+int mmo_score_coords_components(const mmo_receptor *rec, const mmo_ligand *lig, int64_t n_poses,
+                                const double *xs, const double *ys, const double *zs,
+                                double *out_elec, double *out_vdw);
+/* Mol.ene_intra_UFFNB_brute (src/mol.ml:881-903) for n_confs conformers of the ligand;
+ * fp64 in the reference's (i<j) order: bit-identical */
+int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const double *ys,
+                 const double *zs, double *out_E);
+/* statistics of the last FP32 direct launch: pairs whose distance was evaluated, pairs inside the
+ * 12 A cut-off, close-contact pairs re-evaluated in fp64 */
+int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64);
+/* pair statistics cost two extra instructions per pair: off by default, switch on for accounting runs */
+int mmo_set_collect_stats(int on);
+
+/* ---------------------------------------------------------------- energy grids ------------ */
+/* Grid.from_box (src/grid.ml:40-52): dims = ceil(len/step)+1, lowest corner at the origin */
+int mmo_grid_from_box(double step, double bx, double by, double bz, int32_t dims[3]);
+/* Lds.pre_calculate_FF_components_grid (src/lds.ml:452-469) with Mol.ene_inter_UFF_shifted_grid
+ * (src/mol.ml:964-989): T maps of x_dim*y_dim*z_dim float32, index i + j*x_dim + k*x_dim*y_dim,
+ * value = f32(min(1e5, E)) on masked voxels and 0 elsewhere.  mask_bits: bit idx at
+ * (mask[idx>>3] >> (idx&7)) & 1, NULL = every voxel.  out_maps (host, type-major) and out_grid
+ * (device-resident handle) may each be NULL. */
+int mmo_grid_build(const mmo_receptor *rec, double step, const int32_t dims[3],
+                   const uint8_t *mask_bits, int32_t T, const int32_t *type_anum,
+                   const double *type_q, float *out_maps, mmo_grid **out_grid);
+/* maps read back from the reference's .ba1 cache (G3D.of_ba1_file, src/G3D.ml:55-64) */
+int mmo_grid_upload(double step, const int32_t dims[3], int32_t T, const float *maps, mmo_grid **out);
+int mmo_grid_download(const mmo_grid *grid, float *maps);
+int mmo_grid_destroy(mmo_grid *grid);
+/* G3D.to_ba1_file / of_ba1_file (src/G3D.ml:14-64): raw little-endian f32 + `.dims` side-car */
+int mmo_grid_write_ba1(const mmo_grid *grid, int32_t type, const char *path);
+int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out);
+/* G3D.trilin grid arr p (src/G3D.ml:97-157) for n points against map `type` */
+int mmo_trilin(const mmo_grid *grid, int32_t type, int64_t n, const double *xs, const double *ys,
+               const double *zs, double *out);
+/* Mol.ene_inter_UFF_interp grid ff_comps lig (src/mol.ml:1012-1020); fp64 on f32 data in the
+ * reference's order: bit-identical.  The ligand needs `typ`. */
+int mmo_score_interp_coords(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
+                            const double *xs, const double *ys, const double *zs, double *out_E);
+int mmo_score_interp_poses(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
+                           const double *rot9, const double *trans3, double *out_E);
+int mmo_score_interp_poses_dev(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
+                               const double *d_rot9, const double *d_trans3, double *d_out_E);
+
+/* ---------------------------------------------------------------- vdW occupancy mask ------ */
+/* Lds.vdW_volume grid prot (src/lds.ml:148-196): bit set where dist^2 < r^2 to some atom */
+int mmo_vdw_mask_build(int32_t n, const double *xs, const double *ys, const double *zs,
+                       const double *radii, double step, const int32_t dims[3], uint8_t *out_bits,
+                       mmo_mask **out_mask);
+int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out);
+int mmo_mask_destroy(mmo_mask *mask);
+/* Mol.protein_ligand_clash (src/mol.ml:1195-1203): out_flags[p] = 1 when any atom of pose p has any
+ * of its 8 surrounding voxels set (G3D.vdW_clash_OR, src/G3D.ml:162-186) */
+int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses,
+                    const double *rot9, const double *trans3, uint8_t *out_flags);
+
+/* ---------------------------------------------------------------- rotations (host, libm) -- */
+/* SO3.rotations n (src/SO3.ml:18-39 + src/quat.ml:32-36 + src/rot.ml:136-146): n row-major 3x3 */
+int mmo_so3_rotations(int32_t n, double *rot9);
+int mmo_rot_r_xyz(double alpha, double beta, double gamma, double rot9[9]);  /* src/rot.ml:52-66 */
+int mmo_rot_decompose(const double rot9[9], double abg[3]);                  /* src/rot.ml:71-75 */
+
+/* ---------------------------------------------------------------- exhaustive rigid scan ---- */
+/* Lds.exhaustive_rigid_ligand_docking (src/lds.ml:1040-1114).
+ * Lattice = Grid.from_box trans_step over ROI.get_bounds; loop order z, y, x, rotation;
+ * frame = rot_i + n_rot*(i + j*x_dim + k*xy_dim); score = e_intra_const + ene_inter. */
+typedef struct {
+    const mmo_receptor *rec;      /* direct scorer (NULL when grid is given) */
+    const mmo_grid *grid;         /* interpolated scorer (NULL when rec is given) */
+    const mmo_ligand *lig;        /* centred ligand */
+    const mmo_mask *vdw_mask;     /* protein vdW volume prefilter; NULL = no prefilter */
+    int32_t variant, prec;
+    double roi_c[3], roi_r;       /* ROI.sphere in simulation-box coordinates */
+    double trans_step;
+    int32_t n_rot;
+    const double *rot9;           /* host, n_rot x 9 */
+    double e_intra_const;
+    int32_t topk;
+    int64_t first_point, n_points;  /* lattice-point sub-range for sharding; n_points < 0 = all */
+} mmo_scan_params;
+typedef struct {
+    int64_t n_candidates;   /* in-ROI lattice points x rotations */
+    int64_t n_scored;       /* poses that passed the prefilter and were scored */
+    double best_score;
+    int64_t best_frame;
+    double best_pos[3];
+    int32_t best_rot_i;
+    int32_t n_top;
+    int32_t lattice_dims[3];
+    int64_t pairs_evaluated, pairs_inside;   /* direct scorer only */
+    float device_ms;        /* GPU time of the scan, CUDA events on the library stream */
+} mmo_scan_result;
+int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, mmo_scan_result *res);
+/* the same scan as a resident job: rotations, lattice and buffers stay in HBM between calls, so a
+ * caller (bench.py, a multi-GPU driver) can run it slab by slab over the active lattice points
+ * (in-ROI points that passed the centre prefilter, in loop order) and read the result at the end */
+typedef struct mmo_scan_job mmo_scan_job;
+int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **out);
+int mmo_scan_num_points(const mmo_scan_job *job, int64_t *n_active_points);
+int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active);
+int mmo_scan_result_get(const mmo_scan_job *job, double *top_scores, int64_t *top_frames, mmo_scan_result *res);
+int mmo_scan_destroy(mmo_scan_job *job);
+/* K-way merge of per-GPU top-k lists: (score, frame) ascending, ties to the smaller frame */
+int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64_t *frames,
+                   const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

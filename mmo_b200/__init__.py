@@ -1,0 +1,436 @@
+"""mmo_b200 -- host-side mirror (ctypes) of the reference's scoring interface over libmmo_b200.so.
+
+The product is the C-ABI library `mmo_b200/csrc/libmmo_b200.so` (hand-written sm_100a CUDA).  This
+package only binds it for the tests and for bench.py, under the reference's own names:
+
+    Mol.ene_inter_UFF_shifted_brute / _global_brute / _shifted_bst_components   src/mol.ml:796-960
+    Mol.ene_intra_UFFNB_brute                                                    src/mol.ml:881-903
+    Mol.ene_inter_UFF_interp, G3D.trilin                                         src/mol.ml:1012-1020, src/G3D.ml:97-157
+    Lds.pre_calculate_FF_components_grid, Lds.vdW_volume                         src/lds.ml:452-469, 187-196
+    Lds.exhaustive_rigid_ligand_docking                                          src/lds.ml:1040-1114
+    SO3.rotations, Rot.r_xyz, Rot.decompose, Grid.from_box                       src/SO3.ml, src/rot.ml, src/grid.ml
+
+There is NO CPU fallback: if the shared library is missing or no B200 is visible, calls raise.
+No torch import here; numpy arrays in, numpy arrays out.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import pqrs  # noqa: F401  (host-side file formats)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmmo_b200.so")
+
+VARIANT_GLOBAL, VARIANT_SHIFTED = 0, 1      # -ff BrG | BrL/Bst
+PREC_FP32, PREC_FP64 = 0, 1
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_fp = C.POINTER(C.c_float)
+_bp = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+
+
+class MmoError(RuntimeError):
+    pass
+
+
+class ScanParams(C.Structure):
+    _fields_ = [("rec", _vp), ("grid", _vp), ("lig", _vp), ("vdw_mask", _vp),
+                ("variant", C.c_int32), ("prec", C.c_int32),
+                ("roi_c", C.c_double * 3), ("roi_r", C.c_double), ("trans_step", C.c_double),
+                ("n_rot", C.c_int32), ("rot9", _dp), ("e_intra_const", C.c_double), ("topk", C.c_int32),
+                ("first_point", C.c_int64), ("n_points", C.c_int64)]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [("n_candidates", C.c_int64), ("n_scored", C.c_int64), ("best_score", C.c_double),
+                ("best_frame", C.c_int64), ("best_pos", C.c_double * 3), ("best_rot_i", C.c_int32),
+                ("n_top", C.c_int32), ("lattice_dims", C.c_int32 * 3),
+                ("pairs_evaluated", C.c_int64), ("pairs_inside", C.c_int64), ("device_ms", C.c_float)]
+
+
+def lib():
+    """The loaded C-ABI library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MmoError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                           " (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.mmo_last_error.restype = C.c_char_p
+        L.mmo_build_info.restype = C.c_char_p
+        L.mmo_launch_count.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise MmoError(f"libmmo_b200 error {rc}: {lib().mmo_last_error().decode()}")
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+_inited = None
+
+
+def init(device: int = 0):
+    global _inited
+    _ck(lib().mmo_init(C.c_int(device)))
+    _inited = device
+
+
+def _need_init():
+    if _inited is None:
+        init(int(os.environ.get("LOCAL_RANK", os.environ.get("MMO_DEVICE", "0"))))
+
+
+def launch_count() -> int:
+    return int(lib().mmo_launch_count())
+
+
+class Receptor:
+    """Protein atoms in HBM (Mol.t of the receptor, src/mol.ml:17-35)."""
+
+    def __init__(self, xs, ys, zs, q, anum):
+        _need_init()
+        self.n = len(xs)
+        self._keep = [_d(xs), _d(ys), _d(zs), _d(q), _i(anum)]
+        self.h = _vp()
+        k = self._keep
+        _ck(lib().mmo_receptor_create(C.c_int32(self.n), k[0][1], k[1][1], k[2][1], k[3][1], k[4][1], C.byref(self.h)))
+
+    @classmethod
+    def from_mol(cls, m):
+        return cls(m.xs, m.ys, m.zs, m.q, m.anum)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mmo_receptor_destroy(self.h)
+            self.h = None
+
+
+class Ligand:
+    """Ligand template in HBM.  Coordinates must be centred for the *_poses entry points."""
+
+    def __init__(self, xs, ys, zs, q, anum, r=None, typ=None, dists=None, rb_left=None, rb_right=None,
+                 rg_off=None, rg_idx=None):
+        _need_init()
+        self.n = len(xs)
+        nrb = 0 if rb_left is None else len(rb_left)
+        null_d, null_i = C.cast(None, _dp), C.cast(None, _ip)
+        keep = [_d(xs), _d(ys), _d(zs), _d(q), _i(anum)]
+        pr = _d(r) if r is not None else (None, null_d)
+        pt = _i(typ) if typ is not None else (None, null_i)
+        pd = _i(dists) if dists is not None else (None, null_i)
+        pl = _i(rb_left) if nrb else (None, null_i)
+        prr = _i(rb_right) if nrb else (None, null_i)
+        po = _i(rg_off) if nrb else (None, null_i)
+        pi = _i(rg_idx) if nrb else (None, null_i)
+        self._keep = keep + [pr, pt, pd, pl, prr, po, pi]
+        self.h = _vp()
+        _ck(lib().mmo_ligand_create(C.c_int32(self.n), keep[0][1], keep[1][1], keep[2][1], keep[3][1], pr[1],
+                                    keep[4][1], pt[1], pd[1], C.c_int32(nrb), pl[1], prr[1], po[1], pi[1],
+                                    C.byref(self.h)))
+
+    @classmethod
+    def from_mol(cls, m, centered=True):
+        """Ligand of a pqrs.Mol; `centered` translates it to the origin as lds.ml:44-52 does
+        (Mol.translate_to lig V3.origin with the Kahan-averaged centre, mol.ml:353-356)."""
+        xs, ys, zs = m.xs, m.ys, m.zs
+        if centered:
+            c = [favg(m.xs), favg(m.ys), favg(m.zs)]
+            xs, ys, zs = m.xs + (0.0 - c[0]), m.ys + (0.0 - c[1]), m.zs + (0.0 - c[2])
+        off, idx = m.rgroup_csr()
+        o = cls(xs, ys, zs, m.q, m.anum, r=m.r, typ=m.typ, dists=m.dists, rb_left=m.rb_left, rb_right=m.rb_right,
+                rg_off=off, rg_idx=idx)
+        o.xs, o.ys, o.zs = np.array(xs), np.array(ys), np.array(zs)
+        return o
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mmo_ligand_destroy(self.h)
+            self.h = None
+
+
+def favg(a) -> float:
+    """Batteries' A.favg as restated in the oracle: Kahan-compensated sum / n (unpinned library)."""
+    s = 0.0
+    c = 0.0
+    for v in np.asarray(a, np.float64):
+        y = float(v) - c
+        t = s + y
+        c = (t - s) - y
+        s = t
+    return s / len(a)
+
+
+class EnergyGrid:
+    """T float32 energy maps, type-major, resident in HBM (G3D.t array)."""
+
+    def __init__(self, handle, step, dims, T):
+        self.h, self.step, self.dims, self.T = handle, float(step), tuple(int(d) for d in dims), int(T)
+
+    @property
+    def nvox(self):
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+    def download(self):
+        out = np.empty((self.T, self.nvox), np.float32)
+        _ck(lib().mmo_grid_download(self.h, out.ctypes.data_as(_fp)))
+        return out
+
+    def write_ba1(self, t, path):
+        _ck(lib().mmo_grid_write_ba1(self.h, C.c_int32(t), path.encode()))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mmo_grid_destroy(self.h)
+            self.h = None
+
+
+class VdwMask:
+    def __init__(self, handle, step, dims, bits=None):
+        self.h, self.step, self.dims, self.bits = handle, float(step), tuple(int(d) for d in dims), bits
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mmo_mask_destroy(self.h)
+            self.h = None
+
+
+# ------------------------------------------------------------------------------------------------
+class Mol:
+    """src/mol.ml energy functions, batched: coordinates are arrays [n_poses, L]."""
+
+    @staticmethod
+    def _score(rec, lig, variant, prec, xs, ys, zs):
+        xs = np.atleast_2d(np.asarray(xs, np.float64))
+        ys = np.atleast_2d(np.asarray(ys, np.float64))
+        zs = np.atleast_2d(np.asarray(zs, np.float64))
+        n = xs.shape[0]
+        assert xs.shape == (n, lig.n) == ys.shape == zs.shape
+        out = np.empty(n, np.float64)
+        (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+        _ck(lib().mmo_score_coords(rec.h, lig.h, C.c_int(variant), C.c_int(prec), C.c_int64(n), pa, pb, pc,
+                                   out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def ene_inter_UFF_shifted_brute(rec, lig, xs, ys, zs, prec=PREC_FP32):
+        return Mol._score(rec, lig, VARIANT_SHIFTED, prec, xs, ys, zs)
+
+    @staticmethod
+    def ene_inter_UFF_global_brute(rec, lig, xs, ys, zs, prec=PREC_FP32):
+        return Mol._score(rec, lig, VARIANT_GLOBAL, prec, xs, ys, zs)
+
+    @staticmethod
+    def ene_inter_UFF_shifted_bst_components(rec, lig, xs, ys, zs):
+        xs = np.atleast_2d(np.asarray(xs, np.float64)); ys = np.atleast_2d(np.asarray(ys, np.float64))
+        zs = np.atleast_2d(np.asarray(zs, np.float64))
+        n = xs.shape[0]
+        e = np.empty(n); v = np.empty(n)
+        (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+        _ck(lib().mmo_score_coords_components(rec.h, lig.h, C.c_int64(n), pa, pb, pc, e.ctypes.data_as(_dp),
+                                              v.ctypes.data_as(_dp)))
+        return e, v
+
+    @staticmethod
+    def score_poses(rec, lig, rot9, trans3, variant=VARIANT_SHIFTED, prec=PREC_FP32):
+        """rotate_then_translate_copy (mol.ml:669-672) + ene_inter for n poses."""
+        rot9 = np.ascontiguousarray(rot9, np.float64).reshape(-1, 9)
+        trans3 = np.ascontiguousarray(trans3, np.float64).reshape(-1, 3)
+        n = rot9.shape[0]
+        assert trans3.shape[0] == n
+        out = np.empty(n)
+        _ck(lib().mmo_score_poses(rec.h, lig.h, C.c_int(variant), C.c_int(prec), C.c_int64(n),
+                                  rot9.ctypes.data_as(_dp), trans3.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def ene_intra_UFFNB_brute(lig, xs, ys, zs):
+        xs = np.atleast_2d(np.asarray(xs, np.float64)); ys = np.atleast_2d(np.asarray(ys, np.float64))
+        zs = np.atleast_2d(np.asarray(zs, np.float64))
+        n = xs.shape[0]
+        out = np.empty(n)
+        (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+        _ck(lib().mmo_intra_nb(lig.h, C.c_int64(n), pa, pb, pc, out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def ene_inter_UFF_interp(grid, lig, xs, ys, zs):
+        xs = np.atleast_2d(np.asarray(xs, np.float64)); ys = np.atleast_2d(np.asarray(ys, np.float64))
+        zs = np.atleast_2d(np.asarray(zs, np.float64))
+        n = xs.shape[0]
+        out = np.empty(n)
+        (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+        _ck(lib().mmo_score_interp_coords(grid.h, lig.h, C.c_int64(n), pa, pb, pc, out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def interp_poses(grid, lig, rot9, trans3):
+        rot9 = np.ascontiguousarray(rot9, np.float64).reshape(-1, 9)
+        trans3 = np.ascontiguousarray(trans3, np.float64).reshape(-1, 3)
+        n = rot9.shape[0]
+        out = np.empty(n)
+        _ck(lib().mmo_score_interp_poses(grid.h, lig.h, C.c_int64(n), rot9.ctypes.data_as(_dp),
+                                         trans3.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def protein_ligand_clash(mask, lig, rot9, trans3):
+        rot9 = np.ascontiguousarray(rot9, np.float64).reshape(-1, 9)
+        trans3 = np.ascontiguousarray(trans3, np.float64).reshape(-1, 3)
+        n = rot9.shape[0]
+        out = np.empty(n, np.uint8)
+        _ck(lib().mmo_clash_poses(mask.h, lig.h, C.c_int64(n), rot9.ctypes.data_as(_dp), trans3.ctypes.data_as(_dp),
+                                  out.ctypes.data_as(_bp)))
+        return out.astype(bool)
+
+    @staticmethod
+    def last_pair_stats():
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _ck(lib().mmo_last_pair_stats(C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+
+class Grid:
+    @staticmethod
+    def from_box(step, bx, by, bz):
+        dims = (C.c_int32 * 3)()
+        _ck(lib().mmo_grid_from_box(C.c_double(step), C.c_double(bx), C.c_double(by), C.c_double(bz), dims))
+        return tuple(dims)
+
+
+class G3D:
+    @staticmethod
+    def trilin(grid, t, xs, ys, zs):
+        (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+        out = np.empty(len(a))
+        _ck(lib().mmo_trilin(grid.h, C.c_int32(t), C.c_int64(len(a)), pa, pb, pc, out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def upload(step, dims, maps):
+        maps = np.ascontiguousarray(maps, np.float32)
+        T = maps.shape[0]
+        h = _vp()
+        d = (C.c_int32 * 3)(*dims)
+        _ck(lib().mmo_grid_upload(C.c_double(step), d, C.c_int32(T), maps.ctypes.data_as(_fp), C.byref(h)))
+        return EnergyGrid(h, step, dims, T)
+
+    @staticmethod
+    def of_ba1_files(paths):
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        h = _vp()
+        _ck(lib().mmo_grid_read_ba1(arr, C.c_int32(len(paths)), C.byref(h)))
+        step, dims = _parse_dims(paths[0] + ".dims")
+        return EnergyGrid(h, step, dims, len(paths))
+
+
+def _parse_dims(fn):
+    v = [l.split(":")[1] for l in open(fn).read().strip().split("\n")]
+    return float(v[0]), (int(v[1]), int(v[2]), int(v[3]))
+
+
+class Lds:
+    @staticmethod
+    def pre_calculate_FF_components_grid(rec, step, dims, type_anum, type_q, mask_bits=None, want_host=True):
+        """src/lds.ml:452-469.  Returns (EnergyGrid, host maps or None)."""
+        _need_init()
+        T = len(type_anum)
+        (ta, pta), (tq, ptq) = _i(type_anum), _d(type_q)
+        nvox = int(dims[0]) * int(dims[1]) * int(dims[2])
+        host = np.empty((T, nvox), np.float32) if want_host else None
+        pm = C.cast(None, _bp)
+        if mask_bits is not None:
+            mask_bits = np.ascontiguousarray(mask_bits, np.uint8)
+            assert mask_bits.size >= (nvox + 7) // 8
+            pm = mask_bits.ctypes.data_as(_bp)
+        h = _vp()
+        d = (C.c_int32 * 3)(*[int(v) for v in dims])
+        _ck(lib().mmo_grid_build(rec.h, C.c_double(step), d, pm, C.c_int32(T), pta, ptq,
+                                 host.ctypes.data_as(_fp) if want_host else C.cast(None, _fp), C.byref(h)))
+        return EnergyGrid(h, step, dims, T), host
+
+    @staticmethod
+    def vdW_volume(xs, ys, zs, radii, step, dims):
+        """src/lds.ml:187-196 -> (VdwMask, bits as uint8 array, LSB-first)."""
+        _need_init()
+        (a, pa), (b, pb), (c, pc), (r, pr) = _d(xs), _d(ys), _d(zs), _d(radii)
+        nvox = int(dims[0]) * int(dims[1]) * int(dims[2])
+        bits = np.zeros((nvox + 7) // 8, np.uint8)
+        h = _vp()
+        d = (C.c_int32 * 3)(*[int(v) for v in dims])
+        _ck(lib().mmo_vdw_mask_build(C.c_int32(len(a)), pa, pb, pc, pr, C.c_double(step), d,
+                                     bits.ctypes.data_as(_bp), C.byref(h)))
+        return VdwMask(h, step, dims, bits)
+
+    @staticmethod
+    def exhaustive_rigid_ligand_docking(topk, roi, trans_step, rotations, lig, rec=None, grid=None, vdw_mask=None,
+                                        e_intra_const=0.0, variant=VARIANT_SHIFTED, prec=PREC_FP32,
+                                        first_point=0, n_points=-1):
+        """src/lds.ml:1040-1114.  roi = (cx, cy, cz, r) in simulation-box coordinates.
+        Returns dict(top_scores, top_frames, best_score, best_frame, best_pos, best_rot_i, ...)."""
+        _need_init()
+        rot = np.ascontiguousarray(rotations, np.float64).reshape(-1, 9)
+        P = ScanParams()
+        P.rec = rec.h if rec is not None else None
+        P.grid = grid.h if grid is not None else None
+        P.lig = lig.h
+        P.vdw_mask = vdw_mask.h if vdw_mask is not None else None
+        P.variant, P.prec = variant, prec
+        P.roi_c = (C.c_double * 3)(*roi[:3])
+        P.roi_r = roi[3]
+        P.trans_step = trans_step
+        P.n_rot = rot.shape[0]
+        P.rot9 = rot.ctypes.data_as(_dp)
+        P.e_intra_const = e_intra_const
+        P.topk = topk
+        P.first_point, P.n_points = first_point, n_points
+        k = max(topk, 1)
+        ts = np.empty(k); tf = np.empty(k, np.int64)
+        R = ScanResult()
+        _ck(lib().mmo_scan(C.byref(P), ts.ctypes.data_as(_dp), tf.ctypes.data_as(_lp), C.byref(R)))
+        return dict(top_scores=ts[:R.n_top].copy(), top_frames=tf[:R.n_top].copy(), best_score=R.best_score,
+                    best_frame=R.best_frame, best_pos=tuple(R.best_pos), best_rot_i=R.best_rot_i,
+                    n_candidates=R.n_candidates, n_scored=R.n_scored, lattice_dims=tuple(R.lattice_dims),
+                    pairs_evaluated=R.pairs_evaluated, pairs_inside=R.pairs_inside, device_ms=R.device_ms)
+
+
+class SO3:
+    @staticmethod
+    def rotations(n):
+        out = np.empty((n, 9))
+        _ck(lib().mmo_so3_rotations(C.c_int32(n), out.ctypes.data_as(_dp)))
+        return out
+
+
+class Rot:
+    @staticmethod
+    def r_xyz(a, b, g):
+        out = np.empty(9)
+        _ck(lib().mmo_rot_r_xyz(C.c_double(a), C.c_double(b), C.c_double(g), out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def decompose(r):
+        r = np.ascontiguousarray(r, np.float64).reshape(9)
+        out = np.empty(3)
+        _ck(lib().mmo_rot_decompose(r.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
+        return out

@@ -1,0 +1,394 @@
+// api.cu -- extern "C" entry points that move host buffers to HBM, launch, and copy results back.
+// Each function names the reference function it replaces in include/mmo_b200.h.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+#include <string>
+
+using namespace mmo;
+
+namespace {
+
+int check_variant_prec(int variant, int prec) {
+    MMO_REQUIRE(variant == MMO_VARIANT_GLOBAL || variant == MMO_VARIANT_SHIFTED, "bad variant %d", variant);
+    MMO_REQUIRE(prec == MMO_PREC_FP32 || prec == MMO_PREC_FP64, "bad precision %d", prec);
+    return MMO_OK;
+}
+
+int run_direct(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec, const PoseSrc &src,
+               int64_t n, double *d_out) {
+    if (prec == MMO_PREC_FP64) return launch_direct_fp64(rec, lig, variant, src, n, d_out);
+    return launch_direct_fp32(rec, lig, variant, src, n, d_out, rt().collect_stats);
+}
+
+int d2h_sync(void *host, const void *dev, size_t bytes) {
+    MMO_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, rt().stream));
+    MMO_CUDA(cudaStreamSynchronize(rt().stream));
+    return MMO_OK;
+}
+
+PoseSrc coords_src(const double *x, const double *y, const double *z) {
+    PoseSrc s = {};
+    s.kind = 1;
+    s.xs = x; s.ys = y; s.zs = z;
+    return s;
+}
+PoseSrc rt_src(const double *rot9, const double *trans3) {
+    PoseSrc s = {};
+    s.kind = 0;
+    s.rot9 = rot9; s.trans3 = trans3;
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ direct pair path
+int mmo_score_coords(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                     int64_t n_poses, const double *xs, const double *ys, const double *zs, double *out_E) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && lig, "mmo_score_coords: null handle");
+    MMO_TRY(check_variant_prec(variant, prec));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_coords: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(xs && ys && zs && out_E, "mmo_score_coords: null buffer");
+    const size_t m = (size_t)n_poses * lig->n;
+    DevBuf<double> dx, dy, dz, dE;
+    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    MMO_TRY(dE.alloc((size_t)n_poses));
+    MMO_TRY(run_direct(rec, lig, variant, prec, coords_src(dx.p, dy.p, dz.p), n_poses, dE.p));
+    return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
+}
+
+int mmo_score_poses(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                    int64_t n_poses, const double *rot9, const double *trans3, double *out_E) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && lig, "mmo_score_poses: null handle");
+    MMO_TRY(check_variant_prec(variant, prec));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_poses: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(rot9 && trans3 && out_E, "mmo_score_poses: null buffer");
+    DevBuf<double> dr, dt, dE;
+    MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
+    MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
+    MMO_TRY(dE.alloc((size_t)n_poses));
+    MMO_TRY(run_direct(rec, lig, variant, prec, rt_src(dr.p, dt.p), n_poses, dE.p));
+    return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
+}
+
+int mmo_score_poses_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                        int64_t n_poses, const double *d_rot9, const double *d_trans3, double *d_out_E) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && lig, "mmo_score_poses_dev: null handle");
+    MMO_TRY(check_variant_prec(variant, prec));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_poses_dev: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(d_rot9 && d_trans3 && d_out_E, "mmo_score_poses_dev: null buffer");
+    if (prec == MMO_PREC_FP64) return launch_direct_fp64(rec, lig, variant, rt_src(d_rot9, d_trans3), n_poses, d_out_E);
+    return launch_direct_fp32(rec, lig, variant, rt_src(d_rot9, d_trans3), n_poses, d_out_E, rt().collect_stats);
+}
+
+int mmo_score_coords_components(const mmo_receptor *rec, const mmo_ligand *lig, int64_t n_poses,
+                                const double *xs, const double *ys, const double *zs,
+                                double *out_elec, double *out_vdw) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && lig, "mmo_score_coords_components: null handle");
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_coords_components: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(xs && ys && zs && out_elec && out_vdw, "mmo_score_coords_components: null buffer");
+    const size_t m = (size_t)n_poses * lig->n;
+    DevBuf<double> dx, dy, dz, de, dv;
+    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    MMO_TRY(de.alloc((size_t)n_poses)); MMO_TRY(dv.alloc((size_t)n_poses));
+    MMO_TRY(launch_components_fp64(rec, lig, coords_src(dx.p, dy.p, dz.p), n_poses, de.p, dv.p));
+    MMO_TRY(d2h_sync(out_elec, de.p, (size_t)n_poses * sizeof(double)));
+    return d2h_sync(out_vdw, dv.p, (size_t)n_poses * sizeof(double));
+}
+
+int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const double *ys,
+                 const double *zs, double *out_E) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(lig, "mmo_intra_nb: null handle");
+    MMO_REQUIRE(lig->has_dists, "mmo_intra_nb: the ligand was created without topological distances");
+    MMO_REQUIRE(n_confs >= 0, "mmo_intra_nb: negative conformer count");
+    if (n_confs == 0) return MMO_OK;
+    MMO_REQUIRE(xs && ys && zs && out_E, "mmo_intra_nb: null buffer");
+    const size_t m = (size_t)n_confs * lig->n;
+    DevBuf<double> dx, dy, dz, dE;
+    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    MMO_TRY(dE.alloc((size_t)n_confs));
+    MMO_TRY(launch_intra_fp64(lig, n_confs, dx.p, dy.p, dz.p, dE.p));
+    return d2h_sync(out_E, dE.p, (size_t)n_confs * sizeof(double));
+}
+
+int mmo_set_collect_stats(int on) {
+    rt().collect_stats = on != 0;
+    return MMO_OK;
+}
+
+int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64) {
+    if (pairs_evaluated) *pairs_evaluated = rt().stat_pairs;
+    if (pairs_inside) *pairs_inside = rt().stat_inside;
+    if (pairs_fp64) *pairs_fp64 = rt().stat_fp64;
+    return MMO_OK;
+}
+
+// ------------------------------------------------------------------ energy grids
+static int grid_alloc(double step, const int32_t dims[3], int32_t T, mmo_grid **out) {
+    MMO_REQUIRE(out != nullptr, "null grid output pointer");
+    MMO_REQUIRE(step > 0.0 && dims && dims[0] > 1 && dims[1] > 1 && dims[2] > 1 && T > 0, "bad grid geometry");
+    MMO_REQUIRE((double)dims[0] * dims[1] * dims[2] < 2.0e9, "grid too large for 32-bit voxel indices");
+    mmo_grid *g = new mmo_grid();
+    g->step = step;
+    for (int d = 0; d < 3; d++) g->dims[d] = dims[d];
+    g->T = T;
+    g->nvox = (size_t)dims[0] * dims[1] * dims[2];
+    int rc = g->maps.alloc(g->nvox * (size_t)T);
+    if (rc != MMO_OK) { delete g; return rc; }
+    *out = g;
+    return MMO_OK;
+}
+
+int mmo_grid_build(const mmo_receptor *rec, double step, const int32_t dims[3],
+                   const uint8_t *mask_bits, int32_t T, const int32_t *type_anum,
+                   const double *type_q, float *out_maps, mmo_grid **out_grid) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && type_anum && type_q, "mmo_grid_build: null argument");
+    mmo_grid *g = nullptr;
+    MMO_TRY(grid_alloc(step, dims, T, &g));
+    int rc = MMO_OK;
+    do {
+        // G3D.create: BA1.fill arr 0.0 (G3D.ml:47-51)
+        cudaError_t e = cudaMemsetAsync(g->maps.p, 0, g->nvox * (size_t)T * sizeof(float), rt().stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "memset maps", __FILE__, __LINE__); break; }
+        DevBuf<uint32_t> dmask;
+        if (mask_bits) {
+            size_t nwords = (g->nvox + 31) / 32;
+            std::vector<uint32_t> w(nwords, 0u);
+            memcpy(w.data(), mask_bits, (g->nvox + 7) / 8);
+            if ((rc = dmask.upload(w))) break;
+        }
+        std::vector<int32_t> telt(T);
+        for (int t = 0; t < T; t++) telt[t] = elt_index(type_anum[t]);
+        DevBuf<int32_t> dte;
+        DevBuf<double> dtq;
+        if ((rc = dte.upload(telt)) || (rc = dtq.upload(type_q, (size_t)T))) break;
+        if ((rc = launch_grid_build(rec, g, mask_bits ? dmask.p : nullptr, dte.p, dtq.p))) break;
+        if (out_maps) rc = d2h_sync(out_maps, g->maps.p, g->nvox * (size_t)T * sizeof(float));
+        else { cudaError_t e2 = cudaStreamSynchronize(rt().stream); if (e2 != cudaSuccess) rc = cuda_fail(e2, "sync", __FILE__, __LINE__); }
+    } while (0);
+    if (rc != MMO_OK || !out_grid) { delete g; g = nullptr; }
+    if (out_grid) *out_grid = g;
+    return rc;
+}
+
+int mmo_grid_upload(double step, const int32_t dims[3], int32_t T, const float *maps, mmo_grid **out) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(maps != nullptr, "mmo_grid_upload: null maps");
+    mmo_grid *g = nullptr;
+    MMO_TRY(grid_alloc(step, dims, T, &g));
+    cudaError_t e = cudaMemcpyAsync(g->maps.p, maps, g->nvox * (size_t)T * sizeof(float), cudaMemcpyHostToDevice, rt().stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "upload maps", __FILE__, __LINE__); }
+    *out = g;
+    return MMO_OK;
+}
+
+int mmo_grid_download(const mmo_grid *grid, float *maps) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(grid && maps, "mmo_grid_download: null argument");
+    return d2h_sync(maps, grid->maps.p, grid->nvox * (size_t)grid->T * sizeof(float));
+}
+
+int mmo_grid_destroy(mmo_grid *grid) {
+    delete grid;
+    return MMO_OK;
+}
+
+// G3D.to_ba1_file (G3D.ml:14-32): raw f32 image + `.dims` side-car with step/x_dim/y_dim/z_dim
+int mmo_grid_write_ba1(const mmo_grid *grid, int32_t type, const char *path) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(grid && path, "mmo_grid_write_ba1: null argument");
+    MMO_REQUIRE(type >= 0 && type < grid->T, "mmo_grid_write_ba1: type %d out of range", type);
+    std::vector<float> h(grid->nvox);
+    MMO_TRY(d2h_sync(h.data(), grid->maps.p + (size_t)type * grid->nvox, grid->nvox * sizeof(float)));
+    FILE *f = fopen(path, "wb");
+    MMO_REQUIRE(f != nullptr, "mmo_grid_write_ba1: cannot create %s", path);
+    size_t w = fwrite(h.data(), sizeof(float), h.size(), f);
+    fclose(f);
+    MMO_REQUIRE(w == h.size(), "mmo_grid_write_ba1: short write to %s", path);
+    std::string dn = std::string(path) + ".dims";
+    f = fopen(dn.c_str(), "w");
+    MMO_REQUIRE(f != nullptr, "mmo_grid_write_ba1: cannot create %s", dn.c_str());
+    fprintf(f, "step: %g\nx_dim: %d\ny_dim: %d\nz_dim: %d\n", grid->step, grid->dims[0], grid->dims[1], grid->dims[2]);
+    fclose(f);
+    return MMO_OK;
+}
+
+// G3D.parse_dims_file + of_ba1_file (G3D.ml:37-64) for T maps of identical geometry
+int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(paths && T > 0 && out, "mmo_grid_read_ba1: bad arguments");
+    double step = 0.0;
+    int32_t dims[3] = {0, 0, 0};
+    std::vector<float> all;
+    size_t nvox = 0;
+    for (int t = 0; t < T; t++) {
+        std::string dn = std::string(paths[t]) + ".dims";
+        FILE *f = fopen(dn.c_str(), "r");
+        MMO_REQUIRE(f != nullptr, "mmo_grid_read_ba1: cannot open %s", dn.c_str());
+        double s; int a, b, c;
+        int ok = fscanf(f, "step: %lf x_dim: %d y_dim: %d z_dim: %d", &s, &a, &b, &c);
+        fclose(f);
+        MMO_REQUIRE(ok == 4, "mmo_grid_read_ba1: cannot parse %s", dn.c_str());
+        if (t == 0) { step = s; dims[0] = a; dims[1] = b; dims[2] = c; nvox = (size_t)a * b * c; all.resize(nvox * (size_t)T); }
+        MMO_REQUIRE(s == step && a == dims[0] && b == dims[1] && c == dims[2], "mmo_grid_read_ba1: %s has another geometry", dn.c_str());
+        f = fopen(paths[t], "rb");
+        MMO_REQUIRE(f != nullptr, "mmo_grid_read_ba1: cannot open %s", paths[t]);
+        size_t r = fread(all.data() + (size_t)t * nvox, sizeof(float), nvox, f);
+        int extra = fgetc(f);
+        fclose(f);
+        MMO_REQUIRE(r == nvox && extra == EOF, "mmo_grid_read_ba1: %s does not hold %zu floats", paths[t], nvox);   // assert(BA1.dim ba1 = n)
+    }
+    return mmo_grid_upload(step, dims, T, all.data(), out);
+}
+
+int mmo_trilin(const mmo_grid *grid, int32_t type, int64_t n, const double *xs, const double *ys,
+               const double *zs, double *out) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(grid, "mmo_trilin: null grid");
+    MMO_REQUIRE(type >= 0 && type < grid->T, "mmo_trilin: type %d out of range", type);
+    MMO_REQUIRE(n >= 0, "mmo_trilin: negative count");
+    if (n == 0) return MMO_OK;
+    MMO_REQUIRE(xs && ys && zs && out, "mmo_trilin: null buffer");
+    DevBuf<double> dx, dy, dz, dE;
+    MMO_TRY(dx.upload(xs, (size_t)n)); MMO_TRY(dy.upload(ys, (size_t)n)); MMO_TRY(dz.upload(zs, (size_t)n));
+    MMO_TRY(dE.alloc((size_t)n));
+    MMO_TRY(launch_trilin(grid, type, n, dx.p, dy.p, dz.p, dE.p));
+    return d2h_sync(out, dE.p, (size_t)n * sizeof(double));
+}
+
+static int check_interp(const mmo_grid *grid, const mmo_ligand *lig) {
+    MMO_REQUIRE(grid && lig, "interp: null handle");
+    MMO_REQUIRE(lig->has_typ, "interp: the ligand was created without FF atom types");
+    for (int j = 0; j < lig->n; j++)
+        MMO_REQUIRE(lig->htyp[j] >= 0 && lig->htyp[j] < grid->T, "interp: atom %d has type %d but the grid holds %d maps", j, lig->htyp[j], grid->T);
+    return MMO_OK;
+}
+
+int mmo_score_interp_coords(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
+                            const double *xs, const double *ys, const double *zs, double *out_E) {
+    MMO_TRY(require_ready());
+    MMO_TRY(check_interp(grid, lig));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_coords: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(xs && ys && zs && out_E, "mmo_score_interp_coords: null buffer");
+    const size_t m = (size_t)n_poses * lig->n;
+    DevBuf<double> dx, dy, dz, dE;
+    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    MMO_TRY(dE.alloc((size_t)n_poses));
+    MMO_TRY(launch_interp(grid, lig, coords_src(dx.p, dy.p, dz.p), n_poses, dE.p));
+    return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
+}
+
+int mmo_score_interp_poses(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
+                           const double *rot9, const double *trans3, double *out_E) {
+    MMO_TRY(require_ready());
+    MMO_TRY(check_interp(grid, lig));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_poses: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(rot9 && trans3 && out_E, "mmo_score_interp_poses: null buffer");
+    DevBuf<double> dr, dt, dE;
+    MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
+    MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
+    MMO_TRY(dE.alloc((size_t)n_poses));
+    MMO_TRY(launch_interp(grid, lig, rt_src(dr.p, dt.p), n_poses, dE.p));
+    return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
+}
+
+int mmo_score_interp_poses_dev(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
+                               const double *d_rot9, const double *d_trans3, double *d_out_E) {
+    MMO_TRY(require_ready());
+    MMO_TRY(check_interp(grid, lig));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_poses_dev: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(d_rot9 && d_trans3 && d_out_E, "mmo_score_interp_poses_dev: null buffer");
+    return launch_interp(grid, lig, rt_src(d_rot9, d_trans3), n_poses, d_out_E);
+}
+
+// ------------------------------------------------------------------ vdW occupancy mask
+static int mask_alloc(double step, const int32_t dims[3], mmo_mask **out) {
+    MMO_REQUIRE(step > 0.0 && dims && dims[0] > 1 && dims[1] > 1 && dims[2] > 1, "bad mask geometry");
+    MMO_REQUIRE((double)dims[0] * dims[1] * dims[2] < 2.0e9, "mask too large for 32-bit voxel indices");
+    mmo_mask *m = new mmo_mask();
+    m->step = step;
+    for (int d = 0; d < 3; d++) m->dims[d] = dims[d];
+    m->nbits = (size_t)dims[0] * dims[1] * dims[2];
+    size_t nwords = (m->nbits + 31) / 32 + 1;
+    m->hwords.assign(nwords, 0u);
+    int rc = m->words.alloc(nwords);
+    if (rc != MMO_OK) { delete m; return rc; }
+    *out = m;
+    return MMO_OK;
+}
+
+int mmo_vdw_mask_build(int32_t n, const double *xs, const double *ys, const double *zs,
+                       const double *radii, double step, const int32_t dims[3], uint8_t *out_bits,
+                       mmo_mask **out_mask) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(n >= 0 && (n == 0 || (xs && ys && zs && radii)), "mmo_vdw_mask_build: bad atom arrays");
+    mmo_mask *m = nullptr;
+    MMO_TRY(mask_alloc(step, dims, &m));
+    int rc = MMO_OK;
+    do {
+        cudaError_t e = cudaMemsetAsync(m->words.p, 0, m->hwords.size() * sizeof(uint32_t), rt().stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "memset mask", __FILE__, __LINE__); break; }
+        DevBuf<double> dx, dy, dz, dr;
+        if ((rc = dx.upload(xs, (size_t)n)) || (rc = dy.upload(ys, (size_t)n)) || (rc = dz.upload(zs, (size_t)n)) ||
+            (rc = dr.upload(radii, (size_t)n)))
+            break;
+        if ((rc = launch_vdw_mask(n, dx.p, dy.p, dz.p, dr.p, m))) break;
+        rc = d2h_sync(m->hwords.data(), m->words.p, m->hwords.size() * sizeof(uint32_t));
+    } while (0);
+    if (rc == MMO_OK && out_bits) memcpy(out_bits, m->hwords.data(), (m->nbits + 7) / 8);
+    if (rc != MMO_OK || !out_mask) { delete m; m = nullptr; }
+    if (out_mask) *out_mask = m;
+    return rc;
+}
+
+int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(bits && out, "mmo_mask_upload: null argument");
+    mmo_mask *m = nullptr;
+    MMO_TRY(mask_alloc(step, dims, &m));
+    memcpy(m->hwords.data(), bits, (m->nbits + 7) / 8);
+    cudaError_t e = cudaMemcpyAsync(m->words.p, m->hwords.data(), m->hwords.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, rt().stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
+    if (e != cudaSuccess) { delete m; return cuda_fail(e, "upload mask", __FILE__, __LINE__); }
+    *out = m;
+    return MMO_OK;
+}
+
+int mmo_mask_destroy(mmo_mask *mask) {
+    delete mask;
+    return MMO_OK;
+}
+
+int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses,
+                    const double *rot9, const double *trans3, uint8_t *out_flags) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(mask && lig, "mmo_clash_poses: null handle");
+    MMO_REQUIRE(n_poses >= 0, "mmo_clash_poses: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(rot9 && trans3 && out_flags, "mmo_clash_poses: null buffer");
+    DevBuf<double> dr, dt;
+    DevBuf<uint8_t> df;
+    MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
+    MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
+    MMO_TRY(df.alloc((size_t)n_poses));
+    MMO_TRY(launch_clash(mask, lig, rt_src(dr.p, dt.p), n_poses, df.p));
+    return d2h_sync(out_flags, df.p, (size_t)n_poses);
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// common.cuh -- internal declarations shared by the translation units of libmmo_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/mmo_b200.h"
+
+#define MMO_STR2(x) #x
+#define MMO_STR(x) MMO_STR2(x)
+
+namespace mmo {
+
+// ---- error plumbing: no exception crosses the C ABI -------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define MMO_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return mmo::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define MMO_REQUIRE(cond, ...)                                                \
+    do {                                                                      \
+        if (!(cond)) { mmo::set_error(__VA_ARGS__); return MMO_EINVAL; }      \
+    } while (0)
+#define MMO_TRY(call)                                                         \
+    do { int rc__ = (call); if (rc__ != MMO_OK) return rc__; } while (0)
+
+struct Runtime {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void *l2_scratch = nullptr;
+    size_t l2_scratch_bytes = 0;
+    int64_t launches = 0;
+    int64_t stat_pairs = 0, stat_inside = 0, stat_fp64 = 0;
+    bool collect_stats = false;
+};
+Runtime &rt();
+int require_ready();
+
+// per-kernel device timing (CUDA events on the library stream), off unless mmo_kernel_timing(1)
+enum KernelId { K_DIRECT_FP32 = 0, K_HARD_FIX, K_DIRECT_FP64, K_INTRA, K_GRID_BUILD, K_INTERP, K_PREFILTER,
+                K_REDUCE, K_VDW_MASK, K_MC, K_COUNT };
+struct KernelScope {
+    int id;
+    bool on;
+    explicit KernelScope(int kid);
+    ~KernelScope();
+};
+inline void count_launch(int n = 1) { rt().launches += n; }
+#define MMO_LAUNCH_CHECK()                                                    \
+    do { mmo::count_launch(); MMO_CUDA(cudaGetLastError()); } while (0)
+
+// simple owning device buffer
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        MMO_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        n = count;
+        return MMO_OK;
+    }
+    int upload(const T *host, size_t count) {
+        MMO_TRY(alloc(count));
+        if (count) MMO_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, rt().stream));
+        MMO_CUDA(cudaStreamSynchronize(rt().stream));
+        return MMO_OK;
+    }
+    int upload(const std::vector<T> &v) { return upload(v.data(), v.size()); }
+};
+
+// ---- UFF parameters (src/UFF.ml:10-22) in a compact element index ---------------------------------
+constexpr int kNumElt = 12;      // supported elements, index 0 = virtual element without vdW
+constexpr int kEltUnsupported = 12;  // row/column of NaNs (src/UFF.ml:32-37)
+constexpr int kEltTab = 13;
+int elt_index(int anum);         // anum -> compact index, kEltUnsupported if not in the table
+extern const int kEltAnum[kNumElt];
+extern const double kEltXi[kNumElt];
+extern const double kEltDi[kNumElt];
+double vdw_radius(int anum);     // src/ptable.ml:41-54, NaN if unsupported
+constexpr double kElecWeight = 332.0637 / 4.0;   // src/UFF.ml:25, src/const.ml:18
+constexpr double kMaxE = 100000.0;               // src/params.ml:26
+
+// ---- geometry of the fp32 direct kernel -----------------------------------------------------------
+constexpr int kBlob = 16;        // receptor atoms per spatial blob (one cull test per blob)
+// close-contact threshold: pairs with x_i*x_j / r^2 > kTau are re-evaluated in fp64
+constexpr double kTau = 1.5;
+
+struct Aabb { float lo[3], hi[3]; };
+
+}  // namespace mmo
+
+// ---- opaque handles -----------------------------------------------------------------------------------
+struct mmo_receptor {
+    int n = 0;                       // real atoms
+    int n_pad = 0;                   // padded to a multiple of kBlob
+    int n_blobs = 0;
+    double origin[3] = {0, 0, 0};    // fp32 coordinates are relative to this point
+    // original order, double (strict fp64 kernels)
+    mmo::DevBuf<double> x, y, z, q;
+    mmo::DevBuf<int32_t> elt;        // compact element index
+    // blob order, fp32 (fast kernel): xyzq = {x-ox, y-oy, z-oz, EW*q}; ab = {A_i, B_i}
+    mmo::DevBuf<float4> xyzq;
+    mmo::DevBuf<float2> ab;
+    mmo::DevBuf<float> blob_box;     // n_blobs x 6 : lo xyz, hi xyz (relative coordinates)
+    // close-contact voxel lists (fp64 correction pass)
+    double vox_lo[3] = {0, 0, 0};
+    double vox_edge = 2.0;
+    int vox_dim[3] = {0, 0, 0};
+    mmo::DevBuf<int32_t> vox_off;    // nvox + 1
+    mmo::DevBuf<int32_t> vox_idx;    // atom indices (original order)
+    double x_max = 0.0;              // largest UFF x_i among receptor atoms
+    std::vector<double> hx, hy, hz, hq;   // host copies (original order)
+    std::vector<int32_t> hanum;
+};
+
+struct mmo_ligand {
+    int n = 0;
+    std::vector<double> hx, hy, hz, hq, hr;
+    std::vector<int32_t> hanum, htyp, hdists;
+    bool has_r = false, has_typ = false, has_dists = false;
+    int n_rbonds = 0;
+    std::vector<int32_t> rb_left, rb_right, rg_off, rg_idx;
+    double x_max = 0.0;
+    // device copies
+    mmo::DevBuf<double> x, y, z, q;          // template conformer
+    mmo::DevBuf<int32_t> elt, typ;
+    mmo::DevBuf<float4> fparam;              // {A_j, B_j, q_j, 0}
+    mmo::DevBuf<int32_t> pair_i, pair_j;     // interacting pairs (i<j, dists>=3) in reference order
+    int n_pairs = 0;
+    mmo::DevBuf<int32_t> d_rb_left, d_rb_right, d_rg_off, d_rg_idx;
+};
+
+struct mmo_grid {
+    double step = 0.0;
+    int dims[3] = {0, 0, 0};
+    int T = 0;
+    size_t nvox = 0;
+    mmo::DevBuf<float> maps;   // type-major: map t at maps + t*nvox
+};
+
+struct mmo_mask {
+    double step = 0.0;
+    int dims[3] = {0, 0, 0};
+    size_t nbits = 0;
+    mmo::DevBuf<uint32_t> words;   // bit idx at (words[idx>>5] >> (idx&31)) & 1
+    std::vector<uint32_t> hwords;  // host copy (lattice-point AND test of the scan driver)
+};
+
+namespace mmo {
+// pose sources understood by the kernels
+struct PoseSrc {
+    int kind;                    // 0 = rot9/trans3 arrays, 1 = explicit coordinates, 2 = scan frames
+    const double *rot9;          // kind 0: per pose; kind 2: per rotation
+    const double *trans3;        // kind 0
+    const double *xs, *ys, *zs;  // kind 1 (pose-major, stride L)
+    const int64_t *frames;       // kind 2: frame ids
+    int n_rot;                   // kind 2
+    int lat_dims[3];             // kind 2
+    double lat_min[3];           // kind 2
+    double lat_q[3];             // kind 2: node i on axis d at lat_min[d] + i*lat_q[d] (grid.ml:49-51)
+};
+
+// kernels' host entry points (defined in the .cu files)
+int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
+                       int64_t n_poses, double *d_out, bool collect_stats);
+int launch_direct_fp64(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
+                       int64_t n_poses, double *d_out);
+int launch_components_fp64(const mmo_receptor *rec, const mmo_ligand *lig, const PoseSrc &src,
+                           int64_t n_poses, double *d_elec, double *d_vdw);
+int launch_intra_fp64(const mmo_ligand *lig, int64_t n_confs, const double *d_xs, const double *d_ys,
+                      const double *d_zs, double *d_out);
+int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t *d_mask_words,
+                      const int32_t *d_type_elt, const double *d_type_q);
+int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, double *d_out);
+int launch_trilin(const mmo_grid *g, int type, int64_t n, const double *d_x, const double *d_y,
+                  const double *d_z, double *d_out);
+int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d_z, const double *d_r,
+                    const mmo_mask *m);
+int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags);
+int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, const int64_t *d_points,
+                          int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter);
+
+// host-side mirrors (host_math.cu)
+void so3_rotations(int n, double *rot9);
+void rot_r_xyz(double a, double b, double g, double r[9]);
+void rot_decompose(const double r[9], double abg[3]);
+int grid_num_steps(double dx, double length);
+double grid_node(double step, int dim, int i);
+}  // namespace mmo

@@ -1,0 +1,154 @@
+// mask.cu -- K5: protein vdW occupancy bitmask and the clash prefilter.  Compiled with -fmad=false:
+// the comparisons are done on the same IEEE doubles as the reference, so the bits are identical.
+//   Lds.atom_bitmask_set / vdW_volume    src/lds.ml:148-196
+//   Grid.coord_of_point                  src/grid.ml:87-91
+//   G3D.vdW_clash_OR / vdW_clash_AND     src/G3D.ml:162-213
+//   Mol.protein_ligand_clash             src/mol.ml:1195-1203
+#include "common.cuh"
+#include "pose.cuh"
+#include <math.h>
+
+namespace mmo {
+
+// one block per atom; threads sweep the cube of +-ceil(r/step) voxels around the atom's voxel.
+// The reference indexes grid.xs unchecked-by-construction (36 A margin); indices are clipped here.
+__global__ void vdw_mask_kernel(int n, const double *__restrict__ px, const double *__restrict__ py,
+                                const double *__restrict__ pz, const double *__restrict__ pr,
+                                double step, double q0, double q1, double q2,
+                                int dim0, int dim1, int dim2, uint32_t *__restrict__ words) {
+    const int a = blockIdx.x;
+    if (a >= n) return;
+    const double x = px[a], y = py[a], z = pz[a], radius = pr[a];
+    const int ci = (int)((x - 0.0) / step), cj = (int)((y - 0.0) / step), ck = (int)((z - 0.0) / step);
+    const int rs = (int)ceil(radius / step);
+    const double r2 = radius * radius;
+    const int side = 2 * rs + 1;
+    const int total = side * side * side;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int kk = t % side, jj = (t / side) % side, ii = t / (side * side);
+        int i = ci - rs + ii, j = cj - rs + jj, k = ck - rs + kk;
+        if (i < 0 || j < 0 || k < 0 || i >= dim0 || j >= dim1 || k >= dim2) continue;
+        double gx = (double)i * q0, gy = (double)j * q1, gz = (double)k * q2;
+        double dx = x - gx, dy = y - gy, dz = z - gz;      // V3.dist2 xyz (make x y z)
+        if (dx * dx + dy * dy + dz * dz < r2) {
+            size_t idx = (size_t)i + (size_t)j * dim0 + (size_t)k * dim0 * dim1;
+            atomicOr(words + (idx >> 5), 1u << (idx & 31));
+        }
+    }
+}
+
+__device__ __forceinline__ bool bit_at(const uint32_t *__restrict__ w, long idx) {
+    return (__ldg(w + (idx >> 5)) >> (idx & 31)) & 1u;
+}
+
+// G3D.vdW_clash_OR (G3D.ml:162-186)
+__device__ __forceinline__ bool clash_or(const uint32_t *__restrict__ w, double inv, int x_dim, int xy_dim,
+                                         double x, double y, double z) {
+    const int i0 = (int)(x * inv), j0 = (int)(y * inv), k0 = (int)(z * inv);
+    const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    const long j0x = (long)j0 * x_dim, j1x = (long)j1 * x_dim, k0xy = (long)k0 * xy_dim, k1xy = (long)k1 * xy_dim;
+    return bit_at(w, i0 + j0x + k0xy) || bit_at(w, i1 + j0x + k0xy) || bit_at(w, i1 + j1x + k0xy) ||
+           bit_at(w, i0 + j1x + k0xy) || bit_at(w, i0 + j0x + k1xy) || bit_at(w, i1 + j0x + k1xy) ||
+           bit_at(w, i1 + j1x + k1xy) || bit_at(w, i0 + j1x + k1xy);
+}
+
+// Mol.protein_ligand_clash for a batch of poses
+__global__ void __launch_bounds__(128)
+clash_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_dim, int L,
+             const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
+             PoseSrc src, int64_t n_poses, uint8_t *__restrict__ flags) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_poses) return;
+    bool clash = false;
+    if (src.kind == 1) {
+        for (int j = 0; j < L && !clash; j++)
+            clash = clash_or(words, inv, x_dim, xy_dim, src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
+    } else {
+        PoseRT P;
+        load_pose_rt(src, p, P);
+        for (int j = 0; j < L && !clash; j++) {
+            double x, y, z;
+            pose_atom_rt(P, __ldg(lx + j), __ldg(ly + j), __ldg(lz + j), x, y, z);
+            clash = clash_or(words, inv, x_dim, xy_dim, x, y, z);
+        }
+    }
+    flags[p] = clash ? 1 : 0;
+}
+
+// scan prefilter: candidate c of the slab = (active point c / n_rot, rotation c % n_rot);
+// survivors are appended (block-ordered) to `frames`
+__global__ void __launch_bounds__(256)
+scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_dim, int L,
+                      const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
+                      PoseSrc src /* kind 2, frames unused */, const int64_t *__restrict__ points, int64_t n_cand,
+                      int64_t *__restrict__ frames, unsigned long long *__restrict__ counter) {
+    __shared__ unsigned long long s_base;
+    __shared__ int s_warp[8];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    int64_t frame = 0;
+    if (c < n_cand) {
+        int64_t pt = __ldg(points + c / src.n_rot);
+        int rot_i = (int)(c % src.n_rot);
+        frame = (int64_t)rot_i + (int64_t)src.n_rot * pt;
+        keep = true;
+        if (words) {
+            PoseRT P;
+            load_pose_rt_frame(src, frame, P);
+            for (int j = 0; j < L && keep; j++) {
+                double x, y, z;
+                pose_atom_rt(P, __ldg(lx + j), __ldg(ly + j), __ldg(lz + j), x, y, z);
+                keep = !clash_or(words, inv, x_dim, xy_dim, x, y, z);
+            }
+        }
+    }
+    // ordered compaction inside the block, one atomic per block
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { int v = s_warp[w]; s_warp[w] = tot; tot += v; }
+        s_base = atomicAdd(counter, (unsigned long long)tot);
+    }
+    __syncthreads();
+    if (keep) frames[s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1))] = frame;
+}
+
+int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d_z, const double *d_r,
+                    const mmo_mask *m) {
+    if (n == 0) return MMO_OK;
+    double q[3];
+    for (int d = 0; d < 3; d++) {
+        int np = m->dims[d] - 1;
+        q[d] = np > 0 ? (m->step * (double)np) / (double)np : 0.0;
+    }
+    KernelScope ks(K_VDW_MASK);
+    vdw_mask_kernel<<<n, 128, 0, rt().stream>>>(n, d_x, d_y, d_z, d_r, m->step, q[0], q[1], q[2],
+                                                m->dims[0], m->dims[1], m->dims[2], m->words.p);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags) {
+    if (n_poses == 0) return MMO_OK;
+    clash_kernel<<<(unsigned)((n_poses + 127) / 128), 128, 0, rt().stream>>>(
+        m->words.p, 1.0 / m->step, m->dims[0], m->dims[0] * m->dims[1], lig->n, lig->x.p, lig->y.p, lig->z.p,
+        src, n_poses, d_flags);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, const int64_t *d_points,
+                          int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter) {
+    if (n_cand == 0) return MMO_OK;
+    KernelScope ks(K_PREFILTER);
+    scan_prefilter_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, rt().stream>>>(
+        m ? m->words.p : nullptr, m ? 1.0 / m->step : 0.0, m ? m->dims[0] : 0, m ? m->dims[0] * m->dims[1] : 0,
+        lig->n, lig->x.p, lig->y.p, lig->z.p, src, d_points, n_cand, d_frames, d_counter);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+}  // namespace mmo

@@ -1,0 +1,309 @@
+// runtime.cu -- device selection, error plumbing, timers, raw buffers, roofline micro-benchmarks
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace mmo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return MMO_ECUDA;
+}
+Runtime &rt() {
+    static Runtime r;
+    return r;
+}
+// ---- per-kernel timing ---------------------------------------------------------------------------
+struct KTimer {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;
+    struct Rec { int id; cudaEvent_t e0, e1; };
+    std::vector<Rec> pending;
+    double ms[K_COUNT] = {0};
+    long long launches[K_COUNT] = {0};
+};
+static KTimer g_kt;
+static cudaEvent_t kt_event() {
+    if (!g_kt.pool.empty()) { cudaEvent_t e = g_kt.pool.back(); g_kt.pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+static void kt_resolve() {
+    for (auto &r : g_kt.pending) {
+        cudaEventSynchronize(r.e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        g_kt.ms[r.id] += ms;
+        g_kt.launches[r.id]++;
+        g_kt.pool.push_back(r.e0);
+        g_kt.pool.push_back(r.e1);
+    }
+    g_kt.pending.clear();
+}
+KernelScope::KernelScope(int kid) : id(kid), on(g_kt.enabled) {
+    if (on) {
+        KTimer::Rec r{kid, kt_event(), kt_event()};
+        cudaEventRecord(r.e0, rt().stream);
+        g_kt.pending.push_back(r);
+    }
+}
+KernelScope::~KernelScope() {
+    if (on) {
+        cudaEventRecord(g_kt.pending.back().e1, rt().stream);
+        if (g_kt.pending.size() > 4096) kt_resolve();
+    }
+}
+
+int require_ready() {
+    if (!rt().ready) {
+        set_error("mmo_init() has not been called (or failed): there is no CPU fallback");
+        return MMO_ESTATE;
+    }
+    return MMO_OK;
+}
+
+// ---- micro-benchmarks: the measured denominators of the roofline --------------------------------
+// 8 independent FMA chains per thread, enough to saturate the FMA pipes at full occupancy.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_chain_kernel(T *out, int iters, T a, T b) {
+    T v0 = (T)threadIdx.x, v1 = v0 + (T)1, v2 = v0 + (T)2, v3 = v0 + (T)3;
+    T v4 = v0 + (T)4, v5 = v0 + (T)5, v6 = v0 + (T)6, v7 = v0 + (T)7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            v0 = v0 * a + b; v1 = v1 * a + b; v2 = v2 * a + b; v3 = v3 * a + b;
+            v4 = v4 * a + b; v5 = v5 * a + b; v6 = v6 * a + b; v7 = v7 * a + b;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+__global__ void copy_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = in[i];
+}
+
+template <typename T>
+static int measure_fma(double *tflops) {
+    MMO_TRY(require_ready());
+    Runtime &R = rt();
+    const int blocks = R.sm_count * 8, threads = 256, iters = 4096;
+    DevBuf<T> out;
+    MMO_TRY(out.alloc((size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    MMO_CUDA(cudaEventCreate(&e0));
+    MMO_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        MMO_CUDA(cudaEventRecord(e0, R.stream));
+        fma_chain_kernel<T><<<blocks, threads, 0, R.stream>>>(out.p, iters, (T)1.0000001, (T)1e-7);
+        MMO_LAUNCH_CHECK();
+        MMO_CUDA(cudaEventRecord(e1, R.stream));
+        MMO_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MMO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return MMO_OK;
+}
+
+}  // namespace mmo
+
+using namespace mmo;
+
+extern "C" {
+
+const char *mmo_last_error(void) { return g_err; }
+
+const char *mmo_build_info(void) {
+    return "libmmo_b200 sm_100a CUDA " MMO_STR(CUDART_VERSION) " built " __DATE__ " " __TIME__;
+}
+
+int mmo_device_count(int *n) {
+    MMO_REQUIRE(n != nullptr, "mmo_device_count: null pointer");
+    MMO_CUDA(cudaGetDeviceCount(n));
+    return MMO_OK;
+}
+
+int mmo_init(int device) {
+    Runtime &R = rt();
+    if (R.ready && R.device == device) return MMO_OK;
+    if (R.ready) mmo_shutdown();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("mmo_init: no CUDA device available (%s); libmmo_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return MMO_ECUDA;
+    }
+    MMO_REQUIRE(device >= 0 && device < n, "mmo_init: device %d out of range [0,%d)", device, n);
+    MMO_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MMO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("mmo_init: device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+        return MMO_ECUDA;
+    }
+    R.device = device;
+    R.sm_count = prop.multiProcessorCount;
+    MMO_CUDA(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+    MMO_CUDA(cudaEventCreate(&R.ev0));
+    MMO_CUDA(cudaEventCreate(&R.ev1));
+    R.launches = 0;
+    R.ready = true;
+    return MMO_OK;
+}
+
+int mmo_shutdown(void) {
+    Runtime &R = rt();
+    if (!R.ready) return MMO_OK;
+    cudaStreamSynchronize(R.stream);
+    if (R.l2_scratch) cudaFree(R.l2_scratch);
+    R.l2_scratch = nullptr;
+    R.l2_scratch_bytes = 0;
+    cudaEventDestroy(R.ev0);
+    cudaEventDestroy(R.ev1);
+    cudaStreamDestroy(R.stream);
+    R.stream = nullptr;
+    R.ready = false;
+    return MMO_OK;
+}
+
+int64_t mmo_launch_count(void) { return rt().launches; }
+
+int mmo_kernel_timing(int on) {
+    MMO_TRY(require_ready());
+    kt_resolve();
+    g_kt.enabled = on != 0;
+    for (int i = 0; i < K_COUNT; i++) { g_kt.ms[i] = 0.0; g_kt.launches[i] = 0; }
+    return MMO_OK;
+}
+int mmo_kernel_time_get(int kernel_id, double *ms, int64_t *launches) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(kernel_id >= 0 && kernel_id < K_COUNT, "mmo_kernel_time_get: bad kernel id %d", kernel_id);
+    kt_resolve();
+    if (ms) *ms = g_kt.ms[kernel_id];
+    if (launches) *launches = g_kt.launches[kernel_id];
+    return MMO_OK;
+}
+
+int mmo_timer_start(void) {
+    MMO_TRY(require_ready());
+    MMO_CUDA(cudaEventRecord(rt().ev0, rt().stream));
+    return MMO_OK;
+}
+int mmo_timer_stop(float *ms) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(ms != nullptr, "mmo_timer_stop: null pointer");
+    MMO_CUDA(cudaEventRecord(rt().ev1, rt().stream));
+    MMO_CUDA(cudaEventSynchronize(rt().ev1));
+    MMO_CUDA(cudaEventElapsedTime(ms, rt().ev0, rt().ev1));
+    return MMO_OK;
+}
+int mmo_sync(void) {
+    MMO_TRY(require_ready());
+    MMO_CUDA(cudaStreamSynchronize(rt().stream));
+    return MMO_OK;
+}
+int mmo_l2_flush(void) {
+    MMO_TRY(require_ready());
+    Runtime &R = rt();
+    const size_t bytes = (size_t)256 << 20;   // > 126 MB L2
+    if (!R.l2_scratch) {
+        MMO_CUDA(cudaMalloc(&R.l2_scratch, bytes));
+        R.l2_scratch_bytes = bytes;
+    }
+    MMO_CUDA(cudaMemsetAsync(R.l2_scratch, 0x5a, R.l2_scratch_bytes, R.stream));
+    return MMO_OK;
+}
+
+int mmo_measure_fp32_peak(double *tflops) {
+    MMO_REQUIRE(tflops != nullptr, "null pointer");
+    return measure_fma<float>(tflops);
+}
+int mmo_measure_fp64_peak(double *tflops) {
+    MMO_REQUIRE(tflops != nullptr, "null pointer");
+    return measure_fma<double>(tflops);
+}
+int mmo_measure_hbm_copy(double *gbs) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(gbs != nullptr, "null pointer");
+    Runtime &R = rt();
+    const size_t n = (size_t)1 << 26;   // 64 Mi float4 = 1 GiB in, 1 GiB out
+    DevBuf<float4> a, b;
+    MMO_TRY(a.alloc(n));
+    MMO_TRY(b.alloc(n));
+    MMO_CUDA(cudaMemsetAsync(a.p, 0, n * sizeof(float4), R.stream));
+    cudaEvent_t e0, e1;
+    MMO_CUDA(cudaEventCreate(&e0));
+    MMO_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        MMO_CUDA(cudaEventRecord(e0, R.stream));
+        copy_kernel<<<R.sm_count * 16, 512, 0, R.stream>>>(a.p, b.p, n);
+        MMO_LAUNCH_CHECK();
+        MMO_CUDA(cudaEventRecord(e1, R.stream));
+        MMO_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MMO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double g = 2.0 * (double)n * sizeof(float4) / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gbs = best;
+    return MMO_OK;
+}
+
+int mmo_dev_alloc(size_t bytes, void **dptr) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(dptr != nullptr, "mmo_dev_alloc: null pointer");
+    MMO_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return MMO_OK;
+}
+int mmo_dev_free(void *dptr) {
+    MMO_TRY(require_ready());
+    if (dptr) MMO_CUDA(cudaFree(dptr));
+    return MMO_OK;
+}
+int mmo_h2d(void *dptr, const void *host, size_t bytes) {
+    MMO_TRY(require_ready());
+    MMO_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, rt().stream));
+    MMO_CUDA(cudaStreamSynchronize(rt().stream));
+    return MMO_OK;
+}
+int mmo_d2h(void *host, const void *dptr, size_t bytes) {
+    MMO_TRY(require_ready());
+    MMO_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, rt().stream));
+    MMO_CUDA(cudaStreamSynchronize(rt().stream));
+    return MMO_OK;
+}
+int mmo_host_alloc(size_t bytes, void **hptr) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(hptr != nullptr, "mmo_host_alloc: null pointer");
+    MMO_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
+    return MMO_OK;
+}
+int mmo_host_free(void *hptr) {
+    MMO_TRY(require_ready());
+    if (hptr) MMO_CUDA(cudaFreeHost(hptr));
+    return MMO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,362 @@
+// scan.cu -- exhaustive rigid-body scan driver and K7 top-k / argmin.
+//   Lds.exhaustive_rigid_ligand_docking   src/lds.ml:1040-1114
+//   ROI.get_bounds / ROI.is_inside        src/ROI.ml:65-82
+//   Grid.from_box (translation lattice)   src/grid.ml:40-52
+//   G3D.vdW_clash_AND                     src/G3D.ml:189-213
+//   Mol.is_ligand_center_vdW_occuppied    src/mol.ml:1209-1218
+//
+// The reference's loop nest (z, y, x, rotation) becomes: host enumerates the in-ROI lattice points
+// (cheap: <= a few 1e4), the device handles slabs of points x all rotations:
+//   prefilter (bitmask clash)  ->  survivor frame list  ->  score kernel  ->  argmin + top-k filter.
+// frame = rot_i + n_rot*(i + j*x_dim + k*xy_dim) grows monotonically along the reference's loop
+// order, so "first pose wins ties" (strict <, lds.ml:1099) == "smallest frame wins ties".
+#include "common.cuh"
+#include "pose.cuh"
+#include <math.h>
+#include <algorithm>
+
+namespace mmo {
+
+struct ScoreFrame { double s; long long f; };
+
+__device__ __forceinline__ bool sf_less(double s1, long long f1, double s2, long long f2) {
+    return (s1 < s2) || (s1 == s2 && f1 < f2);
+}
+
+// score = e_intra_const +. ene_inter (lds.ml:1324-1325); per-block argmin; candidates with
+// score <= thr are appended to the top-k candidate buffer
+__global__ void __launch_bounds__(256)
+scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restrict__ frames, int64_t n,
+                   double e_intra, const double *__restrict__ thr, double *__restrict__ cand_s,
+                   long long *__restrict__ cand_f, unsigned long long *__restrict__ cand_n,
+                   unsigned long long cand_cap, ScoreFrame *__restrict__ block_best) {
+    __shared__ double sh_s[8];
+    __shared__ long long sh_f[8];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = INFINITY;
+    long long f = 0x7fffffffffffffffLL;
+    if (p < n) {
+        s = e_intra + energies[p];
+        f = frames[p];
+        if (cand_cap && s <= *thr) {
+            unsigned long long k = atomicAdd(cand_n, 1ull);
+            if (k < cand_cap) { cand_s[k] = s; cand_f[k] = f; }
+        }
+        if (!(s == s)) s = INFINITY;     // NaN never wins a strict '<' in the reference
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        long long f2 = __shfl_xor_sync(0xffffffffu, f, o);
+        if (sf_less(s2, f2, s, f)) { s = s2; f = f2; }
+    }
+    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_f[threadIdx.x >> 5] = f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (sf_less(sh_s[w], sh_f[w], s, f)) { s = sh_s[w]; f = sh_f[w]; }
+        block_best[blockIdx.x].s = s;
+        block_best[blockIdx.x].f = f;
+    }
+}
+
+struct ScanJob {
+    mmo_scan_params P;
+    int dims[3];
+    double mins[3], q[3];
+    std::vector<int64_t> points;           // active lattice points of the requested sub-range
+    DevBuf<double> d_rot;
+    DevBuf<int64_t> d_points, d_frames;
+    DevBuf<double> d_E, d_thr, d_cand_s;
+    DevBuf<long long> d_cand_f;
+    DevBuf<unsigned long long> d_counters;  // [0] survivors, [1] candidates
+    DevBuf<ScoreFrame> d_block_best;
+    std::vector<ScoreFrame> top;            // running top-k (ascending)
+    int64_t slab_cap = 0;
+    int64_t n_candidates = 0, n_scored = 0, pairs_eval = 0, pairs_in = 0;
+    double best_s = INFINITY;
+    long long best_f = -1;
+    float device_ms = 0.f;
+    bool collect_stats = false;
+};
+
+static bool host_bit(const mmo_mask *m, long idx) { return (m->hwords[idx >> 5] >> (idx & 31)) & 1u; }
+
+// G3D.vdW_clash_AND on the host copy of the mask
+static bool host_clash_and(const mmo_mask *m, double x, double y, double z) {
+    double inv = 1.0 / m->step;
+    int x_dim = m->dims[0], xy_dim = m->dims[0] * m->dims[1];
+    int i0 = (int)(x * inv), j0 = (int)(y * inv), k0 = (int)(z * inv);
+    int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    long j0x = (long)j0 * x_dim, j1x = (long)j1 * x_dim, k0xy = (long)k0 * xy_dim, k1xy = (long)k1 * xy_dim;
+    return host_bit(m, i0 + j0x + k0xy) && host_bit(m, i1 + j0x + k0xy) && host_bit(m, i1 + j1x + k0xy) &&
+           host_bit(m, i0 + j1x + k0xy) && host_bit(m, i0 + j0x + k1xy) && host_bit(m, i1 + j0x + k1xy) &&
+           host_bit(m, i1 + j1x + k1xy) && host_bit(m, i0 + j1x + k1xy);
+}
+
+static int scan_setup(ScanJob &J) {
+    const mmo_scan_params &P = J.P;
+    // ROI.get_bounds (ROI.ml:76-82) -> Bbox.create_6f -> Grid.from_box trans_step (lds.ml:1065-1069)
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = P.roi_c[d] - P.roi_r; hi[d] = P.roi_c[d] + P.roi_r; J.mins[d] = lo[d]; }
+    for (int d = 0; d < 3; d++) {
+        J.dims[d] = grid_num_steps(P.trans_step, hi[d] - lo[d]) + 1;
+        int np = J.dims[d] - 1;
+        J.q[d] = np > 0 ? (P.trans_step * (double)np) / (double)np : 0.0;
+    }
+    const int64_t nvox = (int64_t)J.dims[0] * J.dims[1] * J.dims[2];
+    int64_t p0 = std::max<int64_t>(0, P.first_point);
+    int64_t p1 = (P.n_points < 0) ? nvox : std::min(nvox, p0 + P.n_points);
+    const mmo_ligand *lig = P.lig;
+    // lds.ml:1044-1052: AND-prefilter on the lattice point only if the ligand's centre is inside one
+    // of its own atoms (mol.ml:1209-1218, V3.dist c xyz < radius)
+    bool center_filter = false;
+    if (P.vdw_mask) {
+        MMO_REQUIRE(lig->has_r, "mmo_scan: the vdW prefilter needs ligand radii");
+        for (int i = 0; i < lig->n && !center_filter; i++) {
+            double dx = 0.0 - lig->hx[i], dy = 0.0 - lig->hy[i], dz = 0.0 - lig->hz[i];
+            if (sqrt(dx * dx + dy * dy + dz * dz) < lig->hr[i]) center_filter = true;
+        }
+    }
+    const double r2 = P.roi_r * P.roi_r;       // ROI.ml:19-20
+    const int x_dim = J.dims[0], xy_dim = J.dims[0] * J.dims[1];
+    J.points.clear();
+    for (int64_t p = p0; p < p1; p++) {
+        int k = (int)(p / xy_dim);
+        int j = (int)((p - (int64_t)k * xy_dim) / x_dim);
+        int i = (int)(p - ((int64_t)k * xy_dim + (int64_t)j * x_dim));
+        double pos[3] = {J.mins[0] + (double)i * J.q[0], J.mins[1] + (double)j * J.q[1], J.mins[2] + (double)k * J.q[2]};
+        double dx = P.roi_c[0] - pos[0], dy = P.roi_c[1] - pos[1], dz = P.roi_c[2] - pos[2];
+        if (!(dx * dx + dy * dy + dz * dz < r2)) continue;           // ROI.is_inside, strict
+        if (center_filter && host_clash_and(P.vdw_mask, pos[0], pos[1], pos[2])) continue;
+        J.points.push_back(p);
+    }
+    MMO_TRY(J.d_rot.upload(P.rot9, (size_t)P.n_rot * 9));
+    MMO_TRY(J.d_points.upload(J.points));
+    // slab: as many lattice points as fit ~4M candidate poses
+    int64_t pts_per_slab = std::max<int64_t>(1, (int64_t)(4 << 20) / std::max(1, P.n_rot));
+    J.slab_cap = pts_per_slab * P.n_rot;
+    MMO_TRY(J.d_frames.alloc((size_t)J.slab_cap));
+    MMO_TRY(J.d_E.alloc((size_t)J.slab_cap));
+    MMO_TRY(J.d_thr.alloc(1));
+    MMO_TRY(J.d_counters.alloc(2));
+    if (P.topk > 0) {
+        MMO_TRY(J.d_cand_s.alloc((size_t)J.slab_cap));
+        MMO_TRY(J.d_cand_f.alloc((size_t)J.slab_cap));
+    }
+    MMO_TRY(J.d_block_best.alloc((size_t)(J.slab_cap + 255) / 256));
+    J.top.clear();
+    return MMO_OK;
+}
+
+static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
+    const mmo_scan_params &P = J.P;
+    Runtime &R = rt();
+    const int64_t pts_per_slab = J.slab_cap / P.n_rot;
+    PoseSrc src = {};
+    src.kind = 2;
+    src.rot9 = J.d_rot.p;
+    src.frames = J.d_frames.p;
+    src.n_rot = P.n_rot;
+    for (int d = 0; d < 3; d++) { src.lat_dims[d] = J.dims[d]; src.lat_min[d] = J.mins[d]; src.lat_q[d] = J.q[d]; }
+    std::vector<ScoreFrame> hbest;
+    std::vector<double> hs;
+    std::vector<long long> hf;
+    for (int64_t s0 = a0; s0 < a1; s0 += pts_per_slab) {
+        const int64_t npts = std::min(pts_per_slab, a1 - s0);
+        const int64_t n_cand = npts * P.n_rot;
+        J.n_candidates += n_cand;
+        const double thr = (P.topk > 0 && (int)J.top.size() >= P.topk) ? J.top.back().s : INFINITY;
+        MMO_CUDA(cudaMemsetAsync(J.d_counters.p, 0, 2 * sizeof(unsigned long long), R.stream));
+        MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &thr, sizeof(double), cudaMemcpyHostToDevice, R.stream));
+        MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, n_cand, J.d_frames.p, J.d_counters.p));
+        unsigned long long n_surv = 0;
+        MMO_CUDA(cudaMemcpyAsync(&n_surv, J.d_counters.p, sizeof n_surv, cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));
+        J.n_scored += (int64_t)n_surv;
+        if (n_surv == 0) continue;
+        if (P.grid) {
+            MMO_TRY(launch_interp(P.grid, P.lig, src, (int64_t)n_surv, J.d_E.p));
+        } else if (P.prec == MMO_PREC_FP64) {
+            MMO_TRY(launch_direct_fp64(P.rec, P.lig, P.variant, src, (int64_t)n_surv, J.d_E.p));
+        } else {
+            MMO_TRY(launch_direct_fp32(P.rec, P.lig, P.variant, src, (int64_t)n_surv, J.d_E.p, J.collect_stats));
+            if (J.collect_stats) { J.pairs_eval += R.stat_pairs; J.pairs_in += R.stat_inside; }
+        }
+        const unsigned blocks = (unsigned)((n_surv + 255) / 256);
+        {
+        KernelScope ks(K_REDUCE);
+        scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(J.d_E.p, J.d_frames.p, (int64_t)n_surv, P.e_intra_const,
+                                                         J.d_thr.p, J.d_cand_s.p, J.d_cand_f.p, J.d_counters.p + 1,
+                                                         P.topk > 0 ? (unsigned long long)J.slab_cap : 0ull,
+                                                         J.d_block_best.p);
+        }
+        MMO_LAUNCH_CHECK();
+        hbest.resize(blocks);
+        unsigned long long n_cnd = 0;
+        MMO_CUDA(cudaMemcpyAsync(hbest.data(), J.d_block_best.p, blocks * sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaMemcpyAsync(&n_cnd, J.d_counters.p + 1, sizeof n_cnd, cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));
+        for (const ScoreFrame &b : hbest)
+            if (b.s < J.best_s || (b.s == J.best_s && b.f < J.best_f && b.s != INFINITY)) { J.best_s = b.s; J.best_f = b.f; }
+        if (P.topk > 0 && n_cnd > 0) {
+            hs.resize(n_cnd); hf.resize(n_cnd);
+            MMO_CUDA(cudaMemcpyAsync(hs.data(), J.d_cand_s.p, n_cnd * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
+            MMO_CUDA(cudaMemcpyAsync(hf.data(), J.d_cand_f.p, n_cnd * sizeof(long long), cudaMemcpyDeviceToHost, R.stream));
+            MMO_CUDA(cudaStreamSynchronize(R.stream));
+            size_t old = J.top.size();
+            J.top.resize(old + n_cnd);
+            for (size_t i = 0; i < n_cnd; i++) { J.top[old + i].s = hs[i]; J.top[old + i].f = hf[i]; }
+            auto less = [](const ScoreFrame &a, const ScoreFrame &b) {
+                // NaN scores sort last; ties to the smaller frame
+                bool an = a.s != a.s, bn = b.s != b.s;
+                if (an != bn) return bn;
+                return (a.s < b.s) || (a.s == b.s && a.f < b.f);
+            };
+            size_t keep = std::min<size_t>(J.top.size(), (size_t)P.topk);
+            std::partial_sort(J.top.begin(), J.top.begin() + keep, J.top.end(), less);
+            J.top.resize(keep);
+        }
+    }
+    return MMO_OK;
+}
+
+static void scan_fill_result(const ScanJob &J, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+    const mmo_scan_params &P = J.P;
+    int ntop = (int)J.top.size();
+    for (int i = 0; i < ntop; i++) {
+        if (top_scores) top_scores[i] = J.top[i].s;
+        if (top_frames) top_frames[i] = J.top[i].f;
+    }
+    res->n_candidates = J.n_candidates;
+    res->n_scored = J.n_scored;
+    res->best_score = J.best_s;
+    res->best_frame = J.best_f;
+    res->n_top = ntop;
+    for (int d = 0; d < 3; d++) res->lattice_dims[d] = J.dims[d];
+    res->best_rot_i = 0;
+    res->best_pos[0] = res->best_pos[1] = res->best_pos[2] = 0.0;   // V3.origin when nothing was scored
+    if (J.best_f >= 0) {
+        int64_t pt = J.best_f / P.n_rot;
+        res->best_rot_i = (int32_t)(J.best_f - pt * P.n_rot);
+        int xy = J.dims[0] * J.dims[1];
+        int k = (int)(pt / xy);
+        int j = (int)((pt - (int64_t)k * xy) / J.dims[0]);
+        int i = (int)(pt - ((int64_t)k * xy + (int64_t)j * J.dims[0]));
+        res->best_pos[0] = J.mins[0] + (double)i * J.q[0];
+        res->best_pos[1] = J.mins[1] + (double)j * J.q[1];
+        res->best_pos[2] = J.mins[2] + (double)k * J.q[2];
+    }
+    res->pairs_evaluated = J.pairs_eval;
+    res->pairs_inside = J.pairs_in;
+    res->device_ms = J.device_ms;
+}
+
+static int scan_check(const mmo_scan_params *p) {
+    MMO_REQUIRE(p != nullptr, "mmo_scan: null parameters");
+    MMO_REQUIRE(p->lig != nullptr, "mmo_scan: null ligand");
+    MMO_REQUIRE((p->rec != nullptr) != (p->grid != nullptr), "mmo_scan: give exactly one of rec (direct) or grid (interpolated)");
+    MMO_REQUIRE(p->n_rot > 0 && p->rot9 != nullptr, "mmo_scan: no rotations");
+    MMO_REQUIRE(p->trans_step > 0.0 && p->roi_r > 0.0, "mmo_scan: bad lattice step or ROI radius");
+    MMO_REQUIRE(p->topk >= 0, "mmo_scan: negative top-k");
+    MMO_REQUIRE(!p->grid || p->lig->has_typ, "mmo_scan: interpolated scoring needs ligand FF types");
+    MMO_REQUIRE(p->variant == MMO_VARIANT_GLOBAL || p->variant == MMO_VARIANT_SHIFTED, "mmo_scan: bad variant");
+    MMO_REQUIRE(p->prec == MMO_PREC_FP32 || p->prec == MMO_PREC_FP64, "mmo_scan: bad precision");
+    return MMO_OK;
+}
+
+}  // namespace mmo
+
+using namespace mmo;
+
+struct mmo_scan_job { ScanJob J; };
+
+extern "C" {
+
+int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **out) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(out != nullptr, "mmo_scan_create: null output pointer");
+    *out = nullptr;
+    MMO_TRY(scan_check(p));
+    mmo_scan_job *h = new mmo_scan_job();
+    h->J.P = *p;
+    h->J.collect_stats = collect_stats != 0;
+    int rc = scan_setup(h->J);
+    if (rc != MMO_OK) { delete h; return rc; }
+    *out = h;
+    return MMO_OK;
+}
+
+int mmo_scan_num_points(const mmo_scan_job *job, int64_t *n_active_points) {
+    MMO_REQUIRE(job && n_active_points, "mmo_scan_num_points: null pointer");
+    *n_active_points = (int64_t)job->J.points.size();
+    return MMO_OK;
+}
+
+int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(job != nullptr, "mmo_scan_run: null job");
+    int64_t n = (int64_t)job->J.points.size();
+    int64_t a0 = std::max<int64_t>(0, first_active);
+    int64_t a1 = n_active < 0 ? n : std::min(n, a0 + n_active);
+    if (a0 >= a1) return MMO_OK;
+    Runtime &R = rt();
+    cudaEvent_t e0, e1;
+    MMO_CUDA(cudaEventCreate(&e0));
+    MMO_CUDA(cudaEventCreate(&e1));
+    MMO_CUDA(cudaEventRecord(e0, R.stream));
+    int rc = scan_run_points(job->J, a0, a1);
+    cudaEventRecord(e1, R.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    job->J.device_ms += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+int mmo_scan_result_get(const mmo_scan_job *job, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+    MMO_REQUIRE(job && res, "mmo_scan_result_get: null pointer");
+    scan_fill_result(job->J, top_scores, top_frames, res);
+    return MMO_OK;
+}
+
+int mmo_scan_destroy(mmo_scan_job *job) {
+    delete job;
+    return MMO_OK;
+}
+
+int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+    MMO_REQUIRE(res != nullptr, "mmo_scan: null result pointer");
+    mmo_scan_job *job = nullptr;
+    MMO_TRY(mmo_scan_create(p, rt().collect_stats ? 1 : 0, &job));
+    int rc = mmo_scan_run(job, 0, -1);
+    if (rc == MMO_OK) scan_fill_result(job->J, top_scores, top_frames, res);
+    mmo_scan_destroy(job);
+    return rc;
+}
+
+// K-way merge of per-GPU lists; lists need not be sorted.  Order: score ascending, NaN last, ties to
+// the smaller frame (= earlier in the reference's loop order).
+int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64_t *frames,
+                   const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n) {
+    MMO_REQUIRE(n_lists >= 0 && k >= 0 && out_n, "mmo_topk_merge: bad arguments");
+    std::vector<ScoreFrame> all;
+    for (int l = 0; l < n_lists; l++) {
+        MMO_REQUIRE(counts[l] >= 0 && counts[l] <= k, "mmo_topk_merge: list %d has %d entries (k = %d)", l, counts[l], k);
+        for (int i = 0; i < counts[l]; i++) all.push_back({scores[(size_t)l * k + i], (long long)frames[(size_t)l * k + i]});
+    }
+    auto less = [](const ScoreFrame &a, const ScoreFrame &b) {
+        bool an = a.s != a.s, bn = b.s != b.s;
+        if (an != bn) return bn;
+        return (a.s < b.s) || (a.s == b.s && a.f < b.f);
+    };
+    std::sort(all.begin(), all.end(), less);
+    int n = (int)std::min<size_t>(all.size(), (size_t)k);
+    for (int i = 0; i < n; i++) { out_scores[i] = all[i].s; out_frames[i] = all[i].f; }
+    *out_n = n;
+    return MMO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,436 @@
+// strict_fp64.cu -- the reference's double-precision arithmetic, operation for operation.
+// Compiled with -fmad=false: no FMA contraction (OCaml native code never fuses), IEEE sqrt and
+// division, and the reference's summation order, so results are bit-identical to the OCaml code
+// (and to oracle/mmo_oracle.c).
+//
+//   direct   : Mol.ene_inter_UFF_shifted_brute / _global_brute   src/mol.ml:796-849
+//   comps    : Mol.ene_inter_UFF_shifted_bst_components          src/mol.ml:928-956
+//   intra    : Mol.ene_intra_UFFNB_brute                         src/mol.ml:881-903
+//   grid     : Mol.ene_inter_UFF_shifted_grid + Lds.pre_calculate_FF_components_grid
+//                                                                src/mol.ml:964-989, src/lds.ml:452-469
+//   trilin   : G3D.trilin, Mol.ene_inter_UFF_interp              src/G3D.ml:97-157, src/mol.ml:1012-1020
+#include "common.cuh"
+#include "pose.cuh"
+#include <math.h>
+
+namespace mmo {
+
+// UFF.ml:32-51: x_ij = sqrt(x_i*x_j), d_ij = sqrt(D_i*D_j), NaN for unsupported elements
+__constant__ double c_xij[kEltTab * kEltTab];
+__constant__ double c_dij[kEltTab * kEltTab];
+static bool g_tables_ready = false;
+
+static int ensure_tables() {
+    if (g_tables_ready) return MMO_OK;
+    double hx[kEltTab * kEltTab], hd[kEltTab * kEltTab];
+    for (int a = 0; a < kEltTab; a++)
+        for (int b = 0; b < kEltTab; b++) {
+            if (a < kNumElt && b < kNumElt) {
+                hx[a * kEltTab + b] = sqrt(kEltXi[a] * kEltXi[b]);   // FF.geo_mean, FF.ml:14-15
+                hd[a * kEltTab + b] = sqrt(kEltDi[a] * kEltDi[b]);
+            } else {
+                hx[a * kEltTab + b] = NAN;
+                hd[a * kEltTab + b] = NAN;
+            }
+        }
+    MMO_CUDA(cudaMemcpyToSymbol(c_xij, hx, sizeof hx));
+    MMO_CUDA(cudaMemcpyToSymbol(c_dij, hd, sizeof hd));
+    g_tables_ready = true;
+    return MMO_OK;
+}
+
+// ---- scalars: FF.ml:5-20, math.ml:58-62 ------------------------------------------------------
+__device__ __forceinline__ double d_sq(double x) { return x * x; }
+__device__ __forceinline__ double d_pow6(double x) { double y = x * x; return (y * y) * y; }
+__device__ __forceinline__ double d_shift(double d) { return (d < 12.0) ? d_sq(1.0 - d_sq(d / 12.0)) : 0.0; }
+__device__ __forceinline__ double d_nzd(double x) { return (x < 0.01) ? 0.01 : x; }
+// V3.dist2 u v (V3.ml:23-28)
+__device__ __forceinline__ double d_dist2(double ux, double uy, double uz, double vx, double vy, double vz) {
+    double dx = ux - vx, dy = uy - vy, dz = uz - vz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// coordinates of one pose into shared memory, laid out [coord][atom][thread]
+__device__ __forceinline__ void stage_pose(const PoseSrc &src, int64_t p, int L, const double *lx,
+                                           const double *ly, const double *lz, double *sm, int nthr, int tid) {
+    double *sx = sm, *sy = sm + (size_t)L * nthr, *sz = sm + 2 * (size_t)L * nthr;
+    if (src.kind == 1) {
+        for (int j = 0; j < L; j++) {
+            sx[j * nthr + tid] = src.xs[p * L + j];
+            sy[j * nthr + tid] = src.ys[p * L + j];
+            sz[j * nthr + tid] = src.zs[p * L + j];
+        }
+    } else {
+        PoseRT P;
+        load_pose_rt(src, p, P);
+        for (int j = 0; j < L; j++) {
+            double x, y, z;
+            pose_atom_rt(P, lx[j], ly[j], lz[j], x, y, z);
+            sx[j * nthr + tid] = x; sy[j * nthr + tid] = y; sz[j * nthr + tid] = z;
+        }
+    }
+}
+
+// ---- direct, receptor outer / ligand inner (mol.ml:802-818, 828-848) ------------------------------
+template <int VARIANT>
+__global__ void strict_direct_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
+                                     const double *__restrict__ pz, const double *__restrict__ pq,
+                                     const int32_t *__restrict__ pelt,
+                                     int L, const double *__restrict__ lx, const double *__restrict__ ly,
+                                     const double *__restrict__ lz, const double *__restrict__ lq,
+                                     const int32_t *__restrict__ lelt,
+                                     PoseSrc src, int64_t n_poses, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    double *sx = sm, *sy = sm + (size_t)L * nthr, *sz = sm + 2 * (size_t)L * nthr;
+    double *sq = sm + 3 * (size_t)L * nthr;
+    int32_t *se = (int32_t *)(sq + L);
+    for (int j = tid; j < L; j += nthr) { sq[j] = lq[j]; se[j] = lelt[j]; }
+    int64_t p = (int64_t)blockIdx.x * nthr + tid;
+    if (p < n_poses) stage_pose(src, p, L, lx, ly, lz, sm, nthr, tid);
+    __syncthreads();
+    if (p >= n_poses) return;
+    double sum_elec = 0.0, sum_vdW = 0.0;
+    for (int i = 0; i < P; i++) {
+        const double xi = __ldg(px + i), yi = __ldg(py + i), zi = __ldg(pz + i), q_i = __ldg(pq + i);
+        const int ei = __ldg(pelt + i) * kEltTab;
+        for (int j = 0; j < L; j++) {
+            double r2 = d_dist2(xi, yi, zi, sx[j * nthr + tid], sy[j * nthr + tid], sz[j * nthr + tid]);
+            if (VARIANT == MMO_VARIANT_SHIFTED) {
+                if (r2 < 144.0) {
+                    double q_j = sq[j];
+                    double r = d_nzd(sqrt(r2));
+                    double w = d_shift(r);
+                    int t = ei + se[j];
+                    double p6 = d_pow6(c_xij[t] / r);
+                    sum_elec = sum_elec + w * ((q_i * q_j) / r);
+                    sum_vdW = sum_vdW + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                }
+            } else {
+                double q_j = sq[j];
+                double r = d_nzd(sqrt(r2));
+                int t = ei + se[j];
+                double p6 = d_pow6(c_xij[t] / r);
+                sum_elec = sum_elec + ((q_i * q_j) / r);
+                sum_vdW = sum_vdW + (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+            }
+        }
+    }
+    out[p] = (kElecWeight * sum_elec) + sum_vdW;
+}
+
+// ---- components, ligand outer / receptor inner in index order (mol.ml:932-956) --------------------
+__global__ void strict_components_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
+                                         const double *__restrict__ pz, const double *__restrict__ pq,
+                                         const int32_t *__restrict__ pelt,
+                                         int L, const double *__restrict__ lx, const double *__restrict__ ly,
+                                         const double *__restrict__ lz, const double *__restrict__ lq,
+                                         const int32_t *__restrict__ lelt,
+                                         PoseSrc src, int64_t n_poses, double *__restrict__ out_elec,
+                                         double *__restrict__ out_vdw) {
+    extern __shared__ double sm[];
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    double *sx = sm, *sy = sm + (size_t)L * nthr, *sz = sm + 2 * (size_t)L * nthr;
+    int64_t p = (int64_t)blockIdx.x * nthr + tid;
+    if (p < n_poses) stage_pose(src, p, L, lx, ly, lz, sm, nthr, tid);
+    __syncthreads();
+    if (p >= n_poses) return;
+    double sum_elec = 0.0, sum_vdW = 0.0;
+    for (int j = 0; j < L; j++) {
+        const double xj = sx[j * nthr + tid], yj = sy[j * nthr + tid], zj = sz[j * nthr + tid];
+        const double q_j = __ldg(lq + j);
+        const int ej = __ldg(lelt + j) * kEltTab;
+        for (int i = 0; i < P; i++) {
+            double d = sqrt(d_dist2(__ldg(px + i), __ldg(py + i), __ldg(pz + i), xj, yj, zj));
+            if (d <= 12.0) {   // BST.neighbors q 12.0; w(12) = 0 makes the boundary convention irrelevant
+                double r = d_nzd(d);
+                double w = d_shift(r);
+                int t = ej + __ldg(pelt + i);
+                double p6 = d_pow6(c_xij[t] / r);
+                sum_elec = sum_elec + w * ((__ldg(pq + i) * q_j) / r);
+                sum_vdW = sum_vdW + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+            }
+        }
+    }
+    out_elec[p] = sum_elec * kElecWeight;
+    out_vdw[p] = sum_vdW;
+}
+
+// ---- intra-ligand non-bonded (mol.ml:885-903): pairs pre-listed in the reference's (i<j) order ----
+__global__ void strict_intra_kernel(int L, int n_pairs, const int32_t *__restrict__ pair_i,
+                                    const int32_t *__restrict__ pair_j, const double *__restrict__ lq,
+                                    const int32_t *__restrict__ lelt, int64_t n_confs,
+                                    const double *__restrict__ xs, const double *__restrict__ ys,
+                                    const double *__restrict__ zs, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    double *sx = sm, *sy = sm + (size_t)L * nthr, *sz = sm + 2 * (size_t)L * nthr;
+    int64_t p = (int64_t)blockIdx.x * nthr + tid;
+    if (p < n_confs)
+        for (int j = 0; j < L; j++) {
+            sx[j * nthr + tid] = xs[p * L + j];
+            sy[j * nthr + tid] = ys[p * L + j];
+            sz[j * nthr + tid] = zs[p * L + j];
+        }
+    __syncthreads();
+    if (p >= n_confs) return;
+    double sum_elec = 0.0, sum_vdW = 0.0;
+    for (int k = 0; k < n_pairs; k++) {
+        const int i = __ldg(pair_i + k), j = __ldg(pair_j + k);
+        double r = d_nzd(sqrt(d_dist2(sx[i * nthr + tid], sy[i * nthr + tid], sz[i * nthr + tid],
+                                      sx[j * nthr + tid], sy[j * nthr + tid], sz[j * nthr + tid])));
+        int t = __ldg(lelt + i) * kEltTab + __ldg(lelt + j);
+        double p6 = d_pow6(c_xij[t] / r);
+        sum_elec = sum_elec + (__ldg(lq + i) * __ldg(lq + j)) / r;
+        sum_vdW = sum_vdW + c_dij[t] * ((-2.0 * p6) + (p6 * p6));
+    }
+    out[p] = (kElecWeight * sum_elec) + sum_vdW;
+}
+
+// ---- grid build (mol.ml:964-989 per voxel, lds.ml:452-469 clamp + f32 store) ----------------------
+// one thread per (voxel, group of TG types); receptor atoms streamed through shared memory in index
+// order; r_ij and w are computed once per atom and reused by the TG types, as in the reference.
+constexpr int kTG = 12;
+constexpr int kGridTile = 256;
+__global__ void __launch_bounds__(128)
+strict_grid_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
+                   const double *__restrict__ pz, const double *__restrict__ pq,
+                   const int32_t *__restrict__ pelt,
+                   int dim0, int dim1, int dim2, double q0, double q1, double q2,
+                   const uint32_t *__restrict__ mask, int T, const int32_t *__restrict__ telt,
+                   const double *__restrict__ tq, float *__restrict__ maps) {
+    __shared__ double sx[kGridTile], sy[kGridTile], sz[kGridTile], sq[kGridTile];
+    __shared__ int32_t se[kGridTile];
+    const size_t nvox = (size_t)dim0 * dim1 * dim2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t0 = blockIdx.y * kTG;
+    const int nt = min(kTG, T - t0);
+    bool active = idx < nvox;
+    if (active && mask) active = (mask[idx >> 5] >> (idx & 31)) & 1u;
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (idx < nvox) {     // Grid.ijk_of_idx, grid.ml:101-105
+        const int xy = dim0 * dim1;
+        int k = (int)(idx / xy);
+        int j = (int)((idx - (size_t)k * xy) / dim0);
+        int i = (int)(idx - ((size_t)k * xy + (size_t)j * dim0));
+        x = (double)i * q0; y = (double)j * q1; z = (double)k * q2;
+    }
+    double se_acc[kTG], sv_acc[kTG], tqv[kTG];
+    int te[kTG];
+#pragma unroll
+    for (int l = 0; l < kTG; l++) {
+        se_acc[l] = 0.0; sv_acc[l] = 0.0;
+        tqv[l] = (l < nt) ? tq[t0 + l] : 0.0;
+        te[l] = (l < nt) ? telt[t0 + l] * kEltTab : 0;
+    }
+    for (int base = 0; base < P; base += kGridTile) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < kGridTile; k += blockDim.x) {
+            int i = base + k;
+            if (i < P) { sx[k] = px[i]; sy[k] = py[i]; sz[k] = pz[i]; sq[k] = pq[i]; se[k] = pelt[i]; }
+        }
+        __syncthreads();
+        if (!active) continue;
+        const int lim = min(kGridTile, P - base);
+        for (int k = 0; k < lim; k++) {
+            double d = sqrt(d_dist2(sx[k], sy[k], sz[k], x, y, z));
+            if (d <= 12.0) {
+                const double q_i = sq[k];
+                const double r = d_nzd(d);
+                const double w = d_shift(r);
+                const int ei = se[k];
+#pragma unroll
+                for (int l = 0; l < kTG; l++) {
+                    if (l < nt) {
+                        int t = te[l] + ei;       // UFF.vdW_xiDi (get_anum lig 0) prot_anum
+                        double p6 = d_pow6(c_xij[t] / r);
+                        se_acc[l] = se_acc[l] + w * ((q_i * tqv[l]) / r);
+                        sv_acc[l] = sv_acc[l] + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int l = 0; l < kTG; l++) {
+        if (l < nt) {
+            double e = kElecWeight * se_acc[l] + sv_acc[l];
+            double v = (kMaxE <= e) ? kMaxE : e;      // OCaml: min max_E e = if max_E <= e then max_E else e
+            maps[(size_t)(t0 + l) * nvox + idx] = (float)v;
+        }
+    }
+}
+
+// ---- trilinear interpolation (G3D.ml:97-157) ---------------------------------------------------
+struct GridGeom {
+    double inv;          // grid.one_div_step
+    double q[3];         // node i at i*q[d]
+    int x_dim, xy_dim;
+    size_t nvox;
+};
+__device__ __forceinline__ double d_trilin(const GridGeom &g, const float *__restrict__ arr,
+                                           double px, double py, double pz) {
+    const int i0 = (int)(px * g.inv), j0 = (int)(py * g.inv), k0 = (int)(pz * g.inv);
+    const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    const int j0x = j0 * g.x_dim, j1x = j1 * g.x_dim, k0xy = k0 * g.xy_dim, k1xy = k1 * g.xy_dim;
+    const double lx = (double)i0 * g.q[0], ly = (double)j0 * g.q[1], lz = (double)k0 * g.q[2];
+    const double wlx = (px - lx) * g.inv, wly = (py - ly) * g.inv, wlz = (pz - lz) * g.inv;
+    const double whx = 1.0 - wlx, why = 1.0 - wly, whz = 1.0 - wlz;
+    return ((double)__ldg(arr + (i0 + j0x + k0xy)) * (whx * why * whz) +
+            (double)__ldg(arr + (i1 + j0x + k0xy)) * (wlx * why * whz) +
+            (double)__ldg(arr + (i1 + j1x + k0xy)) * (wlx * wly * whz) +
+            (double)__ldg(arr + (i0 + j1x + k0xy)) * (whx * wly * whz) +
+            (double)__ldg(arr + (i0 + j0x + k1xy)) * (whx * why * wlz) +
+            (double)__ldg(arr + (i1 + j0x + k1xy)) * (wlx * why * wlz) +
+            (double)__ldg(arr + (i1 + j1x + k1xy)) * (wlx * wly * wlz) +
+            (double)__ldg(arr + (i0 + j1x + k1xy)) * (whx * wly * wlz));
+}
+
+__global__ void strict_trilin_kernel(GridGeom g, const float *__restrict__ arr, int64_t n,
+                                     const double *__restrict__ xs, const double *__restrict__ ys,
+                                     const double *__restrict__ zs, double *__restrict__ out) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) out[p] = d_trilin(g, arr, xs[p], ys[p], zs[p]);
+}
+
+// Mol.ene_inter_UFF_interp (mol.ml:1012-1020): res := !res +. trilin ... for j = 0 .. l-1
+__global__ void __launch_bounds__(128)
+strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
+                     const double *__restrict__ lx, const double *__restrict__ ly,
+                     const double *__restrict__ lz, const int32_t *__restrict__ ltyp,
+                     PoseSrc src, int64_t n_poses, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    double *sx = sm, *sy = sm + L, *sz = sm + 2 * L;
+    int32_t *st = (int32_t *)(sm + 3 * L);
+    for (int j = threadIdx.x; j < L; j += blockDim.x) { sx[j] = lx[j]; sy[j] = ly[j]; sz[j] = lz[j]; st[j] = ltyp[j]; }
+    __syncthreads();
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_poses) return;
+    double res = 0.0;
+    if (src.kind == 1) {
+        for (int j = 0; j < L; j++)
+            res = res + d_trilin(g, maps + (size_t)st[j] * g.nvox, src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
+    } else {
+        PoseRT P;
+        load_pose_rt(src, p, P);
+        for (int j = 0; j < L; j++) {
+            double x, y, z;
+            pose_atom_rt(P, sx[j], sy[j], sz[j], x, y, z);
+            res = res + d_trilin(g, maps + (size_t)st[j] * g.nvox, x, y, z);
+        }
+    }
+    out[p] = res;
+}
+
+// ---- host launchers ------------------------------------------------------------------------------
+static int pick_threads(int L, size_t extra_bytes, size_t *smem) {
+    // [3][L][threads] doubles of pose coordinates; keep at most ~100 KB per block
+    for (int t : {128, 64, 32}) {
+        size_t b = (size_t)3 * L * t * sizeof(double) + extra_bytes;
+        if (b <= 100 * 1024 || t == 32) { *smem = b; return t; }
+    }
+    return 32;
+}
+
+static GridGeom geom_of(const mmo_grid *g) {
+    GridGeom G;
+    G.inv = 1.0 / g->step;                  // grid.ml:41
+    for (int d = 0; d < 3; d++) {
+        int np = g->dims[d] - 1;
+        G.q[d] = np > 0 ? (g->step * (double)np) / (double)np : 0.0;    // grid.ml:49-51
+    }
+    G.x_dim = g->dims[0];
+    G.xy_dim = g->dims[0] * g->dims[1];
+    G.nvox = g->nvox;
+    return G;
+}
+
+int launch_direct_fp64(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
+                       int64_t n_poses, double *d_out) {
+    MMO_TRY(ensure_tables());
+    if (n_poses == 0) return MMO_OK;
+    size_t smem;
+    int L = lig->n;
+    int threads = pick_threads(L, (size_t)L * (sizeof(double) + sizeof(int32_t)) + 16, &smem);
+    MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the fp64 direct kernel", L);
+    int64_t blocks = (n_poses + threads - 1) / threads;
+    auto k = (variant == MMO_VARIANT_SHIFTED) ? strict_direct_kernel<MMO_VARIANT_SHIFTED>
+                                              : strict_direct_kernel<MMO_VARIANT_GLOBAL>;
+    MMO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelScope ks(K_DIRECT_FP64);
+    k<<<(unsigned)blocks, threads, smem, rt().stream>>>(rec->n, rec->x.p, rec->y.p, rec->z.p, rec->q.p, rec->elt.p,
+                                                        L, lig->x.p, lig->y.p, lig->z.p, lig->q.p, lig->elt.p,
+                                                        src, n_poses, d_out);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_components_fp64(const mmo_receptor *rec, const mmo_ligand *lig, const PoseSrc &src,
+                           int64_t n_poses, double *d_elec, double *d_vdw) {
+    MMO_TRY(ensure_tables());
+    if (n_poses == 0) return MMO_OK;
+    size_t smem;
+    int L = lig->n;
+    int threads = pick_threads(L, 0, &smem);
+    MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the fp64 components kernel", L);
+    int64_t blocks = (n_poses + threads - 1) / threads;
+    MMO_CUDA(cudaFuncSetAttribute(strict_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    strict_components_kernel<<<(unsigned)blocks, threads, smem, rt().stream>>>(
+        rec->n, rec->x.p, rec->y.p, rec->z.p, rec->q.p, rec->elt.p, L, lig->x.p, lig->y.p, lig->z.p, lig->q.p,
+        lig->elt.p, src, n_poses, d_elec, d_vdw);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_intra_fp64(const mmo_ligand *lig, int64_t n_confs, const double *d_xs, const double *d_ys,
+                      const double *d_zs, double *d_out) {
+    MMO_TRY(ensure_tables());
+    if (n_confs == 0) return MMO_OK;
+    size_t smem;
+    int L = lig->n;
+    int threads = pick_threads(L, 0, &smem);
+    MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the intra kernel", L);
+    int64_t blocks = (n_confs + threads - 1) / threads;
+    MMO_CUDA(cudaFuncSetAttribute(strict_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelScope ks(K_INTRA);
+    strict_intra_kernel<<<(unsigned)blocks, threads, smem, rt().stream>>>(
+        L, lig->n_pairs, lig->pair_i.p, lig->pair_j.p, lig->q.p, lig->elt.p, n_confs, d_xs, d_ys, d_zs, d_out);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t *d_mask_words,
+                      const int32_t *d_type_elt, const double *d_type_q) {
+    MMO_TRY(ensure_tables());
+    GridGeom G = geom_of(g);
+    dim3 grid((unsigned)((g->nvox + 127) / 128), (unsigned)((g->T + kTG - 1) / kTG));
+    KernelScope ks(K_GRID_BUILD);
+    strict_grid_kernel<<<grid, 128, 0, rt().stream>>>(rec->n, rec->x.p, rec->y.p, rec->z.p, rec->q.p, rec->elt.p,
+                                                      g->dims[0], g->dims[1], g->dims[2], G.q[0], G.q[1], G.q[2],
+                                                      d_mask_words, g->T, d_type_elt, d_type_q, g->maps.p);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_trilin(const mmo_grid *g, int type, int64_t n, const double *d_x, const double *d_y,
+                  const double *d_z, double *d_out) {
+    if (n == 0) return MMO_OK;
+    strict_trilin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, rt().stream>>>(
+        geom_of(g), g->maps.p + (size_t)type * g->nvox, n, d_x, d_y, d_z, d_out);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, double *d_out) {
+    if (n_poses == 0) return MMO_OK;
+    int L = lig->n;
+    size_t smem = (size_t)3 * L * sizeof(double) + (size_t)L * sizeof(int32_t) + 16;
+    KernelScope ks(K_INTERP);
+    strict_interp_kernel<<<(unsigned)((n_poses + 127) / 128), 128, smem, rt().stream>>>(
+        geom_of(g), g->maps.p, L, lig->x.p, lig->y.p, lig->z.p, lig->typ.p, src, n_poses, d_out);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
+}  // namespace mmo

@@ -1,0 +1,135 @@
+"""K1/K2 parity on the GPU through the C ABI: CUDA direct pair path vs the CPU oracle.
+
+fp64 mode: bit-identical (same operations, same order, no FMA).  fp32 mode: within the north-star
+tolerance max(1e-6*|E|, 1e-4 kcal/mol) -- including clashing poses, which the close-contact fp64
+correction pass exists for."""
+import numpy as np
+import pytest
+
+from conftest import tol_ok
+from mmo_b200 import pqrs, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _poses(c2, n, seed, radius=8.0):
+    R, t = workloads.random_poses_in_sphere(n, c2["roi"][:3], radius, seed=seed)
+    R[0] = np.eye(3).reshape(9)
+    t[0] = c2["start_pos"]          # the docked pose itself
+    return R, t
+
+
+@pytest.fixture(scope="module")
+def handles(gpu, c2, c2_roi_rec):
+    rec = gpu.Receptor.from_mol(c2_roi_rec)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    return rec, lig
+
+
+def test_fp64_bit_identical_shifted_and_global(gpu, orc, c2, c2_roi_rec, handles):
+    rec, lig = handles
+    m = c2["lig"]
+    R, t = _poses(c2, 40, seed=11)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    for shifted, variant in ((True, gpu.VARIANT_SHIFTED), (False, gpu.VARIANT_GLOBAL)):
+        want = orc.ene_inter(c2_roi_rec, m.q, m.anum, X, Y, Z, shifted=shifted)
+        got_c = gpu.Mol._score(rec, lig, variant, gpu.PREC_FP64, X, Y, Z)
+        got_p = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP64)
+        assert np.array_equal(got_c, want)
+        assert np.array_equal(got_p, want)      # on-device pose transform == Rot.rotate + translate_by
+
+
+def test_fp32_within_tolerance_including_clashes(gpu, orc, c2, c2_roi_rec, handles):
+    rec, lig = handles
+    m = c2["lig"]
+    R, t = _poses(c2, 600, seed=12)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    for shifted, variant in ((True, gpu.VARIANT_SHIFTED), (False, gpu.VARIANT_GLOBAL)):
+        want = orc.ene_inter(c2_roi_rec, m.q, m.anum, X, Y, Z, shifted=shifted)
+        got = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP32)
+        ok = tol_ok(got, want)
+        assert ok.all(), f"worst: {np.abs(got - want)[~ok].max()} at E={want[~ok]}"
+        got_c = gpu.Mol._score(rec, lig, variant, gpu.PREC_FP32, X, Y, Z)
+        assert tol_ok(got_c, want).all()
+    assert (want > 1e3).sum() > 50 and (want < 0).sum() > 0      # the sample holds clashes and good poses
+
+
+def test_fp32_far_away_pose_is_exactly_zero(gpu, c2, handles):
+    rec, lig = handles
+    t = np.array([[c2["roi"][0] + 80.0, c2["roi"][1], c2["roi"][2]]])
+    e = gpu.Mol.score_poses(rec, lig, np.eye(3).reshape(1, 9), t)
+    assert e[0] == 0.0          # lds.ml:920: E_inter = 0.0 exactly is a reset signal
+
+
+def test_empty_batch_and_ragged_sizes(gpu, orc):
+    rng = np.random.default_rng(5)
+    # receptor size not a multiple of the blob, ligand size not a multiple of the register chunk
+    for P, L in ((1, 1), (17, 3), (33, 9), (250, 13)):
+        rec_m = workloads.synthetic_receptor(P, "cube", 12.0, seed=P)
+        lx, ly, lz = rng.uniform(2, 10, (3, L))
+        lq = rng.uniform(-0.5, 0.5, L)
+        la = rng.choice([1, 6, 7, 8, 16, 17], L).astype(np.int32)
+        rec = gpu.Receptor.from_mol(rec_m)
+        lig = gpu.Ligand(lx, ly, lz, lq, la)
+        X, Y, Z = lx[None, :] + rng.uniform(-1, 1, (5, 1)), ly[None, :] + 0.0, lz[None, :] + 0.0
+        want = orc.ene_inter(rec_m, lq, la, X, Y, Z, shifted=True)
+        assert np.array_equal(gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP64, X, Y, Z), want)
+        assert tol_ok(gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP32, X, Y, Z), want).all()
+        assert gpu.Mol._score(rec, lig, 1, 0, np.empty((0, L)), np.empty((0, L)), np.empty((0, L))).shape == (0,)
+
+
+def test_empty_receptor_gives_zero(gpu):
+    rec = gpu.Receptor(np.empty(0), np.empty(0), np.empty(0), np.empty(0), np.empty(0, np.int32))
+    lig = gpu.Ligand([0.0, 1.0], [0.0, 0.0], [0.0, 0.0], [0.1, -0.1], [6, 8])
+    for prec in (gpu.PREC_FP32, gpu.PREC_FP64):
+        e = gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, prec, [[0.0, 1.0]], [[0.0, 0.0]], [[0.0, 0.0]])
+        assert e[0] == 0.0
+
+
+def test_coincident_atoms_use_the_001_clamp(gpu, orc):
+    # Math.non_zero_dist (math.ml:58-62): r < 0.01 -> 0.01, energies of order 1e30
+    rec_m = pqrs.Mol("one", np.array([5.0]), np.array([5.0]), np.array([5.0]), np.array([0.5]), np.array([1.7]),
+                     np.array([6], np.int32))
+    rec = gpu.Receptor.from_mol(rec_m)
+    lig = gpu.Ligand([0.0], [0.0], [0.0], [0.5], [6])
+    for dx in (0.0, 0.005, 0.0101):
+        X, Y, Z = [[5.0 + dx]], [[5.0]], [[5.0]]
+        want = orc.ene_inter(rec_m, [0.5], [6], X, Y, Z, shifted=True)
+        assert np.array_equal(gpu.Mol._score(rec, lig, 1, gpu.PREC_FP64, X, Y, Z), want)
+        assert tol_ok(gpu.Mol._score(rec, lig, 1, gpu.PREC_FP32, X, Y, Z), want).all()
+    assert want[0] > 1e29
+
+
+def test_unsupported_element_gives_nan_like_the_reference(gpu):
+    rec = gpu.Receptor([0.0], [0.0], [0.0], [0.1], [30])          # Zn is not in UFF.ml:10-22
+    lig = gpu.Ligand([0.0], [0.0], [0.0], [0.1], [6])
+    for prec in (gpu.PREC_FP32, gpu.PREC_FP64):
+        assert np.isnan(gpu.Mol._score(rec, lig, 1, prec, [[3.0]], [[0.0]], [[0.0]])[0])
+
+
+def test_components_and_intra_bit_identical(gpu, orc, c2, c2_roi_rec, handles):
+    rec, lig = handles
+    m = c2["lig"]
+    R, t = _poses(c2, 12, seed=13)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    e, v = gpu.Mol.ene_inter_UFF_shifted_bst_components(rec, lig, X, Y, Z)
+    we, wv = orc.ene_inter_components(c2_roi_rec, m.q, m.anum, X, Y, Z)
+    assert np.array_equal(e, we) and np.array_equal(v, wv)
+    # intra: the docked conformer, rigid copies of it and perturbed conformers
+    rng = np.random.default_rng(14)
+    Xc = np.concatenate([X, X[:4] + rng.normal(0, 0.3, (4, lig.n))])
+    Yc = np.concatenate([Y, Y[:4] + rng.normal(0, 0.3, (4, lig.n))])
+    Zc = np.concatenate([Z, Z[:4] + rng.normal(0, 0.3, (4, lig.n))])
+    assert np.array_equal(gpu.Mol.ene_intra_UFFNB_brute(lig, Xc, Yc, Zc), orc.ene_intra(m, Xc, Yc, Zc))
+
+
+def test_linearity_in_receptor_charges(gpu, c2, c2_roi_rec):
+    """size-independent property: E(q_rec) is affine in the receptor charges (Coulomb term)"""
+    m = c2_roi_rec
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    R, t = _poses(c2, 64, seed=15, radius=3.0)
+    e = []
+    for s in (0.0, 1.0, 2.0):
+        rec = gpu.Receptor(m.xs, m.ys, m.zs, m.q * s, m.anum)
+        e.append(gpu.Mol.score_poses(rec, lig, R, t, prec=gpu.PREC_FP64))
+    assert np.allclose(e[2] - e[1], e[1] - e[0], rtol=1e-9, atol=1e-7 * np.abs(e[1]).max())

@@ -1,0 +1,105 @@
+"""K3/K4/K5 parity: grid-map build, trilinear lookup, vdW bitmask -- bit-identical to the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from mmo_b200 import pqrs, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small(gpu, orc):
+    rec_m = workloads.synthetic_receptor(400, "cube", 20.0, seed=21, origin=(2.0, 2.0, 2.0))
+    dims = orc.grid_from_box(0.375, 9.0, 8.0, 7.0)
+    lig = pqrs.read_ligands_pqrs(os.path.join(workloads.GOLDEN, "ligdecs.pqrs"))[0]
+    ta, tq = pqrs.assign_ff_types([lig])
+    return rec_m, dims, lig, ta, tq
+
+
+def test_grid_build_bit_identical(gpu, orc, small):
+    rec_m, dims, lig, ta, tq = small
+    rec = gpu.Receptor.from_mol(rec_m)
+    want = orc.grid_build(rec_m, 0.375, dims, ta, tq)
+    g, got = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta, tq)
+    assert got.shape == want.shape == (22, dims[0] * dims[1] * dims[2])
+    assert np.array_equal(got, want)
+    assert (got == np.float32(1e5)).any()          # the max_E clamp is exercised
+    assert np.array_equal(g.download(), want)
+
+
+def test_grid_build_masked(gpu, orc, small):
+    rec_m, dims, lig, ta, tq = small
+    rec = gpu.Receptor.from_mol(rec_m)
+    mask = orc.bitmask_sphere(0.375, dims, (4.0, 4.0, 3.0), 3.0)
+    want = orc.grid_build(rec_m, 0.375, dims, ta[:5], tq[:5], mask=mask)
+    g, got = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta[:5], tq[:5], mask_bits=mask)
+    assert np.array_equal(got, want)
+    assert (got == 0.0).sum() > got.size // 3      # unmasked voxels stay exactly 0.0 (G3D.create)
+
+
+def test_trilin_and_interp_bit_identical(gpu, orc, small):
+    rec_m, dims, lig, ta, tq = small
+    rec = gpu.Receptor.from_mol(rec_m)
+    g, maps = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta, tq)
+    rng = np.random.default_rng(22)
+    hi = 0.375 * (np.array(dims) - 1)
+    P = rng.uniform(0.0, 0.999, (500, 3)) * hi
+    for t in (0, 7, 21):
+        got = gpu.G3D.trilin(g, t, P[:, 0], P[:, 1], P[:, 2])
+        want = np.array([orc.trilin(0.375, dims, maps[t], *p) for p in P])
+        assert np.array_equal(got, want)
+    # whole-ligand interpolated energy: small rigid poses that stay inside the grid
+    L = gpu.Ligand.from_mol(lig, centered=True)
+    scale = 0.25                                    # shrink the template so that it fits the 9x8x7 box
+    Ls = gpu.Ligand(L.xs * scale, L.ys * scale, L.zs * scale, lig.q, lig.anum, typ=lig.typ)
+    R, t = workloads.random_poses_in_sphere(200, hi / 2, 0.8, seed=23)
+    X, Y, Z = orc.pose_coords(L.xs * scale, L.ys * scale, L.zs * scale, R, t)
+    assert X.min() > 0 and (X.max(), Y.max(), Z.max()) < tuple(hi)
+    want = orc.ene_inter_interp(0.375, dims, maps, lig.typ, X, Y, Z)
+    assert np.array_equal(gpu.Mol.ene_inter_UFF_interp(g, Ls, X, Y, Z), want)
+    assert np.array_equal(gpu.Mol.interp_poses(g, Ls, R, t), want)
+
+
+def test_trilinear_known_answer_on_device(gpu):
+    dims = (8, 8, 8)
+    arr = np.zeros((1, 512), np.float32)
+    idx = lambda i, j, k: i + j * 8 + k * 64
+    for v, (i, j, k) in zip(range(1, 9), [(2, 3, 4), (3, 3, 4), (3, 4, 4), (2, 4, 4), (2, 3, 5), (3, 3, 5), (3, 4, 5), (2, 4, 5)]):
+        arr[0, idx(i, j, k)] = v
+    g = gpu.G3D.upload(0.5, dims, arr)
+    assert gpu.G3D.trilin(g, 0, [1.1], [1.7], [2.3])[0] == pytest.approx(4.639999999999999, rel=1e-15)
+
+
+def test_ba1_cache_files_roundtrip(gpu, small, tmp_path):
+    rec_m, dims, lig, ta, tq = small
+    rec = gpu.Receptor.from_mol(rec_m)
+    g, maps = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta[:3], tq[:3])
+    paths = []
+    for t in range(3):
+        p = str(tmp_path / f"lig.t{t}.ba1")
+        g.write_ba1(t, p)
+        paths.append(p)
+        raw = np.fromfile(p, "<f4")                 # G3D.to_ba1_file: raw little-endian f32, x fastest
+        assert np.array_equal(raw, maps[t])
+    txt = open(paths[0] + ".dims").read().split("\n")
+    assert txt[:4] == ["step: 0.375", f"x_dim: {dims[0]}", f"y_dim: {dims[1]}", f"z_dim: {dims[2]}"]
+    g2 = gpu.G3D.of_ba1_files(paths)
+    assert np.array_equal(g2.download(), maps)
+
+
+def test_vdw_mask_and_clash_bit_identical(gpu, orc, c2, c2_roi_rec):
+    dims = gpu.Grid.from_box(workloads.GRID_STEP, *c2["sim_dims"])
+    m = c2["rec"]
+    mask = gpu.Lds.vdW_volume(m.xs, m.ys, m.zs, m.r, workloads.GRID_STEP, dims)
+    want = orc.vdw_volume(m.xs, m.ys, m.zs, m.r, workloads.GRID_STEP, dims)
+    assert np.array_equal(mask.bits, want[:len(mask.bits)])
+    assert 0 < np.unpackbits(mask.bits).sum() < 0.2 * mask.bits.size * 8
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    R, t = workloads.random_poses_in_sphere(400, c2["roi"][:3], 9.0, seed=24)
+    got = gpu.Mol.protein_ligand_clash(mask, lig, R, t)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    ref = np.array([orc.protein_ligand_clash(workloads.GRID_STEP, dims, want, X[p], Y[p], Z[p]) for p in range(len(R))])
+    assert np.array_equal(got, ref)
+    assert 0 < ref.sum() < len(ref)

@@ -1,0 +1,99 @@
+"""Exhaustive rigid scan (lds.ml:1040-1114) on the GPU vs the oracle's literal loop nest."""
+import numpy as np
+import pytest
+
+from conftest import tol_ok
+from mmo_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(gpu, orc, c2, c2_roi_rec):
+    rec = gpu.Receptor.from_mol(c2_roi_rec)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    dims = gpu.Grid.from_box(workloads.GRID_STEP, *c2["sim_dims"])
+    m = c2["rec"]
+    mask = gpu.Lds.vdW_volume(m.xs, m.ys, m.zs, m.r, workloads.GRID_STEP, dims)
+    e_intra = orc.ene_intra(c2["lig"], lig.xs, lig.ys, lig.zs)[0]
+    return rec, lig, mask, dims, e_intra
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_scan_fp64_reproduces_argmin_and_topk_order(gpu, orc, c2, c2_roi_rec, setup, use_mask):
+    rec, lig, mask, dims, e_intra = setup
+    rot = gpu.SO3.rotations(48)
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 4.0)
+    kw = dict(vdw_mask=mask.bits, m_step=workloads.GRID_STEP, m_dims=dims) if use_mask else {}
+    want = orc.scan(c2_roi_rec, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 2.0, rot, 25, scorer=0,
+                    e_intra_const=e_intra, **kw)
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(25, roi, 2.0, rot, lig, rec=rec, vdw_mask=mask if use_mask else None,
+                                                  e_intra_const=e_intra, prec=gpu.PREC_FP64)
+    assert got["lattice_dims"] == want["lattice_dims"] == (5, 5, 5)
+    assert got["n_candidates"] == want["n_candidates"] and got["n_scored"] == want["n_scored"]
+    assert got["best_frame"] == want["best_frame"] and got["best_score"] == want["best_score"]
+    assert np.array_equal(got["top_frames"], want["top_frames"])
+    assert np.array_equal(got["top_scores"], want["top_scores"])
+    if use_mask:
+        assert 0 < want["n_scored"] < want["n_candidates"]
+
+
+def test_scan_fp32_within_tolerance_and_same_winner(gpu, orc, c2, c2_roi_rec, setup):
+    rec, lig, mask, dims, e_intra = setup
+    rot = gpu.SO3.rotations(200)
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 3.0)
+    want = orc.scan(c2_roi_rec, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 1.0, rot, 50, scorer=0, e_intra_const=e_intra)
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(50, roi, 1.0, rot, lig, rec=rec, e_intra_const=e_intra,
+                                                  prec=gpu.PREC_FP32)
+    assert got["n_scored"] == want["n_scored"]
+    assert tol_ok(got["top_scores"], want["top_scores"]).all()
+    # ordering can only differ between poses whose reference scores are closer than the tolerance
+    for a, b in zip(got["top_frames"], want["top_frames"]):
+        if a != b:
+            sa = orc.scan(c2_roi_rec, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 1.0, rot, 0, e_intra_const=e_intra,
+                          score_frames=[a, b])
+            assert abs(sa[0] - sa[1]) <= 2 * max(1e-6 * abs(sa[0]), 1e-4)
+    assert got["best_frame"] == want["best_frame"] or abs(got["best_score"] - want["best_score"]) < 2e-4
+
+
+def test_scan_sharded_ranges_merge_to_the_full_scan(gpu, c2, setup):
+    """lattice-point sub-ranges (the multi-GPU sharding unit) + mmo_topk_merge == one full scan"""
+    import ctypes as C
+    rec, lig, mask, dims, e_intra = setup
+    rot = gpu.SO3.rotations(64)
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 4.0)
+    k = 20
+    full = gpu.Lds.exhaustive_rigid_ligand_docking(k, roi, 2.0, rot, lig, rec=rec, prec=gpu.PREC_FP64)
+    nvox = int(np.prod(full["lattice_dims"]))
+    cuts = [0, nvox // 3, 2 * nvox // 3, nvox]
+    parts = [gpu.Lds.exhaustive_rigid_ligand_docking(k, roi, 2.0, rot, lig, rec=rec, prec=gpu.PREC_FP64,
+                                                     first_point=cuts[i], n_points=cuts[i + 1] - cuts[i]) for i in range(3)]
+    assert sum(p["n_scored"] for p in parts) == full["n_scored"]
+    S = np.full((3, k), np.inf); F = np.zeros((3, k), np.int64); cnt = np.zeros(3, np.int32)
+    for i, p in enumerate(parts):
+        n = len(p["top_scores"]); S[i, :n] = p["top_scores"]; F[i, :n] = p["top_frames"]; cnt[i] = n
+    os_, of_ = np.empty(k), np.empty(k, np.int64)
+    n = C.c_int32()
+    dp, lp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    assert gpu.lib().mmo_topk_merge(3, k, S.ctypes.data_as(dp), F.ctypes.data_as(lp), cnt.ctypes.data_as(ip),
+                                    os_.ctypes.data_as(dp), of_.ctypes.data_as(lp), C.byref(n)) == 0
+    assert np.array_equal(os_[:n.value], full["top_scores"]) and np.array_equal(of_[:n.value], full["top_frames"])
+    best = min(parts, key=lambda p: (p["best_score"], p["best_frame"]))
+    assert best["best_frame"] == full["best_frame"]
+
+
+def test_scan_interpolated_scorer(gpu, orc, c2, c2_roi_rec, setup):
+    from mmo_b200 import pqrs
+    rec, lig, mask, dims, e_intra = setup
+    # small energy grid around the ROI centre: origin-anchored grid covering the pocket
+    c = np.array(c2["roi"][:3])
+    gd = gpu.Grid.from_box(1.0, *(c + 16.0))
+    ta, tq = pqrs.assign_ff_types([c2["lig"]])
+    gmask = orc.bitmask_sphere(1.0, gd, c, 14.0)
+    g, maps = gpu.Lds.pre_calculate_FF_components_grid(rec, 1.0, gd, ta, tq, mask_bits=gmask)
+    rot = gpu.SO3.rotations(32)
+    roi = (c[0], c[1], c[2], 2.5)
+    want = orc.scan(None, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 1.0, rot, 10, scorer=2, maps=maps, g_step=1.0, g_dims=gd)
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, grid=g)
+    assert np.array_equal(got["top_frames"], want["top_frames"]) and np.array_equal(got["top_scores"], want["top_scores"])
+    assert got["best_frame"] == want["best_frame"]
