@@ -94,7 +94,7 @@ constexpr double kElecWeight = 332.0637 / 4.0;   // src/UFF.ml:25, src/const.ml:
 constexpr double kMaxE = 100000.0;               // src/params.ml:26
 
 // ---- geometry of the fp32 direct kernel -----------------------------------------------------------
-constexpr int kBlob = 16;        // receptor atoms per spatial blob (one cull test per blob)
+constexpr int kBlob = 8;         // receptor atoms per k-d leaf ("blob"): the unit of distance culling
 // close-contact threshold: pairs with x_i*x_j / r^2 > kTau are re-evaluated in fp64
 constexpr double kTau = 1.5;
 
@@ -111,10 +111,11 @@ struct mmo_receptor {
     // original order, double (strict fp64 kernels)
     mmo::DevBuf<double> x, y, z, q;
     mmo::DevBuf<int32_t> elt;        // compact element index
+    mmo::DevBuf<double4> xyzq64;     // {x, y, z, q} packed for the close-contact pass
     // blob order, fp32 (fast kernel): xyzq = {x-ox, y-oy, z-oz, EW*q}; ab = {A_i, B_i}
     mmo::DevBuf<float4> xyzq;
     mmo::DevBuf<float2> ab;
-    mmo::DevBuf<float> blob_box;     // n_blobs x 6 : lo xyz, hi xyz (relative coordinates)
+    mmo::DevBuf<float4> blob_box;    // n_blobs x 2 : {lo xyz, 0}, {hi xyz, 0} (relative coordinates)
     // close-contact voxel lists (fp64 correction pass)
     double vox_lo[3] = {0, 0, 0};
     double vox_edge = 2.0;
@@ -137,7 +138,10 @@ struct mmo_ligand {
     // device copies
     mmo::DevBuf<double> x, y, z, q;          // template conformer
     mmo::DevBuf<int32_t> elt, typ;
-    mmo::DevBuf<float4> fparam;              // {A_j, B_j, q_j, 0}
+    mmo::DevBuf<float4> fparam;              // {A_j, B_j, q_j, 0} in fast-path (k-d) order
+    mmo::DevBuf<double> fx, fy, fz;          // template conformer in fast-path order
+    int n_fast = 0;                          // atoms in fast-path order, padded to a multiple of 8
+    mmo::DevBuf<int32_t> forder;             // fast-path position -> original atom index
     mmo::DevBuf<int32_t> pair_i, pair_j;     // interacting pairs (i<j, dists>=3) in reference order
     int n_pairs = 0;
     mmo::DevBuf<int32_t> d_rb_left, d_rb_right, d_rg_off, d_rg_idx;
@@ -191,7 +195,11 @@ int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d
                     const mmo_mask *m);
 int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags);
 int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, const int64_t *d_points,
-                          int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter);
+                          const int32_t *d_rot_perm, int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter);
+
+// balanced k-d ordering: permutation of n points such that consecutive groups of `leaf` points are
+// spatially compact (only the last group may be short)
+void kd_order(int n, const double *x, const double *y, const double *z, int leaf, std::vector<int> &order);
 
 // host-side mirrors (host_math.cu)
 void so3_rotations(int n, double *rot9);

@@ -22,152 +22,198 @@
 
 namespace mmo {
 
-constexpr int LJ = 8;            // ligand atoms per register chunk
-constexpr int TPB = 128;         // poses per block
-constexpr int TILE_BLOBS = 32;   // blobs per shared-memory tile
-constexpr int TILE_ATOMS = TILE_BLOBS * kBlob;
+constexpr int LJ = 8;            // ligand atoms per register chunk (= one k-d leaf of the ligand)
+constexpr int TPB = 256;         // poses per block
+static_assert(kBlob == 8 && LJ == 8, "the 4-blobs x 8-atoms lane-parallel cull test assumes 8/8");
 
 struct FastArgs {
     int n_blobs;
     int n_atoms;             // real receptor atoms (the last blob may be padded)
     const float4 *xyzq;
     const float2 *ab;
-    const float *blob_box;
+    const float4 *blob_box;
     double origin[3];
-    int L;
-    const double *lx, *ly, *lz;
-    const float4 *lparam;
+    int L;                   // real ligand atoms
+    int n_fast;              // padded to a multiple of LJ
+    const double *lx, *ly, *lz;      // template in fast-path order
+    const int32_t *forder;           // fast-path position -> original atom index (explicit coordinates)
+    const float4 *lparam;            // fast-path order
     float H;                 // clamp on r^2 (fast path) == close-contact threshold (fix pass)
     unsigned long long *stats;   // [0] pairs evaluated, [1] pairs inside the cut-off (STATS builds)
 };
 
-// one receptor atom against one ligand atom; returns w * (EW q_i q_j / r + d_ij (p6^2 - 2 p6))
+// MUFU.RSQ without the denormal-input fix-up sequence rsqrtf() expands to (the argument is >= H > 1)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// one receptor atom against one ligand atom; adds w * (EW q_i q_j / r + d_ij (p6^2 - 2 p6)) to acc
 template <int VARIANT>
 __device__ __forceinline__ float pair_energy(float dx, float dy, float dz, float qi, float Ai, float Bi,
                                              float qj, float Aj, float Bj, float H, float acc) {
     float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     float r2c = fmaxf(r2, H);                       // close contacts are finished in fp64 elsewhere
-    float rinv = rsqrtf(r2c);
+    float rinv = rsqrt_fast(r2c);
     float s = rinv * rinv;
     float s3 = s * s * s;
     float v = fmaf(Ai * Aj, s3, -(Bi * Bj));        // (A_i A_j) s^3 - B_i B_j
     float er = (qi * qj) * rinv;                    // qi already carries 332.0637/4
     float e = fmaf(v, s3, er);
     if (VARIANT == MMO_VARIANT_SHIFTED) {
-        float u = fmaxf(fmaf(r2c, -1.0f / 144.0f, 1.0f), 0.0f);   // 0 beyond the 12 A cut-off
+        // shift weight (1 - r^2/144)^2 = (144 - r^2)^2 / 144^2; the constant factor is applied once per
+        // receptor atom (kInvCut4), which keeps this at FADD-immediate + FMNMX + FMUL
+        float u = fmaxf(144.0f - r2c, 0.0f);                      // 0 beyond the 12 A cut-off
         return fmaf(u * u, e, acc);
     } else {
         return acc + e;
     }
 }
 
+// Shared memory (dynamic): receptor tile {xyzq[tile_atoms], ab[tile_atoms], box[2*tile_blobs]}, the
+// ligand parameters {A_j, B_j, q_j, real?}[n_fast] and this block's chunk coordinates [LJ][TPB].
 template <int VARIANT, bool STATS>
-__global__ void __launch_bounds__(TPB)
-direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ out) {
-    __shared__ float4 s_xyzq[TILE_ATOMS];
-    __shared__ float2 s_ab[TILE_ATOMS];
-    __shared__ float s_box[TILE_BLOBS * 6];
-    extern __shared__ float4 s_lparam[];          // L entries {A_j, B_j, q_j, 0}
+__global__ void __launch_bounds__(TPB, 2)
+direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_blobs, double *__restrict__ out) {
+    extern __shared__ float4 smem4[];
+    float4 *s_xyzq = smem4;                                   // tile_blobs * 8
+    float4 *s_box = s_xyzq + tile_blobs * kBlob;              // tile_blobs * 2
+    float4 *s_lparam = s_box + tile_blobs * 2;                // n_fast
+    float4 *s_c = s_lparam + a.n_fast;                        // LJ * TPB : {x, y, z, -} of chunk atom jj, pose tid
+    float2 *s_ab = (float2 *)(s_c + LJ * TPB);                // tile_blobs * 8
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const int64_t p = (int64_t)blockIdx.x * TPB + tid;
     const bool valid = p < n_poses;
     const int64_t pp = valid ? p : n_poses - 1;   // idle lanes shadow the last pose, result discarded
-    for (int j = tid; j < a.L; j += TPB) s_lparam[j] = a.lparam[j];
+    for (int j = tid; j < a.n_fast; j += TPB) s_lparam[j] = a.lparam[j];
 
     double acc = 0.0;
     unsigned long long n_eval = 0, n_in = 0;
-    const int n_chunks = (a.L + LJ - 1) / LJ;
-    const int n_tiles = (a.n_blobs + TILE_BLOBS - 1) / TILE_BLOBS;
+    const int n_chunks = a.n_fast / LJ;
+    const int n_tiles = (a.n_blobs + tile_blobs - 1) / tile_blobs;
 
-    for (int c = 0; c < n_chunks; c++) {
-        // ---- this pose's chunk of ligand atoms: reference arithmetic in double, then fp32 -----
-        float cx[LJ], cy[LJ], cz[LJ], cA[LJ], cB[LJ], cQ[LJ];
-        __syncthreads();     // s_lparam visible (first pass); previous tile fully consumed
-        {
-            PoseRT P;
-            if (src.kind != 1) load_pose_rt(src, pp, P);
+    for (int t = 0; t < n_tiles; t++) {
+        // ---- stage a receptor tile (the whole ROI receptor when it fits: one tile, two barriers) ----
+        __syncthreads();
+        const int b0 = t * tile_blobs;
+        const int nb = min(tile_blobs, a.n_blobs - b0);
+        for (int k = tid; k < nb * kBlob; k += TPB) {
+            s_xyzq[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+            s_ab[k] = __ldg(a.ab + (size_t)b0 * kBlob + k);
+        }
+        const int nb4 = (nb + 3) & ~3;
+        for (int k = tid; k < nb4 * 2; k += TPB)
+            s_box[k] = (k < nb * 2) ? __ldg(a.blob_box + (size_t)b0 * 2 + k)
+                                    : make_float4(3e38f, 3e38f, 3e38f, 0.f);   // absent blob: never near
+        __syncthreads();
+
+        for (int c = 0; c < n_chunks; c++) {
+            // ---- this pose's chunk of ligand atoms: reference arithmetic in double, then fp32 -----
+            // (own column of s_c only: no block barrier needed, __syncwarp orders the warp's accesses)
+            float mlo[3] = {3e38f, 3e38f, 3e38f}, mhi[3] = {-3e38f, -3e38f, -3e38f};
+            {
+                PoseRT P;
+                if (src.kind != 1) load_pose_rt(src, pp, P);
 #pragma unroll
-            for (int jj = 0; jj < LJ; jj++) {
-                int j = c * LJ + jj;
-                if (j < a.L) {
-                    double x, y, z;
-                    if (src.kind == 1) {
-                        x = src.xs[pp * a.L + j]; y = src.ys[pp * a.L + j]; z = src.zs[pp * a.L + j];
-                    } else {
-                        pose_atom_rt(P, __ldg(a.lx + j), __ldg(a.ly + j), __ldg(a.lz + j), x, y, z);
+                for (int jj = 0; jj < LJ; jj++) {
+                    const int k = c * LJ + jj;
+                    const bool real = s_lparam[k].w != 0.f;
+                    float4 v = make_float4(-1e6f, -1e6f, -1e6f, 0.f);   // padding atom: never near anything
+                    if (real) {
+                        double x, y, z;
+                        if (src.kind == 1) {
+                            const int j = __ldg(a.forder + k);
+                            x = src.xs[pp * a.L + j]; y = src.ys[pp * a.L + j]; z = src.zs[pp * a.L + j];
+                        } else {
+                            pose_atom_rt(P, __ldg(a.lx + k), __ldg(a.ly + k), __ldg(a.lz + k), x, y, z);
+                        }
+                        v.x = (float)(x - a.origin[0]);
+                        v.y = (float)(y - a.origin[1]);
+                        v.z = (float)(z - a.origin[2]);
                     }
-                    cx[jj] = (float)(x - a.origin[0]);
-                    cy[jj] = (float)(y - a.origin[1]);
-                    cz[jj] = (float)(z - a.origin[2]);
-                    float4 lp = s_lparam[j];
-                    cA[jj] = lp.x; cB[jj] = lp.y; cQ[jj] = lp.z;
-                } else {          // padding atom: no charge, no vdW
-                    cx[jj] = -1e6f; cy[jj] = -1e6f; cz[jj] = -1e6f;
-                    cA[jj] = 0.f; cB[jj] = 0.f; cQ[jj] = 0.f;
-                }
-            }
-        }
-        // ---- warp bounding box of the chunk (real atoms only) ---------------------------------
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-        if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    s_c[jj * TPB + tid] = v;
+                    // per-atom bounding box over the warp's 32 poses; lane keeps the box of atom lane&7
+                    if (VARIANT == MMO_VARIANT_SHIFTED) {
+                        float lo[3] = {v.x, v.y, v.z}, hi[3] = {v.x, v.y, v.z};
 #pragma unroll
-            for (int jj = 0; jj < LJ; jj++) {
-                if (c * LJ + jj < a.L) {
-                    lo[0] = fminf(lo[0], cx[jj]); hi[0] = fmaxf(hi[0], cx[jj]);
-                    lo[1] = fminf(lo[1], cy[jj]); hi[1] = fmaxf(hi[1], cy[jj]);
-                    lo[2] = fminf(lo[2], cz[jj]); hi[2] = fmaxf(hi[2], cz[jj]);
-                }
-            }
+                        for (int d = 0; d < 3; d++) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
+                            for (int o = 16; o > 0; o >>= 1) {
+                                lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+                                hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+                            }
+                        }
+                        if ((lane & 7) == jj && real) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-                    hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-                }
-            }
-        }
-
-        for (int t = 0; t < n_tiles; t++) {
-            if (t > 0) __syncthreads();
-            const int b0 = t * TILE_BLOBS;
-            const int nb = min(TILE_BLOBS, a.n_blobs - b0);
-            for (int k = tid; k < nb * kBlob; k += TPB) {
-                s_xyzq[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
-                s_ab[k] = __ldg(a.ab + (size_t)b0 * kBlob + k);
-            }
-            for (int k = tid; k < nb * 6; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 6 + k);
-            __syncthreads();
-
-            for (int b = 0; b < nb; b++) {
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    const float *bx = s_box + b * 6;
-                    float gx = fmaxf(0.f, fmaxf(bx[0] - hi[0], lo[0] - bx[3]));
-                    float gy = fmaxf(0.f, fmaxf(bx[1] - hi[1], lo[1] - bx[4]));
-                    float gz = fmaxf(0.f, fmaxf(bx[2] - hi[2], lo[2] - bx[5]));
-                    if (fmaf(gz, gz, fmaf(gy, gy, gx * gx)) >= 144.0f) continue;   // warp-uniform
-                }
-                if (STATS) n_eval += (unsigned long long)min(kBlob, a.n_atoms - (b0 + b) * kBlob) * min(LJ, a.L - c * LJ);
-#pragma unroll 2
-                for (int i = 0; i < kBlob; i++) {
-                    const float4 ra = s_xyzq[b * kBlob + i];
-                    const float2 rp = s_ab[b * kBlob + i];
-                    float f = 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < LJ; jj++) {
-                        float dx = ra.x - cx[jj], dy = ra.y - cy[jj], dz = ra.z - cz[jj];
-                        f = pair_energy<VARIANT>(dx, dy, dz, ra.w, rp.x, rp.y, cQ[jj], cA[jj], cB[jj], a.H, f);
-                        if (STATS) {
-                            float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            if (r2 < 144.0f && ra.x < 1e5f && c * LJ + jj < a.L) n_in++;
+                            for (int d = 0; d < 3; d++) { mlo[d] = lo[d]; mhi[d] = hi[d]; }
                         }
                     }
-                    acc += (double)f;
                 }
             }
+            __syncwarp();
+
+            for (int g = 0; g < nb; g += 4) {
+                // lane-parallel cull test: lane (q, jj) = (lane>>3, lane&7) tests blob g+q against atom jj
+                unsigned near = 0xffffffffu;
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    const float4 blo = s_box[(g + (lane >> 3)) * 2], bhi = s_box[(g + (lane >> 3)) * 2 + 1];
+                    float gx = fmaxf(0.f, fmaxf(blo.x - mhi[0], mlo[0] - bhi.x));
+                    float gy = fmaxf(0.f, fmaxf(blo.y - mhi[1], mlo[1] - bhi.y));
+                    float gz = fmaxf(0.f, fmaxf(blo.z - mhi[2], mlo[2] - bhi.z));
+                    near = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f);
+                    if (near == 0u) continue;                 // warp-uniform
+                }
+#pragma unroll 1
+                for (int q = 0; q < 4; q++) {
+                    unsigned m = (near >> (8 * q)) & 0xffu;
+                    const int b = g + q;
+                    if (m == 0u || b >= nb) continue;          // warp-uniform
+                    if (STATS) n_eval += (unsigned long long)max(0, min(kBlob, a.n_atoms - (b0 + b) * kBlob)) * __popc(m);
+                    // the blob's 8 atoms go to registers once; every near ligand atom then runs 8
+                    // independent pair chains (ILP) behind a single warp-uniform loop branch
+                    float4 ra[kBlob];
+                    float2 rp[kBlob];
+#pragma unroll
+                    for (int i = 0; i < kBlob; i++) { ra[i] = s_xyzq[b * kBlob + i]; rp[i] = s_ab[b * kBlob + i]; }
+                    // software-pipelined loop over the near ligand atoms of this blob: the next atom's
+                    // coordinates/parameters are fetched while the current 8 pairs are computed
+                    int jj = __ffs(m) - 1;
+                    m &= m - 1;
+                    float4 lc = s_c[jj * TPB + tid];
+                    float4 lp = s_lparam[c * LJ + jj];
+#pragma unroll 1
+                    while (true) {
+                        float4 lc_n = lc, lp_n = lp;
+                        const bool more = m != 0u;
+                        if (more) {
+                            jj = __ffs(m) - 1;
+                            m &= m - 1;
+                            lc_n = s_c[jj * TPB + tid];
+                            lp_n = s_lparam[c * LJ + jj];
+                        }
+                        float f = 0.f;
+#pragma unroll
+                        for (int i = 0; i < kBlob; i++) {
+                            float dx = ra[i].x - lc.x, dy = ra[i].y - lc.y, dz = ra[i].z - lc.z;
+                            f = pair_energy<VARIANT>(dx, dy, dz, ra[i].w, rp[i].x, rp[i].y, lp.z, lp.x, lp.y, a.H, f);
+                            if (STATS) {
+                                float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                                if (r2 < 144.0f && ra[i].x < 1e5f) n_in++;
+                            }
+                        }
+                        acc += (double)f;
+                        if (!more) break;
+                        lc = lc_n; lp = lp_n;
+                    }
+                }
+            }
+            __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
         }
     }
+    if (VARIANT == MMO_VARIANT_SHIFTED) acc *= 1.0 / (144.0 * 144.0);
     if (valid) out[p] = acc;
     if (STATS && valid) {
         atomicAdd(a.stats + 0, n_eval);
@@ -175,9 +221,13 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, double *__restrict_
     }
 }
 
-// ---- close-contact correction in the reference's double arithmetic ----------------------------------
+// ---- close-contact correction (fp64) ---------------------------------------------------------------
+// For every pair with r^2 < H the fast path evaluated e(sqrt(H)); this pass adds e(r) - e(sqrt(H)) in
+// double.  Same formulas as mol.ml:811-815 / 838-845 (r clamped at 0.01, p6 = (x_ij/r)^6, shift weight),
+// written with one reciprocal square root instead of sqrt + two divisions: the result only has to be
+// accurate to ~1e-12 relative, not bit-identical (MMO_PREC_FP64 is the bit-identical mode).
 struct FixArgs {
-    const double *px, *py, *pz, *pq;     // receptor, original order
+    const double4 *pxyzq;                // receptor {x, y, z, q}, original order
     const int32_t *pelt;
     double vox_lo[3], vox_inv;
     int vox_dim[3];
@@ -186,26 +236,10 @@ struct FixArgs {
     const double *lx, *ly, *lz, *lq;
     const int32_t *lelt;
     double H;                            // exactly the fp32 clamp value
-    const double *xij, *dij;             // kEltTab^2 tables (UFF.ml:32-51)
+    double rinvH, wH;                    // 1/sqrt(H), (1 - H/144)^2
+    const double *xx, *dij, *vdwH;       // kEltTab^2 tables: x_i*x_j, d_ij, d_ij*(p6H^2 - 2 p6H)
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
-
-template <int VARIANT>
-__device__ __forceinline__ double e64(double r2, double qq, double xij, double dij) {
-    // mol.ml:811-815 / 838-845 for one pair
-    double r = sqrt(r2);
-    if (r < 0.01) r = 0.01;
-    double t = xij / r;
-    double t2 = t * t;
-    double p6 = (t2 * t2) * t2;
-    double e = kElecWeight * (qq / r) + dij * ((-2.0 * p6) + (p6 * p6));
-    if (VARIANT == MMO_VARIANT_SHIFTED) {
-        double w = 0.0;
-        if (r < 12.0) { double u = 1.0 - (r / 12.0) * (r / 12.0); w = u * u; }
-        e = w * e;
-    }
-    return e;
-}
 
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(128)
@@ -230,17 +264,30 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ ou
         size_t v = (size_t)vi + (size_t)vj * a.vox_dim[0] + (size_t)vk * a.vox_dim[0] * a.vox_dim[1];
         int k0 = __ldg(a.vox_off + v), k1 = __ldg(a.vox_off + v + 1);
         if (k0 == k1) continue;
-        const double qj = __ldg(a.lq + j);
+        const double qj = kElecWeight * __ldg(a.lq + j);
         const int ej = __ldg(a.lelt + j);
         for (int k = k0; k < k1; k++) {
-            int i = __ldg(a.vox_idx + k);
-            double dx = __ldg(a.px + i) - x, dy = __ldg(a.py + i) - y, dz = __ldg(a.pz + i) - z;
-            double r2 = dx * dx + dy * dy + dz * dz;
+            const int i = __ldg(a.vox_idx + k);
+            const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
+            const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
+            const double4 ra = make_double4(r01.x, r01.y, r23.x, r23.y);
+            const double dx = ra.x - x, dy = ra.y - y, dz = ra.z - z;
+            const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 < a.H) {
-                int t = __ldg(a.pelt + i) * kEltTab + ej;
-                double qq = __ldg(a.pq + i) * qj;
-                double xij = __ldg(a.xij + t), dij = __ldg(a.dij + t);
-                corr += e64<VARIANT>(r2, qq, xij, dij) - e64<VARIANT>(a.H, qq, xij, dij);
+                const int t = __ldg(a.pelt + i) * kEltTab + ej;
+                const double qq = ra.w * qj;
+                const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
+                const double rinv = rsqrt(r2c);
+                const double t2 = __ldg(a.xx + t) * (rinv * rinv);  // (x_ij / r)^2
+                const double p6 = t2 * t2 * t2;
+                double e = qq * rinv + __ldg(a.dij + t) * (p6 * p6 - 2.0 * p6);
+                double eH = qq * a.rinvH + __ldg(a.vdwH + t);
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    const double u = 1.0 - r2c * (1.0 / 144.0);
+                    e *= u * u;
+                    eH *= a.wH;
+                }
+                corr += e - eH;
                 if (STATS) n_fix++;
             }
         }
@@ -250,63 +297,97 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ ou
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static DevBuf<double> g_xij, g_dij;
+static DevBuf<double> g_xx, g_dij, g_vdwH;
 static DevBuf<unsigned long long> g_stats;
+static double g_vdwH_for = -1.0;
 
-static int ensure_fix_tables() {
-    if (g_xij.p) return MMO_OK;
-    std::vector<double> hx(kEltTab * kEltTab), hd(kEltTab * kEltTab);
-    for (int a = 0; a < kEltTab; a++)
-        for (int b = 0; b < kEltTab; b++) {
-            bool ok = a < kNumElt && b < kNumElt;
-            hx[a * kEltTab + b] = ok ? sqrt(kEltXi[a] * kEltXi[b]) : NAN;
-            hd[a * kEltTab + b] = ok ? sqrt(kEltDi[a] * kEltDi[b]) : NAN;
-        }
-    MMO_TRY(g_xij.upload(hx));
-    MMO_TRY(g_dij.upload(hd));
-    MMO_TRY(g_stats.alloc(4));
+static int ensure_fix_tables(double H) {
+    if (!g_xx.p) {
+        std::vector<double> hx(kEltTab * kEltTab), hd(kEltTab * kEltTab);
+        for (int a = 0; a < kEltTab; a++)
+            for (int b = 0; b < kEltTab; b++) {
+                bool ok = a < kNumElt && b < kNumElt;
+                hx[a * kEltTab + b] = ok ? kEltXi[a] * kEltXi[b] : NAN;
+                hd[a * kEltTab + b] = ok ? sqrt(kEltDi[a] * kEltDi[b]) : NAN;
+            }
+        MMO_TRY(g_xx.upload(hx));
+        MMO_TRY(g_dij.upload(hd));
+        MMO_TRY(g_stats.alloc(4));
+    }
+    if (g_vdwH_for != H) {
+        std::vector<double> hv(kEltTab * kEltTab);
+        for (int a = 0; a < kEltTab; a++)
+            for (int b = 0; b < kEltTab; b++) {
+                bool ok = a < kNumElt && b < kNumElt;
+                double t2 = ok ? kEltXi[a] * kEltXi[b] / H : NAN;
+                double p6 = t2 * t2 * t2;
+                hv[a * kEltTab + b] = ok ? sqrt(kEltDi[a] * kEltDi[b]) * (p6 * p6 - 2.0 * p6) : NAN;
+            }
+        MMO_TRY(g_vdwH.upload(hv));
+        g_vdwH_for = H;
+    }
+    return MMO_OK;
+}
+
+static int set_fast_smem(size_t smem) {
+    static size_t done = 0;
+    if (smem <= done) return MMO_OK;
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = smem;
     return MMO_OK;
 }
 
 int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
                        int64_t n_poses, double *d_out, bool collect_stats) {
-    MMO_TRY(ensure_fix_tables());
     if (n_poses == 0) return MMO_OK;
     Runtime &R = rt();
     // clamp / close-contact threshold on r^2; a float so that both kernels see the same number
     const float H = (float)(std::max(rec->x_max, 1.0) * std::max(lig->x_max, 1.0) / kTau);
+    MMO_TRY(ensure_fix_tables((double)H));
     FastArgs fa;
     fa.n_blobs = rec->n_blobs;
     fa.n_atoms = rec->n;
     fa.xyzq = rec->xyzq.p; fa.ab = rec->ab.p; fa.blob_box = rec->blob_box.p;
     for (int d = 0; d < 3; d++) fa.origin[d] = rec->origin[d];
     fa.L = lig->n;
-    fa.lx = lig->x.p; fa.ly = lig->y.p; fa.lz = lig->z.p;
+    fa.n_fast = lig->n_fast;
+    fa.lx = lig->fx.p; fa.ly = lig->fy.p; fa.lz = lig->fz.p;
+    fa.forder = lig->forder.p;
     fa.lparam = lig->fparam.p;
     fa.H = H;
     fa.stats = g_stats.p;
     FixArgs xa;
-    xa.px = rec->x.p; xa.py = rec->y.p; xa.pz = rec->z.p; xa.pq = rec->q.p; xa.pelt = rec->elt.p;
+    xa.pxyzq = rec->xyzq64.p; xa.pelt = rec->elt.p;
     for (int d = 0; d < 3; d++) { xa.vox_lo[d] = rec->vox_lo[d]; xa.vox_dim[d] = rec->vox_dim[d]; }
     xa.vox_inv = 1.0 / rec->vox_edge;
     xa.vox_off = rec->vox_off.p; xa.vox_idx = rec->vox_idx.p;
     xa.L = lig->n;
     xa.lx = lig->x.p; xa.ly = lig->y.p; xa.lz = lig->z.p; xa.lq = lig->q.p; xa.lelt = lig->elt.p;
     xa.H = (double)H;
-    xa.xij = g_xij.p; xa.dij = g_dij.p;
+    xa.rinvH = 1.0 / sqrt((double)H);
+    xa.wH = (1.0 - (double)H / 144.0) * (1.0 - (double)H / 144.0);
+    xa.xx = g_xx.p; xa.dij = g_dij.p; xa.vdwH = g_vdwH.p;
     xa.stats = g_stats.p;
 
     if (collect_stats) MMO_CUDA(cudaMemsetAsync(g_stats.p, 0, 4 * sizeof(unsigned long long), R.stream));
     const unsigned blocks = (unsigned)((n_poses + TPB - 1) / TPB);
-    const size_t smem = (size_t)lig->n * sizeof(float4);
+    // receptor tile: everything when it fits ~52 KB, so that 4 blocks stay resident per SM
+    int tile_blobs = std::min(rec->n_blobs, 256);
+    tile_blobs = std::max(4, (tile_blobs + 3) & ~3);
+    const size_t smem = ((size_t)tile_blobs * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast + (size_t)LJ * TPB) * sizeof(float4) +
+                        (size_t)tile_blobs * kBlob * sizeof(float2);
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
+        MMO_TRY(set_fast_smem(smem));
         {
         KernelScope ks(K_DIRECT_FP32);
-        if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, d_out);
-        else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, d_out);
-        else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, d_out);
-        else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, d_out);
+        if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
+        else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
+        else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
+        else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
         }
         MMO_LAUNCH_CHECK();
         KernelScope ks2(K_HARD_FIX);

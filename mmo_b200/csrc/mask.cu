@@ -80,7 +80,8 @@ clash_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_d
 __global__ void __launch_bounds__(256)
 scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_dim, int L,
                       const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
-                      PoseSrc src /* kind 2, frames unused */, const int64_t *__restrict__ points, int64_t n_cand,
+                      PoseSrc src /* kind 2, frames unused */, const int64_t *__restrict__ points,
+                      const int32_t *__restrict__ rot_perm, int64_t n_cand,
                       int64_t *__restrict__ frames, unsigned long long *__restrict__ counter) {
     __shared__ unsigned long long s_base;
     __shared__ int s_warp[8];
@@ -89,7 +90,9 @@ scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim,
     int64_t frame = 0;
     if (c < n_cand) {
         int64_t pt = __ldg(points + c / src.n_rot);
-        int rot_i = (int)(c % src.n_rot);
+        // rotations are visited in a spatially coherent order (neighbouring lanes = similar rotations);
+        // the frame id keeps the reference's numbering, so results do not depend on the visiting order
+        int rot_i = __ldg(rot_perm + (int)(c % src.n_rot));
         frame = (int64_t)rot_i + (int64_t)src.n_rot * pt;
         keep = true;
         if (words) {
@@ -141,12 +144,12 @@ int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, i
 }
 
 int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, const int64_t *d_points,
-                          int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter) {
+                          const int32_t *d_rot_perm, int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter) {
     if (n_cand == 0) return MMO_OK;
     KernelScope ks(K_PREFILTER);
     scan_prefilter_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, rt().stream>>>(
         m ? m->words.p : nullptr, m ? 1.0 / m->step : 0.0, m ? m->dims[0] : 0, m ? m->dims[0] * m->dims[1] : 0,
-        lig->n, lig->x.p, lig->y.p, lig->z.p, src, d_points, n_cand, d_frames, d_counter);
+        lig->n, lig->x.p, lig->y.p, lig->z.p, src, d_points, d_rot_perm, n_cand, d_frames, d_counter);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }

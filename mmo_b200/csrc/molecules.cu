@@ -30,13 +30,30 @@ double vdw_radius(int anum) {
     }
 }
 
-static inline uint32_t spread3(uint32_t v) {   // 10 bits -> every third bit
-    v &= 0x3ff;
-    v = (v | (v << 16)) & 0x030000ff;
-    v = (v | (v << 8)) & 0x0300f00f;
-    v = (v | (v << 4)) & 0x030c30c3;
-    v = (v | (v << 2)) & 0x09249249;
-    return v;
+static void kd_rec(const double *const c[3], int *idx, int n, int leaf) {
+    if (n <= leaf) return;
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) {
+        lo[d] = hi[d] = c[d][idx[0]];
+        for (int k = 1; k < n; k++) { lo[d] = std::min(lo[d], c[d][idx[k]]); hi[d] = std::max(hi[d], c[d][idx[k]]); }
+    }
+    int ax = 0;
+    if (hi[1] - lo[1] > hi[ax] - lo[ax]) ax = 1;
+    if (hi[2] - lo[2] > hi[ax] - lo[ax]) ax = 2;
+    // left part: a multiple of `leaf`, as close to n/2 as possible -> every leaf but the last is full
+    int nl = ((n / 2 + leaf - 1) / leaf) * leaf;
+    if (nl >= n) nl = n - leaf;
+    const double *v = c[ax];
+    std::nth_element(idx, idx + nl, idx + n, [v](int a, int b) { return v[a] < v[b] || (v[a] == v[b] && a < b); });
+    kd_rec(c, idx, nl, leaf);
+    kd_rec(c, idx + nl, n - nl, leaf);
+}
+
+void kd_order(int n, const double *x, const double *y, const double *z, int leaf, std::vector<int> &order) {
+    order.resize(n);
+    std::iota(order.begin(), order.end(), 0);
+    const double *c[3] = {x, y, z};
+    if (n > 0) kd_rec(c, order.data(), n, leaf);
 }
 
 // vdW factors of the A/B form: d_ij*(p6^2 - 2 p6) = (A_i A_j) s^6 - (B_i B_j) s^3 with s = 1/r^2,
@@ -80,24 +97,14 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     }
     for (int d = 0; d < 3; d++) r->origin[d] = 0.5 * (lo[d] + hi[d]);
 
-    // ---- Morton order -> blobs of kBlob spatially close atoms
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    double ext = 1e-9;
-    for (int d = 0; d < 3; d++) ext = std::max(ext, hi[d] - lo[d]);
-    std::vector<uint32_t> code(n);
-    for (int i = 0; i < n; i++) {
-        uint32_t cx = (uint32_t)std::min(1023.0, (xs[i] - lo[0]) / ext * 1023.0);
-        uint32_t cy = (uint32_t)std::min(1023.0, (ys[i] - lo[1]) / ext * 1023.0);
-        uint32_t cz = (uint32_t)std::min(1023.0, (zs[i] - lo[2]) / ext * 1023.0);
-        code[i] = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+    // ---- k-d leaves -> blobs of kBlob spatially close atoms
+    std::vector<int> order;
+    kd_order(n, xs, ys, zs, kBlob, order);
     r->n_blobs = (n + kBlob - 1) / kBlob;
     r->n_pad = r->n_blobs * kBlob;
     std::vector<float4> xyzq(std::max(1, r->n_pad));
     std::vector<float2> ab(std::max(1, r->n_pad));
-    std::vector<float> box((size_t)std::max(1, r->n_blobs) * 6);
+    std::vector<float4> box((size_t)std::max(1, r->n_blobs) * 2);
     for (int b = 0; b < r->n_blobs; b++) {
         float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
         for (int s = 0; s < kBlob; s++) {
@@ -118,7 +125,8 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
                 ab[k] = make_float2(0.f, 0.f);
             }
         }
-        for (int d = 0; d < 3; d++) { box[(size_t)b * 6 + d] = blo[d]; box[(size_t)b * 6 + 3 + d] = bhi[d]; }
+        box[(size_t)b * 2] = make_float4(blo[0], blo[1], blo[2], 0.f);
+        box[(size_t)b * 2 + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
     }
 
     // ---- close-contact voxel lists: atoms within r_list of any point of the voxel (conservative)
@@ -153,8 +161,11 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
     for (int i = 0; i < n; i++) for_each_voxel(i, [&](size_t v) { idx[fill[v]++] = i; });   // ascending atom index per voxel
 
+    std::vector<double4> xyzq64(std::max(1, n));
+    for (int i = 0; i < n; i++) xyzq64[i] = make_double4(xs[i], ys[i], zs[i], q[i]);
     int rc = MMO_OK;
     do {
+        if ((rc = r->xyzq64.upload(xyzq64))) break;
         if ((rc = r->x.upload(r->hx)) || (rc = r->y.upload(r->hy)) || (rc = r->z.upload(r->hz)) ||
             (rc = r->q.upload(r->hq)) || (rc = r->elt.upload(elt)) || (rc = r->xyzq.upload(xyzq)) ||
             (rc = r->ab.upload(ab)) || (rc = r->blob_box.upload(box)) || (rc = r->vox_off.upload(cnt)) ||
@@ -217,20 +228,29 @@ int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const doubl
         l->rg_off.assign(1, 0);
     }
     std::vector<int32_t> elt(n);
-    std::vector<float4> fp(n);
     l->x_max = 0.0;
     for (int j = 0; j < n; j++) {
         elt[j] = elt_index(anum[j]);
+        if (elt[j] < kNumElt && kEltXi[elt[j]] > l->x_max) l->x_max = kEltXi[elt[j]];
+    }
+    // fast-path order: k-d leaves of 8 atoms = the register chunks of the fp32 kernel
+    std::vector<int> forder;
+    kd_order(n, xs, ys, zs, 8, forder);
+    l->n_fast = ((n + 7) / 8) * 8;
+    std::vector<float4> fp(l->n_fast, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<double> fx(l->n_fast, 0.0), fy(l->n_fast, 0.0), fz(l->n_fast, 0.0);
+    for (int k = 0; k < n; k++) {
+        int j = forder[k];
         float A, B;
         vdw_factors(elt[j], &A, &B);
-        fp[j] = make_float4(A, B, (float)q[j], 0.f);
-        if (elt[j] < kNumElt && kEltXi[elt[j]] > l->x_max) l->x_max = kEltXi[elt[j]];
+        fp[k] = make_float4(A, B, (float)q[j], 1.f);     // .w = 1 marks a real atom
+        fx[k] = xs[j]; fy[k] = ys[j]; fz[k] = zs[j];
     }
     int rc = MMO_OK;
     do {
         if ((rc = l->x.upload(l->hx)) || (rc = l->y.upload(l->hy)) || (rc = l->z.upload(l->hz)) ||
             (rc = l->q.upload(l->hq)) || (rc = l->elt.upload(elt)) || (rc = l->typ.upload(l->htyp)) ||
-            (rc = l->fparam.upload(fp)) || (rc = l->pair_i.upload(pi)) || (rc = l->pair_j.upload(pj)) ||
+            (rc = l->fparam.upload(fp)) || (rc = l->fx.upload(fx)) || (rc = l->fy.upload(fy)) || (rc = l->fz.upload(fz)) || (rc = l->forder.upload(std::vector<int32_t>(forder.begin(), forder.end()))) || (rc = l->pair_i.upload(pi)) || (rc = l->pair_j.upload(pj)) ||
             (rc = l->d_rb_left.upload(l->rb_left)) || (rc = l->d_rb_right.upload(l->rb_right)) ||
             (rc = l->d_rg_off.upload(l->rg_off)) || (rc = l->d_rg_idx.upload(l->rg_idx)))
             break;

@@ -66,6 +66,7 @@ struct ScanJob {
     double mins[3], q[3];
     std::vector<int64_t> points;           // active lattice points of the requested sub-range
     DevBuf<double> d_rot;
+    DevBuf<int32_t> d_rot_perm;
     DevBuf<int64_t> d_points, d_frames;
     DevBuf<double> d_E, d_thr, d_cand_s;
     DevBuf<long long> d_cand_f;
@@ -92,6 +93,49 @@ static bool host_clash_and(const mmo_mask *m, double x, double y, double z) {
     return host_bit(m, i0 + j0x + k0xy) && host_bit(m, i1 + j0x + k0xy) && host_bit(m, i1 + j1x + k0xy) &&
            host_bit(m, i0 + j1x + k0xy) && host_bit(m, i0 + j0x + k1xy) && host_bit(m, i1 + j0x + k1xy) &&
            host_bit(m, i1 + j1x + k1xy) && host_bit(m, i0 + j1x + k1xy);
+}
+
+// Visiting order of the rotations: k-d leaves of 32 over the stereographic image of the unit
+// quaternions, so that the 32 poses of a warp are similar rotations (tight per-atom boxes in the
+// direct kernel).  Cached on the content of rot9: lds builds the rotation set once per run.
+static const std::vector<int32_t> &rotation_visit_order(int n_rot, const double *rot9) {
+    static std::vector<int32_t> cached;
+    static uint64_t cached_hash = 0;
+    static int cached_n = -1;
+    uint64_t h = 1469598103934665603ull;
+    const uint64_t *w = (const uint64_t *)rot9;
+    for (size_t k = 0; k < (size_t)n_rot * 9; k++) { h ^= w[k]; h *= 1099511628211ull; }
+    if (cached_n == n_rot && cached_hash == h) return cached;
+    std::vector<double> gx(n_rot), gy(n_rot), gz(n_rot);
+    for (int r = 0; r < n_rot; r++) {
+        const double *m = rot9 + 9 * (size_t)r;
+        double q[4];     // (w, x, y, z), numerically safe branch on the largest diagonal term
+        double tr = m[0] + m[4] + m[8];
+        if (tr > 0.0) {
+            double s = sqrt(tr + 1.0) * 2.0;
+            q[0] = 0.25 * s; q[1] = (m[7] - m[5]) / s; q[2] = (m[2] - m[6]) / s; q[3] = (m[3] - m[1]) / s;
+        } else if (m[0] > m[4] && m[0] > m[8]) {
+            double s = sqrt(1.0 + m[0] - m[4] - m[8]) * 2.0;
+            q[0] = (m[7] - m[5]) / s; q[1] = 0.25 * s; q[2] = (m[1] + m[3]) / s; q[3] = (m[2] + m[6]) / s;
+        } else if (m[4] > m[8]) {
+            double s = sqrt(1.0 + m[4] - m[0] - m[8]) * 2.0;
+            q[0] = (m[2] - m[6]) / s; q[1] = (m[1] + m[3]) / s; q[2] = 0.25 * s; q[3] = (m[5] + m[7]) / s;
+        } else {
+            double s = sqrt(1.0 + m[8] - m[0] - m[4]) * 2.0;
+            q[0] = (m[3] - m[1]) / s; q[1] = (m[2] + m[6]) / s; q[2] = (m[5] + m[7]) / s; q[3] = 0.25 * s;
+        }
+        if (q[0] < 0.0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+        double den = 1.0 + q[0];
+        if (!(den > 1e-12)) den = 1e-12;
+        gx[r] = q[1] / den; gy[r] = q[2] / den; gz[r] = q[3] / den;
+        if (!(gx[r] == gx[r]) || !(gy[r] == gy[r]) || !(gz[r] == gz[r])) { gx[r] = gy[r] = gz[r] = 0.0; }
+    }
+    std::vector<int> order;
+    kd_order(n_rot, gx.data(), gy.data(), gz.data(), 32, order);
+    cached.assign(order.begin(), order.end());
+    cached_hash = h;
+    cached_n = n_rot;
+    return cached;
 }
 
 static int scan_setup(ScanJob &J) {
@@ -132,9 +176,11 @@ static int scan_setup(ScanJob &J) {
         J.points.push_back(p);
     }
     MMO_TRY(J.d_rot.upload(P.rot9, (size_t)P.n_rot * 9));
+    MMO_TRY(J.d_rot_perm.upload(rotation_visit_order(P.n_rot, P.rot9)));
     MMO_TRY(J.d_points.upload(J.points));
     // slab: as many lattice points as fit ~4M candidate poses
     int64_t pts_per_slab = std::max<int64_t>(1, (int64_t)(4 << 20) / std::max(1, P.n_rot));
+    pts_per_slab = std::max<int64_t>(1, std::min<int64_t>(pts_per_slab, (int64_t)J.points.size()));
     J.slab_cap = pts_per_slab * P.n_rot;
     MMO_TRY(J.d_frames.alloc((size_t)J.slab_cap));
     MMO_TRY(J.d_E.alloc((size_t)J.slab_cap));
@@ -169,7 +215,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         const double thr = (P.topk > 0 && (int)J.top.size() >= P.topk) ? J.top.back().s : INFINITY;
         MMO_CUDA(cudaMemsetAsync(J.d_counters.p, 0, 2 * sizeof(unsigned long long), R.stream));
         MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &thr, sizeof(double), cudaMemcpyHostToDevice, R.stream));
-        MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, n_cand, J.d_frames.p, J.d_counters.p));
+        MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, J.d_rot_perm.p, n_cand, J.d_frames.p, J.d_counters.p));
         unsigned long long n_surv = 0;
         MMO_CUDA(cudaMemcpyAsync(&n_surv, J.d_counters.p, sizeof n_surv, cudaMemcpyDeviceToHost, R.stream));
         MMO_CUDA(cudaStreamSynchronize(R.stream));

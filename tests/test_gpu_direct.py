@@ -71,7 +71,8 @@ def test_empty_batch_and_ragged_sizes(gpu, orc):
         la = rng.choice([1, 6, 7, 8, 16, 17], L).astype(np.int32)
         rec = gpu.Receptor.from_mol(rec_m)
         lig = gpu.Ligand(lx, ly, lz, lq, la)
-        X, Y, Z = lx[None, :] + rng.uniform(-1, 1, (5, 1)), ly[None, :] + 0.0, lz[None, :] + 0.0
+        X = lx[None, :] + rng.uniform(-1, 1, (5, 1))
+        Y, Z = np.tile(ly, (5, 1)), np.tile(lz, (5, 1))
         want = orc.ene_inter(rec_m, lq, la, X, Y, Z, shifted=True)
         assert np.array_equal(gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP64, X, Y, Z), want)
         assert tol_ok(gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP32, X, Y, Z), want).all()

@@ -98,6 +98,8 @@ def test_vdw_mask_and_clash_bit_identical(gpu, orc, c2, c2_roi_rec):
     assert 0 < np.unpackbits(mask.bits).sum() < 0.2 * mask.bits.size * 8
     lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
     R, t = workloads.random_poses_in_sphere(400, c2["roi"][:3], 9.0, seed=24)
+    t[::3] += np.array([0.0, 0.0, 34.0])           # a third of the poses out in the solvent: no clash
+    t[1::3] += np.array([0.0, 0.0, 24.0])          # and a third grazing the surface
     got = gpu.Mol.protein_ligand_clash(mask, lig, R, t)
     X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
     ref = np.array([orc.protein_ligand_clash(workloads.GRID_STEP, dims, want, X[p], Y[p], Z[p]) for p in range(len(R))])

@@ -20,22 +20,31 @@ def setup(gpu, orc, c2, c2_roi_rec):
 
 
 @pytest.mark.parametrize("use_mask", [False, True])
-def test_scan_fp64_reproduces_argmin_and_topk_order(gpu, orc, c2, c2_roi_rec, setup, use_mask):
-    rec, lig, mask, dims, e_intra = setup
+def test_scan_fp64_reproduces_argmin_and_topk_order(gpu, orc, c2, setup, use_mask):
+    _, lig, mask, dims, e_intra = setup
     rot = gpu.SO3.rotations(48)
-    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 4.0)
+    # an ROI straddling the protein surface (the crystallographic pocket is buried: there every pose
+    # of a 48-atom ligand trips the bitmask prefilter), coarse lattice: pocket, surface, solvent points
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2] + 26.0, 10.0)
+    rec_m = c2["rec"]                       # whole receptor: the carved one is centred on the real ROI
+    rec = gpu.Receptor.from_mol(rec_m)
     kw = dict(vdw_mask=mask.bits, m_step=workloads.GRID_STEP, m_dims=dims) if use_mask else {}
-    want = orc.scan(c2_roi_rec, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 2.0, rot, 25, scorer=0,
+    want = orc.scan(rec_m, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 4.0, rot, 25, scorer=0,
                     e_intra_const=e_intra, **kw)
-    got = gpu.Lds.exhaustive_rigid_ligand_docking(25, roi, 2.0, rot, lig, rec=rec, vdw_mask=mask if use_mask else None,
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(25, roi, 4.0, rot, lig, rec=rec, vdw_mask=mask if use_mask else None,
                                                   e_intra_const=e_intra, prec=gpu.PREC_FP64)
-    assert got["lattice_dims"] == want["lattice_dims"] == (5, 5, 5)
+    assert got["lattice_dims"] == want["lattice_dims"]
     assert got["n_candidates"] == want["n_candidates"] and got["n_scored"] == want["n_scored"]
     assert got["best_frame"] == want["best_frame"] and got["best_score"] == want["best_score"]
     assert np.array_equal(got["top_frames"], want["top_frames"])
     assert np.array_equal(got["top_scores"], want["top_scores"])
     if use_mask:
         assert 0 < want["n_scored"] < want["n_candidates"]
+        # same scan, fp32 pair path: identical survivors, energies within tolerance
+        got32 = gpu.Lds.exhaustive_rigid_ligand_docking(25, roi, 4.0, rot, lig, rec=rec, vdw_mask=mask,
+                                                        e_intra_const=e_intra, prec=gpu.PREC_FP32)
+        assert got32["n_scored"] == want["n_scored"]
+        assert tol_ok(got32["top_scores"], want["top_scores"]).all()
 
 
 def test_scan_fp32_within_tolerance_and_same_winner(gpu, orc, c2, c2_roi_rec, setup):
