@@ -229,6 +229,40 @@ int mmo_scan_destroy(mmo_scan_job *job);
 int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64_t *frames,
                    const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n);
 
+/* ---------------------------------------------------------------- Monte-Carlo chains ------- */
+/* Lds.simulate_lig frame loop (src/lds.ml:882-995) for n_chains independent chains in one launch:
+ * alternating rigid-body (Move.rand_rot / rand_trans, src/move.ml:20-54) and conformer moves
+ * (Mol.tweak_rbond / flip_rbond / rotate_bond, src/mol.ml:610-647), interpolated E_inter
+ * (src/mol.ml:1012-1020), E_intra = Mol.ene_intra_UFFNB_brute when intra_nb, Metropolis at
+ * beta = 1/(kB*T) (lds.ml:66-75, 931-934), acceptance windows (src/SW.ml) and adaptive step sizes
+ * (lds.ml:586-621).  The reference's behaviours D1-D6/D14 of SURVEY Appendix D are mirrored
+ * (in particular: nothing is accepted or rejected unless hard_roi is set).  The random stream and
+ * sin/cos/exp are those of include/mmo_detmath.h, not OCaml's: chain c consumes
+ * mmo_rng_uniform(seeds[c], 0, 1, 2, ...). */
+typedef struct {
+    double roi_c[3], roi_r;      /* ROI.sphere in simulation-box coordinates */
+    double temperature_K;        /* -T, default 293.15 */
+    int32_t n_steps;             /* -steps */
+    int32_t tweak_rbonds;        /* 0 = --rigid-ligand */
+    int32_t hard_roi;            /* --hard-ROI */
+    int32_t no_flip;             /* --no-flip */
+    int32_t intra_nb;            /* --intra-NB (0 = --no-E-intra) */
+} mmo_mc_params;
+typedef struct {
+    double best_E, prev_E;
+    double best_rot[9], best_pos[3];
+    double max_rot, max_trans;   /* adapted step sizes at the end of the run */
+    int64_t n_accept_rigid, n_reject_rigid, n_accept_conf, n_reject_conf, n_ooroi, n_ezero;
+    int32_t too_long;            /* Mol.Too_long was raised: the run stopped at frames_done */
+    int32_t frames_done;
+} mmo_mc_result;
+/* start_rot9 / start_pos3: per chain (lds.ml:2034-2047); best_xyz: n_chains x 3 x L (x.. y.. z..),
+ * may be NULL; trace_chain0: n_steps x {curr_E, E_inter, E_intra, accepted(-1 = no test)}, may be NULL */
+int mmo_mc_run(const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
+               int64_t n_chains, const uint64_t *seeds, const double *start_rot9,
+               const double *start_pos3, mmo_mc_result *results, double *best_xyz,
+               double *trace_chain0);
+
 #ifdef __cplusplus
 }
 #endif

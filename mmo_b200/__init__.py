@@ -56,6 +56,20 @@ class ScanResult(C.Structure):
                 ("pairs_evaluated", C.c_int64), ("pairs_inside", C.c_int64), ("device_ms", C.c_float)]
 
 
+class McParams(C.Structure):
+    _fields_ = [("roi_c", C.c_double * 3), ("roi_r", C.c_double), ("temperature_K", C.c_double),
+                ("n_steps", C.c_int32), ("tweak_rbonds", C.c_int32), ("hard_roi", C.c_int32),
+                ("no_flip", C.c_int32), ("intra_nb", C.c_int32)]
+
+
+class McResult(C.Structure):
+    _fields_ = [("best_E", C.c_double), ("prev_E", C.c_double), ("best_rot", C.c_double * 9),
+                ("best_pos", C.c_double * 3), ("max_rot", C.c_double), ("max_trans", C.c_double),
+                ("n_accept_rigid", C.c_int64), ("n_reject_rigid", C.c_int64), ("n_accept_conf", C.c_int64),
+                ("n_reject_conf", C.c_int64), ("n_ooroi", C.c_int64), ("n_ezero", C.c_int64),
+                ("too_long", C.c_int32), ("frames_done", C.c_int32)]
+
+
 def lib():
     """The loaded C-ABI library; raises (never falls back) when it is missing."""
     global _lib
@@ -411,6 +425,35 @@ class Lds:
                     best_frame=R.best_frame, best_pos=tuple(R.best_pos), best_rot_i=R.best_rot_i,
                     n_candidates=R.n_candidates, n_scored=R.n_scored, lattice_dims=tuple(R.lattice_dims),
                     pairs_evaluated=R.pairs_evaluated, pairs_inside=R.pairs_inside, device_ms=R.device_ms)
+
+
+    @staticmethod
+    def simulate_lig(grid, lig, roi, n_steps, seeds, start_rot9, start_pos3, tweak_rbonds=True, hard_roi=True,
+                     no_flip=False, intra_nb=True, temperature_K=293.15, want_xyz=False, want_trace=False):
+        """src/lds.ml:741-1000 frame loop for len(seeds) independent chains in one launch."""
+        _need_init()
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        n = len(seeds)
+        rot = np.ascontiguousarray(start_rot9, np.float64).reshape(n, 9)
+        pos = np.ascontiguousarray(start_pos3, np.float64).reshape(n, 3)
+        P = McParams()
+        P.roi_c = (C.c_double * 3)(*roi[:3]); P.roi_r = roi[3]; P.temperature_K = temperature_K
+        P.n_steps = n_steps; P.tweak_rbonds = int(tweak_rbonds); P.hard_roi = int(hard_roi)
+        P.no_flip = int(no_flip); P.intra_nb = int(intra_nb)
+        res = (McResult * n)()
+        xyz = np.empty((n, 3, lig.n)) if want_xyz else None
+        trace = np.empty((n_steps, 4)) if want_trace else None
+        _ck(lib().mmo_mc_run(grid.h, lig.h, C.byref(P), C.c_int64(n), seeds.ctypes.data_as(C.POINTER(C.c_uint64)),
+                             rot.ctypes.data_as(_dp), pos.ctypes.data_as(_dp), res,
+                             xyz.ctypes.data_as(_dp) if want_xyz else C.cast(None, _dp),
+                             trace.ctypes.data_as(_dp) if want_trace else C.cast(None, _dp)))
+        out = []
+        for r in res:
+            out.append(dict(best_E=r.best_E, prev_E=r.prev_E, best_rot=np.array(r.best_rot), best_pos=np.array(r.best_pos),
+                            max_rot=r.max_rot, max_trans=r.max_trans, n_accept_rigid=r.n_accept_rigid,
+                            n_reject_rigid=r.n_reject_rigid, n_accept_conf=r.n_accept_conf, n_reject_conf=r.n_reject_conf,
+                            n_ooroi=r.n_ooroi, n_ezero=r.n_ezero, too_long=r.too_long, frames_done=r.frames_done))
+        return out, xyz, trace
 
 
 class SO3:

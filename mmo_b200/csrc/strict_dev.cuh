@@ -1,0 +1,62 @@
+// strict_dev.cuh -- device functions of the reference's double arithmetic, shared by the strict
+// translation units (all compiled with -fmad=false).
+#pragma once
+#include "common.cuh"
+
+namespace mmo {
+
+// ---- scalars: FF.ml:5-20, math.ml:58-62 ------------------------------------------------------
+__device__ __forceinline__ double d_sq(double x) { return x * x; }
+__device__ __forceinline__ double d_pow6(double x) { double y = x * x; return (y * y) * y; }
+__device__ __forceinline__ double d_shift(double d) { return (d < 12.0) ? d_sq(1.0 - d_sq(d / 12.0)) : 0.0; }
+__device__ __forceinline__ double d_nzd(double x) { return (x < 0.01) ? 0.01 : x; }
+// V3.dist2 u v (V3.ml:23-28)
+__device__ __forceinline__ double d_dist2(double ux, double uy, double uz, double vx, double vy, double vz) {
+    double dx = ux - vx, dy = uy - vy, dz = uz - vz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// ---- trilinear interpolation (G3D.ml:97-157) ---------------------------------------------------
+struct GridGeom {
+    double inv;          // grid.one_div_step
+    double q[3];         // node i at i*q[d]
+    int x_dim, xy_dim;
+    int dims[3];
+    size_t nvox;
+};
+__device__ __forceinline__ double d_trilin(const GridGeom &g, const float *__restrict__ arr,
+                                           double px, double py, double pz) {
+    const int i0 = (int)(px * g.inv), j0 = (int)(py * g.inv), k0 = (int)(pz * g.inv);
+    const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    // the reference reads unchecked (undefined outside the grid); here an outside voxel contributes 0.0
+    if (i0 < 0 || j0 < 0 || k0 < 0 || i1 >= g.dims[0] || j1 >= g.dims[1] || k1 >= g.dims[2]) return 0.0;
+    const int j0x = j0 * g.x_dim, j1x = j1 * g.x_dim, k0xy = k0 * g.xy_dim, k1xy = k1 * g.xy_dim;
+    const double lx = (double)i0 * g.q[0], ly = (double)j0 * g.q[1], lz = (double)k0 * g.q[2];
+    const double wlx = (px - lx) * g.inv, wly = (py - ly) * g.inv, wlz = (pz - lz) * g.inv;
+    const double whx = 1.0 - wlx, why = 1.0 - wly, whz = 1.0 - wlz;
+    return ((double)__ldg(arr + (i0 + j0x + k0xy)) * (whx * why * whz) +
+            (double)__ldg(arr + (i1 + j0x + k0xy)) * (wlx * why * whz) +
+            (double)__ldg(arr + (i1 + j1x + k0xy)) * (wlx * wly * whz) +
+            (double)__ldg(arr + (i0 + j1x + k0xy)) * (whx * wly * whz) +
+            (double)__ldg(arr + (i0 + j0x + k1xy)) * (whx * why * wlz) +
+            (double)__ldg(arr + (i1 + j0x + k1xy)) * (wlx * why * wlz) +
+            (double)__ldg(arr + (i1 + j1x + k1xy)) * (wlx * wly * wlz) +
+            (double)__ldg(arr + (i0 + j1x + k1xy)) * (whx * wly * wlz));
+}
+
+static inline GridGeom geom_of(const mmo_grid *g) {
+    GridGeom G;
+    G.inv = 1.0 / g->step;                  // grid.ml:41
+    for (int d = 0; d < 3; d++) {
+        int np = g->dims[d] - 1;
+        G.q[d] = np > 0 ? (g->step * (double)np) / (double)np : 0.0;    // grid.ml:49-51
+    }
+    G.x_dim = g->dims[0];
+    for (int d = 0; d < 3; d++) G.dims[d] = g->dims[d];
+    G.xy_dim = g->dims[0] * g->dims[1];
+    G.nvox = g->nvox;
+    return G;
+}
+
+
+}  // namespace mmo

@@ -11,6 +11,7 @@
 //   trilin   : G3D.trilin, Mol.ene_inter_UFF_interp              src/G3D.ml:97-157, src/mol.ml:1012-1020
 #include "common.cuh"
 #include "pose.cuh"
+#include "strict_dev.cuh"
 #include <math.h>
 
 namespace mmo {
@@ -37,17 +38,6 @@ static int ensure_tables() {
     MMO_CUDA(cudaMemcpyToSymbol(c_dij, hd, sizeof hd));
     g_tables_ready = true;
     return MMO_OK;
-}
-
-// ---- scalars: FF.ml:5-20, math.ml:58-62 ------------------------------------------------------
-__device__ __forceinline__ double d_sq(double x) { return x * x; }
-__device__ __forceinline__ double d_pow6(double x) { double y = x * x; return (y * y) * y; }
-__device__ __forceinline__ double d_shift(double d) { return (d < 12.0) ? d_sq(1.0 - d_sq(d / 12.0)) : 0.0; }
-__device__ __forceinline__ double d_nzd(double x) { return (x < 0.01) ? 0.01 : x; }
-// V3.dist2 u v (V3.ml:23-28)
-__device__ __forceinline__ double d_dist2(double ux, double uy, double uz, double vx, double vy, double vz) {
-    double dx = ux - vx, dy = uy - vy, dz = uz - vz;
-    return dx * dx + dy * dy + dz * dz;
 }
 
 // coordinates of one pose into shared memory, laid out [coord][atom][thread]
@@ -262,31 +252,6 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
     }
 }
 
-// ---- trilinear interpolation (G3D.ml:97-157) ---------------------------------------------------
-struct GridGeom {
-    double inv;          // grid.one_div_step
-    double q[3];         // node i at i*q[d]
-    int x_dim, xy_dim;
-    size_t nvox;
-};
-__device__ __forceinline__ double d_trilin(const GridGeom &g, const float *__restrict__ arr,
-                                           double px, double py, double pz) {
-    const int i0 = (int)(px * g.inv), j0 = (int)(py * g.inv), k0 = (int)(pz * g.inv);
-    const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
-    const int j0x = j0 * g.x_dim, j1x = j1 * g.x_dim, k0xy = k0 * g.xy_dim, k1xy = k1 * g.xy_dim;
-    const double lx = (double)i0 * g.q[0], ly = (double)j0 * g.q[1], lz = (double)k0 * g.q[2];
-    const double wlx = (px - lx) * g.inv, wly = (py - ly) * g.inv, wlz = (pz - lz) * g.inv;
-    const double whx = 1.0 - wlx, why = 1.0 - wly, whz = 1.0 - wlz;
-    return ((double)__ldg(arr + (i0 + j0x + k0xy)) * (whx * why * whz) +
-            (double)__ldg(arr + (i1 + j0x + k0xy)) * (wlx * why * whz) +
-            (double)__ldg(arr + (i1 + j1x + k0xy)) * (wlx * wly * whz) +
-            (double)__ldg(arr + (i0 + j1x + k0xy)) * (whx * wly * whz) +
-            (double)__ldg(arr + (i0 + j0x + k1xy)) * (whx * why * wlz) +
-            (double)__ldg(arr + (i1 + j0x + k1xy)) * (wlx * why * wlz) +
-            (double)__ldg(arr + (i1 + j1x + k1xy)) * (wlx * wly * wlz) +
-            (double)__ldg(arr + (i0 + j1x + k1xy)) * (whx * wly * wlz));
-}
-
 __global__ void strict_trilin_kernel(GridGeom g, const float *__restrict__ arr, int64_t n,
                                      const double *__restrict__ xs, const double *__restrict__ ys,
                                      const double *__restrict__ zs, double *__restrict__ out) {
@@ -331,19 +296,6 @@ static int pick_threads(int L, size_t extra_bytes, size_t *smem) {
         if (b <= 100 * 1024 || t == 32) { *smem = b; return t; }
     }
     return 32;
-}
-
-static GridGeom geom_of(const mmo_grid *g) {
-    GridGeom G;
-    G.inv = 1.0 / g->step;                  // grid.ml:41
-    for (int d = 0; d < 3; d++) {
-        int np = g->dims[d] - 1;
-        G.q[d] = np > 0 ? (g->step * (double)np) / (double)np : 0.0;    // grid.ml:49-51
-    }
-    G.x_dim = g->dims[0];
-    G.xy_dim = g->dims[0] * g->dims[1];
-    G.nvox = g->nvox;
-    return G;
 }
 
 int launch_direct_fp64(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,

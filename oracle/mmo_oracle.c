@@ -218,6 +218,10 @@ double orc_trilin(double step, const int dims[3], const float *arr, double px, d
     int x_dim = dims[0], xy_dim = dims[0] * dims[1];
     int i0 = (int)(px * inv), j0 = (int)(py * inv), k0 = (int)(pz * inv);
     int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    /* The reference reads the Bigarray unchecked (G3D.ml:144-151): outside the grid is undefined
+     * behaviour there, prevented by the 36 A margin (lds.ml:1832).  Here, and identically in the CUDA
+     * kernels, a voxel outside the grid contributes 0.0 (the value of an unmasked voxel). */
+    if (i0 < 0 || j0 < 0 || k0 < 0 || i1 >= dims[0] || j1 >= dims[1] || k1 >= dims[2]) return 0.0;
     int j0x = j0 * x_dim, j1x = j1 * x_dim, k0xy = k0 * xy_dim, k1xy = k1 * xy_dim;
     double lx = orc_grid_node(step, dims[0], i0);
     double ly = orc_grid_node(step, dims[1], j0);

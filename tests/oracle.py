@@ -330,3 +330,59 @@ def scan(rec, lig, cx, cy, cz, roi, trans_step, rot9, topk, scorer=0, e_intra_co
     return dict(top_scores=ts[:R.n_top].copy(), top_frames=tf[:R.n_top].copy(), best_score=R.best_score,
                 best_frame=R.best_frame, n_scored=R.n_scored, n_candidates=R.n_candidates,
                 lattice_dims=tuple(R.lattice_dims))
+
+
+# ---- Monte-Carlo chain ---------------------------------------------------------------------------------
+class McArgs(C.Structure):
+    _fields_ = [("L", C.c_int), ("lx", _dp), ("ly", _dp), ("lz", _dp), ("lq", _dp), ("lanum", _ip), ("ltyp", _ip),
+                ("dists", _ip),
+                ("n_rbonds", C.c_int), ("rb_left", _ip), ("rb_right", _ip), ("rg_off", _ip), ("rg_idx", _ip),
+                ("scorer", C.c_int),
+                ("P", C.c_int), ("px", _dp), ("py", _dp), ("pz", _dp), ("pq", _dp), ("panum", _ip),
+                ("g_step", C.c_double), ("g_dims", C.c_int * 3), ("maps", _fp),
+                ("roi_c", C.c_double * 3), ("roi_r", C.c_double),
+                ("tweak_rbonds", C.c_int), ("hard_roi", C.c_int), ("no_flip", C.c_int), ("intra_nb", C.c_int),
+                ("beta", C.c_double), ("n_steps", C.c_int), ("seed", C.c_uint64),
+                ("rot0", C.c_double * 9), ("pos0", C.c_double * 3)]
+
+
+class McResult(C.Structure):
+    _fields_ = [("best_E", C.c_double), ("prev_E", C.c_double), ("best_rot", C.c_double * 9), ("best_pos", C.c_double * 3),
+                ("n_accept_rigid", C.c_int64), ("n_reject_rigid", C.c_int64), ("n_accept_conf", C.c_int64),
+                ("n_reject_conf", C.c_int64), ("n_ooroi", C.c_int64), ("n_ezero", C.c_int64),
+                ("too_long", C.c_int), ("frames_done", C.c_int), ("max_rot", C.c_double), ("max_trans", C.c_double)]
+
+
+def mc_run(lig, cx, cy, cz, roi, n_steps, seed, rot0, pos0, maps=None, g_step=0.0, g_dims=(0, 0, 0), rec=None,
+           tweak_rbonds=True, hard_roi=True, no_flip=False, intra_nb=True, temperature_K=293.15):
+    keep = []
+
+    def K(x):
+        keep.append(x)
+        return x[1]
+    A = McArgs()
+    A.L = lig.n
+    A.lx, A.ly, A.lz, A.lq = K(d(cx)), K(d(cy)), K(d(cz)), K(d(lig.q))
+    A.lanum, A.ltyp, A.dists = K(i32(lig.anum)), K(i32(lig.typ)), K(i32(lig.dists))
+    off, idx = lig.rgroup_csr()
+    A.n_rbonds = lig.n_rbonds
+    A.rb_left, A.rb_right, A.rg_off, A.rg_idx = K(i32(lig.rb_left)), K(i32(lig.rb_right)), K(i32(off)), K(i32(idx))
+    if maps is not None:
+        A.scorer = 2
+        maps = np.ascontiguousarray(maps, np.float32); keep.append(maps)
+        A.maps = maps.ctypes.data_as(_fp); A.g_step = g_step; A.g_dims = (C.c_int * 3)(*g_dims)
+    else:
+        A.scorer = 0
+        A.P = rec.n
+        A.px, A.py, A.pz, A.pq, A.panum = K(d(rec.xs)), K(d(rec.ys)), K(d(rec.zs)), K(d(rec.q)), K(i32(rec.anum))
+    A.roi_c = (C.c_double * 3)(*roi[:3]); A.roi_r = roi[3]
+    A.tweak_rbonds, A.hard_roi, A.no_flip, A.intra_nb = int(tweak_rbonds), int(hard_roi), int(no_flip), int(intra_nb)
+    A.beta = lib().orc_beta(C.c_double(temperature_K))
+    A.n_steps = n_steps; A.seed = int(seed)
+    A.rot0 = (C.c_double * 9)(*np.asarray(rot0, np.float64).reshape(9)); A.pos0 = (C.c_double * 3)(*pos0)
+    R = McResult()
+    xyz = np.empty((3, lig.n)); trace = np.empty((n_steps, 4))
+    lib().orc_mc_run(C.byref(A), C.byref(R), xyz.ctypes.data_as(_dp), trace.ctypes.data_as(_dp))
+    res = {f: getattr(R, f) for f, _ in McResult._fields_ if f not in ("best_rot", "best_pos")}
+    res["best_rot"] = np.array(R.best_rot); res["best_pos"] = np.array(R.best_pos)
+    return res, xyz, trace[:R.frames_done]

@@ -1,0 +1,106 @@
+"""Monte-Carlo chains (lds.ml:741-1000): oracle behaviours on the CPU, and CUDA chains against the
+oracle frame by frame.  Both sides use include/mmo_detmath.h for the random stream and sin/cos/exp,
+so trajectories -- not just distributions -- must agree bit for bit."""
+import numpy as np
+import pytest
+
+from mmo_b200 import pqrs, workloads
+
+
+def _pocket_grid(orc, c2, rec_m, step=1.0, reach=21.0):
+    c = np.array(c2["roi"][:3])
+    dims = orc.grid_from_box(step, *(c + reach + 2.0))
+    mask = orc.bitmask_sphere(step, dims, c, reach)
+    ta, tq = pqrs.assign_ff_types([c2["lig"]])
+    return dims, mask, ta, tq
+
+
+@pytest.fixture(scope="module")
+def mc_setup(orc, c2, c2_roi_rec):
+    dims, mask, ta, tq = _pocket_grid(orc, c2, c2_roi_rec)
+    maps = orc.grid_build(c2_roi_rec, 1.0, dims, ta, tq, mask=mask)
+    return dims, mask, ta, tq, maps
+
+
+def test_oracle_chain_mirrors_the_dangling_else(orc, c2, mc_setup):
+    dims, mask, ta, tq, maps = mc_setup
+    cx, cy, cz = c2["centered"]
+    rot0 = np.eye(3).reshape(9)
+    # without --hard-ROI nothing is ever accepted or rejected
+    r, xyz, tr = orc.mc_run(c2["lig"], cx, cy, cz, c2["roi"], 300, 1234, rot0, c2["start_pos"], maps=maps, g_step=1.0,
+                            g_dims=dims, hard_roi=False)
+    assert r["n_accept_rigid"] + r["n_reject_rigid"] + r["n_accept_conf"] + r["n_reject_conf"] == 0
+    assert (tr[:, 3] == -1).all() and r["frames_done"] == 300
+    # with --hard-ROI the loop is a Metropolis chain
+    r, xyz, tr = orc.mc_run(c2["lig"], cx, cy, cz, c2["roi"], 2000, 1234, rot0, c2["start_pos"], maps=maps, g_step=1.0,
+                            g_dims=dims, hard_roi=True)
+    tested = r["n_accept_rigid"] + r["n_reject_rigid"] + r["n_accept_conf"] + r["n_reject_conf"]
+    assert tested == r["frames_done"] - r["n_ooroi"] - r["n_ezero"]
+    assert 0 < r["n_accept_rigid"] and 0 < r["n_reject_rigid"]
+    assert r["best_E"] <= tr[0, 0] + 1e-9 or r["n_ooroi"] + r["n_ezero"] > 0
+    # D3: best is the minimum over every tested trial since the last reset
+    if r["n_ooroi"] + r["n_ezero"] == 0:
+        start_E = orc.ene_inter_interp(1.0, dims, maps, c2["lig"].typ, *[np.atleast_2d(v) for v in xyz])  # noqa: F841
+        assert r["best_E"] == min(tr[tr[:, 3] >= 0, 0].min(), r["best_E"])
+
+
+def test_oracle_rigid_ligand_keeps_intra_constant(orc, c2, mc_setup):
+    dims, mask, ta, tq, maps = mc_setup
+    cx, cy, cz = c2["centered"]
+    r, xyz, tr = orc.mc_run(c2["lig"], cx, cy, cz, c2["roi"], 200, 7, np.eye(3).reshape(9), c2["start_pos"], maps=maps,
+                            g_step=1.0, g_dims=dims, tweak_rbonds=False)
+    e0 = orc.ene_intra(c2["lig"], cx, cy, cz)[0]
+    assert (tr[:, 2] == e0).all()        # lds.ml:706-712: const_ene_intra of the centred ligand
+
+
+def test_rng_and_detmath_are_platform_independent(orc):
+    import ctypes as C
+    f = orc.lib().orc_rng_uniform
+    assert f(C.c_uint64(1234), C.c_uint64(0)) == 0.73066652454062397
+    assert f(C.c_uint64(1234), C.c_uint64(1)) == 0.59288985801498617
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [dict(), dict(tweak_rbonds=False), dict(no_flip=True, temperature_K=600.0),
+                                   dict(hard_roi=False), dict(intra_nb=False)])
+def test_cuda_chains_match_the_oracle_bit_for_bit(gpu, orc, c2, c2_roi_rec, mc_setup, flags):
+    dims, mask, ta, tq, maps = mc_setup
+    rec = gpu.Receptor.from_mol(c2_roi_rec)
+    g, gmaps = gpu.Lds.pre_calculate_FF_components_grid(rec, 1.0, dims, ta, tq, mask_bits=mask)
+    assert np.array_equal(gmaps, maps)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    n_steps, seeds = 1200, np.array([1234, 99, 20231017, 5], np.uint64)
+    R, t = workloads.random_poses_in_sphere(len(seeds), c2["roi"][:3], 4.0, seed=31)
+    R[0] = np.eye(3).reshape(9); t[0] = c2["start_pos"]
+    res, xyz, trace = gpu.Lds.simulate_lig(g, lig, c2["roi"], n_steps, seeds, R, t, want_xyz=True, want_trace=True, **flags)
+    for c, seed in enumerate(seeds):
+        want, wxyz, wtr = orc.mc_run(c2["lig"], lig.xs, lig.ys, lig.zs, c2["roi"], n_steps, int(seed), R[c], t[c],
+                                     maps=maps, g_step=1.0, g_dims=dims, **flags)
+        got = res[c]
+        if c == 0:
+            assert np.array_equal(trace[:want["frames_done"]], wtr)
+        for k in ("best_E", "prev_E", "max_rot", "max_trans", "n_accept_rigid", "n_reject_rigid", "n_accept_conf",
+                  "n_reject_conf", "n_ooroi", "n_ezero", "too_long", "frames_done"):
+            assert got[k] == want[k], (c, k, got[k], want[k])
+        assert np.array_equal(got["best_rot"], want["best_rot"]) and np.array_equal(got["best_pos"], want["best_pos"])
+        assert np.array_equal(xyz[c], wxyz)
+
+
+@pytest.mark.gpu
+def test_many_chains_statistics(gpu, orc, c2, c2_roi_rec, mc_setup):
+    """512 chains: every chain is the oracle's chain for its seed (spot-checked), acceptance ratios are
+    pulled towards the 0.45-0.55 target band by the adaptive step sizes (lds.ml:586-600)."""
+    dims, mask, ta, tq, maps = mc_setup
+    g = gpu.G3D.upload(1.0, dims, maps)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    n = 512
+    seeds = np.arange(n, dtype=np.uint64) + 20231017
+    R, t = workloads.random_poses_in_sphere(n, c2["roi"][:3], 3.0, seed=32)
+    res, _, _ = gpu.Lds.simulate_lig(g, lig, c2["roi"], 4000, seeds, R, t)
+    for c in (0, 17, 511):
+        want, _, _ = orc.mc_run(c2["lig"], lig.xs, lig.ys, lig.zs, c2["roi"], 4000, int(seeds[c]), R[c], t[c], maps=maps,
+                                g_step=1.0, g_dims=dims)
+        assert res[c]["best_E"] == want["best_E"] and res[c]["n_accept_rigid"] == want["n_accept_rigid"]
+    ar = np.array([r["n_accept_rigid"] / max(1, r["n_accept_rigid"] + r["n_reject_rigid"]) for r in res])
+    assert 0.2 < np.median(ar) < 0.8
+    assert all(r["frames_done"] == 4000 or r["too_long"] for r in res)
