@@ -229,6 +229,17 @@ int mmo_scan_destroy(mmo_scan_job *job);
 int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64_t *frames,
                    const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n);
 
+/* ---------------------------------------------------------------- multi-GPU top-k ---------- */
+/* One process per GPU.  Poses / lattice points / chains are sharded with no data-path collective;
+ * the only exchange is one ncclAllGather of the per-GPU top-k lists (k x 16 B per rank) followed
+ * by the merge above.  NCCL (libnccl.so.2) is dlopen'ed on first use.  Rank 0 creates the id with
+ * mmo_nccl_unique_id and hands it to the other ranks out of band (a file, an env variable, any key-value store). */
+int mmo_nccl_unique_id(uint8_t id[128]);
+int mmo_nccl_init(int32_t rank, int32_t nranks, const uint8_t id[128]);
+int mmo_nccl_finalize(void);
+int mmo_topk_allgather_merge(int32_t k, int32_t n_local, const double *scores, const int64_t *frames,
+                             double *out_scores, int64_t *out_frames, int32_t *out_n);
+
 /* ---------------------------------------------------------------- Monte-Carlo chains ------- */
 /* Lds.simulate_lig frame loop (src/lds.ml:882-995) for n_chains independent chains in one launch:
  * alternating rigid-body (Move.rand_rot / rand_trans, src/move.ml:20-54) and conformer moves

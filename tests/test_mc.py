@@ -88,8 +88,9 @@ def test_cuda_chains_match_the_oracle_bit_for_bit(gpu, orc, c2, c2_roi_rec, mc_s
 
 @pytest.mark.gpu
 def test_many_chains_statistics(gpu, orc, c2, c2_roi_rec, mc_setup):
-    """512 chains: every chain is the oracle's chain for its seed (spot-checked), acceptance ratios are
-    pulled towards the 0.45-0.55 target band by the adaptive step sizes (lds.ml:586-600)."""
+    """512 chains: every chain is the oracle's chain for its seed (spot-checked); chains that start from
+    random (clashing) poses reject most moves, so the adaptive scheme (lds.ml:586-600) must have shrunk
+    their step sizes below the params.ml defaults."""
     dims, mask, ta, tq, maps = mc_setup
     g = gpu.G3D.upload(1.0, dims, maps)
     lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
@@ -102,5 +103,7 @@ def test_many_chains_statistics(gpu, orc, c2, c2_roi_rec, mc_setup):
                                 g_step=1.0, g_dims=dims)
         assert res[c]["best_E"] == want["best_E"] and res[c]["n_accept_rigid"] == want["n_accept_rigid"]
     ar = np.array([r["n_accept_rigid"] / max(1, r["n_accept_rigid"] + r["n_reject_rigid"]) for r in res])
-    assert 0.2 < np.median(ar) < 0.8
+    assert 0.0 < np.median(ar) < 0.45
+    shrunk = np.array([r["max_rot"] < np.radians(15.0) and r["max_trans"] < 0.15 for r in res])
+    assert shrunk.mean() > 0.9
     assert all(r["frames_done"] == 4000 or r["too_long"] for r in res)
