@@ -159,12 +159,19 @@ def main():
             raise RuntimeError(L.mmo_last_error().decode())
 
     dist = None
+    mmo_b200.init(local_rank)
     if world > 1:
+        # control plane (barrier, max over ranks, hand-out of the NCCL id): torch.distributed/gloo on the host.
+        # data plane: the library's own ncclAllGather of the per-GPU top-k lists (mmo_topk_allgather_merge).
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mmo_b200.init(local_rank)
+        dist.init_process_group("gloo")
+        nid = np.zeros(128, np.uint8)
+        if rank == 0:
+            ck(L.mmo_nccl_unique_id(nid.ctypes.data_as(C.POINTER(C.c_uint8))))
+        tid = torch.from_numpy(nid)
+        dist.broadcast(tid, 0)
+        ck(L.mmo_nccl_init(rank, world, tid.numpy().ctypes.data_as(C.POINTER(C.c_uint8))))
 
     c2, rec_m = setup_workload()
     rec = mmo_b200.Receptor.from_mol(rec_m)
@@ -190,20 +197,23 @@ def main():
     pps = args.points_per_step
     total_steps = args.warmup + args.steps
     # rank r owns a contiguous block of the active points (weak scaling: the same slab size per GPU)
-    block = n_active // world
-    first = rank * block
-    assert total_steps * pps <= block, f"not enough lattice points ({block}) for {total_steps} steps of {pps}"
+    # slabs are dealt round-robin: step s of rank r takes slab s*world + r of the active points, so that
+    # every GPU sweeps a statistically similar part of the pocket (weak scaling, same slab size per GPU)
+    assert (total_steps * world + 2 * world) * pps <= n_active, "not enough lattice points for this many steps"
+
+    def slab_first(s):
+        return (s * world + rank) * pps
 
     def barrier():
         ck(L.mmo_sync())
         if dist is not None:
-            torch.cuda.synchronize()
             dist.barrier()
 
     # ---- pair accounting for the timed slabs (untimed pass of the instrumented kernel build) ------
     statjob = C.c_void_p()
     ck(L.mmo_scan_create(C.byref(P), 1, C.byref(statjob)))
-    ck(L.mmo_scan_run(statjob, first + args.warmup * pps, min(2, args.steps) * pps))
+    for s_ in range(args.warmup, args.warmup + min(2, args.steps)):
+        ck(L.mmo_scan_run(statjob, slab_first(s_), pps))
     SR = ScanResult()
     ck(L.mmo_scan_result_get(statjob, None, None, C.byref(SR)))
     stat_poses = SR.n_scored
@@ -213,7 +223,7 @@ def main():
 
     # ---- device-resident timed region --------------------------------------------------------------
     for s in range(args.warmup):
-        ck(L.mmo_scan_run(job, first + s * pps, pps))
+        ck(L.mmo_scan_run(job, slab_first(s), pps))
     stop, samples = threading.Event(), []
     th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True)
     if rank == 0:
@@ -227,7 +237,7 @@ def main():
         ck(L.mmo_l2_flush())           # between timed iterations, outside the timed events
         ck(L.mmo_sync())
         ck(L.mmo_timer_start())
-        ck(L.mmo_scan_run(job, first + (args.warmup + s) * pps, pps))
+        ck(L.mmo_scan_run(job, slab_first(args.warmup + s), pps))
         ck(L.mmo_timer_stop(C.byref(ms)))
         dev_ms += ms.value
     barrier()
@@ -260,7 +270,7 @@ def main():
     t0 = time.perf_counter()
     e2e_poses = 0
     for s in range(e2e_steps):
-        a0 = first + (args.warmup + s) * pps
+        a0 = slab_first(args.warmup + s)
         P.first_point = act[a0]
         P.n_points = act[a0 + pps - 1] - act[a0] + 1
         ck(L.mmo_scan(C.byref(P), ts.ctypes.data_as(C.POINTER(C.c_double)), tf.ctypes.data_as(C.POINTER(C.c_int64)),
@@ -274,32 +284,29 @@ def main():
     # ---- reduce over ranks -------------------------------------------------------------------------
     top_n = SR.n_top
     if dist is not None:
-        tt = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = tt[0].item(), tt[1].item()
-        cnt = torch.tensor([float(e2e_poses), float(launches)], device="cuda", dtype=torch.float64)
+        cnt = torch.tensor([float(e2e_poses), float(launches)], dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         e2e_poses, launches = int(cnt[0].item()), int(cnt[1].item())
-        # the only collective of the path: all-gather of the per-GPU top-k (k x 16 B per rank) + merge
+        # the only collective of the path: NCCL all-gather of the per-GPU top-k (k x 16 B per rank) + merge
         ck(L.mmo_scan_result_get(job, ts.ctypes.data_as(C.POINTER(C.c_double)),
                                  tf.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(SR)))
-        mine_s = torch.full((TOPK,), float("inf"), device="cuda", dtype=torch.float64)
-        mine_f = torch.zeros((TOPK,), device="cuda", dtype=torch.int64)
-        mine_s[:SR.n_top] = torch.from_numpy(ts[:SR.n_top]).cuda()
-        mine_f[:SR.n_top] = torch.from_numpy(tf[:SR.n_top]).cuda()
-        all_s = torch.empty((world, TOPK), device="cuda", dtype=torch.float64)
-        all_f = torch.empty((world, TOPK), device="cuda", dtype=torch.int64)
-        ncnt = torch.tensor([SR.n_top], device="cuda", dtype=torch.int32)
-        all_n = torch.empty((world,), device="cuda", dtype=torch.int32)
-        dist.all_gather_into_tensor(all_s, mine_s)
-        dist.all_gather_into_tensor(all_f, mine_f)
-        dist.all_gather_into_tensor(all_n, ncnt)
-        S = all_s.cpu().numpy(); F = all_f.cpu().numpy(); Nn = all_n.cpu().numpy().astype(np.int32)
+        ms_s, ms_f = np.empty(TOPK), np.empty(TOPK, np.int64)
         out_n = C.c_int32()
-        ck(L.mmo_topk_merge(world, TOPK, S.ctypes.data_as(C.POINTER(C.c_double)), F.ctypes.data_as(C.POINTER(C.c_int64)),
-                            Nn.ctypes.data_as(C.POINTER(C.c_int32)), ts.ctypes.data_as(C.POINTER(C.c_double)),
-                            tf.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(out_n)))
+        t_ag = time.perf_counter()
+        ck(L.mmo_topk_allgather_merge(TOPK, SR.n_top, ts.ctypes.data_as(C.POINTER(C.c_double)),
+                                      tf.ctypes.data_as(C.POINTER(C.c_int64)), ms_s.ctypes.data_as(C.POINTER(C.c_double)),
+                                      ms_f.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(out_n)))
+        t_ag = time.perf_counter() - t_ag
         top_n = out_n.value
+        best = torch.tensor([SR.best_score, float(SR.best_frame)], dtype=torch.float64)
+        allb = [torch.empty_like(best) for _ in range(world)]
+        dist.all_gather(allb, best)
+        gb = min((float(b[0]), int(b[1])) for b in allb if int(b[1]) >= 0)
+        SR.best_score, SR.best_frame = gb[0], gb[1]
+        assert top_n == 0 or ms_s[0] == gb[0], "merged top-1 disagrees with the global argmin"
 
     if rank == 0:
         th.join(timeout=2)
@@ -320,7 +327,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "receptor_atoms": rec_m.n, "ligand_atoms": c2["lig"].n,
                        "poses_per_step_per_gpu": poses_per_step, "timing": "L2 flushed (256 MB memset) between timed steps",
-                       "parallelism": f"lattice points sharded over {world} GPU(s), top-k merged by one all-gather"},
+                       "parallelism": f"lattice-point slabs dealt round-robin to {world} GPU(s), no data-path collective, top-k merged by one NCCL all-gather"},
             "pair_interactions_per_s": pairs_nominal,
             "pairs_evaluated_per_pose": pairs_eval_per_pose, "pairs_inside_cutoff_per_pose": pairs_in_per_pose,
             "gpu_launches": launches,
@@ -334,9 +341,10 @@ def main():
                          "hard_fix_ms_per_launch": fix_ms.value / max(1, kn.value),
                          "flops_per_launch": flops_per_launch},
             "clocks": summarise_clocks(samples),
-            "result": {"best_score": SR.best_score, "best_frame": SR.best_frame, "topk_merged": top_n},
+            "result": {"best_score": SR.best_score, "best_frame": SR.best_frame, "topk_merged": top_n,
+                       "topk_allgather_ms": (1e3 * t_ag if dist is not None else None)},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             pts = lattice_points(c2["roi"], TRANS_STEP)
             nthreads = oracle.num_threads()
             dt = cpu_sample(c2, rec_m, rot, pts, 32 * nthreads, nthreads)
@@ -349,6 +357,7 @@ def main():
     ck(L.mmo_scan_destroy(job))
     if dist is not None:
         dist.barrier()
+        ck(L.mmo_nccl_finalize())
         dist.destroy_process_group()
 
 

@@ -9,7 +9,7 @@
 // One warp per chain.  Scalars (rotation, position, energies, RNG counter) are kept redundantly in
 // every lane -- all lanes execute the same IEEE operations, so they stay identical -- while atoms,
 // pair terms and trilinear look-ups are spread over the lanes.  Sums are then accumulated in the
-// reference's order by shuffling the per-lane terms back one at a time, which keeps every energy
+// reference's order from a shared-memory staging row read as broadcasts, which keeps every energy
 // bit-identical to the sequential loops of the reference (and of oracle/mmo_oracle_mc.c).
 // sin/cos/exp and the random stream come from include/mmo_detmath.h on both sides (see there).
 // Compiled with -fmad=false.  Reference quirks D1-D6, D14 of SURVEY Appendix D are mirrored.
@@ -104,38 +104,49 @@ __device__ __forceinline__ double favg_smem(const double *a, int n) {
     return sum / (double)n;
 }
 
-// Mol.ene_intra_UFFNB_brute (mol.ml:881-903): terms spread over lanes, summed in the (i<j) order
-__device__ double intra_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane) {
+// Mol.ene_intra_UFFNB_brute (mol.ml:881-903): the pair terms are computed 32 at a time, one per lane,
+// parked in shared memory and then added up in the reference's (i<j) order by every lane alike
+// (broadcast reads: one LDS.128 + two DADD per term), which keeps the sum bit-identical.
+__device__ double intra_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
+                               double2 *terms) {
     double se = 0.0, sv = 0.0;
     for (int base = 0; base < a.n_pairs; base += 32) {
         const int k = base + lane;
-        double te = 0.0, tv = 0.0;
+        double2 t = make_double2(0.0, 0.0);
         if (k < a.n_pairs) {
             const int i = __ldg(a.pair_i + k), j = __ldg(a.pair_j + k);
             const double r = d_nzd(sqrt(d_dist2(x[i], y[i], z[i], x[j], y[j], z[j])));
-            const int t = __ldg(a.lelt + i) * kEltTab + __ldg(a.lelt + j);
-            const double p6 = d_pow6(__ldg(a.xij + t) / r);
-            te = (__ldg(a.lq + i) * __ldg(a.lq + j)) / r;
-            tv = __ldg(a.dij + t) * ((-2.0 * p6) + (p6 * p6));
+            const int tt = __ldg(a.lelt + i) * kEltTab + __ldg(a.lelt + j);
+            const double p6 = d_pow6(__ldg(a.xij + tt) / r);
+            t.x = (__ldg(a.lq + i) * __ldg(a.lq + j)) / r;
+            t.y = __ldg(a.dij + tt) * ((-2.0 * p6) + (p6 * p6));
         }
+        __syncwarp();
+        terms[lane] = t;
+        __syncwarp();
         const int lim = min(32, a.n_pairs - base);
         for (int l = 0; l < lim; l++) {
-            se = se + __shfl_sync(0xffffffffu, te, l);
-            sv = sv + __shfl_sync(0xffffffffu, tv, l);
+            const double2 u = terms[l];
+            se = se + u.x;
+            sv = sv + u.y;
         }
     }
     return (kElecWeight * se) + sv;
 }
 
 // Mol.ene_inter_UFF_interp (mol.ml:1012-1020): one trilinear look-up per lane, summed in atom order
-__device__ double interp_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane) {
+__device__ double interp_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
+                                double2 *terms) {
     double res = 0.0;
     for (int base = 0; base < a.L; base += 32) {
         const int j = base + lane;
         double t = 0.0;
         if (j < a.L) t = d_trilin(a.g, a.maps + (size_t)__ldg(a.ltyp + j) * a.g.nvox, x[j], y[j], z[j]);
+        __syncwarp();
+        terms[lane].x = t;
+        __syncwarp();
         const int lim = min(32, a.L - base);
-        for (int l = 0; l < lim; l++) res = res + __shfl_sync(0xffffffffu, t, l);
+        for (int l = 0; l < lim; l++) res = res + terms[l].x;
     }
     return res;
 }
@@ -147,11 +158,12 @@ mc_chains_kernel(McArgs a) {
     const int64_t chain = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (chain >= a.n_chains) return;                    // whole warp leaves together
     const int L = a.L, nrb = a.n_rbonds;
-    const int per_warp = 9 * L + 2 * max(nrb, 1);
+    const int per_warp = ((9 * L + 2 * max(nrb, 1) + 1) & ~1) + 64;     // even, + 32 double2 term slots
     double *cx = smem + (size_t)wib * per_warp, *cy = cx + L, *cz = cy + L;      // conf
     double *px = cz + L, *py = px + L, *pz = py + L;                              // conf' (proposed)
     double *lx = pz + L, *ly = lx + L, *lz = ly + L;                              // lig'
     double *dr = lz + L, *drp = dr + max(nrb, 1);                                 // per-bond step sizes of conf / conf'
+    double2 *terms = (double2 *)(cx + per_warp - 64);                             // 16-byte aligned: per_warp is even
     Sw *sw_bond = (Sw *)(smem + (size_t)kWarpsPerBlock * per_warp) + (size_t)wib * max(nrb, 1);
 
     const bool flexible = a.tweak_rbonds && nrb > 0;
@@ -183,9 +195,9 @@ mc_chains_kernel(McArgs a) {
     }
     __syncwarp();
     double const_intra = 0.0;
-    if (a.intra_nb && !flexible) const_intra = intra_energy(a, cx, cy, cz, lane);
-    double prev_E_intra = !a.intra_nb ? 0.0 : (flexible ? intra_energy(a, lx, ly, lz, lane) : const_intra);
-    double prev_E_inter = interp_energy(a, lx, ly, lz, lane);
+    if (a.intra_nb && !flexible) const_intra = intra_energy(a, cx, cy, cz, lane, terms);
+    double prev_E_intra = !a.intra_nb ? 0.0 : (flexible ? intra_energy(a, lx, ly, lz, lane, terms) : const_intra);
+    double prev_E_inter = interp_energy(a, lx, ly, lz, lane, terms);
     double prev_E = prev_E_inter + prev_E_intra;
     double best_E = prev_E;
     long long rigid_step = 0, conf_step = 0;
@@ -281,8 +293,8 @@ mc_chains_kernel(McArgs a) {
             }
         }
         __syncwarp();
-        if (!rigid && a.intra_nb) prev_E_intra = flexible ? intra_energy(a, lx, ly, lz, lane) : const_intra;   // D2
-        prev_E_inter = interp_energy(a, lx, ly, lz, lane);
+        if (!rigid && a.intra_nb) prev_E_intra = flexible ? intra_energy(a, lx, ly, lz, lane, terms) : const_intra;   // D2
+        prev_E_inter = interp_energy(a, lx, ly, lz, lane, terms);
         const double curr_E = prev_E_inter + prev_E_intra;
         int accepted = -1;
         const double ddx = a.roi_c[0] - (0.0 + posp[0]), ddy = a.roi_c[1] - (0.0 + posp[1]), ddz = a.roi_c[2] - (0.0 + posp[2]);
@@ -445,7 +457,7 @@ extern "C" int mmo_mc_run(const mmo_grid *grid, const mmo_ligand *lig, const mmo
     a.best_E = d_bestE.p; a.prev_E = d_prevE.p; a.best_rot = d_brot.p; a.best_pos = d_bpos.p; a.best_xyz = d_bxyz.p;
     a.step_sizes = d_steps.p; a.counters = d_cnt.p; a.trace = trace_chain0 ? d_trace.p : nullptr;
     const int nrb1 = std::max(lig->n_rbonds, 1);
-    const size_t smem = (size_t)kWarpsPerBlock * (9 * L + 2 * nrb1) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
+    const size_t smem = (size_t)kWarpsPerBlock * (((9 * L + 2 * nrb1 + 1) & ~1) + 64) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
     MMO_REQUIRE(smem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds)", L, lig->n_rbonds);
     MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)((n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock);

@@ -79,7 +79,19 @@ struct ScanJob {
     long long best_f = -1;
     float device_ms = 0.f;
     bool collect_stats = false;
+    // MMO_PREC_FP64 on the direct path: fp32 sweep that keeps every pose that could be in the exact
+    // top-k (score <= tau + 2*delta), then bit-exact re-scoring of those few in the strict kernel
+    bool two_stage = false;
+    int k_eff = 0;
+    std::vector<ScoreFrame> exact_top;       // filled by scan_finalize
+    double exact_best_s = INFINITY;
+    long long exact_best_f = -1;
+    bool exact_ready = false;
 };
+
+// bound used for |E_fp32 - E_ref|: 8x the accuracy contract of MMO_PREC_FP32 (which the parity tests
+// check at 1x on clashing and non-clashing poses alike)
+static inline double fp32_delta(double e) { return 8.0 * std::max(1e-6 * fabs(e), 1e-4); }
 
 static bool host_bit(const mmo_mask *m, long idx) { return (m->hwords[idx >> 5] >> (idx & 31)) & 1u; }
 
@@ -186,7 +198,9 @@ static int scan_setup(ScanJob &J) {
     MMO_TRY(J.d_E.alloc((size_t)J.slab_cap));
     MMO_TRY(J.d_thr.alloc(1));
     MMO_TRY(J.d_counters.alloc(2));
-    if (P.topk > 0) {
+    J.two_stage = (P.prec == MMO_PREC_FP64 && P.rec != nullptr);
+    J.k_eff = J.two_stage ? std::max(P.topk, 1) : P.topk;
+    if (J.k_eff > 0) {
         MMO_TRY(J.d_cand_s.alloc((size_t)J.slab_cap));
         MMO_TRY(J.d_cand_f.alloc((size_t)J.slab_cap));
     }
@@ -212,7 +226,9 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         const int64_t npts = std::min(pts_per_slab, a1 - s0);
         const int64_t n_cand = npts * P.n_rot;
         J.n_candidates += n_cand;
-        const double thr = (P.topk > 0 && (int)J.top.size() >= P.topk) ? J.top.back().s : INFINITY;
+        double thr = (J.k_eff > 0 && (int)J.top.size() >= J.k_eff) ? J.top[J.k_eff - 1].s : INFINITY;
+        if (J.two_stage && thr < INFINITY) thr = thr + 2.0 * fp32_delta(thr);
+        J.exact_ready = false;
         MMO_CUDA(cudaMemsetAsync(J.d_counters.p, 0, 2 * sizeof(unsigned long long), R.stream));
         MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &thr, sizeof(double), cudaMemcpyHostToDevice, R.stream));
         MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, J.d_rot_perm.p, n_cand, J.d_frames.p, J.d_counters.p));
@@ -223,7 +239,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         if (n_surv == 0) continue;
         if (P.grid) {
             MMO_TRY(launch_interp(P.grid, P.lig, src, (int64_t)n_surv, J.d_E.p));
-        } else if (P.prec == MMO_PREC_FP64) {
+        } else if (P.prec == MMO_PREC_FP64 && !J.two_stage) {
             MMO_TRY(launch_direct_fp64(P.rec, P.lig, P.variant, src, (int64_t)n_surv, J.d_E.p));
         } else {
             MMO_TRY(launch_direct_fp32(P.rec, P.lig, P.variant, src, (int64_t)n_surv, J.d_E.p, J.collect_stats));
@@ -234,7 +250,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         KernelScope ks(K_REDUCE);
         scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(J.d_E.p, J.d_frames.p, (int64_t)n_surv, P.e_intra_const,
                                                          J.d_thr.p, J.d_cand_s.p, J.d_cand_f.p, J.d_counters.p + 1,
-                                                         P.topk > 0 ? (unsigned long long)J.slab_cap : 0ull,
+                                                         J.k_eff > 0 ? (unsigned long long)J.slab_cap : 0ull,
                                                          J.d_block_best.p);
         }
         MMO_LAUNCH_CHECK();
@@ -245,7 +261,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         MMO_CUDA(cudaStreamSynchronize(R.stream));
         for (const ScoreFrame &b : hbest)
             if (b.s < J.best_s || (b.s == J.best_s && b.f < J.best_f && b.s != INFINITY)) { J.best_s = b.s; J.best_f = b.f; }
-        if (P.topk > 0 && n_cnd > 0) {
+        if (J.k_eff > 0 && n_cnd > 0) {
             hs.resize(n_cnd); hf.resize(n_cnd);
             MMO_CUDA(cudaMemcpyAsync(hs.data(), J.d_cand_s.p, n_cnd * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
             MMO_CUDA(cudaMemcpyAsync(hf.data(), J.d_cand_f.p, n_cnd * sizeof(long long), cudaMemcpyDeviceToHost, R.stream));
@@ -259,32 +275,89 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
                 if (an != bn) return bn;
                 return (a.s < b.s) || (a.s == b.s && a.f < b.f);
             };
-            size_t keep = std::min<size_t>(J.top.size(), (size_t)P.topk);
-            std::partial_sort(J.top.begin(), J.top.begin() + keep, J.top.end(), less);
-            J.top.resize(keep);
+            size_t keep = std::min<size_t>(J.top.size(), (size_t)J.k_eff);
+            if (!J.two_stage) {
+                std::partial_sort(J.top.begin(), J.top.begin() + keep, J.top.end(), less);
+                J.top.resize(keep);
+            } else {
+                // keep everything within 2*delta of the k-th best fp32 score: a superset of the exact top-k
+                std::sort(J.top.begin(), J.top.end(), less);
+                if (J.top.size() > keep) {
+                    const double tau = J.top[keep - 1].s;
+                    const double lim = tau + 2.0 * fp32_delta(tau);
+                    size_t m = keep;
+                    while (m < J.top.size() && J.top[m].s <= lim) m++;
+                    J.top.resize(m);
+                }
+            }
         }
     }
     return MMO_OK;
 }
 
-static void scan_fill_result(const ScanJob &J, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+// second stage of the fp64 scan: the surviving candidates are re-scored by the strict kernel
+// (reference arithmetic and summation order), sorted exactly, ties to the smaller frame
+static int scan_finalize(ScanJob &J) {
+    if (!J.two_stage || J.exact_ready) return MMO_OK;
     const mmo_scan_params &P = J.P;
-    int ntop = (int)J.top.size();
+    Runtime &R = rt();
+    J.exact_top.clear();
+    J.exact_best_s = INFINITY;
+    J.exact_best_f = -1;
+    const size_t n = J.top.size();
+    if (n > 0) {
+        std::vector<int64_t> fr(n);
+        for (size_t i = 0; i < n; i++) fr[i] = J.top[i].f;
+        DevBuf<int64_t> d_fr;
+        DevBuf<double> d_e;
+        MMO_TRY(d_fr.upload(fr));
+        MMO_TRY(d_e.alloc(n));
+        PoseSrc src = {};
+        src.kind = 2;
+        src.rot9 = J.d_rot.p;
+        src.frames = d_fr.p;
+        src.n_rot = P.n_rot;
+        for (int d = 0; d < 3; d++) { src.lat_dims[d] = J.dims[d]; src.lat_min[d] = J.mins[d]; src.lat_q[d] = J.q[d]; }
+        MMO_TRY(launch_direct_fp64(P.rec, P.lig, P.variant, src, (int64_t)n, d_e.p));
+        std::vector<double> e(n);
+        MMO_CUDA(cudaMemcpyAsync(e.data(), d_e.p, n * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));
+        J.exact_top.resize(n);
+        for (size_t i = 0; i < n; i++) { J.exact_top[i].s = P.e_intra_const + e[i]; J.exact_top[i].f = fr[i]; }
+        std::sort(J.exact_top.begin(), J.exact_top.end(), [](const ScoreFrame &a, const ScoreFrame &b) {
+            bool an = a.s != a.s, bn = b.s != b.s;
+            if (an != bn) return bn;
+            return (a.s < b.s) || (a.s == b.s && a.f < b.f);
+        });
+        if (J.exact_top[0].s < INFINITY) { J.exact_best_s = J.exact_top[0].s; J.exact_best_f = J.exact_top[0].f; }
+        J.exact_top.resize(std::min<size_t>(n, (size_t)std::max(P.topk, 0)));
+    }
+    J.exact_ready = true;
+    return MMO_OK;
+}
+
+static void scan_fill_result(const ScanJob &Jc, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+    const ScanJob &J = Jc;
+    const mmo_scan_params &P = J.P;
+    const std::vector<ScoreFrame> &top = J.two_stage ? J.exact_top : J.top;
+    int ntop = (int)top.size();
     for (int i = 0; i < ntop; i++) {
-        if (top_scores) top_scores[i] = J.top[i].s;
-        if (top_frames) top_frames[i] = J.top[i].f;
+        if (top_scores) top_scores[i] = top[i].s;
+        if (top_frames) top_frames[i] = top[i].f;
     }
     res->n_candidates = J.n_candidates;
     res->n_scored = J.n_scored;
-    res->best_score = J.best_s;
-    res->best_frame = J.best_f;
+    const double best_s = J.two_stage ? J.exact_best_s : J.best_s;
+    const long long best_f = J.two_stage ? J.exact_best_f : J.best_f;
+    res->best_score = best_s;
+    res->best_frame = best_f;
     res->n_top = ntop;
     for (int d = 0; d < 3; d++) res->lattice_dims[d] = J.dims[d];
     res->best_rot_i = 0;
     res->best_pos[0] = res->best_pos[1] = res->best_pos[2] = 0.0;   // V3.origin when nothing was scored
-    if (J.best_f >= 0) {
-        int64_t pt = J.best_f / P.n_rot;
-        res->best_rot_i = (int32_t)(J.best_f - pt * P.n_rot);
+    if (best_f >= 0) {
+        int64_t pt = best_f / P.n_rot;
+        res->best_rot_i = (int32_t)(best_f - pt * P.n_rot);
         int xy = J.dims[0] * J.dims[1];
         int k = (int)(pt / xy);
         int j = (int)((pt - (int64_t)k * xy) / J.dims[0]);
@@ -364,6 +437,7 @@ int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active) {
 
 int mmo_scan_result_get(const mmo_scan_job *job, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
     MMO_REQUIRE(job && res, "mmo_scan_result_get: null pointer");
+    MMO_TRY(scan_finalize(const_cast<mmo_scan_job *>(job)->J));
     scan_fill_result(job->J, top_scores, top_frames, res);
     return MMO_OK;
 }
@@ -378,6 +452,7 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
     mmo_scan_job *job = nullptr;
     MMO_TRY(mmo_scan_create(p, rt().collect_stats ? 1 : 0, &job));
     int rc = mmo_scan_run(job, 0, -1);
+    if (rc == MMO_OK) rc = scan_finalize(job->J);
     if (rc == MMO_OK) scan_fill_result(job->J, top_scores, top_frames, res);
     mmo_scan_destroy(job);
     return rc;

@@ -1,0 +1,90 @@
+(* gpu.ml -- OCaml side of the libmmo_b200 binding (see INTEGRATION.md).
+   NOT COMPILED IN THIS REPOSITORY'S IMAGE (no OCaml toolchain); kept mechanical on purpose.
+   Each external maps 1:1 to a stub in gpu_stubs.c which maps 1:1 to include/mmo_b200.h. *)
+
+type receptor
+type ligand
+type grid
+type mask
+
+(* MMO_VARIANT_* / MMO_PREC_* of include/mmo_b200.h *)
+let variant_global = 0
+let variant_shifted = 1
+let prec_fp32 = 0
+let prec_fp64 = 1
+
+external init : int -> unit = "mmo_ml_init"
+external shutdown : unit -> unit = "mmo_ml_shutdown"
+
+external receptor_create :
+  float array -> float array -> float array -> float array -> int array -> receptor
+  = "mmo_ml_receptor_create"
+
+(* xs ys zs q_a r_a elt_a t_a dists_a rb_left rb_right rgroups *)
+external ligand_create_raw :
+  float array -> float array -> float array -> float array -> float array ->
+  int array -> int array -> int array -> int array -> int array -> int array array -> ligand
+  = "mmo_ml_ligand_create_bc" "mmo_ml_ligand_create"
+
+external score_coords :
+  receptor -> ligand -> int -> int -> float array -> float array -> float array -> float
+  = "mmo_ml_score_coords_bc" "mmo_ml_score_coords"
+
+external score_components :
+  receptor -> ligand -> float array -> float array -> float array -> float * float
+  = "mmo_ml_score_components"
+
+external intra_nb : ligand -> float array -> float array -> float array -> float
+  = "mmo_ml_intra_nb"
+
+(* step x_dim y_dim z_dim mask(as bool array option) types -> maps (filled in place) *)
+external grid_build :
+  receptor -> float -> int -> int -> int -> bool array option -> (int * float) array ->
+  (float, Bigarray.float32_elt, Bigarray.c_layout) Bigarray.Array1.t array -> grid
+  = "mmo_ml_grid_build_bc" "mmo_ml_grid_build"
+
+external grid_upload :
+  float -> int -> int -> int ->
+  (float, Bigarray.float32_elt, Bigarray.c_layout) Bigarray.Array1.t array -> grid
+  = "mmo_ml_grid_upload"
+
+external score_interp : grid -> ligand -> float array -> float array -> float array -> float
+  = "mmo_ml_score_interp"
+
+external trilin : grid -> int -> float -> float -> float -> float = "mmo_ml_trilin"
+
+external vdw_mask_build :
+  float array -> float array -> float array -> float array -> float -> int -> int -> int -> mask
+  = "mmo_ml_vdw_mask_build_bc" "mmo_ml_vdw_mask_build"
+
+(* rec option, grid option, lig, mask option, variant, prec, (roi x y z r), trans_step, rotations
+   (float array of 9*n: Rot.t records are flat), const_ene_intra, topk
+   -> (top scores ascending, best score, best frame) *)
+external scan :
+  receptor option -> grid option -> ligand -> mask option -> int -> int ->
+  float array -> float -> float array -> float -> int -> float array * float * int
+  = "mmo_ml_scan_bc" "mmo_ml_scan"
+
+(* ---- drop-in closures ------------------------------------------------------------------ *)
+
+let ligand_create (m: Mol.t): ligand =
+  let lefts = Array.map (fun b -> b.Bond.left) m.Mol.rbonds_a in
+  let rights = Array.map (fun b -> b.Bond.right) m.Mol.rbonds_a in
+  ligand_create_raw m.Mol.xs m.Mol.ys m.Mol.zs m.Mol.q_a m.Mol.r_a m.Mol.elt_a m.Mol.t_a
+    m.Mol.dists_a lefts rights m.Mol.rgroups_a
+
+(* Mol.ene_inter_UFF_shifted_brute prot (mol.ml:822-849) / _shifted_bst (958-960) *)
+let ene_inter_shifted ?(prec = prec_fp32) rec_h lig_h (lig': Mol.t): float =
+  score_coords rec_h lig_h variant_shifted prec lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs
+
+(* Mol.ene_inter_UFF_global_brute prot (mol.ml:796-818) *)
+let ene_inter_global ?(prec = prec_fp32) rec_h lig_h (lig': Mol.t): float =
+  score_coords rec_h lig_h variant_global prec lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs
+
+(* Mol.ene_inter_UFF_interp grid ff_comps (mol.ml:1012-1020) *)
+let ene_inter_interp grid_h lig_h (lig': Mol.t): float =
+  score_interp grid_h lig_h lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs
+
+(* Mol.ene_intra_UFFNB_brute (mol.ml:881-903) *)
+let ene_intra lig_h (lig': Mol.t): float =
+  intra_nb lig_h lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs

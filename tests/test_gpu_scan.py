@@ -106,3 +106,33 @@ def test_scan_interpolated_scorer(gpu, orc, c2, c2_roi_rec, setup):
     got = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, grid=g)
     assert np.array_equal(got["top_frames"], want["top_frames"]) and np.array_equal(got["top_scores"], want["top_scores"])
     assert got["best_frame"] == want["best_frame"]
+
+
+def test_scan_fp64_two_stage_equals_exhaustive_strict_scoring(gpu, orc, c2, setup):
+    """MMO_PREC_FP64 scans sweep in fp32 and re-score only the poses within the error margin of the k-th
+    best; the outcome must be what strict-fp64 scoring of EVERY pose gives (argmin frame, top-k order)."""
+    rec, lig, mask, dims, e_intra = setup
+    n_rot, k = 3000, 200
+    rot = gpu.SO3.rotations(n_rot)
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 2.6)
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(k, roi, 1.0, rot, lig, rec=rec, e_intra_const=e_intra, prec=gpu.PREC_FP64)
+    # every pose of the same scan through the strict kernel (bit-identical to the oracle, see test_gpu_direct)
+    ld = got["lattice_dims"]
+    lo = [roi[d] - roi[3] for d in range(3)]
+    frames, R, T = [], [], []
+    for kk in range(ld[2]):
+        for jj in range(ld[1]):
+            for ii in range(ld[0]):
+                pos = np.array([lo[0] + orc.grid_node(1.0, ld[0], ii), lo[1] + orc.grid_node(1.0, ld[1], jj),
+                                lo[2] + orc.grid_node(1.0, ld[2], kk)])
+                if ((np.array(roi[:3]) - pos) ** 2).sum() < roi[3] ** 2:
+                    pt = ii + jj * ld[0] + kk * ld[0] * ld[1]
+                    frames.append(np.arange(n_rot, dtype=np.int64) + n_rot * pt)
+                    R.append(rot); T.append(np.tile(pos, (n_rot, 1)))
+    frames = np.concatenate(frames); R = np.concatenate(R); T = np.concatenate(T)
+    assert len(frames) == got["n_scored"]
+    e = e_intra + gpu.Mol.score_poses(rec, lig, R, T, prec=gpu.PREC_FP64)
+    order = np.lexsort((frames, e))[:k]
+    assert np.array_equal(got["top_frames"], frames[order])
+    assert np.array_equal(got["top_scores"], e[order])
+    assert got["best_frame"] == frames[order[0]] and got["best_score"] == e[order[0]]

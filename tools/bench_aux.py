@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the bench.py headline): configs C3 (grid build + interpolated scoring),
+C4 (many MC chains) and C5-shaped direct scoring of arbitrary conformers.  Prints one JSON object.
+Run on a B200:  python tools/bench_aux.py [--quick]"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mmo_b200  # noqa: E402
+from mmo_b200 import pqrs, workloads  # noqa: E402
+
+K = {"direct_fp32": 0, "hard_fix": 1, "direct_fp64": 2, "intra": 3, "grid_build": 4, "interp": 5, "mc": 9}
+
+
+def ktime(L, kid):
+    ms, n = C.c_double(), C.c_int64()
+    L.mmo_kernel_time_get(kid, C.byref(ms), C.byref(n))
+    return ms.value, n.value
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    mmo_b200.init(0)
+    L = mmo_b200.lib()
+    out = {}
+    hbm = C.c_double(); L.mmo_measure_hbm_copy(C.byref(hbm))
+    fp64 = C.c_double(); L.mmo_measure_fp64_peak(C.byref(fp64))
+    fp32 = C.c_double(); L.mmo_measure_fp32_peak(C.byref(fp32))
+    out["peaks"] = {"hbm_copy_gbs": hbm.value, "fp64_fma_tflops": fp64.value, "fp32_fma_tflops": fp32.value}
+
+    # ---- C3: 5000-atom synthetic receptor, 30 A box at 0.375 A (81^3 voxels), 22 ligand types --------
+    rec_m = workloads.synthetic_receptor(5000, "cube", 60.0, seed=workloads.SEED)
+    lig_m = pqrs.read_ligands_pqrs(os.path.join(workloads.GOLDEN, "ligdecs.pqrs"))[0]
+    ta, tq = pqrs.assign_ff_types([lig_m])
+    # Grid.from_box puts the lowest corner at the origin: shift the receptor so that the 30 A box
+    # centred in it starts at the origin
+    rec_m.xs -= 15.0; rec_m.ys -= 15.0; rec_m.zs -= 15.0
+    rec = mmo_b200.Receptor.from_mol(rec_m)
+    dims = mmo_b200.Grid.from_box(0.375, 30.0, 30.0, 30.0)
+    L.mmo_kernel_timing(1)
+    reps = 2 if args.quick else 5
+    for _ in range(reps):
+        g, _ = mmo_b200.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta, tq, want_host=False)
+    ms, n = ktime(L, K["grid_build"])
+    nvox = dims[0] * dims[1] * dims[2]
+    out["c3_grid_build"] = {"dims": dims, "types": len(ta), "receptor_atoms": rec_m.n, "ms_per_build": ms / reps,
+                            "launches_per_build": n / reps, "voxel_types_per_s": nvox * len(ta) / (ms / reps * 1e-3),
+                            "bytes_written": nvox * len(ta) * 4, "write_gbs": nvox * len(ta) * 4 / (ms / reps * 1e-3) / 1e9,
+                            "atom_voxel_pairs": nvox * rec_m.n}
+    # interpolated scoring of 1e6 rigid poses whose atoms stay inside the grid
+    lig = mmo_b200.Ligand.from_mol(lig_m, centered=True)
+    n_poses = 200_000 if args.quick else 1_000_000
+    rng = np.random.default_rng(workloads.SEED)
+    R = workloads.random_rotations(n_poses, rng)
+    rl = workloads.lig_radius((lig.xs, lig.ys, lig.zs))
+    t = rng.uniform(rl + 0.4, 30.0 - rl - 0.4, (n_poses, 3))
+    d_rot = C.c_void_p(); d_t = C.c_void_p(); d_e = C.c_void_p()
+    L.mmo_dev_alloc(C.c_size_t(R.nbytes), C.byref(d_rot)); L.mmo_dev_alloc(C.c_size_t(t.nbytes), C.byref(d_t))
+    L.mmo_dev_alloc(C.c_size_t(n_poses * 8), C.byref(d_e))
+    L.mmo_h2d(d_rot, R.ctypes.data_as(C.c_void_p), C.c_size_t(R.nbytes)); L.mmo_h2d(d_t, t.ctypes.data_as(C.c_void_p), C.c_size_t(t.nbytes))
+    L.mmo_kernel_timing(1)
+    for _ in range(reps + 1):
+        L.mmo_l2_flush()
+        assert L.mmo_score_interp_poses_dev(g.h, lig.h, C.c_int64(n_poses), d_rot, d_t, d_e) == 0
+    L.mmo_sync()
+    ms, n = ktime(L, K["interp"])
+    lookups = n_poses * lig.n
+    out["c3_interp"] = {"poses": n_poses, "ms_per_launch": ms / n, "poses_per_s": n_poses / (ms / n * 1e-3),
+                        "atom_lookups_per_s": lookups / (ms / n * 1e-3),
+                        "algorithmic_gbs": lookups * 48 / (ms / n * 1e-3) / 1e9, "maps_mb": nvox * len(ta) * 4 / 1e6}
+    # direct fp32 scoring of the same poses against the 5000-atom receptor (incoherent poses: C5 shape)
+    n_dir = 50_000 if args.quick else 200_000
+    L.mmo_kernel_timing(1)
+    for _ in range(3):
+        assert L.mmo_score_poses_dev(rec.h, lig.h, 1, 0, C.c_int64(n_dir), d_rot, d_t, d_e) == 0
+    L.mmo_sync()
+    ms, n = ktime(L, K["direct_fp32"])
+    fms, _ = ktime(L, K["hard_fix"])
+    out["c5_shape_direct"] = {"poses": n_dir, "receptor_atoms": rec_m.n, "ligand_atoms": lig.n,
+                              "ms_per_launch": ms / n, "fix_ms_per_launch": fms / n,
+                              "poses_per_s": n_dir / ((ms + fms) / n * 1e-3),
+                              "nominal_pairs_per_s": n_dir * rec_m.n * lig.n / ((ms + fms) / n * 1e-3)}
+    L.mmo_kernel_timing(1)
+    n64 = 5_000 if args.quick else 20_000
+    assert L.mmo_score_poses_dev(rec.h, lig.h, 1, 1, C.c_int64(n64), d_rot, d_t, d_e) == 0
+    L.mmo_sync()
+    ms, n = ktime(L, K["direct_fp64"])
+    out["direct_fp64_strict"] = {"poses": n64, "ms": ms, "poses_per_s": n64 / (ms * 1e-3),
+                                 "nominal_pairs_per_s": n64 * rec_m.n * lig.n / (ms * 1e-3)}
+
+    # ---- C4: MC chains, interpolated E_inter + intra NB, --hard-ROI -----------------------------------
+    c2 = workloads.load_c2("ligdecs")
+    rec2_m = workloads.carve(c2["rec"], c2["roi"][:3], c2["roi"][3] + workloads.lig_radius(c2["centered"]) + 12.0)
+    rec2 = mmo_b200.Receptor.from_mol(rec2_m)
+    import oracle
+    cc = np.array(c2["roi"][:3])
+    gd = mmo_b200.Grid.from_box(0.5, *(cc + 23.0))
+    gmask = oracle.bitmask_sphere(0.5, gd, cc, 21.0)
+    ta2, tq2 = pqrs.assign_ff_types([c2["lig"]])
+    L.mmo_kernel_timing(1)
+    g2, _ = mmo_b200.Lds.pre_calculate_FF_components_grid(rec2, 0.5, gd, ta2, tq2, mask_bits=gmask, want_host=False)
+    ms, _ = ktime(L, K["grid_build"])
+    out["c4_grid_build_ms"] = ms
+    lig2 = mmo_b200.Ligand.from_mol(c2["lig"], centered=True)
+    n_chains, n_steps = (512, 1000) if args.quick else (4096, 10000)
+    seeds = np.arange(n_chains, dtype=np.uint64) + workloads.SEED
+    Rm, tm = workloads.random_poses_in_sphere(n_chains, c2["roi"][:3], 3.0, seed=41)
+    L.mmo_kernel_timing(1)
+    t0 = time.perf_counter()
+    res, _, _ = mmo_b200.Lds.simulate_lig(g2, lig2, c2["roi"], n_steps, seeds, Rm, tm)
+    wall = time.perf_counter() - t0
+    ms, _ = ktime(L, K["mc"])
+    done = sum(r["frames_done"] for r in res)
+    out["c4_mc"] = {"chains": n_chains, "steps": n_steps, "kernel_ms": ms, "wall_s": wall,
+                    "chain_steps_per_s": done / (ms * 1e-3), "median_best_E": float(np.median([r["best_E"] for r in res])),
+                    "too_long": int(sum(r["too_long"] for r in res))}
+    # CPU oracle chain for the side-by-side
+    t0 = time.perf_counter()
+    cx, cy, cz = c2["centered"]
+    gm = g2.download()
+    oracle.mc_run(c2["lig"], cx, cy, cz, c2["roi"], n_steps, int(seeds[0]), Rm[0], tm[0], maps=gm, g_step=0.5, g_dims=gd)
+    out["c4_mc"]["cpu_oracle_chain_steps_per_s_1core"] = n_steps / (time.perf_counter() - t0)
+    L.mmo_kernel_timing(0)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
