@@ -248,6 +248,8 @@ def main():
     ck(L.mmo_kernel_time_get(1, C.byref(fix_ms), None))
     ck(L.mmo_kernel_timing(0))
     stop.set()
+    if rank == 0:
+        th.join(timeout=10)      # a concurrent nvidia-smi query stalls cudaMalloc/cudaFree in the e2e calls below
     ck(L.mmo_scan_result_get(job, None, None, C.byref(SR)))
     poses_per_step = pps * N_ROT
 
@@ -273,8 +275,12 @@ def main():
         a0 = slab_first(args.warmup + s)
         P.first_point = act[a0]
         P.n_points = act[a0 + pps - 1] - act[a0] + 1
+        tc = time.perf_counter()
         ck(L.mmo_scan(C.byref(P), ts.ctypes.data_as(C.POINTER(C.c_double)), tf.ctypes.data_as(C.POINTER(C.c_int64)),
                       C.byref(R2)))
+        if os.environ.get("MMO_BENCH_DEBUG"):
+            print(f"e2e call {s}: raw points {P.first_point}+{P.n_points} scored {R2.n_scored} "
+                  f"wall {1e3 * (time.perf_counter() - tc):.1f} ms device {R2.device_ms:.1f} ms", file=sys.stderr)
         e2e_poses += R2.n_scored
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -309,7 +315,6 @@ def main():
         assert top_n == 0 or ms_s[0] == gb[0], "merged top-1 disagrees with the global argmin"
 
     if rank == 0:
-        th.join(timeout=2)
         total_poses = poses_per_step * args.steps * world
         value = total_poses / (dev_ms * 1e-3)
         pairs_nominal = value * rec_m.n * c2["lig"].n

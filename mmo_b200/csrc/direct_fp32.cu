@@ -62,17 +62,15 @@ __device__ __forceinline__ float pair_energy(float dx, float dy, float dz, float
     float er = (qi * qj) * rinv;                    // qi already carries 332.0637/4
     float e = fmaf(v, s3, er);
     if (VARIANT == MMO_VARIANT_SHIFTED) {
-        // shift weight (1 - r^2/144)^2 = (144 - r^2)^2 / 144^2; the constant factor is applied once per
-        // receptor atom (kInvCut4), which keeps this at FADD-immediate + FMNMX + FMUL
-        float u = fmaxf(144.0f - r2c, 0.0f);                      // 0 beyond the 12 A cut-off
+        // shift weight (1 - r^2/144)^2 from the unclamped r^2, saturated to [0,1]: one FFMA.SAT gives
+        // exactly 0 beyond the 12 A cut-off (FF.shift_12A, FF.ml:17-20)
+        float u = __saturatef(fmaf(r2, -1.0f / 144.0f, 1.0f));
         return fmaf(u * u, e, acc);
     } else {
         return acc + e;
     }
 }
 
-// Shared memory (dynamic): receptor tile {xyzq[tile_atoms], ab[tile_atoms], box[2*tile_blobs]}, the
-// ligand parameters {A_j, B_j, q_j, real?}[n_fast] and this block's chunk coordinates [LJ][TPB].
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(TPB, 2)
 direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_blobs, double *__restrict__ out) {
@@ -213,7 +211,6 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_blobs, dou
             __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
         }
     }
-    if (VARIANT == MMO_VARIANT_SHIFTED) acc *= 1.0 / (144.0 * 144.0);
     if (valid) out[p] = acc;
     if (STATS && valid) {
         atomicAdd(a.stats + 0, n_eval);
@@ -236,7 +233,7 @@ struct FixArgs {
     const double *lx, *ly, *lz, *lq;
     const int32_t *lelt;
     double H;                            // exactly the fp32 clamp value
-    double rinvH, wH;                    // 1/sqrt(H), (1 - H/144)^2
+    double rinvH;                        // 1/sqrt(H)
     const double *xx, *dij, *vdwH;       // kEltTab^2 tables: x_i*x_j, d_ij, d_ij*(p6H^2 - 2 p6H)
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
@@ -280,14 +277,14 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ ou
                 const double rinv = rsqrt(r2c);
                 const double t2 = __ldg(a.xx + t) * (rinv * rinv);  // (x_ij / r)^2
                 const double p6 = t2 * t2 * t2;
-                double e = qq * rinv + __ldg(a.dij + t) * (p6 * p6 - 2.0 * p6);
-                double eH = qq * a.rinvH + __ldg(a.vdwH + t);
+                const double e = qq * rinv + __ldg(a.dij + t) * (p6 * p6 - 2.0 * p6);
+                const double eH = qq * a.rinvH + __ldg(a.vdwH + t);   // what the fast path evaluated (r clamped at sqrt(H))
+                double d = e - eH;
                 if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    const double u = 1.0 - r2c * (1.0 / 144.0);
-                    e *= u * u;
-                    eH *= a.wH;
+                    const double u = 1.0 - r2c * (1.0 / 144.0);        // the fast path weighted e(H) with w(r), not w(H)
+                    d *= u * u;
                 }
-                corr += e - eH;
+                corr += d;
                 if (STATS) n_fix++;
             }
         }
@@ -368,7 +365,6 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.lx = lig->x.p; xa.ly = lig->y.p; xa.lz = lig->z.p; xa.lq = lig->q.p; xa.lelt = lig->elt.p;
     xa.H = (double)H;
     xa.rinvH = 1.0 / sqrt((double)H);
-    xa.wH = (1.0 - (double)H / 144.0) * (1.0 - (double)H / 144.0);
     xa.xx = g_xx.p; xa.dij = g_dij.p; xa.vdwH = g_vdwH.p;
     xa.stats = g_stats.p;
 

@@ -14,6 +14,8 @@
 #include "pose.cuh"
 #include <math.h>
 #include <algorithm>
+#include <chrono>
+#include <stdlib.h>
 
 namespace mmo {
 
@@ -449,12 +451,19 @@ int mmo_scan_destroy(mmo_scan_job *job) {
 
 int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
     MMO_REQUIRE(res != nullptr, "mmo_scan: null result pointer");
+    const bool dbg = getenv("MMO_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     mmo_scan_job *job = nullptr;
     MMO_TRY(mmo_scan_create(p, rt().collect_stats ? 1 : 0, &job));
+    double t1 = now();
     int rc = mmo_scan_run(job, 0, -1);
+    double t2 = now();
     if (rc == MMO_OK) rc = scan_finalize(job->J);
     if (rc == MMO_OK) scan_fill_result(job->J, top_scores, top_frames, res);
+    double t3 = now();
     mmo_scan_destroy(job);
+    if (dbg) fprintf(stderr, "[mmo_scan] create %.1f ms, run %.1f ms, finalize %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
 
