@@ -185,6 +185,17 @@ int mmo_so3_rotations(int32_t n, double *rot9);
 int mmo_rot_r_xyz(double alpha, double beta, double gamma, double rot9[9]);  /* src/rot.ml:52-66 */
 int mmo_rot_decompose(const double rot9[9], double abg[3]);                  /* src/rot.ml:71-75 */
 
+/* ---------------------------------------------------------------- pose builders (host) ----- */
+/* Optim.apply_config centered_lig conf (src/optim.ml:64-80) = the place_ligand tool
+ * (src/place_ligand.ml:11-59): config = x y z alpha beta gamma [rbond angles]; the ligand handle holds the
+ * centred conformer.  too_long = 1 when Mol.check_elongation_exn would raise (coordinates still returned). */
+int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_config, double *out_xs,
+                     double *out_ys, double *out_zs, int32_t *too_long);
+/* lig_rot_sample (src/lig_rot_sample.ml:23-45): Mol.center_rotate_translate_copy mol rot center for n
+ * rotations; out arrays hold n x L coordinates */
+int mmo_rotated_copies(const mmo_ligand *lig, const double center[3], int32_t n, const double *rot9,
+                       double *out_xs, double *out_ys, double *out_zs);
+
 /* ---------------------------------------------------------------- exhaustive rigid scan ---- */
 /* Lds.exhaustive_rigid_ligand_docking (src/lds.ml:1040-1114).
  * Lattice = Grid.from_box trans_step over ROI.get_bounds; loop order z, y, x, rotation;

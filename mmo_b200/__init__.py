@@ -456,6 +456,29 @@ class Lds:
         return out, xyz, trace
 
 
+class Optim:
+    @staticmethod
+    def apply_config(lig, config):
+        """src/optim.ml:64-80 (place_ligand): x y z alpha beta gamma [rbond angles] -> coordinates, too_long"""
+        cfg = np.ascontiguousarray(config, np.float64)
+        x = np.empty(lig.n); y = np.empty(lig.n); z = np.empty(lig.n)
+        tl = C.c_int32()
+        _ck(lib().mmo_apply_config(lig.h, cfg.ctypes.data_as(_dp), C.c_int32(len(cfg)), x.ctypes.data_as(_dp),
+                                   y.ctypes.data_as(_dp), z.ctypes.data_as(_dp), C.byref(tl)))
+        return x, y, z, bool(tl.value)
+
+    @staticmethod
+    def rotated_copies(lig, center, rot9):
+        """src/lig_rot_sample.ml:23-45: Mol.center_rotate_translate_copy mol rot center for every rotation"""
+        rot = np.ascontiguousarray(rot9, np.float64).reshape(-1, 9)
+        n = rot.shape[0]
+        X = np.empty((n, lig.n)); Y = np.empty((n, lig.n)); Z = np.empty((n, lig.n))
+        c = (C.c_double * 3)(*center)
+        _ck(lib().mmo_rotated_copies(lig.h, c, C.c_int32(n), rot.ctypes.data_as(_dp), X.ctypes.data_as(_dp),
+                                     Y.ctypes.data_as(_dp), Z.ctypes.data_as(_dp)))
+        return X, Y, Z
+
+
 class SO3:
     @staticmethod
     def rotations(n):

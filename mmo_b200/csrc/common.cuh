@@ -94,7 +94,7 @@ constexpr double kElecWeight = 332.0637 / 4.0;   // src/UFF.ml:25, src/const.ml:
 constexpr double kMaxE = 100000.0;               // src/params.ml:26
 
 // ---- geometry of the fp32 direct kernel -----------------------------------------------------------
-constexpr int kBlob = 8;         // receptor atoms per k-d leaf ("blob"): the unit of distance culling
+constexpr int kBlob = 32;        // receptor atoms per k-d leaf ("group"): first level of distance culling
 // close-contact threshold: pairs with x_i*x_j / r^2 > kTau are re-evaluated in fp64
 constexpr double kTau = 1.5;
 

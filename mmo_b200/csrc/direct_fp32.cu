@@ -3,14 +3,15 @@
 // Replaces the inner loops of Mol.ene_inter_UFF_shifted_brute / _global_brute (src/mol.ml:796-849)
 // for many poses per launch.  Layout of the computation (no tensor cores: non-linear pair sum):
 //
-//   thread  = one pose; a chunk of LJ ligand atoms lives in registers (coordinates + vdW factors)
-//   block   = 128 poses; receptor blobs (kBlob Morton-sorted atoms, fp32, relative to the receptor
-//             origin) are staged tile by tile in shared memory and read as warp-wide broadcasts
-//   cull    = per (warp, ligand chunk, blob): bounding-box distance >= 12 A  ->  blob skipped
-//             (shifted variant only; a skipped pair has weight exactly 0 in the reference, mol.ml:836)
-//   pair    = 19 issue slots: 3 FADD, FMUL+2 FFMA (r2), FMNMX clamp, MUFU.RSQ, ... see pair_energy()
-//   sum     = the LJ pair terms of one receptor atom are summed in fp32 (<= LJ terms), then added to
-//             a per-thread fp64 accumulator
+//   thread  = one pose, block = 256 poses; the receptor (k-d groups of 32 atoms, fp32, relative to the
+//             receptor origin) is staged in shared memory, the whole ROI receptor at once when it fits
+//   cull    = per (warp, ligand atom): the atom's bounding box over the warp's 32 poses is tested first
+//             against the group boxes (one ballot per 32 groups), then against the individual atoms of
+//             the near groups (one ballot per group); survivors are compacted into a per-warp list.
+//             Shifted variant only: a culled pair has weight exactly 0 in the reference (mol.ml:836)
+//   pair    = 20 SASS instructions (1 MUFU.RSQ), see pair_energy(); the list is consumed 8 atoms at a
+//             time = 8 independent dependency chains per warp
+//   sum     = 8 pair terms in fp32, then one F2F + DADD into a per-thread fp64 accumulator
 //
 // Accuracy contract (MMO_PREC_FP32): |E - E_ref| <= max(1e-6 |E_ref|, 1e-4 kcal/mol).  fp32 cannot
 // deliver that for close contacts (r^-12), so the fast path clamps r^2 at H = x_max_rec*x_max_lig/kTau
@@ -22,13 +23,15 @@
 
 namespace mmo {
 
-constexpr int LJ = 8;            // ligand atoms per register chunk (= one k-d leaf of the ligand)
+constexpr int LJ = 8;            // ligand atoms per chunk (= one k-d leaf of the ligand)
 constexpr int TPB = 256;         // poses per block
-static_assert(kBlob == 8 && LJ == 8, "the 4-blobs x 8-atoms lane-parallel cull test assumes 8/8");
+constexpr int LIST_CAP = 256;    // per-warp list of near receptor atoms (uint16 tile indices)
+constexpr int MAX_TILE_GROUPS = 64;
+static_assert(kBlob == 32, "one receptor group per warp-wide test");
 
 struct FastArgs {
-    int n_blobs;
-    int n_atoms;             // real receptor atoms (the last blob may be padded)
+    int n_blobs;             // receptor groups of 32 atoms (k-d leaves)
+    int n_atoms;             // real receptor atoms (the last group may be padded)
     const float4 *xyzq;
     const float2 *ab;
     const float4 *blob_box;
@@ -71,18 +74,32 @@ __device__ __forceinline__ float pair_energy(float dx, float dy, float dz, float
     }
 }
 
+// squared distance from point p to the box [lo, hi]
+__device__ __forceinline__ float box_dist2(const float4 p, const float *lo, const float *hi) {
+    float gx = fmaxf(0.f, fmaxf(lo[0] - p.x, p.x - hi[0]));
+    float gy = fmaxf(0.f, fmaxf(lo[1] - p.y, p.y - hi[1]));
+    float gz = fmaxf(0.f, fmaxf(lo[2] - p.z, p.z - hi[2]));
+    return fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+}
+
+// Shared memory (dynamic): receptor tile {xyzq[tile_atoms+1], gbox[2*tile_groups], lparam[n_fast],
+// chunk coordinates [LJ][TPB], ab[tile_atoms+2], per-warp near lists}.  Slot tile_atoms is a dummy atom
+// (far away, no charge, no vdW) used to pad a list to a multiple of 8.
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(TPB, 2)
-direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_blobs, double *__restrict__ out) {
+direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, double *__restrict__ out) {
     extern __shared__ float4 smem4[];
-    float4 *s_xyzq = smem4;                                   // tile_blobs * 8
-    float4 *s_box = s_xyzq + tile_blobs * kBlob;              // tile_blobs * 2
-    float4 *s_lparam = s_box + tile_blobs * 2;                // n_fast
+    const int tile_atoms = tile_groups * kBlob;
+    float4 *s_xyzq = smem4;                                   // tile_atoms + 1
+    float4 *s_box = s_xyzq + tile_atoms + 1;                  // tile_groups * 2
+    float4 *s_lparam = s_box + tile_groups * 2;               // n_fast
     float4 *s_c = s_lparam + a.n_fast;                        // LJ * TPB : {x, y, z, -} of chunk atom jj, pose tid
-    float2 *s_ab = (float2 *)(s_c + LJ * TPB);                // tile_blobs * 8
+    float2 *s_ab = (float2 *)(s_c + LJ * TPB);                // tile_atoms + 2
+    unsigned short *s_list = (unsigned short *)(s_ab + tile_atoms + 2) + (threadIdx.x >> 5) * LIST_CAP;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t p = (int64_t)blockIdx.x * TPB + tid;
     const bool valid = p < n_poses;
     const int64_t pp = valid ? p : n_poses - 1;   // idle lanes shadow the last pose, result discarded
@@ -91,36 +108,33 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_blobs, dou
     double acc = 0.0;
     unsigned long long n_eval = 0, n_in = 0;
     const int n_chunks = a.n_fast / LJ;
-    const int n_tiles = (a.n_blobs + tile_blobs - 1) / tile_blobs;
+    const int n_tiles = (a.n_blobs + tile_groups - 1) / tile_groups;
 
     for (int t = 0; t < n_tiles; t++) {
         // ---- stage a receptor tile (the whole ROI receptor when it fits: one tile, two barriers) ----
         __syncthreads();
-        const int b0 = t * tile_blobs;
-        const int nb = min(tile_blobs, a.n_blobs - b0);
+        const int b0 = t * tile_groups;
+        const int nb = min(tile_groups, a.n_blobs - b0);
+        const int n_real = min(nb * kBlob, a.n_atoms - b0 * kBlob);      // real atoms in this tile
         for (int k = tid; k < nb * kBlob; k += TPB) {
             s_xyzq[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
             s_ab[k] = __ldg(a.ab + (size_t)b0 * kBlob + k);
         }
-        const int nb4 = (nb + 3) & ~3;
-        for (int k = tid; k < nb4 * 2; k += TPB)
-            s_box[k] = (k < nb * 2) ? __ldg(a.blob_box + (size_t)b0 * 2 + k)
-                                    : make_float4(3e38f, 3e38f, 3e38f, 0.f);   // absent blob: never near
+        if (tid == 0) { s_xyzq[tile_atoms] = make_float4(1e6f, 1e6f, 1e6f, 0.f); s_ab[tile_atoms] = make_float2(0.f, 0.f); }
+        for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
         __syncthreads();
 
         for (int c = 0; c < n_chunks; c++) {
             // ---- this pose's chunk of ligand atoms: reference arithmetic in double, then fp32 -----
             // (own column of s_c only: no block barrier needed, __syncwarp orders the warp's accesses)
-            float mlo[3] = {3e38f, 3e38f, 3e38f}, mhi[3] = {-3e38f, -3e38f, -3e38f};
             {
                 PoseRT P;
                 if (src.kind != 1) load_pose_rt(src, pp, P);
 #pragma unroll
                 for (int jj = 0; jj < LJ; jj++) {
                     const int k = c * LJ + jj;
-                    const bool real = s_lparam[k].w != 0.f;
-                    float4 v = make_float4(-1e6f, -1e6f, -1e6f, 0.f);   // padding atom: never near anything
-                    if (real) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s_lparam[k].w != 0.f) {
                         double x, y, z;
                         if (src.kind == 1) {
                             const int j = __ldg(a.forder + k);
@@ -133,79 +147,85 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_blobs, dou
                         v.z = (float)(z - a.origin[2]);
                     }
                     s_c[jj * TPB + tid] = v;
-                    // per-atom bounding box over the warp's 32 poses; lane keeps the box of atom lane&7
-                    if (VARIANT == MMO_VARIANT_SHIFTED) {
-                        float lo[3] = {v.x, v.y, v.z}, hi[3] = {v.x, v.y, v.z};
+                }
+            }
+#pragma unroll 1
+            for (int jj = 0; jj < LJ; jj++) {
+                const float4 lp = s_lparam[c * LJ + jj];
+                if (lp.w == 0.f) continue;                              // padding atom (warp-uniform)
+                const float4 lc = s_c[jj * TPB + tid];
+                // bounding box of this ligand atom over the warp's 32 poses
+                float lo[3] = {lc.x, lc.y, lc.z}, hi[3] = {lc.x, lc.y, lc.z};
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
 #pragma unroll
-                        for (int d = 0; d < 3; d++) {
+                    for (int d = 0; d < 3; d++) {
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-                                hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-                            }
-                        }
-                        if ((lane & 7) == jj && real) {
-#pragma unroll
-                            for (int d = 0; d < 3; d++) { mlo[d] = lo[d]; mhi[d] = hi[d]; }
+                        for (int o = 16; o > 0; o >>= 1) {
+                            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+                            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
                         }
                     }
                 }
-            }
-            __syncwarp();
-
-            for (int g = 0; g < nb; g += 4) {
-                // lane-parallel cull test: lane (q, jj) = (lane>>3, lane&7) tests blob g+q against atom jj
-                unsigned near = 0xffffffffu;
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    const float4 blo = s_box[(g + (lane >> 3)) * 2], bhi = s_box[(g + (lane >> 3)) * 2 + 1];
-                    float gx = fmaxf(0.f, fmaxf(blo.x - mhi[0], mlo[0] - bhi.x));
-                    float gy = fmaxf(0.f, fmaxf(blo.y - mhi[1], mlo[1] - bhi.y));
-                    float gz = fmaxf(0.f, fmaxf(blo.z - mhi[2], mlo[2] - bhi.z));
-                    near = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f);
-                    if (near == 0u) continue;                 // warp-uniform
-                }
-#pragma unroll 1
-                for (int q = 0; q < 4; q++) {
-                    unsigned m = (near >> (8 * q)) & 0xffu;
-                    const int b = g + q;
-                    if (m == 0u || b >= nb) continue;          // warp-uniform
-                    if (STATS) n_eval += (unsigned long long)max(0, min(kBlob, a.n_atoms - (b0 + b) * kBlob)) * __popc(m);
-                    // the blob's 8 atoms go to registers once; every near ligand atom then runs 8
-                    // independent pair chains (ILP) behind a single warp-uniform loop branch
-                    float4 ra[kBlob];
-                    float2 rp[kBlob];
-#pragma unroll
-                    for (int i = 0; i < kBlob; i++) { ra[i] = s_xyzq[b * kBlob + i]; rp[i] = s_ab[b * kBlob + i]; }
-                    // software-pipelined loop over the near ligand atoms of this blob: the next atom's
-                    // coordinates/parameters are fetched while the current 8 pairs are computed
-                    int jj = __ffs(m) - 1;
-                    m &= m - 1;
-                    float4 lc = s_c[jj * TPB + tid];
-                    float4 lp = s_lparam[c * LJ + jj];
-#pragma unroll 1
-                    while (true) {
-                        float4 lc_n = lc, lp_n = lp;
-                        const bool more = m != 0u;
-                        if (more) {
-                            jj = __ffs(m) - 1;
-                            m &= m - 1;
-                            lc_n = s_c[jj * TPB + tid];
-                            lp_n = s_lparam[c * LJ + jj];
+                // two-level cull, then the near atoms are processed 8 at a time from a compacted list
+                int g_round = 0;
+                unsigned gm = 0u;                 // near groups of the current round of 32 groups
+                int n = 0;
+                bool groups_left = true;
+                while (groups_left || n > 0) {
+                    // ---- fill the list ----
+                    while (groups_left && n <= LIST_CAP - 32) {
+                        if (gm == 0u) {
+                            if (g_round * 32 >= nb) { groups_left = false; break; }
+                            const int g = g_round * 32 + lane;
+                            bool near = g < nb;
+                            if (VARIANT == MMO_VARIANT_SHIFTED && near) {
+                                // box-box distance between the group's box and the atom's warp box
+                                const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
+                                float gx = fmaxf(0.f, fmaxf(blo.x - hi[0], lo[0] - bhi.x));
+                                float gy = fmaxf(0.f, fmaxf(blo.y - hi[1], lo[1] - bhi.y));
+                                float gz = fmaxf(0.f, fmaxf(blo.z - hi[2], lo[2] - bhi.z));
+                                near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
+                            }
+                            gm = __ballot_sync(0xffffffffu, near);
+                            g_round++;
+                            if (gm == 0u) continue;
                         }
+                        const int g = (g_round - 1) * 32 + __ffs(gm) - 1;
+                        gm &= gm - 1u;
+                        const int atom = g * kBlob + lane;
+                        bool near2 = atom < n_real;
+                        if (VARIANT == MMO_VARIANT_SHIFTED && near2) near2 = box_dist2(s_xyzq[atom], lo, hi) < 144.0f;
+                        const unsigned bm = __ballot_sync(0xffffffffu, near2);
+                        if (near2) s_list[n + __popc(bm & lt_mask)] = (unsigned short)atom;
+                        n += __popc(bm);
+                    }
+                    if (n == 0) continue;
+                    // ---- process the list: 8 independent pair chains per step ----
+                    if (STATS) n_eval += (unsigned long long)n;
+                    const int n8 = (n + 7) & ~7;
+                    if (lane < n8 - n) s_list[n + lane] = (unsigned short)tile_atoms;     // pad with the dummy atom
+                    __syncwarp();
+#pragma unroll 1
+                    for (int k = 0; k < n8; k += 8) {
+                        const uint4 pk = *(const uint4 *)(s_list + k);
+                        const unsigned ix[4] = {pk.x, pk.y, pk.z, pk.w};
                         float f = 0.f;
 #pragma unroll
-                        for (int i = 0; i < kBlob; i++) {
-                            float dx = ra[i].x - lc.x, dy = ra[i].y - lc.y, dz = ra[i].z - lc.z;
-                            f = pair_energy<VARIANT>(dx, dy, dz, ra[i].w, rp[i].x, rp[i].y, lp.z, lp.x, lp.y, a.H, f);
+                        for (int i = 0; i < 8; i++) {
+                            const unsigned at = (ix[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            const float4 ra = s_xyzq[at];
+                            const float2 rp = s_ab[at];
+                            float dx = ra.x - lc.x, dy = ra.y - lc.y, dz = ra.z - lc.z;
+                            f = pair_energy<VARIANT>(dx, dy, dz, ra.w, rp.x, rp.y, lp.z, lp.x, lp.y, a.H, f);
                             if (STATS) {
                                 float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                                if (r2 < 144.0f && ra[i].x < 1e5f) n_in++;
+                                if (r2 < 144.0f && ra.x < 1e5f) n_in++;
                             }
                         }
                         acc += (double)f;
-                        if (!more) break;
-                        lc = lc_n; lp = lp_n;
                     }
+                    n = 0;
+                    __syncwarp();
                 }
             }
             __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
@@ -370,11 +390,10 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
 
     if (collect_stats) MMO_CUDA(cudaMemsetAsync(g_stats.p, 0, 4 * sizeof(unsigned long long), R.stream));
     const unsigned blocks = (unsigned)((n_poses + TPB - 1) / TPB);
-    // receptor tile: everything when it fits ~52 KB, so that 4 blocks stay resident per SM
-    int tile_blobs = std::min(rec->n_blobs, 256);
-    tile_blobs = std::max(4, (tile_blobs + 3) & ~3);
-    const size_t smem = ((size_t)tile_blobs * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast + (size_t)LJ * TPB) * sizeof(float4) +
-                        (size_t)tile_blobs * kBlob * sizeof(float2);
+    // receptor tile: everything when it fits (<= 64 groups = 2048 atoms), so that 2 blocks stay resident per SM
+    const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
+    const size_t smem = ((size_t)tile_blobs * kBlob + 1 + (size_t)tile_blobs * 2 + (size_t)lig->n_fast + (size_t)LJ * TPB) * sizeof(float4) +
+                        ((size_t)tile_blobs * kBlob + 2) * sizeof(float2) + (size_t)(TPB / 32) * LIST_CAP * sizeof(unsigned short) + 16;
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
         MMO_TRY(set_fast_smem(smem));

@@ -4,6 +4,7 @@
 //   SO3.ml:13-39, quat.ml:32-36, rot.ml:52-75,121-146, grid.ml:37-52
 #include "common.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace mmo {
 
@@ -79,9 +80,84 @@ double grid_node(double step, int dim, int i) {
     return (double)i * (span / (double)np);
 }
 
+// rot.ml:97-100
+static void rot_apply(const double *r, double x, double y, double z, double *o) {
+    o[0] = r[0] * x + r[1] * y + r[2] * z;
+    o[1] = r[3] * x + r[4] * y + r[5] * z;
+    o[2] = r[6] * x + r[7] * y + r[8] * z;
+}
+
+// Batteries A.favg restated as in the oracle (Kahan-compensated sum / n; library not vendored)
+static double favg(const std::vector<double> &a) {
+    double sum = 0.0, c = 0.0;
+    for (double v : a) { double y = v - c; double t = sum + y; c = (t - sum) - y; sum = t; }
+    return sum / (double)a.size();
+}
+
 }  // namespace mmo
 
 extern "C" {
+
+// Optim.apply_config centered_lig conf (src/optim.ml:64-80), the body of the place_ligand tool
+// (src/place_ligand.ml:55-59): rotate every rotatable bond by conf[6+b] (Mol.rotate_bond, src/mol.ml:610-631),
+// check the elongation (Mol.check_elongation_exn lig 12.0, src/mol.ml:576-591), then
+// Mol.rotate_then_translate_copy lig (Rot.r_xyz a b g) (x, y, z) (src/mol.ml:669-672).  Host code, libm.
+int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_config, double *out_xs, double *out_ys,
+                     double *out_zs, int32_t *too_long) {
+    MMO_REQUIRE(lig && config && out_xs && out_ys && out_zs, "mmo_apply_config: null argument");
+    MMO_REQUIRE(n_config == 6 || n_config == 6 + lig->n_rbonds, "mmo_apply_config: %d values for a ligand with %d rotatable bonds",
+                n_config, lig->n_rbonds);
+    const int L = lig->n;
+    std::vector<double> x(lig->hx), y(lig->hy), z(lig->hz);
+    double cen[3] = {0.0, 0.0, 0.0};       // centered_lig.center
+    for (int b = 0; b + 6 < n_config; b++) {
+        const int left = lig->rb_left[b], right = lig->rb_right[b];
+        const double cx = x[right], cy = y[right], cz = z[right];
+        const double ax = cx - x[left], ay = cy - y[left], az = cz - z[left];
+        const double mag = sqrt(ax * ax + ay * ay + az * az);
+        double rot[9];
+        mmo::rot_of_axis_angle(ax / mag, ay / mag, az / mag, config[6 + b], rot);
+        for (int g = lig->rg_off[b]; g < lig->rg_off[b + 1]; g++) {
+            const int i = lig->rg_idx[g];
+            double o[3];
+            mmo::rot_apply(rot, x[i] - cx, y[i] - cy, z[i] - cz, o);
+            x[i] = o[0] + cx; y[i] = o[1] + cy; z[i] = o[2] + cz;
+        }
+        cen[0] = mmo::favg(x); cen[1] = mmo::favg(y); cen[2] = mmo::favg(z);     // update_center
+    }
+    double maxi = 0.0;
+    for (int i = 0; i < L; i++) {
+        double dx = cen[0] - x[i], dy = cen[1] - y[i], dz = cen[2] - z[i];
+        maxi = std::max(maxi, 0.01 + sqrt(dx * dx + dy * dy + dz * dz));
+    }
+    if (too_long) *too_long = maxi > 12.0 ? 1 : 0;                                 // Mol.Too_long
+    double rot[9];
+    mmo::rot_r_xyz(config[3], config[4], config[5], rot);
+    for (int i = 0; i < L; i++) {
+        double o[3];
+        mmo::rot_apply(rot, x[i], y[i], z[i], o);
+        out_xs[i] = o[0] + config[0]; out_ys[i] = o[1] + config[1]; out_zs[i] = o[2] + config[2];
+    }
+    return MMO_OK;
+}
+
+// lig_rot_sample (src/lig_rot_sample.ml:23-45): n SO3-rotated copies of the ligand about its own centre:
+// Mol.center_rotate_translate_copy mol rot orig_center (src/mol.ml:705-710).  `center` = Mol.get_center mol.
+int mmo_rotated_copies(const mmo_ligand *lig, const double center[3], int32_t n, const double *rot9,
+                       double *out_xs, double *out_ys, double *out_zs) {
+    MMO_REQUIRE(lig && center && n >= 0 && (n == 0 || (rot9 && out_xs && out_ys && out_zs)), "mmo_rotated_copies: bad arguments");
+    const int L = lig->n;
+    const double nx = -center[0], ny = -center[1], nz = -center[2];      // Mol.center: translate_by (V3.neg mean)
+    for (int r = 0; r < n; r++)
+        for (int i = 0; i < L; i++) {
+            double o[3];
+            mmo::rot_apply(rot9 + 9 * (size_t)r, lig->hx[i] + nx, lig->hy[i] + ny, lig->hz[i] + nz, o);
+            out_xs[(size_t)r * L + i] = o[0] + center[0];
+            out_ys[(size_t)r * L + i] = o[1] + center[1];
+            out_zs[(size_t)r * L + i] = o[2] + center[2];
+        }
+    return MMO_OK;
+}
 
 int mmo_so3_rotations(int32_t n, double *rot9) {
     MMO_REQUIRE(n >= 0 && (n == 0 || rot9 != nullptr), "mmo_so3_rotations: bad arguments");

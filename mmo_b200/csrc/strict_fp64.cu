@@ -178,33 +178,44 @@ __global__ void strict_intra_kernel(int L, int n_pairs, const int32_t *__restric
 }
 
 // ---- grid build (mol.ml:964-989 per voxel, lds.ml:452-469 clamp + f32 store) ----------------------
-// one thread per (voxel, group of TG types); receptor atoms streamed through shared memory in index
-// order; r_ij and w are computed once per atom and reused by the TG types, as in the reference.
+// block = brick of 8x4x4 voxels, thread = (voxel, group of kTG types).  The block first filters the
+// receptor down to the atoms within 12 A of the brick (ordered compaction: the survivors keep their
+// index order, so every voxel still adds its neighbours in the reference's order), staging them in
+// shared memory tile by tile; r_ij and w are computed once per atom and reused by the kTG types, as
+// in the reference.  Atoms farther than 12 A from a voxel fail the exact `d <= 12` test exactly as
+// before, so the culling cannot change a single bit of the maps.
 constexpr int kTG = 12;
 constexpr int kGridTile = 256;
+constexpr int kBrickX = 8, kBrickY = 4, kBrickZ = 4;
 __global__ void __launch_bounds__(128)
 strict_grid_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
                    const double *__restrict__ pz, const double *__restrict__ pq,
                    const int32_t *__restrict__ pelt,
                    int dim0, int dim1, int dim2, double q0, double q1, double q2,
+                   int nbx, int nby,
                    const uint32_t *__restrict__ mask, int T, const int32_t *__restrict__ telt,
                    const double *__restrict__ tq, float *__restrict__ maps) {
     __shared__ double sx[kGridTile], sy[kGridTile], sz[kGridTile], sq[kGridTile];
     __shared__ int32_t se[kGridTile];
+    __shared__ int s_wcount[4];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t nvox = (size_t)dim0 * dim1 * dim2;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int brick = blockIdx.x;
+    const int bz = brick / (nbx * nby), by = (brick - bz * nbx * nby) / nbx, bx = brick - (bz * nby + by) * nbx;
+    const int i = bx * kBrickX + (tid & 7), j = by * kBrickY + ((tid >> 3) & 3), k = bz * kBrickZ + (tid >> 5);
+    const bool in_grid = i < dim0 && j < dim1 && k < dim2;
+    const size_t idx = (size_t)i + (size_t)j * dim0 + (size_t)k * dim0 * dim1;     // Grid.idx_of_ijk, grid.ml:98-99
+    bool active = in_grid;
+    if (active && mask) active = (mask[idx >> 5] >> (idx & 31)) & 1u;
+    if (!__syncthreads_or(active)) return;              // brick entirely outside the bitmask (lds.ml:485)
+    const double x = (double)i * q0, y = (double)j * q1, z = (double)k * q2;      // grid.xs.(i) etc.
+    // the brick's box (all its lattice nodes, clipped to the grid)
+    const double blo[3] = {(double)(bx * kBrickX) * q0, (double)(by * kBrickY) * q1, (double)(bz * kBrickZ) * q2};
+    const double bhi[3] = {(double)min(bx * kBrickX + kBrickX - 1, dim0 - 1) * q0,
+                           (double)min(by * kBrickY + kBrickY - 1, dim1 - 1) * q1,
+                           (double)min(bz * kBrickZ + kBrickZ - 1, dim2 - 1) * q2};
     const int t0 = blockIdx.y * kTG;
     const int nt = min(kTG, T - t0);
-    bool active = idx < nvox;
-    if (active && mask) active = (mask[idx >> 5] >> (idx & 31)) & 1u;
-    double x = 0.0, y = 0.0, z = 0.0;
-    if (idx < nvox) {     // Grid.ijk_of_idx, grid.ml:101-105
-        const int xy = dim0 * dim1;
-        int k = (int)(idx / xy);
-        int j = (int)((idx - (size_t)k * xy) / dim0);
-        int i = (int)(idx - ((size_t)k * xy + (size_t)j * dim0));
-        x = (double)i * q0; y = (double)j * q1; z = (double)k * q2;
-    }
     double se_acc[kTG], sv_acc[kTG], tqv[kTG];
     int te[kTG];
 #pragma unroll
@@ -213,33 +224,57 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
         tqv[l] = (l < nt) ? tq[t0 + l] : 0.0;
         te[l] = (l < nt) ? telt[t0 + l] * kEltTab : 0;
     }
-    for (int base = 0; base < P; base += kGridTile) {
-        __syncthreads();
-        for (int k = threadIdx.x; k < kGridTile; k += blockDim.x) {
-            int i = base + k;
-            if (i < P) { sx[k] = px[i]; sy[k] = py[i]; sz[k] = pz[i]; sq[k] = pq[i]; se[k] = pelt[i]; }
+    int count = 0;                                       // candidates staged in shared memory (block-uniform)
+    for (int base = 0; base < P || count > 0; base += 128) {
+        // ---- ordered compaction of the next 128 atoms into the tile ----
+        if (base < P) {
+            const int a = base + tid;
+            bool near = false;
+            double ax = 0.0, ay = 0.0, az = 0.0;
+            if (a < P) {
+                ax = px[a]; ay = py[a]; az = pz[a];
+                const double gx = fmax(0.0, fmax(blo[0] - ax, ax - bhi[0]));
+                const double gy = fmax(0.0, fmax(blo[1] - ay, ay - bhi[1]));
+                const double gz = fmax(0.0, fmax(blo[2] - az, az - bhi[2]));
+                near = gx * gx + gy * gy + gz * gz <= 144.0 + 1e-6;     // superset of "within 12 A of some voxel"
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, near);
+            if (lane == 0) s_wcount[wid] = __popc(bm);
+            __syncthreads();
+            int off = count;
+            for (int w = 0; w < wid; w++) off += s_wcount[w];
+            const int total = s_wcount[0] + s_wcount[1] + s_wcount[2] + s_wcount[3];
+            if (near) {
+                const int pos = off + __popc(bm & ((1u << lane) - 1u));
+                sx[pos] = ax; sy[pos] = ay; sz[pos] = az; sq[pos] = pq[a]; se[pos] = pelt[a];
+            }
+            count += total;
+            __syncthreads();
+            if (count <= kGridTile - 128 && base + 128 < P) continue;      // room for another batch
         }
-        __syncthreads();
-        if (!active) continue;
-        const int lim = min(kGridTile, P - base);
-        for (int k = 0; k < lim; k++) {
-            double d = sqrt(d_dist2(sx[k], sy[k], sz[k], x, y, z));
-            if (d <= 12.0) {
-                const double q_i = sq[k];
-                const double r = d_nzd(d);
-                const double w = d_shift(r);
-                const int ei = se[k];
+        // ---- every voxel of the brick visits the staged atoms in order ----
+        if (active) {
+            for (int c = 0; c < count; c++) {
+                double d = sqrt(d_dist2(sx[c], sy[c], sz[c], x, y, z));
+                if (d <= 12.0) {
+                    const double q_i = sq[c];
+                    const double r = d_nzd(d);
+                    const double w = d_shift(r);
+                    const int ei = se[c];
 #pragma unroll
-                for (int l = 0; l < kTG; l++) {
-                    if (l < nt) {
-                        int t = te[l] + ei;       // UFF.vdW_xiDi (get_anum lig 0) prot_anum
-                        double p6 = d_pow6(c_xij[t] / r);
-                        se_acc[l] = se_acc[l] + w * ((q_i * tqv[l]) / r);
-                        sv_acc[l] = sv_acc[l] + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                    for (int l = 0; l < kTG; l++) {
+                        if (l < nt) {
+                            int t = te[l] + ei;       // UFF.vdW_xiDi (get_anum lig 0) prot_anum
+                            double p6 = d_pow6(c_xij[t] / r);
+                            se_acc[l] = se_acc[l] + w * ((q_i * tqv[l]) / r);
+                            sv_acc[l] = sv_acc[l] + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                        }
                     }
                 }
             }
         }
+        count = 0;
+        __syncthreads();
     }
     if (!active) return;
 #pragma unroll
@@ -356,11 +391,13 @@ int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t
                       const int32_t *d_type_elt, const double *d_type_q) {
     MMO_TRY(ensure_tables());
     GridGeom G = geom_of(g);
-    dim3 grid((unsigned)((g->nvox + 127) / 128), (unsigned)((g->T + kTG - 1) / kTG));
+    const int nbx = (g->dims[0] + kBrickX - 1) / kBrickX, nby = (g->dims[1] + kBrickY - 1) / kBrickY,
+              nbz = (g->dims[2] + kBrickZ - 1) / kBrickZ;
+    dim3 grid((unsigned)(nbx * nby * nbz), (unsigned)((g->T + kTG - 1) / kTG));
     KernelScope ks(K_GRID_BUILD);
     strict_grid_kernel<<<grid, 128, 0, rt().stream>>>(rec->n, rec->x.p, rec->y.p, rec->z.p, rec->q.p, rec->elt.p,
                                                       g->dims[0], g->dims[1], g->dims[2], G.q[0], G.q[1], G.q[2],
-                                                      d_mask_words, g->T, d_type_elt, d_type_q, g->maps.p);
+                                                      nbx, nby, d_mask_words, g->T, d_type_elt, d_type_q, g->maps.p);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }

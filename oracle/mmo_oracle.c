@@ -530,6 +530,27 @@ double orc_radius(int L, const double *x, const double *y, const double *z, cons
     return maxi;
 }
 
+/* src/optim.ml:64-80 apply_config: rotate bonds (libm), elongation check, r_xyz rotation, translation.
+ * lx/ly/lz = centred ligand (center = origin); returns 1 when Mol.Too_long would be raised */
+int orc_apply_config(int L, const double *lx, const double *ly, const double *lz,
+                     int n_rbonds, const int32_t *rb_left, const int32_t *rb_right,
+                     const int32_t *rg_off, const int32_t *rg_idx,
+                     const double *config, int n_config, double *ox, double *oy, double *oz) {
+    double *x = (double *)malloc(sizeof(double) * 3 * (size_t)L), *y = x + L, *z = y + L;
+    memcpy(x, lx, sizeof(double) * L); memcpy(y, ly, sizeof(double) * L); memcpy(z, lz, sizeof(double) * L);
+    double cen[3] = {0.0, 0.0, 0.0};
+    for (int b = 0; b + 6 < n_config && b < n_rbonds; b++) {
+        orc_rotate_bond(x, y, z, rb_left[b], rb_right[b], rg_off[b + 1] - rg_off[b], rg_idx + rg_off[b], config[6 + b]);
+        cen[0] = orc_favg(L, x); cen[1] = orc_favg(L, y); cen[2] = orc_favg(L, z);      /* update_center */
+    }
+    int too_long = orc_radius(L, x, y, z, cen) > 12.0;
+    double rot[9];
+    orc_rot_r_xyz(config[3], config[4], config[5], rot);
+    orc_rotate_then_translate(L, x, y, z, rot, config, ox, oy, oz);
+    free(x);
+    return too_long;
+}
+
 /* ------------------------------------------------------------------------ */
 /* exhaustive rigid scan: src/lds.ml:1040-1114 */
 static double scan_score_pose(const orc_scan_args *a, const double *x, const double *y, const double *z) {

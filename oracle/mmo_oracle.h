@@ -118,6 +118,11 @@ void orc_rotate_bond(double *x, double *y, double *z, int left, int right,
                      int ngroup, const int32_t *group, double alpha);
 double orc_radius(int L, const double *x, const double *y, const double *z, const double center[3]); /* mol.ml:576-583 */
 
+int orc_apply_config(int L, const double *lx, const double *ly, const double *lz,
+                     int n_rbonds, const int32_t *rb_left, const int32_t *rb_right,
+                     const int32_t *rg_off, const int32_t *rg_idx,
+                     const double *config, int n_config, double *ox, double *oy, double *oz);   /* optim.ml:64-80 */
+
 /* ---- exhaustive rigid scan, lds.ml:1040-1114 ---- */
 typedef struct {
     int P; const double *px, *py, *pz, *pq; const int32_t *panum;           /* receptor */

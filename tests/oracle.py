@@ -386,3 +386,14 @@ def mc_run(lig, cx, cy, cz, roi, n_steps, seed, rot0, pos0, maps=None, g_step=0.
     res = {f: getattr(R, f) for f, _ in McResult._fields_ if f not in ("best_rot", "best_pos")}
     res["best_rot"] = np.array(R.best_rot); res["best_pos"] = np.array(R.best_pos)
     return res, xyz, trace[:R.frames_done]
+
+
+def apply_config(lig, cx, cy, cz, config):
+    off, idx = lig.rgroup_csr()
+    L = lig.n
+    ox = np.empty(L); oy = np.empty(L); oz = np.empty(L)
+    cfg = np.ascontiguousarray(config, np.float64)
+    tl = lib().orc_apply_config(C.c_int(L), d(cx)[1], d(cy)[1], d(cz)[1], C.c_int(lig.n_rbonds), i32(lig.rb_left)[1],
+                                i32(lig.rb_right)[1], i32(off)[1], i32(idx)[1], cfg.ctypes.data_as(_dp), C.c_int(len(cfg)),
+                                ox.ctypes.data_as(_dp), oy.ctypes.data_as(_dp), oz.ctypes.data_as(_dp))
+    return ox, oy, oz, bool(tl)

@@ -134,3 +134,34 @@ def test_linearity_in_receptor_charges(gpu, c2, c2_roi_rec):
         rec = gpu.Receptor(m.xs, m.ys, m.zs, m.q * s, m.anum)
         e.append(gpu.Mol.score_poses(rec, lig, R, t, prec=gpu.PREC_FP64))
     assert np.allclose(e[2] - e[1], e[1] - e[0], rtol=1e-9, atol=1e-7 * np.abs(e[1]).max())
+
+
+def test_pose_tools_bit_identical(gpu, orc, c2):
+    """place_ligand (Optim.apply_config, optim.ml:64-80) and lig_rot_sample (lig_rot_sample.ml:23-45)"""
+    m = c2["lig"]
+    lig = gpu.Ligand.from_mol(m, centered=True)
+    rng = np.random.default_rng(77)
+    for with_bonds in (False, True):
+        cfg = list(rng.uniform(30, 60, 3)) + list(rng.uniform(-3, 3, 3))
+        if with_bonds:
+            cfg += list(rng.uniform(-3.1, 3.1, m.n_rbonds))
+        x, y, z, tl = gpu.Optim.apply_config(lig, cfg)
+        wx, wy, wz, wtl = orc.apply_config(m, lig.xs, lig.ys, lig.zs, cfg)
+        assert np.array_equal(x, wx) and np.array_equal(y, wy) and np.array_equal(z, wz) and tl == wtl
+    # rotated copies about the original centre of the (uncentred) ligand
+    raw = gpu.Ligand.from_mol(m, centered=False)
+    center = [orc.favg(m.xs), orc.favg(m.ys), orc.favg(m.zs)]
+    rot = gpu.SO3.rotations(25)
+    X, Y, Z = gpu.Optim.rotated_copies(raw, center, rot)
+    for r in (0, 7, 24):
+        ox = np.empty(m.n); oy = np.empty(m.n); oz = np.empty(m.n)
+        import ctypes as C
+        dp = C.POINTER(C.c_double)
+        orc.lib().orc_center_rotate_translate(C.c_int(m.n), orc.d(m.xs)[1], orc.d(m.ys)[1], orc.d(m.zs)[1],
+                                              orc.d(center)[1], orc.d(rot[r])[1], orc.d(center)[1],
+                                              ox.ctypes.data_as(dp), oy.ctypes.data_as(dp), oz.ctypes.data_as(dp))
+        assert np.array_equal(X[r], ox) and np.array_equal(Y[r], oy) and np.array_equal(Z[r], oz)
+    # the rotated copies keep every inter-atomic distance (rigid motion)
+    d0 = np.hypot(np.hypot(m.xs[0] - m.xs[5], m.ys[0] - m.ys[5]), m.zs[0] - m.zs[5])
+    d1 = np.hypot(np.hypot(X[:, 0] - X[:, 5], Y[:, 0] - Y[:, 5]), Z[:, 0] - Z[:, 5])
+    assert np.allclose(d1, d0, rtol=1e-13)
