@@ -55,6 +55,13 @@ inline void count_launch(int n = 1) { rt().launches += n; }
 #define MMO_LAUNCH_CHECK()                                                    \
     do { mmo::count_launch(); MMO_CUDA(cudaGetLastError()); } while (0)
 
+// Device allocations go through a small caching pool (runtime.cu): the one-shot entry points
+// (mmo_scan, mmo_score_*) allocate and free the same buffer sizes on every call, and cudaMalloc/cudaFree
+// cost more than the kernels of a small batch.
+int pool_alloc(void **p, size_t bytes);
+void pool_free(void *p);
+void pool_trim();
+
 // simple owning device buffer
 template <typename T>
 struct DevBuf {
@@ -64,11 +71,11 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) pool_free(p); p = nullptr; n = 0; }
     int alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        MMO_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        MMO_TRY(pool_alloc((void **)&p, count * sizeof(T)));
         n = count;
         return MMO_OK;
     }
@@ -112,6 +119,7 @@ struct mmo_receptor {
     mmo::DevBuf<double> x, y, z, q;
     mmo::DevBuf<int32_t> elt;        // compact element index
     mmo::DevBuf<double4> xyzq64;     // {x, y, z, q} packed for the close-contact pass
+    mmo::DevBuf<float4> xyz32v;      // positions relative to vox_lo, fp32 (pre-test of the close-contact pass)
     // blob order, fp32 (fast kernel): xyzq = {x-ox, y-oy, z-oz, EW*q}; ab = {A_i, B_i}
     mmo::DevBuf<float4> xyzq;
     mmo::DevBuf<float2> ab;

@@ -25,7 +25,7 @@ namespace mmo {
 
 constexpr int LJ = 8;            // ligand atoms per chunk (= one k-d leaf of the ligand)
 constexpr int TPB = 256;         // poses per block
-constexpr int LIST_CAP = 256;    // per-warp list of near receptor atoms (uint16 tile indices)
+constexpr int LIST_CAP = 384;    // per-warp list of near receptor atoms (shared-memory addresses)
 constexpr int MAX_TILE_GROUPS = 64;
 static_assert(kBlob == 32, "one receptor group per warp-wide test");
 
@@ -82,20 +82,21 @@ __device__ __forceinline__ float box_dist2(const float4 p, const float *lo, cons
     return fmaf(gz, gz, fmaf(gy, gy, gx * gx));
 }
 
-// Shared memory (dynamic): receptor tile {xyzq[tile_atoms+1], gbox[2*tile_groups], lparam[n_fast],
-// chunk coordinates [LJ][TPB], ab[tile_atoms+2], per-warp near lists}.  Slot tile_atoms is a dummy atom
-// (far away, no charge, no vdW) used to pad a list to a multiple of 8.
+// Shared memory (dynamic): receptor tile as an array of 32-byte atoms {x, y, z, 83.0159*q | A, B, 0, 0}
+// [tile_atoms + 1], group boxes [2*tile_groups], ligand parameters [n_fast], chunk coordinates [LJ][TPB],
+// per-warp near lists (shared-memory byte addresses of the atoms, so that the pair loop needs no index
+// arithmetic).  Slot tile_atoms is a dummy atom (far away, no charge, no vdW) that pads a list to 8.
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(TPB, 2)
 direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, double *__restrict__ out) {
     extern __shared__ float4 smem4[];
     const int tile_atoms = tile_groups * kBlob;
-    float4 *s_xyzq = smem4;                                   // tile_atoms + 1
-    float4 *s_box = s_xyzq + tile_atoms + 1;                  // tile_groups * 2
+    float4 *s_atom = smem4;                                   // 2 * (tile_atoms + 1)
+    float4 *s_box = s_atom + 2 * (tile_atoms + 1);            // tile_groups * 2
     float4 *s_lparam = s_box + tile_groups * 2;               // n_fast
     float4 *s_c = s_lparam + a.n_fast;                        // LJ * TPB : {x, y, z, -} of chunk atom jj, pose tid
-    float2 *s_ab = (float2 *)(s_c + LJ * TPB);                // tile_atoms + 2
-    unsigned short *s_list = (unsigned short *)(s_ab + tile_atoms + 2) + (threadIdx.x >> 5) * LIST_CAP;
+    unsigned *s_list = (unsigned *)(s_c + LJ * TPB) + (threadIdx.x >> 5) * LIST_CAP;
+    const unsigned atom_base = (unsigned)__cvta_generic_to_shared(s_atom);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -117,10 +118,14 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
         const int nb = min(tile_groups, a.n_blobs - b0);
         const int n_real = min(nb * kBlob, a.n_atoms - b0 * kBlob);      // real atoms in this tile
         for (int k = tid; k < nb * kBlob; k += TPB) {
-            s_xyzq[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
-            s_ab[k] = __ldg(a.ab + (size_t)b0 * kBlob + k);
+            const float2 ab = __ldg(a.ab + (size_t)b0 * kBlob + k);
+            s_atom[2 * k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+            s_atom[2 * k + 1] = make_float4(ab.x, ab.y, 0.f, 0.f);
         }
-        if (tid == 0) { s_xyzq[tile_atoms] = make_float4(1e6f, 1e6f, 1e6f, 0.f); s_ab[tile_atoms] = make_float2(0.f, 0.f); }
+        if (tid == 0) {
+            s_atom[2 * tile_atoms] = make_float4(1e6f, 1e6f, 1e6f, 0.f);
+            s_atom[2 * tile_atoms + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
         __syncthreads();
 
@@ -166,55 +171,67 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                         }
                     }
                 }
-                // two-level cull, then the near atoms are processed 8 at a time from a compacted list
-                int g_round = 0;
-                unsigned gm = 0u;                 // near groups of the current round of 32 groups
-                int n = 0;
-                bool groups_left = true;
-                while (groups_left || n > 0) {
-                    // ---- fill the list ----
-                    while (groups_left && n <= LIST_CAP - 32) {
-                        if (gm == 0u) {
-                            if (g_round * 32 >= nb) { groups_left = false; break; }
-                            const int g = g_round * 32 + lane;
-                            bool near = g < nb;
-                            if (VARIANT == MMO_VARIANT_SHIFTED && near) {
-                                // box-box distance between the group's box and the atom's warp box
-                                const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
-                                float gx = fmaxf(0.f, fmaxf(blo.x - hi[0], lo[0] - bhi.x));
-                                float gy = fmaxf(0.f, fmaxf(blo.y - hi[1], lo[1] - bhi.y));
-                                float gz = fmaxf(0.f, fmaxf(blo.z - hi[2], lo[2] - bhi.z));
-                                near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
-                            }
-                            gm = __ballot_sync(0xffffffffu, near);
-                            g_round++;
-                            if (gm == 0u) continue;
+                // ---- level 1: which groups of 32 receptor atoms can be within 12 A of this atom? ----
+                unsigned gm0 = 0xffffffffu, gm1 = 0xffffffffu;      // near masks of groups 0-31 / 32-63
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int g = r * 32 + lane;
+                        bool near = false;
+                        if (g < nb) {
+                            const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
+                            float gx = fmaxf(0.f, fmaxf(blo.x - hi[0], lo[0] - bhi.x));
+                            float gy = fmaxf(0.f, fmaxf(blo.y - hi[1], lo[1] - bhi.y));
+                            float gz = fmaxf(0.f, fmaxf(blo.z - hi[2], lo[2] - bhi.z));
+                            near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
                         }
-                        const int g = (g_round - 1) * 32 + __ffs(gm) - 1;
-                        gm &= gm - 1u;
-                        const int atom = g * kBlob + lane;
-                        bool near2 = atom < n_real;
-                        if (VARIANT == MMO_VARIANT_SHIFTED && near2) near2 = box_dist2(s_xyzq[atom], lo, hi) < 144.0f;
-                        const unsigned bm = __ballot_sync(0xffffffffu, near2);
-                        if (near2) s_list[n + __popc(bm & lt_mask)] = (unsigned short)atom;
-                        n += __popc(bm);
+                        const unsigned m = __ballot_sync(0xffffffffu, near);
+                        if (r == 0) gm0 = m; else gm1 = m;
+                    }
+                }
+                // ---- level 2: per-atom test, 4 groups per step (independent loads and tests), survivors
+                //      compacted into the warp's list; the list is consumed 8 atoms at a time ----
+                int n = 0;
+                for (int g4 = 0; g4 < nb || n > 0; g4 += 4) {
+                    if (g4 < nb) {
+                        const unsigned m4 = ((g4 < 32 ? gm0 : gm1) >> (g4 & 31)) & 0xfu;
+                        if (m4 != 0u) {
+                            bool nr[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int atom = (g4 + u) * kBlob + lane;
+                                nr[u] = ((m4 >> u) & 1u) && atom < n_real;
+                                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                                    // (out-of-tile slots are never read: clamp the address, keep the predicate)
+                                    const float4 pa = s_atom[2 * min(atom, tile_atoms)];
+                                    nr[u] = nr[u] && box_dist2(pa, lo, hi) < 144.0f;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const unsigned bm = __ballot_sync(0xffffffffu, nr[u]);
+                                if (nr[u]) s_list[n + __popc(bm & lt_mask)] = atom_base + (unsigned)((g4 + u) * kBlob + lane) * 32u;
+                                n += __popc(bm);
+                            }
+                        }
+                        if (n <= LIST_CAP - 128 && g4 + 4 < nb) continue;       // room for 4 more groups
                     }
                     if (n == 0) continue;
                     // ---- process the list: 8 independent pair chains per step ----
                     if (STATS) n_eval += (unsigned long long)n;
                     const int n8 = (n + 7) & ~7;
-                    if (lane < n8 - n) s_list[n + lane] = (unsigned short)tile_atoms;     // pad with the dummy atom
+                    if (lane < n8 - n) s_list[n + lane] = atom_base + (unsigned)tile_atoms * 32u;     // pad with the dummy atom
                     __syncwarp();
 #pragma unroll 1
                     for (int k = 0; k < n8; k += 8) {
-                        const uint4 pk = *(const uint4 *)(s_list + k);
-                        const unsigned ix[4] = {pk.x, pk.y, pk.z, pk.w};
+                        const uint4 pk0 = *(const uint4 *)(s_list + k), pk1 = *(const uint4 *)(s_list + k + 4);
+                        const unsigned ad[8] = {pk0.x, pk0.y, pk0.z, pk0.w, pk1.x, pk1.y, pk1.z, pk1.w};
                         float f = 0.f;
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            const unsigned at = (ix[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                            const float4 ra = s_xyzq[at];
-                            const float2 rp = s_ab[at];
+                            float4 ra, rp;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ra.x), "=f"(ra.y), "=f"(ra.z), "=f"(ra.w) : "r"(ad[i]));
+                            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16];" : "=f"(rp.x), "=f"(rp.y) : "r"(ad[i]));
                             float dx = ra.x - lc.x, dy = ra.y - lc.y, dz = ra.z - lc.z;
                             f = pair_energy<VARIANT>(dx, dy, dz, ra.w, rp.x, rp.y, lp.z, lp.x, lp.y, a.H, f);
                             if (STATS) {
@@ -245,6 +262,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
 // accurate to ~1e-12 relative, not bit-identical (MMO_PREC_FP64 is the bit-identical mode).
 struct FixArgs {
     const double4 *pxyzq;                // receptor {x, y, z, q}, original order
+    const float4 *pxyz32;                // the same positions in fp32, relative to vox_lo (pre-test only)
     const int32_t *pelt;
     double vox_lo[3], vox_inv;
     int vox_dim[3];
@@ -283,8 +301,14 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ ou
         if (k0 == k1) continue;
         const double qj = kElecWeight * __ldg(a.lq + j);
         const int ej = __ldg(a.lelt + j);
+        const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
+        const float Hf = (float)a.H + 0.5f;
         for (int k = k0; k < k1; k++) {
             const int i = __ldg(a.vox_idx + k);
+            // cheap fp32 pre-test (coordinates relative to the voxel grid corner, error << the 0.5 A^2 margin)
+            const float4 rf = __ldg(a.pxyz32 + i);
+            const float fdx = rf.x - xf, fdy = rf.y - yf, fdz = rf.z - zf;
+            if (fdx * fdx + fdy * fdy + fdz * fdz >= Hf) continue;
             const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
             const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
             const double4 ra = make_double4(r01.x, r01.y, r23.x, r23.y);
@@ -377,7 +401,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     fa.H = H;
     fa.stats = g_stats.p;
     FixArgs xa;
-    xa.pxyzq = rec->xyzq64.p; xa.pelt = rec->elt.p;
+    xa.pxyzq = rec->xyzq64.p; xa.pxyz32 = rec->xyz32v.p; xa.pelt = rec->elt.p;
     for (int d = 0; d < 3; d++) { xa.vox_lo[d] = rec->vox_lo[d]; xa.vox_dim[d] = rec->vox_dim[d]; }
     xa.vox_inv = 1.0 / rec->vox_edge;
     xa.vox_off = rec->vox_off.p; xa.vox_idx = rec->vox_idx.p;
@@ -392,8 +416,8 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     const unsigned blocks = (unsigned)((n_poses + TPB - 1) / TPB);
     // receptor tile: everything when it fits (<= 64 groups = 2048 atoms), so that 2 blocks stay resident per SM
     const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
-    const size_t smem = ((size_t)tile_blobs * kBlob + 1 + (size_t)tile_blobs * 2 + (size_t)lig->n_fast + (size_t)LJ * TPB) * sizeof(float4) +
-                        ((size_t)tile_blobs * kBlob + 2) * sizeof(float2) + (size_t)(TPB / 32) * LIST_CAP * sizeof(unsigned short) + 16;
+    const size_t smem = (2 * ((size_t)tile_blobs * kBlob + 1) + (size_t)tile_blobs * 2 + (size_t)lig->n_fast + (size_t)LJ * TPB) * sizeof(float4) +
+                        (size_t)(TPB / 32) * LIST_CAP * sizeof(unsigned) + 16;
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
         MMO_TRY(set_fast_smem(smem));

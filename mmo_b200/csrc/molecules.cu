@@ -130,6 +130,13 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     }
 
     // ---- close-contact voxel lists: atoms within r_list of any point of the voxel (conservative)
+    // 1 A voxels (fewer candidates per lookup) while the table stays small, 2 A otherwise
+    {
+        const double rl = sqrt(std::max(r->x_max, 1.0) * 4.5 / kTau);
+        double vol = 1.0;
+        for (int d = 0; d < 3; d++) vol *= (hi[d] - lo[d] + 2.0 * rl);
+        r->vox_edge = (n > 0 && vol <= 2.0e6) ? 1.0 : 2.0;
+    }
     const double g = r->vox_edge;
     const double r_list = sqrt(std::max(r->x_max, 1.0) * 4.5 / kTau);    // 4.5 = largest x_i of src/UFF.ml:22
     const double reach = r_list + 0.5 * g * sqrt(3.0);
@@ -166,6 +173,11 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     int rc = MMO_OK;
     do {
         if ((rc = r->xyzq64.upload(xyzq64))) break;
+        {
+            std::vector<float4> v32(std::max(1, n));
+            for (int i = 0; i < n; i++) v32[i] = make_float4((float)(xs[i] - r->vox_lo[0]), (float)(ys[i] - r->vox_lo[1]), (float)(zs[i] - r->vox_lo[2]), 0.f);
+            if ((rc = r->xyz32v.upload(v32))) break;
+        }
         if ((rc = r->x.upload(r->hx)) || (rc = r->y.upload(r->hy)) || (rc = r->z.upload(r->hz)) ||
             (rc = r->q.upload(r->hq)) || (rc = r->elt.upload(elt)) || (rc = r->xyzq.upload(xyzq)) ||
             (rc = r->ab.upload(ab)) || (rc = r->blob_box.upload(box)) || (rc = r->vox_off.upload(cnt)) ||

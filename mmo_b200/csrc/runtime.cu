@@ -63,6 +63,63 @@ KernelScope::~KernelScope() {
     }
 }
 
+// ---- caching device allocator ------------------------------------------------------------------------
+struct PoolBlock { void *p; size_t bytes; };
+static std::vector<PoolBlock> g_pool_free;          // cached, not in use
+static std::vector<PoolBlock> g_pool_live;          // handed out
+static size_t g_pool_cached = 0;
+static const size_t kPoolMaxCached = (size_t)2 << 30;
+
+int pool_alloc(void **out, size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    int best = -1;
+    for (int i = 0; i < (int)g_pool_free.size(); i++)
+        if (g_pool_free[i].bytes >= bytes && g_pool_free[i].bytes <= 2 * bytes + 4096 &&
+            (best < 0 || g_pool_free[i].bytes < g_pool_free[best].bytes))
+            best = i;
+    if (best >= 0) {
+        PoolBlock b = g_pool_free[best];
+        g_pool_free.erase(g_pool_free.begin() + best);
+        g_pool_cached -= b.bytes;
+        g_pool_live.push_back(b);
+        *out = b.p;
+        return MMO_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {           // give the cache back to the driver and retry once
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    g_pool_live.push_back({p, bytes});
+    *out = p;
+    return MMO_OK;
+}
+void pool_free(void *p) {
+    for (size_t i = 0; i < g_pool_live.size(); i++)
+        if (g_pool_live[i].p == p) {
+            PoolBlock b = g_pool_live[i];
+            g_pool_live.erase(g_pool_live.begin() + i);
+            if (rt().ready && g_pool_cached + b.bytes <= kPoolMaxCached) {
+                // work queued on the library stream may still use the block: the pool is only handed
+                // out again to work on the same stream, which is ordered after it
+                g_pool_free.push_back(b);
+                g_pool_cached += b.bytes;
+            } else {
+                cudaFree(b.p);
+            }
+            return;
+        }
+    cudaFree(p);     // not ours (e.g. allocated before a re-init)
+}
+void pool_trim() {
+    for (auto &b : g_pool_free) cudaFree(b.p);
+    g_pool_free.clear();
+    g_pool_cached = 0;
+}
+
 int require_ready() {
     if (!rt().ready) {
         set_error("mmo_init() has not been called (or failed): there is no CPU fallback");
@@ -175,6 +232,7 @@ int mmo_shutdown(void) {
     Runtime &R = rt();
     if (!R.ready) return MMO_OK;
     cudaStreamSynchronize(R.stream);
+    pool_trim();
     if (R.l2_scratch) cudaFree(R.l2_scratch);
     R.l2_scratch = nullptr;
     R.l2_scratch_bytes = 0;
