@@ -255,7 +255,9 @@ int mmo_topk_allgather_merge(int32_t k, int32_t n_local, const double *scores, c
 /* Lds.simulate_lig frame loop (src/lds.ml:882-995) for n_chains independent chains in one launch:
  * alternating rigid-body (Move.rand_rot / rand_trans, src/move.ml:20-54) and conformer moves
  * (Mol.tweak_rbond / flip_rbond / rotate_bond, src/mol.ml:610-647), interpolated E_inter
- * (src/mol.ml:1012-1020), E_intra = Mol.ene_intra_UFFNB_brute when intra_nb, Metropolis at
+ * (src/mol.ml:1012-1020; give `grid`, rec = NULL) or direct shifted E_inter (--no-interp, src/mol.ml:822-849;
+ * give `rec`, grid = NULL; fp64 pair terms, lane-strided summation: ~1e-13 relative to the reference order),
+ * E_intra = Mol.ene_intra_UFFNB_brute when intra_nb, Metropolis at
  * beta = 1/(kB*T) (lds.ml:66-75, 931-934), acceptance windows (src/SW.ml) and adaptive step sizes
  * (lds.ml:586-621).  The reference's behaviours D1-D6/D14 of SURVEY Appendix D are mirrored
  * (in particular: nothing is accepted or rejected unless hard_roi is set).  The random stream and
@@ -280,7 +282,7 @@ typedef struct {
 } mmo_mc_result;
 /* start_rot9 / start_pos3: per chain (lds.ml:2034-2047); best_xyz: n_chains x 3 x L (x.. y.. z..),
  * may be NULL; trace_chain0: n_steps x {curr_E, E_inter, E_intra, accepted(-1 = no test)}, may be NULL */
-int mmo_mc_run(const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
+int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
                int64_t n_chains, const uint64_t *seeds, const double *start_rot9,
                const double *start_pos3, mmo_mc_result *results, double *best_xyz,
                double *trace_chain0);

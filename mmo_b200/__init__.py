@@ -429,7 +429,7 @@ class Lds:
 
     @staticmethod
     def simulate_lig(grid, lig, roi, n_steps, seeds, start_rot9, start_pos3, tweak_rbonds=True, hard_roi=True,
-                     no_flip=False, intra_nb=True, temperature_K=293.15, want_xyz=False, want_trace=False):
+                     no_flip=False, intra_nb=True, temperature_K=293.15, want_xyz=False, want_trace=False, rec=None):
         """src/lds.ml:741-1000 frame loop for len(seeds) independent chains in one launch."""
         _need_init()
         seeds = np.ascontiguousarray(seeds, np.uint64)
@@ -443,7 +443,7 @@ class Lds:
         res = (McResult * n)()
         xyz = np.empty((n, 3, lig.n)) if want_xyz else None
         trace = np.empty((n_steps, 4)) if want_trace else None
-        _ck(lib().mmo_mc_run(grid.h, lig.h, C.byref(P), C.c_int64(n), seeds.ctypes.data_as(C.POINTER(C.c_uint64)),
+        _ck(lib().mmo_mc_run(rec.h if rec is not None else None, grid.h if grid is not None else None, lig.h, C.byref(P), C.c_int64(n), seeds.ctypes.data_as(C.POINTER(C.c_uint64)),
                              rot.ctypes.data_as(_dp), pos.ctypes.data_as(_dp), res,
                              xyz.ctypes.data_as(_dp) if want_xyz else C.cast(None, _dp),
                              trace.ctypes.data_as(_dp) if want_trace else C.cast(None, _dp)))

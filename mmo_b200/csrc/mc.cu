@@ -17,6 +17,7 @@
 #include "strict_dev.cuh"
 #include "../../include/mmo_detmath.h"
 #include <math.h>
+#include <string.h>
 
 namespace mmo {
 
@@ -51,9 +52,13 @@ struct McArgs {
     const int32_t *pair_i, *pair_j;
     int n_rbonds;
     const int32_t *rb_left, *rb_right, *rg_off, *rg_idx;
-    // interpolated scorer
+    // interpolated scorer (maps != nullptr) ...
     GridGeom g;
     const float *maps;
+    // ... or direct shifted scorer over the receptor atoms
+    int P;
+    const double4 *pxyzq;
+    const int32_t *pelt;
     // UFF tables (kEltTab^2)
     const double *xij, *dij;
     double roi_c[3], roi_r;
@@ -151,6 +156,60 @@ __device__ double interp_energy(const McArgs &a, const double *x, const double *
     return res;
 }
 
+// Mol.ene_inter_UFF_shifted_brute (mol.ml:822-849) for one chain: receptor atoms are dealt to the lanes,
+// every pair term is computed with the reference's own operations (sqrt, divisions, no FMA); the 32
+// per-lane partial sums are then added in lane order.  Only the summation order differs from the
+// reference (receptor-outer/ligand-inner over ALL atoms), i.e. the value agrees to ~1e-13 relative.
+__device__ double direct_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
+                                double2 *terms) {
+    // bounding box of the ligand: receptor atoms farther than 12 A from it have weight 0 (mol.ml:836)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int j = lane; j < a.L; j += 32) {
+        lo[0] = fmin(lo[0], x[j]); hi[0] = fmax(hi[0], x[j]);
+        lo[1] = fmin(lo[1], y[j]); hi[1] = fmax(hi[1], y[j]);
+        lo[2] = fmin(lo[2], z[j]); hi[2] = fmax(hi[2], z[j]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    double se = 0.0, sv = 0.0;
+    for (int i = lane; i < a.P; i += 32) {
+        const double2 p01 = __ldg((const double2 *)(a.pxyzq + i));
+        const double2 p23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
+        const double gx = fmax(0.0, fmax(lo[0] - p01.x, p01.x - hi[0]));
+        const double gy = fmax(0.0, fmax(lo[1] - p01.y, p01.y - hi[1]));
+        const double gz = fmax(0.0, fmax(lo[2] - p23.x, p23.x - hi[2]));
+        if (gx * gx + gy * gy + gz * gz >= 144.0) continue;
+        const double q_i = p23.y;
+        const int ei = __ldg(a.pelt + i) * kEltTab;
+        for (int j = 0; j < a.L; j++) {
+            const double r2 = d_dist2(p01.x, p01.y, p23.x, x[j], y[j], z[j]);
+            if (r2 < 144.0) {
+                const double r = d_nzd(sqrt(r2));
+                const double w = d_shift(r);
+                const int t = ei + __ldg(a.lelt + j);
+                const double p6 = d_pow6(__ldg(a.xij + t) / r);
+                se = se + w * ((q_i * __ldg(a.lq + j)) / r);
+                sv = sv + w * (__ldg(a.dij + t) * ((-2.0 * p6) + (p6 * p6)));
+            }
+        }
+    }
+    __syncwarp();
+    terms[lane] = make_double2(se, sv);
+    __syncwarp();
+    double te = 0.0, tv = 0.0;
+    for (int l = 0; l < 32; l++) { te = te + terms[l].x; tv = tv + terms[l].y; }
+    return (kElecWeight * te) + tv;
+}
+
+__device__ __forceinline__ double inter_energy(const McArgs &a, const double *x, const double *y, const double *z,
+                                               int lane, double2 *terms) {
+    return a.maps ? interp_energy(a, x, y, z, lane, terms) : direct_energy(a, x, y, z, lane, terms);
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 mc_chains_kernel(McArgs a) {
     extern __shared__ double smem[];
@@ -197,7 +256,7 @@ mc_chains_kernel(McArgs a) {
     double const_intra = 0.0;
     if (a.intra_nb && !flexible) const_intra = intra_energy(a, cx, cy, cz, lane, terms);
     double prev_E_intra = !a.intra_nb ? 0.0 : (flexible ? intra_energy(a, lx, ly, lz, lane, terms) : const_intra);
-    double prev_E_inter = interp_energy(a, lx, ly, lz, lane, terms);
+    double prev_E_inter = inter_energy(a, lx, ly, lz, lane, terms);
     double prev_E = prev_E_inter + prev_E_intra;
     double best_E = prev_E;
     long long rigid_step = 0, conf_step = 0;
@@ -294,7 +353,7 @@ mc_chains_kernel(McArgs a) {
         }
         __syncwarp();
         if (!rigid && a.intra_nb) prev_E_intra = flexible ? intra_energy(a, lx, ly, lz, lane, terms) : const_intra;   // D2
-        prev_E_inter = interp_energy(a, lx, ly, lz, lane, terms);
+        prev_E_inter = inter_energy(a, lx, ly, lz, lane, terms);
         const double curr_E = prev_E_inter + prev_E_intra;
         int accepted = -1;
         const double ddx = a.roi_c[0] - (0.0 + posp[0]), ddy = a.roi_c[1] - (0.0 + posp[1]), ddz = a.roi_c[2] - (0.0 + posp[2]);
@@ -410,18 +469,19 @@ static int ensure_mc_tables() {
 
 using namespace mmo;
 
-extern "C" int mmo_mc_run(const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
+extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
                           int64_t n_chains, const uint64_t *seeds, const double *start_rot9,
                           const double *start_pos3, mmo_mc_result *results, double *best_xyz,
                           double *trace_chain0) {
     MMO_TRY(require_ready());
-    MMO_REQUIRE(grid && lig && p, "mmo_mc_run: null handle");
-    MMO_REQUIRE(lig->has_typ, "mmo_mc_run: the ligand needs FF atom types (interpolated scorer)");
+    MMO_REQUIRE(lig && p, "mmo_mc_run: null handle");
+    MMO_REQUIRE((rec != nullptr) != (grid != nullptr), "mmo_mc_run: give exactly one of rec (direct, --no-interp) or grid (interpolated)");
+    MMO_REQUIRE(!grid || lig->has_typ, "mmo_mc_run: the ligand needs FF atom types (interpolated scorer)");
     MMO_REQUIRE(!p->intra_nb || lig->has_dists, "mmo_mc_run: --intra-NB needs topological distances");
     MMO_REQUIRE(n_chains >= 0 && p->n_steps >= 0, "mmo_mc_run: negative size");
     if (n_chains == 0) return MMO_OK;
     MMO_REQUIRE(seeds && start_rot9 && start_pos3 && results, "mmo_mc_run: null buffer");
-    for (int j = 0; j < lig->n; j++)
+    for (int j = 0; grid && j < lig->n; j++)
         MMO_REQUIRE(lig->htyp[j] >= 0 && lig->htyp[j] < grid->T, "mmo_mc_run: atom %d has type %d, grid holds %d maps", j, lig->htyp[j], grid->T);
     MMO_TRY(ensure_mc_tables());
     Runtime &R = rt();
@@ -442,7 +502,8 @@ extern "C" int mmo_mc_run(const mmo_grid *grid, const mmo_ligand *lig, const mmo
     a.n_pairs = lig->n_pairs; a.pair_i = lig->pair_i.p; a.pair_j = lig->pair_j.p;
     a.n_rbonds = lig->n_rbonds; a.rb_left = lig->d_rb_left.p; a.rb_right = lig->d_rb_right.p;
     a.rg_off = lig->d_rg_off.p; a.rg_idx = lig->d_rg_idx.p;
-    a.g = geom_of(grid); a.maps = grid->maps.p;
+    if (grid) { a.g = geom_of(grid); a.maps = grid->maps.p; } else { memset(&a.g, 0, sizeof a.g); a.maps = nullptr; }
+    a.P = rec ? rec->n : 0; a.pxyzq = rec ? rec->xyzq64.p : nullptr; a.pelt = rec ? rec->elt.p : nullptr;
     a.xij = g_mc_xij.p; a.dij = g_mc_dij.p;
     for (int d = 0; d < 3; d++) a.roi_c[d] = p->roi_c[d];
     a.roi_r = p->roi_r;

@@ -107,3 +107,25 @@ def test_many_chains_statistics(gpu, orc, c2, c2_roi_rec, mc_setup):
     shrunk = np.array([r["max_rot"] < np.radians(15.0) and r["max_trans"] < 0.15 for r in res])
     assert shrunk.mean() > 0.9
     assert all(r["frames_done"] == 4000 or r["too_long"] for r in res)
+
+
+@pytest.mark.gpu
+def test_cuda_chain_on_the_direct_scorer_follows_the_oracle(gpu, orc, c2, c2_roi_rec):
+    """--no-interp: E_inter = Mol.ene_inter_UFF_shifted_brute (mol.ml:822-849).  The kernel uses the
+    reference's fp64 pair terms with a lane-strided summation, so energies agree to ~1e-13 relative and
+    the Metropolis decisions -- hence the trajectory -- are the oracle's."""
+    rec = gpu.Receptor.from_mol(c2_roi_rec)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    n_steps, seeds = 400, np.array([4242, 7], np.uint64)
+    R = np.tile(np.eye(3).reshape(9), (2, 1)); t = np.tile(c2["start_pos"], (2, 1))
+    t[1] += 0.3
+    res, xyz, trace = gpu.Lds.simulate_lig(None, lig, c2["roi"], n_steps, seeds, R, t, want_xyz=True, want_trace=True, rec=rec)
+    for c in range(2):
+        want, wxyz, wtr = orc.mc_run(c2["lig"], lig.xs, lig.ys, lig.zs, c2["roi"], n_steps, int(seeds[c]), R[c], t[c],
+                                     rec=c2_roi_rec)
+        if c == 0:
+            assert np.array_equal(trace[:, 3], wtr[:, 3])                       # same accept/reject sequence
+            assert np.allclose(trace[:, :3], wtr[:, :3], rtol=1e-10, atol=1e-9)
+        assert res[c]["n_accept_rigid"] == want["n_accept_rigid"] and res[c]["n_accept_conf"] == want["n_accept_conf"]
+        assert res[c]["best_E"] == pytest.approx(want["best_E"], rel=1e-10, abs=1e-9)
+        assert np.allclose(xyz[c], wxyz, rtol=0, atol=1e-9)
