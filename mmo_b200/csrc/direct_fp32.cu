@@ -3,20 +3,24 @@
 // Replaces the inner loops of Mol.ene_inter_UFF_shifted_brute / _global_brute (src/mol.ml:796-849)
 // for many poses per launch.  Layout of the computation (no tensor cores: non-linear pair sum):
 //
-//   thread  = one pose, block = 256 poses; the receptor (k-d groups of 32 atoms, fp32, relative to the
-//             receptor origin) is staged in shared memory, the whole ROI receptor at once when it fits
-//   cull    = per (warp, ligand atom): the atom's bounding box over the warp's 32 poses is tested first
-//             against the group boxes (one ballot per 32 groups), then against the individual atoms of
-//             the near groups (one ballot per group); survivors are compacted into a per-warp list.
-//             Shifted variant only: a culled pair has weight exactly 0 in the reference (mol.ml:836)
-//   pair    = 20 SASS instructions (1 MUFU.RSQ), see pair_energy(); the list is consumed 8 atoms at a
-//             time = 8 independent dependency chains per warp
-//   sum     = 8 pair terms in fp32, then one F2F + DADD into a per-thread fp64 accumulator
+//   thread  = one pose, block = 256 poses; the receptor (element-sorted k-d groups of 32 atoms, fp32,
+//             relative to the receptor origin) is staged in shared memory, the whole ROI receptor at once
+//             when it fits
+//   cull    = per (warp, ligand atom): the atom's bounding box over the warp's 32 poses (6 CREDUX) is
+//             tested first against the group boxes (one ballot per 32 groups), then against the
+//             individual atoms of the near groups (one ballot per group); the survivors' coordinates and
+//             charge products are compacted into a per-warp structure-of-arrays list.  Shifted variant
+//             only: a culled pair has weight exactly 0 in the reference (mol.ml:836)
+//   pair    = packed fp32 (FFMA2 / FMUL2 / FADD2 of sm_100a): one packed instruction serves two
+//             receptor atoms of the list, 15 packed + 4 FMNMX + 2 MUFU.RSQ per two pairs; the list is
+//             consumed 8 atoms at a time (8 LDS.128 with a warp-uniform address) = 4 independent
+//             packed dependency chains.  A_i A_j and B_i B_j are loop invariants (one list per element)
+//   sum     = fp32 inside a chain for kSumEvery steps, then F2F + DADD into a per-thread fp64 accumulator
 //
 // Accuracy contract (MMO_PREC_FP32): |E - E_ref| <= max(1e-6 |E_ref|, 1e-4 kcal/mol).  fp32 cannot
 // deliver that for close contacts (r^-12), so the fast path clamps r^2 at H = x_max_rec*x_max_lig/kTau
-// and a second, sparse kernel (hard_fix_kernel) adds  e64(r) - e64(sqrt(H))  in the reference's own
-// double arithmetic for the few pairs with r^2 < H, found through the receptor's voxel lists.
+// and a second, sparse kernel (hard_fix_kernel) adds  w(r) e64(r) - w(sqrt H) e64(sqrt H)  in the
+// reference's own double arithmetic for the few pairs with r^2 < H, found through the receptor's voxel lists.
 #include "common.cuh"
 #include "pose.cuh"
 #include <math.h>
@@ -25,15 +29,18 @@ namespace mmo {
 
 constexpr int LJ = 8;            // ligand atoms per chunk (= one k-d leaf of the ligand)
 constexpr int TPB = 256;         // poses per block
-constexpr int LIST_CAP = 384;    // per-warp list of near receptor atoms (shared-memory addresses)
+constexpr int LIST_CAP = 320;    // per-warp list of near receptor atoms (x, y, z, charge product)
 constexpr int MAX_TILE_GROUPS = 64;
+constexpr int kSumEvery = 2;     // list steps (of 8 atoms) summed in fp32 before the fp64 accumulation
 static_assert(kBlob == 32, "one receptor group per warp-wide test");
+static_assert(LIST_CAP % 8 == 0 && LIST_CAP > 128 + 8, "list must take 4 more groups before a flush");
 
 struct FastArgs {
-    int n_blobs;             // receptor groups of 32 atoms (k-d leaves)
-    int n_atoms;             // real receptor atoms (the last group may be padded)
+    int n_blobs;             // receptor groups of 32 atoms (k-d leaves, element-sorted)
+    int n_types;             // receptor elements present
+    int type_g0[kEltTab + 1];    // groups [type_g0[t], type_g0[t+1]) hold element t
+    float type_A[kEltTab], type_B[kEltTab];
     const float4 *xyzq;
-    const float2 *ab;
     const float4 *blob_box;
     double origin[3];
     int L;                   // real ligand atoms
@@ -51,52 +58,64 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// warp-wide min / max of an fp32 value in one instruction (CREDUX, sm_100a), result is warp-uniform
+__device__ __forceinline__ float warp_min(float x) {
+    float y;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float warp_max(float x) {
+    float y;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-// one receptor atom against one ligand atom; adds w * (EW q_i q_j / r + d_ij (p6^2 - 2 p6)) to acc
+// Two receptor atoms (the halves of the packed operands) against one ligand atom.
+//   SHIFTED: acc += (144 - r^2)^2 * e, with A_iA_j, B_iB_j and q_iq_j pre-divided by 144^2, so that the
+//            weight is FF.shift_12A (FF.ml:17-20) and exactly 0 from 12 A on (r^2 is clamped to [H, 144])
+//   GLOBAL : acc += e
+// e = (A_iA_j s^3 - B_iB_j) s^3 + q_iq_j / r with s = 1/r^2   (= d_ij (p6^2 - 2 p6) + 83.0159 q_i q_j / r)
 template <int VARIANT>
-__device__ __forceinline__ float pair_energy(float dx, float dy, float dz, float qi, float Ai, float Bi,
-                                             float qj, float Aj, float Bj, float H, float acc) {
-    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    float r2c = fmaxf(r2, H);                       // close contacts are finished in fp64 elsewhere
-    float rinv = rsqrt_fast(r2c);
-    float s = rinv * rinv;
-    float s3 = s * s * s;
-    float v = fmaf(Ai * Aj, s3, -(Bi * Bj));        // (A_i A_j) s^3 - B_i B_j
-    float er = (qi * qj) * rinv;                    // qi already carries 332.0637/4
-    float e = fmaf(v, s3, er);
+__device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 QQ, float2 nlx, float2 nly, float2 nlz,
+                                        float2 AA, float2 nBB, float H, float2 acc, float2 &r2_out) {
+    const float2 dx = __fadd2_rn(X, nlx), dy = __fadd2_rn(Y, nly), dz = __fadd2_rn(Z, nlz);
+    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    r2_out = r2;
+    float2 r2c;                                      // close contacts are finished in fp64 elsewhere
     if (VARIANT == MMO_VARIANT_SHIFTED) {
-        // shift weight (1 - r^2/144)^2 from the unclamped r^2, saturated to [0,1]: one FFMA.SAT gives
-        // exactly 0 beyond the 12 A cut-off (FF.shift_12A, FF.ml:17-20)
-        float u = __saturatef(fmaf(r2, -1.0f / 144.0f, 1.0f));
-        return fmaf(u * u, e, acc);
+        r2c.x = fminf(fmaxf(r2.x, H), 144.0f);
+        r2c.y = fminf(fmaxf(r2.y, H), 144.0f);
     } else {
-        return acc + e;
+        r2c.x = fmaxf(r2.x, H);
+        r2c.y = fmaxf(r2.y, H);
+    }
+    const float2 rinv = make_float2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
+    const float2 s = __fmul2_rn(rinv, rinv);
+    const float2 s3 = __fmul2_rn(__fmul2_rn(s, s), s);
+    const float2 v = __ffma2_rn(AA, s3, nBB);
+    const float2 e = __ffma2_rn(v, s3, __fmul2_rn(QQ, rinv));
+    if (VARIANT == MMO_VARIANT_SHIFTED) {
+        const float2 up = __ffma2_rn(r2c, make_float2(-1.0f, -1.0f), make_float2(144.0f, 144.0f));
+        return __ffma2_rn(__fmul2_rn(up, up), e, acc);
+    } else {
+        return __fadd2_rn(acc, e);
     }
 }
 
-// squared distance from point p to the box [lo, hi]
-__device__ __forceinline__ float box_dist2(const float4 p, const float *lo, const float *hi) {
-    float gx = fmaxf(0.f, fmaxf(lo[0] - p.x, p.x - hi[0]));
-    float gy = fmaxf(0.f, fmaxf(lo[1] - p.y, p.y - hi[1]));
-    float gz = fmaxf(0.f, fmaxf(lo[2] - p.z, p.z - hi[2]));
-    return fmaf(gz, gz, fmaf(gy, gy, gx * gx));
-}
-
-// Shared memory (dynamic): receptor tile as an array of 32-byte atoms {x, y, z, 83.0159*q | A, B, 0, 0}
-// [tile_atoms + 1], group boxes [2*tile_groups], ligand parameters [n_fast], chunk coordinates [LJ][TPB],
-// per-warp near lists (shared-memory byte addresses of the atoms, so that the pair loop needs no index
-// arithmetic).  Slot tile_atoms is a dummy atom (far away, no charge, no vdW) that pads a list to 8.
+// Shared memory (dynamic): receptor tile float4 {x, y, z, 83.0159*q} [tile_atoms], group boxes
+// [2*tile_groups], ligand parameters [n_fast], chunk coordinates x|y|z [LJ][TPB], per-warp lists
+// x|y|z|qq [LIST_CAP] (structure of arrays: conflict-free compaction stores, LDS.128 = 4 atoms of one field).
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(TPB, 2)
 direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, double *__restrict__ out) {
     extern __shared__ float4 smem4[];
     const int tile_atoms = tile_groups * kBlob;
-    float4 *s_atom = smem4;                                   // 2 * (tile_atoms + 1)
-    float4 *s_box = s_atom + 2 * (tile_atoms + 1);            // tile_groups * 2
+    float4 *s_atom = smem4;                                   // tile_atoms
+    float4 *s_box = s_atom + tile_atoms;                      // tile_groups * 2
     float4 *s_lparam = s_box + tile_groups * 2;               // n_fast
-    float4 *s_c = s_lparam + a.n_fast;                        // LJ * TPB : {x, y, z, -} of chunk atom jj, pose tid
-    unsigned *s_list = (unsigned *)(s_c + LJ * TPB) + (threadIdx.x >> 5) * LIST_CAP;
-    const unsigned atom_base = (unsigned)__cvta_generic_to_shared(s_atom);
+    float *s_c = (float *)(s_lparam + a.n_fast);              // 3 * LJ * TPB : field-major, then chunk atom, then pose
+    float *s_list = s_c + 3 * LJ * TPB + (threadIdx.x >> 5) * (4 * LIST_CAP);
+    float *s_lx = s_list, *s_ly = s_list + LIST_CAP, *s_lz = s_list + 2 * LIST_CAP, *s_lq = s_list + 3 * LIST_CAP;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -105,6 +124,8 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
     const bool valid = p < n_poses;
     const int64_t pp = valid ? p : n_poses - 1;   // idle lanes shadow the last pose, result discarded
     for (int j = tid; j < a.n_fast; j += TPB) s_lparam[j] = a.lparam[j];
+    // SHIFTED: the weight (144 - r^2)^2 / 144^2 is split between the pair and the invariants
+    const float wscale = VARIANT == MMO_VARIANT_SHIFTED ? 1.0f / 20736.0f : 1.0f;
 
     double acc = 0.0;
     unsigned long long n_eval = 0, n_in = 0;
@@ -116,16 +137,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
         __syncthreads();
         const int b0 = t * tile_groups;
         const int nb = min(tile_groups, a.n_blobs - b0);
-        const int n_real = min(nb * kBlob, a.n_atoms - b0 * kBlob);      // real atoms in this tile
-        for (int k = tid; k < nb * kBlob; k += TPB) {
-            const float2 ab = __ldg(a.ab + (size_t)b0 * kBlob + k);
-            s_atom[2 * k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
-            s_atom[2 * k + 1] = make_float4(ab.x, ab.y, 0.f, 0.f);
-        }
-        if (tid == 0) {
-            s_atom[2 * tile_atoms] = make_float4(1e6f, 1e6f, 1e6f, 0.f);
-            s_atom[2 * tile_atoms + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int k = tid; k < nb * kBlob; k += TPB) s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
         for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
         __syncthreads();
 
@@ -138,7 +150,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
 #pragma unroll
                 for (int jj = 0; jj < LJ; jj++) {
                     const int k = c * LJ + jj;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float vx = 0.f, vy = 0.f, vz = 0.f;
                     if (s_lparam[k].w != 0.f) {
                         double x, y, z;
                         if (src.kind == 1) {
@@ -147,33 +159,30 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                         } else {
                             pose_atom_rt(P, __ldg(a.lx + k), __ldg(a.ly + k), __ldg(a.lz + k), x, y, z);
                         }
-                        v.x = (float)(x - a.origin[0]);
-                        v.y = (float)(y - a.origin[1]);
-                        v.z = (float)(z - a.origin[2]);
+                        vx = (float)(x - a.origin[0]);
+                        vy = (float)(y - a.origin[1]);
+                        vz = (float)(z - a.origin[2]);
                     }
-                    s_c[jj * TPB + tid] = v;
+                    s_c[(0 * LJ + jj) * TPB + tid] = vx;
+                    s_c[(1 * LJ + jj) * TPB + tid] = vy;
+                    s_c[(2 * LJ + jj) * TPB + tid] = vz;
                 }
             }
 #pragma unroll 1
             for (int jj = 0; jj < LJ; jj++) {
                 const float4 lp = s_lparam[c * LJ + jj];
                 if (lp.w == 0.f) continue;                              // padding atom (warp-uniform)
-                const float4 lc = s_c[jj * TPB + tid];
+                const float lcx = s_c[(0 * LJ + jj) * TPB + tid], lcy = s_c[(1 * LJ + jj) * TPB + tid],
+                            lcz = s_c[(2 * LJ + jj) * TPB + tid];
+                const float2 nlx = make_float2(-lcx, -lcx), nly = make_float2(-lcy, -lcy), nlz = make_float2(-lcz, -lcz);
                 // bounding box of this ligand atom over the warp's 32 poses
-                float lo[3] = {lc.x, lc.y, lc.z}, hi[3] = {lc.x, lc.y, lc.z};
+                float lo[3] = {lcx, lcy, lcz}, hi[3] = {lcx, lcy, lcz};
+                unsigned long long gmask = ~0ull;                       // near mask of the tile's groups
                 if (VARIANT == MMO_VARIANT_SHIFTED) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-                            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-                        }
-                    }
-                }
-                // ---- level 1: which groups of 32 receptor atoms can be within 12 A of this atom? ----
-                unsigned gm0 = 0xffffffffu, gm1 = 0xffffffffu;      // near masks of groups 0-31 / 32-63
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    lo[0] = warp_min(lcx); lo[1] = warp_min(lcy); lo[2] = warp_min(lcz);
+                    hi[0] = warp_max(lcx); hi[1] = warp_max(lcy); hi[2] = warp_max(lcz);
+                    // ---- level 1: which groups of 32 receptor atoms can be within 12 A of this atom? ----
+                    unsigned gm[2];
 #pragma unroll
                     for (int r = 0; r < 2; r++) {
                         const int g = r * 32 + lane;
@@ -185,64 +194,99 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                             float gz = fmaxf(0.f, fmaxf(blo.z - hi[2], lo[2] - bhi.z));
                             near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
                         }
-                        const unsigned m = __ballot_sync(0xffffffffu, near);
-                        if (r == 0) gm0 = m; else gm1 = m;
+                        gm[r] = __ballot_sync(0xffffffffu, near);
                     }
+                    gmask = ((unsigned long long)gm[1] << 32) | gm[0];
                 }
-                // ---- level 2: per-atom test, 4 groups per step (independent loads and tests), survivors
-                //      compacted into the warp's list; the list is consumed 8 atoms at a time ----
-                int n = 0;
-                for (int g4 = 0; g4 < nb || n > 0; g4 += 4) {
-                    if (g4 < nb) {
-                        const unsigned m4 = ((g4 < 32 ? gm0 : gm1) >> (g4 & 31)) & 0xfu;
-                        if (m4 != 0u) {
-                            bool nr[4];
+                const float qjs = lp.z * wscale;
+                // ---- one list per receptor element: A_i A_j, B_i B_j are invariants of the pair loop ----
+#pragma unroll 1
+                for (int ty = 0; ty < a.n_types; ty++) {
+                    const int g_lo = max(a.type_g0[ty], b0) - b0, g_hi = min(a.type_g0[ty + 1], b0 + nb) - b0;
+                    if (g_lo >= g_hi) continue;
+                    const float AAs = a.type_A[ty] * lp.x * wscale, BBs = a.type_B[ty] * lp.y * wscale;
+                    const float2 AA = make_float2(AAs, AAs), nBB = make_float2(-BBs, -BBs);
+                    // ---- level 2: per-atom test, 4 groups per step (independent loads and tests), survivors
+                    //      compacted into the warp's list; the list is consumed 8 atoms at a time ----
+                    int n = 0;
+                    for (int g4 = g_lo; g4 < g_hi || n > 0; g4 += 4) {
+                        if (g4 < g_hi) {
+                            const unsigned m4 = (unsigned)(gmask >> g4) & (0xfu >> max(0, 4 - (g_hi - g4)));
+                            if (m4 != 0u) {
+                                bool nr[4];
+                                float4 pa[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int atom = (g4 + u) * kBlob + lane;
-                                nr[u] = ((m4 >> u) & 1u) && atom < n_real;
-                                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                                    // (out-of-tile slots are never read: clamp the address, keep the predicate)
-                                    const float4 pa = s_atom[2 * min(atom, tile_atoms)];
-                                    nr[u] = nr[u] && box_dist2(pa, lo, hi) < 144.0f;
+                                for (int u = 0; u < 4; u++) {
+                                    // (slots past the tile are never selected: clamp the address, keep the predicate)
+                                    pa[u] = s_atom[min((g4 + u) * kBlob + lane, tile_atoms - 1)];
+                                    nr[u] = ((m4 >> u) & 1u) && pa[u].x < 0.5f * kFarAway;
+                                    if (VARIANT == MMO_VARIANT_SHIFTED) {
+                                        float gx = fmaxf(0.f, fmaxf(lo[0] - pa[u].x, pa[u].x - hi[0]));
+                                        float gy = fmaxf(0.f, fmaxf(lo[1] - pa[u].y, pa[u].y - hi[1]));
+                                        float gz = fmaxf(0.f, fmaxf(lo[2] - pa[u].z, pa[u].z - hi[2]));
+                                        nr[u] = nr[u] && fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const unsigned bm = __ballot_sync(0xffffffffu, nr[u]);
+                                    if (nr[u]) {
+                                        const int slot = n + __popc(bm & lt_mask);
+                                        s_lx[slot] = pa[u].x; s_ly[slot] = pa[u].y; s_lz[slot] = pa[u].z;
+                                        s_lq[slot] = pa[u].w * qjs;
+                                    }
+                                    n += __popc(bm);
                                 }
                             }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const unsigned bm = __ballot_sync(0xffffffffu, nr[u]);
-                                if (nr[u]) s_list[n + __popc(bm & lt_mask)] = atom_base + (unsigned)((g4 + u) * kBlob + lane) * 32u;
-                                n += __popc(bm);
-                            }
+                            if (n <= LIST_CAP - 128 - 8 && g4 + 4 < g_hi) continue;       // room for 4 more groups
                         }
-                        if (n <= LIST_CAP - 128 && g4 + 4 < nb) continue;       // room for 4 more groups
-                    }
-                    if (n == 0) continue;
-                    // ---- process the list: 8 independent pair chains per step ----
-                    if (STATS) n_eval += (unsigned long long)n;
-                    const int n8 = (n + 7) & ~7;
-                    if (lane < n8 - n) s_list[n + lane] = atom_base + (unsigned)tile_atoms * 32u;     // pad with the dummy atom
-                    __syncwarp();
+                        if (n == 0) continue;
+                        // ---- process the list: 4 packed chains = 8 pairs per step ----
+                        if (STATS) n_eval += (unsigned long long)n;
+                        const int n8 = (n + 7) & ~7;
+                        if (lane < n8 - n) {                                 // pad with far-away, charge-free atoms
+                            s_lx[n + lane] = kFarAway; s_ly[n + lane] = kFarAway; s_lz[n + lane] = kFarAway;
+                            s_lq[n + lane] = 0.f;
+                        }
+                        __syncwarp();
+                        float2 f[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) f[i] = make_float2(0.f, 0.f);
+                        int since = 0;
 #pragma unroll 1
-                    for (int k = 0; k < n8; k += 8) {
-                        const uint4 pk0 = *(const uint4 *)(s_list + k), pk1 = *(const uint4 *)(s_list + k + 4);
-                        const unsigned ad[8] = {pk0.x, pk0.y, pk0.z, pk0.w, pk1.x, pk1.y, pk1.z, pk1.w};
-                        float f = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            float4 ra, rp;
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ra.x), "=f"(ra.y), "=f"(ra.z), "=f"(ra.w) : "r"(ad[i]));
-                            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16];" : "=f"(rp.x), "=f"(rp.y) : "r"(ad[i]));
-                            float dx = ra.x - lc.x, dy = ra.y - lc.y, dz = ra.z - lc.z;
-                            f = pair_energy<VARIANT>(dx, dy, dz, ra.w, rp.x, rp.y, lp.z, lp.x, lp.y, a.H, f);
+                        for (int k = 0; k < n8; k += 8) {
+                            const float4 X0 = *(const float4 *)(s_lx + k), X1 = *(const float4 *)(s_lx + k + 4);
+                            const float4 Y0 = *(const float4 *)(s_ly + k), Y1 = *(const float4 *)(s_ly + k + 4);
+                            const float4 Z0 = *(const float4 *)(s_lz + k), Z1 = *(const float4 *)(s_lz + k + 4);
+                            const float4 Q0 = *(const float4 *)(s_lq + k), Q1 = *(const float4 *)(s_lq + k + 4);
+                            float2 r2[4];
+                            f[0] = pair2<VARIANT>(make_float2(X0.x, X0.y), make_float2(Y0.x, Y0.y), make_float2(Z0.x, Z0.y),
+                                                  make_float2(Q0.x, Q0.y), nlx, nly, nlz, AA, nBB, a.H, f[0], r2[0]);
+                            f[1] = pair2<VARIANT>(make_float2(X0.z, X0.w), make_float2(Y0.z, Y0.w), make_float2(Z0.z, Z0.w),
+                                                  make_float2(Q0.z, Q0.w), nlx, nly, nlz, AA, nBB, a.H, f[1], r2[1]);
+                            f[2] = pair2<VARIANT>(make_float2(X1.x, X1.y), make_float2(Y1.x, Y1.y), make_float2(Z1.x, Z1.y),
+                                                  make_float2(Q1.x, Q1.y), nlx, nly, nlz, AA, nBB, a.H, f[2], r2[2]);
+                            f[3] = pair2<VARIANT>(make_float2(X1.z, X1.w), make_float2(Y1.z, Y1.w), make_float2(Z1.z, Z1.w),
+                                                  make_float2(Q1.z, Q1.w), nlx, nly, nlz, AA, nBB, a.H, f[3], r2[3]);
                             if (STATS) {
-                                float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                                if (r2 < 144.0f && ra.x < 1e5f) n_in++;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) n_in += (r2[i].x < 144.0f) + (r2[i].y < 144.0f);
+                            }
+                            if (++since == kSumEvery) {
+                                const float2 h = __fadd2_rn(__fadd2_rn(f[0], f[1]), __fadd2_rn(f[2], f[3]));
+                                acc += (double)(h.x + h.y);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) f[i] = make_float2(0.f, 0.f);
+                                since = 0;
                             }
                         }
-                        acc += (double)f;
+                        if (since != 0) {
+                            const float2 h = __fadd2_rn(__fadd2_rn(f[0], f[1]), __fadd2_rn(f[2], f[3]));
+                            acc += (double)(h.x + h.y);
+                        }
+                        n = 0;
+                        __syncwarp();
                     }
-                    n = 0;
-                    __syncwarp();
                 }
             }
             __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
@@ -256,8 +300,8 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
 }
 
 // ---- close-contact correction (fp64) ---------------------------------------------------------------
-// For every pair with r^2 < H the fast path evaluated e(sqrt(H)); this pass adds e(r) - e(sqrt(H)) in
-// double.  Same formulas as mol.ml:811-815 / 838-845 (r clamped at 0.01, p6 = (x_ij/r)^6, shift weight),
+// For every pair with r^2 < H the fast path evaluated w(sqrt(H)) e(sqrt(H)); this pass adds
+// w(r) e(r) - w(sqrt(H)) e(sqrt(H)) in double.  Same formulas as mol.ml:811-815 / 838-845 (r clamped at 0.01, p6 = (x_ij/r)^6, shift weight),
 // written with one reciprocal square root instead of sqrt + two divisions: the result only has to be
 // accurate to ~1e-12 relative, not bit-identical (MMO_PREC_FP64 is the bit-identical mode).
 struct FixArgs {
@@ -272,6 +316,7 @@ struct FixArgs {
     const int32_t *lelt;
     double H;                            // exactly the fp32 clamp value
     double rinvH;                        // 1/sqrt(H)
+    double wH;                           // shift weight at r^2 = H
     const double *xx, *dij, *vdwH;       // kEltTab^2 tables: x_i*x_j, d_ij, d_ij*(p6H^2 - 2 p6H)
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
@@ -323,10 +368,12 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ ou
                 const double p6 = t2 * t2 * t2;
                 const double e = qq * rinv + __ldg(a.dij + t) * (p6 * p6 - 2.0 * p6);
                 const double eH = qq * a.rinvH + __ldg(a.vdwH + t);   // what the fast path evaluated (r clamped at sqrt(H))
-                double d = e - eH;
+                double d;
                 if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    const double u = 1.0 - r2c * (1.0 / 144.0);        // the fast path weighted e(H) with w(r), not w(H)
-                    d *= u * u;
+                    const double u = 1.0 - r2c * (1.0 / 144.0);
+                    d = (u * u) * e - a.wH * eH;                       // the fast path clamped r^2 in the weight too
+                } else {
+                    d = e - eH;
                 }
                 corr += d;
                 if (STATS) n_fix++;
@@ -390,8 +437,10 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     MMO_TRY(ensure_fix_tables((double)H));
     FastArgs fa;
     fa.n_blobs = rec->n_blobs;
-    fa.n_atoms = rec->n;
-    fa.xyzq = rec->xyzq.p; fa.ab = rec->ab.p; fa.blob_box = rec->blob_box.p;
+    fa.n_types = rec->n_types;
+    for (int t = 0; t <= kEltTab; t++) fa.type_g0[t] = t <= rec->n_types ? rec->type_g0[t] : rec->n_blobs;
+    for (int t = 0; t < kEltTab; t++) { fa.type_A[t] = rec->type_A[t]; fa.type_B[t] = rec->type_B[t]; }
+    fa.xyzq = rec->xyzq.p; fa.blob_box = rec->blob_box.p;
     for (int d = 0; d < 3; d++) fa.origin[d] = rec->origin[d];
     fa.L = lig->n;
     fa.n_fast = lig->n_fast;
@@ -409,6 +458,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.lx = lig->x.p; xa.ly = lig->y.p; xa.lz = lig->z.p; xa.lq = lig->q.p; xa.lelt = lig->elt.p;
     xa.H = (double)H;
     xa.rinvH = 1.0 / sqrt((double)H);
+    xa.wH = (1.0 - (double)H / 144.0) * (1.0 - (double)H / 144.0);
     xa.xx = g_xx.p; xa.dij = g_dij.p; xa.vdwH = g_vdwH.p;
     xa.stats = g_stats.p;
 
@@ -416,8 +466,8 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     const unsigned blocks = (unsigned)((n_poses + TPB - 1) / TPB);
     // receptor tile: everything when it fits (<= 64 groups = 2048 atoms), so that 2 blocks stay resident per SM
     const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
-    const size_t smem = (2 * ((size_t)tile_blobs * kBlob + 1) + (size_t)tile_blobs * 2 + (size_t)lig->n_fast + (size_t)LJ * TPB) * sizeof(float4) +
-                        (size_t)(TPB / 32) * LIST_CAP * sizeof(unsigned) + 16;
+    const size_t smem = ((size_t)tile_blobs * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
+                        (size_t)3 * LJ * TPB * sizeof(float) + (size_t)(TPB / 32) * 4 * LIST_CAP * sizeof(float);
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
         MMO_TRY(set_fast_smem(smem));

@@ -1,6 +1,6 @@
 // molecules.cu -- receptor / ligand handles: host-side preparation of the HBM layouts.
-//   receptor: original-order fp64 SoA (strict kernels) + Morton-sorted fp32 blobs of kBlob atoms with
-//             bounding boxes (fast kernel) + close-contact voxel lists (fp64 correction pass)
+//   receptor: original-order fp64 SoA (strict kernels) + element-sorted fp32 k-d groups of kBlob atoms
+//             with bounding boxes (fast kernel) + close-contact voxel lists (fp64 correction pass)
 //   ligand  : template conformer, fp32 vdW factors, interacting-pair list, rotatable bonds
 // Reference data model: src/mol.ml:17-35 (Mol.t), src/UFF.ml:10-51, src/ptable.ml:41-54.
 #include "common.cuh"
@@ -97,37 +97,54 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     }
     for (int d = 0; d < 3; d++) r->origin[d] = 0.5 * (lo[d] + hi[d]);
 
-    // ---- k-d leaves -> blobs of kBlob spatially close atoms
-    std::vector<int> order;
-    kd_order(n, xs, ys, zs, kBlob, order);
-    r->n_blobs = (n + kBlob - 1) / kBlob;
-    r->n_pad = r->n_blobs * kBlob;
-    std::vector<float4> xyzq(std::max(1, r->n_pad));
-    std::vector<float2> ab(std::max(1, r->n_pad));
-    std::vector<float4> box((size_t)std::max(1, r->n_blobs) * 2);
-    for (int b = 0; b < r->n_blobs; b++) {
-        float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
-        for (int s = 0; s < kBlob; s++) {
-            int k = b * kBlob + s;
-            if (k < n) {
-                int i = order[k];
-                float4 v;
-                v.x = (float)(xs[i] - r->origin[0]);
-                v.y = (float)(ys[i] - r->origin[1]);
-                v.z = (float)(zs[i] - r->origin[2]);
-                v.w = (float)(kElecWeight * q[i]);
-                xyzq[k] = v;
-                vdw_factors(elt[i], &ab[k].x, &ab[k].y);
-                float p[3] = {v.x, v.y, v.z};
-                for (int d = 0; d < 3; d++) { blo[d] = fminf(blo[d], p[d]); bhi[d] = fmaxf(bhi[d], p[d]); }
-            } else {   // padding: far away, no charge, no vdW -> contributes exactly 0
-                xyzq[k] = make_float4(1e6f, 1e6f, 1e6f, 0.f);
-                ab[k] = make_float2(0.f, 0.f);
+    // ---- typed groups: atoms sorted by element, then k-d leaves of kBlob spatially close atoms inside
+    //      every element (A_i A_j and B_i B_j become loop invariants of the pair loop)
+    std::vector<float4> xyzq;
+    std::vector<float4> box;
+    r->n_types = 0;
+    r->n_blobs = 0;
+    for (int e = 0; e < kEltTab; e++) {
+        std::vector<int> members;
+        for (int i = 0; i < n; i++)
+            if (elt[i] == e) members.push_back(i);
+        if (members.empty()) continue;
+        const int ne = (int)members.size();
+        std::vector<double> ex(ne), ey(ne), ez(ne);
+        for (int k = 0; k < ne; k++) { ex[k] = xs[members[k]]; ey[k] = ys[members[k]]; ez[k] = zs[members[k]]; }
+        std::vector<int> order;
+        kd_order(ne, ex.data(), ey.data(), ez.data(), kBlob, order);
+        const int t = r->n_types++;
+        r->type_elt[t] = e;
+        r->type_g0[t] = r->n_blobs;
+        vdw_factors(e, &r->type_A[t], &r->type_B[t]);
+        const int nb = (ne + kBlob - 1) / kBlob;
+        for (int b = 0; b < nb; b++) {
+            float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
+            for (int s = 0; s < kBlob; s++) {
+                int k = b * kBlob + s;
+                if (k < ne) {
+                    int i = members[order[k]];
+                    float4 v;
+                    v.x = (float)(xs[i] - r->origin[0]);
+                    v.y = (float)(ys[i] - r->origin[1]);
+                    v.z = (float)(zs[i] - r->origin[2]);
+                    v.w = (float)(kElecWeight * q[i]);
+                    xyzq.push_back(v);
+                    float p[3] = {v.x, v.y, v.z};
+                    for (int d = 0; d < 3; d++) { blo[d] = fminf(blo[d], p[d]); bhi[d] = fmaxf(bhi[d], p[d]); }
+                } else {   // padding: far away, no charge -> never listed, contributes exactly 0
+                    xyzq.push_back(make_float4(kFarAway, kFarAway, kFarAway, 0.f));
+                }
             }
+            box.push_back(make_float4(blo[0], blo[1], blo[2], 0.f));
+            box.push_back(make_float4(bhi[0], bhi[1], bhi[2], 0.f));
         }
-        box[(size_t)b * 2] = make_float4(blo[0], blo[1], blo[2], 0.f);
-        box[(size_t)b * 2 + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
+        r->n_blobs += nb;
     }
+    r->type_g0[r->n_types] = r->n_blobs;
+    r->n_pad = r->n_blobs * kBlob;
+    if (xyzq.empty()) { xyzq.push_back(make_float4(kFarAway, kFarAway, kFarAway, 0.f)); }
+    if (box.empty()) { box.resize(2, make_float4(0.f, 0.f, 0.f, 0.f)); }
 
     // ---- close-contact voxel lists: atoms within r_list of any point of the voxel (conservative)
     // 1 A voxels (fewer candidates per lookup) while the table stays small, 2 A otherwise
@@ -180,7 +197,7 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
         }
         if ((rc = r->x.upload(r->hx)) || (rc = r->y.upload(r->hy)) || (rc = r->z.upload(r->hz)) ||
             (rc = r->q.upload(r->hq)) || (rc = r->elt.upload(elt)) || (rc = r->xyzq.upload(xyzq)) ||
-            (rc = r->ab.upload(ab)) || (rc = r->blob_box.upload(box)) || (rc = r->vox_off.upload(cnt)) ||
+            (rc = r->blob_box.upload(box)) || (rc = r->vox_off.upload(cnt)) ||
             (rc = r->vox_idx.upload(idx)))
             break;
     } while (0);
