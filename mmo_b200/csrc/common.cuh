@@ -101,7 +101,7 @@ constexpr double kElecWeight = 332.0637 / 4.0;   // src/UFF.ml:25, src/const.ml:
 constexpr double kMaxE = 100000.0;               // src/params.ml:26
 
 // ---- geometry of the fp32 direct kernel -----------------------------------------------------------
-constexpr int kBlob = 32;        // receptor atoms per k-d leaf ("group"): first level of distance culling
+constexpr int kBlob = 16;        // receptor atoms per k-d leaf ("group"): first level of distance culling
 // close-contact threshold: pairs with x_i*x_j / r^2 > kTau are re-evaluated in fp64
 constexpr double kTau = 1.5;
 constexpr float kFarAway = 1e6f;  // coordinate of padding atoms: beyond every cut-off, squares stay finite in fp32
@@ -113,22 +113,17 @@ struct Aabb { float lo[3], hi[3]; };
 // ---- opaque handles -----------------------------------------------------------------------------------
 struct mmo_receptor {
     int n = 0;                       // real atoms
-    int n_pad = 0;                   // n_blobs * kBlob (every element's last group is padded)
+    int n_pad = 0;                   // n_blobs * kBlob
     int n_blobs = 0;
-    // fast kernel: atoms sorted by element, k-d leaves of kBlob atoms inside every element ("typed groups");
-    // groups [type_g0[t], type_g0[t+1]) hold element type_elt[t], whose vdW factors are type_A/B[t]
-    int n_types = 0;
-    int type_g0[mmo::kEltTab + 1] = {0};
-    int type_elt[mmo::kEltTab] = {0};
-    float type_A[mmo::kEltTab] = {0}, type_B[mmo::kEltTab] = {0};
     double origin[3] = {0, 0, 0};    // fp32 coordinates are relative to this point
     // original order, double (strict fp64 kernels)
     mmo::DevBuf<double> x, y, z, q;
     mmo::DevBuf<int32_t> elt;        // compact element index
     mmo::DevBuf<double4> xyzq64;     // {x, y, z, q} packed for the close-contact pass
     mmo::DevBuf<float4> xyz32v;      // positions relative to vox_lo, fp32 (pre-test of the close-contact pass)
-    // typed-group order, fp32 (fast kernel): xyzq = {x-ox, y-oy, z-oz, EW*q}
+    // group order, fp32 (fast kernel): xyzq = {x-ox, y-oy, z-oz, EW*q}; gelt = compact element index
     mmo::DevBuf<float4> xyzq;
+    mmo::DevBuf<uint8_t> gelt;
     mmo::DevBuf<float4> blob_box;    // n_blobs x 2 : {lo xyz, 0}, {hi xyz, 0} (relative coordinates)
     // close-contact voxel lists (fp64 correction pass)
     double vox_lo[3] = {0, 0, 0};
@@ -213,6 +208,7 @@ int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSr
 
 // balanced k-d ordering: permutation of n points such that consecutive groups of `leaf` points are
 // spatially compact (only the last group may be short)
+void vdw_factors(int elt, float *A, float *B);   // A = sqrt(D) x^6, B = sqrt(2D) x^3 (NaN if unsupported)
 void kd_order(int n, const double *x, const double *y, const double *z, int leaf, std::vector<int> &order);
 
 // host-side mirrors (host_math.cu)

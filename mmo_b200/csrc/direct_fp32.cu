@@ -3,19 +3,21 @@
 // Replaces the inner loops of Mol.ene_inter_UFF_shifted_brute / _global_brute (src/mol.ml:796-849)
 // for many poses per launch.  Layout of the computation (no tensor cores: non-linear pair sum):
 //
-//   thread  = one pose, block = 256 poses; the receptor (element-sorted k-d groups of 32 atoms, fp32,
-//             relative to the receptor origin) is staged in shared memory, the whole ROI receptor at once
-//             when it fits
-//   cull    = per (warp, ligand atom): the atom's bounding box over the warp's 32 poses (6 CREDUX) is
-//             tested first against the group boxes (one ballot per 32 groups), then against the
-//             individual atoms of the near groups (one ballot per group); the survivors' coordinates and
-//             charge products are compacted into a per-warp structure-of-arrays list.  Shifted variant
+//   thread  = two poses (p and p + 32), warp = 64 consecutive poses, block = 512 poses; the receptor
+//             (k-d groups of 16 atoms, fp32, relative to the receptor origin) is staged in shared
+//             memory, the whole ROI receptor at once when it fits
+//   cull    = per (warp, ligand atom): centre c and radius rho of the atom's positions over the warp's 64
+//             poses (CREDUX); level 1: lane g tests the box of group g against the sphere (c, 12 + rho),
+//             one ballot per 32 groups; level 2: the atoms of two near groups per step are tested one
+//             per lane, and the survivors' centred coordinates x' = x - c, |x'|^2, charge product and
+//             vdW products are compacted into a per-warp structure-of-arrays list.  Shifted variant
 //             only: a culled pair has weight exactly 0 in the reference (mol.ml:836)
 //   pair    = packed fp32 (FFMA2 / FMUL2 / FADD2 of sm_100a): one packed instruction serves two
-//             receptor atoms of the list, 15 packed + 4 FMNMX + 2 MUFU.RSQ per two pairs; the list is
-//             consumed 8 atoms at a time (8 LDS.128 with a warp-uniform address) = 4 independent
-//             packed dependency chains.  A_i A_j and B_i B_j are loop invariants (one list per element)
-//   sum     = fp32 inside a chain for kSumEvery steps, then F2F + DADD into a per-thread fp64 accumulator
+//             receptor atoms of the list; r^2 = |x'|^2 + |l'|^2 - 2 x'.l' (l' = ligand atom - c, short
+//             vectors: no harmful cancellation while rho is small, else the difference form is used);
+//             13 packed + 4 FMNMX + 2 MUFU.RSQ per two pairs.  The list is consumed 4 atoms at a time
+//             (7 LDS.128 with a warp-uniform address) for both poses of the thread = 4 independent packed chains
+//   sum     = fp32 inside a chain for kSumEvery steps, then F2F + DADD into per-pose fp64 accumulators
 //
 // Accuracy contract (MMO_PREC_FP32): |E - E_ref| <= max(1e-6 |E_ref|, 1e-4 kcal/mol).  fp32 cannot
 // deliver that for close contacts (r^-12), so the fast path clamps r^2 at H = x_max_rec*x_max_lig/kTau
@@ -27,24 +29,28 @@
 
 namespace mmo {
 
-constexpr int LJ = 8;            // ligand atoms per chunk (= one k-d leaf of the ligand)
-constexpr int TPB = 256;         // poses per block
-constexpr int LIST_CAP = 320;    // per-warp list of near receptor atoms (x, y, z, charge product)
-constexpr int MAX_TILE_GROUPS = 64;
-constexpr int kSumEvery = 2;     // list steps (of 8 atoms) summed in fp32 before the fp64 accumulation
-static_assert(kBlob == 32, "one receptor group per warp-wide test");
-static_assert(LIST_CAP % 8 == 0 && LIST_CAP > 128 + 8, "list must take 4 more groups before a flush");
+constexpr int LJ = 4;            // ligand atoms per chunk (half a k-d leaf of the ligand)
+constexpr int TPB = 256;         // threads per block
+constexpr int PPT = 2;           // poses per thread
+constexpr int PPB = TPB * PPT;   // poses per block
+constexpr int LIST_CAP = 192;    // per-warp list of near receptor atoms
+constexpr int NF = 7;            // list fields: x', y', z', |x'|^2, q_i q_j, A_i A_j, -B_i B_j
+constexpr int MAX_TILE_GROUPS = 128;
+constexpr int kSumEvery = 4;     // list steps (of 4 atoms) summed in fp32 before the fp64 accumulation
+constexpr float kRhoExpand2 = 12.25f;  // the expanded form of r^2 is used while rho <= 3.5 A
+static_assert(kBlob == 16, "two receptor groups per warp-wide test");
+static_assert(LIST_CAP % 4 == 0 && LIST_CAP >= 128, "list must take one more step (64 atoms) before a flush");
+constexpr int NEAR_CAP = MAX_TILE_GROUPS + 8;   // per-warp list of near group ids (bytes)
 
 struct FastArgs {
-    int n_blobs;             // receptor groups of 32 atoms (k-d leaves, element-sorted)
-    int n_types;             // receptor elements present
-    int type_g0[kEltTab + 1];    // groups [type_g0[t], type_g0[t+1]) hold element t
-    float type_A[kEltTab], type_B[kEltTab];
+    int n_blobs;             // receptor groups of 16 atoms (k-d leaves)
+    float tab_A[kEltTab], tab_B[kEltTab];   // vdW factors by compact element index
     const float4 *xyzq;
+    const uint8_t *gelt;
     const float4 *blob_box;
     double origin[3];
     int L;                   // real ligand atoms
-    int n_fast;              // padded to a multiple of LJ
+    int n_fast;              // padded to a multiple of 8
     const double *lx, *ly, *lz;      // template in fast-path order
     const int32_t *forder;           // fast-path position -> original atom index (explicit coordinates)
     const float4 *lparam;            // fast-path order
@@ -69,17 +75,25 @@ __device__ __forceinline__ float warp_max(float x) {
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
 
-// Two receptor atoms (the halves of the packed operands) against one ligand atom.
+// Two receptor atoms (the halves of the packed operands) against one ligand atom of one pose.
+//   EXPAND : r^2 = (|x'|^2 + |l'|^2) - 2 x'.l'   (m2 = -2 l', l2 = |l'|^2)         4 packed ops
+//   else   : r^2 = |x' - l'|^2                   (m2 = -l')                        6 packed ops
 //   SHIFTED: acc += (144 - r^2)^2 * e, with A_iA_j, B_iB_j and q_iq_j pre-divided by 144^2, so that the
 //            weight is FF.shift_12A (FF.ml:17-20) and exactly 0 from 12 A on (r^2 is clamped to [H, 144])
 //   GLOBAL : acc += e
 // e = (A_iA_j s^3 - B_iB_j) s^3 + q_iq_j / r with s = 1/r^2   (= d_ij (p6^2 - 2 p6) + 83.0159 q_i q_j / r)
-template <int VARIANT>
-__device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 QQ, float2 nlx, float2 nly, float2 nlz,
-                                        float2 AA, float2 nBB, float H, float2 acc, float2 &r2_out) {
-    const float2 dx = __fadd2_rn(X, nlx), dy = __fadd2_rn(Y, nly), dz = __fadd2_rn(Z, nlz);
-    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+template <int VARIANT, bool EXPAND>
+__device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 S, float2 QQ, float2 AA, float2 nBB,
+                                        float m2x, float m2y, float m2z, float l2, float H, float2 acc, float2 &r2_out) {
+    float2 r2;
+    if (EXPAND) {
+        r2 = __ffma2_rn(X, bc2(m2x), __ffma2_rn(Y, bc2(m2y), __ffma2_rn(Z, bc2(m2z), __fadd2_rn(S, bc2(l2)))));
+    } else {
+        const float2 dx = __fadd2_rn(X, bc2(m2x)), dy = __fadd2_rn(Y, bc2(m2y)), dz = __fadd2_rn(Z, bc2(m2z));
+        r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    }
     r2_out = r2;
     float2 r2c;                                      // close contacts are finished in fp64 elsewhere
     if (VARIANT == MMO_VARIANT_SHIFTED) {
@@ -95,40 +109,100 @@ __device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 QQ,
     const float2 v = __ffma2_rn(AA, s3, nBB);
     const float2 e = __ffma2_rn(v, s3, __fmul2_rn(QQ, rinv));
     if (VARIANT == MMO_VARIANT_SHIFTED) {
-        const float2 up = __ffma2_rn(r2c, make_float2(-1.0f, -1.0f), make_float2(144.0f, 144.0f));
+        const float2 up = __ffma2_rn(r2c, bc2(-1.0f), bc2(144.0f));
         return __ffma2_rn(__fmul2_rn(up, up), e, acc);
     } else {
         return __fadd2_rn(acc, e);
     }
 }
 
+// consume the warp's list: n4 entries (a multiple of 4, padded), both poses of the thread
+template <int VARIANT, bool EXPAND, bool STATS>
+__device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const float (&m2x)[PPT], const float (&m2y)[PPT],
+                                         const float (&m2z)[PPT], const float (&l2)[PPT], float H, double (&acc)[PPT],
+                                         unsigned long long (&n_in)[PPT]) {
+    float2 f[PPT][2];
+#pragma unroll
+    for (int h = 0; h < PPT; h++) f[h][0] = f[h][1] = make_float2(0.f, 0.f);
+    int since = 0;
+#pragma unroll 1
+    for (int k = 0; k < n4; k += 4) {
+        const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
+        const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
+        const float4 Q = *(const float4 *)(s_l + 4 * LIST_CAP + k), A = *(const float4 *)(s_l + 5 * LIST_CAP + k);
+        const float4 B = *(const float4 *)(s_l + 6 * LIST_CAP + k);
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            float2 ra, rb;
+            f[h][0] = pair2<VARIANT, EXPAND>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
+                                             make_float2(S.x, S.y), make_float2(Q.x, Q.y), make_float2(A.x, A.y),
+                                             make_float2(B.x, B.y), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][0], ra);
+            f[h][1] = pair2<VARIANT, EXPAND>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
+                                             make_float2(S.z, S.w), make_float2(Q.z, Q.w), make_float2(A.z, A.w),
+                                             make_float2(B.z, B.w), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][1], rb);
+            if (STATS) n_in[h] += (ra.x < 144.0f && k < n) + (ra.y < 144.0f && k + 1 < n) + (rb.x < 144.0f && k + 2 < n) +
+                                  (rb.y < 144.0f && k + 3 < n);
+        }
+        if (++since == kSumEvery) {
+#pragma unroll
+            for (int h = 0; h < PPT; h++) {
+                const float2 t = __fadd2_rn(f[h][0], f[h][1]);
+                acc[h] += (double)(t.x + t.y);
+                f[h][0] = f[h][1] = make_float2(0.f, 0.f);
+            }
+            since = 0;
+        }
+    }
+    if (since != 0) {
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            const float2 t = __fadd2_rn(f[h][0], f[h][1]);
+            acc[h] += (double)(t.x + t.y);
+        }
+    }
+}
+
 // Shared memory (dynamic): receptor tile float4 {x, y, z, 83.0159*q} [tile_atoms], group boxes
-// [2*tile_groups], ligand parameters [n_fast], chunk coordinates x|y|z [LJ][TPB], per-warp lists
-// x|y|z|qq [LIST_CAP] (structure of arrays: conflict-free compaction stores, LDS.128 = 4 atoms of one field).
+// [2*tile_groups], ligand parameters [n_fast], vdW table [16] float2, chunk coordinates x|y|z [LJ][PPB],
+// per-warp lists [NF][LIST_CAP] (structure of arrays: conflict-free compaction stores, LDS.128 = 4 atoms
+// of one field), element bytes [tile_atoms].
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(TPB, 2)
 direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, double *__restrict__ out) {
+    // grid = (pose blocks, chunk splits): block (x, y) sums the ligand chunks c = y, y + gridDim.y, ... of its
+    // poses into out[y * n_poses + p]; the splits are added in a fixed order by hard_fix_kernel
     extern __shared__ float4 smem4[];
     const int tile_atoms = tile_groups * kBlob;
-    float4 *s_atom = smem4;                                   // tile_atoms
-    float4 *s_box = s_atom + tile_atoms;                      // tile_groups * 2
+    float4 *s_atom = smem4;                                   // tile_atoms + kBlob (a dummy group of far-away atoms)
+    float4 *s_box = s_atom + tile_atoms + kBlob;                      // tile_groups * 2
     float4 *s_lparam = s_box + tile_groups * 2;               // n_fast
-    float *s_c = (float *)(s_lparam + a.n_fast);              // 3 * LJ * TPB : field-major, then chunk atom, then pose
-    float *s_list = s_c + 3 * LJ * TPB + (threadIdx.x >> 5) * (4 * LIST_CAP);
-    float *s_lx = s_list, *s_ly = s_list + LIST_CAP, *s_lz = s_list + 2 * LIST_CAP, *s_lq = s_list + 3 * LIST_CAP;
+    float2 *s_tab = (float2 *)(s_lparam + a.n_fast);          // 16
+    float *s_c = (float *)(s_tab + 16);                       // 3 * LJ * PPB : field-major, then chunk atom, then pose
+    float *s_l = s_c + 3 * LJ * PPB + (threadIdx.x >> 5) * (NF * LIST_CAP);
+    uint8_t *s_elt = (uint8_t *)(s_c + 3 * LJ * PPB + (TPB / 32) * (NF * LIST_CAP));      // tile_atoms + kBlob
+    uint8_t *s_near = s_elt + tile_atoms + kBlob + (threadIdx.x >> 5) * NEAR_CAP;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t p = (int64_t)blockIdx.x * TPB + tid;
-    const bool valid = p < n_poses;
-    const int64_t pp = valid ? p : n_poses - 1;   // idle lanes shadow the last pose, result discarded
+    const int col0 = (tid >> 5) * (32 * PPT) + lane;          // this thread's columns of s_c: col0 + 32 h
+    int64_t pp[PPT];
+    bool valid[PPT];
+#pragma unroll
+    for (int h = 0; h < PPT; h++) {
+        const int64_t p = (int64_t)blockIdx.x * PPB + col0 + 32 * h;
+        valid[h] = p < n_poses;
+        pp[h] = valid[h] ? p : n_poses - 1;       // idle slots shadow the last pose, result discarded
+    }
     for (int j = tid; j < a.n_fast; j += TPB) s_lparam[j] = a.lparam[j];
-    // SHIFTED: the weight (144 - r^2)^2 / 144^2 is split between the pair and the invariants
+    if (tid < kEltTab) s_tab[tid] = make_float2(a.tab_A[tid], a.tab_B[tid]);
+    // SHIFTED: the weight (144 - r^2)^2 / 144^2 is split between the pair and the list entries
     const float wscale = VARIANT == MMO_VARIANT_SHIFTED ? 1.0f / 20736.0f : 1.0f;
 
-    double acc = 0.0;
-    unsigned long long n_eval = 0, n_in = 0;
+    double acc[PPT];
+    unsigned long long n_eval = 0, n_in[PPT];
+#pragma unroll
+    for (int h = 0; h < PPT; h++) { acc[h] = 0.0; n_in[h] = 0; }
     const int n_chunks = a.n_fast / LJ;
     const int n_tiles = (a.n_blobs + tile_groups - 1) / tile_groups;
 
@@ -137,16 +211,24 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
         __syncthreads();
         const int b0 = t * tile_groups;
         const int nb = min(tile_groups, a.n_blobs - b0);
-        for (int k = tid; k < nb * kBlob; k += TPB) s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+        for (int k = tid; k < nb * kBlob; k += TPB) {
+            s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+            s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
+        }
         for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
+        if (tid < kBlob) {
+            s_atom[tile_atoms + tid] = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
+            s_elt[tile_atoms + tid] = 0;
+        }
         __syncthreads();
 
-        for (int c = 0; c < n_chunks; c++) {
-            // ---- this pose's chunk of ligand atoms: reference arithmetic in double, then fp32 -----
-            // (own column of s_c only: no block barrier needed, __syncwarp orders the warp's accesses)
-            {
+        for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+            // ---- this thread's poses, chunk of ligand atoms: reference arithmetic in double, then fp32 ----
+            // (own columns of s_c only: no block barrier needed, __syncwarp orders the warp's accesses)
+#pragma unroll
+            for (int h = 0; h < PPT; h++) {
                 PoseRT P;
-                if (src.kind != 1) load_pose_rt(src, pp, P);
+                if (src.kind != 1) load_pose_rt(src, pp[h], P);
 #pragma unroll
                 for (int jj = 0; jj < LJ; jj++) {
                     const int k = c * LJ + jj;
@@ -155,7 +237,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                         double x, y, z;
                         if (src.kind == 1) {
                             const int j = __ldg(a.forder + k);
-                            x = src.xs[pp * a.L + j]; y = src.ys[pp * a.L + j]; z = src.zs[pp * a.L + j];
+                            x = src.xs[pp[h] * a.L + j]; y = src.ys[pp[h] * a.L + j]; z = src.zs[pp[h] * a.L + j];
                         } else {
                             pose_atom_rt(P, __ldg(a.lx + k), __ldg(a.ly + k), __ldg(a.lz + k), x, y, z);
                         }
@@ -163,127 +245,110 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                         vy = (float)(y - a.origin[1]);
                         vz = (float)(z - a.origin[2]);
                     }
-                    s_c[(0 * LJ + jj) * TPB + tid] = vx;
-                    s_c[(1 * LJ + jj) * TPB + tid] = vy;
-                    s_c[(2 * LJ + jj) * TPB + tid] = vz;
+                    s_c[(0 * LJ + jj) * PPB + col0 + 32 * h] = vx;
+                    s_c[(1 * LJ + jj) * PPB + col0 + 32 * h] = vy;
+                    s_c[(2 * LJ + jj) * PPB + col0 + 32 * h] = vz;
                 }
             }
 #pragma unroll 1
             for (int jj = 0; jj < LJ; jj++) {
                 const float4 lp = s_lparam[c * LJ + jj];
                 if (lp.w == 0.f) continue;                              // padding atom (warp-uniform)
-                const float lcx = s_c[(0 * LJ + jj) * TPB + tid], lcy = s_c[(1 * LJ + jj) * TPB + tid],
-                            lcz = s_c[(2 * LJ + jj) * TPB + tid];
-                const float2 nlx = make_float2(-lcx, -lcx), nly = make_float2(-lcy, -lcy), nlz = make_float2(-lcz, -lcz);
-                // bounding box of this ligand atom over the warp's 32 poses
-                float lo[3] = {lcx, lcy, lcz}, hi[3] = {lcx, lcy, lcz};
-                unsigned long long gmask = ~0ull;                       // near mask of the tile's groups
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    lo[0] = warp_min(lcx); lo[1] = warp_min(lcy); lo[2] = warp_min(lcz);
-                    hi[0] = warp_max(lcx); hi[1] = warp_max(lcy); hi[2] = warp_max(lcz);
-                    // ---- level 1: which groups of 32 receptor atoms can be within 12 A of this atom? ----
-                    unsigned gm[2];
+                float px[PPT], py[PPT], pz[PPT];
 #pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const int g = r * 32 + lane;
-                        bool near = false;
-                        if (g < nb) {
-                            const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
-                            float gx = fmaxf(0.f, fmaxf(blo.x - hi[0], lo[0] - bhi.x));
-                            float gy = fmaxf(0.f, fmaxf(blo.y - hi[1], lo[1] - bhi.y));
-                            float gz = fmaxf(0.f, fmaxf(blo.z - hi[2], lo[2] - bhi.z));
-                            near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
-                        }
-                        gm[r] = __ballot_sync(0xffffffffu, near);
-                    }
-                    gmask = ((unsigned long long)gm[1] << 32) | gm[0];
+                for (int h = 0; h < PPT; h++) {
+                    px[h] = s_c[(0 * LJ + jj) * PPB + col0 + 32 * h];
+                    py[h] = s_c[(1 * LJ + jj) * PPB + col0 + 32 * h];
+                    pz[h] = s_c[(2 * LJ + jj) * PPB + col0 + 32 * h];
                 }
-                const float qjs = lp.z * wscale;
-                // ---- one list per receptor element: A_i A_j, B_i B_j are invariants of the pair loop ----
-#pragma unroll 1
-                for (int ty = 0; ty < a.n_types; ty++) {
-                    const int g_lo = max(a.type_g0[ty], b0) - b0, g_hi = min(a.type_g0[ty + 1], b0 + nb) - b0;
-                    if (g_lo >= g_hi) continue;
-                    const float AAs = a.type_A[ty] * lp.x * wscale, BBs = a.type_B[ty] * lp.y * wscale;
-                    const float2 AA = make_float2(AAs, AAs), nBB = make_float2(-BBs, -BBs);
-                    // ---- level 2: per-atom test, 4 groups per step (independent loads and tests), survivors
-                    //      compacted into the warp's list; the list is consumed 8 atoms at a time ----
-                    int n = 0;
-                    for (int g4 = g_lo; g4 < g_hi || n > 0; g4 += 4) {
-                        if (g4 < g_hi) {
-                            const unsigned m4 = (unsigned)(gmask >> g4) & (0xfu >> max(0, 4 - (g_hi - g4)));
-                            if (m4 != 0u) {
-                                bool nr[4];
-                                float4 pa[4];
+                // ---- centre and radius of this ligand atom's positions over the warp's 64 poses ----
+                const float cx = 0.5f * (warp_min(fminf(px[0], px[1])) + warp_max(fmaxf(px[0], px[1])));
+                const float cy = 0.5f * (warp_min(fminf(py[0], py[1])) + warp_max(fmaxf(py[0], py[1])));
+                const float cz = 0.5f * (warp_min(fminf(pz[0], pz[1])) + warp_max(fmaxf(pz[0], pz[1])));
+                float l2[PPT];
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    // (slots past the tile are never selected: clamp the address, keep the predicate)
-                                    pa[u] = s_atom[min((g4 + u) * kBlob + lane, tile_atoms - 1)];
-                                    nr[u] = ((m4 >> u) & 1u) && pa[u].x < 0.5f * kFarAway;
-                                    if (VARIANT == MMO_VARIANT_SHIFTED) {
-                                        float gx = fmaxf(0.f, fmaxf(lo[0] - pa[u].x, pa[u].x - hi[0]));
-                                        float gy = fmaxf(0.f, fmaxf(lo[1] - pa[u].y, pa[u].y - hi[1]));
-                                        float gz = fmaxf(0.f, fmaxf(lo[2] - pa[u].z, pa[u].z - hi[2]));
-                                        nr[u] = nr[u] && fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < 144.0f;
-                                    }
-                                }
+                for (int h = 0; h < PPT; h++) {
+                    px[h] -= cx; py[h] -= cy; pz[h] -= cz;              // l' = l - c
+                    l2[h] = fmaf(pz[h], pz[h], fmaf(py[h], py[h], px[h] * px[h]));
+                }
+                const float rho2 = warp_max(fmaxf(l2[0], l2[1]));
+                const bool expand = rho2 <= kRhoExpand2;
+                const float reach = 12.0f + sqrtf(rho2) * 1.0001f + 1e-4f;
+                const float reach2 = reach * reach;
+                float m2x[PPT], m2y[PPT], m2z[PPT];
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const unsigned bm = __ballot_sync(0xffffffffu, nr[u]);
-                                    if (nr[u]) {
-                                        const int slot = n + __popc(bm & lt_mask);
-                                        s_lx[slot] = pa[u].x; s_ly[slot] = pa[u].y; s_lz[slot] = pa[u].z;
-                                        s_lq[slot] = pa[u].w * qjs;
-                                    }
-                                    n += __popc(bm);
-                                }
-                            }
-                            if (n <= LIST_CAP - 128 - 8 && g4 + 4 < g_hi) continue;       // room for 4 more groups
+                for (int h = 0; h < PPT; h++) {
+                    const float m = expand ? -2.0f : -1.0f;
+                    m2x[h] = m * px[h]; m2y[h] = m * py[h]; m2z[h] = m * pz[h];
+                }
+                // ---- level 1: which groups of 16 receptor atoms can be within 12 A of these positions?
+                //      lane g tests group box g; the near group ids are compacted into s_near ----
+                int ng = 0;
+#pragma unroll
+                for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
+                    const int g = r * 32 + lane;
+                    bool near = g < nb;
+                    if (VARIANT == MMO_VARIANT_SHIFTED && near) {
+                        const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
+                        const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
+                        const float gy = fmaxf(0.f, fmaxf(blo.y - cy, cy - bhi.y));
+                        const float gz = fmaxf(0.f, fmaxf(blo.z - cz, cz - bhi.z));
+                        near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+                    }
+                    const unsigned gm = __ballot_sync(0xffffffffu, near);
+                    if (near) s_near[ng + __popc(gm & lt_mask)] = (uint8_t)g;
+                    ng += __popc(gm);
+                }
+                if (lane < 4) s_near[ng + lane] = (uint8_t)tile_groups;        // pad with the dummy group
+                __syncwarp();
+                const float qjs = lp.z * wscale, Ajs = lp.x * wscale, nBjs = -lp.y * wscale;
+                // ---- level 2: the atoms of four near groups per step, two per lane (independent loads and
+                //      tests); survivors are compacted into the warp's list, which is consumed whenever it
+                //      cannot take another step ----
+                int n = 0;
+                for (int i = 0; i < ng || n > 0; i += 4) {
+                    const bool more = i < ng;
+                    if (more) {
+                        const int atomA = s_near[i + (lane >> 4)] * kBlob + (lane & 15);
+                        const int atomB = s_near[i + 2 + (lane >> 4)] * kBlob + (lane & 15);
+                        const float4 pa = s_atom[atomA], pb = s_atom[atomB];
+                        const int ea = s_elt[atomA], eb = s_elt[atomB];
+                        const float Xa = pa.x - cx, Ya = pa.y - cy, Za = pa.z - cz;
+                        const float Xb = pb.x - cx, Yb = pb.y - cy, Zb = pb.z - cz;
+                        const float Sa = fmaf(Za, Za, fmaf(Ya, Ya, Xa * Xa)), Sb = fmaf(Zb, Zb, fmaf(Yb, Yb, Xb * Xb));
+                        const bool na = VARIANT == MMO_VARIANT_SHIFTED ? Sa < reach2 : pa.x < 0.5f * kFarAway;
+                        const bool nb_ = VARIANT == MMO_VARIANT_SHIFTED ? Sb < reach2 : pb.x < 0.5f * kFarAway;
+                        const unsigned bma = __ballot_sync(0xffffffffu, na), bmb = __ballot_sync(0xffffffffu, nb_);
+                        if (na) {
+                            const float2 tab = s_tab[ea];
+                            float *e = s_l + n + __popc(bma & lt_mask);
+                            e[0 * LIST_CAP] = Xa; e[1 * LIST_CAP] = Ya; e[2 * LIST_CAP] = Za; e[3 * LIST_CAP] = Sa;
+                            e[4 * LIST_CAP] = pa.w * qjs; e[5 * LIST_CAP] = tab.x * Ajs; e[6 * LIST_CAP] = tab.y * nBjs;
                         }
-                        if (n == 0) continue;
-                        // ---- process the list: 4 packed chains = 8 pairs per step ----
-                        if (STATS) n_eval += (unsigned long long)n;
-                        const int n8 = (n + 7) & ~7;
-                        if (lane < n8 - n) {                                 // pad with far-away, charge-free atoms
-                            s_lx[n + lane] = kFarAway; s_ly[n + lane] = kFarAway; s_lz[n + lane] = kFarAway;
-                            s_lq[n + lane] = 0.f;
+                        n += __popc(bma);
+                        if (nb_) {
+                            const float2 tab = s_tab[eb];
+                            float *e = s_l + n + __popc(bmb & lt_mask);
+                            e[0 * LIST_CAP] = Xb; e[1 * LIST_CAP] = Yb; e[2 * LIST_CAP] = Zb; e[3 * LIST_CAP] = Sb;
+                            e[4 * LIST_CAP] = pb.w * qjs; e[5 * LIST_CAP] = tab.x * Ajs; e[6 * LIST_CAP] = tab.y * nBjs;
+                        }
+                        n += __popc(bmb);
+                        if (n <= LIST_CAP - 64 && i + 4 < ng) continue;          // room for another step
+                    }
+                    if (n > 0) {
+
+                        // ---- consume the list: 2 poses x 2 packed chains = 8 pairs per step ----
+                        if (STATS) n_eval += (unsigned long long)n * (unsigned)(valid[0] + valid[1]);
+                        const int n4 = (n + 3) & ~3;
+                        if (lane < n4 - n) {                              // pad with far-away, inert atoms
+                            float *e = s_l + n + lane;
+                            e[0 * LIST_CAP] = kFarAway; e[1 * LIST_CAP] = kFarAway; e[2 * LIST_CAP] = kFarAway;
+                            e[3 * LIST_CAP] = 3.0f * kFarAway * kFarAway;
+                            e[4 * LIST_CAP] = 0.f; e[5 * LIST_CAP] = 0.f; e[6 * LIST_CAP] = 0.f;
                         }
                         __syncwarp();
-                        float2 f[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) f[i] = make_float2(0.f, 0.f);
-                        int since = 0;
-#pragma unroll 1
-                        for (int k = 0; k < n8; k += 8) {
-                            const float4 X0 = *(const float4 *)(s_lx + k), X1 = *(const float4 *)(s_lx + k + 4);
-                            const float4 Y0 = *(const float4 *)(s_ly + k), Y1 = *(const float4 *)(s_ly + k + 4);
-                            const float4 Z0 = *(const float4 *)(s_lz + k), Z1 = *(const float4 *)(s_lz + k + 4);
-                            const float4 Q0 = *(const float4 *)(s_lq + k), Q1 = *(const float4 *)(s_lq + k + 4);
-                            float2 r2[4];
-                            f[0] = pair2<VARIANT>(make_float2(X0.x, X0.y), make_float2(Y0.x, Y0.y), make_float2(Z0.x, Z0.y),
-                                                  make_float2(Q0.x, Q0.y), nlx, nly, nlz, AA, nBB, a.H, f[0], r2[0]);
-                            f[1] = pair2<VARIANT>(make_float2(X0.z, X0.w), make_float2(Y0.z, Y0.w), make_float2(Z0.z, Z0.w),
-                                                  make_float2(Q0.z, Q0.w), nlx, nly, nlz, AA, nBB, a.H, f[1], r2[1]);
-                            f[2] = pair2<VARIANT>(make_float2(X1.x, X1.y), make_float2(Y1.x, Y1.y), make_float2(Z1.x, Z1.y),
-                                                  make_float2(Q1.x, Q1.y), nlx, nly, nlz, AA, nBB, a.H, f[2], r2[2]);
-                            f[3] = pair2<VARIANT>(make_float2(X1.z, X1.w), make_float2(Y1.z, Y1.w), make_float2(Z1.z, Z1.w),
-                                                  make_float2(Q1.z, Q1.w), nlx, nly, nlz, AA, nBB, a.H, f[3], r2[3]);
-                            if (STATS) {
-#pragma unroll
-                                for (int i = 0; i < 4; i++) n_in += (r2[i].x < 144.0f) + (r2[i].y < 144.0f);
-                            }
-                            if (++since == kSumEvery) {
-                                const float2 h = __fadd2_rn(__fadd2_rn(f[0], f[1]), __fadd2_rn(f[2], f[3]));
-                                acc += (double)(h.x + h.y);
-#pragma unroll
-                                for (int i = 0; i < 4; i++) f[i] = make_float2(0.f, 0.f);
-                                since = 0;
-                            }
-                        }
-                        if (since != 0) {
-                            const float2 h = __fadd2_rn(__fadd2_rn(f[0], f[1]), __fadd2_rn(f[2], f[3]));
-                            acc += (double)(h.x + h.y);
-                        }
+                        if (expand) run_list<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, n_in);
+                        else run_list<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, n_in);
                         n = 0;
                         __syncwarp();
                     }
@@ -292,10 +357,16 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
             __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
         }
     }
-    if (valid) out[p] = acc;
-    if (STATS && valid) {
+#pragma unroll
+    for (int h = 0; h < PPT; h++) {
+        if (valid[h]) out[(int64_t)blockIdx.y * n_poses + (int64_t)blockIdx.x * PPB + col0 + 32 * h] = acc[h];
+    }
+    if (STATS) {
+        unsigned long long tin = 0;
+#pragma unroll
+        for (int h = 0; h < PPT; h++) tin += valid[h] ? n_in[h] : 0ull;
         atomicAdd(a.stats + 0, n_eval);
-        atomicAdd(a.stats + 1, n_in);
+        atomicAdd(a.stats + 1, tin);
     }
 }
 
@@ -323,7 +394,8 @@ struct FixArgs {
 
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(128)
-hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ out) {
+hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *__restrict__ part, int n_split,
+                double *__restrict__ out) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_poses) return;
     PoseRT P;
@@ -380,7 +452,10 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, double *__restrict__ ou
             }
         }
     }
-    out[p] += corr;
+    // the fast kernel's partial sums (one per chunk split), added in a fixed order
+    double e = 0.0;
+    for (int k = 0; k < n_split; k++) e += part[(int64_t)k * n_poses + p];
+    out[p] = e + corr;
     if (STATS) atomicAdd(a.stats + 2, n_fix);
 }
 
@@ -437,10 +512,8 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     MMO_TRY(ensure_fix_tables((double)H));
     FastArgs fa;
     fa.n_blobs = rec->n_blobs;
-    fa.n_types = rec->n_types;
-    for (int t = 0; t <= kEltTab; t++) fa.type_g0[t] = t <= rec->n_types ? rec->type_g0[t] : rec->n_blobs;
-    for (int t = 0; t < kEltTab; t++) { fa.type_A[t] = rec->type_A[t]; fa.type_B[t] = rec->type_B[t]; }
-    fa.xyzq = rec->xyzq.p; fa.blob_box = rec->blob_box.p;
+    for (int e = 0; e < kEltTab; e++) vdw_factors(e, &fa.tab_A[e], &fa.tab_B[e]);
+    fa.xyzq = rec->xyzq.p; fa.gelt = rec->gelt.p; fa.blob_box = rec->blob_box.p;
     for (int d = 0; d < 3; d++) fa.origin[d] = rec->origin[d];
     fa.L = lig->n;
     fa.n_fast = lig->n_fast;
@@ -463,28 +536,38 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.stats = g_stats.p;
 
     if (collect_stats) MMO_CUDA(cudaMemsetAsync(g_stats.p, 0, 4 * sizeof(unsigned long long), R.stream));
-    const unsigned blocks = (unsigned)((n_poses + TPB - 1) / TPB);
-    // receptor tile: everything when it fits (<= 64 groups = 2048 atoms), so that 2 blocks stay resident per SM
+    const unsigned blocks = (unsigned)((n_poses + PPB - 1) / PPB);
+    // receptor tile: everything when it fits (<= 128 groups = 2048 atoms), so that 2 blocks stay resident per SM
     const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
-    const size_t smem = ((size_t)tile_blobs * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
-                        (size_t)3 * LJ * TPB * sizeof(float) + (size_t)(TPB / 32) * 4 * LIST_CAP * sizeof(float);
+    const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
+                        16 * sizeof(float2) + (size_t)3 * LJ * PPB * sizeof(float) +
+                        (size_t)(TPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob +
+                        (size_t)(TPB / 32) * NEAR_CAP + 16;
+    // chunk splits: enough blocks for >= 24 waves of 2 blocks per SM, so that the last wave costs little
+    const int n_chunks = lig->n_fast / LJ;
+    const int64_t want_blocks = 24LL * 2 * R.sm_count;
+    const int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (want_blocks + blocks - 1) / blocks));
+    DevBuf<double> part;
+    if (n_split > 1) MMO_TRY(part.alloc((size_t)n_split * (size_t)n_poses));
+    double *d_part = n_split > 1 ? part.p : d_out;
+    const dim3 grid(blocks, n_split);
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
         MMO_TRY(set_fast_smem(smem));
         {
         KernelScope ks(K_DIRECT_FP32);
-        if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
-        else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
-        else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
-        else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_out);
+        if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
+        else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
+        else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
+        else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
         }
         MMO_LAUNCH_CHECK();
         KernelScope ks2(K_HARD_FIX);
         const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
-        if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_out);
-        else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_out);
-        else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_out);
-        else hard_fix_kernel<MMO_VARIANT_GLOBAL, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_out);
+        if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
+        else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
+        else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
+        else hard_fix_kernel<MMO_VARIANT_GLOBAL, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
         MMO_LAUNCH_CHECK();
     } else {
         MMO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_poses * sizeof(double), R.stream));

@@ -1,5 +1,5 @@
 // molecules.cu -- receptor / ligand handles: host-side preparation of the HBM layouts.
-//   receptor: original-order fp64 SoA (strict kernels) + element-sorted fp32 k-d groups of kBlob atoms
+//   receptor: original-order fp64 SoA (strict kernels) + fp32 k-d groups of kBlob atoms
 //             with bounding boxes (fast kernel) + close-contact voxel lists (fp64 correction pass)
 //   ligand  : template conformer, fp32 vdW factors, interacting-pair list, rotatable bonds
 // Reference data model: src/mol.ml:17-35 (Mol.t), src/UFF.ml:10-51, src/ptable.ml:41-54.
@@ -58,7 +58,7 @@ void kd_order(int n, const double *x, const double *y, const double *z, int leaf
 
 // vdW factors of the A/B form: d_ij*(p6^2 - 2 p6) = (A_i A_j) s^6 - (B_i B_j) s^3 with s = 1/r^2,
 // A = sqrt(D) x^6, B = sqrt(2 D) x^3 (x_ij = sqrt(x_i x_j), d_ij = sqrt(D_i D_j), src/UFF.ml:44-50)
-static void vdw_factors(int elt, float *A, float *B) {
+void vdw_factors(int elt, float *A, float *B) {
     if (elt >= kNumElt) { *A = NAN; *B = NAN; return; }
     double x = kEltXi[elt], d = kEltDi[elt];
     double x3 = x * x * x;
@@ -97,54 +97,34 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     }
     for (int d = 0; d < 3; d++) r->origin[d] = 0.5 * (lo[d] + hi[d]);
 
-    // ---- typed groups: atoms sorted by element, then k-d leaves of kBlob spatially close atoms inside
-    //      every element (A_i A_j and B_i B_j become loop invariants of the pair loop)
-    std::vector<float4> xyzq;
-    std::vector<float4> box;
-    r->n_types = 0;
-    r->n_blobs = 0;
-    for (int e = 0; e < kEltTab; e++) {
-        std::vector<int> members;
-        for (int i = 0; i < n; i++)
-            if (elt[i] == e) members.push_back(i);
-        if (members.empty()) continue;
-        const int ne = (int)members.size();
-        std::vector<double> ex(ne), ey(ne), ez(ne);
-        for (int k = 0; k < ne; k++) { ex[k] = xs[members[k]]; ey[k] = ys[members[k]]; ez[k] = zs[members[k]]; }
-        std::vector<int> order;
-        kd_order(ne, ex.data(), ey.data(), ez.data(), kBlob, order);
-        const int t = r->n_types++;
-        r->type_elt[t] = e;
-        r->type_g0[t] = r->n_blobs;
-        vdw_factors(e, &r->type_A[t], &r->type_B[t]);
-        const int nb = (ne + kBlob - 1) / kBlob;
-        for (int b = 0; b < nb; b++) {
-            float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
-            for (int s = 0; s < kBlob; s++) {
-                int k = b * kBlob + s;
-                if (k < ne) {
-                    int i = members[order[k]];
-                    float4 v;
-                    v.x = (float)(xs[i] - r->origin[0]);
-                    v.y = (float)(ys[i] - r->origin[1]);
-                    v.z = (float)(zs[i] - r->origin[2]);
-                    v.w = (float)(kElecWeight * q[i]);
-                    xyzq.push_back(v);
-                    float p[3] = {v.x, v.y, v.z};
-                    for (int d = 0; d < 3; d++) { blo[d] = fminf(blo[d], p[d]); bhi[d] = fmaxf(bhi[d], p[d]); }
-                } else {   // padding: far away, no charge -> never listed, contributes exactly 0
-                    xyzq.push_back(make_float4(kFarAway, kFarAway, kFarAway, 0.f));
-                }
-            }
-            box.push_back(make_float4(blo[0], blo[1], blo[2], 0.f));
-            box.push_back(make_float4(bhi[0], bhi[1], bhi[2], 0.f));
-        }
-        r->n_blobs += nb;
-    }
-    r->type_g0[r->n_types] = r->n_blobs;
+    // ---- k-d leaves -> groups of kBlob spatially close atoms (first level of distance culling); the
+    //      element of every slot is kept beside it, its vdW factors come from a 13-entry table
+    std::vector<int> order;
+    kd_order(n, xs, ys, zs, kBlob, order);
+    r->n_blobs = (n + kBlob - 1) / kBlob;
     r->n_pad = r->n_blobs * kBlob;
-    if (xyzq.empty()) { xyzq.push_back(make_float4(kFarAway, kFarAway, kFarAway, 0.f)); }
-    if (box.empty()) { box.resize(2, make_float4(0.f, 0.f, 0.f, 0.f)); }
+    std::vector<float4> xyzq(std::max(1, r->n_pad), make_float4(kFarAway, kFarAway, kFarAway, 0.f));
+    std::vector<uint8_t> gelt(std::max(1, r->n_pad), 0);
+    std::vector<float4> box((size_t)std::max(1, r->n_blobs) * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int b = 0; b < r->n_blobs; b++) {
+        float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int s = 0; s < kBlob; s++) {
+            int k = b * kBlob + s;
+            if (k >= n) break;        // padding slots stay far away and charge-free: never listed
+            int i = order[k];
+            float4 v;
+            v.x = (float)(xs[i] - r->origin[0]);
+            v.y = (float)(ys[i] - r->origin[1]);
+            v.z = (float)(zs[i] - r->origin[2]);
+            v.w = (float)(kElecWeight * q[i]);
+            xyzq[k] = v;
+            gelt[k] = (uint8_t)elt[i];
+            float p[3] = {v.x, v.y, v.z};
+            for (int d = 0; d < 3; d++) { blo[d] = fminf(blo[d], p[d]); bhi[d] = fmaxf(bhi[d], p[d]); }
+        }
+        box[(size_t)b * 2] = make_float4(blo[0], blo[1], blo[2], 0.f);
+        box[(size_t)b * 2 + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
+    }
 
     // ---- close-contact voxel lists: atoms within r_list of any point of the voxel (conservative)
     // 1 A voxels (fewer candidates per lookup) while the table stays small, 2 A otherwise
@@ -196,7 +176,7 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
             if ((rc = r->xyz32v.upload(v32))) break;
         }
         if ((rc = r->x.upload(r->hx)) || (rc = r->y.upload(r->hy)) || (rc = r->z.upload(r->hz)) ||
-            (rc = r->q.upload(r->hq)) || (rc = r->elt.upload(elt)) || (rc = r->xyzq.upload(xyzq)) ||
+            (rc = r->q.upload(r->hq)) || (rc = r->elt.upload(elt)) || (rc = r->xyzq.upload(xyzq)) || (rc = r->gelt.upload(gelt)) ||
             (rc = r->blob_box.upload(box)) || (rc = r->vox_off.upload(cnt)) ||
             (rc = r->vox_idx.upload(idx)))
             break;

@@ -48,10 +48,47 @@ def test_fp32_within_tolerance_including_clashes(gpu, orc, c2, c2_roi_rec, handl
         want = orc.ene_inter(c2_roi_rec, m.q, m.anum, X, Y, Z, shifted=shifted)
         got = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP32)
         ok = tol_ok(got, want)
+        ratio = np.abs(got - want) / np.maximum(1e-6 * np.abs(want), 1e-4)
+        print(f"random poses shifted={shifted}: worst |err|/tol = {ratio.max():.3f}, median {np.median(ratio):.4f}")
         assert ok.all(), f"worst: {np.abs(got - want)[~ok].max()} at E={want[~ok]}"
         got_c = gpu.Mol._score(rec, lig, variant, gpu.PREC_FP32, X, Y, Z)
         assert tol_ok(got_c, want).all()
     assert (want > 1e3).sum() > 50 and (want < 0).sum() > 0      # the sample holds clashes and good poses
+
+
+def _coherent_poses(c2, n, seed, dtheta):
+    """n poses per warp-sized family: one base rotation composed with rotations by < dtheta rad, shared
+    translation -- what a warp of the scan driver sees (k-d ordered SO(3) sample on one lattice point)"""
+    rng = np.random.default_rng(seed)
+    base = workloads.random_rotations(n // 64 + 1, rng)
+    R = np.empty((n, 9))
+    t = np.empty((n, 3))
+    for i in range(n):
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        th = rng.uniform(-dtheta, dtheta)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        dR = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+        R[i] = (dR @ base[i // 64].reshape(3, 3)).reshape(9)
+        fam = np.random.default_rng(seed * 1000 + i // 64)
+        v = fam.normal(size=3); v *= fam.uniform(0, 7.0) / np.linalg.norm(v)
+        t[i] = np.asarray(c2["roi"][:3]) + v
+    return R, t
+
+
+@pytest.mark.parametrize("dtheta", [0.02, 0.15, 0.6])
+def test_fp32_coherent_warps_within_tolerance(gpu, orc, c2, c2_roi_rec, handles, dtheta):
+    """warps of similar poses take the cloud-centred expanded form of r^2 (small dtheta) or the
+    difference form (large dtheta): both must honour the accuracy contract"""
+    rec, lig = handles
+    m = c2["lig"]
+    R, t = _coherent_poses(c2, 64 * 12 + 7, seed=21, dtheta=dtheta)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    for shifted, variant in ((True, gpu.VARIANT_SHIFTED), (False, gpu.VARIANT_GLOBAL)):
+        want = orc.ene_inter(c2_roi_rec, m.q, m.anum, X, Y, Z, shifted=shifted)
+        got = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP32)
+        ratio = np.abs(got - want) / np.maximum(1e-6 * np.abs(want), 1e-4)
+        print(f"dtheta={dtheta} shifted={shifted}: worst |err|/tol = {ratio.max():.3f}, median {np.median(ratio):.4f}")
+        assert (ratio <= 1.0).all(), f"worst ratio {ratio.max()} at E={want[ratio.argmax()]}"
 
 
 def test_fp32_far_away_pose_is_exactly_zero(gpu, c2, handles):
