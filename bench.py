@@ -85,6 +85,10 @@ def cpu_sample(c2, rec_m, rot, points_xyz, n_poses, nthreads):
     return time.perf_counter() - t0
 
 
+def poses_last_slab(SR, pps):
+    return pps * N_ROT
+
+
 def lattice_points(roi, step):
     """in-ROI lattice nodes in the reference's loop order (lds.ml:1065-1091)"""
     import oracle
@@ -219,6 +223,11 @@ def main():
     stat_poses = SR.n_scored
     pairs_eval_per_pose = SR.pairs_evaluated / max(1, stat_poses)
     pairs_in_per_pose = SR.pairs_inside / max(1, stat_poses)
+    a_, b_, c_, f_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    ck(L.mmo_last_pair_stats(C.byref(a_), C.byref(b_), C.byref(c_)))      # the last slab of the accounting pass
+    ck(L.mmo_last_fix_stats(C.byref(f_)))
+    fix_pairs_per_pose = c_.value / max(1, poses_last_slab(SR, pps))
+    flagged_per_pose = f_.value / max(1, poses_last_slab(SR, pps))
     ck(L.mmo_scan_destroy(statjob))
 
     # ---- device-resident timed region --------------------------------------------------------------
@@ -335,6 +344,7 @@ def main():
                        "parallelism": f"lattice-point slabs dealt round-robin to {world} GPU(s), no data-path collective, top-k merged by one NCCL all-gather"},
             "pair_interactions_per_s": pairs_nominal,
             "pairs_evaluated_per_pose": pairs_eval_per_pose, "pairs_inside_cutoff_per_pose": pairs_in_per_pose,
+            "fp64_fix_pairs_per_pose": fix_pairs_per_pose, "atoms_flagged_for_fix_per_pose": flagged_per_pose,
             "gpu_launches": launches,
             "e2e": {"value": e2e_poses / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "mmo_scan() one-shot, host buffers"},

@@ -134,6 +134,8 @@ int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const
 /* statistics of the last FP32 direct launch: pairs whose distance was evaluated, pairs inside the
  * 12 A cut-off, close-contact pairs re-evaluated in fp64 */
 int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64);
+/* (pose, ligand atom) combinations the FP32 kernel flagged for the fp64 close-contact pass in the last launch */
+int mmo_last_fix_stats(int64_t *atoms_flagged);
 /* pair statistics cost two extra instructions per pair: off by default, switch on for accounting runs */
 int mmo_set_collect_stats(int on);
 

@@ -134,6 +134,11 @@ int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t
     return MMO_OK;
 }
 
+int mmo_last_fix_stats(int64_t *atoms_flagged) {
+    if (atoms_flagged) *atoms_flagged = rt().stat_flagged;
+    return MMO_OK;
+}
+
 // ------------------------------------------------------------------ energy grids
 static int grid_alloc(double step, const int32_t dims[3], int32_t T, mmo_grid **out) {
     MMO_REQUIRE(out != nullptr, "null grid output pointer");

@@ -36,8 +36,9 @@ struct Runtime {
     void *l2_scratch = nullptr;
     size_t l2_scratch_bytes = 0;
     int64_t launches = 0;
-    int64_t stat_pairs = 0, stat_inside = 0, stat_fp64 = 0;
+    int64_t stat_pairs = 0, stat_inside = 0, stat_fp64 = 0, stat_flagged = 0;
     bool collect_stats = false;
+    int epoch = 0;                   // bumped by every mmo_init: device-resident caches of an older epoch are stale
 };
 Runtime &rt();
 int require_ready();
@@ -61,6 +62,7 @@ inline void count_launch(int n = 1) { rt().launches += n; }
 int pool_alloc(void **p, size_t bytes);
 void pool_free(void *p);
 void pool_trim();
+void scan_drop_caches();   // scan.cu: device-resident rotation set
 
 // simple owning device buffer
 template <typename T>

@@ -30,6 +30,7 @@
 namespace mmo {
 
 constexpr int LJ = 4;            // ligand atoms per chunk (half a k-d leaf of the ligand)
+constexpr int kFixLJ = LJ;
 constexpr int TPB = 256;         // threads per block
 constexpr int PPT = 2;           // poses per thread
 constexpr int PPB = TPB * PPT;   // poses per block
@@ -55,6 +56,7 @@ struct FastArgs {
     const int32_t *forder;           // fast-path position -> original atom index (explicit coordinates)
     const float4 *lparam;            // fast-path order
     float H;                 // clamp on r^2 (fast path) == close-contact threshold (fix pass)
+    float Hflag;             // H plus a margin for the fp32 r^2: atoms with a pair below it are flagged for the fix pass
     unsigned long long *stats;   // [0] pairs evaluated, [1] pairs inside the cut-off (STATS builds)
 };
 
@@ -120,7 +122,7 @@ __device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 S, 
 template <int VARIANT, bool EXPAND, bool STATS>
 __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const float (&m2x)[PPT], const float (&m2y)[PPT],
                                          const float (&m2z)[PPT], const float (&l2)[PPT], float H, double (&acc)[PPT],
-                                         unsigned long long (&n_in)[PPT]) {
+                                         float (&rmin)[PPT], unsigned long long (&n_in)[PPT]) {
     float2 f[PPT][2];
 #pragma unroll
     for (int h = 0; h < PPT; h++) f[h][0] = f[h][1] = make_float2(0.f, 0.f);
@@ -140,6 +142,7 @@ __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const 
             f[h][1] = pair2<VARIANT, EXPAND>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
                                              make_float2(S.z, S.w), make_float2(Q.z, Q.w), make_float2(A.z, A.w),
                                              make_float2(B.z, B.w), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][1], rb);
+            rmin[h] = fminf(fminf(rmin[h], fminf(ra.x, ra.y)), fminf(rb.x, rb.y));   // close contact seen? (fix pass)
             if (STATS) n_in[h] += (ra.x < 144.0f && k < n) + (ra.y < 144.0f && k + 1 < n) + (rb.x < 144.0f && k + 2 < n) +
                                   (rb.y < 144.0f && k + 3 < n);
         }
@@ -168,13 +171,17 @@ __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const 
 // of one field), element bytes [tile_atoms].
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(TPB, 2)
-direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, double *__restrict__ out) {
-    // grid = (pose blocks, chunk splits): block (x, y) sums the ligand chunks c = y, y + gridDim.y, ... of its
-    // poses into out[y * n_poses + p]; the splits are added in a fixed order by hard_fix_kernel
+direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int tile_groups, int n_split,
+                   unsigned long long *__restrict__ work, double *__restrict__ out, uint8_t *__restrict__ flags) {
+    // Persistent blocks (2 per SM), one launch per receptor tile [b0, b0 + nb) of groups.  A work unit is
+    // (64 consecutive poses, chunk split y): the warp that draws it sums the ligand chunks c = y, y + n_split, ...
+    // of those poses into out[y * n_poses + p]; units are handed out through one atomic counter, so warps never
+    // wait for each other and the tail of the launch is one unit long.  The splits (and tiles) are added in a
+    // fixed order by hard_fix_kernel.
     extern __shared__ float4 smem4[];
     const int tile_atoms = tile_groups * kBlob;
     float4 *s_atom = smem4;                                   // tile_atoms + kBlob (a dummy group of far-away atoms)
-    float4 *s_box = s_atom + tile_atoms + kBlob;                      // tile_groups * 2
+    float4 *s_box = s_atom + tile_atoms + kBlob;              // tile_groups * 2
     float4 *s_lparam = s_box + tile_groups * 2;               // n_fast
     float2 *s_tab = (float2 *)(s_lparam + a.n_fast);          // 16
     float *s_c = (float *)(s_tab + 16);                       // 3 * LJ * PPB : field-major, then chunk atom, then pose
@@ -186,43 +193,48 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int col0 = (tid >> 5) * (32 * PPT) + lane;          // this thread's columns of s_c: col0 + 32 h
-    int64_t pp[PPT];
-    bool valid[PPT];
-#pragma unroll
-    for (int h = 0; h < PPT; h++) {
-        const int64_t p = (int64_t)blockIdx.x * PPB + col0 + 32 * h;
-        valid[h] = p < n_poses;
-        pp[h] = valid[h] ? p : n_poses - 1;       // idle slots shadow the last pose, result discarded
-    }
+    // ---- stage the receptor tile once per block ----
     for (int j = tid; j < a.n_fast; j += TPB) s_lparam[j] = a.lparam[j];
     if (tid < kEltTab) s_tab[tid] = make_float2(a.tab_A[tid], a.tab_B[tid]);
+    for (int k = tid; k < nb * kBlob; k += TPB) {
+        s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+        s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
+    }
+    for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
+    if (tid < kBlob) {
+        s_atom[tile_atoms + tid] = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
+        s_elt[tile_atoms + tid] = 0;
+    }
+    __syncthreads();
     // SHIFTED: the weight (144 - r^2)^2 / 144^2 is split between the pair and the list entries
     const float wscale = VARIANT == MMO_VARIANT_SHIFTED ? 1.0f / 20736.0f : 1.0f;
-
-    double acc[PPT];
-    unsigned long long n_eval = 0, n_in[PPT];
-#pragma unroll
-    for (int h = 0; h < PPT; h++) { acc[h] = 0.0; n_in[h] = 0; }
     const int n_chunks = a.n_fast / LJ;
-    const int n_tiles = (a.n_blobs + tile_groups - 1) / tile_groups;
+    const unsigned long long n_groups = (unsigned long long)((n_poses + 32 * PPT - 1) / (32 * PPT));
+    const unsigned long long n_units = n_groups * (unsigned long long)n_split;
+    unsigned long long n_eval = 0, n_in_tot = 0;
 
-    for (int t = 0; t < n_tiles; t++) {
-        // ---- stage a receptor tile (the whole ROI receptor when it fits: one tile, two barriers) ----
-        __syncthreads();
-        const int b0 = t * tile_groups;
-        const int nb = min(tile_groups, a.n_blobs - b0);
-        for (int k = tid; k < nb * kBlob; k += TPB) {
-            s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
-            s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(work, 1ull);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const int y = (int)(u / n_groups);
+        const int64_t p0 = (int64_t)(u - (unsigned long long)y * n_groups) * (32 * PPT) + lane;
+        int64_t pp[PPT];
+        bool valid[PPT];
+        double acc[PPT];
+        unsigned long long n_in[PPT];
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            const int64_t p = p0 + 32 * h;
+            valid[h] = p < n_poses;
+            pp[h] = valid[h] ? p : n_poses - 1;       // idle slots shadow the last pose, result discarded
+            acc[h] = 0.0;
+            n_in[h] = 0;
         }
-        for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
-        if (tid < kBlob) {
-            s_atom[tile_atoms + tid] = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
-            s_elt[tile_atoms + tid] = 0;
-        }
-        __syncthreads();
 
-        for (int c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+        for (int c = y; c < n_chunks; c += n_split) {
+
             // ---- this thread's poses, chunk of ligand atoms: reference arithmetic in double, then fp32 ----
             // (own columns of s_c only: no block barrier needed, __syncwarp orders the warp's accesses)
 #pragma unroll
@@ -250,10 +262,16 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                     s_c[(2 * LJ + jj) * PPB + col0 + 32 * h] = vz;
                 }
             }
+            unsigned cbits[PPT];     // bit jj: atom jj of the chunk has a receptor atom within sqrt(H) (+ margin)
+#pragma unroll
+            for (int h = 0; h < PPT; h++) cbits[h] = 0u;
 #pragma unroll 1
             for (int jj = 0; jj < LJ; jj++) {
                 const float4 lp = s_lparam[c * LJ + jj];
                 if (lp.w == 0.f) continue;                              // padding atom (warp-uniform)
+                float rmin[PPT];
+#pragma unroll
+                for (int h = 0; h < PPT; h++) rmin[h] = 3e38f;
                 float px[PPT], py[PPT], pz[PPT];
 #pragma unroll
                 for (int h = 0; h < PPT; h++) {
@@ -347,26 +365,32 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int tile_groups, do
                             e[4 * LIST_CAP] = 0.f; e[5 * LIST_CAP] = 0.f; e[6 * LIST_CAP] = 0.f;
                         }
                         __syncwarp();
-                        if (expand) run_list<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, n_in);
-                        else run_list<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, n_in);
+                        if (expand) run_list<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
+                        else run_list<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
                         n = 0;
                         __syncwarp();
                     }
                 }
+#pragma unroll
+                for (int h = 0; h < PPT; h++) cbits[h] |= (rmin[h] < a.Hflag ? 1u : 0u) << jj;
+            }
+            // close-contact flags of this (tile, chunk): one byte per pose, read by hard_fix_kernel
+#pragma unroll
+            for (int h = 0; h < PPT; h++) {
+                if (valid[h])
+                    flags[(int64_t)c * n_poses + p0 + 32 * h] = (uint8_t)cbits[h];
             }
             __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
         }
-    }
 #pragma unroll
-    for (int h = 0; h < PPT; h++) {
-        if (valid[h]) out[(int64_t)blockIdx.y * n_poses + (int64_t)blockIdx.x * PPB + col0 + 32 * h] = acc[h];
+        for (int h = 0; h < PPT; h++) {
+            if (valid[h]) out[(int64_t)y * n_poses + p0 + 32 * h] = acc[h];
+            if (STATS && valid[h]) n_in_tot += n_in[h];
+        }
     }
     if (STATS) {
-        unsigned long long tin = 0;
-#pragma unroll
-        for (int h = 0; h < PPT; h++) tin += valid[h] ? n_in[h] : 0ull;
         atomicAdd(a.stats + 0, n_eval);
-        atomicAdd(a.stats + 1, tin);
+        atomicAdd(a.stats + 1, n_in_tot);
     }
 }
 
@@ -384,6 +408,7 @@ struct FixArgs {
     const int32_t *vox_off, *vox_idx;
     int L;
     const double *lx, *ly, *lz, *lq;
+    const int32_t *forder;               // fast-path position -> original atom index
     const int32_t *lelt;
     double H;                            // exactly the fp32 clamp value
     double rinvH;                        // 1/sqrt(H)
@@ -394,74 +419,83 @@ struct FixArgs {
 
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(128)
-hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *__restrict__ part, int n_split,
-                double *__restrict__ out) {
+hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int n_split,
+                const uint8_t *__restrict__ flags, int n_tiles, int n_chunks, double *out) {   // part may alias out
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_poses) return;
-    PoseRT P;
-    if (src.kind != 1) load_pose_rt(src, p, P);
-    double corr = 0.0;
-    unsigned long long n_fix = 0;
-    for (int j = 0; j < a.L; j++) {
-        double x, y, z;
-        if (src.kind == 1) {
-            x = src.xs[p * a.L + j]; y = src.ys[p * a.L + j]; z = src.zs[p * a.L + j];
-        } else {
-            pose_atom_rt(P, __ldg(a.lx + j), __ldg(a.ly + j), __ldg(a.lz + j), x, y, z);
-        }
-        double fx = (x - a.vox_lo[0]) * a.vox_inv, fy = (y - a.vox_lo[1]) * a.vox_inv, fz = (z - a.vox_lo[2]) * a.vox_inv;
-        if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0)) continue;
-        int vi = (int)fx, vj = (int)fy, vk = (int)fz;
-        if (vi >= a.vox_dim[0] || vj >= a.vox_dim[1] || vk >= a.vox_dim[2]) continue;
-        size_t v = (size_t)vi + (size_t)vj * a.vox_dim[0] + (size_t)vk * a.vox_dim[0] * a.vox_dim[1];
-        int k0 = __ldg(a.vox_off + v), k1 = __ldg(a.vox_off + v + 1);
-        if (k0 == k1) continue;
-        const double qj = kElecWeight * __ldg(a.lq + j);
-        const int ej = __ldg(a.lelt + j);
-        const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
-        const float Hf = (float)a.H + 0.5f;
-        for (int k = k0; k < k1; k++) {
-            const int i = __ldg(a.vox_idx + k);
-            // cheap fp32 pre-test (coordinates relative to the voxel grid corner, error << the 0.5 A^2 margin)
-            const float4 rf = __ldg(a.pxyz32 + i);
-            const float fdx = rf.x - xf, fdy = rf.y - yf, fdz = rf.z - zf;
-            if (fdx * fdx + fdy * fdy + fdz * fdz >= Hf) continue;
-            const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
-            const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
-            const double4 ra = make_double4(r01.x, r01.y, r23.x, r23.y);
-            const double dx = ra.x - x, dy = ra.y - y, dz = ra.z - z;
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            if (r2 < a.H) {
-                const int t = __ldg(a.pelt + i) * kEltTab + ej;
-                const double qq = ra.w * qj;
-                const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
-                const double rinv = rsqrt(r2c);
-                const double t2 = __ldg(a.xx + t) * (rinv * rinv);  // (x_ij / r)^2
-                const double p6 = t2 * t2 * t2;
-                const double e = qq * rinv + __ldg(a.dij + t) * (p6 * p6 - 2.0 * p6);
-                const double eH = qq * a.rinvH + __ldg(a.vdwH + t);   // what the fast path evaluated (r clamped at sqrt(H))
-                double d;
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    const double u = 1.0 - r2c * (1.0 / 144.0);
-                    d = (u * u) * e - a.wH * eH;                       // the fast path clamped r^2 in the weight too
-                } else {
-                    d = e - eH;
-                }
-                corr += d;
-                if (STATS) n_fix++;
-            }
-        }
-    }
     // the fast kernel's partial sums (one per chunk split), added in a fixed order
     double e = 0.0;
     for (int k = 0; k < n_split; k++) e += part[(int64_t)k * n_poses + p];
+    double corr = 0.0;
+    unsigned long long n_fix = 0, n_flag = 0;
+    bool have_pose = false;
+    PoseRT P;
+    for (int c = 0; c < n_chunks; c++) {
+        // atoms of chunk c (fast-path order) for which the fast kernel saw a pair below H (any tile)
+        unsigned bits = 0u;
+        for (int t = 0; t < n_tiles; t++) bits |= flags[((int64_t)t * n_chunks + c) * n_poses + p];
+        while (bits != 0u) {
+            const int jj = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            const int j = __ldg(a.forder + c * kFixLJ + jj);
+            if (STATS) n_flag++;
+            double x, y, z;
+            if (src.kind == 1) {
+                x = src.xs[p * a.L + j]; y = src.ys[p * a.L + j]; z = src.zs[p * a.L + j];
+            } else {
+                if (!have_pose) { load_pose_rt(src, p, P); have_pose = true; }
+                pose_atom_rt(P, __ldg(a.lx + j), __ldg(a.ly + j), __ldg(a.lz + j), x, y, z);
+            }
+            const double fx = (x - a.vox_lo[0]) * a.vox_inv, fy = (y - a.vox_lo[1]) * a.vox_inv, fz = (z - a.vox_lo[2]) * a.vox_inv;
+            if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0)) continue;
+            const int vi = (int)fx, vj = (int)fy, vk = (int)fz;
+            if (vi >= a.vox_dim[0] || vj >= a.vox_dim[1] || vk >= a.vox_dim[2]) continue;
+            const size_t v = (size_t)vi + (size_t)vj * a.vox_dim[0] + (size_t)vk * a.vox_dim[0] * a.vox_dim[1];
+            const int k0 = __ldg(a.vox_off + v), k1 = __ldg(a.vox_off + v + 1);
+            if (k0 == k1) continue;
+            const double qj = kElecWeight * __ldg(a.lq + j);
+            const int ej = __ldg(a.lelt + j);
+            const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
+            const float Hf = (float)a.H + 0.5f;
+            for (int k = k0; k < k1; k++) {
+                const int i = __ldg(a.vox_idx + k);
+                // cheap fp32 pre-test (coordinates relative to the voxel grid corner, error << the 0.5 A^2 margin)
+                const float4 r4 = __ldg(a.pxyz32 + i);
+                const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
+                if (fdx * fdx + fdy * fdy + fdz * fdz >= Hf) continue;
+                const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
+                const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
+                const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 < a.H) {
+                    const int tt = __ldg(a.pelt + i) * kEltTab + ej;
+                    const double qq = r23.y * qj;
+                    const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
+                    const double rinv = rsqrt(r2c);
+                    const double t2 = __ldg(a.xx + tt) * (rinv * rinv);  // (x_ij / r)^2
+                    const double p6 = t2 * t2 * t2;
+                    const double ee = qq * rinv + __ldg(a.dij + tt) * (p6 * p6 - 2.0 * p6);
+                    const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
+                    double d;
+                    if (VARIANT == MMO_VARIANT_SHIFTED) {
+                        const double u = 1.0 - r2c * (1.0 / 144.0);
+                        d = (u * u) * ee - a.wH * eH;                      // the fast path clamped r^2 in the weight too
+                    } else {
+                        d = ee - eH;
+                    }
+                    corr += d;
+                    if (STATS) n_fix++;
+                }
+            }
+        }
+    }
     out[p] = e + corr;
-    if (STATS) atomicAdd(a.stats + 2, n_fix);
+    if (STATS) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, n_flag); }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
 static DevBuf<double> g_xx, g_dij, g_vdwH;
-static DevBuf<unsigned long long> g_stats;
+static DevBuf<unsigned long long> g_stats, g_work;
 static double g_vdwH_for = -1.0;
 
 static int ensure_fix_tables(double H) {
@@ -521,6 +555,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     fa.forder = lig->forder.p;
     fa.lparam = lig->fparam.p;
     fa.H = H;
+    fa.Hflag = H * 1.001f + 0.01f;
     fa.stats = g_stats.p;
     FixArgs xa;
     xa.pxyzq = rec->xyzq64.p; xa.pxyz32 = rec->xyz32v.p; xa.pelt = rec->elt.p;
@@ -529,6 +564,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.vox_off = rec->vox_off.p; xa.vox_idx = rec->vox_idx.p;
     xa.L = lig->n;
     xa.lx = lig->x.p; xa.ly = lig->y.p; xa.lz = lig->z.p; xa.lq = lig->q.p; xa.lelt = lig->elt.p;
+    xa.forder = lig->forder.p;
     xa.H = (double)H;
     xa.rinvH = 1.0 / sqrt((double)H);
     xa.wH = (1.0 - (double)H / 144.0) * (1.0 - (double)H / 144.0);
@@ -536,38 +572,53 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.stats = g_stats.p;
 
     if (collect_stats) MMO_CUDA(cudaMemsetAsync(g_stats.p, 0, 4 * sizeof(unsigned long long), R.stream));
-    const unsigned blocks = (unsigned)((n_poses + PPB - 1) / PPB);
     // receptor tile: everything when it fits (<= 128 groups = 2048 atoms), so that 2 blocks stay resident per SM
     const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
     const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
                         16 * sizeof(float2) + (size_t)3 * LJ * PPB * sizeof(float) +
                         (size_t)(TPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob +
                         (size_t)(TPB / 32) * NEAR_CAP + 16;
-    // chunk splits: enough blocks for >= 24 waves of 2 blocks per SM, so that the last wave costs little
+    // work units = (64 poses, chunk split): at least ~20 per resident warp, so that the dynamic hand-out
+    // balances the warps to a few percent; persistent grid of 2 blocks per SM (fewer for small batches)
     const int n_chunks = lig->n_fast / LJ;
-    const int64_t want_blocks = 24LL * 2 * R.sm_count;
-    const int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (want_blocks + blocks - 1) / blocks));
+    const int64_t n_groups = (n_poses + 32 * PPT - 1) / (32 * PPT);
+    const int64_t resident_warps = 2LL * R.sm_count * (TPB / 32);
+    const int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (20 * resident_warps + n_groups - 1) / n_groups));
+    const int64_t n_units = n_groups * n_split;
+    const unsigned blocks = (unsigned)std::min<int64_t>(2LL * R.sm_count, (n_units + TPB / 32 - 1) / (TPB / 32));
+    const int n_tiles = (rec->n_blobs + tile_blobs - 1) / tile_blobs;
+    const int n_parts = n_tiles * n_split;
     DevBuf<double> part;
-    if (n_split > 1) MMO_TRY(part.alloc((size_t)n_split * (size_t)n_poses));
-    double *d_part = n_split > 1 ? part.p : d_out;
-    const dim3 grid(blocks, n_split);
+    if (n_parts > 1) MMO_TRY(part.alloc((size_t)n_parts * (size_t)n_poses));
+    double *d_part = n_parts > 1 ? part.p : d_out;
+    DevBuf<uint8_t> flags;
+    MMO_TRY(flags.alloc((size_t)n_tiles * (size_t)n_chunks * (size_t)n_poses));
+    if (!g_work.p) MMO_TRY(g_work.alloc(64));
+    MMO_REQUIRE(n_tiles <= 64, "receptor too large for the direct kernel (%d tiles of %d atoms)", n_tiles, MAX_TILE_GROUPS * kBlob);
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
         MMO_TRY(set_fast_smem(smem));
+        MMO_CUDA(cudaMemsetAsync(g_work.p, 0, 64 * sizeof(unsigned long long), R.stream));
         {
         KernelScope ks(K_DIRECT_FP32);
-        if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
-        else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
-        else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
-        else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<grid, TPB, smem, R.stream>>>(fa, src, n_poses, tile_blobs, d_part);
+        for (int t = 0; t < n_tiles; t++) {
+            const int b0 = t * tile_blobs, nb = std::min(tile_blobs, rec->n_blobs - b0);
+            double *o = d_part + (size_t)t * n_split * (size_t)n_poses;
+            uint8_t *f = flags.p + (size_t)t * n_chunks * (size_t)n_poses;
+            unsigned long long *w = g_work.p + t;
+            if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
+            else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
+            else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
+            else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
+            MMO_LAUNCH_CHECK();
         }
-        MMO_LAUNCH_CHECK();
+        }
         KernelScope ks2(K_HARD_FIX);
         const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
-        if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
-        else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
-        else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
-        else hard_fix_kernel<MMO_VARIANT_GLOBAL, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_split, d_out);
+        if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        else hard_fix_kernel<MMO_VARIANT_GLOBAL, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
         MMO_LAUNCH_CHECK();
     } else {
         MMO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_poses * sizeof(double), R.stream));
@@ -576,7 +627,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
         unsigned long long h[4];
         MMO_CUDA(cudaMemcpyAsync(h, g_stats.p, sizeof h, cudaMemcpyDeviceToHost, R.stream));
         MMO_CUDA(cudaStreamSynchronize(R.stream));
-        R.stat_pairs = (int64_t)h[0]; R.stat_inside = (int64_t)h[1]; R.stat_fp64 = (int64_t)h[2];
+        R.stat_pairs = (int64_t)h[0]; R.stat_inside = (int64_t)h[1]; R.stat_fp64 = (int64_t)h[2]; R.stat_flagged = (int64_t)h[3];
     }
     return MMO_OK;
 }

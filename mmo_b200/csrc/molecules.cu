@@ -135,7 +135,8 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
         r->vox_edge = (n > 0 && vol <= 2.0e6) ? 1.0 : 2.0;
     }
     const double g = r->vox_edge;
-    const double r_list = sqrt(std::max(r->x_max, 1.0) * 4.5 / kTau);    // 4.5 = largest x_i of src/UFF.ml:22
+    // 4.5 = largest x_i of src/UFF.ml:22; the slack covers the fp32 position the lookup is made with
+    const double r_list = sqrt(std::max(r->x_max, 1.0) * 4.5 / kTau) + 1e-3;
     const double reach = r_list + 0.5 * g * sqrt(3.0);
     for (int d = 0; d < 3; d++) {
         r->vox_lo[d] = lo[d] - r_list - 1e-6;

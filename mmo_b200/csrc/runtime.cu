@@ -224,6 +224,7 @@ int mmo_init(int device) {
     MMO_CUDA(cudaEventCreate(&R.ev0));
     MMO_CUDA(cudaEventCreate(&R.ev1));
     R.launches = 0;
+    R.epoch++;
     R.ready = true;
     return MMO_OK;
 }
@@ -232,6 +233,7 @@ int mmo_shutdown(void) {
     Runtime &R = rt();
     if (!R.ready) return MMO_OK;
     cudaStreamSynchronize(R.stream);
+    scan_drop_caches();
     pool_trim();
     if (R.l2_scratch) cudaFree(R.l2_scratch);
     R.l2_scratch = nullptr;

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <stdlib.h>
+#include <memory>
 
 namespace mmo {
 
@@ -62,13 +63,20 @@ scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restric
     }
 }
 
+struct RotSet {
+    DevBuf<double> rot;
+    DevBuf<int32_t> perm;
+    uint64_t hash = 0;
+    int n = -1;
+    int epoch = -1;
+};
+
 struct ScanJob {
     mmo_scan_params P;
+    std::shared_ptr<RotSet> rs;
     int dims[3];
     double mins[3], q[3];
     std::vector<int64_t> points;           // active lattice points of the requested sub-range
-    DevBuf<double> d_rot;
-    DevBuf<int32_t> d_rot_perm;
     DevBuf<int64_t> d_points, d_frames;
     DevBuf<double> d_E, d_thr, d_cand_s;
     DevBuf<long long> d_cand_f;
@@ -112,14 +120,7 @@ static bool host_clash_and(const mmo_mask *m, double x, double y, double z) {
 // Visiting order of the rotations: k-d leaves of 32 over the stereographic image of the unit
 // quaternions, so that the 32 poses of a warp are similar rotations (tight per-atom boxes in the
 // direct kernel).  Cached on the content of rot9: lds builds the rotation set once per run.
-static const std::vector<int32_t> &rotation_visit_order(int n_rot, const double *rot9) {
-    static std::vector<int32_t> cached;
-    static uint64_t cached_hash = 0;
-    static int cached_n = -1;
-    uint64_t h = 1469598103934665603ull;
-    const uint64_t *w = (const uint64_t *)rot9;
-    for (size_t k = 0; k < (size_t)n_rot * 9; k++) { h ^= w[k]; h *= 1099511628211ull; }
-    if (cached_n == n_rot && cached_hash == h) return cached;
+static void rotation_visit_order(int n_rot, const double *rot9, std::vector<int32_t> &cached) {
     std::vector<double> gx(n_rot), gy(n_rot), gz(n_rot);
     for (int r = 0; r < n_rot; r++) {
         const double *m = rot9 + 9 * (size_t)r;
@@ -147,10 +148,39 @@ static const std::vector<int32_t> &rotation_visit_order(int n_rot, const double 
     std::vector<int> order;
     kd_order(n_rot, gx.data(), gy.data(), gz.data(), 32, order);
     cached.assign(order.begin(), order.end());
-    cached_hash = h;
-    cached_n = n_rot;
-    return cached;
 }
+
+// The rotation set of a run (lds builds it once, SO3.rotations, and scans every ligand with it) stays
+// resident on the device together with its visiting order; a call that passes the same rotations again
+// (same count, same content hash) skips the 72 n_rot bytes upload and the k-d sort.
+static uint64_t hash_words(const uint64_t *w, size_t n) {
+    uint64_t h0 = 1469598103934665603ull, h1 = h0 ^ 0x9e3779b97f4a7c15ull, h2 = h0 ^ 0xc2b2ae3d27d4eb4full, h3 = ~h0;
+    size_t k = 0;
+    for (; k + 4 <= n; k += 4) {        // four independent FNV-1a lanes: ~4 words per cycle
+        h0 = (h0 ^ w[k]) * 1099511628211ull; h1 = (h1 ^ w[k + 1]) * 1099511628211ull;
+        h2 = (h2 ^ w[k + 2]) * 1099511628211ull; h3 = (h3 ^ w[k + 3]) * 1099511628211ull;
+    }
+    for (; k < n; k++) h0 = (h0 ^ w[k]) * 1099511628211ull;
+    return h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7);
+}
+// leaked on purpose: must not run a destructor after the CUDA context / the allocator are gone
+static std::shared_ptr<RotSet> &g_rotset = *new std::shared_ptr<RotSet>();
+void scan_drop_caches() { g_rotset.reset(); }
+static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out) {
+    const uint64_t h = hash_words((const uint64_t *)rot9, (size_t)n_rot * 9);
+    if (g_rotset && g_rotset->n == n_rot && g_rotset->hash == h && g_rotset->epoch == rt().epoch) { out = g_rotset; return MMO_OK; }
+    g_rotset.reset();
+    std::shared_ptr<RotSet> rs = std::make_shared<RotSet>();
+    rs->n = n_rot; rs->hash = h; rs->epoch = rt().epoch;
+    std::vector<int32_t> perm;
+    rotation_visit_order(n_rot, rot9, perm);
+    MMO_TRY(rs->rot.upload(rot9, (size_t)n_rot * 9));
+    MMO_TRY(rs->perm.upload(perm));
+    g_rotset = rs;
+    out = rs;
+    return MMO_OK;
+}
+
 
 static int scan_setup(ScanJob &J) {
     const mmo_scan_params &P = J.P;
@@ -189,8 +219,7 @@ static int scan_setup(ScanJob &J) {
         if (center_filter && host_clash_and(P.vdw_mask, pos[0], pos[1], pos[2])) continue;
         J.points.push_back(p);
     }
-    MMO_TRY(J.d_rot.upload(P.rot9, (size_t)P.n_rot * 9));
-    MMO_TRY(J.d_rot_perm.upload(rotation_visit_order(P.n_rot, P.rot9)));
+    MMO_TRY(get_rotset(P.n_rot, P.rot9, J.rs));
     MMO_TRY(J.d_points.upload(J.points));
     // slab: as many lattice points as fit ~4M candidate poses
     int64_t pts_per_slab = std::max<int64_t>(1, (int64_t)(4 << 20) / std::max(1, P.n_rot));
@@ -217,7 +246,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
     const int64_t pts_per_slab = J.slab_cap / P.n_rot;
     PoseSrc src = {};
     src.kind = 2;
-    src.rot9 = J.d_rot.p;
+    src.rot9 = J.rs->rot.p;
     src.frames = J.d_frames.p;
     src.n_rot = P.n_rot;
     for (int d = 0; d < 3; d++) { src.lat_dims[d] = J.dims[d]; src.lat_min[d] = J.mins[d]; src.lat_q[d] = J.q[d]; }
@@ -233,7 +262,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         J.exact_ready = false;
         MMO_CUDA(cudaMemsetAsync(J.d_counters.p, 0, 2 * sizeof(unsigned long long), R.stream));
         MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &thr, sizeof(double), cudaMemcpyHostToDevice, R.stream));
-        MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, J.d_rot_perm.p, n_cand, J.d_frames.p, J.d_counters.p));
+        MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, J.rs->perm.p, n_cand, J.d_frames.p, J.d_counters.p));
         unsigned long long n_surv = 0;
         MMO_CUDA(cudaMemcpyAsync(&n_surv, J.d_counters.p, sizeof n_surv, cudaMemcpyDeviceToHost, R.stream));
         MMO_CUDA(cudaStreamSynchronize(R.stream));
@@ -248,16 +277,31 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
             if (J.collect_stats) { J.pairs_eval += R.stat_pairs; J.pairs_in += R.stat_inside; }
         }
         const unsigned blocks = (unsigned)((n_surv + 255) / 256);
-        {
-        KernelScope ks(K_REDUCE);
-        scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(J.d_E.p, J.d_frames.p, (int64_t)n_surv, P.e_intra_const,
-                                                         J.d_thr.p, J.d_cand_s.p, J.d_cand_f.p, J.d_counters.p + 1,
-                                                         J.k_eff > 0 ? (unsigned long long)J.slab_cap : 0ull,
-                                                         J.d_block_best.p);
-        }
-        MMO_LAUNCH_CHECK();
+        auto reduce_pass = [&](bool with_candidates) -> int {
+            KernelScope ks(K_REDUCE);
+            scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(J.d_E.p, J.d_frames.p, (int64_t)n_surv, P.e_intra_const,
+                                                             J.d_thr.p, J.d_cand_s.p, J.d_cand_f.p, J.d_counters.p + 1,
+                                                             with_candidates ? (unsigned long long)J.slab_cap : 0ull,
+                                                             J.d_block_best.p);
+            MMO_LAUNCH_CHECK();
+            return MMO_OK;
+        };
         hbest.resize(blocks);
         unsigned long long n_cnd = 0;
+        if (J.k_eff > 0 && thr == INFINITY && blocks >= (unsigned)J.k_eff) {
+            // No running threshold yet (first slab of a scan): the k-th smallest per-block minimum bounds
+            // the k-th best score from above, so only the few poses below it travel to the host.
+            MMO_TRY(reduce_pass(false));
+            MMO_CUDA(cudaMemcpyAsync(hbest.data(), J.d_block_best.p, blocks * sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
+            MMO_CUDA(cudaStreamSynchronize(R.stream));
+            std::vector<double> mins(blocks);
+            for (unsigned b = 0; b < blocks; b++) mins[b] = hbest[b].s;
+            std::nth_element(mins.begin(), mins.begin() + (J.k_eff - 1), mins.end());
+            double est = mins[J.k_eff - 1];
+            if (J.two_stage && est < INFINITY) est = est + 2.0 * fp32_delta(est);
+            MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &est, sizeof(double), cudaMemcpyHostToDevice, R.stream));
+        }
+        MMO_TRY(reduce_pass(J.k_eff > 0));
         MMO_CUDA(cudaMemcpyAsync(hbest.data(), J.d_block_best.p, blocks * sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
         MMO_CUDA(cudaMemcpyAsync(&n_cnd, J.d_counters.p + 1, sizeof n_cnd, cudaMemcpyDeviceToHost, R.stream));
         MMO_CUDA(cudaStreamSynchronize(R.stream));
@@ -316,7 +360,7 @@ static int scan_finalize(ScanJob &J) {
         MMO_TRY(d_e.alloc(n));
         PoseSrc src = {};
         src.kind = 2;
-        src.rot9 = J.d_rot.p;
+        src.rot9 = J.rs->rot.p;
         src.frames = d_fr.p;
         src.n_rot = P.n_rot;
         for (int d = 0; d < 3; d++) { src.lat_dims[d] = J.dims[d]; src.lat_min[d] = J.mins[d]; src.lat_q[d] = J.q[d]; }
