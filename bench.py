@@ -85,6 +85,17 @@ def cpu_sample(c2, rec_m, rot, points_xyz, n_poses, nthreads):
     return time.perf_counter() - t0
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one direct_fp32_kernel launch of this workload, from
+    the committed ncu --set full capture (profiles/traffic.json; never measured under the timed run)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)["direct_fp32_kernel"]
+        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 def poses_last_slab(SR, pps):
     return pps * N_ROT
 
@@ -146,6 +157,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points-per-step", type=int, default=POINTS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefilter-run", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -262,6 +274,43 @@ def main():
     ck(L.mmo_scan_result_get(job, None, None, C.byref(SR)))
     poses_per_step = pps * N_ROT
 
+    # ---- the same scan with the reference's vdW bitmask prefilter on (lds.ml:1094-1097: clashing poses are
+    #      rejected before scoring); reported beside the headline, not instead of it ----------------------
+    prefilter = None
+    if world == 1 and not args.no_prefilter_run:
+        from mmo_b200 import workloads
+        dims = mmo_b200.Grid.from_box(workloads.GRID_STEP, *c2["sim_dims"])
+        m = c2["rec"]
+        mask = mmo_b200.Lds.vdW_volume(m.xs, m.ys, m.zs, m.r, workloads.GRID_STEP, dims)
+        P.vdw_mask = mask.h
+        mjob = C.c_void_p()
+        ck(L.mmo_scan_create(C.byref(P), 0, C.byref(mjob)))
+        nm = C.c_int64()
+        ck(L.mmo_scan_num_points(mjob, C.byref(nm)))
+        msteps = max(1, min(args.steps, nm.value // pps - 1))
+        ck(L.mmo_scan_run(mjob, 0, pps))                       # warm-up slab
+        MR0 = ScanResult()
+        ck(L.mmo_scan_result_get(mjob, None, None, C.byref(MR0)))
+        pf_ms = 0.0
+        for s_ in range(msteps):
+            ck(L.mmo_l2_flush())
+            ck(L.mmo_sync())
+            ck(L.mmo_timer_start())
+            # slabs spread over the whole ROI sphere (pocket, surface and buried lattice points alike)
+            ck(L.mmo_scan_run(mjob, ((1 + s_) * (nm.value // pps - 1) // (msteps + 1)) * pps, pps))
+            ck(L.mmo_timer_stop(C.byref(ms)))
+            pf_ms += ms.value
+        MR = ScanResult()
+        ck(L.mmo_scan_result_get(mjob, None, None, C.byref(MR)))
+        cand = msteps * pps * N_ROT
+        scored = MR.n_scored - MR0.n_scored
+        prefilter = {"candidate_poses_per_s": cand / (pf_ms * 1e-3), "scored_poses_per_s": scored / (pf_ms * 1e-3),
+                     "surviving_fraction": scored / cand, "steps": msteps, "ms_per_step": pf_ms / msteps,
+                     "active_lattice_points": nm.value,
+                     "note": "vdW_clash_OR bitmask (0.5 A grid, all receptor atoms) before scoring, as lds --ext does"}
+        ck(L.mmo_scan_destroy(mjob))
+        P.vdw_mask = None
+
     # ---- end-to-end: host buffers through the one-shot call, copies inside the timed region ---------
     ts = np.empty(TOPK); tf = np.empty(TOPK, np.int64)
     e2e_steps = max(2, min(args.steps, 5))
@@ -350,7 +399,7 @@ def main():
                     "steps": e2e_steps, "api": "mmo_scan() one-shot, host buffers"},
             "roofline": {"bound": "fp32", "kernel": "direct_fp32_kernel", "achieved": achieved, "peak": fp32_peak.value,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak.value if fp32_peak.value else None,
-                         "traffic": None, "peak_source": "measured on this box: FP32 FMA chain (mmo_measure_fp32_peak); "
+                         "traffic": ncu_traffic(), "peak_source": "measured on this box: FP32 FMA chain (mmo_measure_fp32_peak); "
                          "MEASURED_PEAKS.json has no FP32 ALU figure", "kernel_ms_per_launch": k_ms,
                          "kernel_share_of_step": kms.value / dev_ms if dev_ms else None,
                          "hard_fix_ms_per_launch": fix_ms.value / max(1, kn.value),
@@ -359,6 +408,8 @@ def main():
             "result": {"best_score": SR.best_score, "best_frame": SR.best_frame, "topk_merged": top_n,
                        "topk_allgather_ms": (1e3 * t_ag if dist is not None else None)},
         }
+        if prefilter is not None:
+            line["with_vdw_prefilter"] = prefilter
         if not args.no_cpu_baseline and world == 1:
             pts = lattice_points(c2["roi"], TRANS_STEP)
             nthreads = oracle.num_threads()

@@ -18,7 +18,8 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
-        "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__warps_eligible.avg.per_cycle_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -54,8 +55,20 @@ def launches(tag, fn):
 def ncu(tag, kernel, rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    vals = next((r for r in rows[2:] if kernel in r[ki]), rows[2])     # first profiled launch of that kernel
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    if kernel.startswith("direct_fp32"):
+        # per-launch DRAM traffic of the dominant kernel: bench.py's roofline.traffic reads this file
+        import json
+        def _bytes(key):
+            v, u = d[key]
+            return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        json.dump({"direct_fp32_kernel": {"dram_bytes_read": _bytes("dram__bytes_read.sum"),
+                                          "dram_bytes_write": _bytes("dram__bytes_write.sum"),
+                                          "source": f"profiles/{tag}_ncu_{kernel}.md (ncu --set full, one launch of 800k poses)"}},
+                  open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     out = [f"# {tag}: ncu --set full --clock-control none, kernel `{kernel}`", "", f"source: `{os.path.basename(rep)}` (first profiled launch)", "",
            "| metric | value | unit |", "|---|---:|---|"]
     keep_rows = []
@@ -76,4 +89,5 @@ if __name__ == "__main__":
     if sys.argv[2] != "-":
         launches(tag, sys.argv[2])
     if len(sys.argv) > 4:
-        ncu(tag, sys.argv[3], sys.argv[4])
+        for kern in sys.argv[3].split(","):
+            ncu(tag, kern, sys.argv[4])
