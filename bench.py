@@ -313,7 +313,7 @@ def main():
 
     # ---- end-to-end: host buffers through the one-shot call, copies inside the timed region ---------
     ts = np.empty(TOPK); tf = np.empty(TOPK, np.int64)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 20))
     R2 = ScanResult()
     # translate active-point slabs to raw lattice-point sub-ranges for mmo_scan()
     lat = SR.lattice_dims
