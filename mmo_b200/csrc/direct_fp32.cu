@@ -302,6 +302,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 // ---- level 1: which groups of 16 receptor atoms can be within 12 A of these positions?
                 //      lane g tests group box g; the near group ids are compacted into s_near ----
                 int ng = 0;
+                __syncwarp();        // every lane is done reading the previous atom's s_near
 #pragma unroll
                 for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
                     const int g = r * 32 + lane;

@@ -136,3 +136,44 @@ def test_scan_fp64_two_stage_equals_exhaustive_strict_scoring(gpu, orc, c2, setu
     assert np.array_equal(got["top_frames"], frames[order])
     assert np.array_equal(got["top_scores"], e[order])
     assert got["best_frame"] == frames[order[0]] and got["best_score"] == e[order[0]]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+def test_scan_topk_equals_sorting_every_pose(gpu, orc, c2, setup, prec):
+    """size-independent property at a slab large enough for the first-slab threshold estimate (k-th smallest
+    per-block minimum): the scan's top-k and argmin == scoring every pose of the loop nest and sorting by
+    (score, frame).  fp64: two-stage == strict scoring, bit for bit; fp32: within the accuracy contract (the fp32
+    sum of a pose depends on its warp's companions at the 1e-7 level: x' = x - c is centred per warp)."""
+    rec, lig, mask, dims, e_intra = setup
+    n_rot, k = 1500, 7
+    rot = gpu.SO3.rotations(n_rot)
+    roi = (c2["roi"][0] + 3.0, c2["roi"][1], c2["roi"][2], 2.2)
+    p = gpu.PREC_FP32 if prec == "fp32" else gpu.PREC_FP64
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(k, roi, 1.0, rot, lig, rec=rec, e_intra_const=e_intra, prec=p)
+    assert got["n_scored"] == got["n_candidates"] >= 256 * k          # the estimate path is taken
+    # the loop nest of lds.ml:1071-1105 on the host: frame = rot_i + n_rot * (i + j*x_dim + k*xy_dim)
+    ld = got["lattice_dims"]
+    lo = [roi[d] - roi[3] for d in range(3)]
+    R, T, F = [], [], []
+    for kk in range(ld[2]):
+        for j in range(ld[1]):
+            for i in range(ld[0]):
+                pos = (lo[0] + orc.grid_node(1.0, ld[0], i), lo[1] + orc.grid_node(1.0, ld[1], j),
+                       lo[2] + orc.grid_node(1.0, ld[2], kk))
+                if sum((roi[d] - pos[d]) ** 2 for d in range(3)) < roi[3] ** 2:
+                    pt = i + j * ld[0] + kk * ld[0] * ld[1]
+                    R.append(rot); T.append(np.tile(pos, (n_rot, 1))); F.append(np.arange(n_rot) + n_rot * pt)
+    R, T, F = np.concatenate(R), np.concatenate(T), np.concatenate(F)
+    assert len(F) == got["n_candidates"]
+    e = e_intra + gpu.Mol.score_poses(rec, lig, R, T, prec=p)
+    order = np.lexsort((F, e))[:k]
+    if prec == "fp64":
+        assert np.array_equal(got["top_frames"], F[order])
+        assert np.array_equal(got["top_scores"], e[order])
+        assert got["best_frame"] == F[order[0]] and got["best_score"] == e[order[0]]
+    else:
+        assert tol_ok(got["top_scores"], e[order]).all()
+        by_frame = dict(zip(F.tolist(), e.tolist()))
+        for f, s_ in zip(got["top_frames"], got["top_scores"]):      # every reported pose carries its own score
+            assert tol_ok([s_], [by_frame[int(f)]]).all()
+        assert tol_ok([got["best_score"]], [e[order[0]]]).all()
