@@ -122,6 +122,9 @@ int mmo_score_poses(const mmo_receptor *rec, const mmo_ligand *lig, int variant,
 /* device-resident variant (all three pointers are device memory from mmo_dev_alloc) */
 int mmo_score_poses_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
                         int64_t n_poses, const double *d_rot9, const double *d_trans3, double *d_out_E);
+/* the same for explicit coordinates already resident on the device (pose-major, stride = ligand atoms) */
+int mmo_score_coords_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                         int64_t n_poses, const double *d_xs, const double *d_ys, const double *d_zs, double *d_out_E);
 /* Mol.ene_inter_UFF_shifted_bst_components (src/mol.ml:928-956): EW*sum_elec and sum_vdW apart
  * (fp64, ligand-outer order with receptor atoms in index order) */
 int mmo_score_coords_components(const mmo_receptor *rec, const mmo_ligand *lig, int64_t n_poses,
@@ -134,6 +137,12 @@ int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const
 /* statistics of the last FP32 direct launch: pairs whose distance was evaluated, pairs inside the
  * 12 A cut-off, close-contact pairs re-evaluated in fp64 */
 int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64);
+/* Which FP32 kernel scores a pose list (mmo_score_poses / mmo_score_coords; scans always take the pose kernel):
+ * 0 = automatic (item kernel from 32 k pose-atoms on: incoherent lists are sorted by atom position first),
+ * 1 = pose kernel (warp = 64 consecutive poses), 2 = item kernel (shifted variant only: MMO_VARIANT_GLOBAL has
+ * nothing to cull and always takes the pose kernel, or the fp64 kernel beyond 1.2e5 receptor x ligand atom pairs,
+ * where fp32 rounding noise would break the contract).  Same accuracy contract either way. */
+int mmo_direct_set_mode(int mode);
 /* (pose, ligand atom) combinations the FP32 kernel flagged for the fp64 close-contact pass in the last launch */
 int mmo_last_fix_stats(int64_t *atoms_flagged);
 /* pair statistics cost two extra instructions per pair: off by default, switch on for accounting runs */

@@ -89,6 +89,18 @@ int mmo_score_poses_dev(const mmo_receptor *rec, const mmo_ligand *lig, int vari
     return launch_direct_fp32(rec, lig, variant, rt_src(d_rot9, d_trans3), n_poses, d_out_E, rt().collect_stats);
 }
 
+int mmo_score_coords_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
+                         int64_t n_poses, const double *d_xs, const double *d_ys, const double *d_zs, double *d_out_E) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && lig, "mmo_score_coords_dev: null handle");
+    MMO_TRY(check_variant_prec(variant, prec));
+    MMO_REQUIRE(n_poses >= 0, "mmo_score_coords_dev: negative pose count");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(d_xs && d_ys && d_zs && d_out_E, "mmo_score_coords_dev: null buffer");
+    if (prec == MMO_PREC_FP64) return launch_direct_fp64(rec, lig, variant, coords_src(d_xs, d_ys, d_zs), n_poses, d_out_E);
+    return launch_direct_fp32(rec, lig, variant, coords_src(d_xs, d_ys, d_zs), n_poses, d_out_E, rt().collect_stats);
+}
+
 int mmo_score_coords_components(const mmo_receptor *rec, const mmo_ligand *lig, int64_t n_poses,
                                 const double *xs, const double *ys, const double *zs,
                                 double *out_elec, double *out_vdw) {
@@ -131,6 +143,12 @@ int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t
     if (pairs_evaluated) *pairs_evaluated = rt().stat_pairs;
     if (pairs_inside) *pairs_inside = rt().stat_inside;
     if (pairs_fp64) *pairs_fp64 = rt().stat_fp64;
+    return MMO_OK;
+}
+
+int mmo_direct_set_mode(int mode) {
+    MMO_REQUIRE(mode >= 0 && mode <= 2, "mmo_direct_set_mode: mode must be 0 (auto), 1 (pose kernel) or 2 (item kernel)");
+    direct_set_mode(mode);
     return MMO_OK;
 }
 

@@ -45,7 +45,7 @@ int require_ready();
 
 // per-kernel device timing (CUDA events on the library stream), off unless mmo_kernel_timing(1)
 enum KernelId { K_DIRECT_FP32 = 0, K_HARD_FIX, K_DIRECT_FP64, K_INTRA, K_GRID_BUILD, K_INTERP, K_PREFILTER,
-                K_REDUCE, K_VDW_MASK, K_MC, K_COUNT };
+                K_REDUCE, K_VDW_MASK, K_MC, K_ITEM_PREP, K_COUNT };
 struct KernelScope {
     int id;
     bool on;
@@ -118,6 +118,7 @@ struct mmo_receptor {
     int n_pad = 0;                   // n_blobs * kBlob
     int n_blobs = 0;
     double origin[3] = {0, 0, 0};    // fp32 coordinates are relative to this point
+    double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};   // bounding box of the atoms
     // original order, double (strict fp64 kernels)
     mmo::DevBuf<double> x, y, z, q;
     mmo::DevBuf<int32_t> elt;        // compact element index
@@ -191,6 +192,7 @@ struct PoseSrc {
 // kernels' host entry points (defined in the .cu files)
 int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
                        int64_t n_poses, double *d_out, bool collect_stats);
+void direct_set_mode(int mode);          // 0 auto, 1 pose-mode kernel always, 2 item-mode kernel for every pose list
 int launch_direct_fp64(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
                        int64_t n_poses, double *d_out);
 int launch_components_fp64(const mmo_receptor *rec, const mmo_ligand *lig, const PoseSrc &src,

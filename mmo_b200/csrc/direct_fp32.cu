@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "pose.cuh"
 #include <math.h>
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace mmo {
 
@@ -283,9 +285,10 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 const float cx = 0.5f * (warp_min(fminf(px[0], px[1])) + warp_max(fmaxf(px[0], px[1])));
                 const float cy = 0.5f * (warp_min(fminf(py[0], py[1])) + warp_max(fmaxf(py[0], py[1])));
                 const float cz = 0.5f * (warp_min(fminf(pz[0], pz[1])) + warp_max(fmaxf(pz[0], pz[1])));
-                float l2[PPT];
+                float l2[PPT], m2x[PPT], m2y[PPT], m2z[PPT];
 #pragma unroll
                 for (int h = 0; h < PPT; h++) {
+                    m2x[h] = px[h]; m2y[h] = py[h]; m2z[h] = pz[h];     // l (kept for the difference form)
                     px[h] -= cx; py[h] -= cy; pz[h] -= cz;              // l' = l - c
                     l2[h] = fmaf(pz[h], pz[h], fmaf(py[h], py[h], px[h] * px[h]));
                 }
@@ -293,11 +296,13 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 const bool expand = rho2 <= kRhoExpand2;
                 const float reach = 12.0f + sqrtf(rho2) * 1.0001f + 1e-4f;
                 const float reach2 = reach * reach;
-                float m2x[PPT], m2y[PPT], m2z[PPT];
 #pragma unroll
                 for (int h = 0; h < PPT; h++) {
-                    const float m = expand ? -2.0f : -1.0f;
-                    m2x[h] = m * px[h]; m2y[h] = m * py[h]; m2z[h] = m * pz[h];
+                                        // expanded form: list and ligand atom relative to c; difference form (incoherent warps, c may be far
+                    // from everything): both stay relative to the receptor origin, no second rounding
+                    m2x[h] = expand ? -2.0f * px[h] : -m2x[h];
+                    m2y[h] = expand ? -2.0f * py[h] : -m2y[h];
+                    m2z[h] = expand ? -2.0f * pz[h] : -m2z[h];
                 }
                 // ---- level 1: which groups of 16 receptor atoms can be within 12 A of these positions?
                 //      lane g tests group box g; the near group ids are compacted into s_near ----
@@ -341,14 +346,16 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                         if (na) {
                             const float2 tab = s_tab[ea];
                             float *e = s_l + n + __popc(bma & lt_mask);
-                            e[0 * LIST_CAP] = Xa; e[1 * LIST_CAP] = Ya; e[2 * LIST_CAP] = Za; e[3 * LIST_CAP] = Sa;
+                            e[0 * LIST_CAP] = expand ? Xa : pa.x; e[1 * LIST_CAP] = expand ? Ya : pa.y; e[2 * LIST_CAP] = expand ? Za : pa.z;
+                            e[3 * LIST_CAP] = Sa;
                             e[4 * LIST_CAP] = pa.w * qjs; e[5 * LIST_CAP] = tab.x * Ajs; e[6 * LIST_CAP] = tab.y * nBjs;
                         }
                         n += __popc(bma);
                         if (nb_) {
                             const float2 tab = s_tab[eb];
                             float *e = s_l + n + __popc(bmb & lt_mask);
-                            e[0 * LIST_CAP] = Xb; e[1 * LIST_CAP] = Yb; e[2 * LIST_CAP] = Zb; e[3 * LIST_CAP] = Sb;
+                            e[0 * LIST_CAP] = expand ? Xb : pb.x; e[1 * LIST_CAP] = expand ? Yb : pb.y; e[2 * LIST_CAP] = expand ? Zb : pb.z;
+                            e[3 * LIST_CAP] = Sb;
                             e[4 * LIST_CAP] = pb.w * qjs; e[5 * LIST_CAP] = tab.x * Ajs; e[6 * LIST_CAP] = tab.y * nBjs;
                         }
                         n += __popc(bmb);
@@ -395,6 +402,309 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
     }
 }
 
+// ---- item mode: incoherent pose lists (conformer screens, random poses) ---------------------------------
+// The poses of such a list share nothing a warp could cull with.  The unit of work is therefore the ITEM
+// (pose, ligand atom): item_prepare_kernel computes every item's position (reference arithmetic in double,
+// then fp32) and its cell in a lattice of kItemCell-A cells over the receptor's surroundings; a stable radix
+// sort by cell (cub::DeviceRadixSort, deterministic) makes 64 consecutive items spatial neighbours (rho <=
+// ~2.2 A), and direct_items_kernel runs the same cull -> list -> packed pair loop on 64 items per warp.  Since
+// the ligand atom now differs from lane to lane, the list carries the receptor factors only and the lanes keep
+// three sums each,  E = A_j sum(w A_i s^6) - B_j sum(w B_i s^3) + q_j sum(w q_i / r):  15 packed ops per two pairs.
+constexpr float kItemCell = 2.0f;
+constexpr int kItemTPB = 256;
+constexpr int kItemSumEvery = 4;
+
+struct ItemArgs {
+    float tab_A[kEltTab], tab_B[kEltTab];
+    const float4 *xyzq;
+    const uint8_t *gelt;
+    const float4 *blob_box;
+    const float4 *lparam;        // fast-path order {A_j, B_j, q_j, real?}
+    int n_fast;
+    const float4 *pos;           // item -> position relative to the receptor origin (item = pose * n_fast + k)
+    const uint32_t *perm;        // sorted rank -> item
+    const unsigned long long *n_far;   // items beyond the lattice (energy exactly 0): sorted last
+    unsigned long long n_items;
+    float H, Hflag;
+    double *e_item;              // += E (one tile per launch, launches are serialised)
+    uint8_t *f_item;             // |= close-contact flag
+    unsigned long long *stats;
+};
+
+template <int VARIANT, bool EXPAND, bool STATS>
+__device__ __forceinline__ void run_list_items(const float *s_l, int n, int n4, const float (&m2x)[PPT], const float (&m2y)[PPT],
+                                               const float (&m2z)[PPT], const float (&l2)[PPT], float H,
+                                               double (&EA)[PPT], double (&EB)[PPT], double (&EQ)[PPT],
+                                               float (&rmin)[PPT], unsigned long long (&n_in)[PPT]) {
+    float2 fA[PPT], fB[PPT], fQ[PPT];
+#pragma unroll
+    for (int h = 0; h < PPT; h++) fA[h] = fB[h] = fQ[h] = make_float2(0.f, 0.f);
+    int since = 0;
+#pragma unroll 1
+    for (int k = 0; k < n4; k += 4) {
+        const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
+        const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
+        const float4 Q = *(const float4 *)(s_l + 4 * LIST_CAP + k), A = *(const float4 *)(s_l + 5 * LIST_CAP + k);
+        const float4 B = *(const float4 *)(s_l + 6 * LIST_CAP + k);
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+#pragma unroll
+            for (int pk = 0; pk < 2; pk++) {
+                const float2 x2 = pk ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
+                const float2 y2 = pk ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+                const float2 z2 = pk ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
+                const float2 s2 = pk ? make_float2(S.z, S.w) : make_float2(S.x, S.y);
+                const float2 q2 = pk ? make_float2(Q.z, Q.w) : make_float2(Q.x, Q.y);
+                const float2 a2 = pk ? make_float2(A.z, A.w) : make_float2(A.x, A.y);
+                const float2 b2 = pk ? make_float2(B.z, B.w) : make_float2(B.x, B.y);
+                float2 r2;
+                if (EXPAND) {
+                    r2 = __ffma2_rn(x2, bc2(m2x[h]), __ffma2_rn(y2, bc2(m2y[h]), __ffma2_rn(z2, bc2(m2z[h]), __fadd2_rn(s2, bc2(l2[h])))));
+                } else {
+                    const float2 dx = __fadd2_rn(x2, bc2(m2x[h])), dy = __fadd2_rn(y2, bc2(m2y[h])), dz = __fadd2_rn(z2, bc2(m2z[h]));
+                    r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                }
+                rmin[h] = fminf(rmin[h], fminf(r2.x, r2.y));
+                float2 r2c;
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    r2c.x = fminf(fmaxf(r2.x, H), 144.0f);
+                    r2c.y = fminf(fmaxf(r2.y, H), 144.0f);
+                } else {
+                    r2c.x = fmaxf(r2.x, H);
+                    r2c.y = fmaxf(r2.y, H);
+                }
+                const float2 rinv = make_float2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
+                const float2 s = __fmul2_rn(rinv, rinv);
+                const float2 s3 = __fmul2_rn(__fmul2_rn(s, s), s);
+                float2 ws3 = s3, wr = rinv;
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    const float2 up = __ffma2_rn(r2c, bc2(-1.0f), bc2(144.0f));
+                    const float2 w = __fmul2_rn(up, up);
+                    ws3 = __fmul2_rn(w, s3);
+                    wr = __fmul2_rn(w, rinv);
+                }
+                fB[h] = __ffma2_rn(ws3, b2, fB[h]);
+                fA[h] = __ffma2_rn(__fmul2_rn(ws3, s3), a2, fA[h]);
+                fQ[h] = __ffma2_rn(wr, q2, fQ[h]);
+                if (STATS) n_in[h] += (r2.x < 144.0f && k + 2 * pk < n) + (r2.y < 144.0f && k + 2 * pk + 1 < n);
+            }
+        }
+        if (++since == kItemSumEvery || k + 4 >= n4) {
+#pragma unroll
+            for (int h = 0; h < PPT; h++) {
+                EA[h] += (double)(fA[h].x + fA[h].y);
+                EB[h] += (double)(fB[h].x + fB[h].y);
+                EQ[h] += (double)(fQ[h].x + fQ[h].y);
+                fA[h] = fB[h] = fQ[h] = make_float2(0.f, 0.f);
+            }
+            since = 0;
+        }
+    }
+}
+
+// position (double, then fp32 relative to the receptor origin) and lattice cell of every item; thread = pose
+__global__ void __launch_bounds__(128)
+item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const double *__restrict__ lx, const double *__restrict__ ly,
+                    const double *__restrict__ lz, const int32_t *__restrict__ forder, const float4 *__restrict__ lparam,
+                    double ox, double oy, double oz, float cell_lo_x, float cell_lo_y, float cell_lo_z, float cell_inv,
+                    int nx, int ny, int nz, float4 *__restrict__ pos, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                    unsigned long long *__restrict__ n_far) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_poses) return;
+    PoseRT P;
+    if (src.kind != 1) load_pose_rt(src, p, P);
+    const uint32_t far_key = (uint32_t)nx * ny * nz;
+    unsigned far = 0;
+    for (int k = 0; k < n_fast; k++) {
+        const int64_t it = p * n_fast + k;
+        uint32_t key = far_key;
+        float4 v = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
+        if (__ldg(&lparam[k].w) != 0.f) {
+            double x, y, z;
+            if (src.kind == 1) {
+                const int j = __ldg(forder + k);
+                x = src.xs[p * L + j]; y = src.ys[p * L + j]; z = src.zs[p * L + j];
+            } else {
+                pose_atom_rt(P, __ldg(lx + k), __ldg(ly + k), __ldg(lz + k), x, y, z);
+            }
+            v.x = (float)(x - ox); v.y = (float)(y - oy); v.z = (float)(z - oz);
+            const float fx = (v.x - cell_lo_x) * cell_inv, fy = (v.y - cell_lo_y) * cell_inv, fz = (v.z - cell_lo_z) * cell_inv;
+            if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)nx && fy < (float)ny && fz < (float)nz)
+                key = (uint32_t)((int)fx + nx * ((int)fy + ny * (int)fz));
+        }
+        if (key == far_key) far++;
+        pos[it] = v;
+        keys[it] = key;
+        vals[it] = (uint32_t)it;
+    }
+    if (far) atomicAdd(n_far, (unsigned long long)far);
+}
+
+// Shared memory (dynamic): receptor tile [tile_atoms + kBlob] float4, boxes, ligand parameters, vdW table,
+// per-warp lists [NF][LIST_CAP], element bytes, per-warp near-group ids.
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(kItemTPB, 2)
+direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long long *__restrict__ work) {
+    extern __shared__ float4 smem4[];
+    const int tile_atoms = tile_groups * kBlob;
+    float4 *s_atom = smem4;
+    float4 *s_box = s_atom + tile_atoms + kBlob;
+    float4 *s_lparam = s_box + tile_groups * 2;
+    float2 *s_tab = (float2 *)(s_lparam + a.n_fast);
+    float *s_l = (float *)(s_tab + 16) + (threadIdx.x >> 5) * (NF * LIST_CAP);
+    uint8_t *s_elt = (uint8_t *)((float *)(s_tab + 16) + (kItemTPB / 32) * (NF * LIST_CAP));
+    uint8_t *s_near = s_elt + tile_atoms + kBlob + (threadIdx.x >> 5) * NEAR_CAP;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int j = tid; j < a.n_fast; j += kItemTPB) s_lparam[j] = a.lparam[j];
+    if (tid < kEltTab) s_tab[tid] = make_float2(a.tab_A[tid], a.tab_B[tid]);
+    for (int k = tid; k < nb * kBlob; k += kItemTPB) {
+        s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+        s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
+    }
+    for (int k = tid; k < nb * 2; k += kItemTPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
+    if (tid < kBlob) {
+        s_atom[tile_atoms + tid] = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
+        s_elt[tile_atoms + tid] = 0;
+    }
+    __syncthreads();
+    const float wscale = VARIANT == MMO_VARIANT_SHIFTED ? 1.0f / 20736.0f : 1.0f;
+    const unsigned long long n_near = a.n_items - *a.n_far;
+    const unsigned long long n_units = (n_near + 32 * PPT - 1) / (32 * PPT);
+    unsigned long long n_eval = 0, n_in_tot = 0;
+
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(work, 1ull);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        bool valid[PPT];
+        uint32_t item[PPT];
+        float px[PPT], py[PPT], pz[PPT];
+        float4 lp[PPT];
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            const unsigned long long idx = u * (32 * PPT) + 32 * h + lane;
+            valid[h] = idx < n_near;
+            item[h] = __ldg(a.perm + (valid[h] ? idx : n_near - 1));    // idle slots shadow the last item
+            const float4 v = __ldg(a.pos + item[h]);
+            px[h] = v.x; py[h] = v.y; pz[h] = v.z;
+            lp[h] = s_lparam[item[h] % (uint32_t)a.n_fast];
+        }
+        // ---- centre and radius of the warp's 64 items ----
+        const float cx = 0.5f * (warp_min(fminf(px[0], px[1])) + warp_max(fmaxf(px[0], px[1])));
+        const float cy = 0.5f * (warp_min(fminf(py[0], py[1])) + warp_max(fmaxf(py[0], py[1])));
+        const float cz = 0.5f * (warp_min(fminf(pz[0], pz[1])) + warp_max(fmaxf(pz[0], pz[1])));
+        float l2[PPT], rmin[PPT], m2x[PPT], m2y[PPT], m2z[PPT];
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            m2x[h] = px[h]; m2y[h] = py[h]; m2z[h] = pz[h];
+            px[h] -= cx; py[h] -= cy; pz[h] -= cz;
+            l2[h] = fmaf(pz[h], pz[h], fmaf(py[h], py[h], px[h] * px[h]));
+            rmin[h] = 3e38f;
+        }
+        const float rho2 = warp_max(fmaxf(l2[0], l2[1]));
+        const bool expand = rho2 <= kRhoExpand2;
+        const float reach = 12.0f + sqrtf(rho2) * 1.0001f + 1e-4f;
+        const float reach2 = reach * reach;
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+                        // expanded form: list and ligand atom relative to c; difference form (incoherent warps, c may be far
+                    // from everything): both stay relative to the receptor origin, no second rounding
+                    m2x[h] = expand ? -2.0f * px[h] : -m2x[h];
+                    m2y[h] = expand ? -2.0f * py[h] : -m2y[h];
+                    m2z[h] = expand ? -2.0f * pz[h] : -m2z[h];
+        }
+        double EA[PPT], EB[PPT], EQ[PPT];
+        unsigned long long n_in[PPT];
+#pragma unroll
+        for (int h = 0; h < PPT; h++) { EA[h] = EB[h] = EQ[h] = 0.0; n_in[h] = 0; }
+        // ---- level 1 (group boxes against the sphere (c, 12 + rho)) ----
+        int ng = 0;
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
+            const int g = r * 32 + lane;
+            bool near = g < nb;
+            if (VARIANT == MMO_VARIANT_SHIFTED && near) {
+                const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
+                const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
+                const float gy = fmaxf(0.f, fmaxf(blo.y - cy, cy - bhi.y));
+                const float gz = fmaxf(0.f, fmaxf(blo.z - cz, cz - bhi.z));
+                near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+            }
+            const unsigned gm = __ballot_sync(0xffffffffu, near);
+            if (near) s_near[ng + __popc(gm & lt_mask)] = (uint8_t)g;
+            ng += __popc(gm);
+        }
+        if (lane < 4) s_near[ng + lane] = (uint8_t)tile_groups;
+        __syncwarp();
+        // ---- level 2 + list consumption (as in direct_fp32_kernel; the list carries receptor factors only) ----
+        int n = 0;
+        for (int i = 0; i < ng || n > 0; i += 4) {
+            if (i < ng) {
+                const int atomA = s_near[i + (lane >> 4)] * kBlob + (lane & 15);
+                const int atomB = s_near[i + 2 + (lane >> 4)] * kBlob + (lane & 15);
+                const float4 pa = s_atom[atomA], pb = s_atom[atomB];
+                const int ea = s_elt[atomA], eb = s_elt[atomB];
+                const float Xa = pa.x - cx, Ya = pa.y - cy, Za = pa.z - cz;
+                const float Xb = pb.x - cx, Yb = pb.y - cy, Zb = pb.z - cz;
+                const float Sa = fmaf(Za, Za, fmaf(Ya, Ya, Xa * Xa)), Sb = fmaf(Zb, Zb, fmaf(Yb, Yb, Xb * Xb));
+                const bool na = VARIANT == MMO_VARIANT_SHIFTED ? Sa < reach2 : pa.x < 0.5f * kFarAway;
+                const bool nb_ = VARIANT == MMO_VARIANT_SHIFTED ? Sb < reach2 : pb.x < 0.5f * kFarAway;
+                const unsigned bma = __ballot_sync(0xffffffffu, na), bmb = __ballot_sync(0xffffffffu, nb_);
+                if (na) {
+                    const float2 tab = s_tab[ea];
+                    float *e = s_l + n + __popc(bma & lt_mask);
+                    e[0 * LIST_CAP] = expand ? Xa : pa.x; e[1 * LIST_CAP] = expand ? Ya : pa.y; e[2 * LIST_CAP] = expand ? Za : pa.z;
+                            e[3 * LIST_CAP] = Sa;
+                    e[4 * LIST_CAP] = pa.w * wscale; e[5 * LIST_CAP] = tab.x * wscale; e[6 * LIST_CAP] = tab.y * wscale;
+                }
+                n += __popc(bma);
+                if (nb_) {
+                    const float2 tab = s_tab[eb];
+                    float *e = s_l + n + __popc(bmb & lt_mask);
+                    e[0 * LIST_CAP] = expand ? Xb : pb.x; e[1 * LIST_CAP] = expand ? Yb : pb.y; e[2 * LIST_CAP] = expand ? Zb : pb.z;
+                            e[3 * LIST_CAP] = Sb;
+                    e[4 * LIST_CAP] = pb.w * wscale; e[5 * LIST_CAP] = tab.x * wscale; e[6 * LIST_CAP] = tab.y * wscale;
+                }
+                n += __popc(bmb);
+                if (n <= LIST_CAP - 64 && i + 4 < ng) continue;
+            }
+            if (n > 0) {
+                if (STATS) n_eval += (unsigned long long)n * (unsigned)(valid[0] + valid[1]);
+                const int n4 = (n + 3) & ~3;
+                if (lane < n4 - n) {
+                    float *e = s_l + n + lane;
+                    e[0 * LIST_CAP] = kFarAway; e[1 * LIST_CAP] = kFarAway; e[2 * LIST_CAP] = kFarAway;
+                    e[3 * LIST_CAP] = 3.0f * kFarAway * kFarAway;
+                    e[4 * LIST_CAP] = 0.f; e[5 * LIST_CAP] = 0.f; e[6 * LIST_CAP] = 0.f;
+                }
+                __syncwarp();
+                if (expand) run_list_items<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, EA, EB, EQ, rmin, n_in);
+                else run_list_items<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, EA, EB, EQ, rmin, n_in);
+                n = 0;
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            if (valid[h]) {
+                const double E = (double)lp[h].x * EA[h] - (double)lp[h].y * EB[h] + (double)lp[h].z * EQ[h];
+                a.e_item[item[h]] += E;
+                if (rmin[h] < a.Hflag) a.f_item[item[h]] = 1;
+                if (STATS) n_in_tot += n_in[h];
+            }
+        }
+    }
+    if (STATS) {
+        atomicAdd(a.stats + 0, n_eval);
+        atomicAdd(a.stats + 1, n_in_tot);
+    }
+}
+
 // ---- close-contact correction (fp64) ---------------------------------------------------------------
 // For every pair with r^2 < H the fast path evaluated w(sqrt(H)) e(sqrt(H)); this pass adds
 // w(r) e(r) - w(sqrt(H)) e(sqrt(H)) in double.  Same formulas as mol.ml:811-815 / 838-845 (r clamped at 0.01, p6 = (x_ij/r)^6, shift weight),
@@ -418,15 +728,18 @@ struct FixArgs {
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
 
-template <int VARIANT, bool STATS>
+// ITEMS: part = per-item energies [pose][n_split = n_fast], flags = per-item bytes (direct_items_kernel);
+// else  : part = per-split sums [n_split][pose], flags = per-(tile, chunk) bytes (direct_fp32_kernel)
+template <int VARIANT, bool STATS, bool ITEMS>
 __global__ void __launch_bounds__(128)
 hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int n_split,
                 const uint8_t *__restrict__ flags, int n_tiles, int n_chunks, double *out) {   // part may alias out
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_poses) return;
-    // the fast kernel's partial sums (one per chunk split), added in a fixed order
+    // the fast kernel's partial sums, added in a fixed order
     double e = 0.0;
-    for (int k = 0; k < n_split; k++) e += part[(int64_t)k * n_poses + p];
+    if (ITEMS) for (int k = 0; k < n_split; k++) e += part[p * n_split + k];
+    else for (int k = 0; k < n_split; k++) e += part[(int64_t)k * n_poses + p];
     double corr = 0.0;
     unsigned long long n_fix = 0, n_flag = 0;
     bool have_pose = false;
@@ -434,7 +747,12 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
     for (int c = 0; c < n_chunks; c++) {
         // atoms of chunk c (fast-path order) for which the fast kernel saw a pair below H (any tile)
         unsigned bits = 0u;
-        for (int t = 0; t < n_tiles; t++) bits |= flags[((int64_t)t * n_chunks + c) * n_poses + p];
+        if (ITEMS) {
+#pragma unroll
+            for (int jj = 0; jj < kFixLJ; jj++) bits |= (unsigned)(flags[p * n_split + c * kFixLJ + jj] & 1) << jj;
+        } else {
+            for (int t = 0; t < n_tiles; t++) bits |= flags[((int64_t)t * n_chunks + c) * n_poses + p];
+        }
         while (bits != 0u) {
             const int jj = __ffs(bits) - 1;
             bits &= bits - 1u;
@@ -497,6 +815,12 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
 // ---- host side -----------------------------------------------------------------------------------
 static DevBuf<double> g_xx, g_dij, g_vdwH;
 static DevBuf<unsigned long long> g_stats, g_work;
+static DevBuf<uint8_t> g_item_scratch;             // item mode scratch arena
+constexpr int64_t kItemModeMin = 32768;          // items (poses x ligand atoms) from which item mode pays
+constexpr int64_t kItemBatch = (int64_t)64 << 20;  // items per batch: ~47 B of scratch each (3 GB)
+constexpr int64_t kGlobalFp32MaxPairs = 120000;   // receptor x ligand atoms up to which GLOBAL stays on the fp32 path
+static int g_direct_mode = 0;                     // 0 auto, 1 pose kernel always, 2 item kernel for every pose list
+void direct_set_mode(int mode) { g_direct_mode = mode; }
 static double g_vdwH_for = -1.0;
 
 static int ensure_fix_tables(double H) {
@@ -538,10 +862,119 @@ static int set_fast_smem(size_t smem) {
     return MMO_OK;
 }
 
+// ---- item mode launcher ------------------------------------------------------------------------------
+static int set_items_smem(size_t smem) {
+    static size_t done = 0;
+    if (smem <= done) return MMO_OK;
+    MMO_CUDA(cudaFuncSetAttribute(direct_items_kernel<MMO_VARIANT_SHIFTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_items_kernel<MMO_VARIANT_SHIFTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_items_kernel<MMO_VARIANT_GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_items_kernel<MMO_VARIANT_GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = smem;
+    return MMO_OK;
+}
+
+// poses [p_begin, p_begin + n) of src in item mode; d_out points at the first of them
+static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src_all,
+                              int64_t p_begin, int64_t n_poses, double *d_out, bool collect_stats, const FastArgs &fa,
+                              const FixArgs &xa) {
+    Runtime &R = rt();
+    PoseSrc src = src_all;      // view of the batch
+    if (src.kind == 0) { src.rot9 += 9 * p_begin; src.trans3 += 3 * p_begin; }
+    else if (src.kind == 1) { src.xs += p_begin * lig->n; src.ys += p_begin * lig->n; src.zs += p_begin * lig->n; }
+    else src.frames += p_begin;
+    const int nf = lig->n_fast;
+    const size_t n_items = (size_t)n_poses * nf;
+    // lattice of cells over everything within 12 A (+ one cell) of the receptor's bounding box
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = (float)(rec->bb_lo[d] - rec->origin[d]) - 12.5f; hi[d] = (float)(rec->bb_hi[d] - rec->origin[d]) + 12.5f; }
+    float cell = kItemCell;
+    int nd[3];
+    for (;;) {
+        double tot = 1.0;
+        for (int d = 0; d < 3; d++) { nd[d] = std::max(1, (int)ceilf((hi[d] - lo[d]) / cell)); tot *= nd[d]; }
+        if (tot < (double)(1u << 24)) break;
+        cell *= 1.5f;
+    }
+    const unsigned n_cells = (unsigned)nd[0] * nd[1] * nd[2];
+    int end_bit = 1;
+    while ((1ull << end_bit) <= n_cells) end_bit++;          // keys 0 .. n_cells (n_cells = beyond the lattice)
+
+    // scratch arena (grow-only, reused by every call: cudaMalloc/cudaFree of ~45 B per item would cost more than the kernels)
+    size_t temp_bytes = 0;
+    MMO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                             (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n_items, 0, end_bit, R.stream));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t need = up(n_items * 16) + up(n_items * 8) + 4 * up(n_items * 4) + up(n_items) + up(temp_bytes);
+    if (g_item_scratch.n < need) MMO_TRY(g_item_scratch.alloc(need + need / 8));
+    uint8_t *cur = g_item_scratch.p;
+    auto carve = [&](size_t b) { uint8_t *r = cur; cur += up(b); return r; };
+    float4 *pos = (float4 *)carve(n_items * 16);
+    double *e_item = (double *)carve(n_items * 8);
+    uint32_t *keys = (uint32_t *)carve(n_items * 4), *keys2 = (uint32_t *)carve(n_items * 4);
+    uint32_t *vals = (uint32_t *)carve(n_items * 4), *perm = (uint32_t *)carve(n_items * 4);
+    uint8_t *f_item = carve(n_items), *temp = carve(temp_bytes);
+    if (!g_work.p) MMO_TRY(g_work.alloc(64));
+    MMO_CUDA(cudaMemsetAsync(g_work.p, 0, 64 * sizeof(unsigned long long), R.stream));
+    MMO_CUDA(cudaMemsetAsync(e_item, 0, n_items * sizeof(double), R.stream));
+    MMO_CUDA(cudaMemsetAsync(f_item, 0, n_items, R.stream));
+    unsigned long long *d_far = g_work.p + 63;
+    {
+        KernelScope ks(K_ITEM_PREP);
+        item_prepare_kernel<<<(unsigned)((n_poses + 127) / 128), 128, 0, R.stream>>>(
+            src, n_poses, lig->n, nf, lig->fx.p, lig->fy.p, lig->fz.p, lig->forder.p, lig->fparam.p, rec->origin[0], rec->origin[1],
+            rec->origin[2], lo[0], lo[1], lo[2], 1.0f / cell, nd[0], nd[1], nd[2], pos, keys, vals, d_far);
+        MMO_LAUNCH_CHECK();
+        MMO_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys2, vals, perm, (int64_t)n_items, 0, end_bit, R.stream));
+        count_launch(3);
+    }
+    ItemArgs ia;
+    for (int e = 0; e < kEltTab; e++) { ia.tab_A[e] = fa.tab_A[e]; ia.tab_B[e] = fa.tab_B[e]; }
+    ia.xyzq = fa.xyzq; ia.gelt = fa.gelt; ia.blob_box = fa.blob_box; ia.lparam = fa.lparam; ia.n_fast = nf;
+    ia.pos = pos; ia.perm = perm; ia.n_far = d_far; ia.n_items = n_items;
+    ia.H = fa.H; ia.Hflag = fa.Hflag; ia.e_item = e_item; ia.f_item = f_item; ia.stats = fa.stats;
+    const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
+    const int n_tiles = (rec->n_blobs + tile_blobs - 1) / tile_blobs;
+    MMO_REQUIRE(n_tiles <= 60, "receptor too large for the direct kernel (%d tiles of %d atoms)", n_tiles, MAX_TILE_GROUPS * kBlob);
+    const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)nf) * sizeof(float4) + 16 * sizeof(float2) +
+                        (size_t)(kItemTPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob +
+                        (size_t)(kItemTPB / 32) * NEAR_CAP + 16;
+    MMO_TRY(set_items_smem(smem));
+    const int64_t n_units = ((int64_t)n_items + 63) / 64;
+    const unsigned blocks = (unsigned)std::min<int64_t>(2LL * R.sm_count, (n_units + kItemTPB / 32 - 1) / (kItemTPB / 32));
+    const bool shifted = variant == MMO_VARIANT_SHIFTED;
+    {
+        KernelScope ks(K_DIRECT_FP32);
+        for (int t = 0; t < n_tiles; t++) {
+            const int b0 = t * tile_blobs, nb = std::min(tile_blobs, rec->n_blobs - b0);
+            unsigned long long *w = g_work.p + t;
+            if (shifted && collect_stats) direct_items_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
+            else if (shifted) direct_items_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
+            else if (collect_stats) direct_items_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
+            else direct_items_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
+            MMO_LAUNCH_CHECK();
+        }
+    }
+    KernelScope ks2(K_HARD_FIX);
+    const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
+    const int n_chunks = nf / LJ;
+    if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
+    else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
+    else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
+    else hard_fix_kernel<MMO_VARIANT_GLOBAL, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
 int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
                        int64_t n_poses, double *d_out, bool collect_stats) {
     if (n_poses == 0) return MMO_OK;
     Runtime &R = rt();
+    // Without a cut-off every receptor atom contributes a Coulomb term of order 0.1-1 kcal/mol and the fp32
+    // rounding noise of the sum grows as sqrt(pairs): the contract is verified up to ~1e5 pairs per pose
+    // (worst |err| / tolerance 0.3) and lost near 2e5.  Larger GLOBAL problems take the strict fp64 kernel.
+    if (variant == MMO_VARIANT_GLOBAL && (int64_t)rec->n * lig->n > kGlobalFp32MaxPairs)
+        return launch_direct_fp64(rec, lig, variant, src, n_poses, d_out);
     // clamp / close-contact threshold on r^2; a float so that both kernels see the same number
     const float H = (float)(std::max(rec->x_max, 1.0) * std::max(lig->x_max, 1.0) / kTau);
     MMO_TRY(ensure_fix_tables((double)H));
@@ -573,6 +1006,21 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.stats = g_stats.p;
 
     if (collect_stats) MMO_CUDA(cudaMemsetAsync(g_stats.p, 0, 4 * sizeof(unsigned long long), R.stream));
+    // Pose lists that are not a scan (arbitrary rotations / explicit conformers) have no coherence a warp of
+    // poses could cull with: large ones go through item mode, in batches that bound the scratch memory.
+    if (src.kind != 2 && rec->n > 0 && g_direct_mode != 1 && variant == MMO_VARIANT_SHIFTED &&
+        ((int64_t)n_poses * lig->n_fast >= kItemModeMin || g_direct_mode == 2)) {
+        const int64_t batch = std::max<int64_t>(1, kItemBatch / lig->n_fast);
+        for (int64_t p0 = 0; p0 < n_poses; p0 += batch)
+            MMO_TRY(launch_items_batch(rec, lig, variant, src, p0, std::min(batch, n_poses - p0), d_out + p0, collect_stats, fa, xa));
+        if (collect_stats) {
+            unsigned long long h[4];
+            MMO_CUDA(cudaMemcpyAsync(h, g_stats.p, sizeof h, cudaMemcpyDeviceToHost, R.stream));
+            MMO_CUDA(cudaStreamSynchronize(R.stream));
+            R.stat_pairs = (int64_t)h[0]; R.stat_inside = (int64_t)h[1]; R.stat_fp64 = (int64_t)h[2]; R.stat_flagged = (int64_t)h[3];
+        }
+        return MMO_OK;
+    }
     // receptor tile: everything when it fits (<= 128 groups = 2048 atoms), so that 2 blocks stay resident per SM
     const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
     const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
@@ -616,10 +1064,10 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
         }
         KernelScope ks2(K_HARD_FIX);
         const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
-        if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
-        else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
-        else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
-        else hard_fix_kernel<MMO_VARIANT_GLOBAL, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        else hard_fix_kernel<MMO_VARIANT_GLOBAL, false, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
         MMO_LAUNCH_CHECK();
     } else {
         MMO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_poses * sizeof(double), R.stream));

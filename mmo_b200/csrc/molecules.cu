@@ -95,7 +95,7 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
         }
         if (elt[i] < kNumElt && kEltXi[elt[i]] > r->x_max) r->x_max = kEltXi[elt[i]];
     }
-    for (int d = 0; d < 3; d++) r->origin[d] = 0.5 * (lo[d] + hi[d]);
+    for (int d = 0; d < 3; d++) { r->origin[d] = 0.5 * (lo[d] + hi[d]); r->bb_lo[d] = lo[d]; r->bb_hi[d] = hi[d]; }
 
     // ---- k-d leaves -> groups of kBlob spatially close atoms (first level of distance culling); the
     //      element of every slot is kept beside it, its vdW factors come from a 13-entry table

@@ -141,3 +141,43 @@ def random_poses_in_sphere(n: int, center, radius: float, seed: int = SEED):
         t = np.concatenate([t, c])
     t = t[:n] * radius + np.asarray(center)
     return R, t
+
+
+def c5_ligand(seed: int = SEED) -> pqrs.Mol:
+    """C5 template: 40 heavy atoms as a self-avoiding 1.5 A random walk + 30 hydrogens 1.09 A off
+    random heavy atoms; elements and charges recycled from docked.mol2 (tests/golden/docked.pqrs)."""
+    rng = np.random.default_rng(seed + 5)
+    src = pqrs.read_ligands_pqrs(os.path.join(GOLDEN, "docked.pqrs"))[0]
+    heavy_src = [i for i in range(src.n) if src.anum[i] != 1]
+    h_src = [i for i in range(src.n) if src.anum[i] == 1]
+    pts = [np.zeros(3)]
+    while len(pts) < 40:
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        c = pts[rng.integers(max(0, len(pts) - 3), len(pts))] + 1.5 * d
+        if min(np.linalg.norm(c - p) for p in pts) > 1.3:
+            pts.append(c)
+    anum = [int(src.anum[heavy_src[i % len(heavy_src)]]) for i in range(40)]
+    q = [float(src.q[heavy_src[i % len(heavy_src)]]) for i in range(40)]
+    while len(pts) < 70:
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        c = pts[rng.integers(0, 40)] + 1.09 * d
+        if min(np.linalg.norm(c - p) for p in pts) > 0.95:
+            k = len(pts) - 40
+            pts.append(c); anum.append(1); q.append(float(src.q[h_src[k % len(h_src)]]))
+    pts = np.array(pts); pts -= pts.mean(0)
+    q = np.array(q); q -= q.mean()
+    anum = np.array(anum, np.int32)
+    rad = np.array([pqrs.VDW_RADII[int(a)] for a in anum])
+    return pqrs.Mol("c5lig", pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), q, rad, anum)
+
+
+def c5_conformers(lig: pqrs.Mol, n: int, center, radius: float = 10.0, seed: int = SEED, jitter: float = 0.35):
+    """n conformers as explicit coordinates (pose-major): random rotation, centre uniform in a sphere, and a
+    per-atom Gaussian displacement standing in for the random dihedrals of the C5 recipe."""
+    rng = np.random.default_rng(seed + 55)
+    R, t = random_poses_in_sphere(n, center, radius, seed=seed + 56)
+    P = np.stack([lig.xs, lig.ys, lig.zs])                        # 3 x L
+    Rm = R.reshape(n, 3, 3)
+    X = np.einsum("nij,jl->nil", Rm, P) + t[:, :, None]           # n x 3 x L
+    X += rng.normal(0.0, jitter, X.shape)
+    return np.ascontiguousarray(X[:, 0, :]), np.ascontiguousarray(X[:, 1, :]), np.ascontiguousarray(X[:, 2, :])

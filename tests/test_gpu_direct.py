@@ -39,7 +39,15 @@ def test_fp64_bit_identical_shifted_and_global(gpu, orc, c2, c2_roi_rec, handles
         assert np.array_equal(got_p, want)      # on-device pose transform == Rot.rotate + translate_by
 
 
-def test_fp32_within_tolerance_including_clashes(gpu, orc, c2, c2_roi_rec, handles):
+@pytest.fixture(params=[1, 2], ids=["pose_kernel", "item_kernel"])
+def direct_mode(gpu, request):
+    """both FP32 kernels must honour the contract on every kind of pose list"""
+    assert gpu.lib().mmo_direct_set_mode(request.param) == 0
+    yield request.param
+    gpu.lib().mmo_direct_set_mode(0)
+
+
+def test_fp32_within_tolerance_including_clashes(gpu, orc, c2, c2_roi_rec, handles, direct_mode):
     rec, lig = handles
     m = c2["lig"]
     R, t = _poses(c2, 600, seed=12)
@@ -76,7 +84,7 @@ def _coherent_poses(c2, n, seed, dtheta):
 
 
 @pytest.mark.parametrize("dtheta", [0.02, 0.15, 0.6])
-def test_fp32_coherent_warps_within_tolerance(gpu, orc, c2, c2_roi_rec, handles, dtheta):
+def test_fp32_coherent_warps_within_tolerance(gpu, orc, c2, c2_roi_rec, handles, dtheta, direct_mode):
     """warps of similar poses take the cloud-centred expanded form of r^2 (small dtheta) or the
     difference form (large dtheta): both must honour the accuracy contract"""
     rec, lig = handles
@@ -91,14 +99,14 @@ def test_fp32_coherent_warps_within_tolerance(gpu, orc, c2, c2_roi_rec, handles,
         assert (ratio <= 1.0).all(), f"worst ratio {ratio.max()} at E={want[ratio.argmax()]}"
 
 
-def test_fp32_far_away_pose_is_exactly_zero(gpu, c2, handles):
+def test_fp32_far_away_pose_is_exactly_zero(gpu, c2, handles, direct_mode):
     rec, lig = handles
     t = np.array([[c2["roi"][0] + 80.0, c2["roi"][1], c2["roi"][2]]])
     e = gpu.Mol.score_poses(rec, lig, np.eye(3).reshape(1, 9), t)
     assert e[0] == 0.0          # lds.ml:920: E_inter = 0.0 exactly is a reset signal
 
 
-def test_empty_batch_and_ragged_sizes(gpu, orc):
+def test_empty_batch_and_ragged_sizes(gpu, orc, direct_mode):
     rng = np.random.default_rng(5)
     # receptor size not a multiple of the blob, ligand size not a multiple of the register chunk
     for P, L in ((1, 1), (17, 3), (33, 9), (250, 13)):
@@ -124,7 +132,7 @@ def test_empty_receptor_gives_zero(gpu):
         assert e[0] == 0.0
 
 
-def test_coincident_atoms_use_the_001_clamp(gpu, orc):
+def test_coincident_atoms_use_the_001_clamp(gpu, orc, direct_mode):
     # Math.non_zero_dist (math.ml:58-62): r < 0.01 -> 0.01, energies of order 1e30
     rec_m = pqrs.Mol("one", np.array([5.0]), np.array([5.0]), np.array([5.0]), np.array([0.5]), np.array([1.7]),
                      np.array([6], np.int32))
@@ -202,3 +210,21 @@ def test_pose_tools_bit_identical(gpu, orc, c2):
     d0 = np.hypot(np.hypot(m.xs[0] - m.xs[5], m.ys[0] - m.ys[5]), m.zs[0] - m.zs[5])
     d1 = np.hypot(np.hypot(X[:, 0] - X[:, 5], Y[:, 0] - Y[:, 5]), Z[:, 0] - Z[:, 5])
     assert np.allclose(d1, d0, rtol=1e-13)
+
+
+def test_fp32_conformer_screen_multi_tile(gpu, orc, direct_mode):
+    """C5 shape: explicit conformers of a 70-atom ligand (n_fast = 72: padded chunk) against a receptor of
+    more than one shared-memory tile (3000 atoms > 2048); poses scattered over the whole receptor."""
+    rec_m = workloads.synthetic_receptor(3000, "sphere", 24.0, seed=3, origin=(40.0, 40.0, 40.0))
+    lig_m = workloads.c5_ligand()
+    rec = gpu.Receptor.from_mol(rec_m)
+    lig = gpu.Ligand.from_mol(lig_m, centered=False)
+    X, Y, Z = workloads.c5_conformers(lig_m, 520, (40.0, 40.0, 40.0), radius=36.0, seed=9)
+    for shifted, variant in ((True, gpu.VARIANT_SHIFTED), (False, gpu.VARIANT_GLOBAL)):
+        want = orc.ene_inter(rec_m, lig_m.q, lig_m.anum, X, Y, Z, shifted=shifted)
+        got = gpu.Mol._score(rec, lig, variant, gpu.PREC_FP32, X, Y, Z)
+        ratio = np.abs(got - want) / np.maximum(1e-6 * np.abs(want), 1e-4)
+        print(f"conformers shifted={shifted}: worst |err|/tol = {ratio.max():.3f}")
+        assert (ratio <= 1.0).all(), f"worst ratio {ratio.max()} at E={want[ratio.argmax()]}"
+        assert np.array_equal(gpu.Mol._score(rec, lig, variant, gpu.PREC_FP64, X[:40], Y[:40], Z[:40]), want[:40])
+    assert (np.abs(want) < 50.0).sum() > 20 and (want > 1e3).sum() > 20      # surface poses and clashes alike

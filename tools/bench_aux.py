@@ -89,6 +89,51 @@ def main():
                               "ms_per_launch": ms / n, "fix_ms_per_launch": fms / n,
                               "poses_per_s": n_dir / ((ms + fms) / n * 1e-3),
                               "nominal_pairs_per_s": n_dir * rec_m.n * lig.n / ((ms + fms) / n * 1e-3)}
+    # ---- C5: conformer screen, 70-atom ligand x 10 000-atom receptor sphere, explicit coordinates, top-100 ----
+    rec5_m = workloads.synthetic_receptor(10000, "sphere", 34.0, seed=workloads.SEED + 1, origin=(60.0, 60.0, 60.0))
+    lig5_m = workloads.c5_ligand()
+    rec5 = mmo_b200.Receptor.from_mol(rec5_m)
+    lig5 = mmo_b200.Ligand.from_mol(lig5_m, centered=False)
+    n5 = 50_000 if args.quick else 250_000
+    X5, Y5, Z5 = workloads.c5_conformers(lig5_m, n5, (60.0, 60.0, 60.0))
+    dxyz = [C.c_void_p() for _ in range(3)]
+    d_e5 = C.c_void_p()
+    for dp, arr in zip(dxyz, (X5, Y5, Z5)):
+        L.mmo_dev_alloc(C.c_size_t(arr.nbytes), C.byref(dp)); L.mmo_h2d(dp, arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes))
+    L.mmo_dev_alloc(C.c_size_t(n5 * 8), C.byref(d_e5))
+    L.mmo_set_collect_stats(1)
+    assert L.mmo_score_coords_dev(rec5.h, lig5.h, 1, 0, C.c_int64(n5), dxyz[0], dxyz[1], dxyz[2], d_e5) == 0
+    pe, pi_, pf = C.c_int64(), C.c_int64(), C.c_int64()
+    L.mmo_last_pair_stats(C.byref(pe), C.byref(pi_), C.byref(pf))
+    L.mmo_set_collect_stats(0)
+    c5 = {}
+    for mode, name in ((2, "item_kernel"), (1, "pose_kernel")):
+        L.mmo_direct_set_mode(mode)
+        nn = n5 if mode == 2 else n5 // 10          # the pose kernel evaluates ~20x the pairs: time a tenth
+        L.mmo_kernel_timing(1)
+        tot = 0.0
+        ms1 = C.c_float()
+        for it in range(3):
+            L.mmo_l2_flush(); L.mmo_sync(); L.mmo_timer_start()
+            assert L.mmo_score_coords_dev(rec5.h, lig5.h, 1, 0, C.c_int64(nn), dxyz[0], dxyz[1], dxyz[2], d_e5) == 0
+            L.mmo_timer_stop(C.byref(ms1))
+            if it > 0:
+                tot += ms1.value
+        ms, n = ktime(L, K["direct_fp32"]); fms, _ = ktime(L, K["hard_fix"]); pms, _ = ktime(L, 10)
+        c5[name] = {"conformers": nn, "ms_per_call": tot / 2, "poses_per_s": nn / (tot / 2 * 1e-3),
+                    "pair_kernel_ms": ms / 3, "fix_ms": fms / 3, "prepare_and_sort_ms": pms / 3}
+    L.mmo_direct_set_mode(0)
+    e5 = np.empty(n5)
+    t0 = time.perf_counter()
+    L.mmo_d2h(e5.ctypes.data_as(C.c_void_p), d_e5, C.c_size_t(n5 * 8))
+    top = np.argpartition(e5, 100)[:100]
+    c5["topk_100_host_ms"] = 1e3 * (time.perf_counter() - t0)
+    c5.update({"receptor_atoms": rec5_m.n, "ligand_atoms": lig5_m.n, "pairs_evaluated_per_pose": pe.value / n5,
+               "pairs_inside_cutoff_per_pose": pi_.value / n5, "fp64_fix_pairs_per_pose": pf.value / n5,
+               "nominal_pairs_per_s": c5["item_kernel"]["poses_per_s"] * rec5_m.n * lig5_m.n,
+               "algorithmic_tflops": c5["item_kernel"]["poses_per_s"] * (27.0 * pi_.value + 8.0 * (pe.value - pi_.value)) / n5 / 1e12,
+               "best_E": float(e5[top].min())})
+    out["c5_conformer_screen"] = c5
     L.mmo_kernel_timing(1)
     n64 = 5_000 if args.quick else 20_000
     assert L.mmo_score_poses_dev(rec.h, lig.h, 1, 1, C.c_int64(n64), d_rot, d_t, d_e) == 0
