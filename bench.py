@@ -165,6 +165,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    # stdout carries the one JSON line and nothing else: NCCL's version/debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import mmo_b200
     from mmo_b200 import ScanParams, ScanResult
@@ -188,6 +190,10 @@ def main():
         tid = torch.from_numpy(nid)
         dist.broadcast(tid, 0)
         ck(L.mmo_nccl_init(rank, world, tid.numpy().ctypes.data_as(C.POINTER(C.c_uint8))))
+        # first collective = connection set-up (hundreds of ms): done here, so that the merge timed at the end is the merge
+        w_s, w_f, w_n = np.empty(1), np.empty(1, np.int64), C.c_int32()
+        ck(L.mmo_topk_allgather_merge(1, 0, None, None, w_s.ctypes.data_as(C.POINTER(C.c_double)),
+                                      w_f.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(w_n)))
 
     c2, rec_m = setup_workload()
     rec = mmo_b200.Receptor.from_mol(rec_m)
