@@ -298,6 +298,30 @@ int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const mmo_ligand *
                const double *start_pos3, mmo_mc_result *results, double *best_xyz,
                double *trace_chain0);
 
+/* ---------------------------------------------------------------- N2: ligand / receptor files on the host ----
+ * mol2pqrs (src/mol2pqrs.ml:10-58, src/mol_graph.ml:45-200, src/mol2.ml:139-320) and the .pqrs reader
+ * (src/pqrs.ml:19-87, src/mol.ml:368-440) inside the library: no subprocess, no GPU needed except for
+ * mmo_molfile_ligand.  A molfile holds every molecule of the file in file order; molecules the reference skips
+ * (disconnected atom, malformed block) are counted in n_skipped. */
+typedef struct mmo_molfile mmo_molfile;
+int mmo_molfile_read_mol2(const char *path, mmo_molfile **out);
+int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out);
+int mmo_molfile_count(const mmo_molfile *f, int32_t *n_mols, int32_t *n_skipped);
+int mmo_molfile_shape(const mmo_molfile *f, int32_t k, int32_t *n_atoms, int32_t *n_rbonds, int32_t *rg_total,
+                      char *name, int32_t name_cap);
+/* any output pointer may be NULL; dists is n*n with element (i, j) at i + j*n (src/mol.ml:151-152);
+ * rg_off has n_rbonds + 1 entries, rg_idx the movable atoms of every bond without the axis tip (src/pqrs.ml:80-87) */
+int mmo_molfile_get(const mmo_molfile *f, int32_t k, double *xs, double *ys, double *zs, double *q, double *r,
+                    int32_t *anum, int32_t *typ, int32_t *dists, int32_t *rb_left, int32_t *rb_right,
+                    int32_t *rg_off, int32_t *rg_idx);
+/* FF atom types of the file: (anum, exact charge) -> id in first-seen order (src/mol.ml:280-293, 456-469) */
+int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum, double *type_q);
+/* the text mol2pqrs writes (values through %g) */
+int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path);
+/* molecule k as a device-resident ligand handle; centered != 0 applies Mol.translate_to lig V3.origin (lds.ml:44-52) */
+int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand **out);
+int mmo_molfile_destroy(mmo_molfile *f);
+
 #ifdef __cplusplus
 }
 #endif

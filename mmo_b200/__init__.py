@@ -500,3 +500,67 @@ class Rot:
         out = np.empty(3)
         _ck(lib().mmo_rot_decompose(r.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
         return out
+
+
+class MolFile:
+    """N2: a mol2 / pqrs file parsed by the library's own C++ reader (mmo_molfile_*): mol2pqrs without the
+    subprocess (src/mol2pqrs.ml, src/mol_graph.ml, src/pqrs.ml).  Host only; `ligand(k)` needs the GPU."""
+
+    def __init__(self, path, kind="mol2"):
+        self.h = C.c_void_p()
+        p = os.fsencode(path)
+        if kind == "mol2":
+            _ck(lib().mmo_molfile_read_mol2(p, C.byref(self.h)))
+        else:
+            _ck(lib().mmo_molfile_read_pqrs(p, C.c_int(1 if kind == "receptor_pqrs" else 0), C.byref(self.h)))
+        n, sk = C.c_int32(), C.c_int32()
+        _ck(lib().mmo_molfile_count(self.h, C.byref(n), C.byref(sk)))
+        self.n_mols, self.n_skipped = n.value, sk.value
+
+    def mol(self, k):
+        """molecule k as a pqrs.Mol (same layout as the Python reader's)"""
+        from . import pqrs
+        na, nrb, tot = C.c_int32(), C.c_int32(), C.c_int32()
+        name = C.create_string_buffer(512)
+        _ck(lib().mmo_molfile_shape(self.h, C.c_int32(k), C.byref(na), C.byref(nrb), C.byref(tot), name, C.c_int32(512)))
+        n = na.value
+        xs, ys, zs, q, r = (np.empty(n) for _ in range(5))
+        anum, typ = np.empty(n, np.int32), np.empty(n, np.int32)
+        dists = np.zeros(n * n, np.int32)
+        left, right = np.empty(nrb.value, np.int32), np.empty(nrb.value, np.int32)
+        off, idx = np.zeros(nrb.value + 1, np.int32), np.empty(max(1, tot.value), np.int32)
+        _ck(lib().mmo_molfile_get(self.h, C.c_int32(k), xs.ctypes.data_as(_dp), ys.ctypes.data_as(_dp), zs.ctypes.data_as(_dp),
+                                  q.ctypes.data_as(_dp), r.ctypes.data_as(_dp), anum.ctypes.data_as(_ip), typ.ctypes.data_as(_ip),
+                                  dists.ctypes.data_as(_ip), left.ctypes.data_as(_ip), right.ctypes.data_as(_ip),
+                                  off.ctypes.data_as(_ip), idx.ctypes.data_as(_ip)))
+        groups = [idx[off[b]:off[b + 1]].copy() for b in range(nrb.value)]
+        return pqrs.Mol(name.value.decode(), xs, ys, zs, q, r, anum, dists, left, right, groups, typ)
+
+    def types(self):
+        n = C.c_int32()
+        _ck(lib().mmo_molfile_types(self.h, C.byref(n), None, None))
+        ta, tq = np.empty(n.value, np.int32), np.empty(n.value)
+        _ck(lib().mmo_molfile_types(self.h, C.byref(n), ta.ctypes.data_as(_ip), tq.ctypes.data_as(_dp)))
+        return ta, tq
+
+    def write_pqrs(self, path):
+        _ck(lib().mmo_molfile_write_pqrs(self.h, os.fsencode(path)))
+
+    def ligand(self, k, centered=True):
+        _need_init()
+        m = self.mol(k)
+        o = Ligand.__new__(Ligand)
+        o.h = C.c_void_p()
+        _ck(lib().mmo_molfile_ligand(self.h, C.c_int32(k), C.c_int(1 if centered else 0), C.byref(o.h)))
+        o.n = m.n
+        if centered:
+            c = [favg(m.xs), favg(m.ys), favg(m.zs)]
+            o.xs, o.ys, o.zs = m.xs + (0.0 - c[0]), m.ys + (0.0 - c[1]), m.zs + (0.0 - c[2])
+        else:
+            o.xs, o.ys, o.zs = m.xs, m.ys, m.zs
+        return o
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mmo_molfile_destroy(self.h)
+            self.h = None

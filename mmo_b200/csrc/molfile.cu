@@ -1,0 +1,433 @@
+// molfile.cu -- N2: ligand / receptor preparation on the host, in C++ inside the library (no subprocess, no Python).
+// Restates the reference's input layer:
+//   mol2 reader            src/mol2.ml:139-149 (bond order), 184-228 (atom / bond lines), 243-320 (one molecule),
+//                          lone pairs dropped (mol2.ml:54-56), element from the mol2 type (src/ptable.ml:168-207)
+//   molecular graph        src/mol_graph.ml:45-63 (all-pairs topological distances), 93-102 (degrees),
+//                          108-138 (rotatable bond = single, not in a ring, no terminal atom),
+//                          141-200 (rotatable group = the smaller side once the bond is cut)
+//   .pqrs text             src/mol2pqrs.ml:10-58 (writer, values through %g, mol2.ml:67-69),
+//                          src/pqrs.ml:19-87 + src/mol.ml:368-440 (reader: rotatable bond lines, distance matrix)
+//   FF atom types          src/mol.ml:280-293, 456-469 ((anum, exact charge) -> id in first-seen order over the file)
+// Pure host code: everything but mmo_molfile_ligand works without a GPU.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <queue>
+#include <sstream>
+
+namespace {
+
+struct Molecule {
+    std::string name;
+    std::vector<double> x, y, z, q, r;
+    std::vector<int32_t> anum;
+    bool is_ligand = false;
+    std::vector<int32_t> dists;                  // n*n, element (i, j) at i + j*n (mol.ml:151-152)
+    std::vector<int32_t> rb_src, rb_dst;         // as written in the file (mol2 bond order)
+    std::vector<int32_t> rb_left, rb_right;      // fixed -> movable (pqrs.ml:49-56)
+    std::vector<std::vector<uint8_t>> rb_flags;  // movable side, axis tip included (the pqrs text)
+    std::vector<int32_t> typ;                    // FF types, assigned over the whole file
+    int n() const { return (int)x.size(); }
+};
+
+// src/ptable.ml:41-54, 86-100
+struct Elt { const char *sym; int anum; double radius; };
+const Elt kElts[] = {{"H", 1, 1.2}, {"C", 6, 1.7}, {"N", 7, 1.6}, {"O", 8, 1.55}, {"F", 9, 1.5}, {"Mg", 12, 2.2},
+                     {"P", 15, 1.95}, {"S", 16, 1.8}, {"Cl", 17, 1.8}, {"Br", 35, 1.9}, {"I", 53, 2.1}};
+const Elt *elt_by_sym(const std::string &s) {
+    for (const Elt &e : kElts) if (s == e.sym) return &e;
+    return nullptr;
+}
+const Elt *elt_by_anum(int a) {
+    for (const Elt &e : kElts) if (a == e.anum) return &e;
+    return nullptr;
+}
+
+std::vector<std::string> split_ws(const std::string &l) {
+    std::vector<std::string> t;
+    std::istringstream is(l);
+    std::string w;
+    while (is >> w) t.push_back(w);
+    return t;
+}
+std::string rstrip(std::string s) {
+    while (!s.empty() && (s.back() == '\r' || s.back() == '\n' || s.back() == ' ' || s.back() == '\t')) s.pop_back();
+    return s;
+}
+std::string strip(std::string s) {
+    s = rstrip(s);
+    size_t k = 0;
+    while (k < s.size() && (s[k] == ' ' || s[k] == '\t')) k++;
+    return s.substr(k);
+}
+
+// graph part of mol2pqrs: distances, rotatable bonds, rotatable groups.  false = disconnected atom
+// (Mol_graph.Disconnected_atom: the reference logs an error and emits nothing for that molecule)
+bool analyse_graph(Molecule &m, const std::vector<int> &bs, const std::vector<int> &bd, const std::vector<double> &bo) {
+    const int n = m.n(), nbonds = (int)bs.size();
+    std::vector<std::vector<int>> adj(n);
+    std::vector<int> deg(n, 0);
+    for (int b = 0; b < nbonds; b++) { adj[bs[b]].push_back(bd[b]); adj[bd[b]].push_back(bs[b]); deg[bs[b]]++; deg[bd[b]]++; }
+    m.dists.assign((size_t)n * n, 0);
+    std::vector<int> dist(n);
+    for (int s = 0; s < n; s++) {                // unit edge weights: BFS == the reference's shortest paths
+        std::fill(dist.begin(), dist.end(), -1);
+        dist[s] = 0;
+        std::queue<int> qu;
+        qu.push(s);
+        while (!qu.empty()) {
+            int u = qu.front(); qu.pop();
+            for (int v : adj[u]) if (dist[v] < 0) { dist[v] = dist[u] + 1; qu.push(v); }
+        }
+        for (int j = 0; j < n; j++) {
+            if (dist[j] < 0) return false;
+            m.dists[s + (size_t)j * n] = dist[j];
+        }
+    }
+    std::vector<int> comp(n);
+    for (int b = 0; b < nbonds; b++) {
+        if (bo[b] != 1.0 || deg[bs[b]] <= 1 || deg[bd[b]] <= 1) continue;
+        // components once bond b is cut; label = smallest atom index, as the min-label propagation yields
+        std::fill(comp.begin(), comp.end(), -1);
+        for (int s = 0; s < n; s++) {
+            if (comp[s] >= 0) continue;
+            comp[s] = s;
+            std::queue<int> qu;
+            qu.push(s);
+            while (!qu.empty()) {
+                int u = qu.front(); qu.pop();
+                for (int v : adj[u]) {
+                    if ((u == bs[b] && v == bd[b]) || (u == bd[b] && v == bs[b])) continue;
+                    if (comp[v] < 0) { comp[v] = s; qu.push(v); }
+                }
+            }
+        }
+        if (comp[bs[b]] == comp[bd[b]]) continue;            // ring bond
+        const int g1 = std::min(comp[bs[b]], comp[bd[b]]), g2 = std::max(comp[bs[b]], comp[bd[b]]);
+        int c1 = 0, c2 = 0;
+        for (int i = 0; i < n; i++) { c1 += comp[i] == g1; c2 += comp[i] == g2; }
+        // movable = the smaller side; ties go to the group holding the lower atom index (the reference
+        // takes whichever binding its hash table lists first: unpinned)
+        const int small = c1 <= c2 ? g1 : g2;
+        std::vector<uint8_t> flags(n);
+        for (int i = 0; i < n; i++) flags[i] = comp[i] == small;
+        m.rb_src.push_back(bs[b]); m.rb_dst.push_back(bd[b]);
+        const bool dst_moves = flags[bd[b]];
+        m.rb_left.push_back(dst_moves ? bs[b] : bd[b]);
+        m.rb_right.push_back(dst_moves ? bd[b] : bs[b]);
+        m.rb_flags.push_back(flags);
+    }
+    return true;
+}
+
+int parse_int(const std::string &s, bool &ok) {
+    char *e = nullptr;
+    long v = strtol(s.c_str(), &e, 10);
+    if (e == s.c_str() || *e != 0) ok = false;
+    return (int)v;
+}
+double parse_dbl(const std::string &s, bool &ok) {
+    char *e = nullptr;
+    double v = strtod(s.c_str(), &e);
+    if (e == s.c_str() || *e != 0) ok = false;
+    return v;
+}
+
+}  // namespace
+
+struct mmo_molfile {
+    std::vector<Molecule> mols;
+    int n_skipped = 0;
+    std::vector<int32_t> type_anum;
+    std::vector<double> type_q;
+    void assign_types() {                         // mol.ml:280-293: first-seen order over ligands, then atoms
+        std::map<std::pair<int32_t, double>, int32_t> ids;
+        type_anum.clear(); type_q.clear();
+        for (Molecule &m : mols) {
+            m.typ.resize(m.n());
+            for (int i = 0; i < m.n(); i++) {
+                auto key = std::make_pair(m.anum[i], m.q[i]);
+                auto it = ids.find(key);
+                if (it == ids.end()) {
+                    it = ids.emplace(key, (int32_t)ids.size()).first;
+                    type_anum.push_back(m.anum[i]); type_q.push_back(m.q[i]);
+                }
+                m.typ[i] = it->second;
+            }
+        }
+    }
+};
+
+using namespace mmo;
+
+extern "C" {
+
+int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) {
+    MMO_REQUIRE(path && out, "mmo_molfile_read_mol2: null pointer");
+    *out = nullptr;
+    std::ifstream in(path);
+    MMO_REQUIRE(in.good(), "mmo_molfile_read_mol2: cannot open %s", path);
+    std::vector<std::string> lines;
+    for (std::string l; std::getline(in, l);) lines.push_back(rstrip(l));
+    mmo_molfile *f = new mmo_molfile();
+    size_t p = 0;
+    while (p < lines.size()) {
+        if (lines[p] != "@<TRIPOS>MOLECULE") { p++; continue; }
+        size_t end = p + 1;
+        while (end < lines.size() && lines[end] != "@<TRIPOS>MOLECULE") end++;
+        // one molecule block [p, end)
+        Molecule m;
+        m.is_ligand = true;
+        bool ok = p + 2 < end;
+        int n_atoms = 0, n_bonds = 0;
+        if (ok) {
+            m.name = strip(lines[p + 1]);
+            auto t = split_ws(lines[p + 2]);
+            ok = t.size() >= 2;
+            if (ok) { n_atoms = parse_int(t[0], ok); n_bonds = parse_int(t[1], ok); }
+        }
+        size_t a0 = p + 3;
+        while (ok && a0 < end && lines[a0] != "@<TRIPOS>ATOM") a0++;
+        ok = ok && a0 + 1 + (size_t)n_atoms <= end;
+        std::vector<int> keep;                    // atom id (0-based, file order) -> index after lone-pair removal
+        if (ok) {
+            keep.assign(n_atoms, -1);
+            for (int i = 0; i < n_atoms && ok; i++) {
+                auto t = split_ws(lines[a0 + 1 + i]);      // id name x y z type resnum resname charge
+                if (t.size() < 9) { ok = false; break; }
+                if (t[5] == "LP") continue;                // lone pair: dropped together with its bonds
+                const std::string head = t[5].substr(0, t[5].find('.'));
+                const Elt *e = elt_by_sym(head);
+                if (!e) { set_error("mmo_molfile_read_mol2: unsupported mol2 atom type %s in %s", t[5].c_str(), m.name.c_str()); ok = false; break; }
+                keep[i] = m.n();
+                m.x.push_back(parse_dbl(t[2], ok)); m.y.push_back(parse_dbl(t[3], ok)); m.z.push_back(parse_dbl(t[4], ok));
+                m.q.push_back(parse_dbl(t[8], ok)); m.r.push_back(e->radius); m.anum.push_back(e->anum);
+            }
+        }
+        size_t b0 = a0 + 1 + (size_t)n_atoms;
+        while (ok && b0 < end && lines[b0] != "@<TRIPOS>BOND") b0++;
+        ok = ok && b0 + 1 + (size_t)n_bonds <= end;
+        std::vector<int> bs, bd;
+        std::vector<double> bo;
+        for (int b = 0; b < n_bonds && ok; b++) {
+            auto t = split_ws(lines[b0 + 1 + b]);          // id src dst type
+            if (t.size() < 4) { ok = false; break; }
+            int s = parse_int(t[1], ok) - 1, d = parse_int(t[2], ok) - 1;
+            if (!ok || s < 0 || d < 0 || s >= n_atoms || d >= n_atoms) { ok = false; break; }
+            double order;
+            if (t[3] == "1" || t[3] == "am") order = 1.0;
+            else if (t[3] == "2") order = 2.0;
+            else if (t[3] == "3") order = 3.0;
+            else if (t[3] == "ar") order = 1.5;
+            else { set_error("mmo_molfile_read_mol2: bond type %s in %s", t[3].c_str(), m.name.c_str()); ok = false; break; }
+            if (keep[s] < 0 || keep[d] < 0) continue;
+            bs.push_back(keep[s]); bd.push_back(keep[d]); bo.push_back(order);
+        }
+        if (ok && m.n() > 0 && analyse_graph(m, bs, bd, bo)) f->mols.push_back(std::move(m));
+        else f->n_skipped++;
+        p = end;
+    }
+    f->assign_types();
+    *out = f;
+    return MMO_OK;
+}
+
+int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out) {
+    MMO_REQUIRE(path && out, "mmo_molfile_read_pqrs: null pointer");
+    *out = nullptr;
+    std::ifstream in(path);
+    MMO_REQUIRE(in.good(), "mmo_molfile_read_pqrs: cannot open %s", path);
+    std::vector<std::string> lines;
+    for (std::string l; std::getline(in, l);) lines.push_back(rstrip(l));
+    mmo_molfile *f = new mmo_molfile();
+    size_t p = 0;
+    auto fail = [&](const char *what) { set_error("mmo_molfile_read_pqrs: %s (%s line %zu)", what, path, p + 1); delete f; return MMO_EINVAL; };
+    while (p < lines.size() && !strip(lines[p]).empty()) {
+        Molecule m;
+        m.is_ligand = !is_receptor;
+        // header  N:R:name  (ligand, the name may hold ':')  or  N:name  (receptor)
+        const std::string &h = lines[p];
+        bool ok = true;
+        size_t c1 = h.find(':');
+        if (c1 == std::string::npos) return fail("bad header");
+        const int n = parse_int(h.substr(0, c1), ok);
+        int nrb = 0;
+        if (is_receptor) {
+            m.name = h.substr(c1 + 1);
+        } else {
+            size_t c2 = h.find(':', c1 + 1);
+            if (c2 == std::string::npos) return fail("bad ligand header");
+            nrb = parse_int(h.substr(c1 + 1, c2 - c1 - 1), ok);
+            m.name = h.substr(c2 + 1);
+        }
+        if (!ok || n <= 0 || nrb < 0 || p + 1 + (size_t)n > lines.size()) return fail("bad header counts");
+        p++;
+        for (int i = 0; i < n; i++, p++) {
+            auto t = split_ws(lines[p]);
+            if (t.size() < 6) return fail("bad atom line");
+            const Elt *e = elt_by_sym(t[5]);
+            if (!e) return fail("unknown element symbol");
+            m.x.push_back(parse_dbl(t[0], ok)); m.y.push_back(parse_dbl(t[1], ok)); m.z.push_back(parse_dbl(t[2], ok));
+            m.q.push_back(parse_dbl(t[3], ok)); m.r.push_back(parse_dbl(t[4], ok)); m.anum.push_back(e->anum);
+            if (!ok) return fail("bad number in atom line");
+        }
+        if (!is_receptor) {
+            if (p + (size_t)nrb + (size_t)n > lines.size()) return fail("truncated ligand block");
+            for (int b = 0; b < nrb; b++, p++) {            // src/pqrs.ml:39-61
+                const std::string &l = lines[p];
+                size_t eq = l.find('='), dash = l.find('-');
+                if (eq == std::string::npos || dash == std::string::npos || dash > eq) return fail("bad rotatable bond line");
+                const int s = parse_int(l.substr(0, dash), ok), d = parse_int(l.substr(dash + 1, eq - dash - 1), ok);
+                auto t = split_ws(l.substr(eq + 1));
+                if (!ok || (int)t.size() != n || s < 0 || d < 0 || s >= n || d >= n) return fail("bad rotatable bond line");
+                std::vector<uint8_t> flags(n);
+                for (int i = 0; i < n; i++) flags[i] = t[i] == "1";
+                if (flags[s] == flags[d]) return fail("rotatable bond with both ends on one side");
+                m.rb_src.push_back(s); m.rb_dst.push_back(d);
+                m.rb_left.push_back(flags[d] ? s : d);
+                m.rb_right.push_back(flags[d] ? d : s);
+                m.rb_flags.push_back(flags);
+            }
+            m.dists.assign((size_t)n * n, 0);
+            for (int i = 0; i < n; i++, p++) {              // src/pqrs.ml:63-77
+                auto t = split_ws(lines[p]);
+                if ((int)t.size() != n) return fail("bad distance matrix row");
+                for (int j = 0; j < n; j++) m.dists[i + (size_t)j * n] = parse_int(t[j], ok);
+                if (!ok) return fail("bad distance matrix entry");
+            }
+        }
+        f->mols.push_back(std::move(m));
+        if (is_receptor) break;
+    }
+    for (size_t a = 0; a < f->mols.size(); a++)              // mol.ml:428-438
+        for (size_t b = a + 1; b < f->mols.size(); b++)
+            if (f->mols[a].name == f->mols[b].name) { set_error("mmo_molfile_read_pqrs: duplicate molecule name %s", f->mols[a].name.c_str()); delete f; return MMO_EINVAL; }
+    f->assign_types();
+    *out = f;
+    return MMO_OK;
+}
+
+int mmo_molfile_count(const mmo_molfile *f, int32_t *n_mols, int32_t *n_skipped) {
+    MMO_REQUIRE(f && n_mols, "mmo_molfile_count: null pointer");
+    *n_mols = (int32_t)f->mols.size();
+    if (n_skipped) *n_skipped = f->n_skipped;
+    return MMO_OK;
+}
+
+int mmo_molfile_shape(const mmo_molfile *f, int32_t k, int32_t *n_atoms, int32_t *n_rbonds, int32_t *rg_total,
+                      char *name, int32_t name_cap) {
+    MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_shape: molecule index out of range");
+    const Molecule &m = f->mols[k];
+    if (n_atoms) *n_atoms = m.n();
+    if (n_rbonds) *n_rbonds = (int32_t)m.rb_left.size();
+    if (rg_total) {
+        int tot = 0;
+        for (size_t b = 0; b < m.rb_flags.size(); b++)
+            for (int i = 0; i < m.n(); i++) tot += m.rb_flags[b][i] && i != m.rb_right[b];
+        *rg_total = tot;
+    }
+    if (name && name_cap > 0) { strncpy(name, m.name.c_str(), (size_t)name_cap - 1); name[name_cap - 1] = 0; }
+    return MMO_OK;
+}
+
+int mmo_molfile_get(const mmo_molfile *f, int32_t k, double *xs, double *ys, double *zs, double *q, double *r,
+                    int32_t *anum, int32_t *typ, int32_t *dists, int32_t *rb_left, int32_t *rb_right,
+                    int32_t *rg_off, int32_t *rg_idx) {
+    MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_get: molecule index out of range");
+    const Molecule &m = f->mols[k];
+    const int n = m.n();
+    if (xs) memcpy(xs, m.x.data(), n * sizeof(double));
+    if (ys) memcpy(ys, m.y.data(), n * sizeof(double));
+    if (zs) memcpy(zs, m.z.data(), n * sizeof(double));
+    if (q) memcpy(q, m.q.data(), n * sizeof(double));
+    if (r) memcpy(r, m.r.data(), n * sizeof(double));
+    if (anum) memcpy(anum, m.anum.data(), n * sizeof(int32_t));
+    if (typ) memcpy(typ, m.typ.data(), n * sizeof(int32_t));
+    if (dists && !m.dists.empty()) memcpy(dists, m.dists.data(), (size_t)n * n * sizeof(int32_t));
+    const int nrb = (int)m.rb_left.size();
+    if (rb_left) memcpy(rb_left, m.rb_left.data(), nrb * sizeof(int32_t));
+    if (rb_right) memcpy(rb_right, m.rb_right.data(), nrb * sizeof(int32_t));
+    if (rg_off) {
+        int tot = 0;
+        for (int b = 0; b < nrb; b++) {              // movable atoms, axis tip excluded (pqrs.ml:80-87)
+            rg_off[b] = tot;
+            for (int i = 0; i < n; i++)
+                if (m.rb_flags[b][i] && i != m.rb_right[b]) { if (rg_idx) rg_idx[tot] = i; tot++; }
+        }
+        rg_off[nrb] = tot;
+    }
+    return MMO_OK;
+}
+
+int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum, double *type_q) {
+    MMO_REQUIRE(f && n_types, "mmo_molfile_types: null pointer");
+    *n_types = (int32_t)f->type_anum.size();
+    if (type_anum) memcpy(type_anum, f->type_anum.data(), f->type_anum.size() * sizeof(int32_t));
+    if (type_q) memcpy(type_q, f->type_q.data(), f->type_q.size() * sizeof(double));
+    return MMO_OK;
+}
+
+int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path) {
+    MMO_REQUIRE(f && path, "mmo_molfile_write_pqrs: null pointer");
+    FILE *o = fopen(path, "w");
+    MMO_REQUIRE(o != nullptr, "mmo_molfile_write_pqrs: cannot create %s", path);
+    for (const Molecule &m : f->mols) {
+        const int n = m.n();
+        if (m.is_ligand) fprintf(o, "%d:%d:%s\n", n, (int)m.rb_left.size(), m.name.c_str());
+        else fprintf(o, "%d:%s\n", n, m.name.c_str());
+        for (int i = 0; i < n; i++) {
+            const Elt *e = elt_by_anum(m.anum[i]);
+            fprintf(o, "%g %g %g %g %g %s\n", m.x[i], m.y[i], m.z[i], m.q[i], m.r[i], e ? e->sym : "X");
+        }
+        if (!m.is_ligand) continue;
+        for (size_t b = 0; b < m.rb_flags.size(); b++) {
+            fprintf(o, "%d-%d=", m.rb_src[b], m.rb_dst[b]);
+            for (int i = 0; i < n; i++) fputs(m.rb_flags[b][i] ? " 1" : " 0", o);
+            fputc('\n', o);
+        }
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j < n; j++) fprintf(o, j ? " %d" : "%d", m.dists[i + (size_t)j * n]);
+            fputc('\n', o);
+        }
+    }
+    fclose(o);
+    return MMO_OK;
+}
+
+// straight to the device handle: Mol.translate_to lig V3.origin (lds.ml:44-52) when `centered`, with the
+// Kahan-averaged centre (Batteries A.favg as restated in the oracle)
+int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand **out) {
+    MMO_REQUIRE(f && out && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_ligand: molecule index out of range");
+    const Molecule &m = f->mols[k];
+    const int n = m.n(), nrb = (int)m.rb_left.size();
+    std::vector<double> x = m.x, y = m.y, z = m.z;
+    if (centered) {
+        auto favg = [n](const std::vector<double> &a) {
+            double s = 0.0, c = 0.0;
+            for (int i = 0; i < n; i++) { double yy = a[i] - c, t = s + yy; c = (t - s) - yy; s = t; }
+            return s / n;
+        };
+        const double cx = favg(m.x), cy = favg(m.y), cz = favg(m.z);
+        for (int i = 0; i < n; i++) { x[i] = m.x[i] + (0.0 - cx); y[i] = m.y[i] + (0.0 - cy); z[i] = m.z[i] + (0.0 - cz); }
+    }
+    std::vector<int32_t> off(nrb + 1), idx;
+    {
+        int32_t tot = 0;
+        MMO_TRY(mmo_molfile_shape(f, k, nullptr, nullptr, &tot, nullptr, 0));
+        idx.resize(std::max(1, tot));
+        MMO_TRY(mmo_molfile_get(f, k, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, off.data(), idx.data()));
+    }
+    return mmo_ligand_create(n, x.data(), y.data(), z.data(), m.q.data(), m.r.data(), m.anum.data(), m.typ.data(),
+                             m.dists.empty() ? nullptr : m.dists.data(), nrb, m.rb_left.data(), m.rb_right.data(),
+                             off.data(), idx.data(), out);
+}
+
+int mmo_molfile_destroy(mmo_molfile *f) {
+    delete f;
+    return MMO_OK;
+}
+
+}  // extern "C"
