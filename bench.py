@@ -146,10 +146,28 @@ def run_reference(args, rank, world):
                              "note": "C restatement of the OCaml reference (oracle/mmo_oracle.c, gcc -O2 "
                                      "-ffp-contract=off, OpenMP over poses); OCaml is not installable here"},
             "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE line of stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    # stdout carries the one JSON line and nothing else: whatever a library prints on fd 1 (NCCL's version
+    # banner under NCCL_DEBUG=VERSION, for one) is sent to stderr; the JSON goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -165,8 +183,6 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
-    # stdout carries the one JSON line and nothing else: NCCL's version/debug banner goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import mmo_b200
     from mmo_b200 import ScanParams, ScanResult
@@ -425,7 +441,7 @@ def main():
             line["cpu_baseline"] = {"value": n_s / dt, "unit": "poses/s", "cores": nthreads, "kind": "port",
                                     "sample": f"{n_s} random (rotation, lattice point) poses of the same workload, "
                                               f"{dt:.1f} s, C restatement of the OCaml reference (oracle/), OpenMP"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ck(L.mmo_scan_destroy(job))
     if dist is not None:
         dist.barrier()
