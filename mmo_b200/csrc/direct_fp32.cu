@@ -33,14 +33,15 @@ namespace mmo {
 
 constexpr int LJ = 4;            // ligand atoms per chunk (half a k-d leaf of the ligand)
 constexpr int kFixLJ = LJ;
-constexpr int TPB = 256;         // threads per block
+constexpr int TPB = 512;         // threads per block (one persistent block per SM: one copy of the receptor tile)
+constexpr int kBlocksPerSM = 1;
 constexpr int PPT = 2;           // poses per thread
 constexpr int PPB = TPB * PPT;   // poses per block
-constexpr int LIST_CAP = 192;    // per-warp list of near receptor atoms
+constexpr int LIST_CAP = 256;    // per-warp list of near receptor atoms
 constexpr int NF = 7;            // list fields: x', y', z', |x'|^2, q_i q_j, A_i A_j, -B_i B_j
 constexpr int MAX_TILE_GROUPS = 128;
-constexpr int kSumEvery = 4;     // list steps (of 4 atoms) summed in fp32 before the fp64 accumulation
-constexpr float kRhoExpand2 = 12.25f;  // the expanded form of r^2 is used while rho <= 3.5 A
+constexpr int kSumEvery = 16;    // list steps (of 4 atoms) summed in fp32 before the fp64 accumulation
+constexpr float kRhoExpand2 = 20.25f;  // the expanded form of r^2 is used while rho <= 4.5 A
 static_assert(kBlob == 16, "two receptor groups per warp-wide test");
 static_assert(LIST_CAP % 4 == 0 && LIST_CAP >= 128, "list must take one more step (64 atoms) before a flush");
 constexpr int NEAR_CAP = MAX_TILE_GROUPS + 8;   // per-warp list of near group ids (bytes)
@@ -172,7 +173,7 @@ __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const 
 // per-warp lists [NF][LIST_CAP] (structure of arrays: conflict-free compaction stores, LDS.128 = 4 atoms
 // of one field), element bytes [tile_atoms].
 template <int VARIANT, bool STATS>
-__global__ void __launch_bounds__(TPB, 2)
+__global__ void __launch_bounds__(TPB, kBlocksPerSM)
 direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int tile_groups, int n_split,
                    unsigned long long *__restrict__ work, double *__restrict__ out, uint8_t *__restrict__ flags) {
     // Persistent blocks (2 per SM), one launch per receptor tile [b0, b0 + nb) of groups.  A work unit is
@@ -1031,10 +1032,10 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     // balances the warps to a few percent; persistent grid of 2 blocks per SM (fewer for small batches)
     const int n_chunks = lig->n_fast / LJ;
     const int64_t n_groups = (n_poses + 32 * PPT - 1) / (32 * PPT);
-    const int64_t resident_warps = 2LL * R.sm_count * (TPB / 32);
+    const int64_t resident_warps = (int64_t)kBlocksPerSM * R.sm_count * (TPB / 32);
     const int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (20 * resident_warps + n_groups - 1) / n_groups));
     const int64_t n_units = n_groups * n_split;
-    const unsigned blocks = (unsigned)std::min<int64_t>(2LL * R.sm_count, (n_units + TPB / 32 - 1) / (TPB / 32));
+    const unsigned blocks = (unsigned)std::min<int64_t>((int64_t)kBlocksPerSM * R.sm_count, (n_units + TPB / 32 - 1) / (TPB / 32));
     const int n_tiles = (rec->n_blobs + tile_blobs - 1) / tile_blobs;
     const int n_parts = n_tiles * n_split;
     DevBuf<double> part;
