@@ -183,6 +183,16 @@ int mmo_score_interp_poses_dev(const mmo_grid *grid, const mmo_ligand *lig, int6
 int mmo_vdw_mask_build(int32_t n, const double *xs, const double *ys, const double *zs,
                        const double *radii, double step, const int32_t dims[3], uint8_t *out_bits,
                        mmo_mask **out_mask);
+/* N3: the other bitmasks of the simulation grid, built on the device, same bit layout.
+ *   Lds.first_solvent_shell   (src/lds.ml:172-184): inside r_vdW + 1.4 A of some atom and inside r_vdW of none
+ *   Lds.bitmask_whole_protein (src/lds.ml:97-145) : nearest protein atom closer than 12 A
+ *   Lds.bitmask_ROI_only      (src/lds.ml:269-305): closer than roi_r + 24 A to the ROI centre (the grid-build mask) */
+int mmo_mask_first_solvent_shell(int32_t n, const double *xs, const double *ys, const double *zs, const double *radii,
+                                 double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask);
+int mmo_mask_whole_protein(int32_t n, const double *xs, const double *ys, const double *zs,
+                           double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask);
+int mmo_mask_roi_only(const double roi_c[3], double roi_r, double step, const int32_t dims[3], uint8_t *out_bits,
+                      mmo_mask **out_mask);
 int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out);
 int mmo_mask_destroy(mmo_mask *mask);
 /* Mol.protein_ligand_clash (src/mol.ml:1195-1203): out_flags[p] = 1 when any atom of pose p has any

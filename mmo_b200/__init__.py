@@ -396,6 +396,34 @@ class Lds:
         return VdwMask(h, step, dims, bits)
 
     @staticmethod
+    def _mask_call(fn, dims, step, *args):
+        _need_init()
+        nvox = int(dims[0]) * int(dims[1]) * int(dims[2])
+        bits = np.zeros((nvox + 7) // 8, np.uint8)
+        h = _vp()
+        dd = (C.c_int32 * 3)(*[int(v) for v in dims])
+        _ck(fn(*args, C.c_double(step), dd, bits.ctypes.data_as(_bp), C.byref(h)))
+        return VdwMask(h, step, dims, bits)
+
+    @staticmethod
+    def first_solvent_shell(xs, ys, zs, radii, step, dims):
+        """src/lds.ml:172-184"""
+        (a, pa), (b, pb), (c, pc), (r, pr) = _d(xs), _d(ys), _d(zs), _d(radii)
+        return Lds._mask_call(lib().mmo_mask_first_solvent_shell, dims, step, C.c_int32(len(a)), pa, pb, pc, pr)
+
+    @staticmethod
+    def bitmask_whole_protein(xs, ys, zs, step, dims):
+        """src/lds.ml:97-145"""
+        (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+        return Lds._mask_call(lib().mmo_mask_whole_protein, dims, step, C.c_int32(len(a)), pa, pb, pc)
+
+    @staticmethod
+    def bitmask_ROI_only(roi, step, dims):
+        """src/lds.ml:269-305; roi = (cx, cy, cz, r)"""
+        c = (C.c_double * 3)(*roi[:3])
+        return Lds._mask_call(lib().mmo_mask_roi_only, dims, step, c, C.c_double(roi[3]))
+
+    @staticmethod
     def exhaustive_rigid_ligand_docking(topk, roi, trans_step, rotations, lig, rec=None, grid=None, vdw_mask=None,
                                         e_intra_const=0.0, variant=VARIANT_SHIFTED, prec=PREC_FP32,
                                         first_point=0, n_points=-1):

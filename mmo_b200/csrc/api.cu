@@ -380,6 +380,61 @@ int mmo_vdw_mask_build(int32_t n, const double *xs, const double *ys, const doub
     return rc;
 }
 
+// N3 masks.  mode 0: vdW volume (radii), 1: first solvent shell (radii + 1.4 set, radii unset), 2: whole protein (12 A)
+static int atom_mask_build(int mode, int32_t n, const double *xs, const double *ys, const double *zs, const double *radii,
+                           double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(n >= 0 && (n == 0 || (xs && ys && zs && (radii || mode == 2))), "mask build: bad atom arrays");
+    mmo_mask *m = nullptr;
+    MMO_TRY(mask_alloc(step, dims, &m));
+    int rc = MMO_OK;
+    do {
+        cudaError_t e = cudaMemsetAsync(m->words.p, 0, m->hwords.size() * sizeof(uint32_t), rt().stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "memset mask", __FILE__, __LINE__); break; }
+        std::vector<double> r1((size_t)n);
+        for (int i = 0; i < n; i++) r1[i] = mode == 2 ? 12.0 : (mode == 1 ? radii[i] + 1.4 : radii[i]);   // const.ml:10,12
+        DevBuf<double> dx, dy, dz, dr, dr0;
+        if ((rc = dx.upload(xs, (size_t)n)) || (rc = dy.upload(ys, (size_t)n)) || (rc = dz.upload(zs, (size_t)n)) ||
+            (rc = dr.upload(r1)))
+            break;
+        if ((rc = launch_vdw_mask(n, dx.p, dy.p, dz.p, dr.p, m, true))) break;
+        if (mode == 1) {
+            if ((rc = dr0.upload(radii, (size_t)n))) break;
+            if ((rc = launch_vdw_mask(n, dx.p, dy.p, dz.p, dr0.p, m, false))) break;
+        }
+        rc = d2h_sync(m->hwords.data(), m->words.p, m->hwords.size() * sizeof(uint32_t));
+    } while (0);
+    if (rc == MMO_OK && out_bits) memcpy(out_bits, m->hwords.data(), (m->nbits + 7) / 8);
+    if (rc != MMO_OK || !out_mask) { delete m; m = nullptr; }
+    if (out_mask) *out_mask = m;
+    return rc;
+}
+
+int mmo_mask_first_solvent_shell(int32_t n, const double *xs, const double *ys, const double *zs, const double *radii,
+                                 double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) {
+    return atom_mask_build(1, n, xs, ys, zs, radii, step, dims, out_bits, out_mask);
+}
+
+int mmo_mask_whole_protein(int32_t n, const double *xs, const double *ys, const double *zs,
+                           double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) {
+    return atom_mask_build(2, n, xs, ys, zs, nullptr, step, dims, out_bits, out_mask);
+}
+
+int mmo_mask_roi_only(const double roi_c[3], double roi_r, double step, const int32_t dims[3], uint8_t *out_bits,
+                      mmo_mask **out_mask) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(roi_c && roi_r >= 0.0, "mmo_mask_roi_only: bad ROI");
+    mmo_mask *m = nullptr;
+    MMO_TRY(mask_alloc(step, dims, &m));
+    const double r = roi_r + (12.0 * 2.0);               // lds.ml:272-275: E_inter must be able to vanish outside the ROI
+    int rc = launch_sphere_mask(roi_c[0], roi_c[1], roi_c[2], r, m);
+    if (rc == MMO_OK) rc = d2h_sync(m->hwords.data(), m->words.p, m->hwords.size() * sizeof(uint32_t));
+    if (rc == MMO_OK && out_bits) memcpy(out_bits, m->hwords.data(), (m->nbits + 7) / 8);
+    if (rc != MMO_OK || !out_mask) { delete m; m = nullptr; }
+    if (out_mask) *out_mask = m;
+    return rc;
+}
+
 int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out) {
     MMO_TRY(require_ready());
     MMO_REQUIRE(bits && out, "mmo_mask_upload: null argument");

@@ -205,7 +205,8 @@ int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, 
 int launch_trilin(const mmo_grid *g, int type, int64_t n, const double *d_x, const double *d_y,
                   const double *d_z, double *d_out);
 int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d_z, const double *d_r,
-                    const mmo_mask *m);
+                    const mmo_mask *m, bool set_bits = true);
+int launch_sphere_mask(double cx, double cy, double cz, double r, const mmo_mask *m);
 int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags);
 int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, const int64_t *d_points,
                           const int32_t *d_rot_perm, int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter);

@@ -1,6 +1,9 @@
 // mask.cu -- K5: protein vdW occupancy bitmask and the clash prefilter.  Compiled with -fmad=false:
 // the comparisons are done on the same IEEE doubles as the reference, so the bits are identical.
 //   Lds.atom_bitmask_set / vdW_volume    src/lds.ml:148-196
+//   Lds.first_solvent_shell              src/lds.ml:172-184 (set r + r_H2O, then unset r)
+//   Lds.bitmask_whole_protein            src/lds.ml:97-145  (vdW_volume with r = 12 A for every atom)
+//   Lds.bitmask_ROI_only                 src/lds.ml:269-305
 //   Grid.coord_of_point                  src/grid.ml:87-91
 //   G3D.vdW_clash_OR / vdW_clash_AND     src/G3D.ml:162-213
 //   Mol.protein_ligand_clash             src/mol.ml:1195-1203
@@ -15,7 +18,7 @@ namespace mmo {
 __global__ void vdw_mask_kernel(int n, const double *__restrict__ px, const double *__restrict__ py,
                                 const double *__restrict__ pz, const double *__restrict__ pr,
                                 double step, double q0, double q1, double q2,
-                                int dim0, int dim1, int dim2, uint32_t *__restrict__ words) {
+                                int dim0, int dim1, int dim2, uint32_t *__restrict__ words, int set_bits) {
     const int a = blockIdx.x;
     if (a >= n) return;
     const double x = px[a], y = py[a], z = pz[a], radius = pr[a];
@@ -32,9 +35,29 @@ __global__ void vdw_mask_kernel(int n, const double *__restrict__ px, const doub
         double dx = x - gx, dy = y - gy, dz = z - gz;      // V3.dist2 xyz (make x y z)
         if (dx * dx + dy * dy + dz * dz < r2) {
             size_t idx = (size_t)i + (size_t)j * dim0 + (size_t)k * dim0 * dim1;
-            atomicOr(words + (idx >> 5), 1u << (idx & 31));
+            if (set_bits) atomicOr(words + (idx >> 5), 1u << (idx & 31));
+            else atomicAnd(words + (idx >> 5), ~(1u << (idx & 31)));      // atom_bitmask_set ... false
         }
     }
+}
+
+// Lds.bitmask_ROI_only (src/lds.ml:269-305): grid points closer than r to c; thread = one 32-voxel word
+__global__ void __launch_bounds__(256)
+sphere_mask_kernel(double cx, double cy, double cz, double r2, double q0, double q1, double q2,
+                   int dim0, int dim1, int dim2, size_t nbits, uint32_t *__restrict__ words) {
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32 >= nbits) return;
+    uint32_t bits = 0u;
+    const size_t xy = (size_t)dim0 * dim1;
+    for (int b = 0; b < 32; b++) {
+        const size_t idx = w * 32 + b;
+        if (idx >= nbits) break;
+        const int k = (int)(idx / xy), j = (int)((idx - (size_t)k * xy) / dim0), i = (int)(idx - (size_t)k * xy - (size_t)j * dim0);
+        const double x = (double)i * q0, y = (double)j * q1, z = (double)k * q2;
+        const double dx = cx - x, dy = cy - y, dz = cz - z;            // V3.dist2 c (create x y z)
+        if (dx * dx + dy * dy + dz * dz < r2) bits |= 1u << b;
+    }
+    words[w] = bits;
 }
 
 __device__ __forceinline__ bool bit_at(const uint32_t *__restrict__ w, long idx) {
@@ -119,8 +142,22 @@ scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim,
     if (keep) frames[s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1))] = frame;
 }
 
+int launch_sphere_mask(double cx, double cy, double cz, double r, const mmo_mask *m) {
+    double q[3];
+    for (int d = 0; d < 3; d++) {
+        int np = m->dims[d] - 1;
+        q[d] = np > 0 ? (m->step * (double)np) / (double)np : 0.0;
+    }
+    const size_t nwords = (m->nbits + 31) / 32;
+    KernelScope ks(K_VDW_MASK);
+    sphere_mask_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, rt().stream>>>(cx, cy, cz, r * r, q[0], q[1], q[2], m->dims[0],
+                                                                                 m->dims[1], m->dims[2], m->nbits, m->words.p);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
 int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d_z, const double *d_r,
-                    const mmo_mask *m) {
+                    const mmo_mask *m, bool set_bits) {
     if (n == 0) return MMO_OK;
     double q[3];
     for (int d = 0; d < 3; d++) {
@@ -129,7 +166,7 @@ int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d
     }
     KernelScope ks(K_VDW_MASK);
     vdw_mask_kernel<<<n, 128, 0, rt().stream>>>(n, d_x, d_y, d_z, d_r, m->step, q[0], q[1], q[2],
-                                                m->dims[0], m->dims[1], m->dims[2], m->words.p);
+                                                m->dims[0], m->dims[1], m->dims[2], m->words.p, set_bits ? 1 : 0);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }

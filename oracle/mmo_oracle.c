@@ -328,6 +328,58 @@ void orc_vdw_volume(int P, const double *px, const double *py, const double *pz,
     }
 }
 
+/* src/lds.ml:148-170 atom_bitmask_set with an arbitrary boolean */
+static void atom_bitmask_put(double ax, double ay, double az, double radius, double step, const int dims[3],
+                             uint8_t *mask, int b) {
+    int i = (int)((ax - 0.0) / step), j = (int)((ay - 0.0) / step), k = (int)((az - 0.0) / step);
+    int r_steps = (int)ceil(radius / step);
+    double r2 = radius * radius;
+    for (int ii = i - r_steps; ii <= i + r_steps; ii++) {
+        if (ii < 0 || ii >= dims[0]) continue;
+        double x = orc_grid_node(step, dims[0], ii);
+        for (int jj = j - r_steps; jj <= j + r_steps; jj++) {
+            if (jj < 0 || jj >= dims[1]) continue;
+            double y = orc_grid_node(step, dims[1], jj);
+            for (int kk = k - r_steps; kk <= k + r_steps; kk++) {
+                if (kk < 0 || kk >= dims[2]) continue;
+                double z = orc_grid_node(step, dims[2], kk);
+                if (dist2(ax, ay, az, x, y, z) < r2)
+                    mask_put(mask, (size_t)ii + (size_t)jj * dims[0] + (size_t)kk * dims[0] * dims[1], b);
+            }
+        }
+    }
+}
+
+/* src/lds.ml:172-184 first_solvent_shell: SET inside r_vdW + r_H2O for every atom, then UNSET inside r_vdW
+ * (src/const.ml:10 r_H2O = 1.4) */
+void orc_first_solvent_shell(int P, const double *px, const double *py, const double *pz, const double *pr,
+                             double step, const int dims[3], uint8_t *mask) {
+    for (int a = 0; a < P; a++) atom_bitmask_put(px[a], py[a], pz[a], pr[a] + 1.4, step, dims, mask, 1);
+    for (int a = 0; a < P; a++) atom_bitmask_put(px[a], py[a], pz[a], pr[a], step, dims, mask, 0);
+}
+
+/* src/lds.ml:97-145 bitmask_whole_protein: grid points whose nearest protein atom is closer than
+ * Const.charged_cutoff = 12 A (BST.nearest_neighbor -> V3.dist = sqrt(dist2)); brute force over the atoms */
+void orc_bitmask_whole_protein(int P, const double *px, const double *py, const double *pz,
+                               double step, const int dims[3], uint8_t *mask) {
+    for (int i = 0; i < dims[0]; i++) {
+        double x = orc_grid_node(step, dims[0], i);
+        for (int j = 0; j < dims[1]; j++) {
+            double y = orc_grid_node(step, dims[1], j);
+            for (int k = 0; k < dims[2]; k++) {
+                double z = orc_grid_node(step, dims[2], k);
+                double best = INFINITY;
+                for (int a = 0; a < P; a++) {
+                    double d = sqrt(dist2(x, y, z, px[a], py[a], pz[a]));
+                    if (d < best) best = d;
+                }
+                if (best < 12.0)
+                    mask_put(mask, (size_t)i + (size_t)j * dims[0] + (size_t)k * dims[0] * dims[1], 1);
+            }
+        }
+    }
+}
+
 /* src/G3D.ml:162-186 vdW_clash_OR ; 189-213 vdW_clash_AND */
 static void corner_bits(double step, const int dims[3], const uint8_t *mask,
                         double x, double y, double z, int bits[8]) {

@@ -83,6 +83,11 @@ void orc_bitmask_sphere(double step, const int dims[3], double cx, double cy, do
 /* ---- vdW occupancy mask and clash tests, lds.ml:148-196, G3D.ml:162-213, mol.ml:1195-1218 ---- */
 void orc_vdw_volume(int P, const double *px, const double *py, const double *pz, const double *pr,
                     double step, const int dims[3], uint8_t *mask);
+/* lds.ml:172-184 first solvent shell; lds.ml:97-145 voxels within 12 A of the protein */
+void orc_first_solvent_shell(int P, const double *px, const double *py, const double *pz, const double *pr,
+                             double step, const int dims[3], uint8_t *mask);
+void orc_bitmask_whole_protein(int P, const double *px, const double *py, const double *pz,
+                               double step, const int dims[3], uint8_t *mask);
 int orc_vdw_clash_OR(double step, const int dims[3], const uint8_t *mask, double x, double y, double z);
 int orc_vdw_clash_AND(double step, const int dims[3], const uint8_t *mask, double x, double y, double z);
 int orc_protein_ligand_clash(double step, const int dims[3], const uint8_t *mask,

@@ -265,6 +265,22 @@ def bitmask_sphere(step, dims, c, r):
     return mask
 
 
+def first_solvent_shell(xs, ys, zs, radii, step, dims):
+    nvox = dims[0] * dims[1] * dims[2]
+    mask = np.zeros((nvox + 7) // 8 + 8, np.uint8)
+    lib().orc_first_solvent_shell(C.c_int(len(xs)), d(xs)[1], d(ys)[1], d(zs)[1], d(radii)[1], C.c_double(step),
+                                  (C.c_int * 3)(*dims), mask.ctypes.data_as(_bp))
+    return mask[:(nvox + 7) // 8]
+
+
+def bitmask_whole_protein(xs, ys, zs, step, dims):
+    nvox = dims[0] * dims[1] * dims[2]
+    mask = np.zeros((nvox + 7) // 8 + 8, np.uint8)
+    lib().orc_bitmask_whole_protein(C.c_int(len(xs)), d(xs)[1], d(ys)[1], d(zs)[1], C.c_double(step),
+                                    (C.c_int * 3)(*dims), mask.ctypes.data_as(_bp))
+    return mask[:(nvox + 7) // 8]
+
+
 def vdw_volume(xs, ys, zs, radii, step, dims):
     nvox = dims[0] * dims[1] * dims[2]
     mask = np.zeros((nvox + 7) // 8 + 8, np.uint8)

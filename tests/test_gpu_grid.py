@@ -105,3 +105,22 @@ def test_vdw_mask_and_clash_bit_identical(gpu, orc, c2, c2_roi_rec):
     ref = np.array([orc.protein_ligand_clash(workloads.GRID_STEP, dims, want, X[p], Y[p], Z[p]) for p in range(len(R))])
     assert np.array_equal(got, ref)
     assert 0 < ref.sum() < len(ref)
+
+
+def test_n3_masks_bit_identical(gpu, orc, c2):
+    """first solvent shell, whole-protein and ROI-only bitmasks (lds.ml:97-145, 172-184, 269-305) on the device
+    against the oracle's literal loops; 1 A grid over the simulation box keeps the CPU side short"""
+    m = c2["rec"]
+    dims = gpu.Grid.from_box(1.0, *c2["sim_dims"])
+    got = gpu.Lds.first_solvent_shell(m.xs, m.ys, m.zs, m.r, 1.0, dims)
+    want = orc.first_solvent_shell(m.xs, m.ys, m.zs, m.r, 1.0, dims)
+    assert np.array_equal(got.bits, want) and 0 < np.unpackbits(want).sum()
+    vdw = gpu.Lds.vdW_volume(m.xs, m.ys, m.zs, m.r, 1.0, dims)
+    assert not (got.bits & vdw.bits).any()                 # the shell lies outside every vdW sphere
+    sel = slice(0, 400)                                    # brute-force nearest neighbour on the CPU: a part of the protein
+    gotw = gpu.Lds.bitmask_whole_protein(m.xs[sel], m.ys[sel], m.zs[sel], 1.0, dims)
+    wantw = orc.bitmask_whole_protein(m.xs[sel], m.ys[sel], m.zs[sel], 1.0, dims)
+    assert np.array_equal(gotw.bits, wantw) and np.unpackbits(wantw).sum() > 1000
+    gotr = gpu.Lds.bitmask_ROI_only(c2["roi"], 1.0, dims)
+    wantr = orc.bitmask_sphere(1.0, dims, c2["roi"][:3], c2["roi"][3] + 24.0)
+    assert np.array_equal(gotr.bits, wantr)
