@@ -18,6 +18,7 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "smsp__warps_eligible.avg.per_cycle_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
