@@ -91,9 +91,9 @@ def ncu_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)["direct_fp32_kernel"]
-        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+        return t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
     except Exception:
-        return None
+        return None, None
 
 
 def poses_last_slab(SR, pps):
@@ -421,7 +421,9 @@ def main():
                     "steps": e2e_steps, "api": "mmo_scan() one-shot, host buffers"},
             "roofline": {"bound": "fp32", "kernel": "direct_fp32_kernel", "achieved": achieved, "peak": fp32_peak.value,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak.value if fp32_peak.value else None,
-                         "traffic": ncu_traffic(), "peak_source": "measured on this box: FP32 FMA chain (mmo_measure_fp32_peak); "
+                         "traffic": ncu_traffic()[0], "traffic_unit": "bytes of DRAM per launch", "traffic_source": ncu_traffic()[1],
+                         "algorithmic_bytes_per_launch": rec_m.n * 16 + poses_per_step * 16,
+                         "peak_source": "measured on this box: FP32 FMA chain (mmo_measure_fp32_peak); "
                          "MEASURED_PEAKS.json has no FP32 ALU figure", "kernel_ms_per_launch": k_ms,
                          "kernel_share_of_step": kms.value / dev_ms if dev_ms else None,
                          "hard_fix_ms_per_launch": fix_ms.value / max(1, kn.value),
