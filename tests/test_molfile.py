@@ -182,3 +182,19 @@ def test_molfile_ligand_scores_like_the_python_path(gpu, orc, c2, c2_roi_rec):
     Xc = np.tile(lig_c.xs, (3, 1)) + 40.0
     assert np.array_equal(gpu.Mol.ene_intra_UFFNB_brute(lig_c, Xc, np.tile(lig_c.ys, (3, 1)), np.tile(lig_c.zs, (3, 1))),
                           gpu.Mol.ene_intra_UFFNB_brute(lig_p, Xc, np.tile(lig_p.ys, (3, 1)), np.tile(lig_p.zs, (3, 1))))
+
+
+@pytest.mark.parametrize("name", ["docked", "ligdecs", "minimized", "xtal_rec"])
+def test_reference_pqrs_center_script_agrees(name):
+    """golden vectors made by the reference's own bin/pqrs_center.py run on our fixtures
+    (tools/make_refpy_fixture.py): same header line, same geometric centre through '%g'"""
+    import json
+    want = json.load(open(os.path.join(G, "pqrs_center.json")))[name]
+    f = mmo_b200.MolFile(os.path.join(G, name + ".pqrs"), kind="receptor_pqrs" if name == "xtal_rec" else "ligand_pqrs")
+    m = f.mol(0)
+    header = f"{m.n}:{m.name}" if name == "xtal_rec" else f"{m.n}:{m.n_rbonds}:{m.name}"
+    assert header == want[0]
+    sx = sy = sz = 0.0
+    for i in range(m.n):                         # the script's plain left-to-right sums
+        sx += m.xs[i]; sy += m.ys[i]; sz += m.zs[i]
+    assert "%g %g %g" % (sx / m.n, sy / m.n, sz / m.n) == want[1]
