@@ -177,3 +177,34 @@ def test_scan_topk_equals_sorting_every_pose(gpu, orc, c2, setup, prec):
         for f, s_ in zip(got["top_frames"], got["top_scores"]):      # every reported pose carries its own score
             assert tol_ok([s_], [by_frame[int(f)]]).all()
         assert tol_ok([got["best_score"]], [e[order[0]]]).all()
+
+
+def test_lds_ext_c_program_matches_the_python_path(gpu, orc, c2, c2_roi_rec, setup):
+    """tools/lds_ext.c: `lds --ext` as a plain C program on the C ABI (no Python in that process), fed with the
+    committed .pqrs / .bild files; same lattice, same survivors, same top-k as the ctypes path on the same inputs"""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(gpu.LIB_PATH), "lds_ext")
+    assert os.path.exists(exe), "build it with `make -C mmo_b200/csrc lds_ext` (done by __graft_entry__.build())"
+    G = workloads.GOLDEN
+    for extra in ([], ["--no-prefilter"], ["--no-prefilter", "--fp64"]):
+        out = subprocess.run([exe, "-lig", os.path.join(G, "docked.pqrs"), "-rec", os.path.join(G, "xtal_rec.pqrs"),
+                              "-roi", os.path.join(G, "ROI.bild"), "--ext", "2.0,96", "-top", "12"] + extra,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        lines = out.stdout.strip().split("\n")
+        rows = [l.split("\t") for l in lines if l and l[0].isdigit()]
+        best = [l for l in lines if l.startswith("best")][0].split("\t")
+        rec, lig, mask, dims, e_intra = setup
+        rot = gpu.SO3.rotations(96)
+        want = gpu.Lds.exhaustive_rigid_ligand_docking(
+            12, c2["roi"], 2.0, rot, lig, rec=rec, vdw_mask=None if "--no-prefilter" in extra else mask,
+            e_intra_const=e_intra, prec=gpu.PREC_FP64 if "--fp64" in extra else gpu.PREC_FP32)
+        assert f"candidates {want['n_candidates']}, scored {want['n_scored']}" in lines[0]
+        assert [int(r[2]) for r in rows] == list(want["top_frames"])
+        got_s = np.array([float(r[1]) for r in rows])
+        if "--fp64" in extra:
+            assert np.array_equal(got_s, want["top_scores"])
+            assert int(best[2]) == want["best_frame"] and float(best[1]) == want["best_score"]
+        else:
+            assert tol_ok(got_s, want["top_scores"]).all()
