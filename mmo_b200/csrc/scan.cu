@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <stdlib.h>
+#include <string.h>
 #include <memory>
 
 namespace mmo {
@@ -66,7 +67,7 @@ scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restric
 struct RotSet {
     DevBuf<double> rot;
     DevBuf<int32_t> perm;
-    uint64_t hash = 0;
+    std::vector<double> host;        // the set as it was handed over: compared bytewise on every call
     int n = -1;
     int epoch = -1;
 };
@@ -152,26 +153,17 @@ static void rotation_visit_order(int n_rot, const double *rot9, std::vector<int3
 
 // The rotation set of a run (lds builds it once, SO3.rotations, and scans every ligand with it) stays
 // resident on the device together with its visiting order; a call that passes the same rotations again
-// (same count, same content hash) skips the 72 n_rot bytes upload and the k-d sort.
-static uint64_t hash_words(const uint64_t *w, size_t n) {
-    uint64_t h0 = 1469598103934665603ull, h1 = h0 ^ 0x9e3779b97f4a7c15ull, h2 = h0 ^ 0xc2b2ae3d27d4eb4full, h3 = ~h0;
-    size_t k = 0;
-    for (; k + 4 <= n; k += 4) {        // four independent FNV-1a lanes: ~4 words per cycle
-        h0 = (h0 ^ w[k]) * 1099511628211ull; h1 = (h1 ^ w[k + 1]) * 1099511628211ull;
-        h2 = (h2 ^ w[k + 2]) * 1099511628211ull; h3 = (h3 ^ w[k + 3]) * 1099511628211ull;
-    }
-    for (; k < n; k++) h0 = (h0 ^ w[k]) * 1099511628211ull;
-    return h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7);
-}
+// (same count, same bytes: one memcmp against the host copy) skips the 72 n_rot bytes upload and the k-d sort.
 // leaked on purpose: must not run a destructor after the CUDA context / the allocator are gone
 static std::shared_ptr<RotSet> &g_rotset = *new std::shared_ptr<RotSet>();
 void scan_drop_caches() { g_rotset.reset(); }
 static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out) {
-    const uint64_t h = hash_words((const uint64_t *)rot9, (size_t)n_rot * 9);
-    if (g_rotset && g_rotset->n == n_rot && g_rotset->hash == h && g_rotset->epoch == rt().epoch) { out = g_rotset; return MMO_OK; }
+    if (g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch &&
+        memcmp(g_rotset->host.data(), rot9, (size_t)n_rot * 9 * sizeof(double)) == 0) { out = g_rotset; return MMO_OK; }
     g_rotset.reset();
     std::shared_ptr<RotSet> rs = std::make_shared<RotSet>();
-    rs->n = n_rot; rs->hash = h; rs->epoch = rt().epoch;
+    rs->n = n_rot; rs->epoch = rt().epoch;
+    rs->host.assign(rot9, rot9 + (size_t)n_rot * 9);
     std::vector<int32_t> perm;
     rotation_visit_order(n_rot, rot9, perm);
     MMO_TRY(rs->rot.upload(rot9, (size_t)n_rot * 9));
