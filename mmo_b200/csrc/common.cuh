@@ -63,6 +63,8 @@ int pool_alloc(void **p, size_t bytes);
 void pool_free(void *p);
 void pool_trim();
 void scan_drop_caches();   // scan.cu: device-resident rotation set
+void direct_drop_caches(); // direct_fp32.cu: tables, work counters, item-mode scratch
+void mc_drop_caches();     // mc.cu: UFF tables
 
 // simple owning device buffer
 template <typename T>

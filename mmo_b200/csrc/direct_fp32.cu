@@ -814,15 +814,21 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static DevBuf<double> g_xx, g_dij, g_vdwH;
-static DevBuf<unsigned long long> g_stats, g_work;
-static DevBuf<uint8_t> g_item_scratch;             // item mode scratch arena
+// Library-lifetime device buffers.  Allocated with `new` and never destroyed: no destructor may touch the allocator
+// or the CUDA context during static destruction at process exit; mmo_shutdown releases them (direct_drop_caches).
+static DevBuf<double> &g_xx = *new DevBuf<double>(), &g_dij = *new DevBuf<double>(), &g_vdwH = *new DevBuf<double>();
+static DevBuf<unsigned long long> &g_stats = *new DevBuf<unsigned long long>(), &g_work = *new DevBuf<unsigned long long>();
+static DevBuf<uint8_t> &g_item_scratch = *new DevBuf<uint8_t>();             // item mode scratch arena
 constexpr int64_t kItemModeMin = 32768;          // items (poses x ligand atoms) from which item mode pays
 constexpr int64_t kItemBatch = (int64_t)64 << 20;  // items per batch: ~47 B of scratch each (3 GB)
 constexpr int64_t kGlobalFp32MaxPairs = 120000;   // receptor x ligand atoms up to which GLOBAL stays on the fp32 path
 static int g_direct_mode = 0;                     // 0 auto, 1 pose kernel always, 2 item kernel for every pose list
 void direct_set_mode(int mode) { g_direct_mode = mode; }
 static double g_vdwH_for = -1.0;
+void direct_drop_caches() {
+    g_xx.release(); g_dij.release(); g_vdwH.release(); g_stats.release(); g_work.release(); g_item_scratch.release();
+    g_vdwH_for = -1.0;
+}
 
 static int ensure_fix_tables(double H) {
     if (!g_xx.p) {
@@ -854,6 +860,8 @@ static int ensure_fix_tables(double H) {
 
 static int set_fast_smem(size_t smem) {
     static size_t done = 0;
+    static int done_epoch = -1;
+    if (done_epoch != rt().epoch) { done = 0; done_epoch = rt().epoch; }      // function attributes are per context
     if (smem <= done) return MMO_OK;
     MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -866,6 +874,8 @@ static int set_fast_smem(size_t smem) {
 // ---- item mode launcher ------------------------------------------------------------------------------
 static int set_items_smem(size_t smem) {
     static size_t done = 0;
+    static int done_epoch = -1;
+    if (done_epoch != rt().epoch) { done = 0; done_epoch = rt().epoch; }
     if (smem <= done) return MMO_OK;
     MMO_CUDA(cudaFuncSetAttribute(direct_items_kernel<MMO_VARIANT_SHIFTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MMO_CUDA(cudaFuncSetAttribute(direct_items_kernel<MMO_VARIANT_SHIFTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

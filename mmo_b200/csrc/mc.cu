@@ -449,7 +449,9 @@ mc_chains_kernel(McArgs a) {
     }
 }
 
-static DevBuf<double> g_mc_xij, g_mc_dij;
+// library-lifetime tables: never destroyed at process exit, released by mmo_shutdown (mc_drop_caches)
+static DevBuf<double> &g_mc_xij = *new DevBuf<double>(), &g_mc_dij = *new DevBuf<double>();
+void mc_drop_caches() { g_mc_xij.release(); g_mc_dij.release(); }
 
 static int ensure_mc_tables() {
     if (g_mc_xij.p) return MMO_OK;

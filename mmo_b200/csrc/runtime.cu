@@ -234,6 +234,8 @@ int mmo_shutdown(void) {
     if (!R.ready) return MMO_OK;
     cudaStreamSynchronize(R.stream);
     scan_drop_caches();
+    direct_drop_caches();
+    mc_drop_caches();
     pool_trim();
     if (R.l2_scratch) cudaFree(R.l2_scratch);
     R.l2_scratch = nullptr;

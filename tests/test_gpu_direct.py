@@ -228,3 +228,30 @@ def test_fp32_conformer_screen_multi_tile(gpu, orc, direct_mode):
         assert (ratio <= 1.0).all(), f"worst ratio {ratio.max()} at E={want[ratio.argmax()]}"
         assert np.array_equal(gpu.Mol._score(rec, lig, variant, gpu.PREC_FP64, X[:40], Y[:40], Z[:40]), want[:40])
     assert (np.abs(want) < 50.0).sum() > 20 and (want > 1e3).sum() > 20      # surface poses and clashes alike
+
+
+def test_shutdown_and_reinit_rebuild_every_cache(gpu, orc, c2, c2_roi_rec):
+    """mmo_shutdown drops the library-lifetime device buffers (tables, work counters, scratch, rotation set);
+    a new mmo_init starts from nothing and gives the same numbers.  Runs last in this file on purpose: handles
+    created before the shutdown belong to the old pool and are not used afterwards."""
+    m = c2["lig"]
+    R, t = _poses(c2, 700, seed=31)
+
+    def run():
+        rec = gpu.Receptor.from_mol(c2_roi_rec)
+        lig = gpu.Ligand.from_mol(m, centered=True)
+        e32 = gpu.Mol.score_poses(rec, lig, R, t, prec=gpu.PREC_FP32)          # item kernel (33.6 k items)
+        gpu.lib().mmo_direct_set_mode(1)
+        e32p = gpu.Mol.score_poses(rec, lig, R[:64], t[:64], prec=gpu.PREC_FP32)  # pose kernel
+        gpu.lib().mmo_direct_set_mode(0)
+        rot = gpu.SO3.rotations(64)
+        sc = gpu.Lds.exhaustive_rigid_ligand_docking(5, (c2["roi"][0], c2["roi"][1], c2["roi"][2], 2.5), 2.0, rot, lig, rec=rec)
+        del rec, lig
+        return e32, e32p, sc["top_scores"], sc["top_frames"]
+
+    a = run()
+    assert gpu.lib().mmo_shutdown() == 0
+    gpu.init(0)
+    b = run()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
