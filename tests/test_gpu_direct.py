@@ -255,3 +255,43 @@ def test_shutdown_and_reinit_rebuild_every_cache(gpu, orc, c2, c2_roi_rec):
     b = run()
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_c5_large_conformer_screen_properties(gpu, orc):
+    """BASELINE configs[4] at one GPU's share of the 2-GPU run (500 000 explicit conformers of the 70-atom ligand
+    against the 10 000-atom receptor sphere), through size-independent properties: shard + top-k merge == whole,
+    order independence within the contract, far conformers exactly 0, and a sample against the strict fp64 kernel
+    and the oracle."""
+    from mmo_b200 import sharding
+    rec_m = workloads.synthetic_receptor(10000, "sphere", 34.0, seed=workloads.SEED + 1, origin=(60.0, 60.0, 60.0))
+    lig_m = workloads.c5_ligand()
+    rec = gpu.Receptor.from_mol(rec_m)
+    lig = gpu.Ligand.from_mol(lig_m, centered=False)
+    n, k = 500_000, 100
+    X, Y, Z = workloads.c5_conformers(lig_m, n, (60.0, 60.0, 60.0), radius=44.0, seed=77)    # pocket, surface and solvent
+    X[-1000:] += 200.0                                            # the last thousand: far beyond every cut-off
+    e = gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP32, X, Y, Z)
+    assert (e[-1000:] == 0.0).all() and np.isfinite(e).all()
+    # (1) two shards + merge == top-k of the whole list (ties to the smaller conformer id)
+    ids = np.arange(n, dtype=np.int64)
+    tops = []
+    for r in range(2):
+        a, c = sharding.shard_range(n, r, 2)
+        er = gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP32, X[a:a + c], Y[a:a + c], Z[a:a + c])
+        assert tol_ok(er, e[a:a + c]).all()                       # same conformers, other warp companions
+        o = np.lexsort((ids[a:a + c], er))[:k]
+        tops.append((er[o], ids[a:a + c][o]))
+    ms, mf = sharding.merge_lists(gpu.lib(), k, [t[0] for t in tops], [t[1] for t in tops])
+    whole = np.lexsort((ids, e))[:k]
+    assert tol_ok(ms, e[whole]).all()
+    assert len(set(mf.tolist()) ^ set(ids[whole].tolist())) <= 4   # only near-ties at the k-th place may differ
+    # (2) order independence: a shuffled subset gets the same energies within the contract
+    rng = np.random.default_rng(8)
+    sub = rng.choice(n - 1000, 60_000, replace=False)
+    es = gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP32, X[sub], Y[sub], Z[sub])
+    assert tol_ok(es, e[sub]).all()
+    # (3) the best conformers and a random sample against the strict kernel; part of the sample against the oracle
+    chk = np.concatenate([whole[:50], sub[:150]])
+    strict = gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP64, X[chk], Y[chk], Z[chk])
+    assert tol_ok(e[chk], strict).all()
+    assert np.array_equal(strict[:40], orc.ene_inter(rec_m, lig_m.q, lig_m.anum, X[chk[:40]], Y[chk[:40]], Z[chk[:40]], shifted=True))

@@ -124,3 +124,45 @@ def test_n3_masks_bit_identical(gpu, orc, c2):
     gotr = gpu.Lds.bitmask_ROI_only(c2["roi"], 1.0, dims)
     wantr = orc.bitmask_sphere(1.0, dims, c2["roi"][:3], c2["roi"][3] + 24.0)
     assert np.array_equal(gotr.bits, wantr)
+
+
+def test_c3_full_size_grid_and_lookup(gpu, orc):
+    """BASELINE configs[2] at full size: 22 maps of 81^3 voxels (0.375 A over 30 A) from a 5000-atom receptor,
+    then a million interpolated poses.  The oracle builds the same maps on a random 4000-voxel bitmask (seconds on
+    the CPU); the full device build must carry exactly those values there, and the lookup must reproduce the
+    oracle's trilinear sums bit for bit on a sample of the poses."""
+    rec_m = workloads.synthetic_receptor(5000, "cube", 60.0, seed=workloads.SEED)
+    rec_m.xs -= 15.0; rec_m.ys -= 15.0; rec_m.zs -= 15.0      # the 30 A box centred in the receptor starts at the origin
+    lig_m = pqrs.read_ligands_pqrs(os.path.join(workloads.GOLDEN, "ligdecs.pqrs"))[0]
+    ta, tq = pqrs.assign_ff_types([lig_m])
+    dims = gpu.Grid.from_box(0.375, 30.0, 30.0, 30.0)
+    assert tuple(dims) == (81, 81, 81) and len(ta) == 22
+    rec = gpu.Receptor.from_mol(rec_m)
+    g, maps = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta, tq)
+    nvox = 81 ** 3
+    rng = np.random.default_rng(5)
+    pick = np.sort(rng.choice(nvox, 4000, replace=False))
+    bits = np.zeros(nvox, np.uint8); bits[pick] = 1
+    mask = np.packbits(bits, bitorder="little")
+    want = orc.grid_build(rec_m, 0.375, dims, ta, tq, mask=mask)
+    assert np.array_equal(maps[:, pick], want[:, pick])
+    assert (maps[:, pick] != 0.0).all() and (maps == np.float32(1e5)).any()
+    # a million rigid poses whose atoms stay inside the grid; 300 of them through the oracle
+    lig = gpu.Ligand.from_mol(lig_m, centered=True)
+    rl = workloads.lig_radius((lig.xs, lig.ys, lig.zs))
+    n = 1_000_000
+    R = workloads.random_rotations(n, rng)
+    t = rng.uniform(rl + 0.4, 30.0 - rl - 0.4, (n, 3))
+    e = gpu.Mol.interp_poses(g, lig, R, t)
+    assert np.isfinite(e).all()
+    sel = rng.choice(n, 300, replace=False)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R[sel], t[sel])
+    assert np.array_equal(e[sel], orc.ene_inter_interp(0.375, dims, maps, lig_m.typ, X, Y, Z))
+    # atoms that sit exactly on lattice nodes read the stored value: single-atom "ligands" of three types
+    for typ in (0, 9, 21):
+        one = gpu.Ligand([0.0], [0.0], [0.0], [float(tq[typ])], [int(ta[typ])], typ=np.array([typ], np.int32))
+        nodes = rng.integers(1, 80, (64, 3))
+        tt = nodes * 0.375
+        idx = nodes[:, 0] + nodes[:, 1] * 81 + nodes[:, 2] * 81 * 81
+        got = gpu.Mol.interp_poses(g, one, np.tile(np.eye(3).reshape(9), (64, 1)), tt)
+        assert np.array_equal(got, maps[typ, idx].astype(np.float64))

@@ -208,3 +208,48 @@ def test_lds_ext_c_program_matches_the_python_path(gpu, orc, c2, c2_roi_rec, set
             assert int(best[2]) == want["best_frame"] and float(best[1]) == want["best_score"]
         else:
             assert tol_ok(got_s, want["top_scores"]).all()
+
+
+def test_c2_full_size_scan_properties(gpu, orc, c2, setup):
+    """BASELINE configs[1] at full size (100 000 rotations x 4139 in-ROI lattice points = 4.1e8 poses, ~7 s on a
+    B200), checked through size-independent properties: bookkeeping, ordering, and the three scorers against each
+    other -- the scan's pose kernel (fp32), the item kernel on an independent random sample of the same frames
+    (fp32) and the strict fp64 kernel (bit-identical to the oracle on small cases) on the reported top-k."""
+    rec, lig, mask, dims, e_intra = setup
+    n_rot, k = 100_000, 1000
+    rot = gpu.SO3.rotations(n_rot)
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(k, c2["roi"], 1.0, rot, lig, rec=rec, e_intra_const=e_intra)
+    ld = got["lattice_dims"]
+    assert tuple(ld) == (21, 21, 22)                                   # (c+r)-(c-r) is not exactly 2r: SURVEY 8a21
+    lo0 = [c2["roi"][d] - c2["roi"][3] for d in range(3)]
+    gi, gj, gk = np.meshgrid(np.arange(ld[0]), np.arange(ld[1]), np.arange(ld[2]), indexing="ij")
+    n_in = int((((lo0[0] + gi * 1.0 - c2["roi"][0]) ** 2 + (lo0[1] + gj * 1.0 - c2["roi"][1]) ** 2 +
+                 (lo0[2] + gk * 1.0 - c2["roi"][2]) ** 2) < c2["roi"][3] ** 2).sum())
+    assert 4100 < n_in < 4200                                          # ~ (4/3) pi 10^3
+    assert got["n_candidates"] == got["n_scored"] == n_in * n_rot
+    s, f = got["top_scores"], got["top_frames"]
+    assert len(s) == k and np.all(np.diff(s) >= 0) and len(set(f.tolist())) == k
+    assert got["best_frame"] == f[0] and got["best_score"] == s[0]
+
+    def poses_of(frames):
+        pt = frames // n_rot
+        ri = frames - pt * n_rot
+        kk = pt // (ld[0] * ld[1]); j = (pt - kk * ld[0] * ld[1]) // ld[0]; i = pt - kk * ld[0] * ld[1] - j * ld[0]
+        lo = [c2["roi"][d] - c2["roi"][3] for d in range(3)]
+        T = np.stack([lo[0] + i * 1.0, lo[1] + j * 1.0, lo[2] + kk * 1.0], axis=1)
+        inside = ((T - np.asarray(c2["roi"][:3])) ** 2).sum(1) < c2["roi"][3] ** 2
+        return rot[ri], T, inside
+
+    R, T, inside = poses_of(f)
+    assert inside.all()
+    strict = e_intra + gpu.Mol.score_poses(rec, lig, R, T, prec=gpu.PREC_FP64)
+    assert tol_ok(s, strict).all()                                     # every reported pose carries its true energy
+    # an independent sample of the loop nest through the other fp32 kernel: nothing better than the k-th was missed
+    rng = np.random.default_rng(99)
+    samp = np.unique(rng.integers(0, n_rot * ld[0] * ld[1] * ld[2], 400_000))
+    Rs, Ts, ins = poses_of(samp)
+    samp, Rs, Ts = samp[ins], Rs[ins], Ts[ins]
+    es = e_intra + gpu.Mol.score_poses(rec, lig, Rs, Ts, prec=gpu.PREC_FP32)
+    better = samp[es < s[-1] - 2e-4]
+    assert set(better.tolist()) <= set(f.tolist())
+    assert es.min() >= s[0] - 2e-4

@@ -129,3 +129,32 @@ def test_cuda_chain_on_the_direct_scorer_follows_the_oracle(gpu, orc, c2, c2_roi
         assert res[c]["n_accept_rigid"] == want["n_accept_rigid"] and res[c]["n_accept_conf"] == want["n_accept_conf"]
         assert res[c]["best_E"] == pytest.approx(want["best_E"], rel=1e-10, abs=1e-9)
         assert np.allclose(xyz[c], wxyz, rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_c4_full_size_chains_shard_and_match(gpu, orc, c2, c2_roi_rec, mc_setup):
+    """BASELINE configs[3] at full size: 4096 chains x 10 000 frames (interpolated E_inter + intra NB, --hard-ROI).
+    Chains are independent (one RNG per chain, lds.ml:1997-2000), so (1) an eighth of them run alone -- one GPU's
+    share when the job is sharded over 8 -- must reproduce its slice of the full launch bit for bit, and (2) any
+    chain must be the oracle's chain for its seed (three spot checks, 10 000 frames each on the CPU)."""
+    dims, mask, ta, tq, maps = mc_setup
+    g = gpu.G3D.upload(1.0, dims, maps)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    n, steps = 4096, 10_000
+    seeds = np.arange(n, dtype=np.uint64) + 20231017
+    R, t = workloads.random_poses_in_sphere(n, c2["roi"][:3], 3.0, seed=33)
+    res, _, _ = gpu.Lds.simulate_lig(g, lig, c2["roi"], steps, seeds, R, t)
+    assert all(r["frames_done"] == steps or r["too_long"] for r in res)
+    lo, hi = 5 * 512, 6 * 512                                   # rank 5 of 8
+    part, _, _ = gpu.Lds.simulate_lig(g, lig, c2["roi"], steps, seeds[lo:hi], R[lo:hi], t[lo:hi])
+    keys = ("best_E", "prev_E", "max_rot", "max_trans", "n_accept_rigid", "n_reject_rigid", "n_accept_conf",
+            "n_reject_conf", "n_ooroi", "n_ezero", "too_long", "frames_done")
+    for a, b in zip(part, res[lo:hi]):
+        assert all(a[k] == b[k] for k in keys)
+        assert np.array_equal(a["best_rot"], b["best_rot"]) and np.array_equal(a["best_pos"], b["best_pos"])
+    for c in (3, 2049, 4095):
+        want, _, _ = orc.mc_run(c2["lig"], lig.xs, lig.ys, lig.zs, c2["roi"], steps, int(seeds[c]), R[c], t[c], maps=maps,
+                                g_step=1.0, g_dims=dims)
+        assert all(res[c][k] == want[k] for k in keys), c
+    best = np.array([r["best_E"] for r in res])
+    assert np.isfinite(best).all() and best.min() < np.median(best)
