@@ -210,7 +210,11 @@ __device__ __forceinline__ double inter_energy(const McArgs &a, const double *x,
     return a.maps ? interp_energy(a, x, y, z, lane, terms) : direct_energy(a, x, y, z, lane, terms);
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// Two builds of the same kernel: MINB = 1 keeps every chain's state in registers (248: lowest latency per frame,
+// at most 8 chains per SM) for launches that do not fill the GPU anyway; MINB = 7 caps the registers at 72 (state
+// spills to local memory, slower per chain) so that 28 chains are resident per SM when there are thousands.
+template <int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 mc_chains_kernel(McArgs a) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -522,11 +526,14 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     const int nrb1 = std::max(lig->n_rbonds, 1);
     const size_t smem = (size_t)kWarpsPerBlock * (((9 * L + 2 * nrb1 + 1) & ~1) + 64) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
     MMO_REQUIRE(smem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds)", L, lig->n_rbonds);
-    MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)((n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock);
     {
         KernelScope ks(K_MC);
-        mc_chains_kernel<<<blocks, kWarpsPerBlock * 32, smem, R.stream>>>(a);
+        // more chains than the register-resident build can keep on the GPU (2 blocks per SM)?
+        if ((int64_t)blocks > 2LL * R.sm_count) mc_chains_kernel<7><<<blocks, kWarpsPerBlock * 32, smem, R.stream>>>(a);
+        else mc_chains_kernel<1><<<blocks, kWarpsPerBlock * 32, smem, R.stream>>>(a);
     }
     MMO_LAUNCH_CHECK();
     std::vector<double> hE(n_chains), hP(n_chains), hR((size_t)n_chains * 9), hT((size_t)n_chains * 3), hS((size_t)n_chains * 2);
