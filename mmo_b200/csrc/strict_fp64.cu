@@ -187,7 +187,7 @@ __global__ void strict_intra_kernel(int L, int n_pairs, const int32_t *__restric
 constexpr int kTG = 12;
 constexpr int kGridTile = 256;
 constexpr int kBrickX = 8, kBrickY = 4, kBrickZ = 4;
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 strict_grid_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
                    const double *__restrict__ pz, const double *__restrict__ pq,
                    const int32_t *__restrict__ pelt,
