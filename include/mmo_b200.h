@@ -137,6 +137,10 @@ int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const
 /* statistics of the last FP32 direct launch: pairs whose distance was evaluated, pairs inside the
  * 12 A cut-off, close-contact pairs re-evaluated in fp64 */
 int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64);
+/* The strict (bit-identical) kernels divide many numerators by one r through a shared correctly rounded reciprocal and
+ * two fused corrections; this runs that routine against the IEEE division on n pseudo-random (a, b) of the path's
+ * ranges, hard significands included, and reports how many quotients differ in any bit (must be 0). */
+int mmo_selftest_division(uint64_t seed, int64_t n, int64_t *mismatches);
 /* Which FP32 kernel scores a pose list (mmo_score_poses / mmo_score_coords; scans always take the pose kernel):
  * 0 = automatic (item kernel from 32 k pose-atoms on: incoherent lists are sorted by atom position first),
  * 1 = pose kernel (warp = 64 consecutive poses), 2 = item kernel (shifted variant only: MMO_VARIANT_GLOBAL has

@@ -146,6 +146,12 @@ int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t
     return MMO_OK;
 }
 
+int mmo_selftest_division(uint64_t seed, int64_t n, int64_t *mismatches) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(n > 0 && mismatches, "mmo_selftest_division: bad arguments");
+    return division_selftest(seed, n, mismatches);
+}
+
 int mmo_direct_set_mode(int mode) {
     MMO_REQUIRE(mode >= 0 && mode <= 2, "mmo_direct_set_mode: mode must be 0 (auto), 1 (pose kernel) or 2 (item kernel)");
     direct_set_mode(mode);

@@ -194,6 +194,7 @@ struct PoseSrc {
 // kernels' host entry points (defined in the .cu files)
 int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
                        int64_t n_poses, double *d_out, bool collect_stats);
+int division_selftest(uint64_t seed, int64_t n, int64_t *mismatches);   // strict_fp64.cu: div_by vs '/'
 void direct_set_mode(int mode);          // 0 auto, 1 pose-mode kernel always, 2 item-mode kernel for every pose list
 int launch_direct_fp64(const mmo_receptor *rec, const mmo_ligand *lig, int variant, const PoseSrc &src,
                        int64_t n_poses, double *d_out);

@@ -8,12 +8,41 @@ namespace mmo {
 // ---- scalars: FF.ml:5-20, math.ml:58-62 ------------------------------------------------------
 __device__ __forceinline__ double d_sq(double x) { return x * x; }
 __device__ __forceinline__ double d_pow6(double x) { double y = x * x; return (y * y) * y; }
-__device__ __forceinline__ double d_shift(double d) { return (d < 12.0) ? d_sq(1.0 - d_sq(d / 12.0)) : 0.0; }
 __device__ __forceinline__ double d_nzd(double x) { return (x < 0.01) ? 0.01 : x; }
 // V3.dist2 u v (V3.ml:23-28)
 __device__ __forceinline__ double d_dist2(double ux, double uy, double uz, double vx, double vy, double vz) {
     double dx = ux - vx, dy = uy - vy, dz = uz - vz;
     return dx * dx + dy * dy + dz * dz;
+}
+
+// ---- a / b for many a and one b, bit-identical to the IEEE division ------------------------------
+// rc = RN(1/b) once (one real division), then per quotient: q0 = RN(a rc) (within 1.5 ulp of a/b), r0 = a - q0 b
+// (exact in an fma), q1 = RN(q0 + r0 rc) (a faithful rounding of a/b), r1 = a - q1 b (exact), q2 = RN(q1 + r1 rc).
+// With y the correctly rounded reciprocal and q1 faithful, the last fused step rounds a/b correctly (Markstein 1990;
+// Cornea, Harrison, Tang 2002) unless b's significand is all ones: that case takes the plain division.  No
+// overflow, underflow or subnormals in this path's ranges (b in [0.01, 12], |a| < 1e6).
+struct Divisor { double b, rc; bool plain; };
+__device__ __forceinline__ Divisor make_divisor(double b) {
+    Divisor d;
+    d.b = b;
+    d.rc = 1.0 / b;
+    d.plain = ((__double2hiint(b) & 0x000fffff) == 0x000fffff) && (__double2loint(b) == (int)0xffffffff);
+    return d;
+}
+__device__ __forceinline__ double div_by(double a, const Divisor &d) {
+    if (d.plain) return a / d.b;
+    double q = a * d.rc;
+    double r = fma(-q, d.b, a);
+    q = fma(r, d.rc, q);
+    r = fma(-q, d.b, a);
+    return fma(r, d.rc, q);
+}
+
+// FF.shift_12A (FF.ml:17-20): (1 - (d/12)^2)^2 below the cut-off; d / 12.0 through the shared-reciprocal division
+__device__ __forceinline__ double d_shift(double d) {
+    Divisor by12;
+    by12.b = 12.0; by12.rc = 1.0 / 12.0; by12.plain = false;      // RN(1/12), folded at compile time
+    return (d < 12.0) ? d_sq(1.0 - d_sq(div_by(d, by12))) : 0.0;
 }
 
 // ---- trilinear interpolation (G3D.ml:97-157) ---------------------------------------------------

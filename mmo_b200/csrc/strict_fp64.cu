@@ -261,12 +261,13 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
                     const double r = d_nzd(d);
                     const double w = d_shift(r);
                     const int ei = se[c];
+                    const Divisor by_r = make_divisor(r);       // 2 * kTG quotients by the same r (bit-identical to '/')
 #pragma unroll
                     for (int l = 0; l < kTG; l++) {
                         if (l < nt) {
                             int t = te[l] + ei;       // UFF.vdW_xiDi (get_anum lig 0) prot_anum
-                            double p6 = d_pow6(c_xij[t] / r);
-                            se_acc[l] = se_acc[l] + w * ((q_i * tqv[l]) / r);
+                            double p6 = d_pow6(div_by(c_xij[t], by_r));
+                            se_acc[l] = se_acc[l] + w * div_by(q_i * tqv[l], by_r);
                             sv_acc[l] = sv_acc[l] + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
                         }
                     }
@@ -321,6 +322,26 @@ strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
         }
     }
     out[p] = res;
+}
+
+// ---- self-test of div_by against the IEEE division (tests/test_gpu_direct.py) --------------------------------
+__global__ void division_selftest_kernel(uint64_t seed, int64_t n, unsigned long long *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto mix = [](uint64_t z) { z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); };
+    const uint64_t u = mix(seed + 2 * (uint64_t)i), v = mix(seed + 2 * (uint64_t)i + 1);
+    // divisor: the path's range [0.01, 12.5) with random significands; every 16th one a significand of (nearly) all
+    // ones or all zeros, the known hard cases of reciprocal-based division
+    double b = __longlong_as_double((long long)((u >> 12) | 0x3ff0000000000000ull));          // [1, 2)
+    if ((i & 15) == 0) b = __longlong_as_double((long long)(0x3ff0000000000000ull | (0x000fffffffffffffull - (u & 7))));
+    if ((i & 15) == 1) b = __longlong_as_double((long long)(0x3ff0000000000000ull | (u & 7)));
+    b = ldexp(b, (int)(v % 11) - 7);                                                           // 2^-7 .. 2^3
+    double a = __longlong_as_double((long long)((v >> 12) | 0x3ff0000000000000ull));
+    a = ldexp(a, (int)((v >> 4) % 31) - 15);
+    if (v & 1) a = -a;
+    const Divisor d = make_divisor(b);
+    const double q = div_by(a, d), want = a / b;
+    if (__double_as_longlong(q) != __double_as_longlong(want)) atomicAdd(bad, 1ull);
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
@@ -422,4 +443,19 @@ int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, 
     return MMO_OK;
 }
 
+}  // namespace mmo
+
+namespace mmo {
+int division_selftest(uint64_t seed, int64_t n, int64_t *mismatches) {
+    DevBuf<unsigned long long> bad;
+    MMO_TRY(bad.alloc(1));
+    MMO_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), rt().stream));
+    division_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, rt().stream>>>(seed, n, bad.p);
+    MMO_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    MMO_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof h, cudaMemcpyDeviceToHost, rt().stream));
+    MMO_CUDA(cudaStreamSynchronize(rt().stream));
+    *mismatches = (int64_t)h;
+    return MMO_OK;
+}
 }  // namespace mmo

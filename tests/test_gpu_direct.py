@@ -295,3 +295,12 @@ def test_c5_large_conformer_screen_properties(gpu, orc):
     strict = gpu.Mol._score(rec, lig, gpu.VARIANT_SHIFTED, gpu.PREC_FP64, X[chk], Y[chk], Z[chk])
     assert tol_ok(e[chk], strict).all()
     assert np.array_equal(strict[:40], orc.ene_inter(rec_m, lig_m.q, lig_m.anum, X[chk[:40]], Y[chk[:40]], Z[chk[:40]], shifted=True))
+
+
+def test_shared_reciprocal_division_is_the_ieee_division(gpu):
+    """strict kernels: a / r for many a through RN(1/r) and two fused corrections must equal a / r in every bit"""
+    import ctypes as C
+    bad = C.c_int64(-1)
+    for seed in (1, 20231017):
+        assert gpu.lib().mmo_selftest_division(C.c_uint64(seed), C.c_int64(1 << 28), C.byref(bad)) == 0
+        assert bad.value == 0
