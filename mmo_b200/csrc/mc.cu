@@ -122,8 +122,9 @@ __device__ double intra_energy(const McArgs &a, const double *x, const double *y
             const int i = __ldg(a.pair_i + k), j = __ldg(a.pair_j + k);
             const double r = d_nzd(sqrt(d_dist2(x[i], y[i], z[i], x[j], y[j], z[j])));
             const int tt = __ldg(a.lelt + i) * kEltTab + __ldg(a.lelt + j);
-            const double p6 = d_pow6(__ldg(a.xij + tt) / r);
-            t.x = (__ldg(a.lq + i) * __ldg(a.lq + j)) / r;
+            const Divisor by_r = make_divisor(r);
+            const double p6 = d_pow6(div_by(__ldg(a.xij + tt), by_r));
+            t.x = div_by(__ldg(a.lq + i) * __ldg(a.lq + j), by_r);
             t.y = __ldg(a.dij + tt) * ((-2.0 * p6) + (p6 * p6));
         }
         __syncwarp();
@@ -191,8 +192,9 @@ __device__ double direct_energy(const McArgs &a, const double *x, const double *
                 const double r = d_nzd(sqrt(r2));
                 const double w = d_shift(r);
                 const int t = ei + __ldg(a.lelt + j);
-                const double p6 = d_pow6(__ldg(a.xij + t) / r);
-                se = se + w * ((q_i * __ldg(a.lq + j)) / r);
+                const Divisor by_r = make_divisor(r);
+                const double p6 = d_pow6(div_by(__ldg(a.xij + t), by_r));
+                se = se + w * div_by(q_i * __ldg(a.lq + j), by_r);
                 sv = sv + w * (__ldg(a.dij + t) * ((-2.0 * p6) + (p6 * p6)));
             }
         }

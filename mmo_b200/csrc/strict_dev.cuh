@@ -25,7 +25,7 @@ struct Divisor { double b, rc; bool plain; };
 __device__ __forceinline__ Divisor make_divisor(double b) {
     Divisor d;
     d.b = b;
-    d.rc = 1.0 / b;
+    d.rc = __drcp_rn(b);          // correctly rounded reciprocal
     d.plain = ((__double2hiint(b) & 0x000fffff) == 0x000fffff) && (__double2loint(b) == (int)0xffffffff);
     return d;
 }

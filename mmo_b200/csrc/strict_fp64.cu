@@ -92,16 +92,18 @@ __global__ void strict_direct_kernel(int P, const double *__restrict__ px, const
                     double r = d_nzd(sqrt(r2));
                     double w = d_shift(r);
                     int t = ei + se[j];
-                    double p6 = d_pow6(c_xij[t] / r);
-                    sum_elec = sum_elec + w * ((q_i * q_j) / r);
+                    const Divisor by_r = make_divisor(r);
+                    double p6 = d_pow6(div_by(c_xij[t], by_r));
+                    sum_elec = sum_elec + w * div_by(q_i * q_j, by_r);
                     sum_vdW = sum_vdW + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
                 }
             } else {
                 double q_j = sq[j];
                 double r = d_nzd(sqrt(r2));
                 int t = ei + se[j];
-                double p6 = d_pow6(c_xij[t] / r);
-                sum_elec = sum_elec + ((q_i * q_j) / r);
+                const Divisor by_r = make_divisor(r);
+                double p6 = d_pow6(div_by(c_xij[t], by_r));
+                sum_elec = sum_elec + div_by(q_i * q_j, by_r);
                 sum_vdW = sum_vdW + (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
             }
         }
@@ -136,8 +138,9 @@ __global__ void strict_components_kernel(int P, const double *__restrict__ px, c
                 double r = d_nzd(d);
                 double w = d_shift(r);
                 int t = ej + __ldg(pelt + i);
-                double p6 = d_pow6(c_xij[t] / r);
-                sum_elec = sum_elec + w * ((__ldg(pq + i) * q_j) / r);
+                const Divisor by_r = make_divisor(r);
+                double p6 = d_pow6(div_by(c_xij[t], by_r));
+                sum_elec = sum_elec + w * div_by(__ldg(pq + i) * q_j, by_r);
                 sum_vdW = sum_vdW + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
             }
         }
@@ -170,8 +173,9 @@ __global__ void strict_intra_kernel(int L, int n_pairs, const int32_t *__restric
         double r = d_nzd(sqrt(d_dist2(sx[i * nthr + tid], sy[i * nthr + tid], sz[i * nthr + tid],
                                       sx[j * nthr + tid], sy[j * nthr + tid], sz[j * nthr + tid])));
         int t = __ldg(lelt + i) * kEltTab + __ldg(lelt + j);
-        double p6 = d_pow6(c_xij[t] / r);
-        sum_elec = sum_elec + (__ldg(lq + i) * __ldg(lq + j)) / r;
+        const Divisor by_r = make_divisor(r);
+        double p6 = d_pow6(div_by(c_xij[t], by_r));
+        sum_elec = sum_elec + div_by(__ldg(lq + i) * __ldg(lq + j), by_r);
         sum_vdW = sum_vdW + c_dij[t] * ((-2.0 * p6) + (p6 * p6));
     }
     out[p] = (kElecWeight * sum_elec) + sum_vdW;
