@@ -3,12 +3,13 @@
 // Replaces the inner loops of Mol.ene_inter_UFF_shifted_brute / _global_brute (src/mol.ml:796-849)
 // for many poses per launch.  Layout of the computation (no tensor cores: non-linear pair sum):
 //
-//   thread  = two poses (p and p + 32), warp = 64 consecutive poses, block = 512 poses; the receptor
+//   thread  = two poses (p and p + 32), warp = 64 consecutive poses, one persistent block of 16 warps per SM that
+//             draws (64 poses, chunk split) work units from an atomic counter; the receptor
 //             (k-d groups of 16 atoms, fp32, relative to the receptor origin) is staged in shared
 //             memory, the whole ROI receptor at once when it fits
 //   cull    = per (warp, ligand atom): centre c and radius rho of the atom's positions over the warp's 64
 //             poses (CREDUX); level 1: lane g tests the box of group g against the sphere (c, 12 + rho),
-//             one ballot per 32 groups; level 2: the atoms of two near groups per step are tested one
+//             one ballot per 32 groups; level 2: the atoms of four near groups per step are tested two
 //             per lane, and the survivors' centred coordinates x' = x - c, |x'|^2, charge product and
 //             vdW products are compacted into a per-warp structure-of-arrays list.  Shifted variant
 //             only: a culled pair has weight exactly 0 in the reference (mol.ml:836)
@@ -1032,14 +1033,14 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
         }
         return MMO_OK;
     }
-    // receptor tile: everything when it fits (<= 128 groups = 2048 atoms), so that 2 blocks stay resident per SM
+    // receptor tile: everything when it fits (<= 128 groups = 2048 atoms); larger receptors take one launch per tile
     const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
     const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
                         16 * sizeof(float2) + (size_t)3 * LJ * PPB * sizeof(float) +
                         (size_t)(TPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob +
                         (size_t)(TPB / 32) * NEAR_CAP + 16;
     // work units = (64 poses, chunk split): at least ~20 per resident warp, so that the dynamic hand-out
-    // balances the warps to a few percent; persistent grid of 2 blocks per SM (fewer for small batches)
+    // balances the warps to a few percent; persistent grid of one block per SM (fewer for small batches)
     const int n_chunks = lig->n_fast / LJ;
     const int64_t n_groups = (n_poses + 32 * PPT - 1) / (32 * PPT);
     const int64_t resident_warps = (int64_t)kBlocksPerSM * R.sm_count * (TPB / 32);
