@@ -334,6 +334,19 @@ int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum
 int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path);
 /* molecule k as a device-resident ligand handle; centered != 0 applies Mol.translate_to lig V3.origin (lds.ml:44-52) */
 int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand **out);
+/* Mol2.output_one of Mol.update_mol2 mol2 m (src/mol2.ml:326-343, src/mol.ml:544-552): molecule k (read from a
+ * mol2 file) written n_copies times, copy c with the coordinates xs/ys/zs[c * n_atoms ..] (NULL = the file's own);
+ * append != 0 adds to an existing file */
+int mmo_molfile_write_mol2(const mmo_molfile *f, int32_t k, int32_t n_copies, const double *xs, const double *ys,
+                           const double *zs, const char *path, int append);
+/* host-only bodies of the two pose-feed tools (no GPU, no ligand handle needed):
+ * lig_rot_sample (src/lig_rot_sample.ml:23-45): Mol.center_rotate_translate_copy mol rot (Mol.get_center mol) for n
+ * rotations, out arrays n x n_atoms; place_ligand (src/place_ligand.ml:36-59): Mol.center, then Optim.apply_config
+ * (src/optim.ml:64-80) with config = x y z alpha beta gamma [one angle per rotatable bond] */
+int mmo_molfile_rotated_copies(const mmo_molfile *f, int32_t k, int32_t n, const double *rot9, double *out_xs,
+                               double *out_ys, double *out_zs);
+int mmo_molfile_apply_config(const mmo_molfile *f, int32_t k, const double *config, int32_t n_config, double *out_xs,
+                             double *out_ys, double *out_zs, int32_t *too_long);
 int mmo_molfile_destroy(mmo_molfile *f);
 
 #ifdef __cplusplus

@@ -574,6 +574,36 @@ class MolFile:
     def write_pqrs(self, path):
         _ck(lib().mmo_molfile_write_pqrs(self.h, os.fsencode(path)))
 
+    def write_mol2(self, path, k=0, xs=None, ys=None, zs=None, append=False):
+        """Mol2.output_one of Mol.update_mol2 (mol2.ml:326-343, mol.ml:544-552): molecule k with the coordinates of
+        every row of xs/ys/zs ([n_copies][n_atoms]); without coordinates the file's own, once"""
+        if xs is None:
+            n, px, py, pz = 1, None, None, None
+        else:
+            xs, ys, zs = (np.ascontiguousarray(np.atleast_2d(a), np.float64) for a in (xs, ys, zs))
+            n, px, py, pz = xs.shape[0], xs.ctypes.data_as(_dp), ys.ctypes.data_as(_dp), zs.ctypes.data_as(_dp)
+        _ck(lib().mmo_molfile_write_mol2(self.h, C.c_int32(k), C.c_int32(n), px, py, pz, os.fsencode(path),
+                                         C.c_int(1 if append else 0)))
+
+    def rotated_copies(self, k, rot9):
+        """lig_rot_sample's body on the host (lig_rot_sample.ml:23-45): [n][n_atoms] coordinates"""
+        rot = np.ascontiguousarray(rot9, np.float64).reshape(-1, 9)
+        n, L = rot.shape[0], self.mol(k).n
+        X, Y, Z = (np.empty((n, L)) for _ in range(3))
+        _ck(lib().mmo_molfile_rotated_copies(self.h, C.c_int32(k), C.c_int32(n), rot.ctypes.data_as(_dp),
+                                             X.ctypes.data_as(_dp), Y.ctypes.data_as(_dp), Z.ctypes.data_as(_dp)))
+        return X, Y, Z
+
+    def apply_config(self, k, config):
+        """place_ligand's body on the host (place_ligand.ml:36-59): Mol.center, then Optim.apply_config"""
+        cfg = np.ascontiguousarray(config, np.float64)
+        L = self.mol(k).n
+        x, y, z = (np.empty(L) for _ in range(3))
+        tl = C.c_int32()
+        _ck(lib().mmo_molfile_apply_config(self.h, C.c_int32(k), cfg.ctypes.data_as(_dp), C.c_int32(len(cfg)),
+                                           x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), z.ctypes.data_as(_dp), C.byref(tl)))
+        return x, y, z, bool(tl.value)
+
     def ligand(self, k, centered=True):
         _need_init()
         m = self.mol(k)

@@ -112,6 +112,19 @@ constexpr float kFarAway = 1e6f;  // coordinate of padding atoms: beyond every c
 
 struct Aabb { float lo[3], hi[3]; };
 
+// host pose builders shared by the handle-based entry points (host_math.cu) and the file-based ones (molfile.cu)
+struct HostLig {
+    int n;
+    const double *x, *y, *z;
+    int n_rbonds;
+    const int32_t *rb_left, *rb_right, *rg_off, *rg_idx;
+};
+double favg_host(const double *a, int n);          // Batteries A.favg as restated in the oracle (Kahan sum / n)
+int apply_config_host(const HostLig &lig, const double *config, int32_t n_config, double *out_xs, double *out_ys,
+                      double *out_zs, int32_t *too_long);
+void rotated_copies_host(const HostLig &lig, const double center[3], int32_t n, const double *rot9, double *out_xs,
+                         double *out_ys, double *out_zs);
+
 }  // namespace mmo
 
 // ---- opaque handles -----------------------------------------------------------------------------------

@@ -96,34 +96,39 @@ static double favg(const std::vector<double> &a) {
 
 }  // namespace mmo
 
-extern "C" {
+namespace mmo {
+
+double favg_host(const double *a, int n) {
+    double sum = 0.0, c = 0.0;
+    for (int i = 0; i < n; i++) { double y = a[i] - c; double t = sum + y; c = (t - sum) - y; sum = t; }
+    return sum / (double)n;
+}
 
 // Optim.apply_config centered_lig conf (src/optim.ml:64-80), the body of the place_ligand tool
 // (src/place_ligand.ml:55-59): rotate every rotatable bond by conf[6+b] (Mol.rotate_bond, src/mol.ml:610-631),
 // check the elongation (Mol.check_elongation_exn lig 12.0, src/mol.ml:576-591), then
 // Mol.rotate_then_translate_copy lig (Rot.r_xyz a b g) (x, y, z) (src/mol.ml:669-672).  Host code, libm.
-int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_config, double *out_xs, double *out_ys,
-                     double *out_zs, int32_t *too_long) {
-    MMO_REQUIRE(lig && config && out_xs && out_ys && out_zs, "mmo_apply_config: null argument");
-    MMO_REQUIRE(n_config == 6 || n_config == 6 + lig->n_rbonds, "mmo_apply_config: %d values for a ligand with %d rotatable bonds",
-                n_config, lig->n_rbonds);
-    const int L = lig->n;
-    std::vector<double> x(lig->hx), y(lig->hy), z(lig->hz);
+int apply_config_host(const HostLig &lig, const double *config, int32_t n_config, double *out_xs, double *out_ys,
+                      double *out_zs, int32_t *too_long) {
+    MMO_REQUIRE(n_config == 6 || n_config == 6 + lig.n_rbonds, "mmo_apply_config: %d values for a ligand with %d rotatable bonds",
+                n_config, lig.n_rbonds);
+    const int L = lig.n;
+    std::vector<double> x(lig.x, lig.x + L), y(lig.y, lig.y + L), z(lig.z, lig.z + L);
     double cen[3] = {0.0, 0.0, 0.0};       // centered_lig.center
     for (int b = 0; b + 6 < n_config; b++) {
-        const int left = lig->rb_left[b], right = lig->rb_right[b];
+        const int left = lig.rb_left[b], right = lig.rb_right[b];
         const double cx = x[right], cy = y[right], cz = z[right];
         const double ax = cx - x[left], ay = cy - y[left], az = cz - z[left];
         const double mag = sqrt(ax * ax + ay * ay + az * az);
         double rot[9];
-        mmo::rot_of_axis_angle(ax / mag, ay / mag, az / mag, config[6 + b], rot);
-        for (int g = lig->rg_off[b]; g < lig->rg_off[b + 1]; g++) {
-            const int i = lig->rg_idx[g];
+        rot_of_axis_angle(ax / mag, ay / mag, az / mag, config[6 + b], rot);
+        for (int g = lig.rg_off[b]; g < lig.rg_off[b + 1]; g++) {
+            const int i = lig.rg_idx[g];
             double o[3];
-            mmo::rot_apply(rot, x[i] - cx, y[i] - cy, z[i] - cz, o);
+            rot_apply(rot, x[i] - cx, y[i] - cy, z[i] - cz, o);
             x[i] = o[0] + cx; y[i] = o[1] + cy; z[i] = o[2] + cz;
         }
-        cen[0] = mmo::favg(x); cen[1] = mmo::favg(y); cen[2] = mmo::favg(z);     // update_center
+        cen[0] = favg(x); cen[1] = favg(y); cen[2] = favg(z);     // update_center
     }
     double maxi = 0.0;
     for (int i = 0; i < L; i++) {
@@ -132,13 +137,39 @@ int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_conf
     }
     if (too_long) *too_long = maxi > 12.0 ? 1 : 0;                                 // Mol.Too_long
     double rot[9];
-    mmo::rot_r_xyz(config[3], config[4], config[5], rot);
+    rot_r_xyz(config[3], config[4], config[5], rot);
     for (int i = 0; i < L; i++) {
         double o[3];
-        mmo::rot_apply(rot, x[i], y[i], z[i], o);
+        rot_apply(rot, x[i], y[i], z[i], o);
         out_xs[i] = o[0] + config[0]; out_ys[i] = o[1] + config[1]; out_zs[i] = o[2] + config[2];
     }
     return MMO_OK;
+}
+
+void rotated_copies_host(const HostLig &lig, const double center[3], int32_t n, const double *rot9,
+                         double *out_xs, double *out_ys, double *out_zs) {
+    const int L = lig.n;
+    const double nx = -center[0], ny = -center[1], nz = -center[2];      // Mol.center: translate_by (V3.neg mean)
+    for (int r = 0; r < n; r++)
+        for (int i = 0; i < L; i++) {
+            double o[3];
+            rot_apply(rot9 + 9 * (size_t)r, lig.x[i] + nx, lig.y[i] + ny, lig.z[i] + nz, o);
+            out_xs[(size_t)r * L + i] = o[0] + center[0];
+            out_ys[(size_t)r * L + i] = o[1] + center[1];
+            out_zs[(size_t)r * L + i] = o[2] + center[2];
+        }
+}
+
+}  // namespace mmo
+
+extern "C" {
+
+int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_config, double *out_xs, double *out_ys,
+                     double *out_zs, int32_t *too_long) {
+    MMO_REQUIRE(lig && config && out_xs && out_ys && out_zs, "mmo_apply_config: null argument");
+    const mmo::HostLig h = {lig->n, lig->hx.data(), lig->hy.data(), lig->hz.data(), lig->n_rbonds, lig->rb_left.data(),
+                            lig->rb_right.data(), lig->rg_off.data(), lig->rg_idx.data()};
+    return mmo::apply_config_host(h, config, n_config, out_xs, out_ys, out_zs, too_long);
 }
 
 // lig_rot_sample (src/lig_rot_sample.ml:23-45): n SO3-rotated copies of the ligand about its own centre:
@@ -146,16 +177,8 @@ int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_conf
 int mmo_rotated_copies(const mmo_ligand *lig, const double center[3], int32_t n, const double *rot9,
                        double *out_xs, double *out_ys, double *out_zs) {
     MMO_REQUIRE(lig && center && n >= 0 && (n == 0 || (rot9 && out_xs && out_ys && out_zs)), "mmo_rotated_copies: bad arguments");
-    const int L = lig->n;
-    const double nx = -center[0], ny = -center[1], nz = -center[2];      // Mol.center: translate_by (V3.neg mean)
-    for (int r = 0; r < n; r++)
-        for (int i = 0; i < L; i++) {
-            double o[3];
-            mmo::rot_apply(rot9 + 9 * (size_t)r, lig->hx[i] + nx, lig->hy[i] + ny, lig->hz[i] + nz, o);
-            out_xs[(size_t)r * L + i] = o[0] + center[0];
-            out_ys[(size_t)r * L + i] = o[1] + center[1];
-            out_zs[(size_t)r * L + i] = o[2] + center[2];
-        }
+    const mmo::HostLig h = {lig->n, lig->hx.data(), lig->hy.data(), lig->hz.data(), 0, nullptr, nullptr, nullptr, nullptr};
+    mmo::rotated_copies_host(h, center, n, rot9, out_xs, out_ys, out_zs);
     return MMO_OK;
 }
 

@@ -30,6 +30,10 @@ struct Molecule {
     std::vector<int32_t> rb_left, rb_right;      // fixed -> movable (pqrs.ml:49-56)
     std::vector<std::vector<uint8_t>> rb_flags;  // movable side, axis tip included (the pqrs text)
     std::vector<int32_t> typ;                    // FF types, assigned over the whole file
+    // mol2 text kept for the writer (mol2.ml:40-49, 71-74): atom names / types and bonds, lone pairs removed
+    std::vector<std::string> aname, atype;
+    std::vector<int32_t> b_src, b_dst;
+    std::vector<std::string> b_typ;
     int n() const { return (int)x.size(); }
 };
 
@@ -205,6 +209,7 @@ int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) {
                 keep[i] = m.n();
                 m.x.push_back(parse_dbl(t[2], ok)); m.y.push_back(parse_dbl(t[3], ok)); m.z.push_back(parse_dbl(t[4], ok));
                 m.q.push_back(parse_dbl(t[8], ok)); m.r.push_back(e->radius); m.anum.push_back(e->anum);
+                m.aname.push_back(t[1]); m.atype.push_back(t[5]);
             }
         }
         size_t b0 = a0 + 1 + (size_t)n_atoms;
@@ -225,6 +230,7 @@ int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) {
             else { set_error("mmo_molfile_read_mol2: bond type %s in %s", t[3].c_str(), m.name.c_str()); ok = false; break; }
             if (keep[s] < 0 || keep[d] < 0) continue;
             bs.push_back(keep[s]); bd.push_back(keep[d]); bo.push_back(order);
+            m.b_src.push_back(keep[s]); m.b_dst.push_back(keep[d]); m.b_typ.push_back(t[3]);
         }
         if (ok && m.n() > 0 && analyse_graph(m, bs, bd, bo)) f->mols.push_back(std::move(m));
         else f->n_skipped++;
@@ -423,6 +429,85 @@ int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand
     return mmo_ligand_create(n, x.data(), y.data(), z.data(), m.q.data(), m.r.data(), m.anum.data(), m.typ.data(),
                              m.dists.empty() ? nullptr : m.dists.data(), nrb, m.rb_left.data(), m.rb_right.data(),
                              off.data(), idx.data(), out);
+}
+
+// Mol2.output_one (src/mol2.ml:326-343, line formats 184-190, 209-210) of Mol.update_mol2 mol2 m (src/mol.ml:544-552):
+// molecule k written n_copies times with its coordinates replaced by copy c of xs/ys/zs ([n_copies][n_atoms]; NULL =
+// the file's own).  What lig_rot_sample (one block per rotation) and place_ligand (one block) emit.
+int mmo_molfile_write_mol2(const mmo_molfile *f, int32_t k, int32_t n_copies, const double *xs, const double *ys,
+                           const double *zs, const char *path, int append) {
+    MMO_REQUIRE(f && path && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_write_mol2: molecule index out of range");
+    const Molecule &m = f->mols[k];
+    const int n = m.n();
+    MMO_REQUIRE((int)m.aname.size() == n, "mmo_molfile_write_mol2: molecule %s was not read from a mol2 file", m.name.c_str());
+    MMO_REQUIRE(n_copies >= 0 && ((xs && ys && zs) || (!xs && !ys && !zs)), "mmo_molfile_write_mol2: bad arguments");
+    FILE *o = fopen(path, append ? "a" : "w");
+    MMO_REQUIRE(o != nullptr, "mmo_molfile_write_mol2: cannot create %s", path);
+    for (int c = 0; c < n_copies; c++) {
+        fprintf(o, "@<TRIPOS>MOLECULE\n%s\n%5d%6d%6d%6d%6d\nSMALL\nUSER_CHARGES\n\n@<TRIPOS>ATOM\n", m.name.c_str(), n,
+                (int)m.b_src.size(), 0, 0, 0);
+        for (int i = 0; i < n; i++) {
+            const double x = xs ? xs[(size_t)c * n + i] : m.x[i], y = ys ? ys[(size_t)c * n + i] : m.y[i];
+            const double z = zs ? zs[(size_t)c * n + i] : m.z[i];
+            fprintf(o, "%7d %-8s%10.4f%10.4f%10.4f %-8s  1 <0>     %10.4f\n", i + 1, m.aname[i].c_str(), x, y, z,
+                    m.atype[i].c_str(), m.q[i]);
+        }
+        fputs("@<TRIPOS>BOND\n", o);
+        for (size_t b = 0; b < m.b_src.size(); b++)
+            fprintf(o, "%6d%5d%5d %s\n", (int)b + 1, m.b_src[b] + 1, m.b_dst[b] + 1, m.b_typ[b].c_str());
+    }
+    const bool bad = ferror(o) != 0;
+    MMO_REQUIRE(fclose(o) == 0 && !bad, "mmo_molfile_write_mol2: write error on %s", path);
+    return MMO_OK;
+}
+
+namespace {
+struct HostView {
+    std::vector<int32_t> off, idx;
+    mmo::HostLig h;
+};
+int host_view(const mmo_molfile *f, int32_t k, const std::vector<double> &x, const std::vector<double> &y,
+              const std::vector<double> &z, HostView &v) {
+    const Molecule &m = f->mols[k];
+    const int nrb = (int)m.rb_left.size();
+    int32_t tot = 0;
+    MMO_TRY(mmo_molfile_shape(f, k, nullptr, nullptr, &tot, nullptr, 0));
+    v.off.resize(nrb + 1);
+    v.idx.resize(std::max(1, tot));
+    MMO_TRY(mmo_molfile_get(f, k, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            v.off.data(), v.idx.data()));
+    v.h = {m.n(), x.data(), y.data(), z.data(), nrb, m.rb_left.data(), m.rb_right.data(), v.off.data(), v.idx.data()};
+    return MMO_OK;
+}
+}  // namespace
+
+// the body of the lig_rot_sample tool (src/lig_rot_sample.ml:23-45) on molecule k of the file, host only:
+// Mol.center_rotate_translate_copy mol rot (Mol.get_center mol) for every rotation
+int mmo_molfile_rotated_copies(const mmo_molfile *f, int32_t k, int32_t n, const double *rot9, double *out_xs,
+                               double *out_ys, double *out_zs) {
+    MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_rotated_copies: molecule index out of range");
+    MMO_REQUIRE(n >= 0 && (n == 0 || (rot9 && out_xs && out_ys && out_zs)), "mmo_molfile_rotated_copies: bad arguments");
+    const Molecule &m = f->mols[k];
+    const double center[3] = {favg_host(m.x.data(), m.n()), favg_host(m.y.data(), m.n()), favg_host(m.z.data(), m.n())};
+    const mmo::HostLig h = {m.n(), m.x.data(), m.y.data(), m.z.data(), 0, nullptr, nullptr, nullptr, nullptr};
+    rotated_copies_host(h, center, n, rot9, out_xs, out_ys, out_zs);
+    return MMO_OK;
+}
+
+// the body of the place_ligand tool (src/place_ligand.ml:36-59) on molecule k, host only: Mol.center, then
+// Optim.apply_config centered_lig (x y z a b g [rbond angles]) (src/optim.ml:64-80)
+int mmo_molfile_apply_config(const mmo_molfile *f, int32_t k, const double *config, int32_t n_config, double *out_xs,
+                             double *out_ys, double *out_zs, int32_t *too_long) {
+    MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_apply_config: molecule index out of range");
+    MMO_REQUIRE(config && out_xs && out_ys && out_zs, "mmo_molfile_apply_config: null argument");
+    const Molecule &m = f->mols[k];
+    const int n = m.n();
+    const double cx = favg_host(m.x.data(), n), cy = favg_host(m.y.data(), n), cz = favg_host(m.z.data(), n);
+    std::vector<double> x(n), y(n), z(n);
+    for (int i = 0; i < n; i++) { x[i] = m.x[i] + (0.0 - cx); y[i] = m.y[i] + (0.0 - cy); z[i] = m.z[i] + (0.0 - cz); }
+    HostView v;
+    MMO_TRY(host_view(f, k, x, y, z, v));
+    return apply_config_host(v.h, config, n_config, out_xs, out_ys, out_zs, too_long);
 }
 
 int mmo_molfile_destroy(mmo_molfile *f) {
