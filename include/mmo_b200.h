@@ -204,6 +204,27 @@ int mmo_mask_destroy(mmo_mask *mask);
 int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses,
                     const double *rot9, const double *trans3, uint8_t *out_flags);
 
+/* ---------------------------------------------------------------- N4: desolvation sums ---- */
+/* Majeux, Scarsi and Caflisch (PROTEINS 2001) eq. (2), the rescoring terms next to the pair path.
+ * Lds.protein_desolv roi grid prot_bst prot_solvent_shell prot (src/lds.ml:204-236): for every voxel of the protein's
+ * first solvent shell (mmo_mask_first_solvent_shell of the receptor) inside the ROI, Const.desolvation * (voxel_vol *
+ * sum over protein atoms within 12 A of (q_j / d2)^2); 0.0 elsewhere.  out_contribs (host, one double per voxel, index
+ * i + j*x_dim + k*xy_dim) and out (device-resident handle; prot_shell must outlive it) may each be NULL.
+ * Neighbour order inside BST.neighbors is unpinned (library not vendored): atoms are added in index order. */
+typedef struct mmo_desolv mmo_desolv;
+int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, const double roi_c[3], double roi_r,
+                       double *out_contribs, mmo_desolv **out);
+/* Lds.desolvation_penalty grid prot_desolv_contribs prot_solvent_shell _prot lig (src/lds.ml:239-267) for n_poses
+ * poses of the ligand (created with radii): the ligand's own first solvent shell (src/lds.ml:172-184) ANDed with the
+ * protein's; out_prot[p] = sum of the desolvated voxels' protein contributions, out_lig[p] = Const.desolvation *
+ * (voxel_vol * sum over those voxels and the ligand atoms with d2 < 144 of (q_j / d2)^2), both summed in voxel index
+ * then atom order (Bitv.iteri_true): bit-identical to the reference's doubles */
+int mmo_desolv_penalty_coords(const mmo_desolv *d, const mmo_ligand *lig, int64_t n_poses, const double *xs,
+                              const double *ys, const double *zs, double *out_prot, double *out_lig);
+int mmo_desolv_penalty_poses(const mmo_desolv *d, const mmo_ligand *lig, int64_t n_poses, const double *rot9,
+                             const double *trans3, double *out_prot, double *out_lig);
+int mmo_desolv_destroy(mmo_desolv *d);
+
 /* ---------------------------------------------------------------- rotations (host, libm) -- */
 /* SO3.rotations n (src/SO3.ml:18-39 + src/quat.ml:32-36 + src/rot.ml:136-146): n row-major 3x3 */
 int mmo_so3_rotations(int32_t n, double *rot9);

@@ -228,6 +228,18 @@ class VdwMask:
             self.h = None
 
 
+class Desolv:
+    """Lds.protein_desolv's per-voxel contributions, device resident (N4); keeps the shell mask alive"""
+
+    def __init__(self, handle, shell):
+        self.h, self.shell = handle, shell
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mmo_desolv_destroy(self.h)
+            self.h = None
+
+
 # ------------------------------------------------------------------------------------------------
 class Mol:
     """src/mol.ml energy functions, batched: coordinates are arrays [n_poses, L]."""
@@ -422,6 +434,40 @@ class Lds:
         """src/lds.ml:269-305; roi = (cx, cy, cz, r)"""
         c = (C.c_double * 3)(*roi[:3])
         return Lds._mask_call(lib().mmo_mask_roi_only, dims, step, c, C.c_double(roi[3]))
+
+    @staticmethod
+    def protein_desolv(roi, rec, prot_solvent_shell, want_host=True):
+        """src/lds.ml:204-236; roi = (cx, cy, cz, r), prot_solvent_shell = Lds.first_solvent_shell of the receptor.
+        Returns (Desolv handle, per-voxel contributions or None)."""
+        _need_init()
+        m = prot_solvent_shell
+        nvox = m.dims[0] * m.dims[1] * m.dims[2]
+        host = np.empty(nvox) if want_host else None
+        h = _vp()
+        c = (C.c_double * 3)(*roi[:3])
+        _ck(lib().mmo_desolv_protein(rec.h, m.h, c, C.c_double(roi[3]),
+                                     host.ctypes.data_as(_dp) if want_host else C.cast(None, _dp), C.byref(h)))
+        return Desolv(h, m), host
+
+    @staticmethod
+    def desolvation_penalty(desolv, lig, xs=None, ys=None, zs=None, rot9=None, trans3=None):
+        """src/lds.ml:239-267 for many poses (explicit coordinates [n, L] or rot9/trans3): (prot[n], lig[n])"""
+        if xs is not None:
+            xs, ys, zs = (np.atleast_2d(np.asarray(a, np.float64)) for a in (xs, ys, zs))
+            n = xs.shape[0]
+            assert xs.shape == (n, lig.n) == ys.shape == zs.shape
+            op, ol = np.empty(n), np.empty(n)
+            (a, pa), (b, pb), (c, pc) = _d(xs), _d(ys), _d(zs)
+            _ck(lib().mmo_desolv_penalty_coords(desolv.h, lig.h, C.c_int64(n), pa, pb, pc, op.ctypes.data_as(_dp),
+                                                ol.ctypes.data_as(_dp)))
+            return op, ol
+        rot9 = np.ascontiguousarray(rot9, np.float64).reshape(-1, 9)
+        trans3 = np.ascontiguousarray(trans3, np.float64).reshape(-1, 3)
+        n = rot9.shape[0]
+        op, ol = np.empty(n), np.empty(n)
+        _ck(lib().mmo_desolv_penalty_poses(desolv.h, lig.h, C.c_int64(n), rot9.ctypes.data_as(_dp), trans3.ctypes.data_as(_dp),
+                                           op.ctypes.data_as(_dp), ol.ctypes.data_as(_dp)))
+        return op, ol
 
     @staticmethod
     def exhaustive_rigid_ligand_docking(topk, roi, trans_step, rotations, lig, rec=None, grid=None, vdw_mask=None,

@@ -475,4 +475,63 @@ int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses
     return d2h_sync(out_flags, df.p, (size_t)n_poses);
 }
 
+// ------------------------------------------------------------------ N4: desolvation sums
+int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, const double roi_c[3], double roi_r,
+                       double *out_contribs, mmo_desolv **out) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(rec && prot_shell && roi_c && roi_r >= 0.0, "mmo_desolv_protein: bad arguments");
+    if (out) *out = nullptr;
+    mmo_desolv *d = new mmo_desolv();
+    d->shell = prot_shell;
+    const double roi[4] = {roi_c[0], roi_c[1], roi_c[2], roi_r};
+    int rc = d->contribs.alloc(prot_shell->nbits);
+    if (rc == MMO_OK) rc = launch_desolv_protein(rec, prot_shell, roi, d->contribs.p);
+    if (rc == MMO_OK && out_contribs) rc = d2h_sync(out_contribs, d->contribs.p, prot_shell->nbits * sizeof(double));
+    if (rc == MMO_OK && !out_contribs) { cudaError_t e = cudaStreamSynchronize(rt().stream); if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__); }
+    if (rc != MMO_OK || !out) { delete d; d = nullptr; }
+    if (out) *out = d;
+    return rc;
+}
+
+static int desolv_penalty(const mmo_desolv *d, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses,
+                          double *out_prot, double *out_lig) {
+    MMO_REQUIRE(lig->has_r, "mmo_desolv_penalty: the ligand was created without radii");
+    DevBuf<double> dr, dp, dl;
+    MMO_TRY(dr.upload(lig->hr));
+    MMO_TRY(dp.alloc((size_t)n_poses));
+    MMO_TRY(dl.alloc((size_t)n_poses));
+    MMO_TRY(launch_desolv_penalty(d->shell, d->contribs.p, lig, dr.p, src, n_poses, dp.p, dl.p));
+    MMO_TRY(d2h_sync(out_prot, dp.p, (size_t)n_poses * sizeof(double)));
+    return d2h_sync(out_lig, dl.p, (size_t)n_poses * sizeof(double));
+}
+
+int mmo_desolv_penalty_coords(const mmo_desolv *d, const mmo_ligand *lig, int64_t n_poses, const double *xs,
+                              const double *ys, const double *zs, double *out_prot, double *out_lig) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(d && lig && n_poses >= 0, "mmo_desolv_penalty_coords: bad arguments");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(xs && ys && zs && out_prot && out_lig, "mmo_desolv_penalty_coords: null buffer");
+    DevBuf<double> dx, dy, dz;
+    const size_t n = (size_t)n_poses * lig->n;
+    MMO_TRY(dx.upload(xs, n)); MMO_TRY(dy.upload(ys, n)); MMO_TRY(dz.upload(zs, n));
+    return desolv_penalty(d, lig, coords_src(dx.p, dy.p, dz.p), n_poses, out_prot, out_lig);
+}
+
+int mmo_desolv_penalty_poses(const mmo_desolv *d, const mmo_ligand *lig, int64_t n_poses, const double *rot9,
+                             const double *trans3, double *out_prot, double *out_lig) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(d && lig && n_poses >= 0, "mmo_desolv_penalty_poses: bad arguments");
+    if (n_poses == 0) return MMO_OK;
+    MMO_REQUIRE(rot9 && trans3 && out_prot && out_lig, "mmo_desolv_penalty_poses: null buffer");
+    DevBuf<double> dr, dt;
+    MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
+    MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
+    return desolv_penalty(d, lig, rt_src(dr.p, dt.p), n_poses, out_prot, out_lig);
+}
+
+int mmo_desolv_destroy(mmo_desolv *d) {
+    delete d;
+    return MMO_OK;
+}
+
 }  // extern "C"

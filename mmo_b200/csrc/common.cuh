@@ -190,6 +190,11 @@ struct mmo_mask {
     std::vector<uint32_t> hwords;  // host copy (lattice-point AND test of the scan driver)
 };
 
+struct mmo_desolv {
+    const mmo_mask *shell = nullptr;   // the protein's first solvent shell (not owned: must outlive this handle)
+    mmo::DevBuf<double> contribs;      // Lds.protein_desolv: one double per voxel, 0.0 outside shell AND ROI
+};
+
 namespace mmo {
 // pose sources understood by the kernels
 struct PoseSrc {
@@ -224,6 +229,10 @@ int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d
                     const mmo_mask *m, bool set_bits = true);
 int launch_sphere_mask(double cx, double cy, double cz, double r, const mmo_mask *m);
 int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags);
+// desolv.cu (N4): Lds.protein_desolv / Lds.desolvation_penalty
+int launch_desolv_protein(const mmo_receptor *rec, const mmo_mask *shell, const double roi[4], double *d_contribs);
+int launch_desolv_penalty(const mmo_mask *shell, const double *d_contribs, const mmo_ligand *lig, const double *d_radii,
+                          const PoseSrc &src, int64_t n_poses, double *d_prot, double *d_lig);
 int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, const int64_t *d_points,
                           const int32_t *d_rot_perm, int64_t n_cand, int64_t *d_frames, unsigned long long *d_counter);
 

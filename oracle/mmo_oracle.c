@@ -358,6 +358,73 @@ void orc_first_solvent_shell(int P, const double *px, const double *py, const do
     for (int a = 0; a < P; a++) atom_bitmask_put(px[a], py[a], pz[a], pr[a], step, dims, mask, 0);
 }
 
+/* ---- N4: desolvation sums (Majeux, Scarsi and Caflisch PROTEINS 2001, eq. 2) ------------------------------- */
+/* src/const.ml:31: (1/eps_prot - 1/eps_HOH) / (8 pi), eps_prot = 4.0, eps_HOH = 78.5 (const.ml:17,20), pi = 4 atan 1 */
+static double desolvation_constant(void) {
+    double pi = 4.0 * atan(1.0);
+    return (1.0 / 4.0 - 1.0 / 78.5) / (8.0 * pi);
+}
+
+/* src/lds.ml:204-236 protein_desolv: for every set bit of the protein's first solvent shell whose voxel lies inside
+ * the ROI (ROI.is_inside, strict <, src/ROI.ml:65-66): res = Const.desolvation * (voxel_vol * sum_j (q_j/d2)^2) over
+ * the protein atoms BST.neighbors returns for Const.charged_cutoff = 12 A.  The bst library is not vendored: its
+ * neighbour order is unpinned (restated: atom index order) and its radius test is taken as Atom.dist <= tol.
+ * res has one double per voxel (A.make n 0.0). */
+void orc_protein_desolv(int P, const double *px, const double *py, const double *pz, const double *pq,
+                        double step, const int dims[3], const uint8_t *shell, const double roi[4], double *res) {
+    double voxel_vol = step * step * step;                         /* src/grid.ml:29-30 */
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    long xy = (long)dims[0] * dims[1];
+    for (size_t idx = 0; idx < n; idx++) res[idx] = 0.0;
+    for (size_t idx = 0; idx < n; idx++) {                         /* Bitv.iteri_true */
+        if (!mask_get(shell, idx)) continue;
+        int k = (int)((long)idx / xy);                             /* Grid.ijk_of_idx, src/grid.ml:101-105 */
+        int j = (int)(((long)idx - (long)k * xy) / dims[0]);
+        int i = (int)((long)idx - ((long)k * xy + (long)j * dims[0]));
+        double x = orc_grid_node(step, dims[0], i), y = orc_grid_node(step, dims[1], j), z = orc_grid_node(step, dims[2], k);
+        if (!(dist2(roi[0], roi[1], roi[2], x, y, z) < roi[3] * roi[3])) continue;
+        for (int a = 0; a < P; a++) {
+            if (!(sqrt(dist2(x, y, z, px[a], py[a], pz[a])) <= 12.0)) continue;
+            double d2 = dist2(x, y, z, px[a], py[a], pz[a]);       /* V3.dist2 x_p x_j */
+            double v = pq[a] / d2;
+            res[idx] = res[idx] + (v * v);
+        }
+        res[idx] = desolvation_constant() * (voxel_vol * res[idx]);
+    }
+}
+
+/* src/lds.ml:239-267 desolvation_penalty: desolvated = prot_shell AND first_solvent_shell grid lig; for each such voxel
+ * in index order: the ligand atoms with d2 < 144 add (q_j/d2)^2, the voxel's protein contribution is added to prot;
+ * lig = Const.desolvation * (voxel_vol * sum) */
+void orc_desolvation_penalty(double step, const int dims[3], const uint8_t *prot_shell, const double *contribs,
+                             int L, const double *lx, const double *ly, const double *lz, const double *lq,
+                             const double *lr, double *out_prot, double *out_lig) {
+    double voxel_vol = step * step * step;
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    long xy = (long)dims[0] * dims[1];
+    uint8_t *lig_shell = (uint8_t *)calloc((n + 7) / 8, 1);
+    orc_first_solvent_shell(L, lx, ly, lz, lr, step, dims, lig_shell);
+    double lig_desolv = 0.0, prot_desolv = 0.0;
+    for (size_t idx = 0; idx < n; idx++) {
+        if (!(mask_get(prot_shell, idx) && mask_get(lig_shell, idx))) continue;     /* Bitv.bw_and */
+        int k = (int)((long)idx / xy);
+        int j = (int)(((long)idx - (long)k * xy) / dims[0]);
+        int i = (int)((long)idx - ((long)k * xy + (long)j * dims[0]));
+        double x = orc_grid_node(step, dims[0], i), y = orc_grid_node(step, dims[1], j), z = orc_grid_node(step, dims[2], k);
+        for (int a = 0; a < L; a++) {
+            double d2 = dist2(x, y, z, lx[a], ly[a], lz[a]);
+            if (d2 < 12.0 * 12.0) {                                /* Const.charged_cutoff_squared: hard cut-off */
+                double v = lq[a] / d2;
+                lig_desolv = lig_desolv + (v * v);
+            }
+        }
+        prot_desolv = prot_desolv + contribs[idx];
+    }
+    free(lig_shell);
+    *out_prot = prot_desolv;
+    *out_lig = desolvation_constant() * (voxel_vol * lig_desolv);
+}
+
 /* src/lds.ml:97-145 bitmask_whole_protein: grid points whose nearest protein atom is closer than
  * Const.charged_cutoff = 12 A (BST.nearest_neighbor -> V3.dist = sqrt(dist2)); brute force over the atoms */
 void orc_bitmask_whole_protein(int P, const double *px, const double *py, const double *pz,

@@ -88,6 +88,12 @@ void orc_first_solvent_shell(int P, const double *px, const double *py, const do
                              double step, const int dims[3], uint8_t *mask);
 void orc_bitmask_whole_protein(int P, const double *px, const double *py, const double *pz,
                                double step, const int dims[3], uint8_t *mask);
+/* N4: lds.ml:204-236 protein_desolv (res: one double per voxel), lds.ml:239-267 desolvation_penalty */
+void orc_protein_desolv(int P, const double *px, const double *py, const double *pz, const double *pq,
+                        double step, const int dims[3], const uint8_t *shell, const double roi[4], double *res);
+void orc_desolvation_penalty(double step, const int dims[3], const uint8_t *prot_shell, const double *contribs,
+                             int L, const double *lx, const double *ly, const double *lz, const double *lq,
+                             const double *lr, double *out_prot, double *out_lig);
 int orc_vdw_clash_OR(double step, const int dims[3], const uint8_t *mask, double x, double y, double z);
 int orc_vdw_clash_AND(double step, const int dims[3], const uint8_t *mask, double x, double y, double z);
 int orc_protein_ligand_clash(double step, const int dims[3], const uint8_t *mask,

@@ -281,6 +281,27 @@ def bitmask_whole_protein(xs, ys, zs, step, dims):
     return mask[:(nvox + 7) // 8]
 
 
+def protein_desolv(rec, step, dims, shell, roi):
+    """lds.ml:204-236: one double per voxel"""
+    nvox = dims[0] * dims[1] * dims[2]
+    res = np.empty(nvox)
+    shell = np.ascontiguousarray(shell, np.uint8)
+    lib().orc_protein_desolv(C.c_int(rec.n), d(rec.xs)[1], d(rec.ys)[1], d(rec.zs)[1], d(rec.q)[1], C.c_double(step),
+                             (C.c_int * 3)(*dims), shell.ctypes.data_as(_bp), (C.c_double * 4)(*roi), res.ctypes.data_as(_dp))
+    return res
+
+
+def desolvation_penalty(step, dims, prot_shell, contribs, xs, ys, zs, q, radii):
+    """lds.ml:239-267: (prot, lig) of one ligand pose"""
+    prot_shell = np.ascontiguousarray(prot_shell, np.uint8)
+    contribs = np.ascontiguousarray(contribs, np.float64)
+    op, ol = C.c_double(), C.c_double()
+    lib().orc_desolvation_penalty(C.c_double(step), (C.c_int * 3)(*dims), prot_shell.ctypes.data_as(_bp),
+                                  contribs.ctypes.data_as(_dp), C.c_int(len(xs)), d(xs)[1], d(ys)[1], d(zs)[1], d(q)[1],
+                                  d(radii)[1], C.byref(op), C.byref(ol))
+    return op.value, ol.value
+
+
 def vdw_volume(xs, ys, zs, radii, step, dims):
     nvox = dims[0] * dims[1] * dims[2]
     mask = np.zeros((nvox + 7) // 8 + 8, np.uint8)

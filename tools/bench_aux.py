@@ -174,6 +174,36 @@ def main():
     gm = g2.download()
     oracle.mc_run(c2["lig"], cx, cy, cz, c2["roi"], n_steps, int(seeds[0]), Rm[0], tm[0], maps=gm, g_step=0.5, g_dims=gd)
     out["c4_mc"]["cpu_oracle_chain_steps_per_s_1core"] = n_steps / (time.perf_counter() - t0)
+    # ---- N4: desolvation sums on the reference's own grid (0.5 A over the simulation box) ---------------
+    rm = c2["rec"]
+    sdims = mmo_b200.Grid.from_box(0.5, *c2["sim_dims"])
+    shell = mmo_b200.Lds.first_solvent_shell(rm.xs, rm.ys, rm.zs, rm.r, 0.5, sdims)
+    rec_all = mmo_b200.Receptor.from_mol(rm)
+    L.mmo_sync()
+    t0 = time.perf_counter()
+    dh, _ = mmo_b200.Lds.protein_desolv(c2["roi"], rec_all, shell, want_host=False)
+    t_prot = time.perf_counter() - t0
+    n_pen = 2000 if args.quick else 20000
+    Rp, tp = workloads.random_poses_in_sphere(n_pen, c2["roi"][:3], 6.0, seed=43)
+    mmo_b200.Lds.desolvation_penalty(dh, lig2, rot9=Rp[:64], trans3=tp[:64])
+    t0 = time.perf_counter()
+    dp, dl = mmo_b200.Lds.desolvation_penalty(dh, lig2, rot9=Rp, trans3=tp)
+    t_pen = time.perf_counter() - t0
+    # the oracle on a few of the same poses, one host core
+    t0 = time.perf_counter()
+    contribs = oracle.protein_desolv(rm, 0.5, sdims, shell.bits, c2["roi"])
+    t_prot_cpu = time.perf_counter() - t0
+    X, Y, Z = oracle.pose_coords(lig2.xs, lig2.ys, lig2.zs, Rp[:3], tp[:3])
+    t0 = time.perf_counter()
+    for q in range(3):
+        wp, wl = oracle.desolvation_penalty(0.5, sdims, shell.bits, contribs, X[q], Y[q], Z[q], c2["lig"].q, c2["lig"].r)
+        assert wp == dp[q] and wl == dl[q]
+    t_pen_cpu = (time.perf_counter() - t0) / 3
+    out["n4_desolvation"] = {"grid_dims": list(sdims), "receptor_atoms": rm.n, "protein_desolv_wall_ms": t_prot * 1e3,
+                             "protein_desolv_cpu_oracle_ms": t_prot_cpu * 1e3, "penalty_poses": n_pen,
+                             "penalty_wall_ms": t_pen * 1e3, "penalty_poses_per_s": n_pen / t_pen,
+                             "penalty_cpu_oracle_poses_per_s_1core": 1.0 / t_pen_cpu,
+                             "median_prot": float(np.median(dp)), "median_lig": float(np.median(dl))}
     L.mmo_kernel_timing(0)
     print(json.dumps(out))
 
