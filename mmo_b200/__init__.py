@@ -23,7 +23,8 @@ import numpy as np
 from . import pqrs  # noqa: F401  (host-side file formats)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmmo_b200.so")
+# MMO_B200_LIB: kernel-tuning experiments load an alternative build of the same library (tools/variants.sh)
+LIB_PATH = os.environ.get("MMO_B200_LIB") or os.path.join(_HERE, "csrc", "libmmo_b200.so")
 
 VARIANT_GLOBAL, VARIANT_SHIFTED = 0, 1      # -ff BrG | BrL/Bst
 PREC_FP32, PREC_FP64 = 0, 1

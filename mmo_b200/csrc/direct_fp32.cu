@@ -34,6 +34,18 @@ namespace mmo {
 
 constexpr int LJ = 4;            // ligand atoms per chunk (half a k-d leaf of the ligand)
 constexpr int kFixLJ = LJ;
+// hard_fix_kernel tunables (measured on C2, profiles/README.md): -D overrides are for tools/variants.sh experiments
+#ifndef MMO_FIX_BLOCKS
+#define MMO_FIX_BLOCKS 10
+#endif
+#ifndef MMO_FIX_UNROLL
+#define MMO_FIX_UNROLL 4
+#endif
+#ifndef MMO_FIX_MARGIN
+#define MMO_FIX_MARGIN 0.01f
+#endif
+constexpr int kFixUnroll = MMO_FIX_UNROLL;           // pre-test loop of hard_fix_kernel
+constexpr int kFixBlocksPerSM = MMO_FIX_BLOCKS;   // hard_fix_kernel: 128-thread blocks resident per SM (caps the registers)
 constexpr int TPB = 512;         // threads per block (one persistent block per SM: one copy of the receptor tile)
 constexpr int kBlocksPerSM = 1;
 constexpr int PPT = 2;           // poses per thread
@@ -41,7 +53,10 @@ constexpr int PPB = TPB * PPT;   // poses per block
 constexpr int LIST_CAP = 256;    // per-warp list of near receptor atoms
 constexpr int NF = 7;            // list fields: x', y', z', |x'|^2, q_i q_j, A_i A_j, -B_i B_j
 constexpr int MAX_TILE_GROUPS = 128;
-constexpr int kSumEvery = 16;    // list steps (of 4 atoms) summed in fp32 before the fp64 accumulation
+#ifndef MMO_SUM_EVERY
+#define MMO_SUM_EVERY 32
+#endif
+constexpr int kSumEvery = MMO_SUM_EVERY;    // list steps (of 4 atoms) summed in fp32 before the fp64 accumulation
 constexpr float kRhoExpand2 = 20.25f;  // the expanded form of r^2 is used while rho <= 4.5 A
 static_assert(kBlob == 16, "two receptor groups per warp-wide test");
 static_assert(LIST_CAP % 4 == 0 && LIST_CAP >= 128, "list must take one more step (64 atoms) before a flush");
@@ -82,6 +97,14 @@ __device__ __forceinline__ float warp_max(float x) {
     return y;
 }
 __device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float y;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+    return y;
+}
+#ifndef MMO_SAT_WEIGHT
+#define MMO_SAT_WEIGHT 1
+#endif
 
 // Two receptor atoms (the halves of the packed operands) against one ligand atom of one pose.
 //   EXPAND : r^2 = (|x'|^2 + |l'|^2) - 2 x'.l'   (m2 = -2 l', l2 = |l'|^2)         4 packed ops
@@ -102,7 +125,7 @@ __device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 S, 
     }
     r2_out = r2;
     float2 r2c;                                      // close contacts are finished in fp64 elsewhere
-    if (VARIANT == MMO_VARIANT_SHIFTED) {
+    if (VARIANT == MMO_VARIANT_SHIFTED && !MMO_SAT_WEIGHT) {
         r2c.x = fminf(fmaxf(r2.x, H), 144.0f);
         r2c.y = fminf(fmaxf(r2.y, H), 144.0f);
     } else {
@@ -115,7 +138,13 @@ __device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 S, 
     const float2 v = __ffma2_rn(AA, s3, nBB);
     const float2 e = __ffma2_rn(v, s3, __fmul2_rn(QQ, rinv));
     if (VARIANT == MMO_VARIANT_SHIFTED) {
+#if MMO_SAT_WEIGHT
+        // FF.shift_12A as two scalar saturating FMAs: sat(1 - r^2/144) is exactly 0 from 12 A on, which makes the
+        // upper clamp of r^2 (two FMNMX) unnecessary; same FMA-pipe time as one packed FMA
+        const float2 up = make_float2(fma_sat(r2c.x, -1.0f / 144.0f, 1.0f), fma_sat(r2c.y, -1.0f / 144.0f, 1.0f));
+#else
         const float2 up = __ffma2_rn(r2c, bc2(-1.0f), bc2(144.0f));
+#endif
         return __ffma2_rn(__fmul2_rn(up, up), e, acc);
     } else {
         return __fadd2_rn(acc, e);
@@ -127,40 +156,33 @@ template <int VARIANT, bool EXPAND, bool STATS>
 __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const float (&m2x)[PPT], const float (&m2y)[PPT],
                                          const float (&m2z)[PPT], const float (&l2)[PPT], float H, double (&acc)[PPT],
                                          float (&rmin)[PPT], unsigned long long (&n_in)[PPT]) {
-    float2 f[PPT][2];
-#pragma unroll
-    for (int h = 0; h < PPT; h++) f[h][0] = f[h][1] = make_float2(0.f, 0.f);
-    int since = 0;
+    // blocks of kSumEvery steps: fp32 partial sums inside a block, one F2F + DADD per pose at its end
 #pragma unroll 1
-    for (int k = 0; k < n4; k += 4) {
-        const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
-        const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
-        const float4 Q = *(const float4 *)(s_l + 4 * LIST_CAP + k), A = *(const float4 *)(s_l + 5 * LIST_CAP + k);
-        const float4 B = *(const float4 *)(s_l + 6 * LIST_CAP + k);
+    for (int k0 = 0; k0 < n4; k0 += 4 * kSumEvery) {
+        const int kend = min(n4, k0 + 4 * kSumEvery);
+        float2 f[PPT][2];
 #pragma unroll
-        for (int h = 0; h < PPT; h++) {
-            float2 ra, rb;
-            f[h][0] = pair2<VARIANT, EXPAND>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
-                                             make_float2(S.x, S.y), make_float2(Q.x, Q.y), make_float2(A.x, A.y),
-                                             make_float2(B.x, B.y), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][0], ra);
-            f[h][1] = pair2<VARIANT, EXPAND>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
-                                             make_float2(S.z, S.w), make_float2(Q.z, Q.w), make_float2(A.z, A.w),
-                                             make_float2(B.z, B.w), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][1], rb);
-            rmin[h] = fminf(fminf(rmin[h], fminf(ra.x, ra.y)), fminf(rb.x, rb.y));   // close contact seen? (fix pass)
-            if (STATS) n_in[h] += (ra.x < 144.0f && k < n) + (ra.y < 144.0f && k + 1 < n) + (rb.x < 144.0f && k + 2 < n) +
-                                  (rb.y < 144.0f && k + 3 < n);
-        }
-        if (++since == kSumEvery) {
+        for (int h = 0; h < PPT; h++) f[h][0] = f[h][1] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int k = k0; k < kend; k += 4) {
+            const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
+            const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
+            const float4 Q = *(const float4 *)(s_l + 4 * LIST_CAP + k), A = *(const float4 *)(s_l + 5 * LIST_CAP + k);
+            const float4 B = *(const float4 *)(s_l + 6 * LIST_CAP + k);
 #pragma unroll
             for (int h = 0; h < PPT; h++) {
-                const float2 t = __fadd2_rn(f[h][0], f[h][1]);
-                acc[h] += (double)(t.x + t.y);
-                f[h][0] = f[h][1] = make_float2(0.f, 0.f);
+                float2 ra, rb;
+                f[h][0] = pair2<VARIANT, EXPAND>(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
+                                                 make_float2(S.x, S.y), make_float2(Q.x, Q.y), make_float2(A.x, A.y),
+                                                 make_float2(B.x, B.y), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][0], ra);
+                f[h][1] = pair2<VARIANT, EXPAND>(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
+                                                 make_float2(S.z, S.w), make_float2(Q.z, Q.w), make_float2(A.z, A.w),
+                                                 make_float2(B.z, B.w), m2x[h], m2y[h], m2z[h], l2[h], H, f[h][1], rb);
+                rmin[h] = fminf(fminf(rmin[h], fminf(ra.x, ra.y)), fminf(rb.x, rb.y));   // close contact seen? (fix pass)
+                if (STATS) n_in[h] += (ra.x < 144.0f && k < n) + (ra.y < 144.0f && k + 1 < n) + (rb.x < 144.0f && k + 2 < n) +
+                                      (rb.y < 144.0f && k + 3 < n);
             }
-            since = 0;
         }
-    }
-    if (since != 0) {
 #pragma unroll
         for (int h = 0; h < PPT; h++) {
             const float2 t = __fadd2_rn(f[h][0], f[h][1]);
@@ -211,7 +233,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
     }
     __syncthreads();
     // SHIFTED: the weight (144 - r^2)^2 / 144^2 is split between the pair and the list entries
-    const float wscale = VARIANT == MMO_VARIANT_SHIFTED ? 1.0f / 20736.0f : 1.0f;
+    const float wscale = (VARIANT == MMO_VARIANT_SHIFTED && !MMO_SAT_WEIGHT) ? 1.0f / 20736.0f : 1.0f;
     const int n_chunks = a.n_fast / LJ;
     const unsigned long long n_groups = (unsigned long long)((n_poses + 32 * PPT - 1) / (32 * PPT));
     const unsigned long long n_units = n_groups * (unsigned long long)n_split;
@@ -733,7 +755,7 @@ struct FixArgs {
 // ITEMS: part = per-item energies [pose][n_split = n_fast], flags = per-item bytes (direct_items_kernel);
 // else  : part = per-split sums [n_split][pose], flags = per-(tile, chunk) bytes (direct_fp32_kernel)
 template <int VARIANT, bool STATS, bool ITEMS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, kFixBlocksPerSM)
 hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int n_split,
                 const uint8_t *__restrict__ flags, int n_tiles, int n_chunks, double *out) {   // part may alias out
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -745,7 +767,10 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
     double corr = 0.0;
     unsigned long long n_fix = 0, n_flag = 0;
     bool have_pose = false;
-    PoseRT P;
+    // the pose (rotation + translation, 12 doubles) lives in this thread's shared-memory column, not in 24 registers:
+    // the kernel is latency bound and the registers buy more resident warps
+    __shared__ double s_P[12][128];
+    const int tx = threadIdx.x;
     for (int c = 0; c < n_chunks; c++) {
         // atoms of chunk c (fast-path order) for which the fast kernel saw a pair below H (any tile)
         unsigned bits = 0u;
@@ -764,8 +789,19 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
             if (src.kind == 1) {
                 x = src.xs[p * a.L + j]; y = src.ys[p * a.L + j]; z = src.zs[p * a.L + j];
             } else {
-                if (!have_pose) { load_pose_rt(src, p, P); have_pose = true; }
-                pose_atom_rt(P, __ldg(a.lx + j), __ldg(a.ly + j), __ldg(a.lz + j), x, y, z);
+                if (!have_pose) {
+                    PoseRT P;
+                    load_pose_rt(src, p, P);
+#pragma unroll
+                    for (int q = 0; q < 9; q++) s_P[q][tx] = P.r[q];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) s_P[9 + q][tx] = P.t[q];
+                    have_pose = true;
+                }
+                const double ax = __ldg(a.lx + j), ay = __ldg(a.ly + j), az = __ldg(a.lz + j);
+                x = __dadd_rn(rot_row(s_P[0][tx], s_P[1][tx], s_P[2][tx], ax, ay, az), s_P[9][tx]);
+                y = __dadd_rn(rot_row(s_P[3][tx], s_P[4][tx], s_P[5][tx], ax, ay, az), s_P[10][tx]);
+                z = __dadd_rn(rot_row(s_P[6][tx], s_P[7][tx], s_P[8][tx], ax, ay, az), s_P[11][tx]);
             }
             const double fx = (x - a.vox_lo[0]) * a.vox_inv, fy = (y - a.vox_lo[1]) * a.vox_inv, fz = (z - a.vox_lo[2]) * a.vox_inv;
             if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0)) continue;
@@ -777,35 +813,49 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
             const double qj = kElecWeight * __ldg(a.lq + j);
             const int ej = __ldg(a.lelt + j);
             const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
-            const float Hf = (float)a.H + 0.5f;
-            for (int k = k0; k < k1; k++) {
-                const int i = __ldg(a.vox_idx + k);
-                // cheap fp32 pre-test (coordinates relative to the voxel grid corner, error << the 0.5 A^2 margin)
-                const float4 r4 = __ldg(a.pxyz32 + i);
-                const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
-                if (fdx * fdx + fdy * fdy + fdz * fdz >= Hf) continue;
-                const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
-                const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
-                const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 < a.H) {
-                    const int tt = __ldg(a.pelt + i) * kEltTab + ej;
-                    const double qq = r23.y * qj;
-                    const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
-                    const double rinv = rsqrt(r2c);
-                    const double t2 = __ldg(a.xx + tt) * (rinv * rinv);  // (x_ij / r)^2
-                    const double p6 = t2 * t2 * t2;
-                    const double ee = qq * rinv + __ldg(a.dij + tt) * (p6 * p6 - 2.0 * p6);
-                    const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
-                    double d;
-                    if (VARIANT == MMO_VARIANT_SHIFTED) {
-                        const double u = 1.0 - r2c * (1.0 / 144.0);
-                        d = (u * u) * ee - a.wH * eH;                      // the fast path clamped r^2 in the weight too
-                    } else {
-                        d = ee - eH;
+            const float Hf = (float)a.H + MMO_FIX_MARGIN;     // fp32 r^2 of coordinates below ~200 A: error < 1e-3 A^2
+            // Two phases per window of 64 candidates, so that a warp whose lanes sit in different voxels pays
+            // max(candidates) cheap tests + max(close pairs) fp64 evaluations, not their product: (1) the fp32 pre-test
+            // (coordinates relative to the voxel grid corner, error << the margin) marks the survivors in a
+            // 64-bit mask, (2) the survivors are evaluated in double, in list order.
+            for (int kw = k0; kw < k1; kw += 64) {
+                unsigned long long pass = 0ull;
+                const int kn = min(64, k1 - kw);
+#pragma unroll kFixUnroll
+                for (int b = 0; b < kn; b++) {
+                    const float4 r4 = __ldg(a.pxyz32 + __ldg(a.vox_idx + kw + b));
+                    const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
+                    if (fdx * fdx + fdy * fdy + fdz * fdz < Hf) pass |= 1ull << b;
+                }
+                while (pass != 0ull) {
+                    const int b = __ffsll((long long)pass) - 1;
+                    pass &= pass - 1ull;
+                    const int i = __ldg(a.vox_idx + kw + b);
+                    const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
+                    const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
+                    const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
+                    const double r2 = dx * dx + dy * dy + dz * dz;
+                    if (r2 < a.H) {
+                        const int tt = __ldg(a.pelt + i) * kEltTab + ej;
+                        const double qq = r23.y * qj;
+                        const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
+                        // 1/r: MUFU.RSQ in fp32 (relative error < 2e-7), one Newton step in double (-> < 1e-13)
+                        const double y0 = (double)rsqrtf((float)r2c);
+                        const double rinv = y0 * (1.5 - (0.5 * r2c) * (y0 * y0));
+                        const double t2 = __ldg(a.xx + tt) * (rinv * rinv);  // (x_ij / r)^2
+                        const double p6 = t2 * t2 * t2;
+                        const double ee = qq * rinv + __ldg(a.dij + tt) * (p6 * p6 - 2.0 * p6);
+                        const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
+                        double d;
+                        if (VARIANT == MMO_VARIANT_SHIFTED) {
+                            const double u = 1.0 - r2c * (1.0 / 144.0);
+                            d = (u * u) * ee - a.wH * eH;                      // the fast path clamped r^2 in the weight too
+                        } else {
+                            d = ee - eH;
+                        }
+                        corr += d;
+                        if (STATS) n_fix++;
                     }
-                    corr += d;
-                    if (STATS) n_fix++;
                 }
             }
         }
