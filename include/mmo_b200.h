@@ -333,6 +333,19 @@ int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const mmo_ligand *
                const double *start_pos3, mmo_mc_result *results, double *best_xyz,
                double *trace_chain0);
 
+/* Lds.place_ligand_in_ROI (src/lds.ml:308-345): n_starts random start poses (rotation, position) of the centred
+ * ligand inside the ROI sphere, rejecting poses in which a ligand heavy atom comes closer than 0.8 (r_i + r_j) to a
+ * protein heavy atom (Mol.heavy_atom_clash, src/mol.ml:1170-1190; px.. = ALL receptor atoms, simulation-box
+ * coordinates).  Host code; random numbers mmo_rng_uniform(seed, 0, 1, ...) (not OCaml's Random.State), libm sin/cos.
+ * clash_check = 0 skips the rejection: in the reference Ptable.vdW_max is A.max of an array holding nan
+ * (src/ptable.ml:32,84), so BST.neighbors is called with a nan radius and, if it then returns nothing (bst and
+ * batteries are not vendored: unpinned), no pose is ever rejected -- pass 0 to reproduce that reading, which is also
+ * the only one under which the reference can start on its own data/ example (blind rigid placement into the buried
+ * 3A2J pocket never passes the test as written).  Fails after 100 000 draws, as the reference exits. */
+int mmo_place_ligand_in_roi(int32_t n_rec, const double *px, const double *py, const double *pz, const int32_t *panum,
+                            const mmo_ligand *lig, const double roi_c[3], double roi_r, uint64_t seed, int32_t n_starts,
+                            int32_t clash_check, double *out_rot9, double *out_pos3, int32_t *n_trials);
+
 /* ---------------------------------------------------------------- N2: ligand / receptor files on the host ----
  * mol2pqrs (src/mol2pqrs.ml:10-58, src/mol_graph.ml:45-200, src/mol2.ml:139-320) and the .pqrs reader
  * (src/pqrs.ml:19-87, src/mol.ml:368-440) inside the library: no subprocess, no GPU needed except for

@@ -531,6 +531,19 @@ class Lds:
         return out, xyz, trace
 
 
+def place_ligand_in_ROI(rec_mol, lig, roi, seed, n_starts, clash_check=True):
+    """Lds.place_ligand_in_ROI (src/lds.ml:308-345): (rot9[n], pos3[n], trials); rec_mol = ALL receptor atoms"""
+    (a, pa), (b, pb), (c, pc) = _d(rec_mol.xs), _d(rec_mol.ys), _d(rec_mol.zs)
+    an, pan = _i(rec_mol.anum)
+    rot = np.empty((n_starts, 9)); pos = np.empty((n_starts, 3))
+    tr = C.c_int32()
+    rc = (C.c_double * 3)(*roi[:3])
+    _ck(lib().mmo_place_ligand_in_roi(C.c_int32(len(a)), pa, pb, pc, pan, lig.h, rc, C.c_double(roi[3]), C.c_uint64(seed),
+                                      C.c_int32(n_starts), C.c_int32(1 if clash_check else 0), rot.ctypes.data_as(_dp),
+                                      pos.ctypes.data_as(_dp), C.byref(tr)))
+    return rot, pos, tr.value
+
+
 class Optim:
     @staticmethod
     def apply_config(lig, config):

@@ -3,7 +3,9 @@
 // on the same platform.  Compiled with -ffp-contract=off (OCaml never fuses a*b+c).
 //   SO3.ml:13-39, quat.ml:32-36, rot.ml:52-75,121-146, grid.ml:37-52
 #include "common.cuh"
+#include "../../include/mmo_detmath.h"
 #include <math.h>
+#include <string.h>
 #include <algorithm>
 
 namespace mmo {
@@ -179,6 +181,80 @@ int mmo_rotated_copies(const mmo_ligand *lig, const double center[3], int32_t n,
     MMO_REQUIRE(lig && center && n >= 0 && (n == 0 || (rot9 && out_xs && out_ys && out_zs)), "mmo_rotated_copies: bad arguments");
     const mmo::HostLig h = {lig->n, lig->hx.data(), lig->hy.data(), lig->hz.data(), 0, nullptr, nullptr, nullptr, nullptr};
     mmo::rotated_copies_host(h, center, n, rot9, out_xs, out_ys, out_zs);
+    return MMO_OK;
+}
+
+// Lds.place_ligand_in_ROI rng prot_bst prot roi centered_ligs n (src/lds.ml:308-345): uniform points in the ROI's
+// englobing cube (Bbox.rand_point_inside, src/bbox.ml:50-54) until one lies inside the sphere (ROI.is_inside, strict <),
+// then Move.rand_rot_full (src/move.ml:20-39: three rand_rot of +-pi about a random axis, R' = R_axis * R); the pose is
+// kept unless Mol.heavy_atom_clash (src/mol.ml:1170-1190: two heavy atoms closer than 0.8 (r_i + r_j),
+// src/ptable.ml:61-80).  100 000 draws over all starts are fatal, as in the reference.  Random numbers:
+// mmo_rng_uniform(seed, 0, 1, 2, ...) (include/mmo_detmath.h) instead of OCaml's Random.State, consumed in
+// the reference's order (constructor arguments right to left: z, y, x; then theta, axis three times).  libm sin/cos.
+int mmo_place_ligand_in_roi(int32_t n_rec, const double *px, const double *py, const double *pz, const int32_t *panum,
+                            const mmo_ligand *lig, const double roi_c[3], double roi_r, uint64_t seed, int32_t n_starts,
+                            int32_t clash_check, double *out_rot9, double *out_pos3, int32_t *n_trials) {
+    MMO_REQUIRE(lig && roi_c && roi_r > 0.0 && n_starts >= 0 && n_rec >= 0, "mmo_place_ligand_in_roi: bad arguments");
+    MMO_REQUIRE(n_starts == 0 || (out_rot9 && out_pos3), "mmo_place_ligand_in_roi: null output");
+    MMO_REQUIRE(n_rec == 0 || (px && py && pz && panum), "mmo_place_ligand_in_roi: null receptor arrays");
+    const int L = lig->n;
+    double low[3], dims[3];
+    for (int d = 0; d < 3; d++) { low[d] = roi_c[d] - roi_r; dims[d] = (roi_c[d] + roi_r) - low[d]; }   // Bbox.create_2v
+    const double r2 = roi_r * roi_r;
+    uint64_t ctr = 0;
+    int trials = 0;
+    for (int s = 0; s < n_starts; s++) {
+        for (;;) {
+            const double z = low[2] + mmo_rng_uniform(seed, ctr++) * dims[2];
+            const double y = low[1] + mmo_rng_uniform(seed, ctr++) * dims[1];
+            const double x = low[0] + mmo_rng_uniform(seed, ctr++) * dims[0];
+            trials++;
+            if (trials == 100000) {
+                mmo::set_error("Lds.place_ligands_in_ROI: start conformer cannot be placed in ROI after 100k trials");
+                return MMO_EINVAL;
+            }
+            const double ddx = roi_c[0] - x, ddy = roi_c[1] - y, ddz = roi_c[2] - z;
+            if (!(ddx * ddx + ddy * ddy + ddz * ddz < r2)) continue;
+            double rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            for (int k = 0; k < 3; k++) {
+                const double pi = 4.0 * atan(1.0);
+                const double theta = mmo_rng_uniform(seed, ctr++) * (2.0 * pi) - pi;      // Move.rand_angle
+                int axis = (int)(mmo_rng_uniform(seed, ctr++) * 3.0);                    // Random.State.int rng 3
+                if (axis > 2) axis = 2;
+                const double c = cos(theta), sn = sin(theta);
+                double rb[9];
+                if (axis == 0) { const double t[9] = {1, 0, 0, 0, c, sn, 0, -sn, c}; memcpy(rb, t, sizeof t); }       // Rot.rx
+                else if (axis == 1) { const double t[9] = {c, 0, -sn, 0, 1, 0, sn, 0, c}; memcpy(rb, t, sizeof t); }  // Rot.ry
+                else { const double t[9] = {c, sn, 0, -sn, c, 0, 0, 0, 1}; memcpy(rb, t, sizeof t); }                 // Rot.rz
+                double o[9];
+                for (int a = 0; a < 3; a++)                                              // Rot.mult rotate_by rot
+                    for (int b = 0; b < 3; b++)
+                        o[3 * a + b] = rb[3 * a] * rot[b] + rb[3 * a + 1] * rot[3 + b] + rb[3 * a + 2] * rot[6 + b];
+                memcpy(rot, o, sizeof o);
+            }
+            bool clash = false;
+            if (clash_check) {
+                for (int j = 0; j < L && !clash; j++) {
+                    if (lig->hanum[j] <= 1) continue;
+                    double q[3];
+                    mmo::rot_apply(rot, lig->hx[j], lig->hy[j], lig->hz[j], q);            // rotate_then_translate_copy
+                    q[0] += x; q[1] += y; q[2] += z;
+                    const double rj = mmo::vdw_radius(lig->hanum[j]);
+                    for (int i = 0; i < n_rec; i++) {
+                        if (panum[i] <= 1) continue;
+                        const double lim = 0.8 * (rj + mmo::vdw_radius(panum[i]));         // Ptable.vdW_clash_params2
+                        const double ex = q[0] - px[i], ey = q[1] - py[i], ez = q[2] - pz[i];
+                        if (ex * ex + ey * ey + ez * ez < lim * lim) { clash = true; break; }
+                    }
+                }
+            }
+            if (clash) continue;
+            memcpy(out_rot9 + 9 * (size_t)s, rot, sizeof rot);
+            out_pos3[3 * (size_t)s] = x; out_pos3[3 * (size_t)s + 1] = y; out_pos3[3 * (size_t)s + 2] = z;
+            break;
+        }
+    }
+    if (n_trials) *n_trials = trials;
     return MMO_OK;
 }
 

@@ -158,3 +158,87 @@ def test_c4_full_size_chains_shard_and_match(gpu, orc, c2, c2_roi_rec, mc_setup)
         assert all(res[c][k] == want[k] for k in keys), c
     best = np.array([r["best_E"] for r in res])
     assert np.isfinite(best).all() and best.min() < np.median(best)
+
+
+@pytest.mark.gpu
+def test_place_ligand_in_roi_properties(gpu, orc, c2):
+    """Lds.place_ligand_in_ROI (lds.ml:308-345): every start lies strictly inside the ROI, no ligand heavy atom comes
+    closer than 0.8 (r_i + r_j) to a protein heavy atom (Mol.heavy_atom_clash), the draws are a pure function of the
+    seed, and without the clash test the poses are the first in-ROI draws of the same stream"""
+    import mmo_b200
+    m, lm = c2["rec"], c2["lig"]
+    lig = gpu.Ligand.from_mol(lm, centered=True)
+    # a ROI at the protein surface: some random poses touch the protein and are rejected, others pass
+    roi = (float(m.xs.max()) + 5.0, float(np.median(m.ys)), float(np.median(m.zs)), 8.0)
+    rot, pos, trials = mmo_b200.place_ligand_in_ROI(m, lig, roi, 1234, 12)
+    rot2, pos2, trials2 = mmo_b200.place_ligand_in_ROI(m, lig, roi, 1234, 12)
+    assert np.array_equal(rot, rot2) and np.array_equal(pos, pos2) and trials == trials2 >= 12
+    c, r = np.array(roi[:3]), roi[3]
+    assert (((pos - c) ** 2).sum(1) < r * r).all()
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, rot, pos)
+    heavy_l, heavy_p = lm.anum > 1, m.anum > 1
+    lim = 0.8 * (lm.r[heavy_l][:, None] + m.r[heavy_p][None, :])
+    for p in range(12):
+        d2 = ((X[p][heavy_l][:, None] - m.xs[heavy_p][None, :]) ** 2 + (Y[p][heavy_l][:, None] - m.ys[heavy_p][None, :]) ** 2 +
+              (Z[p][heavy_l][:, None] - m.zs[heavy_p][None, :]) ** 2)
+        assert (d2 >= lim * lim).all()
+        R = rot[p].reshape(3, 3)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and abs(np.linalg.det(R) - 1.0) < 1e-12
+    # without the rejection every in-ROI draw is taken: fewer trials, and the first pose is the first in-ROI point
+    rot0, pos0, trials0 = mmo_b200.place_ligand_in_ROI(m, lig, roi, 1234, 12, clash_check=False)
+    assert 12 <= trials0 < trials
+    u = [orc.lib().orc_rng_uniform for _ in range(1)][0]
+    import ctypes as C
+    u.restype = C.c_double
+    ctr, first = 0, None
+    while first is None:
+        z = (c[2] - r) + u(C.c_uint64(1234), C.c_uint64(ctr)) * ((c[2] + r) - (c[2] - r))
+        y = (c[1] - r) + u(C.c_uint64(1234), C.c_uint64(ctr + 1)) * ((c[1] + r) - (c[1] - r))
+        x = (c[0] - r) + u(C.c_uint64(1234), C.c_uint64(ctr + 2)) * ((c[0] + r) - (c[0] - r))
+        ctr += 3
+        if (c[0] - x) ** 2 + (c[1] - y) ** 2 + (c[2] - z) ** 2 < r * r:
+            first = (x, y, z)
+    assert tuple(pos0[0]) == first
+    # the buried 3A2J pocket itself cannot be populated by blind rigid placement when the clash test is on: the
+    # reference's message after 100 000 draws (with its nan radius the reference never gets there, see the header)
+    with pytest.raises(RuntimeError, match="100k trials"):
+        mmo_b200.place_ligand_in_ROI(m, lig, c2["roi"], 5, 1)
+    _, pos_b, _ = mmo_b200.place_ligand_in_ROI(m, lig, c2["roi"], 5, 3, clash_check=False)
+    assert (((pos_b - np.array(c2["roi"][:3])) ** 2).sum(1) < c2["roi"][3] ** 2).all()
+
+
+@pytest.mark.gpu
+def test_lds_mc_c_program_matches_the_python_path(gpu, orc, c2):
+    """tools/lds_mc.c: `lds` in its Monte-Carlo mode as a plain C program on the C ABI, fed with the committed .pqrs /
+    .bild files: same start poses, same chains, same best energies as the ctypes path on the same inputs"""
+    import os
+    import subprocess
+    import mmo_b200
+    exe = os.path.join(os.path.dirname(gpu.LIB_PATH), "lds_mc")
+    assert os.path.exists(exe), "build it with `make -C mmo_b200/csrc tools` (done by __graft_entry__.build())"
+    G = workloads.GOLDEN
+    n_steps, starts, seed = 400, 5, 77
+    out = subprocess.run([exe, "-lig", os.path.join(G, "docked.pqrs"), "-rec", os.path.join(G, "xtal_rec.pqrs"), "-roi",
+                          os.path.join(G, "ROI.bild"), "-steps", str(n_steps), "-starts", str(starts), "-s", str(seed),
+                          "--intra-NB", "--hard-ROI"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().split("\n")
+    rows = [l.split("\t") for l in lines if l and not l.startswith("#") and "\t" in l]
+    assert len(rows) == starts and lines[-1].startswith(f"{n_steps} frames in ")
+    # the same run through the ctypes mirror: maps on the 0.5 A simulation grid behind the ROI-only bitmask
+    m, lm = c2["rec"], c2["lig"]
+    dims = gpu.Grid.from_box(0.5, *c2["sim_dims"])
+    mask = gpu.Lds.bitmask_ROI_only(c2["roi"], 0.5, dims)
+    ta, tq = pqrs.assign_ff_types([lm])
+    rec = gpu.Receptor.from_mol(m)
+    g, _ = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.5, dims, ta, tq, mask_bits=mask.bits, want_host=False)
+    lig = gpu.Ligand.from_mol(lm, centered=True)
+    rot, pos, _ = mmo_b200.place_ligand_in_ROI(m, lig, c2["roi"], seed, starts, clash_check=False)
+    seeds = np.array([seed + 1 + s for s in range(starts)], np.uint64)
+    res, _, _ = gpu.Lds.simulate_lig(g, lig, c2["roi"], n_steps, seeds, rot, pos)
+    for s, row in enumerate(rows):
+        assert int(row[1]) == s and float(row[2]) == res[s]["best_E"] and int(row[3]) == res[s]["frames_done"]
+        assert int(row[4]) == res[s]["n_accept_rigid"] and int(row[7]) == res[s]["n_reject_conf"]
+    # flag handling of the OCaml main (lds.ml:1759-1771): exactly one E_intra flag
+    bad = subprocess.run([exe, "-lig", "a", "-rec", "b", "-roi", "c", "-steps", "10k"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "which lig_E_intra FF to use?" in bad.stderr
