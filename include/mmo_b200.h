@@ -364,6 +364,9 @@ int mmo_molfile_get(const mmo_molfile *f, int32_t k, double *xs, double *ys, dou
                     int32_t *rg_off, int32_t *rg_idx);
 /* FF atom types of the file: (anum, exact charge) -> id in first-seen order (src/mol.ml:280-293, 456-469) */
 int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum, double *type_q);
+/* lds --less-charges (src/lds.ml:1887-1894, src/mol.ml:256-260, src/utls.ml:127-132): every partial charge of the
+ * file rounded to two decimals (away from zero), then the FF types re-assigned: fewer (anum, q) types, fewer maps */
+int mmo_molfile_reduce_charges(mmo_molfile *f);
 /* the text mol2pqrs writes (values through %g) */
 int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path);
 /* molecule k as a device-resident ligand handle; centered != 0 applies Mol.translate_to lig V3.origin (lds.ml:44-52) */

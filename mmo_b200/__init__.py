@@ -631,6 +631,10 @@ class MolFile:
         _ck(lib().mmo_molfile_types(self.h, C.byref(n), ta.ctypes.data_as(_ip), tq.ctypes.data_as(_dp)))
         return ta, tq
 
+    def reduce_charges(self):
+        """lds --less-charges (lds.ml:1887-1894): charges to two decimals, FF types re-assigned"""
+        _ck(lib().mmo_molfile_reduce_charges(self.h))
+
     def write_pqrs(self, path):
         _ck(lib().mmo_molfile_write_pqrs(self.h, os.fsencode(path)))
 

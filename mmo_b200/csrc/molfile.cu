@@ -376,6 +376,16 @@ int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum
     return MMO_OK;
 }
 
+// lds --less-charges (src/lds.ml:1887-1894): Mol.reduce_partial_charges_precision on every ligand (src/mol.ml:256-260,
+// Utls.reduce_precision src/utls.ml:127-132: two decimals, rounded away from zero), BEFORE the FF types are assigned
+int mmo_molfile_reduce_charges(mmo_molfile *f) {
+    MMO_REQUIRE(f != nullptr, "mmo_molfile_reduce_charges: null pointer");
+    for (Molecule &m : f->mols)
+        for (double &q : m.q) q = (double)(long long)(q * 100.0 + (q >= 0.0 ? 0.5 : -0.5)) / 100.0;
+    f->assign_types();
+    return MMO_OK;
+}
+
 int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path) {
     MMO_REQUIRE(f && path, "mmo_molfile_write_pqrs: null pointer");
     FILE *o = fopen(path, "w");

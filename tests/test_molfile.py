@@ -198,3 +198,17 @@ def test_reference_pqrs_center_script_agrees(name):
     for i in range(m.n):                         # the script's plain left-to-right sums
         sx += m.xs[i]; sy += m.ys[i]; sz += m.zs[i]
     assert "%g %g %g" % (sx / m.n, sy / m.n, sz / m.n) == want[1]
+
+
+def test_less_charges_rounds_away_from_zero_and_merges_types():
+    """lds --less-charges (lds.ml:1887-1894; Utls.reduce_precision, utls.ml:127-132)"""
+    f = mmo_b200.MolFile(os.path.join(G, "ligdecs.pqrs"), kind="ligand_pqrs")
+    before = f.mol(0)
+    ta0, tq0 = f.types()
+    f.reduce_charges()
+    after = f.mol(0)
+    want = np.array([float(int(q * 100.0 + (0.5 if q >= 0.0 else -0.5))) / 100.0 for q in before.q])
+    assert np.array_equal(after.q, want) and np.array_equal(after.xs, before.xs)
+    ta1, tq1 = f.types()
+    assert len(ta1) <= len(ta0) and len(set(zip(ta1.tolist(), tq1.tolist()))) == len(ta1)
+    assert all(tq1[t] == q and ta1[t] == a for t, q, a in zip(after.typ, after.q, after.anum))

@@ -2,7 +2,7 @@
  * of libmmo_b200.so: the reference's flag spellings (src/lds.ml:1691-1734), every (ligand, start) pair one GPU chain.
  *
  *   lds_mc -lig L.{mol2,pqrs} -rec R.pqrs -roi ROI.bild -steps <int>[k|M] {--intra-NB | --no-E-intra}
- *          [-s seed] [-starts n] [-T kelvin] [--hard-ROI] [--no-flip] [--rigid-ligand] [--no-interp [-ff BrL|Bst]] [-dev i]
+ *          [-s seed] [-starts n] [-T kelvin] [--hard-ROI] [--no-flip] [--rigid-ligand] [--no-interp [-ff BrL|Bst]] [--less-charges] [-dev i]
  *
  *   preprocess_protein    src/lds.ml:20-41     receptor into a positive-octant box with a 36 A margin, ROI follows
  *   steps_of_string       src/lds.ml:558-570   10k, 2M
@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
     const char *lig_fn = NULL, *rec_fn = NULL, *roi_fn = NULL, *ff = "Bst";
     long n_steps = -1;
     long long seed = 0;
-    int have_seed = 0, starts = 1, hard_roi = 0, no_flip = 0, tweak_rbonds = 1, intra_nb = 0, no_e_intra = 0, no_interp = 0, dev = 0, clash_check = 0;
+    int have_seed = 0, starts = 1, hard_roi = 0, no_flip = 0, tweak_rbonds = 1, intra_nb = 0, no_e_intra = 0, no_interp = 0, dev = 0, clash_check = 0, less_charges = 0;
     double temp = 293.15;                                       /* Const.room_temp_K */
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-lig") && i + 1 < argc) lig_fn = argv[++i];
@@ -81,6 +81,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--no-E-intra")) no_e_intra = 1;
         else if (!strcmp(argv[i], "--no-interp")) no_interp = 1;
         else if (!strcmp(argv[i], "--clash-check")) clash_check = 1;
+        else if (!strcmp(argv[i], "--less-charges")) less_charges = 1;
         else if (!strcmp(argv[i], "--intra-QM") || !strcmp(argv[i], "--intra-UFF") || !strcmp(argv[i], "--intra-MMFF") ||
                  !strcmp(argv[i], "--no-vdW-clash")) {
             fprintf(stderr, "lds_mc: %s needs rdkit / torchani: outside this build (use --intra-NB or --no-E-intra)\n", argv[i]);
@@ -108,6 +109,7 @@ int main(int argc, char **argv) {
     CK(mmo_molfile_read_pqrs(rec_fn, 1, &rf));
     if (ends_with(lig_fn, ".mol2")) CK(mmo_molfile_read_mol2(lig_fn, &lf));
     else CK(mmo_molfile_read_pqrs(lig_fn, 0, &lf));
+    if (less_charges) CK(mmo_molfile_reduce_charges(lf));     /* lds.ml:1887-1894, before the FF types are used */
     int32_t n_ligs = 0, P = 0;
     CK(mmo_molfile_count(lf, &n_ligs, NULL));
     if (n_ligs < 1) { fprintf(stderr, "lds_mc: no usable ligand in %s\n", lig_fn); return 1; }
