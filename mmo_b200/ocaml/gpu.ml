@@ -65,6 +65,24 @@ external scan :
   float array -> float -> float array -> float -> int -> float array * float * int
   = "mmo_ml_scan_bc" "mmo_ml_scan"
 
+(* N4: Lds.protein_desolv roi grid prot_bst prot_solvent_shell prot (lds.ml:204-236).
+   rec, protein first-solvent-shell mask, (roi x y z r) -> device-resident contributions *)
+type desolv
+external first_solvent_shell :
+  float array -> float array -> float array -> float array -> float -> int -> int -> int -> mask
+  = "mmo_ml_first_solvent_shell_bc" "mmo_ml_first_solvent_shell"
+external desolv_protein : receptor -> mask -> float array -> desolv = "mmo_ml_desolv_protein"
+(* Lds.desolvation_penalty (lds.ml:239-267) of one ligand conformer: (prot, lig) *)
+external desolv_penalty : desolv -> ligand -> float array -> float array -> float array -> float * float
+  = "mmo_ml_desolv_penalty"
+
+(* Lds.place_ligand_in_ROI (lds.ml:308-345): receptor xs ys zs anums, centred ligand, (roi x y z r), seed, starts,
+   clash_check -> flat rotations (9 per start), flat positions (3 per start) *)
+external place_ligand_in_roi :
+  float array -> float array -> float array -> int array -> ligand -> float array -> int -> int -> bool ->
+  float array * float array
+  = "mmo_ml_place_ligand_in_roi_bc" "mmo_ml_place_ligand_in_roi"
+
 (* ---- drop-in closures ------------------------------------------------------------------ *)
 
 let ligand_create (m: Mol.t): ligand =
@@ -88,3 +106,7 @@ let ene_inter_interp grid_h lig_h (lig': Mol.t): float =
 (* Mol.ene_intra_UFFNB_brute (mol.ml:881-903) *)
 let ene_intra lig_h (lig': Mol.t): float =
   intra_nb lig_h lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs
+
+(* Lds.desolvation_penalty grid prot_desolv_contribs prot_solvent_shell prot lig (lds.ml:239-267) *)
+let desolvation_penalty desolv_h lig_h (lig': Mol.t): float * float =
+  desolv_penalty desolv_h lig_h lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs

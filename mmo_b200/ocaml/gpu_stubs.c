@@ -25,10 +25,12 @@ HANDLE(rec, mmo_receptor, mmo_receptor_destroy)
 HANDLE(lig, mmo_ligand, mmo_ligand_destroy)
 HANDLE(grid, mmo_grid, mmo_grid_destroy)
 HANDLE(mask, mmo_mask, mmo_mask_destroy)
+HANDLE(desolv, mmo_desolv, mmo_desolv_destroy)
 #define Rec_val(v) (*(mmo_receptor **)Data_custom_val(v))
 #define Lig_val(v) (*(mmo_ligand **)Data_custom_val(v))
 #define Grid_val(v) (*(mmo_grid **)Data_custom_val(v))
 #define Mask_val(v) (*(mmo_mask **)Data_custom_val(v))
+#define Desolv_val(v) (*(mmo_desolv **)Data_custom_val(v))
 
 /* OCaml float array = flat unboxed doubles */
 #define DARR(v) ((const double *)(v))
@@ -202,3 +204,58 @@ CAMLprim value mmo_ml_scan(value rec_opt, value grid_opt, value lig, value mask_
   CAMLreturn(res);
 }
 CAMLprim value mmo_ml_scan_bc(value *a, int n) { (void)n; return mmo_ml_scan(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]); }
+
+/* ---- N4: desolvation sums (lds.ml:204-267) ---------------------------------------------------- */
+CAMLprim value mmo_ml_first_solvent_shell(value xs, value ys, value zs, value radii, value step, value xd, value yd, value zd) {
+  CAMLparam5(xs, ys, zs, radii, step); CAMLxparam3(xd, yd, zd);
+  int32_t dims[3] = {Int_val(xd), Int_val(yd), Int_val(zd)};
+  mmo_mask *h = NULL;
+  check(mmo_mask_first_solvent_shell((int32_t)DLEN(xs), DARR(xs), DARR(ys), DARR(zs), DARR(radii), Double_val(step), dims, NULL, &h));
+  CAMLreturn(box_mask(h));
+}
+CAMLprim value mmo_ml_first_solvent_shell_bc(value *a, int n) { (void)n; return mmo_ml_first_solvent_shell(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); }
+
+/* the mask value must stay reachable from OCaml for as long as the desolv handle is used (the library keeps a pointer) */
+CAMLprim value mmo_ml_desolv_protein(value rec, value shell, value roi) {
+  CAMLparam3(rec, shell, roi);
+  double c[3] = {Double_flat_field(roi, 0), Double_flat_field(roi, 1), Double_flat_field(roi, 2)};
+  mmo_desolv *h = NULL;
+  check(mmo_desolv_protein(Rec_val(rec), Mask_val(shell), c, Double_flat_field(roi, 3), NULL, &h));
+  CAMLreturn(box_desolv(h));
+}
+
+CAMLprim value mmo_ml_desolv_penalty(value d, value lig, value xs, value ys, value zs) {
+  CAMLparam5(d, lig, xs, ys, zs);
+  CAMLlocal1(res);
+  double prot, ligp;
+  check(mmo_desolv_penalty_coords(Desolv_val(d), Lig_val(lig), 1, DARR(xs), DARR(ys), DARR(zs), &prot, &ligp));
+  res = caml_alloc_tuple(2);
+  Store_field(res, 0, caml_copy_double(prot));
+  Store_field(res, 1, caml_copy_double(ligp));
+  CAMLreturn(res);
+}
+
+/* Lds.place_ligand_in_ROI (lds.ml:308-345) */
+CAMLprim value mmo_ml_place_ligand_in_roi(value xs, value ys, value zs, value anums, value lig, value roi, value seed,
+                                          value starts, value clash) {
+  CAMLparam5(xs, ys, zs, anums, lig); CAMLxparam4(roi, seed, starts, clash);
+  CAMLlocal3(res, rots, poss);
+  int32_t n = Int_val(starts), trials = 0;
+  int32_t *an = ints_of(anums);
+  double c[3] = {Double_flat_field(roi, 0), Double_flat_field(roi, 1), Double_flat_field(roi, 2)};
+  double *r9 = (double *)malloc(sizeof(double) * 12 * (size_t)(n > 0 ? n : 1)), *p3 = r9 + 9 * (size_t)(n > 0 ? n : 1);
+  int rc = mmo_place_ligand_in_roi((int32_t)DLEN(xs), DARR(xs), DARR(ys), DARR(zs), an, Lig_val(lig), c, Double_flat_field(roi, 3),
+                                   (uint64_t)Long_val(seed), n, Bool_val(clash), r9, p3, &trials);
+  free(an);
+  if (rc != MMO_OK) { free(r9); check(rc); }
+  rots = caml_alloc_float_array(9 * (mlsize_t)n);
+  poss = caml_alloc_float_array(3 * (mlsize_t)n);
+  for (int i = 0; i < 9 * n; i++) Store_double_flat_field(rots, i, r9[i]);
+  for (int i = 0; i < 3 * n; i++) Store_double_flat_field(poss, i, p3[i]);
+  free(r9);
+  res = caml_alloc_tuple(2);
+  Store_field(res, 0, rots);
+  Store_field(res, 1, poss);
+  CAMLreturn(res);
+}
+CAMLprim value mmo_ml_place_ligand_in_roi_bc(value *a, int n) { (void)n; return mmo_ml_place_ligand_in_roi(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); }
