@@ -16,7 +16,7 @@
 //   pair    = packed fp32 (FFMA2 / FMUL2 / FADD2 of sm_100a): one packed instruction serves two
 //             receptor atoms of the list; r^2 = |x'|^2 + |l'|^2 - 2 x'.l' (l' = ligand atom - c, short
 //             vectors: no harmful cancellation while rho is small, else the difference form is used);
-//             13 packed + 4 FMNMX + 2 MUFU.RSQ per two pairs.  The list is consumed 4 atoms at a time
+//             12 packed + 2 FFMA.SAT + 2 FMNMX + 2 MUFU.RSQ per two pairs.  The list is consumed 4 atoms at a time
 //             (7 LDS.128 with a warp-uniform address) for both poses of the thread = 4 independent packed chains
 //   sum     = fp32 inside a chain for kSumEvery steps, then F2F + DADD into per-pose fp64 accumulators
 //
@@ -102,15 +102,12 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
     asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
     return y;
 }
-#ifndef MMO_SAT_WEIGHT
-#define MMO_SAT_WEIGHT 1
-#endif
 
 // Two receptor atoms (the halves of the packed operands) against one ligand atom of one pose.
 //   EXPAND : r^2 = (|x'|^2 + |l'|^2) - 2 x'.l'   (m2 = -2 l', l2 = |l'|^2)         4 packed ops
 //   else   : r^2 = |x' - l'|^2                   (m2 = -l')                        6 packed ops
-//   SHIFTED: acc += (144 - r^2)^2 * e, with A_iA_j, B_iB_j and q_iq_j pre-divided by 144^2, so that the
-//            weight is FF.shift_12A (FF.ml:17-20) and exactly 0 from 12 A on (r^2 is clamped to [H, 144])
+//   SHIFTED: acc += sat(1 - r^2/144)^2 * e: FF.shift_12A (FF.ml:17-20), exactly 0 from 12 A on through the saturation,
+//            so r^2 is only clamped from below (at H)
 //   GLOBAL : acc += e
 // e = (A_iA_j s^3 - B_iB_j) s^3 + q_iq_j / r with s = 1/r^2   (= d_ij (p6^2 - 2 p6) + 83.0159 q_i q_j / r)
 template <int VARIANT, bool EXPAND>
@@ -125,26 +122,17 @@ __device__ __forceinline__ float2 pair2(float2 X, float2 Y, float2 Z, float2 S, 
     }
     r2_out = r2;
     float2 r2c;                                      // close contacts are finished in fp64 elsewhere
-    if (VARIANT == MMO_VARIANT_SHIFTED && !MMO_SAT_WEIGHT) {
-        r2c.x = fminf(fmaxf(r2.x, H), 144.0f);
-        r2c.y = fminf(fmaxf(r2.y, H), 144.0f);
-    } else {
-        r2c.x = fmaxf(r2.x, H);
-        r2c.y = fmaxf(r2.y, H);
-    }
+    r2c.x = fmaxf(r2.x, H);                          // no upper clamp: the shift weight saturates at 0
+    r2c.y = fmaxf(r2.y, H);
     const float2 rinv = make_float2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
     const float2 s = __fmul2_rn(rinv, rinv);
     const float2 s3 = __fmul2_rn(__fmul2_rn(s, s), s);
     const float2 v = __ffma2_rn(AA, s3, nBB);
     const float2 e = __ffma2_rn(v, s3, __fmul2_rn(QQ, rinv));
     if (VARIANT == MMO_VARIANT_SHIFTED) {
-#if MMO_SAT_WEIGHT
         // FF.shift_12A as two scalar saturating FMAs: sat(1 - r^2/144) is exactly 0 from 12 A on, which makes the
         // upper clamp of r^2 (two FMNMX) unnecessary; same FMA-pipe time as one packed FMA
         const float2 up = make_float2(fma_sat(r2c.x, -1.0f / 144.0f, 1.0f), fma_sat(r2c.y, -1.0f / 144.0f, 1.0f));
-#else
-        const float2 up = __ffma2_rn(r2c, bc2(-1.0f), bc2(144.0f));
-#endif
         return __ffma2_rn(__fmul2_rn(up, up), e, acc);
     } else {
         return __fadd2_rn(acc, e);
@@ -232,8 +220,6 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
         s_elt[tile_atoms + tid] = 0;
     }
     __syncthreads();
-    // SHIFTED: the weight (144 - r^2)^2 / 144^2 is split between the pair and the list entries
-    const float wscale = (VARIANT == MMO_VARIANT_SHIFTED && !MMO_SAT_WEIGHT) ? 1.0f / 20736.0f : 1.0f;
     const int n_chunks = a.n_fast / LJ;
     const unsigned long long n_groups = (unsigned long long)((n_poses + 32 * PPT - 1) / (32 * PPT));
     const unsigned long long n_units = n_groups * (unsigned long long)n_split;
@@ -349,7 +335,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 }
                 if (lane < 4) s_near[ng + lane] = (uint8_t)tile_groups;        // pad with the dummy group
                 __syncwarp();
-                const float qjs = lp.z * wscale, Ajs = lp.x * wscale, nBjs = -lp.y * wscale;
+                const float qjs = lp.z, Ajs = lp.x, nBjs = -lp.y;
                 // ---- level 2: the atoms of four near groups per step, two per lane (independent loads and
                 //      tests); survivors are compacted into the warp's list, which is consumed whenever it
                 //      cannot take another step ----
@@ -460,68 +446,62 @@ __device__ __forceinline__ void run_list_items(const float *s_l, int n, int n4, 
                                                const float (&m2z)[PPT], const float (&l2)[PPT], float H,
                                                double (&EA)[PPT], double (&EB)[PPT], double (&EQ)[PPT],
                                                float (&rmin)[PPT], unsigned long long (&n_in)[PPT]) {
-    float2 fA[PPT], fB[PPT], fQ[PPT];
-#pragma unroll
-    for (int h = 0; h < PPT; h++) fA[h] = fB[h] = fQ[h] = make_float2(0.f, 0.f);
-    int since = 0;
+    // blocks of kItemSumEvery steps in fp32, then F2F + DADD (nested loops: no per-step counter)
 #pragma unroll 1
-    for (int k = 0; k < n4; k += 4) {
-        const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
-        const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
-        const float4 Q = *(const float4 *)(s_l + 4 * LIST_CAP + k), A = *(const float4 *)(s_l + 5 * LIST_CAP + k);
-        const float4 B = *(const float4 *)(s_l + 6 * LIST_CAP + k);
+    for (int k0 = 0; k0 < n4; k0 += 4 * kItemSumEvery) {
+        const int kend = min(n4, k0 + 4 * kItemSumEvery);
+        float2 fA[PPT], fB[PPT], fQ[PPT];
 #pragma unroll
-        for (int h = 0; h < PPT; h++) {
-#pragma unroll
-            for (int pk = 0; pk < 2; pk++) {
-                const float2 x2 = pk ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
-                const float2 y2 = pk ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
-                const float2 z2 = pk ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
-                const float2 s2 = pk ? make_float2(S.z, S.w) : make_float2(S.x, S.y);
-                const float2 q2 = pk ? make_float2(Q.z, Q.w) : make_float2(Q.x, Q.y);
-                const float2 a2 = pk ? make_float2(A.z, A.w) : make_float2(A.x, A.y);
-                const float2 b2 = pk ? make_float2(B.z, B.w) : make_float2(B.x, B.y);
-                float2 r2;
-                if (EXPAND) {
-                    r2 = __ffma2_rn(x2, bc2(m2x[h]), __ffma2_rn(y2, bc2(m2y[h]), __ffma2_rn(z2, bc2(m2z[h]), __fadd2_rn(s2, bc2(l2[h])))));
-                } else {
-                    const float2 dx = __fadd2_rn(x2, bc2(m2x[h])), dy = __fadd2_rn(y2, bc2(m2y[h])), dz = __fadd2_rn(z2, bc2(m2z[h]));
-                    r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                }
-                rmin[h] = fminf(rmin[h], fminf(r2.x, r2.y));
-                float2 r2c;
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    r2c.x = fminf(fmaxf(r2.x, H), 144.0f);
-                    r2c.y = fminf(fmaxf(r2.y, H), 144.0f);
-                } else {
-                    r2c.x = fmaxf(r2.x, H);
-                    r2c.y = fmaxf(r2.y, H);
-                }
-                const float2 rinv = make_float2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
-                const float2 s = __fmul2_rn(rinv, rinv);
-                const float2 s3 = __fmul2_rn(__fmul2_rn(s, s), s);
-                float2 ws3 = s3, wr = rinv;
-                if (VARIANT == MMO_VARIANT_SHIFTED) {
-                    const float2 up = __ffma2_rn(r2c, bc2(-1.0f), bc2(144.0f));
-                    const float2 w = __fmul2_rn(up, up);
-                    ws3 = __fmul2_rn(w, s3);
-                    wr = __fmul2_rn(w, rinv);
-                }
-                fB[h] = __ffma2_rn(ws3, b2, fB[h]);
-                fA[h] = __ffma2_rn(__fmul2_rn(ws3, s3), a2, fA[h]);
-                fQ[h] = __ffma2_rn(wr, q2, fQ[h]);
-                if (STATS) n_in[h] += (r2.x < 144.0f && k + 2 * pk < n) + (r2.y < 144.0f && k + 2 * pk + 1 < n);
-            }
-        }
-        if (++since == kItemSumEvery || k + 4 >= n4) {
+        for (int h = 0; h < PPT; h++) fA[h] = fB[h] = fQ[h] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int k = k0; k < kend; k += 4) {
+            const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
+            const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
+            const float4 Q = *(const float4 *)(s_l + 4 * LIST_CAP + k), A = *(const float4 *)(s_l + 5 * LIST_CAP + k);
+            const float4 B = *(const float4 *)(s_l + 6 * LIST_CAP + k);
 #pragma unroll
             for (int h = 0; h < PPT; h++) {
-                EA[h] += (double)(fA[h].x + fA[h].y);
-                EB[h] += (double)(fB[h].x + fB[h].y);
-                EQ[h] += (double)(fQ[h].x + fQ[h].y);
-                fA[h] = fB[h] = fQ[h] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int pk = 0; pk < 2; pk++) {
+                    const float2 x2 = pk ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
+                    const float2 y2 = pk ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+                    const float2 z2 = pk ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
+                    const float2 s2 = pk ? make_float2(S.z, S.w) : make_float2(S.x, S.y);
+                    const float2 q2 = pk ? make_float2(Q.z, Q.w) : make_float2(Q.x, Q.y);
+                    const float2 a2 = pk ? make_float2(A.z, A.w) : make_float2(A.x, A.y);
+                    const float2 b2 = pk ? make_float2(B.z, B.w) : make_float2(B.x, B.y);
+                    float2 r2;
+                    if (EXPAND) {
+                        r2 = __ffma2_rn(x2, bc2(m2x[h]), __ffma2_rn(y2, bc2(m2y[h]), __ffma2_rn(z2, bc2(m2z[h]), __fadd2_rn(s2, bc2(l2[h])))));
+                    } else {
+                        const float2 dx = __fadd2_rn(x2, bc2(m2x[h])), dy = __fadd2_rn(y2, bc2(m2y[h])), dz = __fadd2_rn(z2, bc2(m2z[h]));
+                        r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                    }
+                    rmin[h] = fminf(rmin[h], fminf(r2.x, r2.y));
+                    const float2 r2c = make_float2(fmaxf(r2.x, H), fmaxf(r2.y, H));      // no upper clamp: the weight saturates
+                    const float2 rinv = make_float2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
+                    const float2 s = __fmul2_rn(rinv, rinv);
+                    const float2 s3 = __fmul2_rn(__fmul2_rn(s, s), s);
+                    float2 ws3 = s3, wr = rinv;
+                    if (VARIANT == MMO_VARIANT_SHIFTED) {
+                        // FF.shift_12A: sat(1 - r^2/144)^2, exactly 0 from 12 A on (see pair2)
+                        const float2 up = make_float2(fma_sat(r2c.x, -1.0f / 144.0f, 1.0f), fma_sat(r2c.y, -1.0f / 144.0f, 1.0f));
+                        const float2 w = __fmul2_rn(up, up);
+                        ws3 = __fmul2_rn(w, s3);
+                        wr = __fmul2_rn(w, rinv);
+                    }
+                    fB[h] = __ffma2_rn(ws3, b2, fB[h]);
+                    fA[h] = __ffma2_rn(__fmul2_rn(ws3, s3), a2, fA[h]);
+                    fQ[h] = __ffma2_rn(wr, q2, fQ[h]);
+                    if (STATS) n_in[h] += (r2.x < 144.0f && k + 2 * pk < n) + (r2.y < 144.0f && k + 2 * pk + 1 < n);
+                }
             }
-            since = 0;
+        }
+#pragma unroll
+        for (int h = 0; h < PPT; h++) {
+            EA[h] += (double)(fA[h].x + fA[h].y);
+            EB[h] += (double)(fB[h].x + fB[h].y);
+            EQ[h] += (double)(fQ[h].x + fQ[h].y);
         }
     }
 }
@@ -594,7 +574,6 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
         s_elt[tile_atoms + tid] = 0;
     }
     __syncthreads();
-    const float wscale = VARIANT == MMO_VARIANT_SHIFTED ? 1.0f / 20736.0f : 1.0f;
     const unsigned long long n_near = a.n_items - *a.n_far;
     const unsigned long long n_units = (n_near + 32 * PPT - 1) / (32 * PPT);
     unsigned long long n_eval = 0, n_in_tot = 0;
@@ -684,7 +663,7 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
                     float *e = s_l + n + __popc(bma & lt_mask);
                     e[0 * LIST_CAP] = expand ? Xa : pa.x; e[1 * LIST_CAP] = expand ? Ya : pa.y; e[2 * LIST_CAP] = expand ? Za : pa.z;
                             e[3 * LIST_CAP] = Sa;
-                    e[4 * LIST_CAP] = pa.w * wscale; e[5 * LIST_CAP] = tab.x * wscale; e[6 * LIST_CAP] = tab.y * wscale;
+                    e[4 * LIST_CAP] = pa.w; e[5 * LIST_CAP] = tab.x; e[6 * LIST_CAP] = tab.y;
                 }
                 n += __popc(bma);
                 if (nb_) {
@@ -692,7 +671,7 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
                     float *e = s_l + n + __popc(bmb & lt_mask);
                     e[0 * LIST_CAP] = expand ? Xb : pb.x; e[1 * LIST_CAP] = expand ? Yb : pb.y; e[2 * LIST_CAP] = expand ? Zb : pb.z;
                             e[3 * LIST_CAP] = Sb;
-                    e[4 * LIST_CAP] = pb.w * wscale; e[5 * LIST_CAP] = tab.x * wscale; e[6 * LIST_CAP] = tab.y * wscale;
+                    e[4 * LIST_CAP] = pb.w; e[5 * LIST_CAP] = tab.x; e[6 * LIST_CAP] = tab.y;
                 }
                 n += __popc(bmb);
                 if (n <= LIST_CAP - 64 && i + 4 < ng) continue;
