@@ -731,7 +731,72 @@ struct FixArgs {
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
 
-// ITEMS: part = per-item energies [pose][n_split = n_fast], flags = per-item bytes (direct_items_kernel);
+// The close-contact correction of ONE ligand atom at (x, y, z) (original atom index j): sum over the receptor atoms
+// with r^2 < H of  w(r) e(r) - w(sqrt H) e(sqrt H), found through the atom's voxel list.
+template <int VARIANT, bool STATS>
+__device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x, double y, double z, int j,
+                                                     unsigned long long &n_fix) {
+    double corr = 0.0;
+    const double fx = (x - a.vox_lo[0]) * a.vox_inv, fy = (y - a.vox_lo[1]) * a.vox_inv, fz = (z - a.vox_lo[2]) * a.vox_inv;
+    if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0)) return corr;
+    const int vi = (int)fx, vj = (int)fy, vk = (int)fz;
+    if (vi >= a.vox_dim[0] || vj >= a.vox_dim[1] || vk >= a.vox_dim[2]) return corr;
+    const size_t v = (size_t)vi + (size_t)vj * a.vox_dim[0] + (size_t)vk * a.vox_dim[0] * a.vox_dim[1];
+    const int k0 = __ldg(a.vox_off + v), k1 = __ldg(a.vox_off + v + 1);
+    if (k0 == k1) return corr;
+    const double qj = kElecWeight * __ldg(a.lq + j);
+    const int ej = __ldg(a.lelt + j);
+    const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
+    const float Hf = (float)a.H + MMO_FIX_MARGIN;     // fp32 r^2 of coordinates below ~200 A: error < 1e-3 A^2
+    // Two phases per window of 64 candidates, so that a warp whose lanes sit in different voxels pays
+    // max(candidates) cheap tests + max(close pairs) fp64 evaluations, not their product: (1) the fp32 pre-test
+    // (coordinates relative to the voxel grid corner, error << the margin) marks the survivors in a
+    // 64-bit mask, (2) the survivors are evaluated in double, in list order.
+    for (int kw = k0; kw < k1; kw += 64) {
+        unsigned long long pass = 0ull;
+        const int kn = min(64, k1 - kw);
+#pragma unroll kFixUnroll
+        for (int b = 0; b < kn; b++) {
+            const float4 r4 = __ldg(a.pxyz32 + __ldg(a.vox_idx + kw + b));
+            const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
+            if (fdx * fdx + fdy * fdy + fdz * fdz < Hf) pass |= 1ull << b;
+        }
+        while (pass != 0ull) {
+            const int b = __ffsll((long long)pass) - 1;
+            pass &= pass - 1ull;
+            const int i = __ldg(a.vox_idx + kw + b);
+            const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
+            const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
+            const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 < a.H) {
+                const int tt = __ldg(a.pelt + i) * kEltTab + ej;
+                const double qq = r23.y * qj;
+                const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
+                // 1/r: MUFU.RSQ in fp32 (relative error < 2e-7), one Newton step in double (-> < 1e-13)
+                const double y0 = (double)rsqrtf((float)r2c);
+                const double rinv = y0 * (1.5 - (0.5 * r2c) * (y0 * y0));
+                const double t2 = __ldg(a.xx + tt) * (rinv * rinv);  // (x_ij / r)^2
+                const double p6 = t2 * t2 * t2;
+                const double ee = qq * rinv + __ldg(a.dij + tt) * (p6 * p6 - 2.0 * p6);
+                const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
+                double d;
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    const double u = 1.0 - r2c * (1.0 / 144.0);
+                    d = (u * u) * ee - a.wH * eH;                      // the fast path clamped r^2 in the weight too
+                } else {
+                    d = ee - eH;
+                }
+                corr += d;
+                if (STATS) n_fix++;
+            }
+        }
+    }
+    return corr;
+}
+
+// ITEMS: part = per-item energies [pose][n_split = n_fast], corrections already added by item_fix_kernel: called with
+//        n_chunks = 0, the kernel only sums the items of a pose in atom order;
 // else  : part = per-split sums [n_split][pose], flags = per-(tile, chunk) bytes (direct_fp32_kernel)
 template <int VARIANT, bool STATS, bool ITEMS>
 __global__ void __launch_bounds__(128, kFixBlocksPerSM)
@@ -753,12 +818,7 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
     for (int c = 0; c < n_chunks; c++) {
         // atoms of chunk c (fast-path order) for which the fast kernel saw a pair below H (any tile)
         unsigned bits = 0u;
-        if (ITEMS) {
-#pragma unroll
-            for (int jj = 0; jj < kFixLJ; jj++) bits |= (unsigned)(flags[p * n_split + c * kFixLJ + jj] & 1) << jj;
-        } else {
-            for (int t = 0; t < n_tiles; t++) bits |= flags[((int64_t)t * n_chunks + c) * n_poses + p];
-        }
+        for (int t = 0; t < n_tiles; t++) bits |= flags[((int64_t)t * n_chunks + c) * n_poses + p];
         while (bits != 0u) {
             const int jj = __ffs(bits) - 1;
             bits &= bits - 1u;
@@ -782,65 +842,51 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
                 y = __dadd_rn(rot_row(s_P[3][tx], s_P[4][tx], s_P[5][tx], ax, ay, az), s_P[10][tx]);
                 z = __dadd_rn(rot_row(s_P[6][tx], s_P[7][tx], s_P[8][tx], ax, ay, az), s_P[11][tx]);
             }
-            const double fx = (x - a.vox_lo[0]) * a.vox_inv, fy = (y - a.vox_lo[1]) * a.vox_inv, fz = (z - a.vox_lo[2]) * a.vox_inv;
-            if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0)) continue;
-            const int vi = (int)fx, vj = (int)fy, vk = (int)fz;
-            if (vi >= a.vox_dim[0] || vj >= a.vox_dim[1] || vk >= a.vox_dim[2]) continue;
-            const size_t v = (size_t)vi + (size_t)vj * a.vox_dim[0] + (size_t)vk * a.vox_dim[0] * a.vox_dim[1];
-            const int k0 = __ldg(a.vox_off + v), k1 = __ldg(a.vox_off + v + 1);
-            if (k0 == k1) continue;
-            const double qj = kElecWeight * __ldg(a.lq + j);
-            const int ej = __ldg(a.lelt + j);
-            const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
-            const float Hf = (float)a.H + MMO_FIX_MARGIN;     // fp32 r^2 of coordinates below ~200 A: error < 1e-3 A^2
-            // Two phases per window of 64 candidates, so that a warp whose lanes sit in different voxels pays
-            // max(candidates) cheap tests + max(close pairs) fp64 evaluations, not their product: (1) the fp32 pre-test
-            // (coordinates relative to the voxel grid corner, error << the margin) marks the survivors in a
-            // 64-bit mask, (2) the survivors are evaluated in double, in list order.
-            for (int kw = k0; kw < k1; kw += 64) {
-                unsigned long long pass = 0ull;
-                const int kn = min(64, k1 - kw);
-#pragma unroll kFixUnroll
-                for (int b = 0; b < kn; b++) {
-                    const float4 r4 = __ldg(a.pxyz32 + __ldg(a.vox_idx + kw + b));
-                    const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
-                    if (fdx * fdx + fdy * fdy + fdz * fdz < Hf) pass |= 1ull << b;
-                }
-                while (pass != 0ull) {
-                    const int b = __ffsll((long long)pass) - 1;
-                    pass &= pass - 1ull;
-                    const int i = __ldg(a.vox_idx + kw + b);
-                    const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
-                    const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
-                    const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
-                    const double r2 = dx * dx + dy * dy + dz * dz;
-                    if (r2 < a.H) {
-                        const int tt = __ldg(a.pelt + i) * kEltTab + ej;
-                        const double qq = r23.y * qj;
-                        const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
-                        // 1/r: MUFU.RSQ in fp32 (relative error < 2e-7), one Newton step in double (-> < 1e-13)
-                        const double y0 = (double)rsqrtf((float)r2c);
-                        const double rinv = y0 * (1.5 - (0.5 * r2c) * (y0 * y0));
-                        const double t2 = __ldg(a.xx + tt) * (rinv * rinv);  // (x_ij / r)^2
-                        const double p6 = t2 * t2 * t2;
-                        const double ee = qq * rinv + __ldg(a.dij + tt) * (p6 * p6 - 2.0 * p6);
-                        const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
-                        double d;
-                        if (VARIANT == MMO_VARIANT_SHIFTED) {
-                            const double u = 1.0 - r2c * (1.0 / 144.0);
-                            d = (u * u) * ee - a.wH * eH;                      // the fast path clamped r^2 in the weight too
-                        } else {
-                            d = ee - eH;
-                        }
-                        corr += d;
-                        if (STATS) n_fix++;
-                    }
-                }
-            }
+            corr += close_contact_corr<VARIANT, STATS>(a, x, y, z, j, n_fix);
         }
     }
     out[p] = e + corr;
     if (STATS) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, n_flag); }
+}
+
+// Item mode: the same correction with thread = ITEM in cell-sorted order (the order direct_items_kernel works in).  The
+// lanes of a warp then sit in neighbouring voxels: their candidate lists are the same few cache lines and about equally
+// long, which a warp of unrelated conformers (thread = pose) has neither of.  The correction is added to the item's
+// energy; hard_fix_kernel<ITEMS> (called with n_chunks = 0) then only sums the items of a pose in atom order.
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(128, kFixBlocksPerSM)
+item_fix_kernel(FixArgs a, PoseSrc src, int n_fast, const uint32_t *__restrict__ perm,
+                const unsigned long long *__restrict__ n_far, unsigned long long n_items,
+                const uint8_t *__restrict__ f_item, double *__restrict__ e_item) {
+    __shared__ double s_P[12][128];
+    const int tx = threadIdx.x;
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + tx;
+    if (r >= n_items - *n_far) return;                      // items beyond the lattice are sorted last: energy exactly 0
+    const uint32_t item = __ldg(perm + r);
+    if (!f_item[item]) return;
+    const int64_t p = item / (uint32_t)n_fast;
+    const int j = __ldg(a.forder + (int)(item - (uint32_t)p * (uint32_t)n_fast));
+    double x, y, z;
+    if (src.kind == 1) {
+        x = src.xs[p * a.L + j]; y = src.ys[p * a.L + j]; z = src.zs[p * a.L + j];
+    } else {
+        {
+            PoseRT P;
+            load_pose_rt(src, p, P);
+#pragma unroll
+            for (int q = 0; q < 9; q++) s_P[q][tx] = P.r[q];
+#pragma unroll
+            for (int q = 0; q < 3; q++) s_P[9 + q][tx] = P.t[q];
+        }
+        const double ax = __ldg(a.lx + j), ay = __ldg(a.ly + j), az = __ldg(a.lz + j);
+        x = __dadd_rn(rot_row(s_P[0][tx], s_P[1][tx], s_P[2][tx], ax, ay, az), s_P[9][tx]);
+        y = __dadd_rn(rot_row(s_P[3][tx], s_P[4][tx], s_P[5][tx], ax, ay, az), s_P[10][tx]);
+        z = __dadd_rn(rot_row(s_P[6][tx], s_P[7][tx], s_P[8][tx], ax, ay, az), s_P[11][tx]);
+    }
+    unsigned long long n_fix = 0;
+    const double corr = close_contact_corr<VARIANT, STATS>(a, x, y, z, j, n_fix);
+    e_item[item] += corr;
+    if (STATS) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, 1ull); }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -997,12 +1043,15 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
         }
     }
     KernelScope ks2(K_HARD_FIX);
+    // close contacts per item, in the sorted (spatially coherent) order; then the items of a pose are summed in atom order
+    const unsigned iblocks = (unsigned)((n_items + 127) / 128);
+    if (shifted && collect_stats) item_fix_kernel<MMO_VARIANT_SHIFTED, true><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
+    else if (shifted) item_fix_kernel<MMO_VARIANT_SHIFTED, false><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
+    else if (collect_stats) item_fix_kernel<MMO_VARIANT_GLOBAL, true><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
+    else item_fix_kernel<MMO_VARIANT_GLOBAL, false><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
+    MMO_LAUNCH_CHECK();
     const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
-    const int n_chunks = nf / LJ;
-    if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
-    else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
-    else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
-    else hard_fix_kernel<MMO_VARIANT_GLOBAL, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, n_chunks, d_out);
+    hard_fix_kernel<MMO_VARIANT_SHIFTED, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, 0, d_out);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }
