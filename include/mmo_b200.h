@@ -204,6 +204,13 @@ int mmo_mask_destroy(mmo_mask *mask);
 int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses,
                     const double *rot9, const double *trans3, uint8_t *out_flags);
 
+/* ---------------------------------------------------------------- N3: binding-site carve --- */
+/* scissors (src/scissors.ml:48-62): out_keep[i] = 1 for the protein atoms whose nearest ligand atom is within the
+ * cut-off (BST.nearest_neighbor: dist = sqrt(dist2), kept if dist <= cutoff; default 5 A around the ligand) */
+int mmo_carve_near_ligand(int32_t n_rec, const double *px, const double *py, const double *pz, int32_t n_lig,
+                          const double *lx, const double *ly, const double *lz, double cutoff, uint8_t *out_keep,
+                          int32_t *n_kept);
+
 /* ---------------------------------------------------------------- N4: desolvation sums ---- */
 /* Majeux, Scarsi and Caflisch (PROTEINS 2001) eq. (2), the rescoring terms next to the pair path.
  * Lds.protein_desolv roi grid prot_bst prot_solvent_shell prot (src/lds.ml:204-236): for every voxel of the protein's
@@ -353,6 +360,9 @@ int mmo_place_ligand_in_roi(int32_t n_rec, const double *px, const double *py, c
  * (disconnected atom, malformed block) are counted in n_skipped. */
 typedef struct mmo_molfile mmo_molfile;
 int mmo_molfile_read_mol2(const char *path, mmo_molfile **out);
+/* Mol2.read_one_from_file (src/mol2.ml:350-356) as `scissors` reads its two inputs: the first molecule only, atoms and
+ * bonds as written (lone pairs dropped), no graph analysis -- a protein is not one connected molecule */
+int mmo_molfile_read_mol2_atoms(const char *path, mmo_molfile **out);
 int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out);
 int mmo_molfile_count(const mmo_molfile *f, int32_t *n_mols, int32_t *n_skipped);
 int mmo_molfile_shape(const mmo_molfile *f, int32_t k, int32_t *n_atoms, int32_t *n_rbonds, int32_t *rg_total,

@@ -475,6 +475,26 @@ int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses
     return d2h_sync(out_flags, df.p, (size_t)n_poses);
 }
 
+// ------------------------------------------------------------------ N3: ligand-defined binding site (scissors)
+int mmo_carve_near_ligand(int32_t n_rec, const double *px, const double *py, const double *pz, int32_t n_lig,
+                          const double *lx, const double *ly, const double *lz, double cutoff, uint8_t *out_keep,
+                          int32_t *n_kept) {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(n_rec >= 0 && n_lig >= 0 && cutoff >= 0.0, "mmo_carve_near_ligand: bad sizes");
+    if (n_kept) *n_kept = 0;
+    if (n_rec == 0) return MMO_OK;
+    MMO_REQUIRE(px && py && pz && out_keep && (n_lig == 0 || (lx && ly && lz)), "mmo_carve_near_ligand: null buffer");
+    DevBuf<double> dpx, dpy, dpz, dlx, dly, dlz;
+    DevBuf<uint8_t> dk;
+    MMO_TRY(dpx.upload(px, (size_t)n_rec)); MMO_TRY(dpy.upload(py, (size_t)n_rec)); MMO_TRY(dpz.upload(pz, (size_t)n_rec));
+    MMO_TRY(dlx.upload(lx, (size_t)n_lig)); MMO_TRY(dly.upload(ly, (size_t)n_lig)); MMO_TRY(dlz.upload(lz, (size_t)n_lig));
+    MMO_TRY(dk.alloc((size_t)n_rec));
+    MMO_TRY(launch_carve(n_rec, dpx.p, dpy.p, dpz.p, n_lig, dlx.p, dly.p, dlz.p, cutoff, dk.p));
+    MMO_TRY(d2h_sync(out_keep, dk.p, (size_t)n_rec));
+    if (n_kept) for (int32_t i = 0; i < n_rec; i++) *n_kept += out_keep[i];
+    return MMO_OK;
+}
+
 // ------------------------------------------------------------------ N4: desolvation sums
 int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, const double roi_c[3], double roi_r,
                        double *out_contribs, mmo_desolv **out) {

@@ -229,6 +229,8 @@ int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d
                     const mmo_mask *m, bool set_bits = true);
 int launch_sphere_mask(double cx, double cy, double cz, double r, const mmo_mask *m);
 int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags);
+int launch_carve(int n_rec, const double *d_px, const double *d_py, const double *d_pz, int n_lig, const double *d_lx,
+                 const double *d_ly, const double *d_lz, double cutoff, uint8_t *d_keep);
 // desolv.cu (N4): Lds.protein_desolv / Lds.desolvation_penalty
 int launch_desolv_protein(const mmo_receptor *rec, const mmo_mask *shell, const double roi[4], double *d_contribs);
 int launch_desolv_penalty(const mmo_mask *shell, const double *d_contribs, const mmo_ligand *lig, const double *d_radii,

@@ -142,6 +142,37 @@ scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim,
     if (keep) frames[s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1))] = frame;
 }
 
+// scissors (src/scissors.ml:52-62): keep the protein atoms whose nearest ligand atom is not farther than the cut-off
+// (BST.nearest_neighbor -> dist = sqrt(dist2), kept if dist <= cutoff); thread = protein atom, ligand in shared memory
+__global__ void __launch_bounds__(256)
+carve_kernel(int n_rec, const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
+             int n_lig, const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
+             double cutoff, uint8_t *__restrict__ keep) {
+    __shared__ double s_x[256], s_y[256], s_z[256];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double x = i < n_rec ? px[i] : 0.0, y = i < n_rec ? py[i] : 0.0, z = i < n_rec ? pz[i] : 0.0;
+    double best = INFINITY;
+    for (int j0 = 0; j0 < n_lig; j0 += 256) {
+        __syncthreads();
+        if (j0 + threadIdx.x < n_lig) { s_x[threadIdx.x] = lx[j0 + threadIdx.x]; s_y[threadIdx.x] = ly[j0 + threadIdx.x]; s_z[threadIdx.x] = lz[j0 + threadIdx.x]; }
+        __syncthreads();
+        const int m = min(256, n_lig - j0);
+        for (int j = 0; j < m; j++) {
+            const double dx = x - s_x[j], dy = y - s_y[j], dz = z - s_z[j];
+            best = fmin(best, sqrt(dx * dx + dy * dy + dz * dz));
+        }
+    }
+    if (i < n_rec) keep[i] = best <= cutoff ? 1 : 0;
+}
+
+int launch_carve(int n_rec, const double *d_px, const double *d_py, const double *d_pz, int n_lig, const double *d_lx,
+                 const double *d_ly, const double *d_lz, double cutoff, uint8_t *d_keep) {
+    if (n_rec == 0) return MMO_OK;
+    carve_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, rt().stream>>>(n_rec, d_px, d_py, d_pz, n_lig, d_lx, d_ly, d_lz, cutoff, d_keep);
+    MMO_LAUNCH_CHECK();
+    return MMO_OK;
+}
+
 int launch_sphere_mask(double cx, double cy, double cz, double r, const mmo_mask *m) {
     double q[3];
     for (int d = 0; d < 3; d++) {

@@ -169,7 +169,9 @@ using namespace mmo;
 
 extern "C" {
 
-int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) {
+// analyse = false: Mol2.read_one_from_file as scissors uses it (src/scissors.ml:48-55): the first molecule only, atoms and
+// bonds as written, no graph analysis (a protein is not one connected molecule), never skipped for its topology
+static int read_mol2(const char *path, bool analyse, mmo_molfile **out) {
     MMO_REQUIRE(path && out, "mmo_molfile_read_mol2: null pointer");
     *out = nullptr;
     std::ifstream in(path);
@@ -232,14 +234,18 @@ int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) {
             bs.push_back(keep[s]); bd.push_back(keep[d]); bo.push_back(order);
             m.b_src.push_back(keep[s]); m.b_dst.push_back(keep[d]); m.b_typ.push_back(t[3]);
         }
-        if (ok && m.n() > 0 && analyse_graph(m, bs, bd, bo)) f->mols.push_back(std::move(m));
+        if (ok && m.n() > 0 && (!analyse || analyse_graph(m, bs, bd, bo))) f->mols.push_back(std::move(m));
         else f->n_skipped++;
         p = end;
+        if (!analyse) break;
     }
     f->assign_types();
     *out = f;
     return MMO_OK;
 }
+
+int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) { return read_mol2(path, true, out); }
+int mmo_molfile_read_mol2_atoms(const char *path, mmo_molfile **out) { return read_mol2(path, false, out); }
 
 int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out) {
     MMO_REQUIRE(path && out, "mmo_molfile_read_pqrs: null pointer");

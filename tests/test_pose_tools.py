@@ -160,3 +160,71 @@ def test_identity_placement_reproduces_the_reference_mol2_atom_lines(tmp_path, o
     (nm, counts, atoms, bonds), = _blocks(out)
     assert nm == lines[1].strip() and atoms == lines[a0 + 1:b0]
     assert bonds == [l for l in lines[b0 + 1:b0 + 1 + len(bonds)]]
+
+
+def test_mol2_atoms_reader_takes_disconnected_molecules(tmp_path):
+    """Mol2.read_one_from_file as scissors uses it (scissors.ml:48-55): first molecule only, no graph analysis"""
+    import ctypes as C
+    fn = tmp_path / "three.mol2"
+    fn.write_text(MOL2)
+    L = mmo_b200.lib()
+    h = C.c_void_p()
+    assert L.mmo_molfile_read_mol2_atoms(os.fsencode(str(fn)), C.byref(h)) == 0
+    n, sk = C.c_int32(), C.c_int32()
+    assert L.mmo_molfile_count(h, C.byref(n), C.byref(sk)) == 0 and (n.value, sk.value) == (1, 0)
+    na = C.c_int32()
+    assert L.mmo_molfile_shape(h, 0, C.byref(na), None, None, None, 0) == 0 and na.value == 12   # lone pair dropped
+    L.mmo_molfile_destroy(h)
+    # a molecule in two pieces is skipped by the mol2pqrs reader but is fine for the atoms-only one
+    broken = tmp_path / "broken.mol2"
+    broken.write_text("@<TRIPOS>MOLECULE\n" + MOL2.split("@<TRIPOS>MOLECULE\n")[2])
+    assert mmo_b200.MolFile(str(broken)).n_mols == 0
+    assert L.mmo_molfile_read_mol2_atoms(os.fsencode(str(broken)), C.byref(h)) == 0
+    assert L.mmo_molfile_count(h, C.byref(n), C.byref(sk)) == 0 and (n.value, sk.value) == (1, 0)
+    L.mmo_molfile_destroy(h)
+
+
+@pytest.mark.gpu
+def test_scissors_tool_and_carve_kernel(tmp_path, gpu, c2):
+    """scissors (scissors.ml:24-66): protein atoms whose nearest ligand atom is within the cut-off, as pqrs lines"""
+    import ctypes as C
+    m, lm = c2["rec_orig"], c2["lig"]
+    # the carve itself against numpy (sqrt of the nearest squared distance <= cutoff)
+    keep = np.zeros(m.n, np.uint8)
+    nk = C.c_int32()
+    dp = C.POINTER(C.c_double)
+    arr = [np.ascontiguousarray(a, np.float64) for a in (m.xs, m.ys, m.zs, lm.xs, lm.ys, lm.zs)]
+    rc = gpu.lib().mmo_carve_near_ligand(C.c_int32(m.n), arr[0].ctypes.data_as(dp), arr[1].ctypes.data_as(dp), arr[2].ctypes.data_as(dp),
+                                         C.c_int32(lm.n), arr[3].ctypes.data_as(dp), arr[4].ctypes.data_as(dp), arr[5].ctypes.data_as(dp),
+                                         C.c_double(5.0), keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nk))
+    assert rc == 0
+    d2 = ((m.xs[:, None] - lm.xs[None, :]) ** 2 + (m.ys[:, None] - lm.ys[None, :]) ** 2) + (m.zs[:, None] - lm.zs[None, :]) ** 2
+    want = np.sqrt(d2.min(axis=1)) <= 5.0
+    assert np.array_equal(keep.astype(bool), want) and nk.value == want.sum() and 20 < nk.value < m.n
+    # the tool: protein and ligand as mol2 files (written here from the fixtures), output = "%g %g %g %g %g %s" lines
+    sym = {1: "H", 6: "C", 7: "N", 8: "O", 9: "F", 12: "Mg", 15: "P", 16: "S", 17: "Cl", 35: "Br", 53: "I"}
+
+    def write_mol2(path, mol):
+        with open(path, "w") as f:
+            f.write("@<TRIPOS>MOLECULE\n%s\n%5d%6d%6d%6d%6d\nSMALL\nUSER_CHARGES\n\n@<TRIPOS>ATOM\n" % (mol.name, mol.n, 0, 0, 0, 0))
+            for i in range(mol.n):
+                f.write("%7d %-8s%10.4f%10.4f%10.4f %-8s  1 <0>     %10.4f\n" %
+                        (i + 1, "A%d" % i, mol.xs[i], mol.ys[i], mol.zs[i], sym[int(mol.anum[i])], mol.q[i]))
+            f.write("@<TRIPOS>BOND\n")
+    write_mol2(tmp_path / "prot.mol2", m)
+    write_mol2(tmp_path / "lig.mol2", lm)
+    out = tmp_path / "site.pqrs"
+    r = subprocess.run([_exe("scissors"), "-l", str(tmp_path / "lig.mol2"), "-p", str(tmp_path / "prot.mol2"), "-o", str(out), "-d", "6.5"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    # what the tool saw are the 4-decimal coordinates of the mol2 text
+    rx, ry, rz = (np.array([float("%.4f" % v) for v in a]) for a in (m.xs, m.ys, m.zs))
+    qx, qy, qz = (np.array([float("%.4f" % v) for v in a]) for a in (lm.xs, lm.ys, lm.zs))
+    d2 = ((rx[:, None] - qx[None, :]) ** 2 + (ry[:, None] - qy[None, :]) ** 2) + (rz[:, None] - qz[None, :]) ** 2
+    k = np.sqrt(d2.min(axis=1)) <= 6.5
+    lines = open(out).read().strip().split("\n")
+    want_lines = ["%g %g %g %g %g %s" % (rx[i], ry[i], rz[i], float("%.4f" % m.q[i]), m.r[i], sym[int(m.anum[i])])
+                  for i in range(m.n) if k[i]]
+    assert lines == want_lines
+    r = subprocess.run([_exe("scissors")], capture_output=True, text=True)
+    assert r.returncode == 1 and "-l <ligand.mol2>: xtal ligand input file" in r.stderr
