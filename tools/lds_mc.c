@@ -159,6 +159,7 @@ int main(int argc, char **argv) {
         double *tq = malloc(sizeof(double) * T);
         CK(mmo_molfile_types(lf, &T, ta, tq));
         CK(mmo_grid_build(rec, 0.5, dims, bits, T, ta, tq, NULL, &grid));
+        CK(mmo_sync());
         fprintf(stderr, "lds_mc: %d FF maps of %dx%dx%d voxels in %.2f s\n", (int)T, dims[0], dims[1], dims[2], now_s() - t_grid0);
         free(bits); free(ta); free(tq);
     }
