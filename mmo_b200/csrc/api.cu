@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points that move host buffers to HBM, launch, and copy results back.
 // Each function names the reference function it replaces in include/mmo_b200.h.
 #include "common.cuh"
+#include <algorithm>
 #include <math.h>
 #include <string.h>
 #include <string>
@@ -198,12 +199,18 @@ int mmo_grid_build(const mmo_receptor *rec, double step, const int32_t dims[3],
             memcpy(w.data(), mask_bits, (g->nvox + 7) / 8);
             if ((rc = dmask.upload(w))) break;
         }
-        std::vector<int32_t> telt(T);
-        for (int t = 0; t < T; t++) telt[t] = elt_index(type_anum[t]);
-        DevBuf<int32_t> dte;
+        // The kernel visits the types sorted by element (stable): types of one element are neighbours inside a
+        // thread's group, so the vdW term -- a function of the two elements only -- is formed once per element and
+        // reused; the maps keep the caller's type order (tidx) and every value is the same double as before.
+        std::vector<int32_t> ord(T), telt(T), tidx(T);
+        for (int t = 0; t < T; t++) ord[t] = t;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return elt_index(type_anum[a]) < elt_index(type_anum[b]); });
+        std::vector<double> tqs(T);
+        for (int t = 0; t < T; t++) { telt[t] = elt_index(type_anum[ord[t]]); tqs[t] = type_q[ord[t]]; tidx[t] = ord[t]; }
+        DevBuf<int32_t> dte, dti;
         DevBuf<double> dtq;
-        if ((rc = dte.upload(telt)) || (rc = dtq.upload(type_q, (size_t)T))) break;
-        if ((rc = launch_grid_build(rec, g, mask_bits ? dmask.p : nullptr, dte.p, dtq.p))) break;
+        if ((rc = dte.upload(telt)) || (rc = dtq.upload(tqs)) || (rc = dti.upload(tidx))) break;
+        if ((rc = launch_grid_build(rec, g, mask_bits ? dmask.p : nullptr, dte.p, dtq.p, dti.p))) break;
         if (out_maps) rc = d2h_sync(out_maps, g->maps.p, g->nvox * (size_t)T * sizeof(float));
         else { cudaError_t e2 = cudaStreamSynchronize(rt().stream); if (e2 != cudaSuccess) rc = cuda_fail(e2, "sync", __FILE__, __LINE__); }
     } while (0);

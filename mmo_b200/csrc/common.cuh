@@ -221,7 +221,7 @@ int launch_components_fp64(const mmo_receptor *rec, const mmo_ligand *lig, const
 int launch_intra_fp64(const mmo_ligand *lig, int64_t n_confs, const double *d_xs, const double *d_ys,
                       const double *d_zs, double *d_out);
 int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t *d_mask_words,
-                      const int32_t *d_type_elt, const double *d_type_q);
+                      const int32_t *d_type_elt, const double *d_type_q, const int32_t *d_type_idx);
 int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, double *d_out);
 int launch_trilin(const mmo_grid *g, int type, int64_t n, const double *d_x, const double *d_y,
                   const double *d_z, double *d_out);

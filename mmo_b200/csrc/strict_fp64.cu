@@ -198,7 +198,7 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
                    int dim0, int dim1, int dim2, double q0, double q1, double q2,
                    int nbx, int nby,
                    const uint32_t *__restrict__ mask, int T, const int32_t *__restrict__ telt,
-                   const double *__restrict__ tq, float *__restrict__ maps) {
+                   const double *__restrict__ tq, const int32_t *__restrict__ tidx, float *__restrict__ maps) {
     __shared__ double sx[kGridTile], sy[kGridTile], sz[kGridTile], sq[kGridTile];
     __shared__ int32_t se[kGridTile];
     __shared__ int s_wcount[4];
@@ -222,11 +222,13 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
     const int nt = min(kTG, T - t0);
     double se_acc[kTG], sv_acc[kTG], tqv[kTG];
     int te[kTG];
+    unsigned same = 0u;         // bit l: type l has the element of type l - 1 (types arrive sorted by element)
 #pragma unroll
     for (int l = 0; l < kTG; l++) {
         se_acc[l] = 0.0; sv_acc[l] = 0.0;
         tqv[l] = (l < nt) ? tq[t0 + l] : 0.0;
         te[l] = (l < nt) ? telt[t0 + l] * kEltTab : 0;
+        if (l > 0 && l < nt && te[l] == te[l - 1]) same |= 1u << l;
     }
     int count = 0;                                       // candidates staged in shared memory (block-uniform)
     for (int base = 0; base < P || count > 0; base += 128) {
@@ -266,13 +268,17 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
                     const double w = d_shift(r);
                     const int ei = se[c];
                     const Divisor by_r = make_divisor(r);       // 2 * kTG quotients by the same r (bit-identical to '/')
+                    double vdw = 0.0;           // w * d_ij (p6^2 - 2 p6): depends on the two elements only
 #pragma unroll
                     for (int l = 0; l < kTG; l++) {
                         if (l < nt) {
-                            int t = te[l] + ei;       // UFF.vdW_xiDi (get_anum lig 0) prot_anum
-                            double p6 = d_pow6(div_by(c_xij[t], by_r));
+                            if (!((same >> l) & 1u)) {
+                                int t = te[l] + ei;       // UFF.vdW_xiDi (get_anum lig 0) prot_anum
+                                double p6 = d_pow6(div_by(c_xij[t], by_r));
+                                vdw = w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                            }
                             se_acc[l] = se_acc[l] + w * div_by(q_i * tqv[l], by_r);
-                            sv_acc[l] = sv_acc[l] + w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                            sv_acc[l] = sv_acc[l] + vdw;
                         }
                     }
                 }
@@ -287,7 +293,7 @@ strict_grid_kernel(int P, const double *__restrict__ px, const double *__restric
         if (l < nt) {
             double e = kElecWeight * se_acc[l] + sv_acc[l];
             double v = (kMaxE <= e) ? kMaxE : e;      // OCaml: min max_E e = if max_E <= e then max_E else e
-            maps[(size_t)(t0 + l) * nvox + idx] = (float)v;
+            maps[(size_t)tidx[t0 + l] * nvox + idx] = (float)v;      // the caller's type order
         }
     }
 }
@@ -413,7 +419,7 @@ int launch_intra_fp64(const mmo_ligand *lig, int64_t n_confs, const double *d_xs
 }
 
 int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t *d_mask_words,
-                      const int32_t *d_type_elt, const double *d_type_q) {
+                      const int32_t *d_type_elt, const double *d_type_q, const int32_t *d_type_idx) {
     MMO_TRY(ensure_tables());
     GridGeom G = geom_of(g);
     const int nbx = (g->dims[0] + kBrickX - 1) / kBrickX, nby = (g->dims[1] + kBrickY - 1) / kBrickY,
@@ -422,7 +428,7 @@ int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t
     KernelScope ks(K_GRID_BUILD);
     strict_grid_kernel<<<grid, 128, 0, rt().stream>>>(rec->n, rec->x.p, rec->y.p, rec->z.p, rec->q.p, rec->elt.p,
                                                       g->dims[0], g->dims[1], g->dims[2], G.q[0], G.q[1], G.q[2],
-                                                      nbx, nby, d_mask_words, g->T, d_type_elt, d_type_q, g->maps.p);
+                                                      nbx, nby, d_mask_words, g->T, d_type_elt, d_type_q, d_type_idx, g->maps.p);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }
