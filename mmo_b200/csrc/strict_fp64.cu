@@ -305,6 +305,10 @@ __global__ void strict_trilin_kernel(GridGeom g, const float *__restrict__ arr, 
     if (p < n) out[p] = d_trilin(g, arr, xs[p], ys[p], zs[p]);
 }
 
+#ifndef MMO_INTERP_UNROLL
+#define MMO_INTERP_UNROLL 4
+#endif
+constexpr int kInterpUnroll = MMO_INTERP_UNROLL;
 // Mol.ene_inter_UFF_interp (mol.ml:1012-1020): res := !res +. trilin ... for j = 0 .. l-1
 __global__ void __launch_bounds__(128)
 strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
@@ -319,12 +323,15 @@ strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_poses) return;
     double res = 0.0;
+    // unrolled by kInterpUnroll: the gathers of several atoms are in flight together (the kernel waits on L2), the sum keeps its order
     if (src.kind == 1) {
+#pragma unroll kInterpUnroll
         for (int j = 0; j < L; j++)
             res = res + d_trilin(g, maps + (size_t)st[j] * g.nvox, src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
     } else {
         PoseRT P;
         load_pose_rt(src, p, P);
+#pragma unroll kInterpUnroll
         for (int j = 0; j < L; j++) {
             double x, y, z;
             pose_atom_rt(P, sx[j], sy[j], sz[j], x, y, z);
