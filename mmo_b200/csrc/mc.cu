@@ -112,30 +112,49 @@ __device__ __forceinline__ double favg_smem(const double *a, int n) {
 // Mol.ene_intra_UFFNB_brute (mol.ml:881-903): the pair terms are computed 32 at a time, one per lane,
 // parked in shared memory and then added up in the reference's (i<j) order by every lane alike
 // (broadcast reads: one LDS.128 + two DADD per term), which keeps the sum bit-identical.
+constexpr int kTermDoubles = 128;      // per warp: two buffers of 32 double2 term slots
+__device__ __forceinline__ double2 intra_term(const McArgs &a, const double *x, const double *y, const double *z, int k) {
+    double2 t = make_double2(0.0, 0.0);
+    if (k < a.n_pairs) {
+        const int i = __ldg(a.pair_i + k), j = __ldg(a.pair_j + k);
+        const double r = d_nzd(sqrt(d_dist2(x[i], y[i], z[i], x[j], y[j], z[j])));
+        const int tt = __ldg(a.lelt + i) * kEltTab + __ldg(a.lelt + j);
+        const Divisor by_r = make_divisor(r);
+        const double p6 = d_pow6(div_by(__ldg(a.xij + tt), by_r));
+        t.x = div_by(__ldg(a.lq + i) * __ldg(a.lq + j), by_r);
+        t.y = __ldg(a.dij + tt) * ((-2.0 * p6) + (p6 * p6));
+    }
+    return t;
+}
+// Software pipelined: the terms of round r + 1 are computed (sqrt and division chains) between the store of round r
+// and its in-order summation, two independent dependency chains the scheduler can interleave; two term buffers.
 __device__ double intra_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
                                double2 *terms) {
     double se = 0.0, sv = 0.0;
+    double2 t = intra_term(a, x, y, z, lane);
+    int buf = 0;
     for (int base = 0; base < a.n_pairs; base += 32) {
-        const int k = base + lane;
-        double2 t = make_double2(0.0, 0.0);
-        if (k < a.n_pairs) {
-            const int i = __ldg(a.pair_i + k), j = __ldg(a.pair_j + k);
-            const double r = d_nzd(sqrt(d_dist2(x[i], y[i], z[i], x[j], y[j], z[j])));
-            const int tt = __ldg(a.lelt + i) * kEltTab + __ldg(a.lelt + j);
-            const Divisor by_r = make_divisor(r);
-            const double p6 = d_pow6(div_by(__ldg(a.xij + tt), by_r));
-            t.x = div_by(__ldg(a.lq + i) * __ldg(a.lq + j), by_r);
-            t.y = __ldg(a.dij + tt) * ((-2.0 * p6) + (p6 * p6));
-        }
+        double2 *tb = terms + 32 * buf;
         __syncwarp();
-        terms[lane] = t;
+        tb[lane] = t;
         __syncwarp();
+        t = intra_term(a, x, y, z, base + 32 + lane);                 // next round (zeros beyond the last pair)
         const int lim = min(32, a.n_pairs - base);
-        for (int l = 0; l < lim; l++) {
-            const double2 u = terms[l];
-            se = se + u.x;
-            sv = sv + u.y;
+        if (lim == 32) {
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                const double2 u = tb[l];
+                se = se + u.x;
+                sv = sv + u.y;
+            }
+        } else {
+            for (int l = 0; l < lim; l++) {
+                const double2 u = tb[l];
+                se = se + u.x;
+                sv = sv + u.y;
+            }
         }
+        buf ^= 1;
     }
     return (kElecWeight * se) + sv;
 }
@@ -223,12 +242,12 @@ mc_chains_kernel(McArgs a) {
     const int64_t chain = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (chain >= a.n_chains) return;                    // whole warp leaves together
     const int L = a.L, nrb = a.n_rbonds;
-    const int per_warp = ((9 * L + 2 * max(nrb, 1) + 1) & ~1) + 64;     // even, + 32 double2 term slots
+    const int per_warp = ((9 * L + 2 * max(nrb, 1) + 1) & ~1) + kTermDoubles;     // even, + 2 x 32 double2 term slots
     double *cx = smem + (size_t)wib * per_warp, *cy = cx + L, *cz = cy + L;      // conf
     double *px = cz + L, *py = px + L, *pz = py + L;                              // conf' (proposed)
     double *lx = pz + L, *ly = lx + L, *lz = ly + L;                              // lig'
     double *dr = lz + L, *drp = dr + max(nrb, 1);                                 // per-bond step sizes of conf / conf'
-    double2 *terms = (double2 *)(cx + per_warp - 64);                             // 16-byte aligned: per_warp is even
+    double2 *terms = (double2 *)(cx + per_warp - kTermDoubles);                   // 16-byte aligned: per_warp is even
     Sw *sw_bond = (Sw *)(smem + (size_t)kWarpsPerBlock * per_warp) + (size_t)wib * max(nrb, 1);
 
     const bool flexible = a.tweak_rbonds && nrb > 0;
@@ -526,7 +545,7 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     a.best_E = d_bestE.p; a.prev_E = d_prevE.p; a.best_rot = d_brot.p; a.best_pos = d_bpos.p; a.best_xyz = d_bxyz.p;
     a.step_sizes = d_steps.p; a.counters = d_cnt.p; a.trace = trace_chain0 ? d_trace.p : nullptr;
     const int nrb1 = std::max(lig->n_rbonds, 1);
-    const size_t smem = (size_t)kWarpsPerBlock * (((9 * L + 2 * nrb1 + 1) & ~1) + 64) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
+    const size_t smem = (size_t)kWarpsPerBlock * (((9 * L + 2 * nrb1 + 1) & ~1) + kTermDoubles) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
     MMO_REQUIRE(smem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds)", L, lig->n_rbonds);
     MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
