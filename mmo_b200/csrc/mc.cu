@@ -97,16 +97,17 @@ __device__ __forceinline__ void rot_apply(const double *r, double x, double y, d
     oy = r[3] * x + r[4] * y + r[5] * z;
     oz = r[6] * x + r[7] * y + r[8] * z;
 }
-// Batteries A.favg restated as in the oracle: Kahan-compensated sum / n (same order in every lane)
-__device__ __forceinline__ double favg_smem(const double *a, int n) {
-    double sum = 0.0, c = 0.0;
+// Batteries A.favg restated as in the oracle: Kahan-compensated sum / n (same order in every lane);
+// the three coordinates at once: three independent Kahan chains in one loop (the same operations per chain, interleaved)
+__device__ __forceinline__ void favg3_smem(const double *ax, const double *ay, const double *az, int n, double *out) {
+    double s0 = 0.0, c0 = 0.0, s1 = 0.0, c1 = 0.0, s2 = 0.0, c2 = 0.0;
     for (int i = 0; i < n; i++) {
-        double y = a[i] - c;
-        double t = sum + y;
-        c = (t - sum) - y;
-        sum = t;
+        const double y0 = ax[i] - c0, y1 = ay[i] - c1, y2 = az[i] - c2;
+        const double t0 = s0 + y0, t1 = s1 + y1, t2 = s2 + y2;
+        c0 = (t0 - s0) - y0; c1 = (t1 - s1) - y1; c2 = (t2 - s2) - y2;
+        s0 = t0; s1 = t1; s2 = t2;
     }
-    return sum / (double)n;
+    out[0] = s0 / (double)n; out[1] = s1 / (double)n; out[2] = s2 / (double)n;
 }
 
 // Mol.ene_intra_UFFNB_brute (mol.ml:881-903): the pair terms are computed 32 at a time, one per lane,
@@ -330,7 +331,7 @@ mc_chains_kernel(McArgs a) {
                     px[i] = x + ox; py[i] = y + oy; pz[i] = z + oz;
                 }
                 __syncwarp();
-                pcen[0] = favg_smem(px, L); pcen[1] = favg_smem(py, L); pcen[2] = favg_smem(pz, L);   // update_center
+                favg3_smem(px, py, pz, L, pcen);                                                       // update_center
                 just_rotated = bond;
                 // Mol.check_elongation_exn lig 12.0 (mol.ml:576-591)
                 double maxi = 0.0;
