@@ -73,6 +73,14 @@ def setup_workload():
     return c2, rec_m
 
 
+def host_threads():
+    """every host thread this process may run on -- not OMP_NUM_THREADS, which torchrun sets to 1 for N > 1"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(c2, rec_m, rot, points_xyz, n_poses, nthreads):
     """Times the oracle (C restatement of mol.ml:822-849 + mol.ml:669-672) on n_poses of the workload."""
     import oracle
@@ -125,7 +133,7 @@ def run_reference(args, rank, world):
     c2, rec_m = setup_workload()
     rot = oracle.so3_rotations(N_ROT)
     pts = lattice_points(c2["roi"], TRANS_STEP)
-    nthreads = oracle.num_threads()
+    nthreads = host_threads()
     # size a step to ~2.5 s of CPU work
     dt = cpu_sample(c2, rec_m, rot, pts, 64 * nthreads, nthreads)
     per_step = max(nthreads, int(64 * nthreads * 2.5 / max(dt, 1e-6)))
@@ -445,7 +453,7 @@ def main():
             line["with_vdw_prefilter"] = prefilter
         if not args.no_cpu_baseline and world == 1:
             pts = lattice_points(c2["roi"], TRANS_STEP)
-            nthreads = oracle.num_threads()
+            nthreads = host_threads()
             dt = cpu_sample(c2, rec_m, rot, pts, 32 * nthreads, nthreads)
             n_s = max(nthreads, int(32 * nthreads * 12.0 / max(dt, 1e-6)))
             dt = cpu_sample(c2, rec_m, rot, pts, n_s, nthreads)
