@@ -727,7 +727,7 @@ struct FixArgs {
     double H;                            // exactly the fp32 clamp value
     double rinvH;                        // 1/sqrt(H)
     double wH;                           // shift weight at r^2 = H
-    const double *xx, *dij, *vdwH;       // kEltTab^2 tables: x_i*x_j, d_ij, d_ij*(p6H^2 - 2 p6H)
+    const double *xx, *dij, *vdwH;       // kEltTab^2 tables: A = d_ij x_ij^12, B = 2 d_ij x_ij^6, d_ij*(p6H^2 - 2 p6H)
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
 
@@ -776,9 +776,8 @@ __device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x,
                 // 1/r: MUFU.RSQ in fp32 (relative error < 2e-7), one Newton step in double (-> < 1e-13)
                 const double y0 = (double)rsqrtf((float)r2c);
                 const double rinv = y0 * (1.5 - (0.5 * r2c) * (y0 * y0));
-                const double t2 = __ldg(a.xx + tt) * (rinv * rinv);  // (x_ij / r)^2
-                const double p6 = t2 * t2 * t2;
-                const double ee = qq * rinv + __ldg(a.dij + tt) * (p6 * p6 - 2.0 * p6);
+                const double s1 = rinv * rinv, s3 = (s1 * s1) * s1;
+                const double ee = (__ldg(a.xx + tt) * s3 - __ldg(a.dij + tt)) * s3 + qq * rinv;     // (A s^3 - B) s^3 + qq / r
                 const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
                 double d;
                 if (VARIANT == MMO_VARIANT_SHIFTED) {
@@ -912,8 +911,10 @@ static int ensure_fix_tables(double H) {
         for (int a = 0; a < kEltTab; a++)
             for (int b = 0; b < kEltTab; b++) {
                 bool ok = a < kNumElt && b < kNumElt;
-                hx[a * kEltTab + b] = ok ? kEltXi[a] * kEltXi[b] : NAN;
-                hd[a * kEltTab + b] = ok ? sqrt(kEltDi[a] * kEltDi[b]) : NAN;
+                // d_ij (p6^2 - 2 p6) with p6 = (x_i x_j / r^2)^3  ==  A s^6 - B s^3,  s = 1/r^2
+                const double x2 = ok ? kEltXi[a] * kEltXi[b] : NAN, d = ok ? sqrt(kEltDi[a] * kEltDi[b]) : NAN;
+                hx[a * kEltTab + b] = d * ((x2 * x2 * x2) * (x2 * x2 * x2));       // A
+                hd[a * kEltTab + b] = 2.0 * d * (x2 * x2 * x2);                    // B
             }
         MMO_TRY(g_xx.upload(hx));
         MMO_TRY(g_dij.upload(hd));
