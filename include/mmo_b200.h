@@ -29,6 +29,7 @@ extern "C" {
 #define MMO_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, out of memory) */
 #define MMO_ESTATE (-3)   /* library not initialised / handle destroyed */
 #define MMO_ENCCL (-4)    /* NCCL not loadable or a collective failed */
+#define MMO_ENOMEM (-5)   /* host allocation failed */
 
 /* -ff BrG | BrL/Bst  (src/lds.ml:570-584) */
 #define MMO_VARIANT_GLOBAL 0   /* Mol.ene_inter_UFF_global_brute,  src/mol.ml:796-818 */
@@ -334,7 +335,8 @@ typedef struct {
     int32_t frames_done;
 } mmo_mc_result;
 /* start_rot9 / start_pos3: per chain (lds.ml:2034-2047); best_xyz: n_chains x 3 x L (x.. y.. z..),
- * may be NULL; trace_chain0: n_steps x {curr_E, E_inter, E_intra, accepted(-1 = no test)}, may be NULL */
+ * may be NULL; trace_chain0: n_steps x {curr_E, E_inter, E_intra, accepted(-1 = no test)}, may be NULL; the frames
+ * from results[0].frames_done on (a run cut short by Mol.Too_long) hold NaN */
 int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
                int64_t n_chains, const uint64_t *seeds, const double *start_rot9,
                const double *start_pos3, mmo_mc_result *results, double *best_xyz,

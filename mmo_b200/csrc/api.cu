@@ -47,7 +47,7 @@ extern "C" {
 
 // ------------------------------------------------------------------ direct pair path
 int mmo_score_coords(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
-                     int64_t n_poses, const double *xs, const double *ys, const double *zs, double *out_E) {
+                     int64_t n_poses, const double *xs, const double *ys, const double *zs, double *out_E) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && lig, "mmo_score_coords: null handle");
     MMO_TRY(check_variant_prec(variant, prec));
@@ -60,10 +60,10 @@ int mmo_score_coords(const mmo_receptor *rec, const mmo_ligand *lig, int variant
     MMO_TRY(dE.alloc((size_t)n_poses));
     MMO_TRY(run_direct(rec, lig, variant, prec, coords_src(dx.p, dy.p, dz.p), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
-}
+} MMO_CATCH_ALL
 
 int mmo_score_poses(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
-                    int64_t n_poses, const double *rot9, const double *trans3, double *out_E) {
+                    int64_t n_poses, const double *rot9, const double *trans3, double *out_E) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && lig, "mmo_score_poses: null handle");
     MMO_TRY(check_variant_prec(variant, prec));
@@ -76,10 +76,10 @@ int mmo_score_poses(const mmo_receptor *rec, const mmo_ligand *lig, int variant,
     MMO_TRY(dE.alloc((size_t)n_poses));
     MMO_TRY(run_direct(rec, lig, variant, prec, rt_src(dr.p, dt.p), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
-}
+} MMO_CATCH_ALL
 
 int mmo_score_poses_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
-                        int64_t n_poses, const double *d_rot9, const double *d_trans3, double *d_out_E) {
+                        int64_t n_poses, const double *d_rot9, const double *d_trans3, double *d_out_E) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && lig, "mmo_score_poses_dev: null handle");
     MMO_TRY(check_variant_prec(variant, prec));
@@ -88,10 +88,10 @@ int mmo_score_poses_dev(const mmo_receptor *rec, const mmo_ligand *lig, int vari
     MMO_REQUIRE(d_rot9 && d_trans3 && d_out_E, "mmo_score_poses_dev: null buffer");
     if (prec == MMO_PREC_FP64) return launch_direct_fp64(rec, lig, variant, rt_src(d_rot9, d_trans3), n_poses, d_out_E);
     return launch_direct_fp32(rec, lig, variant, rt_src(d_rot9, d_trans3), n_poses, d_out_E, rt().collect_stats);
-}
+} MMO_CATCH_ALL
 
 int mmo_score_coords_dev(const mmo_receptor *rec, const mmo_ligand *lig, int variant, int prec,
-                         int64_t n_poses, const double *d_xs, const double *d_ys, const double *d_zs, double *d_out_E) {
+                         int64_t n_poses, const double *d_xs, const double *d_ys, const double *d_zs, double *d_out_E) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && lig, "mmo_score_coords_dev: null handle");
     MMO_TRY(check_variant_prec(variant, prec));
@@ -100,11 +100,11 @@ int mmo_score_coords_dev(const mmo_receptor *rec, const mmo_ligand *lig, int var
     MMO_REQUIRE(d_xs && d_ys && d_zs && d_out_E, "mmo_score_coords_dev: null buffer");
     if (prec == MMO_PREC_FP64) return launch_direct_fp64(rec, lig, variant, coords_src(d_xs, d_ys, d_zs), n_poses, d_out_E);
     return launch_direct_fp32(rec, lig, variant, coords_src(d_xs, d_ys, d_zs), n_poses, d_out_E, rt().collect_stats);
-}
+} MMO_CATCH_ALL
 
 int mmo_score_coords_components(const mmo_receptor *rec, const mmo_ligand *lig, int64_t n_poses,
                                 const double *xs, const double *ys, const double *zs,
-                                double *out_elec, double *out_vdw) {
+                                double *out_elec, double *out_vdw) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && lig, "mmo_score_coords_components: null handle");
     MMO_REQUIRE(n_poses >= 0, "mmo_score_coords_components: negative pose count");
@@ -117,10 +117,10 @@ int mmo_score_coords_components(const mmo_receptor *rec, const mmo_ligand *lig, 
     MMO_TRY(launch_components_fp64(rec, lig, coords_src(dx.p, dy.p, dz.p), n_poses, de.p, dv.p));
     MMO_TRY(d2h_sync(out_elec, de.p, (size_t)n_poses * sizeof(double)));
     return d2h_sync(out_vdw, dv.p, (size_t)n_poses * sizeof(double));
-}
+} MMO_CATCH_ALL
 
 int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const double *ys,
-                 const double *zs, double *out_E) {
+                 const double *zs, double *out_E) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(lig, "mmo_intra_nb: null handle");
     MMO_REQUIRE(lig->has_dists, "mmo_intra_nb: the ligand was created without topological distances");
@@ -133,36 +133,36 @@ int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const
     MMO_TRY(dE.alloc((size_t)n_confs));
     MMO_TRY(launch_intra_fp64(lig, n_confs, dx.p, dy.p, dz.p, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_confs * sizeof(double));
-}
+} MMO_CATCH_ALL
 
-int mmo_set_collect_stats(int on) {
+int mmo_set_collect_stats(int on) try {
     rt().collect_stats = on != 0;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64) {
+int mmo_last_pair_stats(int64_t *pairs_evaluated, int64_t *pairs_inside, int64_t *pairs_fp64) try {
     if (pairs_evaluated) *pairs_evaluated = rt().stat_pairs;
     if (pairs_inside) *pairs_inside = rt().stat_inside;
     if (pairs_fp64) *pairs_fp64 = rt().stat_fp64;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_selftest_division(uint64_t seed, int64_t n, int64_t *mismatches) {
+int mmo_selftest_division(uint64_t seed, int64_t n, int64_t *mismatches) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(n > 0 && mismatches, "mmo_selftest_division: bad arguments");
     return division_selftest(seed, n, mismatches);
-}
+} MMO_CATCH_ALL
 
-int mmo_direct_set_mode(int mode) {
+int mmo_direct_set_mode(int mode) try {
     MMO_REQUIRE(mode >= 0 && mode <= 2, "mmo_direct_set_mode: mode must be 0 (auto), 1 (pose kernel) or 2 (item kernel)");
     direct_set_mode(mode);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_last_fix_stats(int64_t *atoms_flagged) {
+int mmo_last_fix_stats(int64_t *atoms_flagged) try {
     if (atoms_flagged) *atoms_flagged = rt().stat_flagged;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // ------------------------------------------------------------------ energy grids
 static int grid_alloc(double step, const int32_t dims[3], int32_t T, mmo_grid **out) {
@@ -182,7 +182,7 @@ static int grid_alloc(double step, const int32_t dims[3], int32_t T, mmo_grid **
 
 int mmo_grid_build(const mmo_receptor *rec, double step, const int32_t dims[3],
                    const uint8_t *mask_bits, int32_t T, const int32_t *type_anum,
-                   const double *type_q, float *out_maps, mmo_grid **out_grid) {
+                   const double *type_q, float *out_maps, mmo_grid **out_grid) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && type_anum && type_q, "mmo_grid_build: null argument");
     mmo_grid *g = nullptr;
@@ -217,9 +217,9 @@ int mmo_grid_build(const mmo_receptor *rec, double step, const int32_t dims[3],
     if (rc != MMO_OK || !out_grid) { delete g; g = nullptr; }
     if (out_grid) *out_grid = g;
     return rc;
-}
+} MMO_CATCH_ALL
 
-int mmo_grid_upload(double step, const int32_t dims[3], int32_t T, const float *maps, mmo_grid **out) {
+int mmo_grid_upload(double step, const int32_t dims[3], int32_t T, const float *maps, mmo_grid **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(maps != nullptr, "mmo_grid_upload: null maps");
     mmo_grid *g = nullptr;
@@ -229,21 +229,21 @@ int mmo_grid_upload(double step, const int32_t dims[3], int32_t T, const float *
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "upload maps", __FILE__, __LINE__); }
     *out = g;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_grid_download(const mmo_grid *grid, float *maps) {
+int mmo_grid_download(const mmo_grid *grid, float *maps) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(grid && maps, "mmo_grid_download: null argument");
     return d2h_sync(maps, grid->maps.p, grid->nvox * (size_t)grid->T * sizeof(float));
-}
+} MMO_CATCH_ALL
 
-int mmo_grid_destroy(mmo_grid *grid) {
+int mmo_grid_destroy(mmo_grid *grid) try {
     delete grid;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // G3D.to_ba1_file (G3D.ml:14-32): raw f32 image + `.dims` side-car with step/x_dim/y_dim/z_dim
-int mmo_grid_write_ba1(const mmo_grid *grid, int32_t type, const char *path) {
+int mmo_grid_write_ba1(const mmo_grid *grid, int32_t type, const char *path) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(grid && path, "mmo_grid_write_ba1: null argument");
     MMO_REQUIRE(type >= 0 && type < grid->T, "mmo_grid_write_ba1: type %d out of range", type);
@@ -260,10 +260,10 @@ int mmo_grid_write_ba1(const mmo_grid *grid, int32_t type, const char *path) {
     fprintf(f, "step: %g\nx_dim: %d\ny_dim: %d\nz_dim: %d\n", grid->step, grid->dims[0], grid->dims[1], grid->dims[2]);
     fclose(f);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // G3D.parse_dims_file + of_ba1_file (G3D.ml:37-64) for T maps of identical geometry
-int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) {
+int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(paths && T > 0 && out, "mmo_grid_read_ba1: bad arguments");
     double step = 0.0;
@@ -278,7 +278,11 @@ int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) {
         int ok = fscanf(f, "step: %lf x_dim: %d y_dim: %d z_dim: %d", &s, &a, &b, &c);
         fclose(f);
         MMO_REQUIRE(ok == 4, "mmo_grid_read_ba1: cannot parse %s", dn.c_str());
-        if (t == 0) { step = s; dims[0] = a; dims[1] = b; dims[2] = c; nvox = (size_t)a * b * c; all.resize(nvox * (size_t)T); }
+        if (t == 0) {
+            // the .dims side-car is untrusted text: check it before it sizes an allocation
+            MMO_REQUIRE(s > 0.0 && a > 1 && b > 1 && c > 1 && (double)a * b * c * T < 2.0e9, "mmo_grid_read_ba1: %s: bad geometry (step %g, %d x %d x %d, %d maps)", dn.c_str(), s, a, b, c, T);
+            step = s; dims[0] = a; dims[1] = b; dims[2] = c; nvox = (size_t)a * b * c; all.resize(nvox * (size_t)T);
+        }
         MMO_REQUIRE(s == step && a == dims[0] && b == dims[1] && c == dims[2], "mmo_grid_read_ba1: %s has another geometry", dn.c_str());
         f = fopen(paths[t], "rb");
         MMO_REQUIRE(f != nullptr, "mmo_grid_read_ba1: cannot open %s", paths[t]);
@@ -288,10 +292,10 @@ int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) {
         MMO_REQUIRE(r == nvox && extra == EOF, "mmo_grid_read_ba1: %s does not hold %zu floats", paths[t], nvox);   // assert(BA1.dim ba1 = n)
     }
     return mmo_grid_upload(step, dims, T, all.data(), out);
-}
+} MMO_CATCH_ALL
 
 int mmo_trilin(const mmo_grid *grid, int32_t type, int64_t n, const double *xs, const double *ys,
-               const double *zs, double *out) {
+               const double *zs, double *out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(grid, "mmo_trilin: null grid");
     MMO_REQUIRE(type >= 0 && type < grid->T, "mmo_trilin: type %d out of range", type);
@@ -303,7 +307,7 @@ int mmo_trilin(const mmo_grid *grid, int32_t type, int64_t n, const double *xs, 
     MMO_TRY(dE.alloc((size_t)n));
     MMO_TRY(launch_trilin(grid, type, n, dx.p, dy.p, dz.p, dE.p));
     return d2h_sync(out, dE.p, (size_t)n * sizeof(double));
-}
+} MMO_CATCH_ALL
 
 static int check_interp(const mmo_grid *grid, const mmo_ligand *lig) {
     MMO_REQUIRE(grid && lig, "interp: null handle");
@@ -314,7 +318,7 @@ static int check_interp(const mmo_grid *grid, const mmo_ligand *lig) {
 }
 
 int mmo_score_interp_coords(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
-                            const double *xs, const double *ys, const double *zs, double *out_E) {
+                            const double *xs, const double *ys, const double *zs, double *out_E) try {
     MMO_TRY(require_ready());
     MMO_TRY(check_interp(grid, lig));
     MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_coords: negative pose count");
@@ -326,10 +330,10 @@ int mmo_score_interp_coords(const mmo_grid *grid, const mmo_ligand *lig, int64_t
     MMO_TRY(dE.alloc((size_t)n_poses));
     MMO_TRY(launch_interp(grid, lig, coords_src(dx.p, dy.p, dz.p), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
-}
+} MMO_CATCH_ALL
 
 int mmo_score_interp_poses(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
-                           const double *rot9, const double *trans3, double *out_E) {
+                           const double *rot9, const double *trans3, double *out_E) try {
     MMO_TRY(require_ready());
     MMO_TRY(check_interp(grid, lig));
     MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_poses: negative pose count");
@@ -341,17 +345,17 @@ int mmo_score_interp_poses(const mmo_grid *grid, const mmo_ligand *lig, int64_t 
     MMO_TRY(dE.alloc((size_t)n_poses));
     MMO_TRY(launch_interp(grid, lig, rt_src(dr.p, dt.p), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
-}
+} MMO_CATCH_ALL
 
 int mmo_score_interp_poses_dev(const mmo_grid *grid, const mmo_ligand *lig, int64_t n_poses,
-                               const double *d_rot9, const double *d_trans3, double *d_out_E) {
+                               const double *d_rot9, const double *d_trans3, double *d_out_E) try {
     MMO_TRY(require_ready());
     MMO_TRY(check_interp(grid, lig));
     MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_poses_dev: negative pose count");
     if (n_poses == 0) return MMO_OK;
     MMO_REQUIRE(d_rot9 && d_trans3 && d_out_E, "mmo_score_interp_poses_dev: null buffer");
     return launch_interp(grid, lig, rt_src(d_rot9, d_trans3), n_poses, d_out_E);
-}
+} MMO_CATCH_ALL
 
 // ------------------------------------------------------------------ vdW occupancy mask
 static int mask_alloc(double step, const int32_t dims[3], mmo_mask **out) {
@@ -371,7 +375,7 @@ static int mask_alloc(double step, const int32_t dims[3], mmo_mask **out) {
 
 int mmo_vdw_mask_build(int32_t n, const double *xs, const double *ys, const double *zs,
                        const double *radii, double step, const int32_t dims[3], uint8_t *out_bits,
-                       mmo_mask **out_mask) {
+                       mmo_mask **out_mask) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(n >= 0 && (n == 0 || (xs && ys && zs && radii)), "mmo_vdw_mask_build: bad atom arrays");
     mmo_mask *m = nullptr;
@@ -391,7 +395,7 @@ int mmo_vdw_mask_build(int32_t n, const double *xs, const double *ys, const doub
     if (rc != MMO_OK || !out_mask) { delete m; m = nullptr; }
     if (out_mask) *out_mask = m;
     return rc;
-}
+} MMO_CATCH_ALL
 
 // N3 masks.  mode 0: vdW volume (radii), 1: first solvent shell (radii + 1.4 set, radii unset), 2: whole protein (12 A)
 static int atom_mask_build(int mode, int32_t n, const double *xs, const double *ys, const double *zs, const double *radii,
@@ -424,17 +428,17 @@ static int atom_mask_build(int mode, int32_t n, const double *xs, const double *
 }
 
 int mmo_mask_first_solvent_shell(int32_t n, const double *xs, const double *ys, const double *zs, const double *radii,
-                                 double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) {
+                                 double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) try {
     return atom_mask_build(1, n, xs, ys, zs, radii, step, dims, out_bits, out_mask);
-}
+} MMO_CATCH_ALL
 
 int mmo_mask_whole_protein(int32_t n, const double *xs, const double *ys, const double *zs,
-                           double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) {
+                           double step, const int32_t dims[3], uint8_t *out_bits, mmo_mask **out_mask) try {
     return atom_mask_build(2, n, xs, ys, zs, nullptr, step, dims, out_bits, out_mask);
-}
+} MMO_CATCH_ALL
 
 int mmo_mask_roi_only(const double roi_c[3], double roi_r, double step, const int32_t dims[3], uint8_t *out_bits,
-                      mmo_mask **out_mask) {
+                      mmo_mask **out_mask) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(roi_c && roi_r >= 0.0, "mmo_mask_roi_only: bad ROI");
     mmo_mask *m = nullptr;
@@ -446,9 +450,9 @@ int mmo_mask_roi_only(const double roi_c[3], double roi_r, double step, const in
     if (rc != MMO_OK || !out_mask) { delete m; m = nullptr; }
     if (out_mask) *out_mask = m;
     return rc;
-}
+} MMO_CATCH_ALL
 
-int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out) {
+int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(bits && out, "mmo_mask_upload: null argument");
     mmo_mask *m = nullptr;
@@ -459,15 +463,15 @@ int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo
     if (e != cudaSuccess) { delete m; return cuda_fail(e, "upload mask", __FILE__, __LINE__); }
     *out = m;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_mask_destroy(mmo_mask *mask) {
+int mmo_mask_destroy(mmo_mask *mask) try {
     delete mask;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses,
-                    const double *rot9, const double *trans3, uint8_t *out_flags) {
+                    const double *rot9, const double *trans3, uint8_t *out_flags) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(mask && lig, "mmo_clash_poses: null handle");
     MMO_REQUIRE(n_poses >= 0, "mmo_clash_poses: negative pose count");
@@ -480,12 +484,12 @@ int mmo_clash_poses(const mmo_mask *mask, const mmo_ligand *lig, int64_t n_poses
     MMO_TRY(df.alloc((size_t)n_poses));
     MMO_TRY(launch_clash(mask, lig, rt_src(dr.p, dt.p), n_poses, df.p));
     return d2h_sync(out_flags, df.p, (size_t)n_poses);
-}
+} MMO_CATCH_ALL
 
 // ------------------------------------------------------------------ N3: ligand-defined binding site (scissors)
 int mmo_carve_near_ligand(int32_t n_rec, const double *px, const double *py, const double *pz, int32_t n_lig,
                           const double *lx, const double *ly, const double *lz, double cutoff, uint8_t *out_keep,
-                          int32_t *n_kept) {
+                          int32_t *n_kept) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(n_rec >= 0 && n_lig >= 0 && cutoff >= 0.0, "mmo_carve_near_ligand: bad sizes");
     if (n_kept) *n_kept = 0;
@@ -500,11 +504,11 @@ int mmo_carve_near_ligand(int32_t n_rec, const double *px, const double *py, con
     MMO_TRY(d2h_sync(out_keep, dk.p, (size_t)n_rec));
     if (n_kept) for (int32_t i = 0; i < n_rec; i++) *n_kept += out_keep[i];
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // ------------------------------------------------------------------ N4: desolvation sums
 int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, const double roi_c[3], double roi_r,
-                       double *out_contribs, mmo_desolv **out) {
+                       double *out_contribs, mmo_desolv **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(rec && prot_shell && roi_c && roi_r >= 0.0, "mmo_desolv_protein: bad arguments");
     if (out) *out = nullptr;
@@ -518,7 +522,7 @@ int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, cons
     if (rc != MMO_OK || !out) { delete d; d = nullptr; }
     if (out) *out = d;
     return rc;
-}
+} MMO_CATCH_ALL
 
 static int desolv_penalty(const mmo_desolv *d, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses,
                           double *out_prot, double *out_lig) {
@@ -533,7 +537,7 @@ static int desolv_penalty(const mmo_desolv *d, const mmo_ligand *lig, const Pose
 }
 
 int mmo_desolv_penalty_coords(const mmo_desolv *d, const mmo_ligand *lig, int64_t n_poses, const double *xs,
-                              const double *ys, const double *zs, double *out_prot, double *out_lig) {
+                              const double *ys, const double *zs, double *out_prot, double *out_lig) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(d && lig && n_poses >= 0, "mmo_desolv_penalty_coords: bad arguments");
     if (n_poses == 0) return MMO_OK;
@@ -542,10 +546,10 @@ int mmo_desolv_penalty_coords(const mmo_desolv *d, const mmo_ligand *lig, int64_
     const size_t n = (size_t)n_poses * lig->n;
     MMO_TRY(dx.upload(xs, n)); MMO_TRY(dy.upload(ys, n)); MMO_TRY(dz.upload(zs, n));
     return desolv_penalty(d, lig, coords_src(dx.p, dy.p, dz.p), n_poses, out_prot, out_lig);
-}
+} MMO_CATCH_ALL
 
 int mmo_desolv_penalty_poses(const mmo_desolv *d, const mmo_ligand *lig, int64_t n_poses, const double *rot9,
-                             const double *trans3, double *out_prot, double *out_lig) {
+                             const double *trans3, double *out_prot, double *out_lig) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(d && lig && n_poses >= 0, "mmo_desolv_penalty_poses: bad arguments");
     if (n_poses == 0) return MMO_OK;
@@ -554,11 +558,11 @@ int mmo_desolv_penalty_poses(const mmo_desolv *d, const mmo_ligand *lig, int64_t
     MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
     MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
     return desolv_penalty(d, lig, rt_src(dr.p, dt.p), n_poses, out_prot, out_lig);
-}
+} MMO_CATCH_ALL
 
-int mmo_desolv_destroy(mmo_desolv *d) {
+int mmo_desolv_destroy(mmo_desolv *d) try {
     delete d;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

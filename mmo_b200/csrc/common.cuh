@@ -24,6 +24,10 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     do {                                                                      \
         if (!(cond)) { mmo::set_error(__VA_ARGS__); return MMO_EINVAL; }      \
     } while (0)
+// every extern "C" entry point is a function-try-block closed by this macro: std::bad_alloc / std::length_error from a
+// host-side container never unwinds into the C (or OCaml) caller
+int on_exception();
+#define MMO_CATCH_ALL catch (...) { return mmo::on_exception(); }
 #define MMO_TRY(call)                                                         \
     do { int rc__ = (call); if (rc__ != MMO_OK) return rc__; } while (0)
 

@@ -167,22 +167,22 @@ void rotated_copies_host(const HostLig &lig, const double center[3], int32_t n, 
 extern "C" {
 
 int mmo_apply_config(const mmo_ligand *lig, const double *config, int32_t n_config, double *out_xs, double *out_ys,
-                     double *out_zs, int32_t *too_long) {
+                     double *out_zs, int32_t *too_long) try {
     MMO_REQUIRE(lig && config && out_xs && out_ys && out_zs, "mmo_apply_config: null argument");
     const mmo::HostLig h = {lig->n, lig->hx.data(), lig->hy.data(), lig->hz.data(), lig->n_rbonds, lig->rb_left.data(),
                             lig->rb_right.data(), lig->rg_off.data(), lig->rg_idx.data()};
     return mmo::apply_config_host(h, config, n_config, out_xs, out_ys, out_zs, too_long);
-}
+} MMO_CATCH_ALL
 
 // lig_rot_sample (src/lig_rot_sample.ml:23-45): n SO3-rotated copies of the ligand about its own centre:
 // Mol.center_rotate_translate_copy mol rot orig_center (src/mol.ml:705-710).  `center` = Mol.get_center mol.
 int mmo_rotated_copies(const mmo_ligand *lig, const double center[3], int32_t n, const double *rot9,
-                       double *out_xs, double *out_ys, double *out_zs) {
+                       double *out_xs, double *out_ys, double *out_zs) try {
     MMO_REQUIRE(lig && center && n >= 0 && (n == 0 || (rot9 && out_xs && out_ys && out_zs)), "mmo_rotated_copies: bad arguments");
     const mmo::HostLig h = {lig->n, lig->hx.data(), lig->hy.data(), lig->hz.data(), 0, nullptr, nullptr, nullptr, nullptr};
     mmo::rotated_copies_host(h, center, n, rot9, out_xs, out_ys, out_zs);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // Lds.place_ligand_in_ROI rng prot_bst prot roi centered_ligs n (src/lds.ml:308-345): uniform points in the ROI's
 // englobing cube (Bbox.rand_point_inside, src/bbox.ml:50-54) until one lies inside the sphere (ROI.is_inside, strict <),
@@ -193,7 +193,7 @@ int mmo_rotated_copies(const mmo_ligand *lig, const double center[3], int32_t n,
 // the reference's order (constructor arguments right to left: z, y, x; then theta, axis three times).  libm sin/cos.
 int mmo_place_ligand_in_roi(int32_t n_rec, const double *px, const double *py, const double *pz, const int32_t *panum,
                             const mmo_ligand *lig, const double roi_c[3], double roi_r, uint64_t seed, int32_t n_starts,
-                            int32_t clash_check, double *out_rot9, double *out_pos3, int32_t *n_trials) {
+                            int32_t clash_check, double *out_rot9, double *out_pos3, int32_t *n_trials) try {
     MMO_REQUIRE(lig && roi_c && roi_r > 0.0 && n_starts >= 0 && n_rec >= 0, "mmo_place_ligand_in_roi: bad arguments");
     MMO_REQUIRE(n_starts == 0 || (out_rot9 && out_pos3), "mmo_place_ligand_in_roi: null output");
     MMO_REQUIRE(n_rec == 0 || (px && py && pz && panum), "mmo_place_ligand_in_roi: null receptor arrays");
@@ -256,29 +256,29 @@ int mmo_place_ligand_in_roi(int32_t n_rec, const double *px, const double *py, c
     }
     if (n_trials) *n_trials = trials;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_so3_rotations(int32_t n, double *rot9) {
+int mmo_so3_rotations(int32_t n, double *rot9) try {
     MMO_REQUIRE(n >= 0 && (n == 0 || rot9 != nullptr), "mmo_so3_rotations: bad arguments");
     mmo::so3_rotations(n, rot9);
     return MMO_OK;
-}
-int mmo_rot_r_xyz(double a, double b, double g, double rot9[9]) {
+} MMO_CATCH_ALL
+int mmo_rot_r_xyz(double a, double b, double g, double rot9[9]) try {
     MMO_REQUIRE(rot9 != nullptr, "mmo_rot_r_xyz: null pointer");
     mmo::rot_r_xyz(a, b, g, rot9);
     return MMO_OK;
-}
-int mmo_rot_decompose(const double rot9[9], double abg[3]) {
+} MMO_CATCH_ALL
+int mmo_rot_decompose(const double rot9[9], double abg[3]) try {
     MMO_REQUIRE(rot9 != nullptr && abg != nullptr, "mmo_rot_decompose: null pointer");
     mmo::rot_decompose(rot9, abg);
     return MMO_OK;
-}
-int mmo_grid_from_box(double step, double bx, double by, double bz, int32_t dims[3]) {
+} MMO_CATCH_ALL
+int mmo_grid_from_box(double step, double bx, double by, double bz, int32_t dims[3]) try {
     MMO_REQUIRE(dims != nullptr && step > 0.0, "mmo_grid_from_box: bad arguments");
     dims[0] = mmo::grid_num_steps(step, bx) + 1;
     dims[1] = mmo::grid_num_steps(step, by) + 1;
     dims[2] = mmo::grid_num_steps(step, bz) + 1;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

@@ -60,24 +60,29 @@ sphere_mask_kernel(double cx, double cy, double cz, double r2, double q0, double
     words[w] = bits;
 }
 
-__device__ __forceinline__ bool bit_at(const uint32_t *__restrict__ w, long idx) {
+// Bitv.get raises outside the vector (the reference would abort the run); here a voxel outside the mask box reads
+// as "not occupied", the same convention d_trilin uses for out-of-grid corners (0.0), in the kernels, on the host
+// (scan.cu host_clash_and) and in the oracle alike
+__device__ __forceinline__ bool bit_ijk(const uint32_t *__restrict__ w, int dim0, int dim1, int dim2, int i, int j, int k) {
+    if ((unsigned)i >= (unsigned)dim0 || (unsigned)j >= (unsigned)dim1 || (unsigned)k >= (unsigned)dim2) return false;
+    const size_t idx = (size_t)i + (size_t)j * dim0 + (size_t)k * dim0 * dim1;
     return (__ldg(w + (idx >> 5)) >> (idx & 31)) & 1u;
 }
 
 // G3D.vdW_clash_OR (G3D.ml:162-186)
-__device__ __forceinline__ bool clash_or(const uint32_t *__restrict__ w, double inv, int x_dim, int xy_dim,
+__device__ __forceinline__ bool clash_or(const uint32_t *__restrict__ w, double inv, int dim0, int dim1, int dim2,
                                          double x, double y, double z) {
     const int i0 = (int)(x * inv), j0 = (int)(y * inv), k0 = (int)(z * inv);
     const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
-    const long j0x = (long)j0 * x_dim, j1x = (long)j1 * x_dim, k0xy = (long)k0 * xy_dim, k1xy = (long)k1 * xy_dim;
-    return bit_at(w, i0 + j0x + k0xy) || bit_at(w, i1 + j0x + k0xy) || bit_at(w, i1 + j1x + k0xy) ||
-           bit_at(w, i0 + j1x + k0xy) || bit_at(w, i0 + j0x + k1xy) || bit_at(w, i1 + j0x + k1xy) ||
-           bit_at(w, i1 + j1x + k1xy) || bit_at(w, i0 + j1x + k1xy);
+    return bit_ijk(w, dim0, dim1, dim2, i0, j0, k0) || bit_ijk(w, dim0, dim1, dim2, i1, j0, k0) ||
+           bit_ijk(w, dim0, dim1, dim2, i1, j1, k0) || bit_ijk(w, dim0, dim1, dim2, i0, j1, k0) ||
+           bit_ijk(w, dim0, dim1, dim2, i0, j0, k1) || bit_ijk(w, dim0, dim1, dim2, i1, j0, k1) ||
+           bit_ijk(w, dim0, dim1, dim2, i1, j1, k1) || bit_ijk(w, dim0, dim1, dim2, i0, j1, k1);
 }
 
 // Mol.protein_ligand_clash for a batch of poses
 __global__ void __launch_bounds__(128)
-clash_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_dim, int L,
+clash_kernel(const uint32_t *__restrict__ words, double inv, int dim0, int dim1, int dim2, int L,
              const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
              PoseSrc src, int64_t n_poses, uint8_t *__restrict__ flags) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,14 +90,14 @@ clash_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_d
     bool clash = false;
     if (src.kind == 1) {
         for (int j = 0; j < L && !clash; j++)
-            clash = clash_or(words, inv, x_dim, xy_dim, src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
+            clash = clash_or(words, inv, dim0, dim1, dim2, src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
     } else {
         PoseRT P;
         load_pose_rt(src, p, P);
         for (int j = 0; j < L && !clash; j++) {
             double x, y, z;
             pose_atom_rt(P, __ldg(lx + j), __ldg(ly + j), __ldg(lz + j), x, y, z);
-            clash = clash_or(words, inv, x_dim, xy_dim, x, y, z);
+            clash = clash_or(words, inv, dim0, dim1, dim2, x, y, z);
         }
     }
     flags[p] = clash ? 1 : 0;
@@ -101,7 +106,7 @@ clash_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_d
 // scan prefilter: candidate c of the slab = (active point c / n_rot, rotation c % n_rot);
 // survivors are appended (block-ordered) to `frames`
 __global__ void __launch_bounds__(256)
-scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim, int xy_dim, int L,
+scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int dim0, int dim1, int dim2, int L,
                       const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
                       PoseSrc src /* kind 2, frames unused */, const int64_t *__restrict__ points,
                       const int32_t *__restrict__ rot_perm, int64_t n_cand,
@@ -124,7 +129,7 @@ scan_prefilter_kernel(const uint32_t *__restrict__ words, double inv, int x_dim,
             for (int j = 0; j < L && keep; j++) {
                 double x, y, z;
                 pose_atom_rt(P, __ldg(lx + j), __ldg(ly + j), __ldg(lz + j), x, y, z);
-                keep = !clash_or(words, inv, x_dim, xy_dim, x, y, z);
+                keep = !clash_or(words, inv, dim0, dim1, dim2, x, y, z);
             }
         }
     }
@@ -205,7 +210,7 @@ int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d
 int launch_clash(const mmo_mask *m, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, uint8_t *d_flags) {
     if (n_poses == 0) return MMO_OK;
     clash_kernel<<<(unsigned)((n_poses + 127) / 128), 128, 0, rt().stream>>>(
-        m->words.p, 1.0 / m->step, m->dims[0], m->dims[0] * m->dims[1], lig->n, lig->x.p, lig->y.p, lig->z.p,
+        m->words.p, 1.0 / m->step, m->dims[0], m->dims[1], m->dims[2], lig->n, lig->x.p, lig->y.p, lig->z.p,
         src, n_poses, d_flags);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
@@ -216,7 +221,7 @@ int launch_scan_prefilter(const mmo_mask *m, const mmo_ligand *lig, const PoseSr
     if (n_cand == 0) return MMO_OK;
     KernelScope ks(K_PREFILTER);
     scan_prefilter_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, rt().stream>>>(
-        m ? m->words.p : nullptr, m ? 1.0 / m->step : 0.0, m ? m->dims[0] : 0, m ? m->dims[0] * m->dims[1] : 0,
+        m ? m->words.p : nullptr, m ? 1.0 / m->step : 0.0, m ? m->dims[0] : 0, m ? m->dims[1] : 0, m ? m->dims[2] : 0,
         lig->n, lig->x.p, lig->y.p, lig->z.p, src, d_points, d_rot_perm, n_cand, d_frames, d_counter);
     MMO_LAUNCH_CHECK();
     return MMO_OK;

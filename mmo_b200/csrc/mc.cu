@@ -500,7 +500,7 @@ using namespace mmo;
 extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const mmo_ligand *lig, const mmo_mc_params *p,
                           int64_t n_chains, const uint64_t *seeds, const double *start_rot9,
                           const double *start_pos3, mmo_mc_result *results, double *best_xyz,
-                          double *trace_chain0) {
+                          double *trace_chain0) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(lig && p, "mmo_mc_run: null handle");
     MMO_REQUIRE((rec != nullptr) != (grid != nullptr), "mmo_mc_run: give exactly one of rec (direct, --no-interp) or grid (interpolated)");
@@ -524,7 +524,12 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     MMO_TRY(d_brot.alloc((size_t)n_chains * 9)); MMO_TRY(d_bpos.alloc((size_t)n_chains * 3));
     MMO_TRY(d_bxyz.alloc((size_t)n_chains * 3 * L)); MMO_TRY(d_steps.alloc((size_t)n_chains * 2));
     MMO_TRY(d_cnt.alloc((size_t)n_chains * 8));
-    if (trace_chain0) MMO_TRY(d_trace.alloc((size_t)std::max(1, p->n_steps) * 4));
+    if (trace_chain0) {
+        // frames after a Mol.Too_long break are never written by the kernel: NaN, not stale pool memory
+        // (frames_done of chain 0 is the valid length)
+        MMO_TRY(d_trace.alloc((size_t)std::max(1, p->n_steps) * 4));
+        MMO_CUDA(cudaMemsetAsync(d_trace.p, 0xff, (size_t)std::max(1, p->n_steps) * 4 * sizeof(double), R.stream));
+    }
     McArgs a;
     a.L = L; a.lx = lig->x.p; a.ly = lig->y.p; a.lz = lig->z.p; a.lq = lig->q.p; a.lelt = lig->elt.p; a.ltyp = lig->typ.p;
     a.n_pairs = lig->n_pairs; a.pair_i = lig->pair_i.p; a.pair_j = lig->pair_j.p;
@@ -580,4 +585,4 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
         r.too_long = (int32_t)hC[c * 8 + 6]; r.frames_done = (int32_t)hC[c * 8 + 7];
     }
     return MMO_OK;
-}
+} MMO_CATCH_ALL

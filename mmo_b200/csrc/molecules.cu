@@ -73,7 +73,7 @@ using namespace mmo;
 extern "C" {
 
 int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const double *zs,
-                        const double *q, const int32_t *anum, mmo_receptor **out) {
+                        const double *q, const int32_t *anum, mmo_receptor **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(out != nullptr, "mmo_receptor_create: null output pointer");
     *out = nullptr;
@@ -185,18 +185,18 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     if (rc != MMO_OK) { delete r; return rc; }
     *out = r;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_receptor_destroy(mmo_receptor *rec) {
+int mmo_receptor_destroy(mmo_receptor *rec) try {
     delete rec;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const double *zs,
                       const double *q, const double *r, const int32_t *anum, const int32_t *typ,
                       const int32_t *dists,
                       int32_t n_rbonds, const int32_t *rb_left, const int32_t *rb_right,
-                      const int32_t *rg_off, const int32_t *rg_idx, mmo_ligand **out) {
+                      const int32_t *rg_off, const int32_t *rg_idx, mmo_ligand **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(out != nullptr, "mmo_ligand_create: null output pointer");
     *out = nullptr;
@@ -205,6 +205,10 @@ int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const doubl
     MMO_REQUIRE(n_rbonds >= 0, "mmo_ligand_create: negative rotatable-bond count");
     MMO_REQUIRE(n_rbonds == 0 || (rb_left && rb_right && rg_off && rg_idx),
                 "mmo_ligand_create: rotatable bonds announced but arrays are null");
+    // the CSR offsets are lengths of caller memory: validated before anything is copied with them
+    for (int b = 0; b < n_rbonds; b++)
+        MMO_REQUIRE(rg_off[0] == 0 && rg_off[b] >= 0 && rg_off[b] <= rg_off[b + 1] && rg_off[b + 1] <= n_rbonds * n,
+                    "mmo_ligand_create: rotatable group offsets are not a monotonic CSR (bond %d)", b);
     mmo_ligand *l = new mmo_ligand();
     l->n = n;
     l->hx.assign(xs, xs + n); l->hy.assign(ys, ys + n); l->hz.assign(zs, zs + n);
@@ -268,11 +272,11 @@ int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const doubl
     if (rc != MMO_OK) { delete l; return rc; }
     *out = l;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_ligand_destroy(mmo_ligand *lig) {
+int mmo_ligand_destroy(mmo_ligand *lig) try {
     delete lig;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

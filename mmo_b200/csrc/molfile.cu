@@ -244,10 +244,10 @@ static int read_mol2(const char *path, bool analyse, mmo_molfile **out) {
     return MMO_OK;
 }
 
-int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) { return read_mol2(path, true, out); }
-int mmo_molfile_read_mol2_atoms(const char *path, mmo_molfile **out) { return read_mol2(path, false, out); }
+int mmo_molfile_read_mol2(const char *path, mmo_molfile **out) try { return read_mol2(path, true, out); } MMO_CATCH_ALL
+int mmo_molfile_read_mol2_atoms(const char *path, mmo_molfile **out) try { return read_mol2(path, false, out); } MMO_CATCH_ALL
 
-int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out) {
+int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out) try {
     MMO_REQUIRE(path && out, "mmo_molfile_read_pqrs: null pointer");
     *out = nullptr;
     std::ifstream in(path);
@@ -320,17 +320,17 @@ int mmo_molfile_read_pqrs(const char *path, int is_receptor, mmo_molfile **out) 
     f->assign_types();
     *out = f;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_molfile_count(const mmo_molfile *f, int32_t *n_mols, int32_t *n_skipped) {
+int mmo_molfile_count(const mmo_molfile *f, int32_t *n_mols, int32_t *n_skipped) try {
     MMO_REQUIRE(f && n_mols, "mmo_molfile_count: null pointer");
     *n_mols = (int32_t)f->mols.size();
     if (n_skipped) *n_skipped = f->n_skipped;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 int mmo_molfile_shape(const mmo_molfile *f, int32_t k, int32_t *n_atoms, int32_t *n_rbonds, int32_t *rg_total,
-                      char *name, int32_t name_cap) {
+                      char *name, int32_t name_cap) try {
     MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_shape: molecule index out of range");
     const Molecule &m = f->mols[k];
     if (n_atoms) *n_atoms = m.n();
@@ -343,11 +343,11 @@ int mmo_molfile_shape(const mmo_molfile *f, int32_t k, int32_t *n_atoms, int32_t
     }
     if (name && name_cap > 0) { strncpy(name, m.name.c_str(), (size_t)name_cap - 1); name[name_cap - 1] = 0; }
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 int mmo_molfile_get(const mmo_molfile *f, int32_t k, double *xs, double *ys, double *zs, double *q, double *r,
                     int32_t *anum, int32_t *typ, int32_t *dists, int32_t *rb_left, int32_t *rb_right,
-                    int32_t *rg_off, int32_t *rg_idx) {
+                    int32_t *rg_off, int32_t *rg_idx) try {
     MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_get: molecule index out of range");
     const Molecule &m = f->mols[k];
     const int n = m.n();
@@ -372,27 +372,27 @@ int mmo_molfile_get(const mmo_molfile *f, int32_t k, double *xs, double *ys, dou
         rg_off[nrb] = tot;
     }
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum, double *type_q) {
+int mmo_molfile_types(const mmo_molfile *f, int32_t *n_types, int32_t *type_anum, double *type_q) try {
     MMO_REQUIRE(f && n_types, "mmo_molfile_types: null pointer");
     *n_types = (int32_t)f->type_anum.size();
     if (type_anum) memcpy(type_anum, f->type_anum.data(), f->type_anum.size() * sizeof(int32_t));
     if (type_q) memcpy(type_q, f->type_q.data(), f->type_q.size() * sizeof(double));
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // lds --less-charges (src/lds.ml:1887-1894): Mol.reduce_partial_charges_precision on every ligand (src/mol.ml:256-260,
 // Utls.reduce_precision src/utls.ml:127-132: two decimals, rounded away from zero), BEFORE the FF types are assigned
-int mmo_molfile_reduce_charges(mmo_molfile *f) {
+int mmo_molfile_reduce_charges(mmo_molfile *f) try {
     MMO_REQUIRE(f != nullptr, "mmo_molfile_reduce_charges: null pointer");
     for (Molecule &m : f->mols)
         for (double &q : m.q) q = (double)(long long)(q * 100.0 + (q >= 0.0 ? 0.5 : -0.5)) / 100.0;
     f->assign_types();
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path) {
+int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path) try {
     MMO_REQUIRE(f && path, "mmo_molfile_write_pqrs: null pointer");
     FILE *o = fopen(path, "w");
     MMO_REQUIRE(o != nullptr, "mmo_molfile_write_pqrs: cannot create %s", path);
@@ -417,11 +417,11 @@ int mmo_molfile_write_pqrs(const mmo_molfile *f, const char *path) {
     }
     fclose(o);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // straight to the device handle: Mol.translate_to lig V3.origin (lds.ml:44-52) when `centered`, with the
 // Kahan-averaged centre (Batteries A.favg as restated in the oracle)
-int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand **out) {
+int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand **out) try {
     MMO_REQUIRE(f && out && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_ligand: molecule index out of range");
     const Molecule &m = f->mols[k];
     const int n = m.n(), nrb = (int)m.rb_left.size();
@@ -445,13 +445,13 @@ int mmo_molfile_ligand(const mmo_molfile *f, int32_t k, int centered, mmo_ligand
     return mmo_ligand_create(n, x.data(), y.data(), z.data(), m.q.data(), m.r.data(), m.anum.data(), m.typ.data(),
                              m.dists.empty() ? nullptr : m.dists.data(), nrb, m.rb_left.data(), m.rb_right.data(),
                              off.data(), idx.data(), out);
-}
+} MMO_CATCH_ALL
 
 // Mol2.output_one (src/mol2.ml:326-343, line formats 184-190, 209-210) of Mol.update_mol2 mol2 m (src/mol.ml:544-552):
 // molecule k written n_copies times with its coordinates replaced by copy c of xs/ys/zs ([n_copies][n_atoms]; NULL =
 // the file's own).  What lig_rot_sample (one block per rotation) and place_ligand (one block) emit.
 int mmo_molfile_write_mol2(const mmo_molfile *f, int32_t k, int32_t n_copies, const double *xs, const double *ys,
-                           const double *zs, const char *path, int append) {
+                           const double *zs, const char *path, int append) try {
     MMO_REQUIRE(f && path && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_write_mol2: molecule index out of range");
     const Molecule &m = f->mols[k];
     const int n = m.n();
@@ -475,7 +475,7 @@ int mmo_molfile_write_mol2(const mmo_molfile *f, int32_t k, int32_t n_copies, co
     const bool bad = ferror(o) != 0;
     MMO_REQUIRE(fclose(o) == 0 && !bad, "mmo_molfile_write_mol2: write error on %s", path);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 namespace {
 struct HostView {
@@ -500,7 +500,7 @@ int host_view(const mmo_molfile *f, int32_t k, const std::vector<double> &x, con
 // the body of the lig_rot_sample tool (src/lig_rot_sample.ml:23-45) on molecule k of the file, host only:
 // Mol.center_rotate_translate_copy mol rot (Mol.get_center mol) for every rotation
 int mmo_molfile_rotated_copies(const mmo_molfile *f, int32_t k, int32_t n, const double *rot9, double *out_xs,
-                               double *out_ys, double *out_zs) {
+                               double *out_ys, double *out_zs) try {
     MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_rotated_copies: molecule index out of range");
     MMO_REQUIRE(n >= 0 && (n == 0 || (rot9 && out_xs && out_ys && out_zs)), "mmo_molfile_rotated_copies: bad arguments");
     const Molecule &m = f->mols[k];
@@ -508,12 +508,12 @@ int mmo_molfile_rotated_copies(const mmo_molfile *f, int32_t k, int32_t n, const
     const mmo::HostLig h = {m.n(), m.x.data(), m.y.data(), m.z.data(), 0, nullptr, nullptr, nullptr, nullptr};
     rotated_copies_host(h, center, n, rot9, out_xs, out_ys, out_zs);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // the body of the place_ligand tool (src/place_ligand.ml:36-59) on molecule k, host only: Mol.center, then
 // Optim.apply_config centered_lig (x y z a b g [rbond angles]) (src/optim.ml:64-80)
 int mmo_molfile_apply_config(const mmo_molfile *f, int32_t k, const double *config, int32_t n_config, double *out_xs,
-                             double *out_ys, double *out_zs, int32_t *too_long) {
+                             double *out_ys, double *out_zs, int32_t *too_long) try {
     MMO_REQUIRE(f && k >= 0 && k < (int32_t)f->mols.size(), "mmo_molfile_apply_config: molecule index out of range");
     MMO_REQUIRE(config && out_xs && out_ys && out_zs, "mmo_molfile_apply_config: null argument");
     const Molecule &m = f->mols[k];
@@ -524,11 +524,11 @@ int mmo_molfile_apply_config(const mmo_molfile *f, int32_t k, const double *conf
     HostView v;
     MMO_TRY(host_view(f, k, x, y, z, v));
     return apply_config_host(v.h, config, n_config, out_xs, out_ys, out_zs, too_long);
-}
+} MMO_CATCH_ALL
 
-int mmo_molfile_destroy(mmo_molfile *f) {
+int mmo_molfile_destroy(mmo_molfile *f) try {
     delete f;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

@@ -58,7 +58,7 @@ using namespace mmo;
 
 extern "C" {
 
-int mmo_nccl_unique_id(uint8_t id[128]) {
+int mmo_nccl_unique_id(uint8_t id[128]) try {
     MMO_REQUIRE(id != nullptr, "mmo_nccl_unique_id: null pointer");
     MMO_TRY(nccl_load());
     ncclUniqueId u;
@@ -66,9 +66,9 @@ int mmo_nccl_unique_id(uint8_t id[128]) {
     if (r != 0) return nccl_fail(r, "ncclGetUniqueId");
     memcpy(id, u.internal, 128);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_nccl_init(int32_t rank, int32_t nranks, const uint8_t id[128]) {
+int mmo_nccl_init(int32_t rank, int32_t nranks, const uint8_t id[128]) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(id != nullptr && nranks > 0 && rank >= 0 && rank < nranks, "mmo_nccl_init: bad arguments");
     MMO_TRY(nccl_load());
@@ -80,18 +80,18 @@ int mmo_nccl_init(int32_t rank, int32_t nranks, const uint8_t id[128]) {
     g_nccl.rank = rank;
     g_nccl.nranks = nranks;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_nccl_finalize(void) {
+int mmo_nccl_finalize(void) try {
     if (g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
     g_nccl.nranks = 1;
     g_nccl.rank = 0;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 // collective: every rank calls it with its local list (n_local <= k entries); every rank gets the merged top-k
 int mmo_topk_allgather_merge(int32_t k, int32_t n_local, const double *scores, const int64_t *frames,
-                             double *out_scores, int64_t *out_frames, int32_t *out_n) {
+                             double *out_scores, int64_t *out_frames, int32_t *out_n) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(k > 0 && n_local >= 0 && n_local <= k && out_scores && out_frames && out_n, "mmo_topk_allgather_merge: bad arguments");
     MMO_REQUIRE(n_local == 0 || (scores && frames), "mmo_topk_allgather_merge: null list");
@@ -119,6 +119,6 @@ int mmo_topk_allgather_merge(int32_t k, int32_t n_local, const double *scores, c
         for (int i = 0; i < k; i++) { S[(size_t)q * k + i] = all[(size_t)q * (k + 1) + i].s; F[(size_t)q * k + i] = all[(size_t)q * (k + 1) + i].f; }
     }
     return mmo_topk_merge(nr, k, S.data(), F.data(), cnt.data(), out_scores, out_frames, out_n);
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <new>
+#include <stdexcept>
 
 namespace mmo {
 
@@ -16,6 +18,12 @@ void set_error(const char *fmt, ...) {
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
     return MMO_ECUDA;
+}
+int on_exception() {
+    try { throw; }
+    catch (const std::bad_alloc &) { set_error("out of host memory"); return MMO_ENOMEM; }
+    catch (const std::exception &e) { set_error("internal error: %s", e.what()); return MMO_EINVAL; }
+    catch (...) { set_error("internal error (unknown exception)"); return MMO_EINVAL; }
 }
 Runtime &rt() {
     static Runtime r;
@@ -64,7 +72,7 @@ KernelScope::~KernelScope() {
 }
 
 // ---- caching device allocator ------------------------------------------------------------------------
-struct PoolBlock { void *p; size_t bytes; };
+struct PoolBlock { void *p; size_t bytes; int epoch; };   // epoch = the mmo_init (device) the block was allocated under
 static std::vector<PoolBlock> g_pool_free;          // cached, not in use
 static std::vector<PoolBlock> g_pool_live;          // handed out
 static size_t g_pool_cached = 0;
@@ -74,7 +82,7 @@ int pool_alloc(void **out, size_t bytes) {
     bytes = (bytes + 511) & ~(size_t)511;
     int best = -1;
     for (int i = 0; i < (int)g_pool_free.size(); i++)
-        if (g_pool_free[i].bytes >= bytes && g_pool_free[i].bytes <= 2 * bytes + 4096 &&
+        if (g_pool_free[i].epoch == rt().epoch && g_pool_free[i].bytes >= bytes && g_pool_free[i].bytes <= 2 * bytes + 4096 &&
             (best < 0 || g_pool_free[i].bytes < g_pool_free[best].bytes))
             best = i;
     if (best >= 0) {
@@ -93,7 +101,7 @@ int pool_alloc(void **out, size_t bytes) {
         e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
-    g_pool_live.push_back({p, bytes});
+    g_pool_live.push_back({p, bytes, rt().epoch});
     *out = p;
     return MMO_OK;
 }
@@ -102,7 +110,7 @@ void pool_free(void *p) {
         if (g_pool_live[i].p == p) {
             PoolBlock b = g_pool_live[i];
             g_pool_live.erase(g_pool_live.begin() + i);
-            if (rt().ready && g_pool_cached + b.bytes <= kPoolMaxCached) {
+            if (rt().ready && b.epoch == rt().epoch && g_pool_cached + b.bytes <= kPoolMaxCached) {     // a block of an earlier device is never cached
                 // work queued on the library stream may still use the block: the pool is only handed
                 // out again to work on the same stream, which is ordered after it
                 g_pool_free.push_back(b);
@@ -193,13 +201,13 @@ const char *mmo_build_info(void) {
     return "libmmo_b200 sm_100a CUDA " MMO_STR(CUDART_VERSION) " built " __DATE__ " " __TIME__;
 }
 
-int mmo_device_count(int *n) {
+int mmo_device_count(int *n) try {
     MMO_REQUIRE(n != nullptr, "mmo_device_count: null pointer");
     MMO_CUDA(cudaGetDeviceCount(n));
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_init(int device) {
+int mmo_init(int device) try {
     Runtime &R = rt();
     if (R.ready && R.device == device) return MMO_OK;
     if (R.ready) mmo_shutdown();
@@ -227,9 +235,9 @@ int mmo_init(int device) {
     R.epoch++;
     R.ready = true;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_shutdown(void) {
+int mmo_shutdown(void) try {
     Runtime &R = rt();
     if (!R.ready) return MMO_OK;
     cudaStreamSynchronize(R.stream);
@@ -246,45 +254,45 @@ int mmo_shutdown(void) {
     R.stream = nullptr;
     R.ready = false;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 int64_t mmo_launch_count(void) { return rt().launches; }
 
-int mmo_kernel_timing(int on) {
+int mmo_kernel_timing(int on) try {
     MMO_TRY(require_ready());
     kt_resolve();
     g_kt.enabled = on != 0;
     for (int i = 0; i < K_COUNT; i++) { g_kt.ms[i] = 0.0; g_kt.launches[i] = 0; }
     return MMO_OK;
-}
-int mmo_kernel_time_get(int kernel_id, double *ms, int64_t *launches) {
+} MMO_CATCH_ALL
+int mmo_kernel_time_get(int kernel_id, double *ms, int64_t *launches) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(kernel_id >= 0 && kernel_id < K_COUNT, "mmo_kernel_time_get: bad kernel id %d", kernel_id);
     kt_resolve();
     if (ms) *ms = g_kt.ms[kernel_id];
     if (launches) *launches = g_kt.launches[kernel_id];
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_timer_start(void) {
+int mmo_timer_start(void) try {
     MMO_TRY(require_ready());
     MMO_CUDA(cudaEventRecord(rt().ev0, rt().stream));
     return MMO_OK;
-}
-int mmo_timer_stop(float *ms) {
+} MMO_CATCH_ALL
+int mmo_timer_stop(float *ms) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(ms != nullptr, "mmo_timer_stop: null pointer");
     MMO_CUDA(cudaEventRecord(rt().ev1, rt().stream));
     MMO_CUDA(cudaEventSynchronize(rt().ev1));
     MMO_CUDA(cudaEventElapsedTime(ms, rt().ev0, rt().ev1));
     return MMO_OK;
-}
-int mmo_sync(void) {
+} MMO_CATCH_ALL
+int mmo_sync(void) try {
     MMO_TRY(require_ready());
     MMO_CUDA(cudaStreamSynchronize(rt().stream));
     return MMO_OK;
-}
-int mmo_l2_flush(void) {
+} MMO_CATCH_ALL
+int mmo_l2_flush(void) try {
     MMO_TRY(require_ready());
     Runtime &R = rt();
     const size_t bytes = (size_t)256 << 20;   // > 126 MB L2
@@ -294,17 +302,17 @@ int mmo_l2_flush(void) {
     }
     MMO_CUDA(cudaMemsetAsync(R.l2_scratch, 0x5a, R.l2_scratch_bytes, R.stream));
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_measure_fp32_peak(double *tflops) {
+int mmo_measure_fp32_peak(double *tflops) try {
     MMO_REQUIRE(tflops != nullptr, "null pointer");
     return measure_fma<float>(tflops);
-}
-int mmo_measure_fp64_peak(double *tflops) {
+} MMO_CATCH_ALL
+int mmo_measure_fp64_peak(double *tflops) try {
     MMO_REQUIRE(tflops != nullptr, "null pointer");
     return measure_fma<double>(tflops);
-}
-int mmo_measure_hbm_copy(double *gbs) {
+} MMO_CATCH_ALL
+int mmo_measure_hbm_copy(double *gbs) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(gbs != nullptr, "null pointer");
     Runtime &R = rt();
@@ -332,41 +340,41 @@ int mmo_measure_hbm_copy(double *gbs) {
     cudaEventDestroy(e1);
     *gbs = best;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_dev_alloc(size_t bytes, void **dptr) {
+int mmo_dev_alloc(size_t bytes, void **dptr) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(dptr != nullptr, "mmo_dev_alloc: null pointer");
     MMO_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
     return MMO_OK;
-}
-int mmo_dev_free(void *dptr) {
+} MMO_CATCH_ALL
+int mmo_dev_free(void *dptr) try {
     MMO_TRY(require_ready());
     if (dptr) MMO_CUDA(cudaFree(dptr));
     return MMO_OK;
-}
-int mmo_h2d(void *dptr, const void *host, size_t bytes) {
+} MMO_CATCH_ALL
+int mmo_h2d(void *dptr, const void *host, size_t bytes) try {
     MMO_TRY(require_ready());
     MMO_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, rt().stream));
     MMO_CUDA(cudaStreamSynchronize(rt().stream));
     return MMO_OK;
-}
-int mmo_d2h(void *host, const void *dptr, size_t bytes) {
+} MMO_CATCH_ALL
+int mmo_d2h(void *host, const void *dptr, size_t bytes) try {
     MMO_TRY(require_ready());
     MMO_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, rt().stream));
     MMO_CUDA(cudaStreamSynchronize(rt().stream));
     return MMO_OK;
-}
-int mmo_host_alloc(size_t bytes, void **hptr) {
+} MMO_CATCH_ALL
+int mmo_host_alloc(size_t bytes, void **hptr) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(hptr != nullptr, "mmo_host_alloc: null pointer");
     MMO_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
     return MMO_OK;
-}
-int mmo_host_free(void *hptr) {
+} MMO_CATCH_ALL
+int mmo_host_free(void *hptr) try {
     MMO_TRY(require_ready());
     if (hptr) MMO_CUDA(cudaFreeHost(hptr));
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

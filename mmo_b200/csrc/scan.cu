@@ -104,18 +104,20 @@ struct ScanJob {
 // check at 1x on clashing and non-clashing poses alike)
 static inline double fp32_delta(double e) { return 8.0 * std::max(1e-6 * fabs(e), 1e-4); }
 
-static bool host_bit(const mmo_mask *m, long idx) { return (m->hwords[idx >> 5] >> (idx & 31)) & 1u; }
+// Bitv.get raises outside the vector; here a voxel outside the mask box reads as "not occupied" (mask.cu bit_ijk)
+static bool host_bit(const mmo_mask *m, int i, int j, int k) {
+    if (i < 0 || j < 0 || k < 0 || i >= m->dims[0] || j >= m->dims[1] || k >= m->dims[2]) return false;
+    const size_t idx = (size_t)i + (size_t)j * m->dims[0] + (size_t)k * m->dims[0] * m->dims[1];
+    return (m->hwords[idx >> 5] >> (idx & 31)) & 1u;
+}
 
 // G3D.vdW_clash_AND on the host copy of the mask
 static bool host_clash_and(const mmo_mask *m, double x, double y, double z) {
     double inv = 1.0 / m->step;
-    int x_dim = m->dims[0], xy_dim = m->dims[0] * m->dims[1];
     int i0 = (int)(x * inv), j0 = (int)(y * inv), k0 = (int)(z * inv);
     int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
-    long j0x = (long)j0 * x_dim, j1x = (long)j1 * x_dim, k0xy = (long)k0 * xy_dim, k1xy = (long)k1 * xy_dim;
-    return host_bit(m, i0 + j0x + k0xy) && host_bit(m, i1 + j0x + k0xy) && host_bit(m, i1 + j1x + k0xy) &&
-           host_bit(m, i0 + j1x + k0xy) && host_bit(m, i0 + j0x + k1xy) && host_bit(m, i1 + j0x + k1xy) &&
-           host_bit(m, i1 + j1x + k1xy) && host_bit(m, i0 + j1x + k1xy);
+    return host_bit(m, i0, j0, k0) && host_bit(m, i1, j0, k0) && host_bit(m, i1, j1, k0) && host_bit(m, i0, j1, k0) &&
+           host_bit(m, i0, j0, k1) && host_bit(m, i1, j0, k1) && host_bit(m, i1, j1, k1) && host_bit(m, i0, j1, k1);
 }
 
 // Visiting order of the rotations: k-d leaves of 32 over the stereographic image of the unit
@@ -430,7 +432,7 @@ struct mmo_scan_job { ScanJob J; };
 
 extern "C" {
 
-int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **out) {
+int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **out) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(out != nullptr, "mmo_scan_create: null output pointer");
     *out = nullptr;
@@ -442,15 +444,15 @@ int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **
     if (rc != MMO_OK) { delete h; return rc; }
     *out = h;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_scan_num_points(const mmo_scan_job *job, int64_t *n_active_points) {
+int mmo_scan_num_points(const mmo_scan_job *job, int64_t *n_active_points) try {
     MMO_REQUIRE(job && n_active_points, "mmo_scan_num_points: null pointer");
     *n_active_points = (int64_t)job->J.points.size();
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active) {
+int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active) try {
     MMO_TRY(require_ready());
     MMO_REQUIRE(job != nullptr, "mmo_scan_run: null job");
     int64_t n = (int64_t)job->J.points.size();
@@ -471,21 +473,21 @@ int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return rc;
-}
+} MMO_CATCH_ALL
 
-int mmo_scan_result_get(const mmo_scan_job *job, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+int mmo_scan_result_get(const mmo_scan_job *job, double *top_scores, int64_t *top_frames, mmo_scan_result *res) try {
     MMO_REQUIRE(job && res, "mmo_scan_result_get: null pointer");
     MMO_TRY(scan_finalize(const_cast<mmo_scan_job *>(job)->J));
     scan_fill_result(job->J, top_scores, top_frames, res);
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_scan_destroy(mmo_scan_job *job) {
+int mmo_scan_destroy(mmo_scan_job *job) try {
     delete job;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
-int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, mmo_scan_result *res) {
+int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, mmo_scan_result *res) try {
     MMO_REQUIRE(res != nullptr, "mmo_scan: null result pointer");
     const bool dbg = getenv("MMO_DEBUG_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -501,12 +503,12 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
     mmo_scan_destroy(job);
     if (dbg) fprintf(stderr, "[mmo_scan] create %.1f ms, run %.1f ms, finalize %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
-}
+} MMO_CATCH_ALL
 
 // K-way merge of per-GPU lists; lists need not be sorted.  Order: score ascending, NaN last, ties to
 // the smaller frame (= earlier in the reference's loop order).
 int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64_t *frames,
-                   const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n) {
+                   const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n) try {
     MMO_REQUIRE(n_lists >= 0 && k >= 0 && out_n, "mmo_topk_merge: bad arguments");
     std::vector<ScoreFrame> all;
     for (int l = 0; l < n_lists; l++) {
@@ -523,6 +525,6 @@ int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64
     for (int i = 0; i < n; i++) { out_scores[i] = all[i].s; out_frames[i] = all[i].f; }
     *out_n = n;
     return MMO_OK;
-}
+} MMO_CATCH_ALL
 
 }  // extern "C"

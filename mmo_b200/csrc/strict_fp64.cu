@@ -19,10 +19,10 @@ namespace mmo {
 // UFF.ml:32-51: x_ij = sqrt(x_i*x_j), d_ij = sqrt(D_i*D_j), NaN for unsupported elements
 __constant__ double c_xij[kEltTab * kEltTab];
 __constant__ double c_dij[kEltTab * kEltTab];
-static bool g_tables_ready = false;
+static int g_tables_epoch = -1;     // __constant__ memory is per device: re-uploaded after every mmo_init (Runtime::epoch)
 
 static int ensure_tables() {
-    if (g_tables_ready) return MMO_OK;
+    if (g_tables_epoch == rt().epoch) return MMO_OK;
     double hx[kEltTab * kEltTab], hd[kEltTab * kEltTab];
     for (int a = 0; a < kEltTab; a++)
         for (int b = 0; b < kEltTab; b++) {
@@ -36,7 +36,7 @@ static int ensure_tables() {
         }
     MMO_CUDA(cudaMemcpyToSymbol(c_xij, hx, sizeof hx));
     MMO_CUDA(cudaMemcpyToSymbol(c_dij, hd, sizeof hd));
-    g_tables_ready = true;
+    g_tables_epoch = rt().epoch;
     return MMO_OK;
 }
 
@@ -453,6 +453,8 @@ int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, 
     if (n_poses == 0) return MMO_OK;
     int L = lig->n;
     size_t smem = (size_t)3 * L * sizeof(double) + (size_t)L * sizeof(int32_t) + 16;
+    MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the interpolation kernel", L);
+    if (smem > 48 * 1024) MMO_CUDA(cudaFuncSetAttribute(strict_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelScope ks(K_INTERP);
     strict_interp_kernel<<<(unsigned)((n_poses + 127) / 128), 128, smem, rt().stream>>>(
         geom_of(g), g->maps.p, L, lig->x.p, lig->y.p, lig->z.p, lig->typ.p, src, n_poses, d_out);

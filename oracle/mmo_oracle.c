@@ -448,21 +448,25 @@ void orc_bitmask_whole_protein(int P, const double *px, const double *py, const 
 }
 
 /* src/G3D.ml:162-186 vdW_clash_OR ; 189-213 vdW_clash_AND */
+/* Bitv.get raises outside the vector (the reference would abort); checker and library agree that a voxel outside
+ * the mask box reads as "not occupied"  */
+static int bit_ijk(const int dims[3], const uint8_t *mask, int i, int j, int k) {
+    if (i < 0 || j < 0 || k < 0 || i >= dims[0] || j >= dims[1] || k >= dims[2]) return 0;
+    return mask_get(mask, (size_t)i + (size_t)j * dims[0] + (size_t)k * dims[0] * dims[1]);
+}
 static void corner_bits(double step, const int dims[3], const uint8_t *mask,
                         double x, double y, double z, int bits[8]) {
     double inv = 1.0 / step;
-    int x_dim = dims[0], xy_dim = dims[0] * dims[1];
     int i0 = (int)(x * inv), j0 = (int)(y * inv), k0 = (int)(z * inv);
     int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
-    long j0x = (long)j0 * x_dim, j1x = (long)j1 * x_dim, k0xy = (long)k0 * xy_dim, k1xy = (long)k1 * xy_dim;
-    bits[0] = mask_get(mask, (size_t)(i0 + j0x + k0xy));
-    bits[1] = mask_get(mask, (size_t)(i1 + j0x + k0xy));
-    bits[2] = mask_get(mask, (size_t)(i1 + j1x + k0xy));
-    bits[3] = mask_get(mask, (size_t)(i0 + j1x + k0xy));
-    bits[4] = mask_get(mask, (size_t)(i0 + j0x + k1xy));
-    bits[5] = mask_get(mask, (size_t)(i1 + j0x + k1xy));
-    bits[6] = mask_get(mask, (size_t)(i1 + j1x + k1xy));
-    bits[7] = mask_get(mask, (size_t)(i0 + j1x + k1xy));
+    bits[0] = bit_ijk(dims, mask, i0, j0, k0);
+    bits[1] = bit_ijk(dims, mask, i1, j0, k0);
+    bits[2] = bit_ijk(dims, mask, i1, j1, k0);
+    bits[3] = bit_ijk(dims, mask, i0, j1, k0);
+    bits[4] = bit_ijk(dims, mask, i0, j0, k1);
+    bits[5] = bit_ijk(dims, mask, i1, j0, k1);
+    bits[6] = bit_ijk(dims, mask, i1, j1, k1);
+    bits[7] = bit_ijk(dims, mask, i0, j1, k1);
 }
 int orc_vdw_clash_OR(double step, const int dims[3], const uint8_t *mask, double x, double y, double z) {
     int b[8];

@@ -3,6 +3,8 @@
 fp64 mode: bit-identical (same operations, same order, no FMA).  fp32 mode: within the north-star
 tolerance max(1e-6*|E|, 1e-4 kcal/mol) -- including clashing poses, which the close-contact fp64
 correction pass exists for."""
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,7 @@ from conftest import tol_ok
 from mmo_b200 import pqrs, workloads
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _poses(c2, n, seed, radius=8.0):
@@ -304,3 +307,36 @@ def test_shared_reciprocal_division_is_the_ieee_division(gpu):
     for seed in (1, 20231017):
         assert gpu.lib().mmo_selftest_division(C.c_uint64(seed), C.c_int64(1 << 28), C.byref(bad)) == 0
         assert bad.value == 0
+
+
+def test_strict_tables_survive_a_reinit(tmp_path):
+    """mmo_shutdown + mmo_init start a new epoch: the __constant__ UFF tables of the strict kernels and the pooled
+    blocks belong to the old one.  Run in a subprocess so that the session's handles stay valid."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, mmo_b200, oracle
+from mmo_b200 import workloads
+c2 = workloads.load_c2("docked")
+rec_m = workloads.carve(c2["rec"], c2["roi"][:3], 25.0)
+R, t = workloads.random_poses_in_sphere(64, c2["roi"][:3], 5.0, seed=3)
+def run():
+    rec = mmo_b200.Receptor.from_mol(rec_m); lig = mmo_b200.Ligand.from_mol(c2["lig"], centered=True)
+    e = mmo_b200.Mol.score_poses(rec, lig, R, t, prec=mmo_b200.PREC_FP64)
+    X, Y, Z = oracle.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    want = oracle.ene_inter(rec_m, c2["lig"].q, c2["lig"].anum, X, Y, Z, shifted=True)
+    assert np.array_equal(e, want), "strict energies differ from the oracle"
+    i = mmo_b200.Mol.ene_intra_UFFNB_brute(lig, X[:4], Y[:4], Z[:4])
+    assert np.array_equal(i, oracle.ene_intra(c2["lig"], X[:4], Y[:4], Z[:4]))
+    del rec, lig
+mmo_b200.init(0); run()
+assert mmo_b200.lib().mmo_shutdown() == 0
+mmo_b200.init(0); run()
+print("reinit ok")
+'''
+    script = tmp_path / "reinit.py"
+    script.write_text(code)
+    r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "reinit ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

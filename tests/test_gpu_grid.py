@@ -107,6 +107,34 @@ def test_vdw_mask_and_clash_bit_identical(gpu, orc, c2, c2_roi_rec):
     assert 0 < ref.sum() < len(ref)
 
 
+@pytest.mark.gpu
+def test_clash_poses_partly_outside_the_mask_box(gpu, orc, c2):
+    """poses whose atoms leave the mask box (negative coordinates, beyond the last voxel): Bitv.get would raise in the
+    reference; kernel, host prefilter and oracle agree that outside voxels read as not occupied -- no out-of-bounds
+    read, same flags"""
+    dims = gpu.Grid.from_box(workloads.GRID_STEP, *c2["sim_dims"])
+    m = c2["rec"]
+    mask = gpu.Lds.vdW_volume(m.xs, m.ys, m.zs, m.r, workloads.GRID_STEP, dims)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    rng = np.random.default_rng(77)
+    R, _ = workloads.random_poses_in_sphere(600, (0, 0, 0), 1.0, seed=25)
+    ext = np.array(dims) * workloads.GRID_STEP
+    t = rng.uniform(-30.0, 1.0, (600, 3)) * (rng.random((600, 3)) < 0.5) + rng.uniform(0.0, 1.0, (600, 3)) * ext
+    t[::4] = rng.uniform(-1e4, 1e4, (150, 3))                   # far outside, both signs
+    t[1::4] = ext + rng.uniform(-3.0, 20.0, (150, 3))           # around the upper corner
+    got = gpu.Mol.protein_ligand_clash(mask, lig, R, t)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    ref = np.array([orc.protein_ligand_clash(workloads.GRID_STEP, dims, mask.bits, X[p], Y[p], Z[p]) for p in range(len(R))])
+    assert np.array_equal(got, ref)
+    assert not got[::4].any()
+    # the scan's host-side centre prefilter (vdW_clash_AND) with a ROI that pokes out of the mask box
+    rot = gpu.SO3.rotations(4)
+    roi = (1.0, 1.0, 1.0, 3.0)
+    res = gpu.Lds.exhaustive_rigid_ligand_docking(3, roi, 1.0, rot, lig, rec=gpu.Receptor.from_mol(workloads.carve(m, roi[:3], 30.0)),
+                                                  vdw_mask=mask)
+    assert res["n_scored"] >= 0
+
+
 def test_n3_masks_bit_identical(gpu, orc, c2):
     """first solvent shell, whole-protein and ROI-only bitmasks (lds.ml:97-145, 172-184, 269-305) on the device
     against the oracle's literal loops; 1 A grid over the simulation box keeps the CPU side short"""
