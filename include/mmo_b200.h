@@ -78,6 +78,9 @@ int mmo_sync(void);
 int mmo_measure_fp32_peak(double *tflops);
 int mmo_measure_fp64_peak(double *tflops);
 int mmo_measure_hbm_copy(double *gbs);
+/* the gather roof of the interpolated lookup (K4): 8-corner reads of pseudo-random cells of T type-major f32 maps of
+ * the given dims (L2 resident when they fit), no arithmetic; lookups/s (x 32 B = gathered bytes/s) */
+int mmo_measure_l2_gather(const int32_t dims[3], int32_t T, double *lookups_per_s);
 /* raw device buffers, so that a caller can keep pose batches resident in HBM */
 int mmo_dev_alloc(size_t bytes, void **dptr);
 int mmo_dev_free(void *dptr);
@@ -290,6 +293,15 @@ int mmo_scan_num_points(const mmo_scan_job *job, int64_t *n_active_points);
 int mmo_scan_run(mmo_scan_job *job, int64_t first_active, int64_t n_active);
 int mmo_scan_result_get(const mmo_scan_job *job, double *top_scores, int64_t *top_frames, mmo_scan_result *res);
 int mmo_scan_destroy(mmo_scan_job *job);
+/* The rotation set of a run stays resident on the device between mmo_scan calls (lds builds it once per run,
+ * src/lds.ml:1748-1752): a call that hands over the same bytes again skips the upload.  mode 1 = copy the caller's
+ * rotations to the device on every call anyway (bench.py's end-to-end figure: every byte of the step's input moves);
+ * the visiting order (a k-d sort on the host) is reused whenever the bytes are unchanged.  Default 0. */
+int mmo_scan_set_rot_cache(int mode);
+/* k smallest of n device-resident energies (a conformer screen's top-k, src/lds.ml:1055-1064 semantics: ascending,
+ * NaN last, ties to the smaller id); id of entry p = id_base + p.  out arrays hold k entries. */
+int mmo_topk_select_dev(const double *d_E, int64_t n, int32_t k, int64_t id_base, double *out_scores,
+                        int64_t *out_ids, int32_t *out_n);
 /* K-way merge of per-GPU top-k lists: (score, frame) ascending, ties to the smaller frame */
 int mmo_topk_merge(int32_t n_lists, int32_t k, const double *scores, const int64_t *frames,
                    const int32_t *counts, double *out_scores, int64_t *out_frames, int32_t *out_n);

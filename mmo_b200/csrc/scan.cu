@@ -30,7 +30,7 @@ __device__ __forceinline__ bool sf_less(double s1, long long f1, double s2, long
 // score = e_intra_const +. ene_inter (lds.ml:1324-1325); per-block argmin; candidates with
 // score <= thr are appended to the top-k candidate buffer
 __global__ void __launch_bounds__(256)
-scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restrict__ frames, int64_t n,
+scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restrict__ frames, int64_t id_base, int64_t n,
                    double e_intra, const double *__restrict__ thr, double *__restrict__ cand_s,
                    long long *__restrict__ cand_f, unsigned long long *__restrict__ cand_n,
                    unsigned long long cand_cap, ScoreFrame *__restrict__ block_best) {
@@ -41,7 +41,7 @@ scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restric
     long long f = 0x7fffffffffffffffLL;
     if (p < n) {
         s = e_intra + energies[p];
-        f = frames[p];
+        f = frames ? frames[p] : id_base + p;
         if (cand_cap && s <= *thr) {
             unsigned long long k = atomicAdd(cand_n, 1ull);
             if (k < cand_cap) { cand_s[k] = s; cand_f[k] = f; }
@@ -158,10 +158,18 @@ static void rotation_visit_order(int n_rot, const double *rot9, std::vector<int3
 // (same count, same bytes: one memcmp against the host copy) skips the 72 n_rot bytes upload and the k-d sort.
 // leaked on purpose: must not run a destructor after the CUDA context / the allocator are gone
 static std::shared_ptr<RotSet> &g_rotset = *new std::shared_ptr<RotSet>();
+static int g_rot_cache_mode = 0;      // mmo_scan_set_rot_cache: 1 = move the rotation bytes on every call
 void scan_drop_caches() { g_rotset.reset(); }
 static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out) {
     if (g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch &&
-        memcmp(g_rotset->host.data(), rot9, (size_t)n_rot * 9 * sizeof(double)) == 0) { out = g_rotset; return MMO_OK; }
+        memcmp(g_rotset->host.data(), rot9, (size_t)n_rot * 9 * sizeof(double)) == 0) {
+        if (g_rot_cache_mode == 1) {
+            MMO_CUDA(cudaMemcpyAsync(g_rotset->rot.p, rot9, (size_t)n_rot * 9 * sizeof(double), cudaMemcpyHostToDevice, rt().stream));
+            MMO_CUDA(cudaStreamSynchronize(rt().stream));
+        }
+        out = g_rotset;
+        return MMO_OK;
+    }
     g_rotset.reset();
     std::shared_ptr<RotSet> rs = std::make_shared<RotSet>();
     rs->n = n_rot; rs->epoch = rt().epoch;
@@ -273,7 +281,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         const unsigned blocks = (unsigned)((n_surv + 255) / 256);
         auto reduce_pass = [&](bool with_candidates) -> int {
             KernelScope ks(K_REDUCE);
-            scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(J.d_E.p, J.d_frames.p, (int64_t)n_surv, P.e_intra_const,
+            scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(J.d_E.p, J.d_frames.p, 0, (int64_t)n_surv, P.e_intra_const,
                                                              J.d_thr.p, J.d_cand_s.p, J.d_cand_f.p, J.d_counters.p + 1,
                                                              with_candidates ? (unsigned long long)J.slab_cap : 0ull,
                                                              J.d_block_best.p);
@@ -503,6 +511,75 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
     mmo_scan_destroy(job);
     if (dbg) fprintf(stderr, "[mmo_scan] create %.1f ms, run %.1f ms, finalize %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
+} MMO_CATCH_ALL
+
+int mmo_scan_set_rot_cache(int mode) try {
+    MMO_REQUIRE(mode == 0 || mode == 1, "mmo_scan_set_rot_cache: mode must be 0 or 1");
+    g_rot_cache_mode = mode;
+    return MMO_OK;
+} MMO_CATCH_ALL
+
+// top-k of a device-resident energy list: per-block minima first (their k-th smallest bounds the k-th best from above),
+// then only the entries below that bound travel to the host, where they are sorted with the reference's tie rule
+int mmo_topk_select_dev(const double *d_E, int64_t n, int32_t k, int64_t id_base, double *out_scores,
+                        int64_t *out_ids, int32_t *out_n) try {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(k > 0 && n >= 0 && out_scores && out_ids && out_n, "mmo_topk_select_dev: bad arguments");
+    *out_n = 0;
+    if (n == 0) return MMO_OK;
+    MMO_REQUIRE(d_E != nullptr, "mmo_topk_select_dev: null energies");
+    Runtime &R = rt();
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    DevBuf<ScoreFrame> d_bb;
+    DevBuf<double> d_thr, d_cs;
+    DevBuf<long long> d_cf;
+    DevBuf<unsigned long long> d_cn;
+    MMO_TRY(d_bb.alloc(blocks)); MMO_TRY(d_thr.alloc(1)); MMO_TRY(d_cn.alloc(1));
+    double thr = INFINITY;
+    std::vector<ScoreFrame> hb(blocks);
+    if (blocks >= (unsigned)k) {
+        KernelScope ks(K_REDUCE);
+        scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(d_E, nullptr, id_base, n, 0.0, d_thr.p, nullptr, nullptr, nullptr, 0ull, d_bb.p);
+        MMO_LAUNCH_CHECK();
+        MMO_CUDA(cudaMemcpyAsync(hb.data(), d_bb.p, blocks * sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));
+        std::vector<double> mins(blocks);
+        for (unsigned b = 0; b < blocks; b++) mins[b] = hb[b].s;
+        std::nth_element(mins.begin(), mins.begin() + (k - 1), mins.end());
+        thr = mins[k - 1];
+    }
+    // capacity: every entry <= thr; thr = +inf (few blocks, or fewer than k finite minima) keeps everything
+    const size_t cap = (size_t)n;
+    MMO_TRY(d_cs.alloc(cap)); MMO_TRY(d_cf.alloc(cap));
+    MMO_CUDA(cudaMemsetAsync(d_cn.p, 0, sizeof(unsigned long long), R.stream));
+    MMO_CUDA(cudaMemcpyAsync(d_thr.p, &thr, sizeof(double), cudaMemcpyHostToDevice, R.stream));
+    {
+        KernelScope ks(K_REDUCE);
+        scan_reduce_kernel<<<blocks, 256, 0, R.stream>>>(d_E, nullptr, id_base, n, 0.0, d_thr.p, d_cs.p, d_cf.p, d_cn.p, (unsigned long long)cap, d_bb.p);
+        MMO_LAUNCH_CHECK();
+    }
+    unsigned long long nc = 0;
+    MMO_CUDA(cudaMemcpyAsync(&nc, d_cn.p, sizeof nc, cudaMemcpyDeviceToHost, R.stream));
+    MMO_CUDA(cudaStreamSynchronize(R.stream));
+    std::vector<double> hs(nc);
+    std::vector<long long> hf(nc);
+    if (nc) {
+        MMO_CUDA(cudaMemcpyAsync(hs.data(), d_cs.p, nc * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaMemcpyAsync(hf.data(), d_cf.p, nc * sizeof(long long), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));
+    }
+    std::vector<ScoreFrame> all(nc);
+    for (size_t i = 0; i < nc; i++) { all[i].s = hs[i]; all[i].f = hf[i]; }
+    auto less = [](const ScoreFrame &a, const ScoreFrame &b) {
+        bool an = a.s != a.s, bn = b.s != b.s;
+        if (an != bn) return bn;
+        return (a.s < b.s) || (a.s == b.s && a.f < b.f);
+    };
+    const size_t keep = std::min<size_t>(all.size(), (size_t)k);
+    std::partial_sort(all.begin(), all.begin() + keep, all.end(), less);
+    for (size_t i = 0; i < keep; i++) { out_scores[i] = all[i].s; out_ids[i] = all[i].f; }
+    *out_n = (int32_t)keep;
+    return MMO_OK;
 } MMO_CATCH_ALL
 
 // K-way merge of per-GPU lists; lists need not be sorted.  Order: score ascending, NaN last, ties to

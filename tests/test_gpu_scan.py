@@ -253,3 +253,45 @@ def test_c2_full_size_scan_properties(gpu, orc, c2, setup):
     better = samp[es < s[-1] - 2e-4]
     assert set(better.tolist()) <= set(f.tolist())
     assert es.min() >= s[0] - 2e-4
+
+
+def test_topk_select_dev_matches_a_host_sort(gpu):
+    """mmo_topk_select_dev (a conformer screen's top-k): ascending, ties to the smaller id, NaN never selected"""
+    import ctypes as C
+    L = gpu.lib()
+    rng = np.random.default_rng(5)
+    for n, k in ((1, 3), (200, 50), (100_000, 100), (300_001, 1000)):
+        e = rng.normal(size=n).round(2)                 # many exact ties
+        e[rng.integers(0, n, max(1, n // 50))] = np.nan
+        if n > 10:
+            e[7] = e[3] = np.nanmin(e) - 1.0            # a tie for the best: the smaller id must come first
+        d = C.c_void_p()
+        assert L.mmo_dev_alloc(C.c_size_t(n * 8), C.byref(d)) == 0
+        assert L.mmo_h2d(d, e.ctypes.data_as(C.c_void_p), C.c_size_t(n * 8)) == 0
+        s, f, m = np.empty(k), np.empty(k, np.int64), C.c_int32()
+        rc = L.mmo_topk_select_dev(d, C.c_int64(n), C.c_int32(k), C.c_int64(1000), s.ctypes.data_as(C.POINTER(C.c_double)),
+                                   f.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(m))
+        assert rc == 0, L.mmo_last_error()
+        L.mmo_dev_free(d)
+        ok = ~np.isnan(e)
+        ids = np.arange(n)[ok]
+        order = np.lexsort((ids, e[ok]))[:k]
+        assert m.value == len(order)
+        assert np.array_equal(s[:m.value], e[ok][order]) and np.array_equal(f[:m.value], ids[order] + 1000)
+
+
+def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
+    import ctypes as C
+    L = gpu.lib()
+    rec = gpu.Receptor.from_mol(c2_roi_rec)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    rot = gpu.SO3.rotations(64)
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 2.0)
+    a = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
+    assert L.mmo_scan_set_rot_cache(1) == 0
+    b = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
+    assert L.mmo_scan_set_rot_cache(0) == 0 and L.mmo_scan_set_rot_cache(7) != 0
+    assert np.array_equal(a["top_scores"], b["top_scores"]) and np.array_equal(a["top_frames"], b["top_frames"])
+    lps = C.c_double()
+    assert L.mmo_measure_l2_gather((C.c_int32 * 3)(81, 81, 81), C.c_int32(22), C.byref(lps)) == 0
+    assert lps.value > 1e9
