@@ -174,6 +174,8 @@ struct mmo_ligand {
     int n_fast = 0;                          // atoms in fast-path order, padded to a multiple of 8
     mmo::DevBuf<int32_t> forder;             // fast-path position -> original atom index
     mmo::DevBuf<int32_t> pair_i, pair_j;     // interacting pairs (i<j, dists>=3) in reference order
+    std::vector<int32_t> h_pair_i, h_pair_j; // host copy
+    mmo::DevBuf<double4> mc_pair_tab;        // mc.cu, built on first use: {x_ij, d_ij, q_i q_j, bits(i | j << 16)} per pair
     int n_pairs = 0;
     mmo::DevBuf<int32_t> d_rb_left, d_rb_right, d_rg_off, d_rg_idx;
 };

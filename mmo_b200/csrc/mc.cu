@@ -6,11 +6,10 @@
 // the intra-ligand non-bonded energy (src/mol.ml:881-903), the Metropolis test (lds.ml:931-934), the
 // acceptance windows (src/SW.ml) and the adaptive step sizes (lds.ml:586-621).
 //
-// One warp per chain.  Scalars (rotation, position, energies, RNG counter) are kept redundantly in
-// every lane -- all lanes execute the same IEEE operations, so they stay identical -- while atoms,
-// pair terms and trilinear look-ups are spread over the lanes.  Sums are then accumulated in the
-// reference's order from a shared-memory staging row read as broadcasts, which keeps every energy
-// bit-identical to the sequential loops of the reference (and of oracle/mmo_oracle_mc.c).
+// One block per chain (see "block per chain" below): warp 0 runs the frame loop, its scalars replicated in its
+// lanes, the other warps produce the energy terms in parallel, and warp 0 adds them up one by one in the
+// reference's order, which keeps every energy bit-identical to the sequential loops of the reference (and of
+// oracle/mmo_oracle_mc.c).
 // sin/cos/exp and the random stream come from include/mmo_detmath.h on both sides (see there).
 // Compiled with -fmad=false.  Reference quirks D1-D6, D14 of SURVEY Appendix D are mirrored.
 #include "common.cuh"
@@ -18,11 +17,11 @@
 #include "../../include/mmo_detmath.h"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace mmo {
 
 constexpr int kBlockSize = 100;      // params.ml:29
-constexpr int kWarpsPerBlock = 4;
 
 struct Sw { unsigned bits[4]; int head, n, accepts, rejects; };   // SW.ml, window of 100 events
 
@@ -50,6 +49,7 @@ struct McArgs {
     const int32_t *lelt, *ltyp;
     int n_pairs;
     const int32_t *pair_i, *pair_j;
+    const double4 *pair_tab;            // {x_ij, d_ij, q_i q_j, bits(i | j << 16)}: one coalesced load per term
     int n_rbonds;
     const int32_t *rb_left, *rb_right, *rg_off, *rg_idx;
     // interpolated scorer (maps != nullptr) ...
@@ -73,6 +73,7 @@ struct McArgs {
     double *best_E, *prev_E, *best_rot, *best_pos, *best_xyz, *step_sizes;   // step_sizes: max_rot, max_trans
     long long *counters;                // 8 per chain: acc_rigid, rej_rigid, acc_conf, rej_conf, ooroi, ezero, too_long, frames
     double *trace;                      // optional: chain 0 only, 4 doubles per frame
+    long long *prof;                    // optional (MMO_MC_PROFILE): chain 0's clock cycles per phase of the frame loop
 };
 
 // rot.ml:22-46
@@ -110,71 +111,21 @@ __device__ __forceinline__ void favg3_smem(const double *ax, const double *ay, c
     out[0] = s0 / (double)n; out[1] = s1 / (double)n; out[2] = s2 / (double)n;
 }
 
-// Mol.ene_intra_UFFNB_brute (mol.ml:881-903): the pair terms are computed 32 at a time, one per lane,
-// parked in shared memory and then added up in the reference's (i<j) order by every lane alike
-// (broadcast reads: one LDS.128 + two DADD per term), which keeps the sum bit-identical.
-constexpr int kTermDoubles = 128;      // per warp: two buffers of 32 double2 term slots
-__device__ __forceinline__ double2 intra_term(const McArgs &a, const double *x, const double *y, const double *z, int k) {
-    double2 t = make_double2(0.0, 0.0);
-    if (k < a.n_pairs) {
-        const int i = __ldg(a.pair_i + k), j = __ldg(a.pair_j + k);
-        const double r = d_nzd(sqrt(d_dist2(x[i], y[i], z[i], x[j], y[j], z[j])));
-        const int tt = __ldg(a.lelt + i) * kEltTab + __ldg(a.lelt + j);
-        const Divisor by_r = make_divisor(r);
-        const double p6 = d_pow6(div_by(__ldg(a.xij + tt), by_r));
-        t.x = div_by(__ldg(a.lq + i) * __ldg(a.lq + j), by_r);
-        t.y = __ldg(a.dij + tt) * ((-2.0 * p6) + (p6 * p6));
-    }
+// one term of Mol.ene_intra_UFFNB_brute (mol.ml:881-903): {q_i q_j / r, d_ij (p6^2 - 2 p6)} of interacting pair k
+__device__ __forceinline__ double4 ld_tab(const double4 *p) {
+    const double2 u = __ldg((const double2 *)p), v = __ldg((const double2 *)p + 1);
+    return make_double4(u.x, u.y, v.x, v.y);
+}
+__device__ __forceinline__ double2 intra_term(const double4 e, const double *x, const double *y, const double *z) {
+    const unsigned ij = (unsigned)__double2loint(e.w);
+    const int i = (int)(ij & 0xffffu), j = (int)(ij >> 16);
+    const double r = d_nzd(sqrt(d_dist2(x[i], y[i], z[i], x[j], y[j], z[j])));
+    const Divisor by_r = make_divisor(r);
+    const double p6 = d_pow6(div_by(e.x, by_r));                  // UFF.vdW_xiDi: x_ij = sqrt(x_i x_j)
+    double2 t;
+    t.x = div_by(e.z, by_r);                                      // (q_i *. q_j) /. r
+    t.y = e.y * ((-2.0 * p6) + (p6 * p6));
     return t;
-}
-// Software pipelined: the terms of round r + 1 are computed (sqrt and division chains) between the store of round r
-// and its in-order summation, two independent dependency chains the scheduler can interleave; two term buffers.
-__device__ double intra_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
-                               double2 *terms) {
-    double se = 0.0, sv = 0.0;
-    double2 t = intra_term(a, x, y, z, lane);
-    int buf = 0;
-    for (int base = 0; base < a.n_pairs; base += 32) {
-        double2 *tb = terms + 32 * buf;
-        __syncwarp();
-        tb[lane] = t;
-        __syncwarp();
-        t = intra_term(a, x, y, z, base + 32 + lane);                 // next round (zeros beyond the last pair)
-        const int lim = min(32, a.n_pairs - base);
-        if (lim == 32) {
-#pragma unroll
-            for (int l = 0; l < 32; l++) {
-                const double2 u = tb[l];
-                se = se + u.x;
-                sv = sv + u.y;
-            }
-        } else {
-            for (int l = 0; l < lim; l++) {
-                const double2 u = tb[l];
-                se = se + u.x;
-                sv = sv + u.y;
-            }
-        }
-        buf ^= 1;
-    }
-    return (kElecWeight * se) + sv;
-}
-
-// Mol.ene_inter_UFF_interp (mol.ml:1012-1020): one trilinear look-up per lane, summed in atom order
-__device__ double interp_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
-                                double2 *terms) {
-    double res = 0.0;
-    for (int base = 0; base < a.L; base += 32) {
-        const int j = base + lane;
-        double t = 0.0;
-        if (j < a.L) t = d_trilin(a.g, a.maps + (size_t)__ldg(a.ltyp + j) * a.g.nvox, x[j], y[j], z[j]);
-        __syncwarp();
-        terms[lane].x = t;
-        __syncwarp();
-        const int lim = min(32, a.L - base);
-        for (int l = 0; l < lim; l++) res = res + terms[l].x;
-    }
-    return res;
 }
 
 // Mol.ene_inter_UFF_shifted_brute (mol.ml:822-849) for one chain: receptor atoms are dealt to the lanes,
@@ -227,9 +178,496 @@ __device__ double direct_energy(const McArgs &a, const double *x, const double *
     return (kElecWeight * te) + tv;
 }
 
-__device__ __forceinline__ double inter_energy(const McArgs &a, const double *x, const double *y, const double *z,
+// ---- block per chain ------------------------------------------------------------------------------------
+// One block of NT threads runs one chain.  Warp 0 owns the chain: every scalar of the frame loop (rotation, position,
+// energies, RNG counter, windows) lives in its registers, replicated in its 32 lanes, and it alone adds up the energy
+// terms, one by one in the reference's order -- which is what keeps every energy bit-identical to the sequential
+// loops of the reference and sets the latency floor of a frame (991 dependent double additions for the fixture).
+// The other warps ("helpers") only produce terms: after warp 0 has published the trial coordinates (one
+// __syncthreads per frame), they compute the intra-ligand pair terms chunk by chunk, all chunks' terms in parallel
+// across the block, and signal every finished chunk on its own named barrier (bar.arrive); warp 0 sums chunk c
+// (bar.sync on its barrier) while the helpers are already on chunk c + 1.  The trilinear look-ups of E_inter go the
+// same way (one per thread of the first warps, barrier 15).  Commands to the helpers are double buffered by sequence
+// number, so that warp 0 can post the next one while a helper still reads the last.
+constexpr int kMaxChunks = 14;                     // named barriers 1..14 carry the intra chunks, 15 the look-ups
+struct McCmd { int src, do_intra, do_inter, quit; };
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct McShared {                                  // pointers into the block's dynamic shared memory
+    double *cx, *cy, *cz, *px, *py, *pz, *lx, *ly, *lz, *dr, *drp, *iterms, *keep;
+    double2 *terms, *scratch;
+    Sw *sw_bond;
+    volatile McCmd *cmd;
+    int *ltyp, *rb;                                // FF types [L]; rotatable bonds: left[nrb] right[nrb] rg_off[nrb + 1] rg_idx[...]
+};
+
+// helper side of one command: the intra chunks (table entry of the next term prefetched while the current one is
+// computed), then the look-up terms (threads of the first n_lw helper warps)
+template <int NT>
+__device__ __forceinline__ void mc_produce(const McArgs &a, const McShared &S, const McCmd c, int tid, int n_lw, int R, int CH) {
+    const int h = tid - 32, H = NT - 32;
+    const double *x = c.src ? S.cx : S.lx, *y = c.src ? S.cy : S.ly, *z = c.src ? S.cz : S.lz;
+    const long long tp0 = clock64();
+    if (c.do_intra) {
+        // invariant: at the start of chunk r, e = the table entry of this thread's first term of the chunk (if it has one)
+        double4 e = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (R > 0 && h < min(a.n_pairs, CH)) e = ld_tab(a.pair_tab + h);
+        for (int r = 0; r < R; r++) {
+            const int k1 = min(a.n_pairs, (r + 1) * CH);
+            const int kf = (r + 1) * CH + h;                       // this thread's first term of the next chunk
+            const bool has_next = (r + 1 < R) && kf < min(a.n_pairs, (r + 2) * CH);
+            int k = r * CH + h;
+            if (k >= k1 && has_next) e = ld_tab(a.pair_tab + kf);
+            for (; k < k1; k += H) {
+                const int kn = k + H;
+                double4 en = e;
+                if (kn < k1) en = ld_tab(a.pair_tab + kn);
+                else if (has_next) en = ld_tab(a.pair_tab + kf);
+                S.terms[k] = intra_term(e, x, y, z);
+                e = en;
+            }
+            for (; k < (r + 1) * CH; k += H) S.terms[k] = make_double2(0.0, 0.0);      // padding of the last chunk(s)
+            __threadfence_block();
+            bar_arrive(1 + r, NT);
+        }
+        if (a.prof && blockIdx.x == 0 && h == 0) a.prof[7] += clock64() - tp0;
+    }
+    if (c.do_inter && h < n_lw * 32) {
+        for (int j = h; j < a.L; j += n_lw * 32)
+            S.iterms[j] = d_trilin(a.g, a.maps + (size_t)S.ltyp[j] * a.g.nvox, x[j], y[j], z[j]);
+        __threadfence_block();
+        bar_arrive(15, n_lw * 32 + 32);
+    }
+}
+
+// warp 0: post a command, then add everything up in the reference's order as the helpers deliver it
+template <int NT>
+__device__ __forceinline__ void mc_eval(const McArgs &a, const McShared &S, int lane, int &seq, int src, bool do_intra,
+                                        bool do_inter, int n_lw, int R, int CH, double &E_intra, double &E_inter, long long *pc) {
+    const bool interp = do_inter && a.maps != nullptr;
+    long long t0 = clock64();
+    if (lane == 0) {
+        volatile McCmd *dst = S.cmd + (seq & 1);
+        dst->src = src; dst->do_intra = do_intra ? 1 : 0; dst->do_inter = interp ? 1 : 0; dst->quit = 0;
+    }
+    seq++;
+    __syncthreads();                              // coordinates and command visible to the helpers
+    const double *x = src ? S.cx : S.lx, *y = src ? S.cy : S.ly, *z = src ? S.cz : S.lz;
+    { const long long t = clock64(); pc[2] += t - t0; t0 = t; }
+    if (do_inter && !interp) E_inter = direct_energy(a, x, y, z, lane, S.scratch);
+    if (do_intra) {
+        double se = 0.0, sv = 0.0;                 // Mol.ene_intra_UFFNB_brute (mol.ml:881-903), pairs in (i<j) order
+        for (int r = 0; r < R; r++) {
+            const long long tb = clock64();
+            bar_sync(1 + r, NT);
+            pc[6] += clock64() - tb;
+            // Rotating buffer of 8 terms: the load of term k + 8 is issued when term k is consumed, ~66 cycles (8 dependent
+            // DADDs) ahead of its own use, so the chain never waits on shared memory.  Every chunk holds CH terms (a
+            // multiple of 8): the helpers fill the slots beyond the last pair with +0.0, which leaves the (never -0.0)
+            // running sums unchanged.
+            const double2 *tk = S.terms + r * CH;
+            double2 u[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) u[q] = tk[q];
+            for (int k = 8; k < CH; k += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    se = se + u[q].x;
+                    sv = sv + u[q].y;
+                    u[q] = tk[k + q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) { se = se + u[q].x; sv = sv + u[q].y; }
+        }
+        E_intra = (kElecWeight * se) + sv;
+        { const long long t = clock64(); pc[4] += t - t0; t0 = t; }
+    }
+    if (interp) {
+        bar_sync(15, n_lw * 32 + 32);
+        double res = 0.0;                          // Mol.ene_inter_UFF_interp (mol.ml:1012-1020): res := !res +. trilin ...
+        int j = 0;
+        for (; j + 8 <= a.L; j += 8) {
+            double u[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) u[q] = S.iterms[j + q];
+#pragma unroll
+            for (int q = 0; q < 8; q++) res = res + u[q];
+        }
+        for (; j < a.L; j++) res = res + S.iterms[j];
+        E_inter = res;
+    }
+    pc[3] += clock64() - t0;
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+mc_chain_kernel(McArgs a) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t chain = blockIdx.x;
+    const int L = a.L, nrb = a.n_rbonds, nrb1 = max(nrb, 1);
+    // chunks of the intra terms (one named barrier each)
+    const int H = NT - 32;
+    const int R = a.n_pairs > 0 ? min(kMaxChunks, (a.n_pairs + H - 1) / H) : 0;
+    const int CH = R > 0 ? (((a.n_pairs + R - 1) / R + 7) & ~7) : 8;      // a multiple of 8 (warp 0's rotating buffer)
+    McShared S;
+    S.cx = smem; S.cy = S.cx + L; S.cz = S.cy + L;                                  // conf
+    S.px = S.cz + L; S.py = S.px + L; S.pz = S.py + L;                              // conf' (proposed)
+    S.lx = S.pz + L; S.ly = S.lx + L; S.lz = S.ly + L;                              // lig'
+    S.dr = S.lz + L; S.drp = S.dr + nrb1;                                           // per-bond step sizes of conf / conf'
+    S.iterms = S.drp + nrb1;                                                        // L look-up terms
+    S.keep = S.iterms + L;                                                          // rot0[9] pos0[3] best_rot[9] best_pos[3]
+    double *end = S.keep + 24;
+    end += ((size_t)(end - smem) & 1);                                              // 16-byte alignment
+    S.scratch = (double2 *)end;                                                     // 32 slots (direct scorer)
+    S.terms = S.scratch + 32;                                                       // n_pairs intra terms
+    S.sw_bond = (Sw *)(S.terms + max(R * CH, 1));
+    S.cmd = (volatile McCmd *)(S.sw_bond + nrb1);
+    S.ltyp = (int *)(S.cmd + 2);
+    S.rb = S.ltyp + L;
+    const int n_lw = min(NT / 32 - 1, (L + 31) / 32);      // helper warps that share the look-ups
+    // constant tables of the chain in shared memory (global loads would sit on warp 0's critical path)
+    const int rg_total = nrb > 0 ? __ldg(a.rg_off + nrb) : 0;
+    for (int j = tid; j < L; j += NT) S.ltyp[j] = a.maps ? __ldg(a.ltyp + j) : 0;
+    for (int b = tid; b < nrb; b += NT) { S.rb[b] = __ldg(a.rb_left + b); S.rb[nrb + b] = __ldg(a.rb_right + b); }
+    for (int b = tid; b <= nrb && nrb > 0; b += NT) S.rb[2 * nrb + b] = __ldg(a.rg_off + b);
+    for (int g = tid; g < rg_total; g += NT) S.rb[3 * nrb + 1 + g] = __ldg(a.rg_idx + g);
+    __syncthreads();
+    const int *const s_left = S.rb, *const s_right = S.rb + nrb, *const s_rgoff = S.rb + 2 * nrb, *const s_rgidx = S.rb + 3 * nrb + 1;
+
+    if (wid != 0) {
+        // ---- helpers: wait for a command, produce its terms ----
+        for (int seq = 0;; seq++) {
+            __syncthreads();
+            const volatile McCmd *src = S.cmd + (seq & 1);
+            McCmd c;
+            c.src = src->src; c.do_intra = src->do_intra; c.do_inter = src->do_inter; c.quit = src->quit;
+            if (c.quit) return;
+            mc_produce<NT>(a, S, c, tid, n_lw, R, CH);
+        }
+    }
+
+    // ---- warp 0: the chain ----
+    int seq = 0;
+    double *const cx = S.cx, *const cy = S.cy, *const cz = S.cz, *const px = S.px, *const py = S.py, *const pz = S.pz;
+    double *const lx = S.lx, *const ly = S.ly, *const lz = S.lz, *const dr = S.dr, *const drp = S.drp;
+    double *const rot0 = S.keep, *const pos0 = S.keep + 9, *const best_rot = S.keep + 12, *const best_pos = S.keep + 21;
+    Sw *const sw_bond = S.sw_bond;
+    const bool flexible = a.tweak_rbonds && nrb > 0;
+    // frame counters fit 32 bits (n_steps is an int32): 32-bit remainders instead of the 64-bit software division
+    const int rbf = a.no_flip ? 0x7fffffff : kBlockSize;
+    const double target_low = 0.5 - 0.05, target_high = 0.5 + 0.05;    // lds.ml:651-652
+    const uint64_t seed = a.seeds[chain];
+    uint64_t ctr = 0;
+
+    for (int j = lane; j < L; j += 32) { cx[j] = a.lx[j]; cy[j] = a.ly[j]; cz[j] = a.lz[j]; }
+    for (int b = lane; b < nrb; b += 32) { dr[b] = a.p_max_rbond_rot; sw_reset(sw_bond[b]); }
+    double ccen[3] = {0.0, 0.0, 0.0}, pcen[3] = {0.0, 0.0, 0.0};        // conf.center, conf'.center
+    Sw sw_rigid;
+    sw_reset(sw_rigid);
+    double max_rot = a.p_max_rot, max_trans = a.p_max_trans;
+    double rot[9], pos[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) rot[k] = a.rot0[chain * 9 + k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pos[k] = a.pos0[chain * 3 + k];
+    if (lane < 9) { rot0[lane] = a.rot0[chain * 9 + lane]; best_rot[lane] = (lane % 4 == 0) ? 1.0 : 0.0; }
+    if (lane < 3) { pos0[lane] = a.pos0[chain * 3 + lane]; best_pos[lane] = 0.0; }
+    double *bxyz = a.best_xyz + chain * 3 * (int64_t)L;
+    __syncwarp();
+    // start_conf = rotate_then_translate_copy centered_lig rot0 pos0 (lds.ml:758)
+    for (int j = lane; j < L; j += 32) {
+        double x, y, z;
+        rot_apply(rot, cx[j], cy[j], cz[j], x, y, z);
+        lx[j] = x + pos[0]; ly[j] = y + pos[1]; lz[j] = z + pos[2];
+        bxyz[j] = lx[j]; bxyz[L + j] = ly[j]; bxyz[2 * L + j] = lz[j];
+    }
+    double const_intra = 0.0, dummy = 0.0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles: 0 conformer move, 1 rigid move + lig', 2 hand-over, 3 E_inter, 4 E_intra sum, 5 accept/bookkeeping
+    if (a.intra_nb && !flexible) mc_eval<NT>(a, S, lane, seq, 1, true, false, n_lw, R, CH, const_intra, dummy, pc);
+    double prev_E_intra = 0.0, prev_E_inter = 0.0;
+    if (a.intra_nb && !flexible) prev_E_intra = const_intra;
+    mc_eval<NT>(a, S, lane, seq, 0, a.intra_nb && flexible, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
+    double prev_E = prev_E_inter + prev_E_intra;
+#pragma unroll
+    for (int k = 0; k < 8; k++) pc[k] = 0;
+    double best_E = prev_E;
+    int rigid_step = 0, conf_step = 0;
+    int n_acc_r = 0, n_rej_r = 0, n_acc_c = 0, n_rej_c = 0, n_ooroi = 0, n_ezero = 0, too_long = 0;
+    int frame = 0;
+    for (; frame < a.n_steps; frame++) {
+        const bool rigid = (frame & 1) == 0;
+        int just_rotated = -1;
+        int which = 0;                                  // conf' is: 0 = conf, 1 = proposed copy, 2 = centred template
+        long long tf0 = clock64();
+        if (!rigid) {
+            if (flexible) {
+                for (int j = lane; j < L; j += 32) { px[j] = cx[j]; py[j] = cy[j]; pz[j] = cz[j]; }
+                for (int b = lane; b < nrb; b += 32) drp[b] = dr[b];
+                __syncwarp();
+                int bond;
+                double alpha;
+                {
+                    double u = mmo_rng_uniform(seed, ctr++);
+                    bond = (int)(u * (double)nrb);
+                    if (bond >= nrb) bond = nrb - 1;
+                    double u2 = mmo_rng_uniform(seed, ctr++);
+                    if (conf_step > 0 && conf_step % rbf == 0) alpha = (2.0 * a.pi) * u2 - a.pi;     // Mol.flip_rbond
+                    else { double d = drp[bond]; alpha = (2.0 * d) * u2 - d; }                       // Mol.tweak_rbond
+                }
+                // Mol.rotate_bond (mol.ml:610-631)
+                const int left = s_left[bond], right = s_right[bond];
+                const double ox = px[right], oy = py[right], oz = pz[right];
+                const double ax = ox - px[left], ay = oy - py[left], az = oz - pz[left];
+                const double mag = sqrt(ax * ax + ay * ay + az * az);
+                double br[9];
+                {
+                    const Divisor by_mag = make_divisor(mag);      // three IEEE quotients by the same |v| (V3.normalize), bit-identical
+                    const double ux = div_by(ax, by_mag), uy = div_by(ay, by_mag), uz = div_by(az, by_mag);
+                    double s, c;
+                    mmo_det_sincos(alpha, &s, &c);
+                    const double omc = 1.0 - c;                  // rot.ml:136-146
+                    br[0] = c + ux * ux * omc; br[1] = ux * uy * omc - uz * s; br[2] = ux * uz * omc + uy * s;
+                    br[3] = ux * uy * omc + uz * s; br[4] = c + uy * uy * omc; br[5] = uy * uz * omc - ux * s;
+                    br[6] = ux * uz * omc - uy * s; br[7] = uy * uz * omc + ux * s; br[8] = c + uz * uz * omc;
+                }
+                __syncwarp();
+                const int g0 = s_rgoff[bond], g1 = s_rgoff[bond + 1];
+                for (int g = g0 + lane; g < g1; g += 32) {
+                    const int i = s_rgidx[g];
+                    double x, y, z;
+                    rot_apply(br, px[i] - ox, py[i] - oy, pz[i] - oz, x, y, z);
+                    px[i] = x + ox; py[i] = y + oy; pz[i] = z + oz;
+                }
+                __syncwarp();
+                favg3_smem(px, py, pz, L, pcen);                                                       // update_center
+                just_rotated = bond;
+                // Mol.check_elongation_exn lig 12.0 (mol.ml:576-591): maxi = max_j (0.01 +. dist center xyz_j).  sqrt and +. are
+                // monotonic, so the maximum is taken over the squared distances and one square root gives the same double
+                double maxd2 = 0.0;
+                for (int j = lane; j < L; j += 32) maxd2 = fmax(maxd2, d_dist2(pcen[0], pcen[1], pcen[2], px[j], py[j], pz[j]));
+                for (int o = 16; o > 0; o >>= 1) maxd2 = fmax(maxd2, __shfl_xor_sync(0xffffffffu, maxd2, o));
+                const double maxi = 0.01 + sqrt(maxd2);
+                if (maxi > 12.0) { too_long = 1; break; }          // Mol.Too_long ends this run (lds.ml:996-997)
+                which = 1;
+            } else {
+                which = 2;
+            }
+        }
+        { const long long t = clock64(); pc[0] += t - tf0; tf0 = t; }
+        double rotp[9], posp[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) rotp[k] = rot[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) posp[k] = pos[k];
+        if (rigid) {
+            // right-to-left evaluation: rand_trans (z, y, x) before rand_rot (theta, axis)
+            const double dz = 2.0 * mmo_rng_uniform(seed, ctr++) - 1.0;
+            const double dy = 2.0 * mmo_rng_uniform(seed, ctr++) - 1.0;
+            const double dx = 2.0 * mmo_rng_uniform(seed, ctr++) - 1.0;
+            posp[0] = pos[0] + dx * max_trans; posp[1] = pos[1] + dy * max_trans; posp[2] = pos[2] + dz * max_trans;
+            const double theta = (2.0 * max_rot) * mmo_rng_uniform(seed, ctr++) - max_rot;
+            int axis = (int)(mmo_rng_uniform(seed, ctr++) * 3.0);
+            if (axis > 2) axis = 2;
+            double rb[9];
+            det_rot_axis(axis, theta, rb);
+            rot_mult(rb, rot, rotp);                               // move.ml:31
+        }
+        // lig' = center_rotate_translate_copy conf' rot' pos' (mol.ml:705-710)
+        {
+            const double *sx = which == 1 ? px : (which == 2 ? a.lx : cx);
+            const double *sy = which == 1 ? py : (which == 2 ? a.ly : cy);
+            const double *sz = which == 1 ? pz : (which == 2 ? a.lz : cz);
+            const double *cen = which == 1 ? pcen : ccen;
+            const double nx = which == 2 ? -0.0 : -cen[0], ny = which == 2 ? -0.0 : -cen[1], nz = which == 2 ? -0.0 : -cen[2];
+            for (int j = lane; j < L; j += 32) {
+                double x, y, z;
+                rot_apply(rotp, sx[j] + nx, sy[j] + ny, sz[j] + nz, x, y, z);
+                lx[j] = x + posp[0]; ly[j] = y + posp[1]; lz[j] = z + posp[2];
+            }
+        }
+        // D2: a conformer frame overwrites prev_E_intra with the trial's value, accepted or not
+        if (!rigid && a.intra_nb && !flexible) prev_E_intra = const_intra;
+        { const long long t = clock64(); pc[1] += t - tf0; }
+        mc_eval<NT>(a, S, lane, seq, 0, !rigid && a.intra_nb && flexible, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
+        tf0 = clock64();
+        const double curr_E = prev_E_inter + prev_E_intra;
+        int accepted = -1;
+        const double ddx = a.roi_c[0] - (0.0 + posp[0]), ddy = a.roi_c[1] - (0.0 + posp[1]), ddz = a.roi_c[2] - (0.0 + posp[2]);
+        const double dist_roi = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+        bool do_reset = false;
+        if (a.hard_roi) {                                    // D1: everything below hangs off --hard-ROI
+            if (dist_roi > a.roi_r) { do_reset = true; n_ooroi++; }
+            else if (prev_E_inter == 0.0) { do_reset = true; n_ezero++; }          // D6
+            else {
+                bool acc = curr_E <= prev_E;
+                if (!acc) acc = mmo_rng_uniform(seed, ctr++) < mmo_det_exp((-(curr_E - prev_E)) * a.beta);
+                accepted = acc ? 1 : 0;
+                if (rigid) { sw_process(sw_rigid, acc); if (acc) n_acc_r++; else n_rej_r++; }
+                else {
+                    if (just_rotated > -1 && lane == 0) sw_process(sw_bond[just_rotated], acc);
+                    if (acc) n_acc_c++; else n_rej_c++;
+                }
+                __syncwarp();
+                if (acc) {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) rot[k] = rotp[k];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) pos[k] = posp[k];
+                    prev_E = curr_E;
+                    if (which == 1) {                              // conf := conf'
+                        for (int j = lane; j < L; j += 32) { cx[j] = px[j]; cy[j] = py[j]; cz[j] = pz[j]; }
+                        for (int b = lane; b < nrb; b += 32) dr[b] = drp[b];
+                        ccen[0] = pcen[0]; ccen[1] = pcen[1]; ccen[2] = pcen[2];
+                    } else if (which == 2) {
+                        for (int j = lane; j < L; j += 32) { cx[j] = a.lx[j]; cy[j] = a.ly[j]; cz[j] = a.lz[j]; }
+                        for (int b = lane; b < nrb; b += 32) dr[b] = a.p_max_rbond_rot;
+                        ccen[0] = ccen[1] = ccen[2] = 0.0;
+                    }
+                }
+                if (curr_E < best_E) {                             // D3
+                    best_E = curr_E;
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 9; k++) best_rot[k] = rotp[k];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) best_pos[k] = posp[k];
+                    }
+                    for (int j = lane; j < L; j += 32) { bxyz[j] = lx[j]; bxyz[L + j] = ly[j]; bxyz[2 * L + j] = lz[j]; }
+                }
+                if (rigid && rigid_step > 0 && rigid_step % kBlockSize == 0) {     // lds.ml:586-600
+                    const double ar = sw_ratio(sw_rigid);
+                    if (ar <= target_low) { max_trans = 0.95 * max_trans; max_rot = 0.95 * max_rot; }
+                    else if (ar >= target_high) {
+                        max_trans = 1.05 * max_trans;
+                        const double m = 1.05 * max_rot;
+                        max_rot = (a.pi <= m) ? a.pi : m;
+                    }
+                }
+                if (flexible && !rigid && conf_step > 0 && conf_step % (kBlockSize * nrb) == 0) {
+                    __syncwarp();
+                    double *tgt = acc ? dr : drp;                  // D4
+                    for (int b = lane; b < nrb; b += 32) {
+                        const double ar = sw_ratio(sw_bond[b]);
+                        if (ar <= target_low) tgt[b] = 0.95 * tgt[b];
+                        else if (ar >= target_high) { const double m = 1.05 * tgt[b]; tgt[b] = (a.pi <= m) ? a.pi : m; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (do_reset) {                                      // reset_run_params (lds.ml:632-648)
+            max_rot = a.p_max_rot; max_trans = a.p_max_trans;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 9; k++) rot[k] = rot0[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) pos[k] = pos0[k];
+            __syncwarp();
+            if (lane < 9) best_rot[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
+            if (lane < 3) best_pos[lane] = 0.0;
+            prev_E = INFINITY; best_E = INFINITY;
+            for (int j = lane; j < L; j += 32) {
+                double x, y, z;
+                rot_apply(rot, a.lx[j], a.ly[j], a.lz[j], x, y, z);
+                bxyz[j] = x + pos[0]; bxyz[L + j] = y + pos[1]; bxyz[2 * L + j] = z + pos[2];
+            }
+            sw_reset(sw_rigid);
+        }
+        if (a.trace && chain == 0 && lane == 0) {
+            a.trace[4 * (size_t)frame] = curr_E; a.trace[4 * (size_t)frame + 1] = prev_E_inter;
+            a.trace[4 * (size_t)frame + 2] = prev_E_intra; a.trace[4 * (size_t)frame + 3] = (double)accepted;
+        }
+        if (rigid) rigid_step++; else conf_step++;
+        __syncwarp();
+        pc[5] += clock64() - tf0;
+    }
+    if (a.prof && chain == 0 && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) a.prof[k] = pc[k];
+    }
+    // release the helpers
+    if (lane == 0) { volatile McCmd *dst = S.cmd + (seq & 1); dst->quit = 1; }
+    __syncthreads();
+    if (lane == 0) {
+        a.best_E[chain] = best_E;
+        a.prev_E[chain] = prev_E;
+        for (int k = 0; k < 9; k++) a.best_rot[chain * 9 + k] = best_rot[k];
+        for (int k = 0; k < 3; k++) a.best_pos[chain * 3 + k] = best_pos[k];
+        a.step_sizes[chain * 2] = max_rot; a.step_sizes[chain * 2 + 1] = max_trans;
+        long long *c = a.counters + chain * 8;
+        c[0] = n_acc_r; c[1] = n_rej_r; c[2] = n_acc_c; c[3] = n_rej_c; c[4] = n_ooroi; c[5] = n_ezero; c[6] = too_long; c[7] = frame;
+    }
+}
+
+// ---- warp per chain -------------------------------------------------------------------------------------
+// The round-1 kernel, kept for launches with thousands of chains per GPU: one warp does everything a block does above
+// (terms 32 at a time, then the same in-order sum), 20 us per frame instead of 7, but 28 chains are resident per SM
+// instead of 4, which wins once the chains outnumber what the block kernel can keep on the GPU.  Same arithmetic, same
+// results.
+constexpr int kWarpsPerBlock = 4;
+constexpr int kTermDoubles = 128;      // per warp: two buffers of 32 double2 term slots
+__device__ __forceinline__ double2 w_intra_term(const McArgs &a, const double *x, const double *y, const double *z, int k) {
+    if (k >= a.n_pairs) return make_double2(0.0, 0.0);
+    return intra_term(ld_tab(a.pair_tab + k), x, y, z);
+}
+// Software pipelined: the terms of round r + 1 are computed (sqrt and division chains) between the store of round r
+// and its in-order summation, two independent dependency chains the scheduler can interleave; two term buffers.
+__device__ double w_intra_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
+                               double2 *terms) {
+    double se = 0.0, sv = 0.0;
+    double2 t = w_intra_term(a, x, y, z, lane);
+    int buf = 0;
+    for (int base = 0; base < a.n_pairs; base += 32) {
+        double2 *tb = terms + 32 * buf;
+        __syncwarp();
+        tb[lane] = t;
+        __syncwarp();
+        t = w_intra_term(a, x, y, z, base + 32 + lane);                 // next round (zeros beyond the last pair)
+        const int lim = min(32, a.n_pairs - base);
+        if (lim == 32) {
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                const double2 u = tb[l];
+                se = se + u.x;
+                sv = sv + u.y;
+            }
+        } else {
+            for (int l = 0; l < lim; l++) {
+                const double2 u = tb[l];
+                se = se + u.x;
+                sv = sv + u.y;
+            }
+        }
+        buf ^= 1;
+    }
+    return (kElecWeight * se) + sv;
+}
+
+// Mol.ene_inter_UFF_interp (mol.ml:1012-1020): one trilinear look-up per lane, summed in atom order
+__device__ double w_interp_energy(const McArgs &a, const double *x, const double *y, const double *z, int lane,
+                                double2 *terms) {
+    double res = 0.0;
+    for (int base = 0; base < a.L; base += 32) {
+        const int j = base + lane;
+        double t = 0.0;
+        if (j < a.L) t = d_trilin(a.g, a.maps + (size_t)__ldg(a.ltyp + j) * a.g.nvox, x[j], y[j], z[j]);
+        __syncwarp();
+        terms[lane].x = t;
+        __syncwarp();
+        const int lim = min(32, a.L - base);
+        for (int l = 0; l < lim; l++) res = res + terms[l].x;
+    }
+    return res;
+}
+
+__device__ __forceinline__ double w_inter_energy(const McArgs &a, const double *x, const double *y, const double *z,
                                                int lane, double2 *terms) {
-    return a.maps ? interp_energy(a, x, y, z, lane, terms) : direct_energy(a, x, y, z, lane, terms);
+    return a.maps ? w_interp_energy(a, x, y, z, lane, terms) : direct_energy(a, x, y, z, lane, terms);
 }
 
 // Two builds of the same kernel: MINB = 1 keeps every chain's state in registers (248: lowest latency per frame,
@@ -237,7 +675,7 @@ __device__ __forceinline__ double inter_energy(const McArgs &a, const double *x,
 // spills to local memory, slower per chain) so that 28 chains are resident per SM when there are thousands.
 template <int MINB>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
-mc_chains_kernel(McArgs a) {
+mc_warp_kernel(McArgs a) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t chain = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
@@ -280,9 +718,9 @@ mc_chains_kernel(McArgs a) {
     }
     __syncwarp();
     double const_intra = 0.0;
-    if (a.intra_nb && !flexible) const_intra = intra_energy(a, cx, cy, cz, lane, terms);
-    double prev_E_intra = !a.intra_nb ? 0.0 : (flexible ? intra_energy(a, lx, ly, lz, lane, terms) : const_intra);
-    double prev_E_inter = inter_energy(a, lx, ly, lz, lane, terms);
+    if (a.intra_nb && !flexible) const_intra = w_intra_energy(a, cx, cy, cz, lane, terms);
+    double prev_E_intra = !a.intra_nb ? 0.0 : (flexible ? w_intra_energy(a, lx, ly, lz, lane, terms) : const_intra);
+    double prev_E_inter = w_inter_energy(a, lx, ly, lz, lane, terms);
     double prev_E = prev_E_inter + prev_E_intra;
     double best_E = prev_E;
     long long rigid_step = 0, conf_step = 0;
@@ -378,8 +816,8 @@ mc_chains_kernel(McArgs a) {
             }
         }
         __syncwarp();
-        if (!rigid && a.intra_nb) prev_E_intra = flexible ? intra_energy(a, lx, ly, lz, lane, terms) : const_intra;   // D2
-        prev_E_inter = inter_energy(a, lx, ly, lz, lane, terms);
+        if (!rigid && a.intra_nb) prev_E_intra = flexible ? w_intra_energy(a, lx, ly, lz, lane, terms) : const_intra;   // D2
+        prev_E_inter = w_inter_energy(a, lx, ly, lz, lane, terms);
         const double curr_E = prev_E_inter + prev_E_intra;
         int accepted = -1;
         const double ddx = a.roi_c[0] - (0.0 + posp[0]), ddy = a.roi_c[1] - (0.0 + posp[1]), ddz = a.roi_c[2] - (0.0 + posp[2]);
@@ -533,6 +971,23 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     McArgs a;
     a.L = L; a.lx = lig->x.p; a.ly = lig->y.p; a.lz = lig->z.p; a.lq = lig->q.p; a.lelt = lig->elt.p; a.ltyp = lig->typ.p;
     a.n_pairs = lig->n_pairs; a.pair_i = lig->pair_i.p; a.pair_j = lig->pair_j.p;
+    if (lig->n_pairs > 0 && !lig->mc_pair_tab.p) {
+        // per interacting pair: UFF.vdW_xiDi of the two elements (x_ij, d_ij), q_i *. q_j, and the two atom indices
+        MMO_REQUIRE(L <= 65535, "mmo_mc_run: ligand too large (%d atoms)", L);
+        std::vector<double4> tab((size_t)lig->n_pairs);
+        for (int k = 0; k < lig->n_pairs; k++) {
+            const int i = lig->h_pair_i[k], j = lig->h_pair_j[k];
+            const int ei = elt_index(lig->hanum[i]), ej = elt_index(lig->hanum[j]);
+            const bool ok = ei < kNumElt && ej < kNumElt;
+            tab[k].x = ok ? sqrt(kEltXi[ei] * kEltXi[ej]) : NAN;       // FF.geo_mean (same doubles as the kEltTab^2 tables)
+            tab[k].y = ok ? sqrt(kEltDi[ei] * kEltDi[ej]) : NAN;
+            tab[k].z = lig->hq[i] * lig->hq[j];
+            const long long bits = (long long)((unsigned)i | ((unsigned)j << 16));
+            memcpy(&tab[k].w, &bits, sizeof bits);
+        }
+        MMO_TRY(const_cast<mmo_ligand *>(lig)->mc_pair_tab.upload(tab));
+    }
+    a.pair_tab = lig->mc_pair_tab.p;
     a.n_rbonds = lig->n_rbonds; a.rb_left = lig->d_rb_left.p; a.rb_right = lig->d_rb_right.p;
     a.rg_off = lig->d_rg_off.p; a.rg_idx = lig->d_rg_idx.p;
     if (grid) { a.g = geom_of(grid); a.maps = grid->maps.p; } else { memset(&a.g, 0, sizeof a.g); a.maps = nullptr; }
@@ -550,17 +1005,40 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     a.p_max_rbond_rot = 5.0 * (a.pi / 180.0);                    // params.ml:17
     a.best_E = d_bestE.p; a.prev_E = d_prevE.p; a.best_rot = d_brot.p; a.best_pos = d_bpos.p; a.best_xyz = d_bxyz.p;
     a.step_sizes = d_steps.p; a.counters = d_cnt.p; a.trace = trace_chain0 ? d_trace.p : nullptr;
+    DevBuf<long long> d_prof;
+    const bool want_prof = getenv("MMO_MC_PROFILE") != nullptr;
+    if (want_prof) { MMO_TRY(d_prof.alloc(8)); MMO_CUDA(cudaMemsetAsync(d_prof.p, 0, 64, R.stream)); }
+    a.prof = want_prof ? d_prof.p : nullptr;
     const int nrb1 = std::max(lig->n_rbonds, 1);
-    const size_t smem = (size_t)kWarpsPerBlock * (((9 * L + 2 * nrb1 + 1) & ~1) + kTermDoubles) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
-    MMO_REQUIRE(smem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds)", L, lig->n_rbonds);
-    MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(mc_chains_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)((n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    // conf, conf', lig' (9 L), step sizes (2 nrb), look-up terms (L), kept scalars (24), alignment (1), direct-scorer
+    // scratch (32 double2), intra terms (n_pairs double2), per-bond windows, two command slots
+    const size_t smem = ((size_t)10 * L + 2 * nrb1 + 24 + 1) * sizeof(double) + ((size_t)32 + lig->n_pairs + 14 * 9 + 8) * sizeof(double2) +
+                        (size_t)nrb1 * sizeof(Sw) + 2 * sizeof(McCmd) +
+                        ((size_t)L + 3 * (size_t)lig->n_rbonds + 1 + lig->rg_idx.size()) * sizeof(int) + 16;
+    MMO_REQUIRE(smem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds, %d interacting pairs)", L, lig->n_rbonds, lig->n_pairs);
+    // One block of 128 threads per chain while the block kernel can keep (nearly) all chains on the GPU at once (4 blocks per
+    // SM): lowest latency per frame.  Beyond ~12 chains per SM the warp-per-chain kernel (28 chains resident per SM) has
+    // the higher throughput.  MMO_MC_THREADS = 32 | 64 | 128 | 256 overrides (32 = warp per chain).
+    int nt = (n_chains > 12LL * R.sm_count) ? 32 : 128;
+    if (const char *e = getenv("MMO_MC_THREADS")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) nt = v; }
     {
         KernelScope ks(K_MC);
-        // more chains than the register-resident build can keep on the GPU (2 blocks per SM)?
-        if ((int64_t)blocks > 2LL * R.sm_count) mc_chains_kernel<7><<<blocks, kWarpsPerBlock * 32, smem, R.stream>>>(a);
-        else mc_chains_kernel<1><<<blocks, kWarpsPerBlock * 32, smem, R.stream>>>(a);
+        if (nt == 32) {
+            const size_t wsmem = (size_t)kWarpsPerBlock * (((9 * L + 2 * nrb1 + 1) & ~1) + kTermDoubles) * sizeof(double) + (size_t)kWarpsPerBlock * nrb1 * sizeof(Sw);
+            MMO_REQUIRE(wsmem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds)", L, lig->n_rbonds);
+            MMO_CUDA(cudaFuncSetAttribute(mc_warp_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            const unsigned blocks = (unsigned)((n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock);
+            mc_warp_kernel<7><<<blocks, kWarpsPerBlock * 32, wsmem, R.stream>>>(a);
+        } else if (nt == 64) {
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<64, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<64, 10><<<(unsigned)n_chains, 64, smem, R.stream>>>(a);
+        } else if (nt == 128) {
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<128, 4><<<(unsigned)n_chains, 128, smem, R.stream>>>(a);
+        } else {
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<256, 2><<<(unsigned)n_chains, 256, smem, R.stream>>>(a);
+        }
     }
     MMO_LAUNCH_CHECK();
     std::vector<double> hE(n_chains), hP(n_chains), hR((size_t)n_chains * 9), hT((size_t)n_chains * 3), hS((size_t)n_chains * 2);
@@ -574,6 +1052,14 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     if (best_xyz) MMO_CUDA(cudaMemcpyAsync(best_xyz, d_bxyz.p, (size_t)n_chains * 3 * L * 8, cudaMemcpyDeviceToHost, R.stream));
     if (trace_chain0) MMO_CUDA(cudaMemcpyAsync(trace_chain0, d_trace.p, (size_t)p->n_steps * 4 * 8, cudaMemcpyDeviceToHost, R.stream));
     MMO_CUDA(cudaStreamSynchronize(R.stream));
+    if (want_prof) {
+        long long h[8];
+        MMO_CUDA(cudaMemcpy(h, d_prof.p, sizeof h, cudaMemcpyDeviceToHost));
+        const double f = std::max(1, p->n_steps);
+        fprintf(stderr, "[mmo_mc_run] chain 0, cycles per frame (%d threads per chain, %lld chains): conformer move %.0f, rigid move + lig' %.0f, "
+                        "hand-over %.0f, E_inter %.0f, E_intra sum %.0f (of which waiting at chunk barriers %.0f; helper thread 0 produces for %.0f), accept %.0f\n",
+                nt, (long long)n_chains, h[0] / f, h[1] / f, h[2] / f, h[3] / f, h[4] / f, h[6] / f, h[7] / f, h[5] / f);
+    }
     for (int64_t c = 0; c < n_chains; c++) {
         mmo_mc_result &r = results[c];
         r.best_E = hE[c]; r.prev_E = hP[c];

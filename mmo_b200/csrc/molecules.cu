@@ -225,6 +225,7 @@ int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const doubl
                 if (dists[i + (size_t)j * n] >= 3) { pi.push_back(i); pj.push_back(j); }   // mol.ml:203-208
     }
     l->n_pairs = (int)pi.size();
+    l->h_pair_i = pi; l->h_pair_j = pj;
     l->n_rbonds = n_rbonds;
     if (n_rbonds > 0) {
         l->rb_left.assign(rb_left, rb_left + n_rbonds);

@@ -61,9 +61,11 @@ def test_rng_and_detmath_are_platform_independent(orc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("threads", ["128", "32", "64", "256"])      # block per chain (default), warp per chain, other block sizes
 @pytest.mark.parametrize("flags", [dict(), dict(tweak_rbonds=False), dict(no_flip=True, temperature_K=600.0),
                                    dict(hard_roi=False), dict(intra_nb=False)])
-def test_cuda_chains_match_the_oracle_bit_for_bit(gpu, orc, c2, c2_roi_rec, mc_setup, flags):
+def test_cuda_chains_match_the_oracle_bit_for_bit(gpu, orc, c2, c2_roi_rec, mc_setup, flags, threads, monkeypatch):
+    monkeypatch.setenv("MMO_MC_THREADS", threads)
     dims, mask, ta, tq, maps = mc_setup
     rec = gpu.Receptor.from_mol(c2_roi_rec)
     g, gmaps = gpu.Lds.pre_calculate_FF_components_grid(rec, 1.0, dims, ta, tq, mask_bits=mask)
@@ -110,7 +112,7 @@ def test_many_chains_statistics(gpu, orc, c2, c2_roi_rec, mc_setup):
 
 
 @pytest.mark.gpu
-def test_cuda_chain_on_the_direct_scorer_follows_the_oracle(gpu, orc, c2, c2_roi_rec):
+def test_cuda_chain_on_the_direct_scorer_follows_the_oracle(gpu, orc, c2, c2_roi_rec, monkeypatch):
     """--no-interp: E_inter = Mol.ene_inter_UFF_shifted_brute (mol.ml:822-849).  The kernel uses the
     reference's fp64 pair terms with a lane-strided summation, so energies agree to ~1e-13 relative and
     the Metropolis decisions -- hence the trajectory -- are the oracle's."""
@@ -120,6 +122,9 @@ def test_cuda_chain_on_the_direct_scorer_follows_the_oracle(gpu, orc, c2, c2_roi
     R = np.tile(np.eye(3).reshape(9), (2, 1)); t = np.tile(c2["start_pos"], (2, 1))
     t[1] += 0.3
     res, xyz, trace = gpu.Lds.simulate_lig(None, lig, c2["roi"], n_steps, seeds, R, t, want_xyz=True, want_trace=True, rec=rec)
+    monkeypatch.setenv("MMO_MC_THREADS", "32")         # the warp-per-chain kernel runs the same arithmetic
+    res32, xyz32, trace32 = gpu.Lds.simulate_lig(None, lig, c2["roi"], n_steps, seeds, R, t, want_xyz=True, want_trace=True, rec=rec)
+    assert np.array_equal(trace, trace32) and np.array_equal(xyz, xyz32)
     for c in range(2):
         want, wxyz, wtr = orc.mc_run(c2["lig"], lig.xs, lig.ys, lig.zs, c2["roi"], n_steps, int(seeds[c]), R[c], t[c],
                                      rec=c2_roi_rec)

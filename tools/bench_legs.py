@@ -370,14 +370,17 @@ def leg_fp64_scan(ctx, job_params, n_active, pps, n_rot, quick=False):
             "scaling": "weak", "best_score": SR.best_score, "best_frame": SR.best_frame, "clocks": ck.summary()}
 
 
-def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0):
+def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0, only=None):
     out = {}
     t0 = time.perf_counter()
     pk = peaks(ctx)
     out["peaks"] = pk
-    out["c3_grid_build"], out["c3_lookup"] = leg_c3(ctx, pk, quick)
-    out["c4_mc"] = leg_c4(ctx, quick)
-    out["c5_screen"] = leg_c5(ctx, pk, quick)
+    if only in (None, "c3"):
+        out["c3_grid_build"], out["c3_lookup"] = leg_c3(ctx, pk, quick)
+    if only in (None, "c4"):
+        out["c4_mc"] = leg_c4(ctx, quick)
+    if only in (None, "c5"):
+        out["c5_screen"] = leg_c5(ctx, pk, quick)
     if scan_params is not None:
         out["c2_fp64_scan"] = leg_fp64_scan(ctx, scan_params, n_active, pps, n_rot, quick)
     ctx.ck(ctx.L.mmo_kernel_timing(0))
@@ -388,4 +391,5 @@ def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0):
 if __name__ == "__main__":
     import mmo_b200
     mmo_b200.init(0)
-    print(json.dumps(run_all(Ctx(mmo_b200.lib()), quick="--quick" in sys.argv)))
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    print(json.dumps(run_all(Ctx(mmo_b200.lib()), quick="--quick" in sys.argv, only=only)))
