@@ -1,0 +1,180 @@
+"""The C oracle (oracle/mmo_oracle*.c) against a second restatement written independently from the OCaml text in pure
+Python (oracle/pycheck/mmo_ref.py): whole-pose energies on C2- and C5-shaped inputs, one map voxel and one trilinear
+cell on a C3-shaped input, intra-ligand energies, and 200 Monte-Carlo frames -- all BIT FOR BIT.  Plus a 40-digit mpmath
+evaluation of the same whole-pose sums, which bounds the rounding error of either.  CPU only.
+
+VERDICT r1 'weak #1': the oracle and the kernels came from one reading of the source; this removes the transcription
+risk (two languages, two data layouts).  A shared misreading of the OCaml text would survive: DESIGN.md section 2 lists
+the readings that stay single-source."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "pycheck"))
+import mmo_ref as ref  # noqa: E402
+
+from mmo_b200 import pqrs, workloads  # noqa: E402
+
+
+def _ref_prot(m):
+    return ref.Mol(m.xs, m.ys, m.zs, m.q, m.anum)
+
+
+def _ref_lig(lig, xs, ys, zs, center=None):
+    groups = [list(g) for g in lig.groups] if hasattr(lig, "groups") else []
+    pi = 4.0 * np.arctan(1.0)
+    return ref.Mol(xs, ys, zs, lig.q, lig.anum, t_a=lig.typ, dists_a=lig.dists,
+                   rbonds=list(zip(lig.rb_left, lig.rb_right)), rgroups=groups, max_rbond_rot=5.0 * (pi / 180.0), center=center)
+
+
+def _groups(lig):
+    off, idx = lig.rgroup_csr()
+    return [list(idx[off[b]:off[b + 1]]) for b in range(lig.n_rbonds)]
+
+
+@pytest.fixture(scope="module")
+def c2lig(c2):
+    lig = c2["lig"]
+    lig.groups = _groups(lig)
+    return lig
+
+
+def test_whole_pose_energies_c2_shape_bit_for_bit(orc, c2, c2_roi_rec, c2lig):
+    """docked.mol2 against the 1837-atom ROI receptor: docked pose, a clashing pose, a far pose; shifted and global"""
+    cx, cy, cz = c2["centered"]
+    R, t = workloads.random_poses_in_sphere(3, c2["roi"][:3], 6.0, seed=11)
+    R[0] = np.eye(3).reshape(9); t[0] = c2["start_pos"]
+    t[2] = np.array(c2["roi"][:3]) + np.array([0.0, 0.0, 27.0])
+    X, Y, Z = orc.pose_coords(cx, cy, cz, R, t)
+    prot = _ref_prot(c2_roi_rec)
+    for shifted, fn in ((True, ref.ene_inter_UFF_shifted_brute), (False, ref.ene_inter_UFF_global_brute)):
+        want = orc.ene_inter(c2_roi_rec, c2lig.q, c2lig.anum, X, Y, Z, shifted=shifted)
+        for p in range(3):
+            got = fn(prot, _ref_lig(c2lig, X[p], Y[p], Z[p]))
+            assert got == want[p], (shifted, p, got, want[p])
+    # the pose builder itself: Mol.rotate_then_translate_copy (mol.ml:664-672)
+    m = ref.rotate_then_translate_copy(_ref_lig(c2lig, cx, cy, cz, center=(0, 0, 0)), tuple(R[1]), tuple(t[1]))
+    assert m.xs == list(X[1]) and m.ys == list(Y[1]) and m.zs == list(Z[1])
+
+
+def test_whole_pose_energy_c5_shape_bit_for_bit(orc):
+    """a 70-atom conformer against a 10 000-atom synthetic receptor sphere (BASELINE configs[4])"""
+    rec = workloads.synthetic_receptor(10000, "sphere", 34.0, seed=workloads.SEED + 1, origin=(60.0, 60.0, 60.0))
+    lig = workloads.c5_ligand()
+    X, Y, Z = workloads.c5_conformers(lig, 2, (60.0, 60.0, 60.0))
+    want = orc.ene_inter(rec, lig.q, lig.anum, X, Y, Z, shifted=True)
+    prot = _ref_prot(rec)
+    for p in range(2):
+        got = ref.ene_inter_UFF_shifted_brute(prot, ref.Mol(X[p], Y[p], Z[p], lig.q, lig.anum))
+        assert got == want[p]
+
+
+def test_whole_pose_sum_against_40_digit_arithmetic(orc, c2, c2_roi_rec, c2lig):
+    """the same sums in 40-digit arithmetic: the double-precision result of the reference's evaluation order is within
+    1e-11 relative (+ 1e-9 absolute) of the exact value of the formula -- a bound on what summation order can move"""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    cx, cy, cz = c2["centered"]
+    X, Y, Z = orc.pose_coords(cx, cy, cz, np.eye(3).reshape(1, 9), np.array([c2["start_pos"]]))
+    want = orc.ene_inter(c2_roi_rec, c2lig.q, c2lig.anum, X, Y, Z, shifted=True)[0]
+    se = mp.mpf(0); sv = mp.mpf(0)
+    P = c2_roi_rec
+    for i in range(P.n):
+        for j in range(c2lig.n):
+            dx, dy, dz = mp.mpf(P.xs[i]) - mp.mpf(X[0][j]), mp.mpf(P.ys[i]) - mp.mpf(Y[0][j]), mp.mpf(P.zs[i]) - mp.mpf(Z[0][j])
+            r2 = dx * dx + dy * dy + dz * dz
+            if r2 < 144:
+                r = mp.sqrt(r2)
+                if r < mp.mpf("0.01"):
+                    r = mp.mpf("0.01")
+                w = (1 - (r / 12) ** 2) ** 2
+                xi = dict(ref.ANUM_XI_DI)
+                x_ij = mp.sqrt(mp.mpf(xi[int(P.anum[i])][0]) * mp.mpf(xi[int(c2lig.anum[j])][0]))
+                d_ij = mp.sqrt(mp.mpf(xi[int(P.anum[i])][1]) * mp.mpf(xi[int(c2lig.anum[j])][1]))
+                p6 = (x_ij / r) ** 6
+                se += w * (mp.mpf(P.q[i]) * mp.mpf(c2lig.q[j]) / r)
+                sv += w * d_ij * (p6 * p6 - 2 * p6)
+    exact = mp.mpf(332.0637) / 4 * se + sv
+    assert abs(mp.mpf(want) - exact) <= mp.mpf("1e-11") * abs(exact) + mp.mpf("1e-9")
+
+
+def test_intra_energy_bit_for_bit(orc, c2, c2lig):
+    cx, cy, cz = c2["centered"]
+    want = orc.ene_intra(c2lig, cx, cy, cz)[0]
+    assert ref.ene_intra_UFFNB_brute(_ref_lig(c2lig, cx, cy, cz)) == want
+    rng = np.random.default_rng(3)
+    x2, y2, z2 = cx + rng.normal(0, 0.2, len(cx)), cy + rng.normal(0, 0.2, len(cx)), cz + rng.normal(0, 0.2, len(cx))
+    assert ref.ene_intra_UFFNB_brute(_ref_lig(c2lig, x2, y2, z2)) == orc.ene_intra(c2lig, x2, y2, z2)[0]
+
+
+def test_map_voxels_and_trilinear_cell_c3_shape_bit_for_bit(orc):
+    """C3 shape: 5000-atom receptor, 0.375 A grid, the 22 FF types of ligdecs.mol2: the 22 values of three voxels
+    (Mol.ene_inter_UFF_shifted_grid + clamp + float32 store) and look-ups inside one cell of a small map set"""
+    rec = workloads.synthetic_receptor(5000, "cube", 60.0, seed=workloads.SEED)
+    rec.xs -= 15.0; rec.ys -= 15.0; rec.zs -= 15.0
+    lig = pqrs.read_ligands_pqrs(os.path.join(workloads.GOLDEN, "ligdecs.pqrs"))[0]
+    ta, tq = pqrs.assign_ff_types([lig])
+    dims = orc.grid_from_box(0.375, 30.0, 30.0, 30.0)
+    g = ref.Grid(0.375, 30.0, 30.0, 30.0)
+    assert (g.x_dim, g.y_dim, g.z_dim) == tuple(dims) == (81, 81, 81)
+    assert all(g.xs[i] == orc.grid_node(0.375, dims[0], i) for i in range(dims[0]))
+    vox = [(40, 40, 40), (0, 80, 13), (17, 3, 66)]
+    nvox = dims[0] * dims[1] * dims[2]
+    mask = np.zeros((nvox + 7) // 8, np.uint8)
+    for i, j, k in vox:
+        idx = i + j * dims[0] + k * dims[0] * dims[1]
+        mask[idx >> 3] |= 1 << (idx & 7)
+    maps = orc.grid_build(rec, 0.375, dims, ta, tq, mask=mask)
+    prot = _ref_prot(rec)
+    probes = list(zip([int(a) for a in ta], [float(q) for q in tq]))
+    for i, j, k in vox:
+        idx = i + j * dims[0] + k * dims[0] * dims[1]
+        e = ref.ene_inter_UFF_shifted_grid(prot, (g.xs[i], g.ys[j], g.zs[k]), probes)
+        got = [ref.map_value(v) for v in e]
+        assert got == [float(maps[t][idx]) for t in range(len(ta))]
+        assert any(v != 0.0 for v in got)
+    # trilinear: a small dense map set from the oracle, look-ups compared point by point
+    sd = orc.grid_from_box(0.375, 3.0, 2.25, 2.625)
+    small = orc.grid_build(rec, 0.375, sd, ta[:2], tq[:2])
+    sg = ref.Grid(0.375, 3.0, 2.25, 2.625)
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(0.0, 1.0, (40, 3)) * (np.array(sd) - 1.001) * 0.375
+    pts[0] = (0.375 * 2, 0.375 * 3, 0.375 * 4)                   # exactly on a node
+    for t in range(2):
+        for p in pts:
+            assert ref.trilin(sg, small[t], tuple(p)) == orc.trilin(0.375, sd, small[t], p[0], p[1], p[2])
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(tweak_rbonds=False), dict(hard_roi=False), dict(no_flip=True, temperature_K=450.0)])
+def test_200_monte_carlo_frames_bit_for_bit(orc, c2, c2_roi_rec, c2lig, flags):
+    """Lds.simulate_lig (lds.ml:741-1000) re-read from the OCaml text: molecule copies, shared acceptance windows,
+    right-to-left draws, the dangling else -- 200 frames (600 with the default flags, so that adaptive step sizes and a
+    bond flip are reached), every energy of every frame equal to the C oracle's"""
+    c = np.array(c2["roi"][:3])
+    dims = orc.grid_from_box(1.0, *(c + 23.0))
+    mask = orc.bitmask_sphere(1.0, dims, c, 21.0)
+    ta, tq = pqrs.assign_ff_types([c2lig])
+    maps = orc.grid_build(c2_roi_rec, 1.0, dims, ta, tq, mask=mask)
+    cx, cy, cz = c2["centered"]
+    n_steps = 600 if not flags else 200
+    rot0 = np.eye(3).reshape(9)
+    want, wxyz, wtr = orc.mc_run(c2lig, cx, cy, cz, c2["roi"], n_steps, 1234, rot0, c2["start_pos"], maps=maps, g_step=1.0,
+                                 g_dims=dims, **flags)
+    g = ref.Grid(1.0, *(c + 23.0))
+    assert (g.x_dim, g.y_dim, g.z_dim) == tuple(dims)
+    comps = [maps[t] for t in range(len(ta))]
+    centered = _ref_lig(c2lig, cx, cy, cz, center=(0.0, 0.0, 0.0))
+    kw = dict(tweak_rbonds=flags.get("tweak_rbonds", True), enforce_ROI=flags.get("hard_roi", True),
+              no_flip=flags.get("no_flip", False), temperature_K=flags.get("temperature_K", 293.15))
+    trace, best_E, prev_E, cnt = ref.simulate_lig(centered, lambda m: ref.ene_inter_UFF_interp(g, comps, m), n_steps, 1234,
+                                                  tuple(rot0), tuple(c2["start_pos"]), c2["roi"], **kw)
+    assert cnt["frames"] == want["frames_done"] == len(trace)
+    assert np.array_equal(np.array(trace), wtr)
+    assert best_E == want["best_E"] and prev_E == want["prev_E"]
+    assert (cnt["acc_rigid"], cnt["rej_rigid"], cnt["acc_conf"], cnt["rej_conf"], cnt["ooroi"], cnt["ezero"]) == \
+        (want["n_accept_rigid"], want["n_reject_rigid"], want["n_accept_conf"], want["n_reject_conf"], want["n_ooroi"], want["n_ezero"])
+    if not flags:
+        assert cnt["acc_rigid"] > 0 and cnt["rej_rigid"] > 0 and cnt["acc_conf"] + cnt["rej_conf"] > 0
