@@ -147,6 +147,8 @@ struct mmo_receptor {
     mmo::DevBuf<float4> xyzq;
     mmo::DevBuf<uint8_t> gelt;
     mmo::DevBuf<float4> blob_box;    // n_blobs x 2 : {lo xyz, 0}, {hi xyz, 0} (relative coordinates)
+    mmo::DevBuf<float4> sup_box;     // n_sup x 2 : boxes of 32 consecutive groups
+    int n_sup = 0;
     // close-contact voxel lists (fp64 correction pass)
     double vox_lo[3] = {0, 0, 0};
     double vox_edge = 2.0;

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "pose.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -422,13 +423,24 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
 // three sums each,  E = A_j sum(w A_i s^6) - B_j sum(w B_i s^3) + q_j sum(w q_i / r):  15 packed ops per two pairs.
 constexpr float kItemCell = 2.0f;
 constexpr int kItemTPB = 256;
-constexpr int kItemSumEvery = 4;
+#ifndef MMO_ITEM_SUM_EVERY
+#define MMO_ITEM_SUM_EVERY 8
+#endif
+#ifndef MMO_ITEM_MINB
+#define MMO_ITEM_MINB 2
+#endif
+#ifndef MMO_ITEM_PREFETCH
+#define MMO_ITEM_PREFETCH 0      /* requesting the next four groups' atoms one step ahead: measured, no gain (L1 hits) */
+#endif
+constexpr int kItemSumEvery = MMO_ITEM_SUM_EVERY;
 
 struct ItemArgs {
     float tab_A[kEltTab], tab_B[kEltTab];
-    const float4 *xyzq;
+    const float4 *xyzq;          // receptor groups of 16 atoms (+ one dummy group of far-away atoms at index n_blobs)
     const uint8_t *gelt;
-    const float4 *blob_box;
+    const float4 *blob_box;      // {lo, hi} per group
+    const float4 *sup_box;       // {lo, hi} per super-group of 32 consecutive groups (k-d order: spatially compact)
+    int n_blobs, n_sup;
     const float4 *lparam;        // fast-path order {A_j, B_j, q_j, real?}
     int n_fast;
     const float4 *pos;           // item -> position relative to the receptor origin (item = pose * n_fast + k)
@@ -436,8 +448,8 @@ struct ItemArgs {
     const unsigned long long *n_far;   // items beyond the lattice (energy exactly 0): sorted last
     unsigned long long n_items;
     float H, Hflag;
-    double *e_item;              // += E (one tile per launch, launches are serialised)
-    uint8_t *f_item;             // |= close-contact flag
+    double *e_item;              // = E (written once per item; items beyond the lattice keep the 0 of the memset)
+    uint8_t *f_item;             // = close-contact flag
     unsigned long long *stats;
 };
 
@@ -506,22 +518,21 @@ __device__ __forceinline__ void run_list_items(const float *s_l, int n, int n4, 
     }
 }
 
-// position (double, then fp32 relative to the receptor origin) and lattice cell of every item; thread = pose
-__global__ void __launch_bounds__(128)
+// position (double, then fp32 relative to the receptor origin) and lattice cell of every item; thread = item, so that
+// the 24 bytes written per item (and the coordinates read, for explicit conformers) are coalesced
+__global__ void __launch_bounds__(256)
 item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const double *__restrict__ lx, const double *__restrict__ ly,
                     const double *__restrict__ lz, const int32_t *__restrict__ forder, const float4 *__restrict__ lparam,
                     double ox, double oy, double oz, float cell_lo_x, float cell_lo_y, float cell_lo_z, float cell_inv,
                     int nx, int ny, int nz, float4 *__restrict__ pos, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                     unsigned long long *__restrict__ n_far) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_poses) return;
-    PoseRT P;
-    if (src.kind != 1) load_pose_rt(src, p, P);
+    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_items = n_poses * n_fast;
     const uint32_t far_key = (uint32_t)nx * ny * nz;
-    unsigned far = 0;
-    for (int k = 0; k < n_fast; k++) {
-        const int64_t it = p * n_fast + k;
-        uint32_t key = far_key;
+    uint32_t key = far_key;
+    if (it < n_items) {
+        const int64_t p = it / n_fast;
+        const int k = (int)(it - p * n_fast);
         float4 v = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
         if (__ldg(&lparam[k].w) != 0.f) {
             double x, y, z;
@@ -529,6 +540,8 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
                 const int j = __ldg(forder + k);
                 x = src.xs[p * L + j]; y = src.ys[p * L + j]; z = src.zs[p * L + j];
             } else {
+                PoseRT P;
+                load_pose_rt(src, p, P);
                 pose_atom_rt(P, __ldg(lx + k), __ldg(ly + k), __ldg(lz + k), x, y, z);
             }
             v.x = (float)(x - ox); v.y = (float)(y - oy); v.z = (float)(z - oz);
@@ -536,65 +549,74 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
             if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)nx && fy < (float)ny && fz < (float)nz)
                 key = (uint32_t)((int)fx + nx * ((int)fy + ny * (int)fz));
         }
-        if (key == far_key) far++;
         pos[it] = v;
         keys[it] = key;
         vals[it] = (uint32_t)it;
     }
-    if (far) atomicAdd(n_far, (unsigned long long)far);
+    // one atomic per warp
+    const unsigned far = __ballot_sync(0xffffffffu, it < n_items && key == far_key);
+    if ((threadIdx.x & 31) == 0 && far) atomicAdd(n_far, (unsigned long long)__popc(far));
 }
 
-// Shared memory (dynamic): receptor tile [tile_atoms + kBlob] float4, boxes, ligand parameters, vdW table,
-// per-warp lists [NF][LIST_CAP], element bytes, per-warp near-group ids.
+// One launch for the whole receptor.  The receptor is NOT staged in shared memory: 64 cell-sorted items only touch the
+// groups within 12 A + rho of their centre (a few dozen of, say, 625), consecutive units touch the same ones, and the
+// read-only path keeps them in L1 -- while a shared-memory tile of 2048 atoms would mean five launches for a 10 000-atom
+// receptor, each one gathering the items, culling and scattering the energies again.  Level 1 is two-staged: lane s
+// tests the box of super-group s (32 consecutive k-d leaves), then lane g the box of group g of every near super-group.
+// The next unit's items (two dependent gathers: rank -> item -> position) are requested before the current unit's pair
+// loop and arrive behind it.
+// Shared memory (dynamic): super-group boxes [2 * n_sup] float4, ligand parameters, vdW table, per-warp lists
+// [NF][LIST_CAP], per-warp near-group ids (uint16).
+struct ItemUnit { bool valid[PPT]; uint32_t item[PPT]; float4 v[PPT]; };
+
+__device__ __forceinline__ void load_item_unit(const ItemArgs &a, unsigned long long u, unsigned long long n_near, int lane, ItemUnit &U) {
+#pragma unroll
+    for (int h = 0; h < PPT; h++) {
+        const unsigned long long idx = u * (32 * PPT) + 32 * h + lane;
+        U.valid[h] = idx < n_near;
+        U.item[h] = __ldg(a.perm + (U.valid[h] ? idx : n_near - 1));    // idle slots shadow the last item
+        U.v[h] = __ldg(a.pos + U.item[h]);
+    }
+}
+
 template <int VARIANT, bool STATS>
-__global__ void __launch_bounds__(kItemTPB, 2)
-direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long long *__restrict__ work) {
+__global__ void __launch_bounds__(kItemTPB, MMO_ITEM_MINB)
+direct_items_kernel(ItemArgs a, int near_cap, unsigned long long *__restrict__ work) {
     extern __shared__ float4 smem4[];
-    const int tile_atoms = tile_groups * kBlob;
-    float4 *s_atom = smem4;
-    float4 *s_box = s_atom + tile_atoms + kBlob;
-    float4 *s_lparam = s_box + tile_groups * 2;
+    float4 *s_sup = smem4;                                    // 2 * n_sup
+    float4 *s_lparam = s_sup + 2 * a.n_sup;
     float2 *s_tab = (float2 *)(s_lparam + a.n_fast);
     float *s_l = (float *)(s_tab + 16) + (threadIdx.x >> 5) * (NF * LIST_CAP);
-    uint8_t *s_elt = (uint8_t *)((float *)(s_tab + 16) + (kItemTPB / 32) * (NF * LIST_CAP));
-    uint8_t *s_near = s_elt + tile_atoms + kBlob + (threadIdx.x >> 5) * NEAR_CAP;
+    uint16_t *s_near = (uint16_t *)((float *)(s_tab + 16) + (kItemTPB / 32) * (NF * LIST_CAP)) + (threadIdx.x >> 5) * near_cap;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int j = tid; j < a.n_fast; j += kItemTPB) s_lparam[j] = a.lparam[j];
     if (tid < kEltTab) s_tab[tid] = make_float2(a.tab_A[tid], a.tab_B[tid]);
-    for (int k = tid; k < nb * kBlob; k += kItemTPB) {
-        s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
-        s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
-    }
-    for (int k = tid; k < nb * 2; k += kItemTPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
-    if (tid < kBlob) {
-        s_atom[tile_atoms + tid] = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
-        s_elt[tile_atoms + tid] = 0;
-    }
+    for (int k = tid; k < 2 * a.n_sup; k += kItemTPB) s_sup[k] = __ldg(a.sup_box + k);
     __syncthreads();
     const unsigned long long n_near = a.n_items - *a.n_far;
     const unsigned long long n_units = (n_near + 32 * PPT - 1) / (32 * PPT);
     unsigned long long n_eval = 0, n_in_tot = 0;
 
-    for (;;) {
+    auto grab = [&]() {
         unsigned long long u = 0;
         if (lane == 0) u = atomicAdd(work, 1ull);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= n_units) break;
-        bool valid[PPT];
-        uint32_t item[PPT];
+        return __shfl_sync(0xffffffffu, u, 0);
+    };
+    unsigned long long u = grab();
+    ItemUnit cur, nxt;
+    if (u < n_units) load_item_unit(a, u, n_near, lane, cur);
+    while (u < n_units) {
+        const unsigned long long un = grab();
+        if (un < n_units) load_item_unit(a, un, n_near, lane, nxt);          // in flight during this unit's pair loop
         float px[PPT], py[PPT], pz[PPT];
         float4 lp[PPT];
 #pragma unroll
         for (int h = 0; h < PPT; h++) {
-            const unsigned long long idx = u * (32 * PPT) + 32 * h + lane;
-            valid[h] = idx < n_near;
-            item[h] = __ldg(a.perm + (valid[h] ? idx : n_near - 1));    // idle slots shadow the last item
-            const float4 v = __ldg(a.pos + item[h]);
-            px[h] = v.x; py[h] = v.y; pz[h] = v.z;
-            lp[h] = s_lparam[item[h] % (uint32_t)a.n_fast];
+            px[h] = cur.v[h].x; py[h] = cur.v[h].y; pz[h] = cur.v[h].z;
+            lp[h] = s_lparam[cur.item[h] % (uint32_t)a.n_fast];
         }
         // ---- centre and radius of the warp's 64 items ----
         const float cx = 0.5f * (warp_min(fminf(px[0], px[1])) + warp_max(fmaxf(px[0], px[1])));
@@ -614,44 +636,71 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
         const float reach2 = reach * reach;
 #pragma unroll
         for (int h = 0; h < PPT; h++) {
-                        // expanded form: list and ligand atom relative to c; difference form (incoherent warps, c may be far
-                    // from everything): both stay relative to the receptor origin, no second rounding
-                    m2x[h] = expand ? -2.0f * px[h] : -m2x[h];
-                    m2y[h] = expand ? -2.0f * py[h] : -m2y[h];
-                    m2z[h] = expand ? -2.0f * pz[h] : -m2z[h];
+            // expanded form: list and item relative to c; difference form (incoherent warps, c may be far from
+            // everything): both stay relative to the receptor origin, no second rounding
+            m2x[h] = expand ? -2.0f * px[h] : -m2x[h];
+            m2y[h] = expand ? -2.0f * py[h] : -m2y[h];
+            m2z[h] = expand ? -2.0f * pz[h] : -m2z[h];
         }
         double EA[PPT], EB[PPT], EQ[PPT];
         unsigned long long n_in[PPT];
 #pragma unroll
         for (int h = 0; h < PPT; h++) { EA[h] = EB[h] = EQ[h] = 0.0; n_in[h] = 0; }
-        // ---- level 1 (group boxes against the sphere (c, 12 + rho)) ----
+        // ---- level 1: super-group boxes, then the group boxes of the near super-groups, against the sphere (c, 12 + rho) ----
+        auto box_near = [&](const float4 blo, const float4 bhi) {
+            const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
+            const float gy = fmaxf(0.f, fmaxf(blo.y - cy, cy - bhi.y));
+            const float gz = fmaxf(0.f, fmaxf(blo.z - cz, cz - bhi.z));
+            return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+        };
         int ng = 0;
         __syncwarp();
-#pragma unroll
-        for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
-            const int g = r * 32 + lane;
-            bool near = g < nb;
-            if (VARIANT == MMO_VARIANT_SHIFTED && near) {
-                const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
-                const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
-                const float gy = fmaxf(0.f, fmaxf(blo.y - cy, cy - bhi.y));
-                const float gz = fmaxf(0.f, fmaxf(blo.z - cz, cz - bhi.z));
-                near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+        for (int s0 = 0; s0 < a.n_sup; s0 += 32) {
+            const int sidx = s0 + lane;
+            bool sn = sidx < a.n_sup;
+            if (VARIANT == MMO_VARIANT_SHIFTED && sn) sn = box_near(s_sup[2 * sidx], s_sup[2 * sidx + 1]);
+            unsigned sm = __ballot_sync(0xffffffffu, sn);
+            while (sm) {
+                const int g = (s0 + __ffs(sm) - 1) * 32 + lane;
+                sm &= sm - 1u;
+                bool near = g < a.n_blobs;
+                if (VARIANT == MMO_VARIANT_SHIFTED && near) near = box_near(__ldg(a.blob_box + 2 * g), __ldg(a.blob_box + 2 * g + 1));
+                const unsigned gm = __ballot_sync(0xffffffffu, near);
+                if (near) s_near[ng + __popc(gm & lt_mask)] = (uint16_t)g;
+                ng += __popc(gm);
             }
-            const unsigned gm = __ballot_sync(0xffffffffu, near);
-            if (near) s_near[ng + __popc(gm & lt_mask)] = (uint8_t)g;
-            ng += __popc(gm);
         }
-        if (lane < 4) s_near[ng + lane] = (uint8_t)tile_groups;
+        if (lane < 4) s_near[ng + lane] = (uint16_t)a.n_blobs;        // pad with the dummy group
         __syncwarp();
-        // ---- level 2 + list consumption (as in direct_fp32_kernel; the list carries receptor factors only) ----
+        // ---- level 2 + list consumption (as in direct_fp32_kernel; the list carries receptor factors only).  The atoms
+        //      of the next four groups are requested (L1 / L2) before the current four are tested ----
         int n = 0;
+#if MMO_ITEM_PREFETCH
+        float4 pa_n = make_float4(0.f, 0.f, 0.f, 0.f), pb_n = pa_n;
+        int ea_n = 0, eb_n = 0;
+        if (ng > 0) {
+            const int atomA = s_near[(lane >> 4)] * kBlob + (lane & 15), atomB = s_near[2 + (lane >> 4)] * kBlob + (lane & 15);
+            pa_n = __ldg(a.xyzq + atomA); pb_n = __ldg(a.xyzq + atomB);
+            ea_n = __ldg(a.gelt + atomA); eb_n = __ldg(a.gelt + atomB);
+        }
+#endif
         for (int i = 0; i < ng || n > 0; i += 4) {
             if (i < ng) {
+#if MMO_ITEM_PREFETCH
+                const float4 pa = pa_n, pb = pb_n;
+                const int ea = ea_n, eb = eb_n;
+                if (i + 4 < ng) {
+                    const int atomA = s_near[i + 4 + (lane >> 4)] * kBlob + (lane & 15);
+                    const int atomB = s_near[i + 6 + (lane >> 4)] * kBlob + (lane & 15);
+                    pa_n = __ldg(a.xyzq + atomA); pb_n = __ldg(a.xyzq + atomB);
+                    ea_n = __ldg(a.gelt + atomA); eb_n = __ldg(a.gelt + atomB);
+                }
+#else
                 const int atomA = s_near[i + (lane >> 4)] * kBlob + (lane & 15);
                 const int atomB = s_near[i + 2 + (lane >> 4)] * kBlob + (lane & 15);
-                const float4 pa = s_atom[atomA], pb = s_atom[atomB];
-                const int ea = s_elt[atomA], eb = s_elt[atomB];
+                const float4 pa = __ldg(a.xyzq + atomA), pb = __ldg(a.xyzq + atomB);
+                const int ea = __ldg(a.gelt + atomA), eb = __ldg(a.gelt + atomB);
+#endif
                 const float Xa = pa.x - cx, Ya = pa.y - cy, Za = pa.z - cz;
                 const float Xb = pb.x - cx, Yb = pb.y - cy, Zb = pb.z - cz;
                 const float Sa = fmaf(Za, Za, fmaf(Ya, Ya, Xa * Xa)), Sb = fmaf(Zb, Zb, fmaf(Yb, Yb, Xb * Xb));
@@ -662,7 +711,7 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
                     const float2 tab = s_tab[ea];
                     float *e = s_l + n + __popc(bma & lt_mask);
                     e[0 * LIST_CAP] = expand ? Xa : pa.x; e[1 * LIST_CAP] = expand ? Ya : pa.y; e[2 * LIST_CAP] = expand ? Za : pa.z;
-                            e[3 * LIST_CAP] = Sa;
+                    e[3 * LIST_CAP] = Sa;
                     e[4 * LIST_CAP] = pa.w; e[5 * LIST_CAP] = tab.x; e[6 * LIST_CAP] = tab.y;
                 }
                 n += __popc(bma);
@@ -670,14 +719,14 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
                     const float2 tab = s_tab[eb];
                     float *e = s_l + n + __popc(bmb & lt_mask);
                     e[0 * LIST_CAP] = expand ? Xb : pb.x; e[1 * LIST_CAP] = expand ? Yb : pb.y; e[2 * LIST_CAP] = expand ? Zb : pb.z;
-                            e[3 * LIST_CAP] = Sb;
+                    e[3 * LIST_CAP] = Sb;
                     e[4 * LIST_CAP] = pb.w; e[5 * LIST_CAP] = tab.x; e[6 * LIST_CAP] = tab.y;
                 }
                 n += __popc(bmb);
                 if (n <= LIST_CAP - 64 && i + 4 < ng) continue;
             }
             if (n > 0) {
-                if (STATS) n_eval += (unsigned long long)n * (unsigned)(valid[0] + valid[1]);
+                if (STATS) n_eval += (unsigned long long)n * (unsigned)(cur.valid[0] + cur.valid[1]);
                 const int n4 = (n + 3) & ~3;
                 if (lane < n4 - n) {
                     float *e = s_l + n + lane;
@@ -694,13 +743,14 @@ direct_items_kernel(ItemArgs a, int b0, int nb, int tile_groups, unsigned long l
         }
 #pragma unroll
         for (int h = 0; h < PPT; h++) {
-            if (valid[h]) {
-                const double E = (double)lp[h].x * EA[h] - (double)lp[h].y * EB[h] + (double)lp[h].z * EQ[h];
-                a.e_item[item[h]] += E;
-                if (rmin[h] < a.Hflag) a.f_item[item[h]] = 1;
+            if (cur.valid[h]) {
+                a.e_item[cur.item[h]] = (double)lp[h].x * EA[h] - (double)lp[h].y * EB[h] + (double)lp[h].z * EQ[h];
+                a.f_item[cur.item[h]] = rmin[h] < a.Hflag ? 1 : 0;
                 if (STATS) n_in_tot += n_in[h];
             }
         }
+        cur = nxt;
+        u = un;
     }
     if (STATS) {
         atomicAdd(a.stats + 0, n_eval);
@@ -976,12 +1026,15 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     // lattice of cells over everything within 12 A (+ one cell) of the receptor's bounding box
     float lo[3], hi[3];
     for (int d = 0; d < 3; d++) { lo[d] = (float)(rec->bb_lo[d] - rec->origin[d]) - 12.5f; hi[d] = (float)(rec->bb_hi[d] - rec->origin[d]) + 12.5f; }
-    float cell = kItemCell;
+    // 1 A cells once the list is large enough to fill them (a warp's 64 items then sit within rho <= 0.87 A of their
+    // centre: ~18 % fewer pairs to evaluate than with 2 A cells), MMO_ITEM_CELL overrides (tuning)
+    float cell = n_items >= ((size_t)1 << 21) ? 1.0f : kItemCell;
+    if (const char *e = getenv("MMO_ITEM_CELL")) { const float v = (float)atof(e); if (v >= 0.25f && v <= 8.0f) cell = v; }
     int nd[3];
     for (;;) {
         double tot = 1.0;
         for (int d = 0; d < 3; d++) { nd[d] = std::max(1, (int)ceilf((hi[d] - lo[d]) / cell)); tot *= nd[d]; }
-        if (tot < (double)(1u << 24)) break;
+        if (tot < (double)(1u << 26)) break;
         cell *= 1.5f;
     }
     const unsigned n_cells = (unsigned)nd[0] * nd[1] * nd[2];
@@ -1009,7 +1062,7 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     unsigned long long *d_far = g_work.p + 63;
     {
         KernelScope ks(K_ITEM_PREP);
-        item_prepare_kernel<<<(unsigned)((n_poses + 127) / 128), 128, 0, R.stream>>>(
+        item_prepare_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, R.stream>>>(
             src, n_poses, lig->n, nf, lig->fx.p, lig->fy.p, lig->fz.p, lig->forder.p, lig->fparam.p, rec->origin[0], rec->origin[1],
             rec->origin[2], lo[0], lo[1], lo[2], 1.0f / cell, nd[0], nd[1], nd[2], pos, keys, vals, d_far);
         MMO_LAUNCH_CHECK();
@@ -1018,30 +1071,27 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     }
     ItemArgs ia;
     for (int e = 0; e < kEltTab; e++) { ia.tab_A[e] = fa.tab_A[e]; ia.tab_B[e] = fa.tab_B[e]; }
-    ia.xyzq = fa.xyzq; ia.gelt = fa.gelt; ia.blob_box = fa.blob_box; ia.lparam = fa.lparam; ia.n_fast = nf;
+    ia.xyzq = fa.xyzq; ia.gelt = fa.gelt; ia.blob_box = fa.blob_box; ia.sup_box = rec->sup_box.p;
+    ia.n_blobs = rec->n_blobs; ia.n_sup = rec->n_sup; ia.lparam = fa.lparam; ia.n_fast = nf;
     ia.pos = pos; ia.perm = perm; ia.n_far = d_far; ia.n_items = n_items;
     ia.H = fa.H; ia.Hflag = fa.Hflag; ia.e_item = e_item; ia.f_item = f_item; ia.stats = fa.stats;
-    const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
-    const int n_tiles = (rec->n_blobs + tile_blobs - 1) / tile_blobs;
-    MMO_REQUIRE(n_tiles <= 60, "receptor too large for the direct kernel (%d tiles of %d atoms)", n_tiles, MAX_TILE_GROUPS * kBlob);
-    const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)nf) * sizeof(float4) + 16 * sizeof(float2) +
-                        (size_t)(kItemTPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob +
-                        (size_t)(kItemTPB / 32) * NEAR_CAP + 16;
+    MMO_REQUIRE(rec->n_blobs < 65535, "receptor too large for the direct kernel (%d atoms)", rec->n);
+    const int near_cap = (rec->n_blobs + 8 + 7) & ~7;
+    const size_t smem = ((size_t)2 * rec->n_sup + (size_t)nf) * sizeof(float4) + 16 * sizeof(float2) +
+                        (size_t)(kItemTPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(kItemTPB / 32) * near_cap * sizeof(uint16_t) + 16;
+    MMO_REQUIRE(smem <= 200 * 1024, "receptor too large for the direct kernel (%d atoms)", rec->n);
     MMO_TRY(set_items_smem(smem));
     const int64_t n_units = ((int64_t)n_items + 63) / 64;
     const unsigned blocks = (unsigned)std::min<int64_t>(2LL * R.sm_count, (n_units + kItemTPB / 32 - 1) / (kItemTPB / 32));
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     {
         KernelScope ks(K_DIRECT_FP32);
-        for (int t = 0; t < n_tiles; t++) {
-            const int b0 = t * tile_blobs, nb = std::min(tile_blobs, rec->n_blobs - b0);
-            unsigned long long *w = g_work.p + t;
-            if (shifted && collect_stats) direct_items_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
-            else if (shifted) direct_items_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
-            else if (collect_stats) direct_items_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
-            else direct_items_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, kItemTPB, smem, R.stream>>>(ia, b0, nb, tile_blobs, w);
-            MMO_LAUNCH_CHECK();
-        }
+        unsigned long long *w = g_work.p;
+        if (shifted && collect_stats) direct_items_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, kItemTPB, smem, R.stream>>>(ia, near_cap, w);
+        else if (shifted) direct_items_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, kItemTPB, smem, R.stream>>>(ia, near_cap, w);
+        else if (collect_stats) direct_items_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, kItemTPB, smem, R.stream>>>(ia, near_cap, w);
+        else direct_items_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, kItemTPB, smem, R.stream>>>(ia, near_cap, w);
+        MMO_LAUNCH_CHECK();
     }
     KernelScope ks2(K_HARD_FIX);
     // close contacts per item, in the sorted (spatially coherent) order; then the items of a pose are summed in atom order

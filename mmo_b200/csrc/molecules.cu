@@ -103,8 +103,9 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     kd_order(n, xs, ys, zs, kBlob, order);
     r->n_blobs = (n + kBlob - 1) / kBlob;
     r->n_pad = r->n_blobs * kBlob;
-    std::vector<float4> xyzq(std::max(1, r->n_pad), make_float4(kFarAway, kFarAway, kFarAway, 0.f));
-    std::vector<uint8_t> gelt(std::max(1, r->n_pad), 0);
+    // one more group than there are leaves: group n_blobs holds far-away, charge-free atoms (padding of the near lists)
+    std::vector<float4> xyzq((size_t)r->n_pad + kBlob, make_float4(kFarAway, kFarAway, kFarAway, 0.f));
+    std::vector<uint8_t> gelt((size_t)r->n_pad + kBlob, 0);
     std::vector<float4> box((size_t)std::max(1, r->n_blobs) * 2, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int b = 0; b < r->n_blobs; b++) {
         float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
@@ -124,6 +125,20 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
         }
         box[(size_t)b * 2] = make_float4(blo[0], blo[1], blo[2], 0.f);
         box[(size_t)b * 2 + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
+    }
+
+    // super-groups: 32 consecutive leaves of the balanced k-d order are one subtree (or two neighbouring ones), i.e.
+    // spatially compact: first stage of the item kernel's group culling
+    r->n_sup = (r->n_blobs + 31) / 32;
+    std::vector<float4> sup((size_t)std::max(1, r->n_sup) * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int sg = 0; sg < r->n_sup; sg++) {
+        float4 lo4 = make_float4(3e38f, 3e38f, 3e38f, 0.f), hi4 = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+        for (int b = sg * 32; b < std::min(r->n_blobs, sg * 32 + 32); b++) {
+            const float4 bl = box[(size_t)b * 2], bh = box[(size_t)b * 2 + 1];
+            lo4.x = fminf(lo4.x, bl.x); lo4.y = fminf(lo4.y, bl.y); lo4.z = fminf(lo4.z, bl.z);
+            hi4.x = fmaxf(hi4.x, bh.x); hi4.y = fmaxf(hi4.y, bh.y); hi4.z = fmaxf(hi4.z, bh.z);
+        }
+        sup[(size_t)sg * 2] = lo4; sup[(size_t)sg * 2 + 1] = hi4;
     }
 
     // ---- close-contact voxel lists: atoms within r_list of any point of the voxel (conservative)
@@ -178,7 +193,7 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
         }
         if ((rc = r->x.upload(r->hx)) || (rc = r->y.upload(r->hy)) || (rc = r->z.upload(r->hz)) ||
             (rc = r->q.upload(r->hq)) || (rc = r->elt.upload(elt)) || (rc = r->xyzq.upload(xyzq)) || (rc = r->gelt.upload(gelt)) ||
-            (rc = r->blob_box.upload(box)) || (rc = r->vox_off.upload(cnt)) ||
+            (rc = r->blob_box.upload(box)) || (rc = r->sup_box.upload(sup)) || (rc = r->vox_off.upload(cnt)) ||
             (rc = r->vox_idx.upload(idx)))
             break;
     } while (0);
