@@ -202,6 +202,19 @@ int mmo_mask_whole_protein(int32_t n, const double *xs, const double *ys, const 
 int mmo_mask_roi_only(const double roi_c[3], double roi_r, double step, const int32_t dims[3], uint8_t *out_bits,
                       mmo_mask **out_mask);
 int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo_mask **out);
+int mmo_mask_download(const mmo_mask *mask, uint8_t *out_bits);
+/* N1: the `<rec>.bitmask` cache file of lds (Utls.bitmask_to_file / bitmask_from_file, src/utls.ml:12-20, used at
+ * src/lds.ml:1543-1553): one text line of '0'/'1', Bitv.M.to_string.  bitv is not vendored; per its documentation M
+ * puts the most significant bit first (character 0 = bit n-1): msb_first = 1.  UNPINNED -- msb_first = 0 writes /
+ * reads the other order (Bitv.L) should a real lds file turn out to use it. */
+int mmo_mask_write_bitmask(const mmo_mask *mask, const char *path, int msb_first);
+int mmo_mask_read_bitmask(const char *path, double step, const int32_t dims[3], int msb_first, mmo_mask **out);
+/* N1: the `.ba1.zst` variant of the map cache (Utls.zstd_compress_file / zstd_uncompress_file, src/utls.ml:22-45):
+ * like the reference, the external `zstd` program does the work (`zstd --rm -qf F`, `zstd -dqfk F.zst`); fails with
+ * MMO_EINVAL when it is not installed.  mmo_grid_read_ba1 accepts paths ending in .zst (lds.ml:540-553: uncompressed
+ * beside the file, read, transient copy removed; the .dims side-car is never compressed). */
+int mmo_zstd_compress_file(const char *path);
+int mmo_zstd_uncompress_file(const char *path_zst);
 int mmo_mask_destroy(mmo_mask *mask);
 /* Mol.protein_ligand_clash (src/mol.ml:1195-1203): out_flags[p] = 1 when any atom of pose p has any
  * of its 8 surrounding voxels set (G3D.vdW_clash_OR, src/G3D.ml:162-186) */
@@ -220,7 +233,7 @@ int mmo_carve_near_ligand(int32_t n_rec, const double *px, const double *py, con
  * Lds.protein_desolv roi grid prot_bst prot_solvent_shell prot (src/lds.ml:204-236): for every voxel of the protein's
  * first solvent shell (mmo_mask_first_solvent_shell of the receptor) inside the ROI, Const.desolvation * (voxel_vol *
  * sum over protein atoms within 12 A of (q_j / d2)^2); 0.0 elsewhere.  out_contribs (host, one double per voxel, index
- * i + j*x_dim + k*xy_dim) and out (device-resident handle; prot_shell must outlive it) may each be NULL.
+ * i + j*x_dim + k*xy_dim) and out (device-resident handle; it keeps its own copy of prot_shell) may each be NULL.
  * Neighbour order inside BST.neighbors is unpinned (library not vendored): atoms are added in index order. */
 typedef struct mmo_desolv mmo_desolv;
 int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, const double roi_c[3], double roi_r,

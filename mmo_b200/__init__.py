@@ -366,7 +366,8 @@ class G3D:
         arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
         h = _vp()
         _ck(lib().mmo_grid_read_ba1(arr, C.c_int32(len(paths)), C.byref(h)))
-        step, dims = _parse_dims(paths[0] + ".dims")
+        first = paths[0][:-4] if paths[0].endswith(".zst") else paths[0]      # the .dims side-car is never compressed
+        step, dims = _parse_dims(first + ".dims")
         return EnergyGrid(h, step, dims, len(paths))
 
 

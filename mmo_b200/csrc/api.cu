@@ -1,6 +1,8 @@
 // api.cu -- extern "C" entry points that move host buffers to HBM, launch, and copy results back.
 // Each function names the reference function it replaces in include/mmo_b200.h.
 #include "common.cuh"
+#include <ctype.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <math.h>
 #include <string.h>
@@ -271,7 +273,15 @@ int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) try {
     std::vector<float> all;
     size_t nvox = 0;
     for (int t = 0; t < T; t++) {
-        std::string dn = std::string(paths[t]) + ".dims";
+        // a compressed cache file (lds.ml:540-553): uncompressed next to it, read, and the transient copy removed
+        std::string fn = paths[t];
+        const bool zst = fn.size() > 4 && fn.compare(fn.size() - 4, 4, ".zst") == 0;
+        if (zst) {
+            MMO_TRY(mmo_zstd_uncompress_file(fn.c_str()));
+            fn.resize(fn.size() - 4);
+        }
+        struct Cleanup { std::string f; bool on; ~Cleanup() { if (on) remove(f.c_str()); } } cleanup{fn, zst};
+        std::string dn = fn + ".dims";
         FILE *f = fopen(dn.c_str(), "r");
         MMO_REQUIRE(f != nullptr, "mmo_grid_read_ba1: cannot open %s", dn.c_str());
         double s; int a, b, c;
@@ -284,12 +294,12 @@ int mmo_grid_read_ba1(const char *const *paths, int32_t T, mmo_grid **out) try {
             step = s; dims[0] = a; dims[1] = b; dims[2] = c; nvox = (size_t)a * b * c; all.resize(nvox * (size_t)T);
         }
         MMO_REQUIRE(s == step && a == dims[0] && b == dims[1] && c == dims[2], "mmo_grid_read_ba1: %s has another geometry", dn.c_str());
-        f = fopen(paths[t], "rb");
-        MMO_REQUIRE(f != nullptr, "mmo_grid_read_ba1: cannot open %s", paths[t]);
+        f = fopen(fn.c_str(), "rb");
+        MMO_REQUIRE(f != nullptr, "mmo_grid_read_ba1: cannot open %s", fn.c_str());
         size_t r = fread(all.data() + (size_t)t * nvox, sizeof(float), nvox, f);
         int extra = fgetc(f);
         fclose(f);
-        MMO_REQUIRE(r == nvox && extra == EOF, "mmo_grid_read_ba1: %s does not hold %zu floats", paths[t], nvox);   // assert(BA1.dim ba1 = n)
+        MMO_REQUIRE(r == nvox && extra == EOF, "mmo_grid_read_ba1: %s does not hold %zu floats", fn.c_str(), nvox);   // assert(BA1.dim ba1 = n)
     }
     return mmo_grid_upload(step, dims, T, all.data(), out);
 } MMO_CATCH_ALL
@@ -465,6 +475,81 @@ int mmo_mask_upload(double step, const int32_t dims[3], const uint8_t *bits, mmo
     return MMO_OK;
 } MMO_CATCH_ALL
 
+// Utls.bitmask_to_file / bitmask_from_file (src/utls.ml:12-20): one line of '0'/'1' characters, Bitv.M.to_string mask.
+// Bitv.M is the "most significant bit first" flavour of the bitv library (not vendored: the order is taken from its
+// documentation, UNPINNED): the first character is bit n - 1, the last one bit 0.  msb_first = 0 gives Bitv.L's order.
+int mmo_mask_write_bitmask(const mmo_mask *mask, const char *path, int msb_first) try {
+    MMO_REQUIRE(mask && path, "mmo_mask_write_bitmask: null argument");
+    const size_t n = mask->nbits;
+    std::string line(n + 1, '0');
+    for (size_t i = 0; i < n; i++) {
+        const bool b = (mask->hwords[i >> 5] >> (i & 31)) & 1u;
+        line[msb_first ? n - 1 - i : i] = b ? '1' : '0';
+    }
+    line[n] = '\n';
+    FILE *f = fopen(path, "w");
+    MMO_REQUIRE(f != nullptr, "mmo_mask_write_bitmask: cannot create %s", path);
+    const size_t w = fwrite(line.data(), 1, line.size(), f);
+    fclose(f);
+    MMO_REQUIRE(w == line.size(), "mmo_mask_write_bitmask: short write to %s", path);
+    return MMO_OK;
+} MMO_CATCH_ALL
+
+int mmo_mask_read_bitmask(const char *path, double step, const int32_t dims[3], int msb_first, mmo_mask **out) try {
+    MMO_TRY(require_ready());
+    MMO_REQUIRE(path && dims && out, "mmo_mask_read_bitmask: null argument");
+    *out = nullptr;
+    MMO_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && (double)dims[0] * dims[1] * dims[2] < 4.0e9, "mmo_mask_read_bitmask: bad dims");
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    FILE *f = fopen(path, "r");
+    MMO_REQUIRE(f != nullptr, "mmo_mask_read_bitmask: cannot open %s", path);
+    std::string line(n + 2, '\0');
+    const size_t r = fread(&line[0], 1, n + 2, f);
+    fclose(f);
+    // input_line: everything up to the first newline; Bitv.M.of_string raises on another length or character
+    size_t len = 0;
+    while (len < r && line[len] != '\n') len++;
+    MMO_REQUIRE(len == n, "mmo_mask_read_bitmask: %s holds %zu bits, the grid has %zu voxels", path, len, n);
+    std::vector<uint8_t> bits((n + 7) / 8 + 4, 0);
+    for (size_t c = 0; c < n; c++) {
+        const char ch = line[c];
+        MMO_REQUIRE(ch == '0' || ch == '1', "mmo_mask_read_bitmask: %s: character %d at column %zu", path, (int)ch, c);
+        const size_t i = msb_first ? n - 1 - c : c;
+        if (ch == '1') bits[i >> 3] |= (uint8_t)(1u << (i & 7));
+    }
+    return mmo_mask_upload(step, dims, bits.data(), out);
+} MMO_CATCH_ALL
+
+int mmo_mask_download(const mmo_mask *mask, uint8_t *out_bits) try {
+    MMO_REQUIRE(mask && out_bits, "mmo_mask_download: null argument");
+    memcpy(out_bits, mask->hwords.data(), (mask->nbits + 7) / 8);
+    return MMO_OK;
+} MMO_CATCH_ALL
+
+// Utls.zstd_compress_file / zstd_uncompress_file (src/utls.ml:22-45): the reference shells out to the zstd program, and
+// so does this (same command lines); an image without zstd gets MMO_EINVAL and keeps the uncompressed cache file
+static bool shell_safe(const char *p) {
+    for (; *p; p++)
+        if (!(isalnum((unsigned char)*p) || *p == '/' || *p == '.' || *p == '_' || *p == '-' || *p == '+' || *p == ',' || *p == '=' || *p == '@')) return false;
+    return true;
+}
+int mmo_zstd_compress_file(const char *path) try {
+    MMO_REQUIRE(path && *path && shell_safe(path), "mmo_zstd_compress_file: path must be made of [A-Za-z0-9/._+,=@-]");
+    const std::string cmd = std::string("zstd --rm -qf ") + path;        // remove quiet force
+    const int ret = system(cmd.c_str());
+    MMO_REQUIRE(ret == 0, "mmo_zstd_compress_file: command failed (is zstd installed?): %s", cmd.c_str());
+    return MMO_OK;
+} MMO_CATCH_ALL
+int mmo_zstd_uncompress_file(const char *path_zst) try {
+    MMO_REQUIRE(path_zst && shell_safe(path_zst), "mmo_zstd_uncompress_file: path must be made of [A-Za-z0-9/._+,=@-]");
+    const size_t n = strlen(path_zst);
+    MMO_REQUIRE(n > 4 && strcmp(path_zst + n - 4, ".zst") == 0, "mmo_zstd_uncompress_file: %s does not end in .zst", path_zst);
+    const std::string cmd = std::string("zstd -dqfk ") + path_zst;       // decompress quiet force keep
+    const int ret = system(cmd.c_str());
+    MMO_REQUIRE(ret == 0, "mmo_zstd_uncompress_file: command failed (is zstd installed?): %s", cmd.c_str());
+    return MMO_OK;
+} MMO_CATCH_ALL
+
 int mmo_mask_destroy(mmo_mask *mask) try {
     delete mask;
     return MMO_OK;
@@ -513,13 +598,18 @@ int mmo_desolv_protein(const mmo_receptor *rec, const mmo_mask *prot_shell, cons
     MMO_REQUIRE(rec && prot_shell && roi_c && roi_r >= 0.0, "mmo_desolv_protein: bad arguments");
     if (out) *out = nullptr;
     mmo_desolv *d = new mmo_desolv();
-    d->shell = prot_shell;
+    {
+        mmo_mask *own = nullptr;
+        int rc0 = mmo_mask_upload(prot_shell->step, prot_shell->dims, (const uint8_t *)prot_shell->hwords.data(), &own);
+        if (rc0 != MMO_OK) { delete d; return rc0; }
+        d->shell = own;
+    }
     const double roi[4] = {roi_c[0], roi_c[1], roi_c[2], roi_r};
     int rc = d->contribs.alloc(prot_shell->nbits);
     if (rc == MMO_OK) rc = launch_desolv_protein(rec, prot_shell, roi, d->contribs.p);
     if (rc == MMO_OK && out_contribs) rc = d2h_sync(out_contribs, d->contribs.p, prot_shell->nbits * sizeof(double));
     if (rc == MMO_OK && !out_contribs) { cudaError_t e = cudaStreamSynchronize(rt().stream); if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__); }
-    if (rc != MMO_OK || !out) { delete d; d = nullptr; }
+    if (rc != MMO_OK || !out) { delete d->shell; delete d; d = nullptr; }
     if (out) *out = d;
     return rc;
 } MMO_CATCH_ALL
@@ -561,6 +651,7 @@ int mmo_desolv_penalty_poses(const mmo_desolv *d, const mmo_ligand *lig, int64_t
 } MMO_CATCH_ALL
 
 int mmo_desolv_destroy(mmo_desolv *d) try {
+    if (d) delete d->shell;
     delete d;
     return MMO_OK;
 } MMO_CATCH_ALL

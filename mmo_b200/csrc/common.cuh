@@ -199,7 +199,8 @@ struct mmo_mask {
 };
 
 struct mmo_desolv {
-    const mmo_mask *shell = nullptr;   // the protein's first solvent shell (not owned: must outlive this handle)
+    const mmo_mask *shell = nullptr;   // the protein's first solvent shell: the handle's own copy (2 MB for the 0.5 A grid),
+                                       // so that the caller's mask may be destroyed (or garbage collected) first
     mmo::DevBuf<double> contribs;      // Lds.protein_desolv: one double per voxel, 0.0 outside shell AND ROI
 };
 

@@ -83,6 +83,18 @@ external place_ligand_in_roi :
   float array * float array
   = "mmo_ml_place_ligand_in_roi_bc" "mmo_ml_place_ligand_in_roi"
 
+(* Lds.simulate_lig frame loop (lds.ml:741-1000) for many chains in one launch -- chains = (ligand, start) pairs
+   (lds.ml:1997-2000, 2034-2050).  rec option (--no-interp) / grid option (interpolated), centred ligand,
+   (roi x y z r), temperature (K), steps, (tweak_rbonds, hard_roi, no_flip, intra_nb, num_atoms), seeds,
+   start rotations (9 floats per chain), start positions (3 per chain)
+   -> best_E per chain, best rotations (flat), best positions (flat), best coordinates (3 L per chain: xs ys zs),
+      frames done per chain (negative when Mol.Too_long ended the run) *)
+external mc_run :
+  receptor option -> grid option -> ligand -> float array -> float -> int ->
+  (bool * bool * bool * bool * int) -> int array -> float array -> float array ->
+  float array * float array * float array * float array * int array
+  = "mmo_ml_mc_run_bc" "mmo_ml_mc_run"
+
 (* ---- drop-in closures ------------------------------------------------------------------ *)
 
 let ligand_create (m: Mol.t): ligand =
@@ -110,3 +122,10 @@ let ene_intra lig_h (lig': Mol.t): float =
 (* Lds.desolvation_penalty grid prot_desolv_contribs prot_solvent_shell prot lig (lds.ml:239-267) *)
 let desolvation_penalty desolv_h lig_h (lig': Mol.t): float * float =
   desolv_penalty desolv_h lig_h lig'.Mol.xs lig'.Mol.ys lig'.Mol.zs
+
+(* Lds.simulate_lig for every start of one ligand at once: what main's array_pariteri over starts (lds.ml:2050) does
+   with one forked process per start.  Returns, per start, (best_E, best_rot as Rot.t-ordered floats, best_pos). *)
+let simulate_lig_starts ?rec_h ?grid_h lig_h (centered_lig: Mol.t) ~roi ~temperature ~nsteps
+    ~tweak_rbonds ~hard_roi ~no_flip ~intra_nb ~(seeds: int array) ~(rots: float array) ~(poss: float array) =
+  mc_run rec_h grid_h lig_h roi temperature nsteps
+    (tweak_rbonds, hard_roi, no_flip, intra_nb, Mol.num_atoms centered_lig) seeds rots poss

@@ -194,3 +194,68 @@ def test_c3_full_size_grid_and_lookup(gpu, orc):
         idx = nodes[:, 0] + nodes[:, 1] * 81 + nodes[:, 2] * 81 * 81
         got = gpu.Mol.interp_poses(g, one, np.tile(np.eye(3).reshape(9), (64, 1)), tt)
         assert np.array_equal(got, maps[typ, idx].astype(np.float64))
+
+
+def test_bitmask_text_file_round_trip(gpu, c2, tmp_path):
+    """N1: `<rec>.bitmask` (Utls.bitmask_to_file, utls.ml:12-20): one line of n '0'/'1' characters, Bitv.M order
+    (first character = bit n-1; unpinned library), read back to the same bits"""
+    import ctypes as C
+    L = gpu.lib()
+    dims = gpu.Grid.from_box(2.0, *c2["sim_dims"])
+    m = c2["rec"]
+    mask = gpu.Lds.vdW_volume(m.xs, m.ys, m.zs, m.r, 2.0, dims)
+    n = dims[0] * dims[1] * dims[2]
+    want = np.unpackbits(mask.bits, bitorder="little")[:n]
+    fn = str(tmp_path / "rec.pqrs.bitmask")
+    for msb in (1, 0):
+        assert L.mmo_mask_write_bitmask(mask.h, fn.encode(), C.c_int(msb)) == 0, L.mmo_last_error()
+        txt = open(fn).read()
+        assert txt.endswith("\n") and len(txt) == n + 1 and set(txt[:-1]) <= {"0", "1"}
+        chars = np.frombuffer(txt[:-1].encode(), np.uint8) - ord("0")
+        assert np.array_equal(chars[::-1] if msb else chars, want)
+        h = C.c_void_p()
+        assert L.mmo_mask_read_bitmask(fn.encode(), C.c_double(2.0), (C.c_int32 * 3)(*dims), C.c_int(msb), C.byref(h)) == 0, L.mmo_last_error()
+        got = np.zeros_like(mask.bits)
+        assert L.mmo_mask_download(h, got.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+        L.mmo_mask_destroy(h)
+        assert np.array_equal(got, mask.bits)
+    # wrong length / wrong character are refused (Bitv.M.of_string raises)
+    open(fn, "w").write("0101\n")
+    h = C.c_void_p()
+    assert L.mmo_mask_read_bitmask(fn.encode(), C.c_double(2.0), (C.c_int32 * 3)(*dims), C.c_int(1), C.byref(h)) != 0
+
+
+def test_ba1_zst_cache_through_the_zstd_program(gpu, small, tmp_path, monkeypatch):
+    """N1: `.ba1.zst` (utls.ml:22-45, lds.ml:516-553).  The reference shells out to `zstd`; this image has none, so a
+    stand-in script with the same command line (--rm -qf / -dqfk) is put on PATH: the test pins the commands the library
+    issues and the uncompress-read-remove sequence, not the compression format"""
+    import ctypes as C
+    import shutil
+    import stat
+    L = gpu.lib()
+    rec_m, dims, lig, ta, tq = small
+    rec = gpu.Receptor.from_mol(rec_m)
+    g, maps = gpu.Lds.pre_calculate_FF_components_grid(rec, 0.375, dims, ta[:2], tq[:2])
+    paths = [str(tmp_path / f"lig.mol2.t{t}.ba1") for t in range(2)]
+    if shutil.which("zstd") is None:
+        h = C.c_void_p()
+        g.write_ba1(0, paths[0])
+        assert L.mmo_zstd_compress_file(paths[0].encode()) != 0 and b"zstd" in L.mmo_last_error()
+        fake = tmp_path / "bin"
+        fake.mkdir()
+        (fake / "zstd").write_text('#!/bin/sh\n'
+                                   'case "$1" in\n'
+                                   '  --rm) [ "$2" = "-qf" ] || exit 2; cp "$3" "$3.zst" && rm "$3";;\n'
+                                   '  -dqfk) cp "$2" "${2%.zst}";;\n'
+                                   '  *) exit 2;;\n'
+                                   'esac\n')
+        os.chmod(fake / "zstd", os.stat(fake / "zstd").st_mode | stat.S_IEXEC)
+        monkeypatch.setenv("PATH", str(fake) + os.pathsep + os.environ["PATH"])
+    for t in range(2):
+        g.write_ba1(t, paths[t])
+        assert L.mmo_zstd_compress_file(paths[t].encode()) == 0, L.mmo_last_error()
+        assert not os.path.exists(paths[t]) and os.path.exists(paths[t] + ".zst") and os.path.exists(paths[t] + ".dims")
+    g2 = gpu.G3D.of_ba1_files([p + ".zst" for p in paths])
+    assert np.array_equal(g2.download(), maps)
+    assert not os.path.exists(paths[0])                     # the transient uncompressed copy is gone (lds.ml:551-552)
+    assert L.mmo_zstd_uncompress_file(b"/tmp/x; rm -rf y.zst") != 0      # nothing but plain path characters reaches the shell
