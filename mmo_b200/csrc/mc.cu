@@ -189,7 +189,8 @@ __device__ double direct_energy(const McArgs &a, const double *x, const double *
 // (bar.sync on its barrier) while the helpers are already on chunk c + 1.  The trilinear look-ups of E_inter go the
 // same way (one per thread of the first warps, barrier 15).  Commands to the helpers are double buffered by sequence
 // number, so that warp 0 can post the next one while a helper still reads the last.
-constexpr int kMaxChunks = 14;                     // named barriers 1..14 carry the intra chunks, 15 the look-ups
+constexpr int kMaxChunks = 13;                     // named barriers 1..13 carry the intra chunks, 14 the look-ups, 15 the hand-over
+constexpr int kBarLookups = 14, kBarHandOver = 15;  // (barrier 0 stays __syncthreads' own: every thread, one place in the code)
 struct McCmd { int src, do_intra, do_inter, quit; };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -230,6 +231,7 @@ __device__ __forceinline__ void mc_produce(const McArgs &a, const McShared &S, c
             }
             for (; k < (r + 1) * CH; k += H) S.terms[k] = make_double2(0.0, 0.0);      // padding of the last chunk(s)
             __threadfence_block();
+            __syncwarp();                 // bar.arrive is warp-aligned: the lanes' trip counts above differ
             bar_arrive(1 + r, NT);
         }
         if (a.prof && blockIdx.x == 0 && h == 0) a.prof[7] += clock64() - tp0;
@@ -238,24 +240,28 @@ __device__ __forceinline__ void mc_produce(const McArgs &a, const McShared &S, c
         for (int j = h; j < a.L; j += n_lw * 32)
             S.iterms[j] = d_trilin(a.g, a.maps + (size_t)S.ltyp[j] * a.g.nvox, x[j], y[j], z[j]);
         __threadfence_block();
-        bar_arrive(15, n_lw * 32 + 32);
+        __syncwarp();
+        bar_arrive(kBarLookups, n_lw * 32 + 32);
     }
 }
 
-// warp 0: post a command, then add everything up in the reference's order as the helpers deliver it
-template <int NT>
-__device__ __forceinline__ void mc_eval(const McArgs &a, const McShared &S, int lane, int &seq, int src, bool do_intra,
-                                        bool do_inter, int n_lw, int R, int CH, double &E_intra, double &E_inter, long long *pc) {
-    const bool interp = do_inter && a.maps != nullptr;
-    long long t0 = clock64();
+// warp 0, before the hand-over barrier: publish what the helpers have to produce
+__device__ __forceinline__ void mc_post(const McShared &S, int lane, int &seq, int src, bool do_intra, bool interp, bool quit) {
     if (lane == 0) {
         volatile McCmd *dst = S.cmd + (seq & 1);
-        dst->src = src; dst->do_intra = do_intra ? 1 : 0; dst->do_inter = interp ? 1 : 0; dst->quit = 0;
+        dst->src = src; dst->do_intra = do_intra ? 1 : 0; dst->do_inter = interp ? 1 : 0; dst->quit = quit ? 1 : 0;
     }
     seq++;
-    __syncthreads();                              // coordinates and command visible to the helpers
+    __syncwarp();                                 // lane 0 back with the others: bar.sync is warp-aligned
+}
+
+// warp 0, after the hand-over: add everything up in the reference's order as the helpers deliver it
+template <int NT>
+__device__ __forceinline__ void mc_sum(const McArgs &a, const McShared &S, int lane, int src, bool do_intra, bool do_inter,
+                                       int n_lw, int R, int CH, double &E_intra, double &E_inter, long long *pc) {
+    const bool interp = do_inter && a.maps != nullptr;
+    long long t0 = clock64();
     const double *x = src ? S.cx : S.lx, *y = src ? S.cy : S.ly, *z = src ? S.cz : S.lz;
-    { const long long t = clock64(); pc[2] += t - t0; t0 = t; }
     if (do_inter && !interp) E_inter = direct_energy(a, x, y, z, lane, S.scratch);
     if (do_intra) {
         double se = 0.0, sv = 0.0;                 // Mol.ene_intra_UFFNB_brute (mol.ml:881-903), pairs in (i<j) order
@@ -286,7 +292,7 @@ __device__ __forceinline__ void mc_eval(const McArgs &a, const McShared &S, int 
         { const long long t = clock64(); pc[4] += t - t0; t0 = t; }
     }
     if (interp) {
-        bar_sync(15, n_lw * 32 + 32);
+        bar_sync(kBarLookups, n_lw * 32 + 32);
         double res = 0.0;                          // Mol.ene_inter_UFF_interp (mol.ml:1012-1020): res := !res +. trilin ...
         int j = 0;
         for (; j + 8 <= a.L; j += 8) {
@@ -338,19 +344,10 @@ mc_chain_kernel(McArgs a) {
     __syncthreads();
     const int *const s_left = S.rb, *const s_right = S.rb + nrb, *const s_rgoff = S.rb + 2 * nrb, *const s_rgidx = S.rb + 3 * nrb + 1;
 
-    if (wid != 0) {
-        // ---- helpers: wait for a command, produce its terms ----
-        for (int seq = 0;; seq++) {
-            __syncthreads();
-            const volatile McCmd *src = S.cmd + (seq & 1);
-            McCmd c;
-            c.src = src->src; c.do_intra = src->do_intra; c.do_inter = src->do_inter; c.quit = src->quit;
-            if (c.quit) return;
-            mc_produce<NT>(a, S, c, tid, n_lw, R, CH);
-        }
-    }
-
-    // ---- warp 0: the chain ----
+    // ---- every warp runs the loop below and meets the others at ONE hand-over barrier per evaluation; warp 0 (w0) owns the
+    //      chain, the other warps only produce terms.  The state declared here lives in warp 0's registers (the helpers'
+    //      copies are dead).  phase 0: constant E_intra of the rigid ligand, 1: start energies, 2: the frames.
+    const bool w0 = wid == 0;
     int seq = 0;
     double *const cx = S.cx, *const cy = S.cy, *const cz = S.cz, *const px = S.px, *const py = S.py, *const pz = S.pz;
     double *const lx = S.lx, *const ly = S.ly, *const lz = S.lz, *const dr = S.dr, *const drp = S.drp;
@@ -363,8 +360,10 @@ mc_chain_kernel(McArgs a) {
     const uint64_t seed = a.seeds[chain];
     uint64_t ctr = 0;
 
-    for (int j = lane; j < L; j += 32) { cx[j] = a.lx[j]; cy[j] = a.ly[j]; cz[j] = a.lz[j]; }
-    for (int b = lane; b < nrb; b += 32) { dr[b] = a.p_max_rbond_rot; sw_reset(sw_bond[b]); }
+    if (w0) {
+        for (int j = lane; j < L; j += 32) { cx[j] = a.lx[j]; cy[j] = a.ly[j]; cz[j] = a.lz[j]; }
+        for (int b = lane; b < nrb; b += 32) { dr[b] = a.p_max_rbond_rot; sw_reset(sw_bond[b]); }
+    }
     double ccen[3] = {0.0, 0.0, 0.0}, pcen[3] = {0.0, 0.0, 0.0};        // conf.center, conf'.center
     Sw sw_rigid;
     sw_reset(sw_rigid);
@@ -374,35 +373,45 @@ mc_chain_kernel(McArgs a) {
     for (int k = 0; k < 9; k++) rot[k] = a.rot0[chain * 9 + k];
 #pragma unroll
     for (int k = 0; k < 3; k++) pos[k] = a.pos0[chain * 3 + k];
-    if (lane < 9) { rot0[lane] = a.rot0[chain * 9 + lane]; best_rot[lane] = (lane % 4 == 0) ? 1.0 : 0.0; }
-    if (lane < 3) { pos0[lane] = a.pos0[chain * 3 + lane]; best_pos[lane] = 0.0; }
     double *bxyz = a.best_xyz + chain * 3 * (int64_t)L;
-    __syncwarp();
-    // start_conf = rotate_then_translate_copy centered_lig rot0 pos0 (lds.ml:758)
-    for (int j = lane; j < L; j += 32) {
-        double x, y, z;
-        rot_apply(rot, cx[j], cy[j], cz[j], x, y, z);
-        lx[j] = x + pos[0]; ly[j] = y + pos[1]; lz[j] = z + pos[2];
-        bxyz[j] = lx[j]; bxyz[L + j] = ly[j]; bxyz[2 * L + j] = lz[j];
+    if (w0) {
+        if (lane < 9) { rot0[lane] = a.rot0[chain * 9 + lane]; best_rot[lane] = (lane % 4 == 0) ? 1.0 : 0.0; }
+        if (lane < 3) { pos0[lane] = a.pos0[chain * 3 + lane]; best_pos[lane] = 0.0; }
+        __syncwarp();
+        // start_conf = rotate_then_translate_copy centered_lig rot0 pos0 (lds.ml:758)
+        for (int j = lane; j < L; j += 32) {
+            double x, y, z;
+            rot_apply(rot, cx[j], cy[j], cz[j], x, y, z);
+            lx[j] = x + pos[0]; ly[j] = y + pos[1]; lz[j] = z + pos[2];
+            bxyz[j] = lx[j]; bxyz[L + j] = ly[j]; bxyz[2 * L + j] = lz[j];
+        }
     }
-    double const_intra = 0.0, dummy = 0.0;
+    double const_intra = 0.0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles: 0 conformer move, 1 rigid move + lig', 2 hand-over, 3 E_inter, 4 E_intra sum, 5 accept/bookkeeping
-    if (a.intra_nb && !flexible) mc_eval<NT>(a, S, lane, seq, 1, true, false, n_lw, R, CH, const_intra, dummy, pc);
-    double prev_E_intra = 0.0, prev_E_inter = 0.0;
-    if (a.intra_nb && !flexible) prev_E_intra = const_intra;
-    mc_eval<NT>(a, S, lane, seq, 0, a.intra_nb && flexible, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
-    double prev_E = prev_E_inter + prev_E_intra;
-#pragma unroll
-    for (int k = 0; k < 8; k++) pc[k] = 0;
-    double best_E = prev_E;
+    double prev_E_intra = 0.0, prev_E_inter = 0.0, prev_E = 0.0, best_E = 0.0;
     int rigid_step = 0, conf_step = 0;
     int n_acc_r = 0, n_rej_r = 0, n_acc_c = 0, n_rej_c = 0, n_ooroi = 0, n_ezero = 0, too_long = 0;
     int frame = 0;
-    for (; frame < a.n_steps; frame++) {
-        const bool rigid = (frame & 1) == 0;
-        int just_rotated = -1;
-        int which = 0;                                  // conf' is: 0 = conf, 1 = proposed copy, 2 = centred template
-        long long tf0 = clock64();
+    int phase = (a.intra_nb && !flexible) ? 0 : 1;
+    // per-frame state of warp 0 that lives across the hand-over
+    bool rigid = true;
+    int just_rotated = -1, which = 0;                   // conf' is: 0 = conf, 1 = proposed copy, 2 = centred template
+    double rotp[9], posp[3];
+    long long tf0 = 0;
+    int cmd_src = 0;
+    bool cmd_intra = false, cmd_inter = false;
+    for (;;) {
+      bool quit = false;
+      if (w0) {
+        // ---- warp 0 before the hand-over: what is evaluated next, on which coordinates ----
+        if (phase == 0) { cmd_src = 1; cmd_intra = true; cmd_inter = false; }
+        else if (phase == 1) { cmd_src = 0; cmd_intra = a.intra_nb && flexible; cmd_inter = true; }
+        else if (frame >= a.n_steps) quit = true;
+        else {
+        rigid = (frame & 1) == 0;
+        just_rotated = -1;
+        which = 0;
+        tf0 = clock64();
         if (!rigid) {
             if (flexible) {
                 for (int j = lane; j < L; j += 32) { px[j] = cx[j]; py[j] = cy[j]; pz[j] = cz[j]; }
@@ -451,14 +460,13 @@ mc_chain_kernel(McArgs a) {
                 for (int j = lane; j < L; j += 32) maxd2 = fmax(maxd2, d_dist2(pcen[0], pcen[1], pcen[2], px[j], py[j], pz[j]));
                 for (int o = 16; o > 0; o >>= 1) maxd2 = fmax(maxd2, __shfl_xor_sync(0xffffffffu, maxd2, o));
                 const double maxi = 0.01 + sqrt(maxd2);
-                if (maxi > 12.0) { too_long = 1; break; }          // Mol.Too_long ends this run (lds.ml:996-997)
+                if (maxi > 12.0) { too_long = 1; quit = true; }    // Mol.Too_long ends this run (lds.ml:996-997)
                 which = 1;
             } else {
                 which = 2;
             }
         }
         { const long long t = clock64(); pc[0] += t - tf0; tf0 = t; }
-        double rotp[9], posp[3];
 #pragma unroll
         for (int k = 0; k < 9; k++) rotp[k] = rot[k];
 #pragma unroll
@@ -492,7 +500,42 @@ mc_chain_kernel(McArgs a) {
         // D2: a conformer frame overwrites prev_E_intra with the trial's value, accepted or not
         if (!rigid && a.intra_nb && !flexible) prev_E_intra = const_intra;
         { const long long t = clock64(); pc[1] += t - tf0; }
-        mc_eval<NT>(a, S, lane, seq, 0, !rigid && a.intra_nb && flexible, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
+        cmd_src = 0; cmd_intra = !rigid && a.intra_nb && flexible; cmd_inter = true;
+        }
+        tf0 = clock64();
+        mc_post(S, lane, seq, cmd_src, cmd_intra, cmd_inter && a.maps != nullptr, quit);
+      }
+      // ---- the hand-over: ONE barrier instruction for every warp of the block (coordinates and command visible) ----
+      bar_sync(kBarHandOver, NT);
+      if (!w0) {
+        const volatile McCmd *src = S.cmd + (seq & 1);
+        McCmd c;
+        c.src = src->src; c.do_intra = src->do_intra; c.do_inter = src->do_inter; c.quit = src->quit;
+        seq++;
+        if (c.quit) break;
+        mc_produce<NT>(a, S, c, tid, n_lw, R, CH);
+        continue;
+      }
+      if (quit) break;
+      pc[2] += clock64() - tf0;
+      // ---- warp 0 after the hand-over: the sums, then the bookkeeping of the phase ----
+      if (phase == 0) {
+        double dummy = 0.0;
+        mc_sum<NT>(a, S, lane, 1, true, false, n_lw, R, CH, const_intra, dummy, pc);
+        prev_E_intra = const_intra;
+        phase = 1;
+        continue;
+      }
+      mc_sum<NT>(a, S, lane, 0, cmd_intra, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
+      if (phase == 1) {
+        prev_E = prev_E_inter + prev_E_intra;
+        best_E = prev_E;
+#pragma unroll
+        for (int k = 0; k < 8; k++) pc[k] = 0;
+        phase = 2;
+        continue;
+      }
+      {
         tf0 = clock64();
         const double curr_E = prev_E_inter + prev_E_intra;
         int accepted = -1;
@@ -585,14 +628,14 @@ mc_chain_kernel(McArgs a) {
         if (rigid) rigid_step++; else conf_step++;
         __syncwarp();
         pc[5] += clock64() - tf0;
+        frame++;
+      }
     }
+    if (!w0) return;
     if (a.prof && chain == 0 && lane == 0) {
 #pragma unroll
         for (int k = 0; k < 7; k++) a.prof[k] = pc[k];
     }
-    // release the helpers
-    if (lane == 0) { volatile McCmd *dst = S.cmd + (seq & 1); dst->quit = 1; }
-    __syncthreads();
     if (lane == 0) {
         a.best_E[chain] = best_E;
         a.prev_E[chain] = prev_E;
@@ -1012,7 +1055,7 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     const int nrb1 = std::max(lig->n_rbonds, 1);
     // conf, conf', lig' (9 L), step sizes (2 nrb), look-up terms (L), kept scalars (24), alignment (1), direct-scorer
     // scratch (32 double2), intra terms (n_pairs double2), per-bond windows, two command slots
-    const size_t smem = ((size_t)10 * L + 2 * nrb1 + 24 + 1) * sizeof(double) + ((size_t)32 + lig->n_pairs + 14 * 9 + 8) * sizeof(double2) +
+    const size_t smem = ((size_t)10 * L + 2 * nrb1 + 24 + 1) * sizeof(double) + ((size_t)32 + lig->n_pairs + 13 * 9 + 16) * sizeof(double2) +
                         (size_t)nrb1 * sizeof(Sw) + 2 * sizeof(McCmd) +
                         ((size_t)L + 3 * (size_t)lig->n_rbonds + 1 + lig->rg_idx.size()) * sizeof(int) + 16;
     MMO_REQUIRE(smem <= 200 * 1024, "mmo_mc_run: ligand too large (%d atoms, %d rotatable bonds, %d interacting pairs)", L, lig->n_rbonds, lig->n_pairs);

@@ -1,0 +1,13 @@
+#!/bin/bash
+# On the GPU box: compute-sanitizer over small invocations of every kernel family; one summary file per tool under
+# gpurun_out/ (copied to profiles/ afterwards).  Usage: tools/sanitize.sh <tag>
+cd "$(dirname "$0")/.."
+tag=${1:-r2}
+mkdir -p gpurun_out
+for tool in memcheck racecheck synccheck initcheck; do
+  out=gpurun_out/${tag}_sanitizer_${tool}.log
+  extra=""
+  [ $tool = memcheck ] && extra="--leak-check no"
+  timeout 900 compute-sanitizer --tool $tool $extra --print-limit 20 python tools/sanitize_driver.py > $out 2>&1
+  echo "== $tool: exit $? =="; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_driver done|Error:|Race reported|hazard" $out | sort | uniq -c | head -12
+done
