@@ -256,19 +256,19 @@ __device__ __forceinline__ void mc_post(const McShared &S, int lane, int &seq, i
 }
 
 // warp 0, after the hand-over: add everything up in the reference's order as the helpers deliver it
-template <int NT>
+template <int NT, bool PROF>
 __device__ __forceinline__ void mc_sum(const McArgs &a, const McShared &S, int lane, int src, bool do_intra, bool do_inter,
                                        int n_lw, int R, int CH, double &E_intra, double &E_inter, long long *pc) {
     const bool interp = do_inter && a.maps != nullptr;
-    long long t0 = clock64();
+    long long t0 = PROF ? clock64() : 0;
     const double *x = src ? S.cx : S.lx, *y = src ? S.cy : S.ly, *z = src ? S.cz : S.lz;
     if (do_inter && !interp) E_inter = direct_energy(a, x, y, z, lane, S.scratch);
     if (do_intra) {
         double se = 0.0, sv = 0.0;                 // Mol.ene_intra_UFFNB_brute (mol.ml:881-903), pairs in (i<j) order
         for (int r = 0; r < R; r++) {
-            const long long tb = clock64();
+            const long long tb = PROF ? clock64() : 0;
             bar_sync(1 + r, NT);
-            pc[6] += clock64() - tb;
+            if (PROF) pc[6] += clock64() - tb;
             // Rotating buffer of 8 terms: the load of term k + 8 is issued when term k is consumed, ~66 cycles (8 dependent
             // DADDs) ahead of its own use, so the chain never waits on shared memory.  Every chunk holds CH terms (a
             // multiple of 8): the helpers fill the slots beyond the last pair with +0.0, which leaves the (never -0.0)
@@ -289,7 +289,7 @@ __device__ __forceinline__ void mc_sum(const McArgs &a, const McShared &S, int l
             for (int q = 0; q < 8; q++) { se = se + u[q].x; sv = sv + u[q].y; }
         }
         E_intra = (kElecWeight * se) + sv;
-        { const long long t = clock64(); pc[4] += t - t0; t0 = t; }
+        if (PROF) { const long long t = clock64(); pc[4] += t - t0; t0 = t; }
     }
     if (interp) {
         bar_sync(kBarLookups, n_lw * 32 + 32);
@@ -305,10 +305,10 @@ __device__ __forceinline__ void mc_sum(const McArgs &a, const McShared &S, int l
         for (; j < a.L; j++) res = res + S.iterms[j];
         E_inter = res;
     }
-    pc[3] += clock64() - t0;
+    if (PROF) pc[3] += clock64() - t0;
 }
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool PROF>
 __global__ void __launch_bounds__(NT, MINB)
 mc_chain_kernel(McArgs a) {
     extern __shared__ double smem[];
@@ -411,7 +411,7 @@ mc_chain_kernel(McArgs a) {
         rigid = (frame & 1) == 0;
         just_rotated = -1;
         which = 0;
-        tf0 = clock64();
+        if (PROF) tf0 = clock64();
         if (!rigid) {
             if (flexible) {
                 for (int j = lane; j < L; j += 32) { px[j] = cx[j]; py[j] = cy[j]; pz[j] = cz[j]; }
@@ -466,7 +466,7 @@ mc_chain_kernel(McArgs a) {
                 which = 2;
             }
         }
-        { const long long t = clock64(); pc[0] += t - tf0; tf0 = t; }
+        if (PROF) { const long long t = clock64(); pc[0] += t - tf0; tf0 = t; }
 #pragma unroll
         for (int k = 0; k < 9; k++) rotp[k] = rot[k];
 #pragma unroll
@@ -499,10 +499,10 @@ mc_chain_kernel(McArgs a) {
         }
         // D2: a conformer frame overwrites prev_E_intra with the trial's value, accepted or not
         if (!rigid && a.intra_nb && !flexible) prev_E_intra = const_intra;
-        { const long long t = clock64(); pc[1] += t - tf0; }
+        if (PROF) { const long long t = clock64(); pc[1] += t - tf0; }
         cmd_src = 0; cmd_intra = !rigid && a.intra_nb && flexible; cmd_inter = true;
         }
-        tf0 = clock64();
+        if (PROF) tf0 = clock64();
         mc_post(S, lane, seq, cmd_src, cmd_intra, cmd_inter && a.maps != nullptr, quit);
       }
       // ---- the hand-over: ONE barrier instruction for every warp of the block (coordinates and command visible) ----
@@ -517,16 +517,16 @@ mc_chain_kernel(McArgs a) {
         continue;
       }
       if (quit) break;
-      pc[2] += clock64() - tf0;
+      if (PROF) pc[2] += clock64() - tf0;
       // ---- warp 0 after the hand-over: the sums, then the bookkeeping of the phase ----
       if (phase == 0) {
         double dummy = 0.0;
-        mc_sum<NT>(a, S, lane, 1, true, false, n_lw, R, CH, const_intra, dummy, pc);
+        mc_sum<NT, PROF>(a, S, lane, 1, true, false, n_lw, R, CH, const_intra, dummy, pc);
         prev_E_intra = const_intra;
         phase = 1;
         continue;
       }
-      mc_sum<NT>(a, S, lane, 0, cmd_intra, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
+      mc_sum<NT, PROF>(a, S, lane, 0, cmd_intra, true, n_lw, R, CH, prev_E_intra, prev_E_inter, pc);
       if (phase == 1) {
         prev_E = prev_E_inter + prev_E_intra;
         best_E = prev_E;
@@ -536,7 +536,7 @@ mc_chain_kernel(McArgs a) {
         continue;
       }
       {
-        tf0 = clock64();
+        if (PROF) tf0 = clock64();
         const double curr_E = prev_E_inter + prev_E_intra;
         int accepted = -1;
         const double ddx = a.roi_c[0] - (0.0 + posp[0]), ddy = a.roi_c[1] - (0.0 + posp[1]), ddz = a.roi_c[2] - (0.0 + posp[2]);
@@ -627,12 +627,12 @@ mc_chain_kernel(McArgs a) {
         }
         if (rigid) rigid_step++; else conf_step++;
         __syncwarp();
-        pc[5] += clock64() - tf0;
+        if (PROF) pc[5] += clock64() - tf0;
         frame++;
       }
     }
     if (!w0) return;
-    if (a.prof && chain == 0 && lane == 0) {
+    if (PROF && a.prof && chain == 0 && lane == 0) {
 #pragma unroll
         for (int k = 0; k < 7; k++) a.prof[k] = pc[k];
     }
@@ -1073,14 +1073,17 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
             const unsigned blocks = (unsigned)((n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock);
             mc_warp_kernel<7><<<blocks, kWarpsPerBlock * 32, wsmem, R.stream>>>(a);
         } else if (nt == 64) {
-            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<64, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            mc_chain_kernel<64, 10><<<(unsigned)n_chains, 64, smem, R.stream>>>(a);
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<64, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<64, 10, false><<<(unsigned)n_chains, 64, smem, R.stream>>>(a);
+        } else if (nt == 128 && want_prof) {       // MMO_MC_PROFILE: the build with cycle counters around every phase
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<128, 4, true><<<(unsigned)n_chains, 128, smem, R.stream>>>(a);
         } else if (nt == 128) {
-            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            mc_chain_kernel<128, 4><<<(unsigned)n_chains, 128, smem, R.stream>>>(a);
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<128, 4, false><<<(unsigned)n_chains, 128, smem, R.stream>>>(a);
         } else {
-            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            mc_chain_kernel<256, 2><<<(unsigned)n_chains, 256, smem, R.stream>>>(a);
+            MMO_CUDA(cudaFuncSetAttribute(mc_chain_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mc_chain_kernel<256, 2, false><<<(unsigned)n_chains, 256, smem, R.stream>>>(a);
         }
     }
     MMO_LAUNCH_CHECK();

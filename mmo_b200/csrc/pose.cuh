@@ -20,8 +20,18 @@ __device__ __forceinline__ double rot_row(double a, double b, double c, double x
 
 // scan frame -> (rotation, lattice node): frame = rot_i + n_rot*(i + j*x_dim + k*xy_dim) (src/lds.ml:1100)
 __device__ __forceinline__ void load_pose_rt_frame(const PoseSrc &s, int64_t frame, PoseRT &o) {
-    int64_t pt = frame / s.n_rot;
-    int rot_i = (int)(frame - pt * s.n_rot);
+    // 32-bit division whenever the frame id allows it (C2: 9702 lattice nodes x 1e5 rotations < 2^32): the 64-bit
+    // software division costs ~100 instructions, and the fp32 kernel decodes every pose once per ligand chunk
+    int64_t pt;
+    int rot_i;
+    if ((unsigned long long)frame < 0x100000000ull) {
+        const unsigned f = (unsigned)frame, q = f / (unsigned)s.n_rot;
+        pt = q;
+        rot_i = (int)(f - q * (unsigned)s.n_rot);
+    } else {
+        pt = frame / s.n_rot;
+        rot_i = (int)(frame - pt * s.n_rot);
+    }
     int xy = s.lat_dims[0] * s.lat_dims[1];
     int k = (int)(pt / xy);
     int j = (int)((pt - (int64_t)k * xy) / s.lat_dims[0]);
