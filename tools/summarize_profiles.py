@@ -27,7 +27,8 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 
 
 def launches(tag, fn):
@@ -77,6 +78,10 @@ def ncu(tag, kernel, rep):
         if k in d:
             out.append(f"| {k} | {d[k][0]} | {d[k][1]} |")
             keep_rows.append((k, d[k][0], d[k][1]))
+    # per-phase split of the warp-stall samples (tools/ncu_phases.py: segments by execution count)
+    ph = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_phases.py"), rep, kernel, "12"], capture_output=True, text=True).stdout
+    if ph.strip():
+        out += ["", "## where the warps spend their time (source page, stall samples per code segment)", "", "```", ph.rstrip(), "```"]
     open(os.path.join(ROOT, "profiles", f"{tag}_ncu_{kernel}.md"), "w").write("\n".join(out) + "\n")
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_{kernel}.csv"), "w") as f:
         w = csv.writer(f)
