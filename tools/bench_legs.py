@@ -370,6 +370,33 @@ def leg_fp64_scan(ctx, job_params, n_active, pps, n_rot, quick=False):
             "scaling": "weak", "best_score": SR.best_score, "best_frame": SR.best_frame, "clocks": ck.summary()}
 
 
+def leg_n4(ctx, quick=False):
+    """N4: the Majeux-Caflisch desolvation sums on the reference's own 0.5 A grid over the simulation box (wall clock,
+    one GPU; bit-identical to the oracle's loops in tests/test_desolv.py)"""
+    import mmo_b200
+    from mmo_b200 import workloads
+    c2 = workloads.load_c2("ligdecs")
+    rm = c2["rec"]
+    sdims = mmo_b200.Grid.from_box(0.5, *c2["sim_dims"])
+    lig = mmo_b200.Ligand.from_mol(c2["lig"], centered=True)
+    shell = mmo_b200.Lds.first_solvent_shell(rm.xs, rm.ys, rm.zs, rm.r, 0.5, sdims)
+    rec_all = mmo_b200.Receptor.from_mol(rm)
+    ctx.ck(ctx.L.mmo_sync())
+    t0 = time.perf_counter()
+    dh, _ = mmo_b200.Lds.protein_desolv(c2["roi"], rec_all, shell, want_host=False)
+    t_prot = time.perf_counter() - t0
+    n_pen = 2000 if quick else 20000
+    Rp, tp = workloads.random_poses_in_sphere(n_pen, c2["roi"][:3], 6.0, seed=43)
+    mmo_b200.Lds.desolvation_penalty(dh, lig, rot9=Rp[:64], trans3=tp[:64])
+    t0 = time.perf_counter()
+    dp, dl = mmo_b200.Lds.desolvation_penalty(dh, lig, rot9=Rp, trans3=tp)
+    t_pen = time.perf_counter() - t0
+    return {"workload": "N4 desolvation: Lds.protein_desolv on the 0.5 A simulation grid, then Lds.desolvation_penalty of random poses",
+            "grid_dims": list(sdims), "receptor_atoms": rm.n, "protein_desolv_wall_ms": t_prot * 1e3, "penalty_poses": n_pen,
+            "penalty_wall_ms": t_pen * 1e3, "penalty_poses_per_s": n_pen / t_pen, "median_prot": float(np.median(dp)),
+            "median_lig": float(np.median(dl))}
+
+
 def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0, only=None):
     out = {}
     t0 = time.perf_counter()
@@ -381,6 +408,8 @@ def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0, only
         out["c4_mc"] = leg_c4(ctx, quick)
     if only in (None, "c5"):
         out["c5_screen"] = leg_c5(ctx, pk, quick)
+    if only == "n4":
+        out["n4_desolvation"] = leg_n4(ctx, quick)
     if scan_params is not None:
         out["c2_fp64_scan"] = leg_fp64_scan(ctx, scan_params, n_active, pps, n_rot, quick)
     ctx.ck(ctx.L.mmo_kernel_timing(0))
