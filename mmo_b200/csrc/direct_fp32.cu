@@ -69,6 +69,8 @@ struct FastArgs {
     const float4 *xyzq;
     const uint8_t *gelt;
     const float4 *blob_box;
+    const float4 *sup_box;       // boxes of 32 consecutive groups (untiled mode: receptors of more than 2048 atoms)
+    int n_sup;
     double origin[3];
     int L;                   // real ligand atoms
     int n_fast;              // padded to a multiple of 8
@@ -184,9 +186,12 @@ __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const 
 // [2*tile_groups], ligand parameters [n_fast], vdW table [16] float2, chunk coordinates x|y|z [LJ][PPB],
 // per-warp lists [NF][LIST_CAP] (structure of arrays: conflict-free compaction stores, LDS.128 = 4 atoms
 // of one field), element bytes [tile_atoms].
-template <int VARIANT, bool STATS>
+// TILED: the (ROI) receptor fits one shared-memory tile (<= 2048 atoms: C2).  Otherwise the groups are read through L1
+// (read-only path) and culled in two stages over super-groups of 32, as in the item kernel: ONE launch for a receptor of
+// any size instead of one per tile, each of which decoded the poses and re-derived the ligand coordinates again.
+template <int VARIANT, bool STATS, bool TILED>
 __global__ void __launch_bounds__(TPB, kBlocksPerSM)
-direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int tile_groups, int n_split,
+direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int tile_groups, int n_split, int near_cap,
                    unsigned long long *__restrict__ work, double *__restrict__ out, uint8_t *__restrict__ flags) {
     // Persistent blocks (2 per SM), one launch per receptor tile [b0, b0 + nb) of groups.  A work unit is
     // (64 consecutive poses, chunk split y): the warp that draws it sums the ligand chunks c = y, y + n_split, ...
@@ -202,7 +207,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
     float *s_c = (float *)(s_tab + 16);                       // 3 * LJ * PPB : field-major, then chunk atom, then pose
     float *s_l = s_c + 3 * LJ * PPB + (threadIdx.x >> 5) * (NF * LIST_CAP);
     uint8_t *s_elt = (uint8_t *)(s_c + 3 * LJ * PPB + (TPB / 32) * (NF * LIST_CAP));      // tile_atoms + kBlob
-    uint8_t *s_near = s_elt + tile_atoms + kBlob + (threadIdx.x >> 5) * NEAR_CAP;
+    uint16_t *s_near = (uint16_t *)(s_elt + ((tile_atoms + kBlob + 15) & ~15)) + (threadIdx.x >> 5) * near_cap;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -211,11 +216,13 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
     // ---- stage the receptor tile once per block ----
     for (int j = tid; j < a.n_fast; j += TPB) s_lparam[j] = a.lparam[j];
     if (tid < kEltTab) s_tab[tid] = make_float2(a.tab_A[tid], a.tab_B[tid]);
-    for (int k = tid; k < nb * kBlob; k += TPB) {
-        s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
-        s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
+    if (TILED) {
+        for (int k = tid; k < nb * kBlob; k += TPB) {
+            s_atom[k] = __ldg(a.xyzq + (size_t)b0 * kBlob + k);
+            s_elt[k] = __ldg(a.gelt + (size_t)b0 * kBlob + k);
+        }
+        for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
     }
-    for (int k = tid; k < nb * 2; k += TPB) s_box[k] = __ldg(a.blob_box + (size_t)b0 * 2 + k);
     if (tid < kBlob) {
         s_atom[tile_atoms + tid] = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
         s_elt[tile_atoms + tid] = 0;
@@ -319,22 +326,47 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 //      lane g tests group box g; the near group ids are compacted into s_near ----
                 int ng = 0;
                 __syncwarp();        // every lane is done reading the previous atom's s_near
+                if (TILED) {
 #pragma unroll
-                for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
-                    const int g = r * 32 + lane;
-                    bool near = g < nb;
-                    if (VARIANT == MMO_VARIANT_SHIFTED && near) {
-                        const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
+                    for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
+                        const int g = r * 32 + lane;
+                        bool near = g < nb;
+                        if (VARIANT == MMO_VARIANT_SHIFTED && near) {
+                            const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
+                            const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
+                            const float gy = fmaxf(0.f, fmaxf(blo.y - cy, cy - bhi.y));
+                            const float gz = fmaxf(0.f, fmaxf(blo.z - cz, cz - bhi.z));
+                            near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+                        }
+                        const unsigned gm = __ballot_sync(0xffffffffu, near);
+                        if (near) s_near[ng + __popc(gm & lt_mask)] = (uint16_t)g;
+                        ng += __popc(gm);
+                    }
+                    if (lane < 4) s_near[ng + lane] = (uint16_t)tile_groups;        // pad with the dummy group
+                } else {
+                    auto box_near = [&](const float4 blo, const float4 bhi) {
                         const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
                         const float gy = fmaxf(0.f, fmaxf(blo.y - cy, cy - bhi.y));
                         const float gz = fmaxf(0.f, fmaxf(blo.z - cz, cz - bhi.z));
-                        near = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+                        return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) < reach2;
+                    };
+                    for (int s0 = 0; s0 < a.n_sup; s0 += 32) {
+                        const int sidx = s0 + lane;
+                        bool sn = sidx < a.n_sup;
+                        if (VARIANT == MMO_VARIANT_SHIFTED && sn) sn = box_near(__ldg(a.sup_box + 2 * sidx), __ldg(a.sup_box + 2 * sidx + 1));
+                        unsigned sm = __ballot_sync(0xffffffffu, sn);
+                        while (sm) {
+                            const int g = (s0 + __ffs(sm) - 1) * 32 + lane;
+                            sm &= sm - 1u;
+                            bool near = g < nb;
+                            if (VARIANT == MMO_VARIANT_SHIFTED && near) near = box_near(__ldg(a.blob_box + 2 * g), __ldg(a.blob_box + 2 * g + 1));
+                            const unsigned gm = __ballot_sync(0xffffffffu, near);
+                            if (near) s_near[ng + __popc(gm & lt_mask)] = (uint16_t)g;
+                            ng += __popc(gm);
+                        }
                     }
-                    const unsigned gm = __ballot_sync(0xffffffffu, near);
-                    if (near) s_near[ng + __popc(gm & lt_mask)] = (uint8_t)g;
-                    ng += __popc(gm);
+                    if (lane < 4) s_near[ng + lane] = (uint16_t)nb;                  // the far-away group behind the last one
                 }
-                if (lane < 4) s_near[ng + lane] = (uint8_t)tile_groups;        // pad with the dummy group
                 __syncwarp();
                 const float qjs = lp.z, Ajs = lp.x, nBjs = -lp.y;
                 // ---- level 2: the atoms of four near groups per step, two per lane (independent loads and
@@ -346,8 +378,8 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                     if (more) {
                         const int atomA = s_near[i + (lane >> 4)] * kBlob + (lane & 15);
                         const int atomB = s_near[i + 2 + (lane >> 4)] * kBlob + (lane & 15);
-                        const float4 pa = s_atom[atomA], pb = s_atom[atomB];
-                        const int ea = s_elt[atomA], eb = s_elt[atomB];
+                        const float4 pa = TILED ? s_atom[atomA] : __ldg(a.xyzq + atomA), pb = TILED ? s_atom[atomB] : __ldg(a.xyzq + atomB);
+                        const int ea = TILED ? (int)s_elt[atomA] : (int)__ldg(a.gelt + atomA), eb = TILED ? (int)s_elt[atomB] : (int)__ldg(a.gelt + atomB);
                         const float Xa = pa.x - cx, Ya = pa.y - cy, Za = pa.z - cz;
                         const float Xb = pb.x - cx, Yb = pb.y - cy, Zb = pb.z - cz;
                         const float Sa = fmaf(Za, Za, fmaf(Ya, Ya, Xa * Xa)), Sb = fmaf(Zb, Zb, fmaf(Yb, Yb, Xb * Xb));
@@ -990,10 +1022,14 @@ static int set_fast_smem(size_t smem) {
     static int done_epoch = -1;
     if (done_epoch != rt().epoch) { done = 0; done_epoch = rt().epoch; }      // function attributes are per context
     if (smem <= done) return MMO_OK;
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = smem;
     return MMO_OK;
 }
@@ -1122,7 +1158,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     FastArgs fa;
     fa.n_blobs = rec->n_blobs;
     for (int e = 0; e < kEltTab; e++) vdw_factors(e, &fa.tab_A[e], &fa.tab_B[e]);
-    fa.xyzq = rec->xyzq.p; fa.gelt = rec->gelt.p; fa.blob_box = rec->blob_box.p;
+    fa.xyzq = rec->xyzq.p; fa.gelt = rec->gelt.p; fa.blob_box = rec->blob_box.p; fa.sup_box = rec->sup_box.p; fa.n_sup = rec->n_sup;
     for (int d = 0; d < 3; d++) fa.origin[d] = rec->origin[d];
     fa.L = lig->n;
     fa.n_fast = lig->n_fast;
@@ -1162,12 +1198,17 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
         }
         return MMO_OK;
     }
-    // receptor tile: everything when it fits (<= 128 groups = 2048 atoms); larger receptors take one launch per tile
-    const int tile_blobs = std::max(1, std::min(rec->n_blobs, MAX_TILE_GROUPS));
+    // receptor: one shared-memory tile when it fits (<= 128 groups = 2048 atoms); larger receptors stay in global memory
+    // and are read through L1 (untiled kernel): one launch either way
+    const bool tiled = rec->n_blobs <= MAX_TILE_GROUPS;
+    const int tile_blobs = tiled ? std::max(1, rec->n_blobs) : 0;
+    MMO_REQUIRE(rec->n_blobs < 65535, "receptor too large for the direct kernel (%d atoms)", rec->n);
+    const int near_cap = ((tiled ? MAX_TILE_GROUPS : rec->n_blobs) + 8 + 7) & ~7;
     const size_t smem = ((size_t)(tile_blobs + 1) * kBlob + (size_t)tile_blobs * 2 + (size_t)lig->n_fast) * sizeof(float4) +
                         16 * sizeof(float2) + (size_t)3 * LJ * PPB * sizeof(float) +
-                        (size_t)(TPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob +
-                        (size_t)(TPB / 32) * NEAR_CAP + 16;
+                        (size_t)(TPB / 32) * NF * LIST_CAP * sizeof(float) + (size_t)(tile_blobs + 1) * kBlob + 16 +
+                        (size_t)(TPB / 32) * near_cap * sizeof(uint16_t) + 16;
+    MMO_REQUIRE(smem <= 227 * 1024, "receptor too large for the direct kernel (%d atoms)", rec->n);
     // work units = (64 poses, chunk split): at least ~20 per resident warp, so that the dynamic hand-out
     // balances the warps to a few percent; persistent grid of one block per SM (fewer for small batches)
     const int n_chunks = lig->n_fast / LJ;
@@ -1176,7 +1217,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     const int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (20 * resident_warps + n_groups - 1) / n_groups));
     const int64_t n_units = n_groups * n_split;
     const unsigned blocks = (unsigned)std::min<int64_t>((int64_t)kBlocksPerSM * R.sm_count, (n_units + TPB / 32 - 1) / (TPB / 32));
-    const int n_tiles = (rec->n_blobs + tile_blobs - 1) / tile_blobs;
+    const int n_tiles = 1;
     const int n_parts = n_tiles * n_split;
     DevBuf<double> part;
     if (n_parts > 1) MMO_TRY(part.alloc((size_t)n_parts * (size_t)n_poses));
@@ -1184,22 +1225,30 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     DevBuf<uint8_t> flags;
     MMO_TRY(flags.alloc((size_t)n_tiles * (size_t)n_chunks * (size_t)n_poses));
     if (!g_work.p) MMO_TRY(g_work.alloc(64));
-    MMO_REQUIRE(n_tiles <= 64, "receptor too large for the direct kernel (%d tiles of %d atoms)", n_tiles, MAX_TILE_GROUPS * kBlob);
     const bool shifted = variant == MMO_VARIANT_SHIFTED;
     if (rec->n > 0) {
         MMO_TRY(set_fast_smem(smem));
         MMO_CUDA(cudaMemsetAsync(g_work.p, 0, 64 * sizeof(unsigned long long), R.stream));
         {
         KernelScope ks(K_DIRECT_FP32);
-        for (int t = 0; t < n_tiles; t++) {
-            const int b0 = t * tile_blobs, nb = std::min(tile_blobs, rec->n_blobs - b0);
-            double *o = d_part + (size_t)t * n_split * (size_t)n_poses;
-            uint8_t *f = flags.p + (size_t)t * n_chunks * (size_t)n_poses;
-            unsigned long long *w = g_work.p + t;
-            if (shifted && collect_stats) direct_fp32_kernel<MMO_VARIANT_SHIFTED, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
-            else if (shifted) direct_fp32_kernel<MMO_VARIANT_SHIFTED, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
-            else if (collect_stats) direct_fp32_kernel<MMO_VARIANT_GLOBAL, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
-            else direct_fp32_kernel<MMO_VARIANT_GLOBAL, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, w, o, f);
+        {
+            const int b0 = 0, nb = rec->n_blobs;
+            double *o = d_part;
+            uint8_t *f = flags.p;
+            unsigned long long *w = g_work.p;
+#define MMO_LAUNCH_K1(V, S_, T_) direct_fp32_kernel<V, S_, T_><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, near_cap, w, o, f)
+            if (tiled) {
+                if (shifted && collect_stats) MMO_LAUNCH_K1(MMO_VARIANT_SHIFTED, true, true);
+                else if (shifted) MMO_LAUNCH_K1(MMO_VARIANT_SHIFTED, false, true);
+                else if (collect_stats) MMO_LAUNCH_K1(MMO_VARIANT_GLOBAL, true, true);
+                else MMO_LAUNCH_K1(MMO_VARIANT_GLOBAL, false, true);
+            } else {
+                if (shifted && collect_stats) MMO_LAUNCH_K1(MMO_VARIANT_SHIFTED, true, false);
+                else if (shifted) MMO_LAUNCH_K1(MMO_VARIANT_SHIFTED, false, false);
+                else if (collect_stats) MMO_LAUNCH_K1(MMO_VARIANT_GLOBAL, true, false);
+                else MMO_LAUNCH_K1(MMO_VARIANT_GLOBAL, false, false);
+            }
+#undef MMO_LAUNCH_K1
             MMO_LAUNCH_CHECK();
         }
         }

@@ -295,3 +295,27 @@ def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
     lps = C.c_double()
     assert L.mmo_measure_l2_gather((C.c_int32 * 3)(81, 81, 81), C.c_int32(22), C.byref(lps)) == 0
     assert lps.value > 1e9
+
+
+def test_scan_against_a_receptor_larger_than_one_tile(gpu, orc, c2):
+    """a ROI receptor of more than 2048 atoms (a protonated pocket): the pose kernel reads the groups through L1 in one
+    launch (untiled variant) instead of one launch per shared-memory tile; the fp64 scan (fp32 sweep + strict re-scoring)
+    must still be the oracle's scan, and the fp32 scores must honour the contract"""
+    from mmo_b200 import workloads
+    rec_m = workloads.synthetic_receptor(2900, "sphere", 22.0, seed=77, origin=tuple(c2["roi"][:3]))
+    # carve a pocket so that some poses do not clash
+    d = np.sqrt((rec_m.xs - c2["roi"][0]) ** 2 + (rec_m.ys - c2["roi"][1]) ** 2 + (rec_m.zs - c2["roi"][2]) ** 2)
+    keep = d > 7.0
+    from mmo_b200 import pqrs
+    rec_m = pqrs.Mol("pocket", rec_m.xs[keep], rec_m.ys[keep], rec_m.zs[keep], rec_m.q[keep], rec_m.r[keep], rec_m.anum[keep])
+    assert rec_m.n > 2048 + 200
+    rec = gpu.Receptor.from_mol(rec_m)
+    lig = gpu.Ligand.from_mol(c2["lig"], centered=True)
+    rot = gpu.SO3.rotations(24)
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 2.5)
+    want = orc.scan(rec_m, c2["lig"], lig.xs, lig.ys, lig.zs, roi, 1.0, rot, 20)
+    got = gpu.Lds.exhaustive_rigid_ligand_docking(20, roi, 1.0, rot, lig, rec=rec, prec=gpu.PREC_FP64)
+    assert got["best_frame"] == want["best_frame"] and np.array_equal(got["top_frames"], want["top_frames"])
+    assert np.array_equal(got["top_scores"], want["top_scores"])
+    g32 = gpu.Lds.exhaustive_rigid_ligand_docking(20, roi, 1.0, rot, lig, rec=rec, prec=gpu.PREC_FP32)
+    assert tol_ok(g32["top_scores"], want["top_scores"]).all()
