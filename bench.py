@@ -459,7 +459,7 @@ def main():
     e2e_pass(1, args.warmup, 0)
     e2e_s, e2e_poses = e2e_pass(1, e2e_steps, args.warmup)            # headline: the rotation bytes move on every call
     e2e_s0, e2e_poses0 = e2e_pass(0, e2e_steps, args.warmup)          # rotation set left resident (memcmp'ed, not moved)
-    ck(L.mmo_scan_set_rot_cache(0))
+    ck(L.mmo_scan_set_rot_cache(1))
     h2d = N_ROT * 72 + pps * 8 + 16          # rotations + the slab's lattice points + the threshold
     h2d_resident = pps * 8 + 16
     d2h = TOPK * 16 + 64
@@ -510,11 +510,12 @@ def main():
             "gpu_launches": launches,
             "e2e": {"value": e2e_poses / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "warmup": args.warmup,
-                    "api": "mmo_scan() one-shot per step, host buffers (rotations in pinned memory, copied on every call: "
-                           "mmo_scan_set_rot_cache(1)), running top-k merged on the host, NCCL merge at the end",
+                    "api": "mmo_scan() one-shot per step, host buffers (rotations in pinned memory, copied to the device on every call "
+                           "and compared there with the resident set: the library default, mmo_scan_set_rot_cache(1)), running top-k "
+                           "merged on the host, NCCL merge at the end",
                     "rotations_left_resident": {"value": e2e_poses0 / e2e_s0, "h2d_bytes_per_step": h2d_resident,
-                                                "note": "library default: a call that hands over the same rotation bytes again (one memcmp) "
-                                                        "skips the upload, as lds builds the set once per run"},
+                                                "note": "mmo_scan_set_rot_cache(0): the same rotation bytes handed over again are recognised by "
+                                                        "one memcmp on the host and not uploaded; slower here than moving them"},
                     "cold_first_call": {"ms": cold_ms, "poses": cold_poses,
                                         "note": "first mmo_scan of the process: device allocations, rotation upload + k-d visiting order, module load"}},
             "roofline": {"bound": "fp32", "kernel": "direct_fp32_kernel", "achieved": achieved, "peak": fp32_peak.value,

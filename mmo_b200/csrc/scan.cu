@@ -158,15 +158,37 @@ static void rotation_visit_order(int n_rot, const double *rot9, std::vector<int3
 // (same count, same bytes: one memcmp against the host copy) skips the 72 n_rot bytes upload and the k-d sort.
 // leaked on purpose: must not run a destructor after the CUDA context / the allocator are gone
 static std::shared_ptr<RotSet> &g_rotset = *new std::shared_ptr<RotSet>();
-static int g_rot_cache_mode = 0;      // mmo_scan_set_rot_cache: 1 = move the rotation bytes on every call
+static int g_rot_cache_mode = 1;      // mmo_scan_set_rot_cache: 1 = upload + compare on the device (default), 0 = memcmp on the host
 void scan_drop_caches() { g_rotset.reset(); }
+// device-side comparison of a freshly uploaded rotation set with the resident one (mode 1: the bytes move on every call,
+// the k-d visiting order is reused when they turn out to be the same set)
+__global__ void __launch_bounds__(256)
+rot_compare_kernel(const unsigned long long *__restrict__ a, const unsigned long long *__restrict__ b, size_t n, int *__restrict__ differ) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool d = false;
+    for (; i < n; i += stride) d |= a[i] != b[i];
+    if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) atomicOr(differ, 1);
+}
+
 static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out) {
-    if (g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch &&
-        memcmp(g_rotset->host.data(), rot9, (size_t)n_rot * 9 * sizeof(double)) == 0) {
-        if (g_rot_cache_mode == 1) {
-            MMO_CUDA(cudaMemcpyAsync(g_rotset->rot.p, rot9, (size_t)n_rot * 9 * sizeof(double), cudaMemcpyHostToDevice, rt().stream));
-            MMO_CUDA(cudaStreamSynchronize(rt().stream));
-        }
+    if (g_rot_cache_mode == 1 && g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch) {
+        Runtime &R = rt();
+        const size_t nw = (size_t)n_rot * 9;
+        DevBuf<double> fresh;
+        DevBuf<int> flag;
+        MMO_TRY(fresh.alloc(nw));
+        MMO_TRY(flag.alloc(1));
+        MMO_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), R.stream));
+        MMO_CUDA(cudaMemcpyAsync(fresh.p, rot9, nw * sizeof(double), cudaMemcpyHostToDevice, R.stream));
+        rot_compare_kernel<<<R.sm_count * 4, 256, 0, R.stream>>>((const unsigned long long *)fresh.p, (const unsigned long long *)g_rotset->rot.p, nw, flag.p);
+        MMO_LAUNCH_CHECK();
+        int differ = 0;
+        MMO_CUDA(cudaMemcpyAsync(&differ, flag.p, sizeof(int), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));
+        if (!differ) { out = g_rotset; return MMO_OK; }
+    } else if (g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch &&
+               memcmp(g_rotset->host.data(), rot9, (size_t)n_rot * 9 * sizeof(double)) == 0) {
         out = g_rotset;
         return MMO_OK;
     }

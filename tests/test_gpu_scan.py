@@ -290,7 +290,10 @@ def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
     a = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
     assert L.mmo_scan_set_rot_cache(1) == 0
     b = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
-    assert L.mmo_scan_set_rot_cache(0) == 0 and L.mmo_scan_set_rot_cache(7) != 0
+    assert L.mmo_scan_set_rot_cache(7) != 0 and L.mmo_scan_set_rot_cache(0) == 0
+    c = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
+    assert L.mmo_scan_set_rot_cache(1) == 0
+    assert np.array_equal(a["top_scores"], c["top_scores"])
     assert np.array_equal(a["top_scores"], b["top_scores"]) and np.array_equal(a["top_frames"], b["top_frames"])
     lps = C.c_double()
     assert L.mmo_measure_l2_gather((C.c_int32 * 3)(81, 81, 81), C.c_int32(22), C.byref(lps)) == 0
