@@ -295,6 +295,16 @@ def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
     assert L.mmo_scan_set_rot_cache(1) == 0
     assert np.array_equal(a["top_scores"], c["top_scores"])
     assert np.array_equal(a["top_scores"], b["top_scores"]) and np.array_equal(a["top_frames"], b["top_frames"])
+    # another set of the same size: the device-side comparison must notice and rebuild the visiting order
+    rot2 = np.ascontiguousarray(rot[::-1])
+    d1 = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot2, lig, rec=rec)
+    assert L.mmo_scan_set_rot_cache(0) == 0
+    d0 = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot2, lig, rec=rec)
+    assert L.mmo_scan_set_rot_cache(1) == 0
+    assert np.array_equal(d1["top_scores"], d0["top_scores"]) and np.array_equal(d1["top_frames"], d0["top_frames"])
+    n_rot = len(rot)
+    assert np.array_equal(np.sort(d1["top_scores"]), np.sort(a["top_scores"]))          # the same poses under other frame ids
+    assert sorted((f // n_rot, n_rot - 1 - f % n_rot) for f in d1["top_frames"]) == sorted((f // n_rot, f % n_rot) for f in a["top_frames"])
     lps = C.c_double()
     assert L.mmo_measure_l2_gather((C.c_int32 * 3)(81, 81, 81), C.c_int32(22), C.byref(lps)) == 0
     assert lps.value > 1e9
