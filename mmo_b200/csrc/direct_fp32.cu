@@ -453,7 +453,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
 // ~2.2 A), and direct_items_kernel runs the same cull -> list -> packed pair loop on 64 items per warp.  Since
 // the ligand atom now differs from lane to lane, the list carries the receptor factors only and the lanes keep
 // three sums each,  E = A_j sum(w A_i s^6) - B_j sum(w B_i s^3) + q_j sum(w q_i / r):  15 packed ops per two pairs.
-constexpr float kItemCell = 2.0f;
+constexpr float kItemCell = 0.5f;
 constexpr int kItemTPB = 256;
 #ifndef MMO_ITEM_SUM_EVERY
 #define MMO_ITEM_SUM_EVERY 8
@@ -550,6 +550,16 @@ __device__ __forceinline__ void run_list_items(const float *s_l, int n, int n4, 
     }
 }
 
+// 10 bits -> every third bit (Morton / Z-order interleave)
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
 // position (double, then fp32 relative to the receptor origin) and lattice cell of every item; thread = item, so that
 // the 24 bytes written per item (and the coordinates read, for explicit conformers) are coalesced
 __global__ void __launch_bounds__(256)
@@ -560,7 +570,7 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
                     unsigned long long *__restrict__ n_far) {
     const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_items = n_poses * n_fast;
-    const uint32_t far_key = (uint32_t)nx * ny * nz;
+    const uint32_t far_key = 1u << 30;        // beyond every Morton code of 3 x 10 bits
     uint32_t key = far_key;
     if (it < n_items) {
         const int64_t p = it / n_fast;
@@ -579,7 +589,7 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
             v.x = (float)(x - ox); v.y = (float)(y - oy); v.z = (float)(z - oz);
             const float fx = (v.x - cell_lo_x) * cell_inv, fy = (v.y - cell_lo_y) * cell_inv, fz = (v.z - cell_lo_z) * cell_inv;
             if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)nx && fy < (float)ny && fz < (float)nz)
-                key = (uint32_t)((int)fx + nx * ((int)fy + ny * (int)fz));
+                key = spread3((uint32_t)fx) | (spread3((uint32_t)fy) << 1) | (spread3((uint32_t)fz) << 2);     // Z-order
         }
         pos[it] = v;
         keys[it] = key;
@@ -1062,20 +1072,20 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     // lattice of cells over everything within 12 A (+ one cell) of the receptor's bounding box
     float lo[3], hi[3];
     for (int d = 0; d < 3; d++) { lo[d] = (float)(rec->bb_lo[d] - rec->origin[d]) - 12.5f; hi[d] = (float)(rec->bb_hi[d] - rec->origin[d]) + 12.5f; }
-    // 1 A cells once the list is large enough to fill them (a warp's 64 items then sit within rho <= 0.87 A of their
-    // centre: ~18 % fewer pairs to evaluate than with 2 A cells), MMO_ITEM_CELL overrides (tuning)
-    float cell = n_items >= ((size_t)1 << 21) ? 1.0f : kItemCell;
+    // 0.5 A cells in Z-order (Morton codes of 3 x 10 bits): 64 consecutive items of the sorted list are spatial
+    // neighbours at every density -- a dense screen fills single cells (rho <= 0.43 A), a short list spans a compact block
+    // of cells -- so there is nothing to tune to the list size.  The cell grows only if the lattice would need more than
+    // 1024 cells per axis.  MMO_ITEM_CELL overrides (tuning).
+    float cell = kItemCell;
     if (const char *e = getenv("MMO_ITEM_CELL")) { const float v = (float)atof(e); if (v >= 0.25f && v <= 8.0f) cell = v; }
     int nd[3];
     for (;;) {
-        double tot = 1.0;
-        for (int d = 0; d < 3; d++) { nd[d] = std::max(1, (int)ceilf((hi[d] - lo[d]) / cell)); tot *= nd[d]; }
-        if (tot < (double)(1u << 26)) break;
-        cell *= 1.5f;
+        bool ok = true;
+        for (int d = 0; d < 3; d++) { nd[d] = std::max(1, (int)ceilf((hi[d] - lo[d]) / cell)); ok = ok && nd[d] <= 1024; }
+        if (ok) break;
+        cell *= 1.25f;
     }
-    const unsigned n_cells = (unsigned)nd[0] * nd[1] * nd[2];
-    int end_bit = 1;
-    while ((1ull << end_bit) <= n_cells) end_bit++;          // keys 0 .. n_cells (n_cells = beyond the lattice)
+    const int end_bit = 31;          // keys 0 .. 2^30 (2^30 = beyond the lattice)
 
     // scratch arena (grow-only, reused by every call: cudaMalloc/cudaFree of ~45 B per item would cost more than the kernels)
     size_t temp_bytes = 0;
