@@ -232,6 +232,9 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
     const unsigned long long n_groups = (unsigned long long)((n_poses + 32 * PPT - 1) / (32 * PPT));
     const unsigned long long n_units = n_groups * (unsigned long long)n_split;
     unsigned long long n_eval = 0, n_in_tot = 0;
+#ifdef MMO_EXPERIMENT_NOCULL
+    bool exp_have_list = false;
+#endif
 
     for (;;) {
         unsigned long long u = 0;
@@ -322,6 +325,16 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                     m2y[h] = expand ? -2.0f * py[h] : -m2y[h];
                     m2z[h] = expand ? -2.0f * pz[h] : -m2z[h];
                 }
+#ifdef MMO_EXPERIMENT_NOCULL
+                // ceiling experiment (WRONG energies): after a warp's first list, every atom re-uses the stale list, 2 x 224
+                // entries, i.e. the pair work of an average C2 atom without any culling -- what perfect overlap could reach
+                if (exp_have_list) {
+                    run_list<VARIANT, true, STATS>(s_l, 224, 224, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
+                    run_list<VARIANT, true, STATS>(s_l, 224, 224, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
+                    continue;
+                }
+                exp_have_list = true;
+#endif
                 // ---- level 1: which groups of 16 receptor atoms can be within 12 A of these positions?
                 //      lane g tests group box g; the near group ids are compacted into s_near ----
                 int ng = 0;
