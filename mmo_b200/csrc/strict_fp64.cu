@@ -13,6 +13,7 @@
 #include "pose.cuh"
 #include "strict_dev.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace mmo {
 
@@ -111,6 +112,89 @@ __global__ void strict_direct_kernel(int P, const double *__restrict__ px, const
     out[p] = (kElecWeight * sum_elec) + sum_vdW;
 }
 
+// The same sum for a moderate number of poses (single evaluations of the `ene_inter` closure, the re-scoring stage of the
+// fp64 scan): block = pose.  Tile by tile of 64 receptor atoms, thread t counts the ligand atoms within the cut-off of
+// receptor atom i0 + t, a block-wide prefix sum gives every thread its place in the reference's (i outer, j inner) order,
+// the terms are computed in parallel and stored there, and thread 0 adds them up one by one: the same doubles in the same
+// order as the loop above, 0.1 ms per pose instead of the 9.6 ms one thread needs for 1837 x 48 pairs.
+constexpr int kDirTile = 64;
+template <int VARIANT>
+__global__ void __launch_bounds__(kDirTile)
+strict_direct_block_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
+                           const double *__restrict__ pz, const double *__restrict__ pq,
+                           const int32_t *__restrict__ pelt,
+                           int L, const double *__restrict__ lx, const double *__restrict__ ly,
+                           const double *__restrict__ lz, const double *__restrict__ lq,
+                           const int32_t *__restrict__ lelt,
+                           PoseSrc src, int64_t n_poses, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    double *sx = sm, *sy = sm + L, *sz = sm + 2 * L, *sq = sm + 3 * L;
+    int32_t *se = (int32_t *)(sq + L);                                   // L ints
+    int *s_cnt = (int *)(se + L);                                        // kDirTile + 1
+    double2 *terms = (double2 *)(sm + ((4 * L * 2 + L + kDirTile + 2 + 3) / 4) * 2);     // 16-byte aligned, behind the ints
+    const int tid = threadIdx.x;
+    const int64_t p = blockIdx.x;
+    if (src.kind == 1) {
+        for (int j = tid; j < L; j += kDirTile) { sx[j] = src.xs[p * L + j]; sy[j] = src.ys[p * L + j]; sz[j] = src.zs[p * L + j]; }
+    } else {
+        PoseRT Pp;
+        load_pose_rt(src, p, Pp);
+        for (int j = tid; j < L; j += kDirTile) pose_atom_rt(Pp, lx[j], ly[j], lz[j], sx[j], sy[j], sz[j]);
+    }
+    for (int j = tid; j < L; j += kDirTile) { sq[j] = lq[j]; se[j] = lelt[j]; }
+    __syncthreads();
+    double sum_elec = 0.0, sum_vdW = 0.0;            // thread 0 only
+    for (int i0 = 0; i0 < P; i0 += kDirTile) {
+        const int i = i0 + tid;
+        double xi = 0.0, yi = 0.0, zi = 0.0, q_i = 0.0;
+        int ei = 0, cnt = 0;
+        if (i < P) {
+            xi = __ldg(px + i); yi = __ldg(py + i); zi = __ldg(pz + i); q_i = __ldg(pq + i);
+            ei = __ldg(pelt + i) * kEltTab;
+            if (VARIANT == MMO_VARIANT_SHIFTED) {
+                for (int j = 0; j < L; j++) cnt += d_dist2(xi, yi, zi, sx[j], sy[j], sz[j]) < 144.0 ? 1 : 0;
+            } else {
+                cnt = L;
+            }
+        }
+        // exclusive prefix sum of the 64 counts (two warps)
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+        if ((tid & 31) == 31) s_cnt[tid >> 5] = incl;
+        __syncthreads();
+        const int base = (tid >> 5) ? s_cnt[0] : 0;
+        const int total = s_cnt[0] + s_cnt[1];
+        int pos = base + incl - cnt;
+        if (i < P) {
+            for (int j = 0; j < L; j++) {
+                const double r2 = d_dist2(xi, yi, zi, sx[j], sy[j], sz[j]);
+                if (VARIANT == MMO_VARIANT_SHIFTED) {
+                    if (r2 < 144.0) {
+                        const double r = d_nzd(sqrt(r2));
+                        const double w = d_shift(r);
+                        const int t = ei + se[j];
+                        const Divisor by_r = make_divisor(r);
+                        const double p6 = d_pow6(div_by(c_xij[t], by_r));
+                        terms[pos++] = make_double2(w * div_by(q_i * sq[j], by_r), w * (c_dij[t] * ((-2.0 * p6) + (p6 * p6))));
+                    }
+                } else {
+                    const double r = d_nzd(sqrt(r2));
+                    const int t = ei + se[j];
+                    const Divisor by_r = make_divisor(r);
+                    const double p6 = d_pow6(div_by(c_xij[t], by_r));
+                    terms[pos++] = make_double2(div_by(q_i * sq[j], by_r), c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int k = 0; k < total; k++) { const double2 u = terms[k]; sum_elec = sum_elec + u.x; sum_vdW = sum_vdW + u.y; }
+        __syncthreads();
+    }
+    if (tid == 0) out[p] = (kElecWeight * sum_elec) + sum_vdW;
+}
+
 // ---- components, ligand outer / receptor inner in index order (mol.ml:932-956) --------------------
 __global__ void strict_components_kernel(int P, const double *__restrict__ px, const double *__restrict__ py,
                                          const double *__restrict__ pz, const double *__restrict__ pq,
@@ -179,6 +263,35 @@ __global__ void strict_intra_kernel(int L, int n_pairs, const int32_t *__restric
         sum_vdW = sum_vdW + c_dij[t] * ((-2.0 * p6) + (p6 * p6));
     }
     out[p] = (kElecWeight * sum_elec) + sum_vdW;
+}
+
+// The same energy for a FEW conformers (the literal `ene_intra : Mol.t -> float` closure, one conformer per call): block =
+// conformer, the pair terms are computed by all threads in parallel, then one thread adds them up in the reference's
+// (i<j) order -- the same doubles as the loop above, 30 us instead of 380 us for one 48-atom conformer.
+__global__ void __launch_bounds__(128)
+strict_intra_block_kernel(int L, int n_pairs, const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
+                          const double *__restrict__ lq, const int32_t *__restrict__ lelt, const double *__restrict__ xs,
+                          const double *__restrict__ ys, const double *__restrict__ zs, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    double *sx = sm, *sy = sm + L, *sz = sm + 2 * L;
+    double2 *terms = (double2 *)(sm + 3 * L + ((3 * L) & 1));
+    const int64_t p = blockIdx.x;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) { sx[j] = xs[p * L + j]; sy[j] = ys[p * L + j]; sz[j] = zs[p * L + j]; }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_pairs; k += blockDim.x) {
+        const int i = __ldg(pair_i + k), j = __ldg(pair_j + k);
+        const double r = d_nzd(sqrt(d_dist2(sx[i], sy[i], sz[i], sx[j], sy[j], sz[j])));
+        const int t = __ldg(lelt + i) * kEltTab + __ldg(lelt + j);
+        const Divisor by_r = make_divisor(r);
+        const double p6 = d_pow6(div_by(c_xij[t], by_r));
+        terms[k] = make_double2(div_by(__ldg(lq + i) * __ldg(lq + j), by_r), c_dij[t] * ((-2.0 * p6) + (p6 * p6)));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum_elec = 0.0, sum_vdW = 0.0;
+        for (int k = 0; k < n_pairs; k++) { const double2 u = terms[k]; sum_elec = sum_elec + u.x; sum_vdW = sum_vdW + u.y; }
+        out[p] = (kElecWeight * sum_elec) + sum_vdW;
+    }
 }
 
 // ---- grid build (mol.ml:964-989 per voxel, lds.ml:452-469 clamp + f32 store) ----------------------
@@ -377,6 +490,18 @@ int launch_direct_fp64(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     if (n_poses == 0) return MMO_OK;
     size_t smem;
     int L = lig->n;
+    {   // up to a few ten thousand poses: block per pose (0.1 ms each, spread over the GPU) beats thread per pose (9.6 ms flat)
+        const size_t bsmem = ((size_t)(4 * L * 2 + L + kDirTile + 2 + 3) / 4) * 2 * sizeof(double) + (size_t)kDirTile * L * sizeof(double2);
+        if (n_poses < 32768 && bsmem <= 200 * 1024 && rec->n > 0) {
+            auto kb = (variant == MMO_VARIANT_SHIFTED) ? strict_direct_block_kernel<MMO_VARIANT_SHIFTED> : strict_direct_block_kernel<MMO_VARIANT_GLOBAL>;
+            MMO_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+            KernelScope ks(K_DIRECT_FP64);
+            kb<<<(unsigned)n_poses, kDirTile, bsmem, rt().stream>>>(rec->n, rec->x.p, rec->y.p, rec->z.p, rec->q.p, rec->elt.p, L, lig->x.p,
+                                                                     lig->y.p, lig->z.p, lig->q.p, lig->elt.p, src, n_poses, d_out);
+            MMO_LAUNCH_CHECK();
+            return MMO_OK;
+        }
+    }
     int threads = pick_threads(L, (size_t)L * (sizeof(double) + sizeof(int32_t)) + 16, &smem);
     MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the fp64 direct kernel", L);
     int64_t blocks = (n_poses + threads - 1) / threads;
@@ -414,6 +539,17 @@ int launch_intra_fp64(const mmo_ligand *lig, int64_t n_confs, const double *d_xs
     if (n_confs == 0) return MMO_OK;
     size_t smem;
     int L = lig->n;
+    {   // a few conformers: block per conformer (terms in parallel, ordered sum by one thread)
+        const size_t bsmem = ((size_t)3 * L + 1) * sizeof(double) + (size_t)std::max(lig->n_pairs, 1) * sizeof(double2);
+        if (n_confs <= 2LL * rt().sm_count && bsmem <= 200 * 1024) {
+            if (bsmem > 48 * 1024) MMO_CUDA(cudaFuncSetAttribute(strict_intra_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+            KernelScope ks(K_INTRA);
+            strict_intra_block_kernel<<<(unsigned)n_confs, 128, bsmem, rt().stream>>>(L, lig->n_pairs, lig->pair_i.p, lig->pair_j.p, lig->q.p,
+                                                                                   lig->elt.p, d_xs, d_ys, d_zs, d_out);
+            MMO_LAUNCH_CHECK();
+            return MMO_OK;
+        }
+    }
     int threads = pick_threads(L, 0, &smem);
     MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the intra kernel", L);
     int64_t blocks = (n_confs + threads - 1) / threads;

@@ -340,3 +340,27 @@ print("reinit ok")
     script.write_text(code)
     r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "reinit ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_strict_kernels_block_per_pose_and_thread_per_pose_agree(gpu, orc, c2):
+    """MMO_PREC_FP64 has two kernels behind it: block per pose (up to 32 k poses: single evaluations, the re-scoring stage
+    of the fp64 scan) and thread per pose (beyond).  Same doubles in the same order: both bit-identical to the oracle,
+    hence to each other; likewise the two intra-ligand kernels (block per conformer for a few, thread per conformer)."""
+    rec_m = workloads.carve(c2["rec"], c2["roi"][:3], 9.0)
+    assert 100 < rec_m.n < 400
+    rec = gpu.Receptor.from_mol(rec_m)
+    m = c2["lig"]
+    lig = gpu.Ligand.from_mol(m, centered=True)
+    n = 33000
+    R, t = workloads.random_poses_in_sphere(n, c2["roi"][:3], 7.0, seed=71)
+    for variant, shifted in ((gpu.VARIANT_SHIFTED, True), (gpu.VARIANT_GLOBAL, False)):
+        big = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP64)              # thread per pose
+        small = gpu.Mol.score_poses(rec, lig, R[:700], t[:700], variant=variant, prec=gpu.PREC_FP64)  # block per pose
+        one = gpu.Mol.score_poses(rec, lig, R[5:6], t[5:6], variant=variant, prec=gpu.PREC_FP64)
+        assert np.array_equal(big[:700], small) and one[0] == big[5]
+        X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R[:3000], t[:3000])
+        assert np.array_equal(big[:3000], orc.ene_inter(rec_m, m.q, m.anum, X, Y, Z, shifted=shifted))
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R[:1200], t[:1200])
+    few = gpu.Mol.ene_intra_UFFNB_brute(lig, X[:7], Y[:7], Z[:7])               # block per conformer
+    many = gpu.Mol.ene_intra_UFFNB_brute(lig, X, Y, Z)                          # thread per conformer
+    assert np.array_equal(few, many[:7]) and np.array_equal(many, orc.ene_intra(m, X, Y, Z))

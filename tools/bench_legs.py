@@ -370,6 +370,39 @@ def leg_fp64_scan(ctx, job_params, n_active, pps, n_rot, quick=False):
             "scaling": "weak", "best_score": SR.best_score, "best_frame": SR.best_frame, "clocks": ck.summary()}
 
 
+def leg_closure(ctx, quick=False):
+    """the literal drop-in shape: `ene_inter : Mol.t -> float` (lds.ml:1952-1979) = ONE pose per call through the C ABI,
+    host coordinates in, one double out; what an unmodified frame loop on the host would pay per evaluation"""
+    import mmo_b200
+    from mmo_b200 import pqrs, workloads
+    c2 = workloads.load_c2("docked")
+    rec_m = workloads.carve(c2["rec"], c2["roi"][:3], c2["roi"][3] + workloads.lig_radius(c2["centered"]) + 12.0)
+    rec = mmo_b200.Receptor.from_mol(rec_m)
+    lig = mmo_b200.Ligand.from_mol(c2["lig"], centered=True)
+    R, t = workloads.random_poses_in_sphere(64, c2["roi"][:3], 3.0, seed=2)
+    xs = (R[:, 0:1] * lig.xs + R[:, 1:2] * lig.ys + R[:, 2:3] * lig.zs) + t[:, 0:1]
+    ys = (R[:, 3:4] * lig.xs + R[:, 4:5] * lig.ys + R[:, 5:6] * lig.zs) + t[:, 1:2]
+    zs = (R[:, 6:7] * lig.xs + R[:, 7:8] * lig.ys + R[:, 8:9] * lig.zs) + t[:, 2:3]
+    cc = np.array(c2["roi"][:3])
+    gd = mmo_b200.Grid.from_box(1.0, *(cc + 23.0))
+    ta, tq = pqrs.assign_ff_types([c2["lig"]])
+    grid, _ = mmo_b200.Lds.pre_calculate_FF_components_grid(rec, 1.0, gd, ta, tq, mask_bits=sphere_mask_bits(1.0, gd, cc, 21.0), want_host=False)
+    n = 100 if quick else 400
+    out = {}
+    for name, fn in (("direct_fp32", lambda k: mmo_b200.Mol.ene_inter_UFF_shifted_brute(rec, lig, xs[k], ys[k], zs[k])),
+                     ("direct_fp64", lambda k: mmo_b200.Mol.ene_inter_UFF_shifted_brute(rec, lig, xs[k], ys[k], zs[k], prec=mmo_b200.PREC_FP64)),
+                     ("interp", lambda k: mmo_b200.Mol.ene_inter_UFF_interp(grid, lig, xs[k], ys[k], zs[k])),
+                     ("intra_nb", lambda k: mmo_b200.Mol.ene_intra_UFFNB_brute(lig, xs[k], ys[k], zs[k]))):
+        for k in range(8):
+            fn(k)
+        t0 = time.perf_counter()
+        for k in range(n):
+            fn(k % 64)
+        out[name + "_us_per_call"] = 1e6 * (time.perf_counter() - t0) / n
+    out["workload"] = "one pose per call (docked.mol2, 48 atoms, 1837-atom ROI receptor) through mmo_score_coords / mmo_score_interp_coords / mmo_intra_nb, ctypes overhead included"
+    return out
+
+
 def leg_n4(ctx, quick=False):
     """N4: the Majeux-Caflisch desolvation sums on the reference's own 0.5 A grid over the simulation box (wall clock,
     one GPU; bit-identical to the oracle's loops in tests/test_desolv.py)"""
@@ -410,6 +443,8 @@ def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0, only
         out["c5_screen"] = leg_c5(ctx, pk, quick)
     if only == "n4":
         out["n4_desolvation"] = leg_n4(ctx, quick)
+    if only in (None, "closure") and ctx.rank == 0:
+        out["single_pose_calls"] = leg_closure(ctx, quick)
     if scan_params is not None:
         out["c2_fp64_scan"] = leg_fp64_scan(ctx, scan_params, n_active, pps, n_rot, quick)
     ctx.ck(ctx.L.mmo_kernel_timing(0))
