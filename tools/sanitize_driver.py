@@ -34,8 +34,12 @@ if "items" in which:         # item kernel: prepare, sort, direct_items_kernel, 
     e = mmo_b200.Mol.ene_inter_UFF_shifted_brute(rec5, lig5, X, Y, Z)
     mmo_b200.lib().mmo_direct_set_mode(0)
 if "strict" in which:
-    mmo_b200.Mol.score_poses(rec, lig, R[:64], t[:64], prec=mmo_b200.PREC_FP64)
-    mmo_b200.Mol.ene_intra_UFFNB_brute(lig, np.tile(lig.xs, (8, 1)), np.tile(lig.ys, (8, 1)), np.tile(lig.zs, (8, 1)))
+    mmo_b200.Mol.score_poses(rec, lig, R[:64], t[:64], prec=mmo_b200.PREC_FP64)                  # block per pose
+    mmo_b200.Mol.ene_intra_UFFNB_brute(lig, np.tile(lig.xs, (8, 1)), np.tile(lig.ys, (8, 1)), np.tile(lig.zs, (8, 1)))   # block per conformer
+    rec_s = mmo_b200.Receptor.from_mol(workloads.carve(c2["rec"], c2["roi"][:3], 6.0))
+    Rb, tb = workloads.random_poses_in_sphere(33000, c2["roi"][:3], 6.0, seed=4)
+    mmo_b200.Mol.score_poses(rec_s, lig, Rb, tb, prec=mmo_b200.PREC_FP64)                        # thread per pose
+    mmo_b200.Mol.ene_intra_UFFNB_brute(lig, np.tile(lig.xs, (400, 1)), np.tile(lig.ys, (400, 1)), np.tile(lig.zs, (400, 1)))   # thread per conformer
 ta, tq = pqrs.assign_ff_types([c2["lig"]])
 cc = np.array(c2["roi"][:3])
 if "grid" in which or "mc" in which or "scan" in which:
