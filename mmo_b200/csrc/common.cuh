@@ -154,7 +154,7 @@ struct mmo_receptor {
     double vox_edge = 2.0;
     int vox_dim[3] = {0, 0, 0};
     mmo::DevBuf<int32_t> vox_off;    // nvox + 1
-    mmo::DevBuf<int32_t> vox_idx;    // atom indices (original order)
+    mmo::DevBuf<int32_t> vox_idx;    // atom indices (original order) | compact element index << 24
     double x_max = 0.0;              // largest UFF x_i among receptor atoms
     std::vector<double> hx, hy, hz, hq;   // host copies (original order)
     std::vector<int32_t> hanum;

@@ -862,26 +862,29 @@ __device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x,
         const int kn = min(64, k1 - kw);
 #pragma unroll kFixUnroll
         for (int b = 0; b < kn; b++) {
-            const float4 r4 = __ldg(a.pxyz32 + __ldg(a.vox_idx + kw + b));
+            const float4 r4 = __ldg(a.pxyz32 + (__ldg(a.vox_idx + kw + b) & 0xffffff));
             const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
             if (fdx * fdx + fdy * fdy + fdz * fdz < Hf) pass |= 1ull << b;
         }
         while (pass != 0ull) {
             const int b = __ffsll((long long)pass) - 1;
             pass &= pass - 1ull;
-            const int i = __ldg(a.vox_idx + kw + b);
+            const int ie = __ldg(a.vox_idx + kw + b);
+            const int i = ie & 0xffffff;
             const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
             const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
             const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
             const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 < a.H) {
-                const int tt = __ldg(a.pelt + i) * kEltTab + ej;
+                const int tt = (int)((unsigned)ie >> 24) * kEltTab + ej;
                 const double qq = r23.y * qj;
                 const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
                 // 1/r: MUFU.RSQ in fp32 (relative error < 2e-7), one Newton step in double (-> < 1e-13)
                 const double y0 = (double)rsqrtf((float)r2c);
                 const double rinv = y0 * (1.5 - (0.5 * r2c) * (y0 * y0));
                 const double s1 = rinv * rinv, s3 = (s1 * s1) * s1;
+                // (the three tables stay in global memory / L1: staging them in shared memory per block was measured,
+                //  0 % for hard_fix_kernel, +22 % time for item_fix_kernel, whose blocks mostly exit at once)
                 const double ee = (__ldg(a.xx + tt) * s3 - __ldg(a.dij + tt)) * s3 + qq * rinv;     // (A s^3 - B) s^3 + qq / r
                 const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
                 double d;

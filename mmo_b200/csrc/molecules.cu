@@ -179,7 +179,10 @@ int mmo_receptor_create(int32_t n, const double *xs, const double *ys, const dou
     for (size_t v = 0; v < nvox; v++) cnt[v + 1] += cnt[v];
     std::vector<int32_t> idx(std::max<size_t>(1, (size_t)cnt[nvox]));
     std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
-    for (int i = 0; i < n; i++) for_each_voxel(i, [&](size_t v) { idx[fill[v]++] = i; });   // ascending atom index per voxel
+    // ascending atom index per voxel; the atom's compact element index rides in the top byte (one load less per pair in
+    // the close-contact pass)
+    MMO_REQUIRE(n < (1 << 24), "mmo_receptor_create: more than 16 M atoms");
+    for (int i = 0; i < n; i++) for_each_voxel(i, [&](size_t v) { idx[fill[v]++] = i | (elt[i] << 24); });
 
     std::vector<double4> xyzq64(std::max(1, n));
     for (int i = 0; i < n; i++) xyzq64[i] = make_double4(xs[i], ys[i], zs[i], q[i]);
