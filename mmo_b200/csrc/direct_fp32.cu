@@ -77,8 +77,8 @@ struct FastArgs {
     const double *lx, *ly, *lz;      // template in fast-path order
     const int32_t *forder;           // fast-path position -> original atom index (explicit coordinates)
     const float4 *lparam;            // fast-path order
-    float H;                 // clamp on r^2 (fast path) == close-contact threshold (fix pass)
-    float Hflag;             // H plus a margin for the fp32 r^2: atoms with a pair below it are flagged for the fix pass
+    float hscale;            // x_max(receptor) / kTau: the clamp on r^2 (fast path) == close-contact threshold (fix pass) of
+                             // ligand atom j is H_j = hscale * x_j (lparam.w); atoms with a pair below H_j + margin are flagged
     unsigned long long *stats;   // [0] pairs evaluated, [1] pairs inside the cut-off (STATS builds)
 };
 
@@ -329,8 +329,8 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 // ceiling experiment (WRONG energies): after a warp's first list, every atom re-uses the stale list, 2 x 224
                 // entries, i.e. the pair work of an average C2 atom without any culling -- what perfect overlap could reach
                 if (exp_have_list) {
-                    run_list<VARIANT, true, STATS>(s_l, 224, 224, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
-                    run_list<VARIANT, true, STATS>(s_l, 224, 224, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
+                    run_list<VARIANT, true, STATS>(s_l, 224, 224, m2x, m2y, m2z, l2, a.hscale * lp.w, acc, rmin, n_in);
+                    run_list<VARIANT, true, STATS>(s_l, 224, 224, m2x, m2y, m2z, l2, a.hscale * lp.w, acc, rmin, n_in);
                     continue;
                 }
                 exp_have_list = true;
@@ -382,6 +382,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                 }
                 __syncwarp();
                 const float qjs = lp.z, Ajs = lp.x, nBjs = -lp.y;
+                const float Hj = a.hscale * lp.w;       // this ligand atom's clamp / close-contact threshold on r^2 (warp-uniform)
                 // ---- level 2: the atoms of four near groups per step, two per lane (independent loads and
                 //      tests); survivors are compacted into the warp's list, which is consumed whenever it
                 //      cannot take another step ----
@@ -429,14 +430,14 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                             e[4 * LIST_CAP] = 0.f; e[5 * LIST_CAP] = 0.f; e[6 * LIST_CAP] = 0.f;
                         }
                         __syncwarp();
-                        if (expand) run_list<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
-                        else run_list<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, acc, rmin, n_in);
+                        if (expand) run_list<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, Hj, acc, rmin, n_in);
+                        else run_list<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, Hj, acc, rmin, n_in);
                         n = 0;
                         __syncwarp();
                     }
                 }
 #pragma unroll
-                for (int h = 0; h < PPT; h++) cbits[h] |= (rmin[h] < a.Hflag ? 1u : 0u) << jj;
+                for (int h = 0; h < PPT; h++) cbits[h] |= (rmin[h] < Hj * 1.001f + 0.01f ? 1u : 0u) << jj;
             }
             // close-contact flags of this (tile, chunk): one byte per pose, read by hard_fix_kernel
 #pragma unroll
@@ -492,7 +493,7 @@ struct ItemArgs {
     const uint32_t *perm;        // sorted rank -> item
     const unsigned long long *n_far;   // items beyond the lattice (energy exactly 0): sorted last
     unsigned long long n_items;
-    float H, Hflag;
+    float hscale;                // H of an item = hscale * lparam.w of its ligand atom (per lane)
     double *e_item;              // = E (written once per item; items beyond the lattice keep the 0 of the memset)
     uint8_t *f_item;             // = close-contact flag
     unsigned long long *stats;
@@ -500,7 +501,7 @@ struct ItemArgs {
 
 template <int VARIANT, bool EXPAND, bool STATS>
 __device__ __forceinline__ void run_list_items(const float *s_l, int n, int n4, const float (&m2x)[PPT], const float (&m2y)[PPT],
-                                               const float (&m2z)[PPT], const float (&l2)[PPT], float H,
+                                               const float (&m2z)[PPT], const float (&l2)[PPT], const float (&H)[PPT],
                                                double (&EA)[PPT], double (&EB)[PPT], double (&EQ)[PPT],
                                                float (&rmin)[PPT], unsigned long long (&n_in)[PPT]) {
     // blocks of kItemSumEvery steps in fp32, then F2F + DADD (nested loops: no per-step counter)
@@ -535,7 +536,7 @@ __device__ __forceinline__ void run_list_items(const float *s_l, int n, int n4, 
                         r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
                     }
                     rmin[h] = fminf(rmin[h], fminf(r2.x, r2.y));
-                    const float2 r2c = make_float2(fmaxf(r2.x, H), fmaxf(r2.y, H));      // no upper clamp: the weight saturates
+                    const float2 r2c = make_float2(fmaxf(r2.x, H[h]), fmaxf(r2.y, H[h]));      // no upper clamp: the weight saturates
                     const float2 rinv = make_float2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
                     const float2 s = __fmul2_rn(rinv, rinv);
                     const float2 s3 = __fmul2_rn(__fmul2_rn(s, s), s);
@@ -699,8 +700,9 @@ direct_items_kernel(ItemArgs a, int near_cap, unsigned long long *__restrict__ w
         }
         double EA[PPT], EB[PPT], EQ[PPT];
         unsigned long long n_in[PPT];
+        float Hl[PPT];
 #pragma unroll
-        for (int h = 0; h < PPT; h++) { EA[h] = EB[h] = EQ[h] = 0.0; n_in[h] = 0; }
+        for (int h = 0; h < PPT; h++) { EA[h] = EB[h] = EQ[h] = 0.0; n_in[h] = 0; Hl[h] = a.hscale * lp[h].w; }
         // ---- level 1: super-group boxes, then the group boxes of the near super-groups, against the sphere (c, 12 + rho) ----
         auto box_near = [&](const float4 blo, const float4 bhi) {
             const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
@@ -790,8 +792,8 @@ direct_items_kernel(ItemArgs a, int near_cap, unsigned long long *__restrict__ w
                     e[4 * LIST_CAP] = 0.f; e[5 * LIST_CAP] = 0.f; e[6 * LIST_CAP] = 0.f;
                 }
                 __syncwarp();
-                if (expand) run_list_items<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, EA, EB, EQ, rmin, n_in);
-                else run_list_items<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, a.H, EA, EB, EQ, rmin, n_in);
+                if (expand) run_list_items<VARIANT, true, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, Hl, EA, EB, EQ, rmin, n_in);
+                else run_list_items<VARIANT, false, STATS>(s_l, n, n4, m2x, m2y, m2z, l2, Hl, EA, EB, EQ, rmin, n_in);
                 n = 0;
                 __syncwarp();
             }
@@ -800,7 +802,7 @@ direct_items_kernel(ItemArgs a, int near_cap, unsigned long long *__restrict__ w
         for (int h = 0; h < PPT; h++) {
             if (cur.valid[h]) {
                 a.e_item[cur.item[h]] = (double)lp[h].x * EA[h] - (double)lp[h].y * EB[h] + (double)lp[h].z * EQ[h];
-                a.f_item[cur.item[h]] = rmin[h] < a.Hflag ? 1 : 0;
+                a.f_item[cur.item[h]] = rmin[h] < Hl[h] * 1.001f + 0.01f ? 1 : 0;
                 if (STATS) n_in_tot += n_in[h];
             }
         }
@@ -829,10 +831,10 @@ struct FixArgs {
     const double *lx, *ly, *lz, *lq;
     const int32_t *forder;               // fast-path position -> original atom index
     const int32_t *lelt;
-    double H;                            // exactly the fp32 clamp value
-    double rinvH;                        // 1/sqrt(H)
-    double wH;                           // shift weight at r^2 = H
-    const double *xx, *dij, *vdwH;       // kEltTab^2 tables: A = d_ij x_ij^12, B = 2 d_ij x_ij^6, d_ij*(p6H^2 - 2 p6H)
+    double H[kEltTab];                   // by ligand element: exactly the fp32 clamp value hscale * x_j
+    double rinvH[kEltTab];               // 1/sqrt(H)
+    double wH[kEltTab];                  // shift weight at r^2 = H
+    const double *xx, *dij, *vdwH;       // kEltTab^2 tables: A = d_ij x_ij^12, B = 2 d_ij x_ij^6, d_ij*(p6H^2 - 2 p6H) at the H of the ligand element
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
 
@@ -852,7 +854,8 @@ __device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x,
     const double qj = kElecWeight * __ldg(a.lq + j);
     const int ej = __ldg(a.lelt + j);
     const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
-    const float Hf = (float)a.H + MMO_FIX_MARGIN;     // fp32 r^2 of coordinates below ~200 A: error < 1e-3 A^2
+    const double H = a.H[ej], rinvH = a.rinvH[ej], wH = a.wH[ej];
+    const float Hf = (float)H + MMO_FIX_MARGIN;       // fp32 r^2 of coordinates below ~200 A: error < 1e-3 A^2
     // Two phases per window of 64 candidates, so that a warp whose lanes sit in different voxels pays
     // max(candidates) cheap tests + max(close pairs) fp64 evaluations, not their product: (1) the fp32 pre-test
     // (coordinates relative to the voxel grid corner, error << the margin) marks the survivors in a
@@ -875,7 +878,7 @@ __device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x,
             const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
             const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
             const double r2 = dx * dx + dy * dy + dz * dz;
-            if (r2 < a.H) {
+            if (r2 < H) {
                 const int tt = (int)((unsigned)ie >> 24) * kEltTab + ej;
                 const double qq = r23.y * qj;
                 const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
@@ -886,11 +889,11 @@ __device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x,
                 // (the three tables stay in global memory / L1: staging them in shared memory per block was measured,
                 //  0 % for hard_fix_kernel, +22 % time for item_fix_kernel, whose blocks mostly exit at once)
                 const double ee = (__ldg(a.xx + tt) * s3 - __ldg(a.dij + tt)) * s3 + qq * rinv;     // (A s^3 - B) s^3 + qq / r
-                const double eH = qq * a.rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
+                const double eH = qq * rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
                 double d;
                 if (VARIANT == MMO_VARIANT_SHIFTED) {
                     const double u = 1.0 - r2c * (1.0 / 144.0);
-                    d = (u * u) * ee - a.wH * eH;                      // the fast path clamped r^2 in the weight too
+                    d = (u * u) * ee - wH * eH;                        // the fast path clamped r^2 in the weight too
                 } else {
                     d = ee - eH;
                 }
@@ -1013,7 +1016,14 @@ void direct_drop_caches() {
     g_vdwH_for = -1.0;
 }
 
-static int ensure_fix_tables(double H) {
+// the fp32 clamp value of a ligand atom of compact element e: the same float product the kernels form (hscale * lparam.w)
+static float clamp_H(float hscale, int e) {
+    const float xj = (float)std::max(e < kNumElt ? kEltXi[e] : 1.0, 1.0);
+    volatile float h = hscale * xj;       // one IEEE float product, no contraction
+    return h;
+}
+
+static int ensure_fix_tables(float hscale) {
     if (!g_xx.p) {
         std::vector<double> hx(kEltTab * kEltTab), hd(kEltTab * kEltTab);
         for (int a = 0; a < kEltTab; a++)
@@ -1028,17 +1038,20 @@ static int ensure_fix_tables(double H) {
         MMO_TRY(g_dij.upload(hd));
         MMO_TRY(g_stats.alloc(4));
     }
-    if (g_vdwH_for != H) {
+    if (g_vdwH_for != (double)hscale) {
+        // what the fast path adds for a clamped pair: the vdW term at r^2 = H, H being that of the LIGAND atom's element
+        // (index: receptor element * kEltTab + ligand element)
         std::vector<double> hv(kEltTab * kEltTab);
         for (int a = 0; a < kEltTab; a++)
             for (int b = 0; b < kEltTab; b++) {
                 bool ok = a < kNumElt && b < kNumElt;
+                const double H = (double)clamp_H(hscale, b);
                 double t2 = ok ? kEltXi[a] * kEltXi[b] / H : NAN;
                 double p6 = t2 * t2 * t2;
                 hv[a * kEltTab + b] = ok ? sqrt(kEltDi[a] * kEltDi[b]) * (p6 * p6 - 2.0 * p6) : NAN;
             }
         MMO_TRY(g_vdwH.upload(hv));
-        g_vdwH_for = H;
+        g_vdwH_for = (double)hscale;
     }
     return MMO_OK;
 }
@@ -1136,7 +1149,7 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     ia.xyzq = fa.xyzq; ia.gelt = fa.gelt; ia.blob_box = fa.blob_box; ia.sup_box = rec->sup_box.p;
     ia.n_blobs = rec->n_blobs; ia.n_sup = rec->n_sup; ia.lparam = fa.lparam; ia.n_fast = nf;
     ia.pos = pos; ia.perm = perm; ia.n_far = d_far; ia.n_items = n_items;
-    ia.H = fa.H; ia.Hflag = fa.Hflag; ia.e_item = e_item; ia.f_item = f_item; ia.stats = fa.stats;
+    ia.hscale = fa.hscale; ia.e_item = e_item; ia.f_item = f_item; ia.stats = fa.stats;
     MMO_REQUIRE(rec->n_blobs < 65535, "receptor too large for the direct kernel (%d atoms)", rec->n);
     const int near_cap = (rec->n_blobs + 8 + 7) & ~7;
     const size_t smem = ((size_t)2 * rec->n_sup + (size_t)nf) * sizeof(float4) + 16 * sizeof(float2) +
@@ -1178,9 +1191,10 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     // (worst |err| / tolerance 0.3) and lost near 2e5.  Larger GLOBAL problems take the strict fp64 kernel.
     if (variant == MMO_VARIANT_GLOBAL && (int64_t)rec->n * lig->n > kGlobalFp32MaxPairs)
         return launch_direct_fp64(rec, lig, variant, src, n_poses, d_out);
-    // clamp / close-contact threshold on r^2; a float so that both kernels see the same number
-    const float H = (float)(std::max(rec->x_max, 1.0) * std::max(lig->x_max, 1.0) / kTau);
-    MMO_TRY(ensure_fix_tables((double)H));
+    // clamp / close-contact threshold on r^2 per ligand atom: H_j = hscale * x_j; floats, so that the fast kernel and the
+    // fp64 pass see the same numbers
+    const float hscale = (float)(std::max(rec->x_max, 1.0) / kTau);
+    MMO_TRY(ensure_fix_tables(hscale));
     FastArgs fa;
     fa.n_blobs = rec->n_blobs;
     for (int e = 0; e < kEltTab; e++) vdw_factors(e, &fa.tab_A[e], &fa.tab_B[e]);
@@ -1191,8 +1205,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     fa.lx = lig->fx.p; fa.ly = lig->fy.p; fa.lz = lig->fz.p;
     fa.forder = lig->forder.p;
     fa.lparam = lig->fparam.p;
-    fa.H = H;
-    fa.Hflag = H * 1.001f + 0.01f;
+    fa.hscale = hscale;
     fa.stats = g_stats.p;
     FixArgs xa;
     xa.pxyzq = rec->xyzq64.p; xa.pxyz32 = rec->xyz32v.p; xa.pelt = rec->elt.p;
@@ -1202,9 +1215,12 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     xa.L = lig->n;
     xa.lx = lig->x.p; xa.ly = lig->y.p; xa.lz = lig->z.p; xa.lq = lig->q.p; xa.lelt = lig->elt.p;
     xa.forder = lig->forder.p;
-    xa.H = (double)H;
-    xa.rinvH = 1.0 / sqrt((double)H);
-    xa.wH = (1.0 - (double)H / 144.0) * (1.0 - (double)H / 144.0);
+    for (int e = 0; e < kEltTab; e++) {
+        const double H = (double)clamp_H(hscale, e);
+        xa.H[e] = H;
+        xa.rinvH[e] = 1.0 / sqrt(H);
+        xa.wH[e] = (1.0 - H / 144.0) * (1.0 - H / 144.0);
+    }
     xa.xx = g_xx.p; xa.dij = g_dij.p; xa.vdwH = g_vdwH.p;
     xa.stats = g_stats.p;
 

@@ -276,7 +276,9 @@ int mmo_ligand_create(int32_t n, const double *xs, const double *ys, const doubl
         int j = forder[k];
         float A, B;
         vdw_factors(elt[j], &A, &B);
-        fp[k] = make_float4(A, B, (float)q[j], 1.f);     // .w = 1 marks a real atom
+        // .w = the atom's UFF distance x_j (>= 1: also marks a real atom; 0 = padding): the close-contact threshold of
+        // the fp32 kernels is per ligand atom, H_j = hscale * x_j with hscale = x_max(receptor) / kTau
+        fp[k] = make_float4(A, B, (float)q[j], (float)std::max(elt[j] < kNumElt ? kEltXi[elt[j]] : 1.0, 1.0));
         fx[k] = xs[j]; fy[k] = ys[j]; fz[k] = zs[j];
     }
     int rc = MMO_OK;
