@@ -21,7 +21,7 @@
 //   sum     = fp32 inside a chain for kSumEvery steps, then F2F + DADD into per-pose fp64 accumulators
 //
 // Accuracy contract (MMO_PREC_FP32): |E - E_ref| <= max(1e-6 |E_ref|, 1e-4 kcal/mol).  fp32 cannot
-// deliver that for close contacts (r^-12), so the fast path clamps r^2 at H = x_max_rec*x_max_lig/kTau
+// deliver that for close contacts (r^-12), so the fast path clamps r^2 per ligand atom at H_j = x_j*x_max_rec/kTau
 // and a second, sparse kernel (hard_fix_kernel) adds  w(r) e64(r) - w(sqrt H) e64(sqrt H)  in the
 // reference's own double arithmetic for the few pairs with r^2 < H, found through the receptor's voxel lists.
 #include "common.cuh"
@@ -832,9 +832,9 @@ struct FixArgs {
     const int32_t *forder;               // fast-path position -> original atom index
     const int32_t *lelt;
     double H[kEltTab];                   // by ligand element: exactly the fp32 clamp value hscale * x_j
-    double rinvH[kEltTab];               // 1/sqrt(H)
-    double wH[kEltTab];                  // shift weight at r^2 = H
-    const double *xx, *dij, *vdwH;       // kEltTab^2 tables: A = d_ij x_ij^12, B = 2 d_ij x_ij^6, d_ij*(p6H^2 - 2 p6H) at the H of the ligand element
+    double wrH[kEltTab];                 // w(H) / sqrt(H): weight (1 for GLOBAL) x Coulomb factor of what the fast path evaluated
+    const double4 *tab;                  // [receptor element * kEltTab + ligand element] {A = d_ij x_ij^12, B = 2 d_ij x_ij^6,
+                                         //  w(H) d_ij (p6H^2 - 2 p6H) at the H of the ligand element, 0}: one 32 B sector per pair
     unsigned long long *stats;           // [2] pairs re-evaluated
 };
 
@@ -854,46 +854,50 @@ __device__ __forceinline__ double close_contact_corr(const FixArgs &a, double x,
     const double qj = kElecWeight * __ldg(a.lq + j);
     const int ej = __ldg(a.lelt + j);
     const float xf = (float)(x - a.vox_lo[0]), yf = (float)(y - a.vox_lo[1]), zf = (float)(z - a.vox_lo[2]);
-    const double H = a.H[ej], rinvH = a.rinvH[ej], wH = a.wH[ej];
+    const double H = a.H[ej], wrH = a.wrH[ej];
     const float Hf = (float)H + MMO_FIX_MARGIN;       // fp32 r^2 of coordinates below ~200 A: error < 1e-3 A^2
-    // Two phases per window of 64 candidates, so that a warp whose lanes sit in different voxels pays
+    const int32_t *__restrict__ idx = a.vox_idx + k0;
+    const int nk = k1 - k0;
+    // Two phases per window of 32 candidates, so that a warp whose lanes sit in different voxels pays
     // max(candidates) cheap tests + max(close pairs) fp64 evaluations, not their product: (1) the fp32 pre-test
     // (coordinates relative to the voxel grid corner, error << the margin) marks the survivors in a
-    // 64-bit mask, (2) the survivors are evaluated in double, in list order.
-    for (int kw = k0; kw < k1; kw += 64) {
-        unsigned long long pass = 0ull;
-        const int kn = min(64, k1 - kw);
+    // 32-bit mask, (2) the survivors are evaluated in double, in list order.
+    for (int kw = 0; kw < nk; kw += 32) {
+        unsigned pass = 0u;
+        const int kn = min(32, nk - kw);
 #pragma unroll kFixUnroll
         for (int b = 0; b < kn; b++) {
-            const float4 r4 = __ldg(a.pxyz32 + (__ldg(a.vox_idx + kw + b) & 0xffffff));
+            const float4 r4 = __ldg(a.pxyz32 + (__ldg(idx + kw + b) & 0xffffff));
             const float fdx = r4.x - xf, fdy = r4.y - yf, fdz = r4.z - zf;
-            if (fdx * fdx + fdy * fdy + fdz * fdz < Hf) pass |= 1ull << b;
+            if (fdx * fdx + fdy * fdy + fdz * fdz < Hf) pass |= 1u << b;
         }
-        while (pass != 0ull) {
-            const int b = __ffsll((long long)pass) - 1;
-            pass &= pass - 1ull;
-            const int ie = __ldg(a.vox_idx + kw + b);
+        while (pass != 0u) {
+            const int b = __ffs((int)pass) - 1;
+            pass &= pass - 1u;
+            const int ie = __ldg(idx + kw + b);
             const int i = ie & 0xffffff;
             const double2 r01 = __ldg((const double2 *)(a.pxyzq + i));
             const double2 r23 = __ldg((const double2 *)(a.pxyzq + i) + 1);
             const double dx = r01.x - x, dy = r01.y - y, dz = r23.x - z;
             const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 < H) {
-                const int tt = (int)((unsigned)ie >> 24) * kEltTab + ej;
+                const double2 *t = (const double2 *)(a.tab + ((int)((unsigned)ie >> 24) * kEltTab + ej));
+                const double2 AB = __ldg(t);
+                const double wvH = __ldg((const double *)(t + 1));
                 const double qq = r23.y * qj;
-                const double r2c = fmax(r2, 1e-4);                  // Math.non_zero_dist on r
+                const double r2c = r2 < 1e-4 ? 1e-4 : r2;           // Math.non_zero_dist on r (r2 is never NaN here)
                 // 1/r: MUFU.RSQ in fp32 (relative error < 2e-7), one Newton step in double (-> < 1e-13)
-                const double y0 = (double)rsqrtf((float)r2c);
+                const double y0 = (double)rsqrt_fast((float)r2c);
                 const double rinv = y0 * (1.5 - (0.5 * r2c) * (y0 * y0));
                 const double s1 = rinv * rinv, s3 = (s1 * s1) * s1;
-                // (the three tables stay in global memory / L1: staging them in shared memory per block was measured,
+                // (the table stays in global memory / L1: staging it in shared memory per block was measured,
                 //  0 % for hard_fix_kernel, +22 % time for item_fix_kernel, whose blocks mostly exit at once)
-                const double ee = (__ldg(a.xx + tt) * s3 - __ldg(a.dij + tt)) * s3 + qq * rinv;     // (A s^3 - B) s^3 + qq / r
-                const double eH = qq * rinvH + __ldg(a.vdwH + tt);   // what the fast path evaluated (r clamped at sqrt(H))
+                const double ee = (AB.x * s3 - AB.y) * s3 + qq * rinv;     // (A s^3 - B) s^3 + qq / r
+                const double eH = qq * wrH + wvH;     // w(H) x what the fast path evaluated (r clamped at sqrt(H), in the weight too)
                 double d;
                 if (VARIANT == MMO_VARIANT_SHIFTED) {
                     const double u = 1.0 - r2c * (1.0 / 144.0);
-                    d = (u * u) * ee - wH * eH;                        // the fast path clamped r^2 in the weight too
+                    d = (u * u) * ee - eH;
                 } else {
                     d = ee - eH;
                 }
@@ -1002,7 +1006,7 @@ item_fix_kernel(FixArgs a, PoseSrc src, int n_fast, const uint32_t *__restrict__
 // ---- host side -----------------------------------------------------------------------------------
 // Library-lifetime device buffers.  Allocated with `new` and never destroyed: no destructor may touch the allocator
 // or the CUDA context during static destruction at process exit; mmo_shutdown releases them (direct_drop_caches).
-static DevBuf<double> &g_xx = *new DevBuf<double>(), &g_dij = *new DevBuf<double>(), &g_vdwH = *new DevBuf<double>();
+static DevBuf<double4> &g_fixtab = *new DevBuf<double4>();                   // FixArgs::tab
 static DevBuf<unsigned long long> &g_stats = *new DevBuf<unsigned long long>(), &g_work = *new DevBuf<unsigned long long>();
 static DevBuf<uint8_t> &g_item_scratch = *new DevBuf<uint8_t>();             // item mode scratch arena
 constexpr int64_t kItemModeMin = 32768;          // items (poses x ligand atoms) from which item mode pays
@@ -1010,10 +1014,10 @@ constexpr int64_t kItemBatch = (int64_t)64 << 20;  // items per batch: ~47 B of 
 constexpr int64_t kGlobalFp32MaxPairs = 120000;   // receptor x ligand atoms up to which GLOBAL stays on the fp32 path
 static int g_direct_mode = 0;                     // 0 auto, 1 pose kernel always, 2 item kernel for every pose list
 void direct_set_mode(int mode) { g_direct_mode = mode; }
-static double g_vdwH_for = -1.0;
+static double g_fixtab_for = 0.0;                 // +-hscale the table was built for (sign: SHIFTED / GLOBAL)
 void direct_drop_caches() {
-    g_xx.release(); g_dij.release(); g_vdwH.release(); g_stats.release(); g_work.release(); g_item_scratch.release();
-    g_vdwH_for = -1.0;
+    g_fixtab.release(); g_stats.release(); g_work.release(); g_item_scratch.release();
+    g_fixtab_for = 0.0;
 }
 
 // the fp32 clamp value of a ligand atom of compact element e: the same float product the kernels form (hscale * lparam.w)
@@ -1023,35 +1027,26 @@ static float clamp_H(float hscale, int e) {
     return h;
 }
 
-static int ensure_fix_tables(float hscale) {
-    if (!g_xx.p) {
-        std::vector<double> hx(kEltTab * kEltTab), hd(kEltTab * kEltTab);
-        for (int a = 0; a < kEltTab; a++)
-            for (int b = 0; b < kEltTab; b++) {
-                bool ok = a < kNumElt && b < kNumElt;
+static int ensure_fix_tables(float hscale, bool shifted) {
+    if (!g_stats.p) MMO_TRY(g_stats.alloc(4));
+    const double key = shifted ? (double)hscale : -(double)hscale;
+    if (g_fixtab_for != key) {
+        std::vector<double4> ht(kEltTab * kEltTab);
+        for (int a = 0; a < kEltTab; a++)            // receptor element
+            for (int b = 0; b < kEltTab; b++) {      // ligand element
+                const bool ok = a < kNumElt && b < kNumElt;
                 // d_ij (p6^2 - 2 p6) with p6 = (x_i x_j / r^2)^3  ==  A s^6 - B s^3,  s = 1/r^2
                 const double x2 = ok ? kEltXi[a] * kEltXi[b] : NAN, d = ok ? sqrt(kEltDi[a] * kEltDi[b]) : NAN;
-                hx[a * kEltTab + b] = d * ((x2 * x2 * x2) * (x2 * x2 * x2));       // A
-                hd[a * kEltTab + b] = 2.0 * d * (x2 * x2 * x2);                    // B
-            }
-        MMO_TRY(g_xx.upload(hx));
-        MMO_TRY(g_dij.upload(hd));
-        MMO_TRY(g_stats.alloc(4));
-    }
-    if (g_vdwH_for != (double)hscale) {
-        // what the fast path adds for a clamped pair: the vdW term at r^2 = H, H being that of the LIGAND atom's element
-        // (index: receptor element * kEltTab + ligand element)
-        std::vector<double> hv(kEltTab * kEltTab);
-        for (int a = 0; a < kEltTab; a++)
-            for (int b = 0; b < kEltTab; b++) {
-                bool ok = a < kNumElt && b < kNumElt;
+                const double x6 = x2 * x2 * x2;
+                // what the fast path adds for a clamped pair: the vdW term at r^2 = H, H being that of the LIGAND atom's
+                // element, times the shift weight at H (SHIFTED)
                 const double H = (double)clamp_H(hscale, b);
-                double t2 = ok ? kEltXi[a] * kEltXi[b] / H : NAN;
-                double p6 = t2 * t2 * t2;
-                hv[a * kEltTab + b] = ok ? sqrt(kEltDi[a] * kEltDi[b]) * (p6 * p6 - 2.0 * p6) : NAN;
+                const double t2 = x2 / H, p6 = t2 * t2 * t2;
+                const double wH = shifted ? (1.0 - H / 144.0) * (1.0 - H / 144.0) : 1.0;
+                ht[a * kEltTab + b] = make_double4(d * (x6 * x6), 2.0 * d * x6, wH * (d * (p6 * p6 - 2.0 * p6)), 0.0);
             }
-        MMO_TRY(g_vdwH.upload(hv));
-        g_vdwH_for = (double)hscale;
+        MMO_TRY(g_fixtab.upload(ht));
+        g_fixtab_for = key;
     }
     return MMO_OK;
 }
@@ -1194,7 +1189,7 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     // clamp / close-contact threshold on r^2 per ligand atom: H_j = hscale * x_j; floats, so that the fast kernel and the
     // fp64 pass see the same numbers
     const float hscale = (float)(std::max(rec->x_max, 1.0) / kTau);
-    MMO_TRY(ensure_fix_tables(hscale));
+    MMO_TRY(ensure_fix_tables(hscale, variant == MMO_VARIANT_SHIFTED));
     FastArgs fa;
     fa.n_blobs = rec->n_blobs;
     for (int e = 0; e < kEltTab; e++) vdw_factors(e, &fa.tab_A[e], &fa.tab_B[e]);
@@ -1218,10 +1213,9 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     for (int e = 0; e < kEltTab; e++) {
         const double H = (double)clamp_H(hscale, e);
         xa.H[e] = H;
-        xa.rinvH[e] = 1.0 / sqrt(H);
-        xa.wH[e] = (1.0 - H / 144.0) * (1.0 - H / 144.0);
+        xa.wrH[e] = (variant == MMO_VARIANT_SHIFTED ? (1.0 - H / 144.0) * (1.0 - H / 144.0) : 1.0) / sqrt(H);
     }
-    xa.xx = g_xx.p; xa.dij = g_dij.p; xa.vdwH = g_vdwH.p;
+    xa.tab = g_fixtab.p;
     xa.stats = g_stats.p;
 
     if (collect_stats) MMO_CUDA(cudaMemsetAsync(g_stats.p, 0, 4 * sizeof(unsigned long long), R.stream));
