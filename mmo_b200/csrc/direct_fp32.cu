@@ -489,13 +489,14 @@ struct ItemArgs {
     int n_blobs, n_sup;
     const float4 *lparam;        // fast-path order {A_j, B_j, q_j, real?}
     int n_fast;
-    const float4 *pos;           // item -> position relative to the receptor origin (item = pose * n_fast + k)
+    const float4 *pos;           // item -> two float4: position relative to the receptor origin {x, y, z, 0} and the fp32
+                                 // remainders of the double {lo_x, lo_y, lo_z, 0} (read by item_fix_kernel): one 32 B sector
     const uint32_t *perm;        // sorted rank -> item
     const unsigned long long *n_far;   // items beyond the lattice (energy exactly 0): sorted last
     unsigned long long n_items;
     float hscale;                // H of an item = hscale * lparam.w of its ligand atom (per lane)
-    double *e_item;              // = E (written once per item; items beyond the lattice keep the 0 of the memset)
-    uint8_t *f_item;             // = close-contact flag
+    double *e_rank;              // = E of the item at sorted rank r (coalesced; item_fix_kernel scatters it to item order)
+    uint8_t *f_rank;             // = its close-contact flag
     unsigned long long *stats;
 };
 
@@ -575,7 +576,7 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
 }
 
 // position (double, then fp32 relative to the receptor origin) and lattice cell of every item; thread = item, so that
-// the 24 bytes written per item (and the coordinates read, for explicit conformers) are coalesced
+// the 40 bytes written per item (and the coordinates read, for explicit conformers) are coalesced
 __global__ void __launch_bounds__(256)
 item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const double *__restrict__ lx, const double *__restrict__ ly,
                     const double *__restrict__ lz, const int32_t *__restrict__ forder, const float4 *__restrict__ lparam,
@@ -589,7 +590,7 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
     if (it < n_items) {
         const int64_t p = it / n_fast;
         const int k = (int)(it - p * n_fast);
-        float4 v = make_float4(kFarAway, kFarAway, kFarAway, 0.f);
+        float4 v = make_float4(kFarAway, kFarAway, kFarAway, 0.f), vlo = make_float4(0.f, 0.f, 0.f, 0.f);
         if (__ldg(&lparam[k].w) != 0.f) {
             double x, y, z;
             if (src.kind == 1) {
@@ -600,12 +601,16 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
                 load_pose_rt(src, p, P);
                 pose_atom_rt(P, __ldg(lx + k), __ldg(ly + k), __ldg(lz + k), x, y, z);
             }
-            v.x = (float)(x - ox); v.y = (float)(y - oy); v.z = (float)(z - oz);
+            const double Dx = x - ox, Dy = y - oy, Dz = z - oz;
+            v.x = (float)Dx; v.y = (float)Dy; v.z = (float)Dz;
+            // hi + lo carries 48 bits of the double (< 2e-13 A at 50 A): what the fp64 close-contact pass works with
+            vlo.x = (float)(Dx - (double)v.x); vlo.y = (float)(Dy - (double)v.y); vlo.z = (float)(Dz - (double)v.z);
             const float fx = (v.x - cell_lo_x) * cell_inv, fy = (v.y - cell_lo_y) * cell_inv, fz = (v.z - cell_lo_z) * cell_inv;
             if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)nx && fy < (float)ny && fz < (float)nz)
                 key = spread3((uint32_t)fx) | (spread3((uint32_t)fy) << 1) | (spread3((uint32_t)fz) << 2);     // Z-order
         }
-        pos[it] = v;
+        pos[2 * it] = v;
+        pos[2 * it + 1] = vlo;
         keys[it] = key;
         vals[it] = (uint32_t)it;
     }
@@ -631,7 +636,7 @@ __device__ __forceinline__ void load_item_unit(const ItemArgs &a, unsigned long 
         const unsigned long long idx = u * (32 * PPT) + 32 * h + lane;
         U.valid[h] = idx < n_near;
         U.item[h] = __ldg(a.perm + (U.valid[h] ? idx : n_near - 1));    // idle slots shadow the last item
-        U.v[h] = __ldg(a.pos + U.item[h]);
+        U.v[h] = __ldg(a.pos + 2 * (size_t)U.item[h]);
     }
 }
 
@@ -801,8 +806,9 @@ direct_items_kernel(ItemArgs a, int near_cap, unsigned long long *__restrict__ w
 #pragma unroll
         for (int h = 0; h < PPT; h++) {
             if (cur.valid[h]) {
-                a.e_item[cur.item[h]] = (double)lp[h].x * EA[h] - (double)lp[h].y * EB[h] + (double)lp[h].z * EQ[h];
-                a.f_item[cur.item[h]] = rmin[h] < Hl[h] * 1.001f + 0.01f ? 1 : 0;
+                const unsigned long long r = u * (32 * PPT) + 32 * h + lane;       // sorted rank: coalesced stores
+                a.e_rank[r] = (double)lp[h].x * EA[h] - (double)lp[h].y * EB[h] + (double)lp[h].z * EQ[h];
+                a.f_rank[r] = rmin[h] < Hl[h] * 1.001f + 0.01f ? 1 : 0;
                 if (STATS) n_in_tot += n_in[h];
             }
         }
@@ -965,42 +971,28 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
 
 // Item mode: the same correction with thread = ITEM in cell-sorted order (the order direct_items_kernel works in).  The
 // lanes of a warp then sit in neighbouring voxels: their candidate lists are the same few cache lines and about equally
-// long, which a warp of unrelated conformers (thread = pose) has neither of.  The correction is added to the item's
-// energy; hard_fix_kernel<ITEMS> (called with n_chunks = 0) then only sums the items of a pose in atom order.
+// long, which a warp of unrelated conformers (thread = pose) has neither of.  Everything read per item is either
+// coalesced (rank -> item, energy and flag as direct_items_kernel stored them, by rank) or ONE 32-byte sector (the
+// item's position record); the corrected energy is scattered to item order, one 8-byte store per item -- the only
+// pass over e_item before hard_fix_kernel<ITEMS> (called with n_chunks = 0) sums the items of a pose in atom order.
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(128, kFixBlocksPerSM)
-item_fix_kernel(FixArgs a, PoseSrc src, int n_fast, const uint32_t *__restrict__ perm,
-                const unsigned long long *__restrict__ n_far, unsigned long long n_items,
-                const uint8_t *__restrict__ f_item, double *__restrict__ e_item) {
-    __shared__ double s_P[12][128];
-    const int tx = threadIdx.x;
-    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + tx;
-    if (r >= n_items - *n_far) return;                      // items beyond the lattice are sorted last: energy exactly 0
+item_fix_kernel(FixArgs a, double ox, double oy, double oz, int n_fast, const uint32_t *__restrict__ perm,
+                const float4 *__restrict__ pos, const unsigned long long *__restrict__ n_far, unsigned long long n_items,
+                const uint8_t *__restrict__ f_rank, const double *__restrict__ e_rank, double *__restrict__ e_item) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_items - *n_far) return;                      // items beyond the lattice are sorted last: energy exactly 0 (memset)
     const uint32_t item = __ldg(perm + r);
-    if (!f_item[item]) return;
-    const int64_t p = item / (uint32_t)n_fast;
-    const int j = __ldg(a.forder + (int)(item - (uint32_t)p * (uint32_t)n_fast));
-    double x, y, z;
-    if (src.kind == 1) {
-        x = src.xs[p * a.L + j]; y = src.ys[p * a.L + j]; z = src.zs[p * a.L + j];
-    } else {
-        {
-            PoseRT P;
-            load_pose_rt(src, p, P);
-#pragma unroll
-            for (int q = 0; q < 9; q++) s_P[q][tx] = P.r[q];
-#pragma unroll
-            for (int q = 0; q < 3; q++) s_P[9 + q][tx] = P.t[q];
-        }
-        const double ax = __ldg(a.lx + j), ay = __ldg(a.ly + j), az = __ldg(a.lz + j);
-        x = __dadd_rn(rot_row(s_P[0][tx], s_P[1][tx], s_P[2][tx], ax, ay, az), s_P[9][tx]);
-        y = __dadd_rn(rot_row(s_P[3][tx], s_P[4][tx], s_P[5][tx], ax, ay, az), s_P[10][tx]);
-        z = __dadd_rn(rot_row(s_P[6][tx], s_P[7][tx], s_P[8][tx], ax, ay, az), s_P[11][tx]);
+    double e = __ldg(e_rank + r);
+    if (__ldg(f_rank + r)) {
+        const float4 hi = __ldg(pos + 2 * (size_t)item), lo = __ldg(pos + 2 * (size_t)item + 1);
+        const int j = __ldg(a.forder + (int)(item % (uint32_t)n_fast));
+        const double x = ((double)hi.x + (double)lo.x) + ox, y = ((double)hi.y + (double)lo.y) + oy, z = ((double)hi.z + (double)lo.z) + oz;
+        unsigned long long n_fix = 0;
+        e += close_contact_corr<VARIANT, STATS>(a, x, y, z, j, n_fix);
+        if (STATS) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, 1ull); }
     }
-    unsigned long long n_fix = 0;
-    const double corr = close_contact_corr<VARIANT, STATS>(a, x, y, z, j, n_fix);
-    e_item[item] += corr;
-    if (STATS) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, 1ull); }
+    e_item[item] = e;
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -1010,7 +1002,7 @@ static DevBuf<double4> &g_fixtab = *new DevBuf<double4>();                   // 
 static DevBuf<unsigned long long> &g_stats = *new DevBuf<unsigned long long>(), &g_work = *new DevBuf<unsigned long long>();
 static DevBuf<uint8_t> &g_item_scratch = *new DevBuf<uint8_t>();             // item mode scratch arena
 constexpr int64_t kItemModeMin = 32768;          // items (poses x ligand atoms) from which item mode pays
-constexpr int64_t kItemBatch = (int64_t)64 << 20;  // items per batch: ~47 B of scratch each (3 GB)
+constexpr int64_t kItemBatch = (int64_t)64 << 20;  // items per batch: ~65 B of scratch each (4.4 GB)
 constexpr int64_t kGlobalFp32MaxPairs = 120000;   // receptor x ligand atoms up to which GLOBAL stays on the fp32 path
 static int g_direct_mode = 0;                     // 0 auto, 1 pose kernel always, 2 item kernel for every pose list
 void direct_set_mode(int mode) { g_direct_mode = mode; }
@@ -1111,24 +1103,23 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     }
     const int end_bit = 31;          // keys 0 .. 2^30 (2^30 = beyond the lattice)
 
-    // scratch arena (grow-only, reused by every call: cudaMalloc/cudaFree of ~45 B per item would cost more than the kernels)
+    // scratch arena (grow-only, reused by every call: cudaMalloc/cudaFree of ~65 B per item would cost more than the kernels)
     size_t temp_bytes = 0;
     MMO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                              (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n_items, 0, end_bit, R.stream));
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t need = up(n_items * 16) + up(n_items * 8) + 4 * up(n_items * 4) + up(n_items) + up(temp_bytes);
+    const size_t need = up(n_items * 32) + 2 * up(n_items * 8) + 4 * up(n_items * 4) + up(n_items) + up(temp_bytes);
     if (g_item_scratch.n < need) MMO_TRY(g_item_scratch.alloc(need + need / 8));
     uint8_t *cur = g_item_scratch.p;
     auto carve = [&](size_t b) { uint8_t *r = cur; cur += up(b); return r; };
-    float4 *pos = (float4 *)carve(n_items * 16);
-    double *e_item = (double *)carve(n_items * 8);
+    float4 *pos = (float4 *)carve(n_items * 32);
+    double *e_item = (double *)carve(n_items * 8), *e_rank = (double *)carve(n_items * 8);
     uint32_t *keys = (uint32_t *)carve(n_items * 4), *keys2 = (uint32_t *)carve(n_items * 4);
     uint32_t *vals = (uint32_t *)carve(n_items * 4), *perm = (uint32_t *)carve(n_items * 4);
-    uint8_t *f_item = carve(n_items), *temp = carve(temp_bytes);
+    uint8_t *f_rank = carve(n_items), *temp = carve(temp_bytes);
     if (!g_work.p) MMO_TRY(g_work.alloc(64));
     MMO_CUDA(cudaMemsetAsync(g_work.p, 0, 64 * sizeof(unsigned long long), R.stream));
     MMO_CUDA(cudaMemsetAsync(e_item, 0, n_items * sizeof(double), R.stream));
-    MMO_CUDA(cudaMemsetAsync(f_item, 0, n_items, R.stream));
     unsigned long long *d_far = g_work.p + 63;
     {
         KernelScope ks(K_ITEM_PREP);
@@ -1144,7 +1135,7 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     ia.xyzq = fa.xyzq; ia.gelt = fa.gelt; ia.blob_box = fa.blob_box; ia.sup_box = rec->sup_box.p;
     ia.n_blobs = rec->n_blobs; ia.n_sup = rec->n_sup; ia.lparam = fa.lparam; ia.n_fast = nf;
     ia.pos = pos; ia.perm = perm; ia.n_far = d_far; ia.n_items = n_items;
-    ia.hscale = fa.hscale; ia.e_item = e_item; ia.f_item = f_item; ia.stats = fa.stats;
+    ia.hscale = fa.hscale; ia.e_rank = e_rank; ia.f_rank = f_rank; ia.stats = fa.stats;
     MMO_REQUIRE(rec->n_blobs < 65535, "receptor too large for the direct kernel (%d atoms)", rec->n);
     const int near_cap = (rec->n_blobs + 8 + 7) & ~7;
     const size_t smem = ((size_t)2 * rec->n_sup + (size_t)nf) * sizeof(float4) + 16 * sizeof(float2) +
@@ -1166,13 +1157,13 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     KernelScope ks2(K_HARD_FIX);
     // close contacts per item, in the sorted (spatially coherent) order; then the items of a pose are summed in atom order
     const unsigned iblocks = (unsigned)((n_items + 127) / 128);
-    if (shifted && collect_stats) item_fix_kernel<MMO_VARIANT_SHIFTED, true><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
-    else if (shifted) item_fix_kernel<MMO_VARIANT_SHIFTED, false><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
-    else if (collect_stats) item_fix_kernel<MMO_VARIANT_GLOBAL, true><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
-    else item_fix_kernel<MMO_VARIANT_GLOBAL, false><<<iblocks, 128, 0, R.stream>>>(xa, src, nf, perm, d_far, n_items, f_item, e_item);
+    if (shifted && collect_stats) item_fix_kernel<MMO_VARIANT_SHIFTED, true><<<iblocks, 128, 0, R.stream>>>(xa, rec->origin[0], rec->origin[1], rec->origin[2], nf, perm, pos, d_far, n_items, f_rank, e_rank, e_item);
+    else if (shifted) item_fix_kernel<MMO_VARIANT_SHIFTED, false><<<iblocks, 128, 0, R.stream>>>(xa, rec->origin[0], rec->origin[1], rec->origin[2], nf, perm, pos, d_far, n_items, f_rank, e_rank, e_item);
+    else if (collect_stats) item_fix_kernel<MMO_VARIANT_GLOBAL, true><<<iblocks, 128, 0, R.stream>>>(xa, rec->origin[0], rec->origin[1], rec->origin[2], nf, perm, pos, d_far, n_items, f_rank, e_rank, e_item);
+    else item_fix_kernel<MMO_VARIANT_GLOBAL, false><<<iblocks, 128, 0, R.stream>>>(xa, rec->origin[0], rec->origin[1], rec->origin[2], nf, perm, pos, d_far, n_items, f_rank, e_rank, e_item);
     MMO_LAUNCH_CHECK();
     const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
-    hard_fix_kernel<MMO_VARIANT_SHIFTED, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, f_item, 1, 0, d_out);
+    hard_fix_kernel<MMO_VARIANT_SHIFTED, false, true><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, e_item, nf, nullptr, 1, 0, d_out);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }
