@@ -581,11 +581,10 @@ __global__ void __launch_bounds__(256)
 item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const double *__restrict__ lx, const double *__restrict__ ly,
                     const double *__restrict__ lz, const int32_t *__restrict__ forder, const float4 *__restrict__ lparam,
                     double ox, double oy, double oz, float cell_lo_x, float cell_lo_y, float cell_lo_z, float cell_inv,
-                    int nx, int ny, int nz, float4 *__restrict__ pos, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                    int nx, int ny, int nz, uint32_t far_key, float4 *__restrict__ pos, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                     unsigned long long *__restrict__ n_far) {
     const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_items = n_poses * n_fast;
-    const uint32_t far_key = 1u << 30;        // beyond every Morton code of 3 x 10 bits
     uint32_t key = far_key;
     if (it < n_items) {
         const int64_t p = it / n_fast;
@@ -1097,11 +1096,16 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     int nd[3];
     for (;;) {
         bool ok = true;
-        for (int d = 0; d < 3; d++) { nd[d] = std::max(1, (int)ceilf((hi[d] - lo[d]) / cell)); ok = ok && nd[d] <= 1024; }
+        for (int d = 0; d < 3; d++) { nd[d] = std::max(1, (int)ceilf((hi[d] - lo[d]) / cell)); ok = ok && nd[d] <= 1023; }
         if (ok) break;
         cell *= 1.25f;
     }
-    const int end_bit = 31;          // keys 0 .. 2^30 (2^30 = beyond the lattice)
+    // the sort only looks at the bits the lattice needs: b per axis with every nd <= 2^b - 1, so that the all-ones code is
+    // free for "beyond the lattice" (sorted last) -- 24 bits = three radix passes for a lattice of up to 255 cells per axis
+    int axis_bits = 1;
+    while (std::max(nd[0], std::max(nd[1], nd[2])) > (1 << axis_bits) - 1) axis_bits++;
+    const int end_bit = 3 * axis_bits;
+    const uint32_t far_key = (1u << end_bit) - 1u;
 
     // scratch arena (grow-only, reused by every call: cudaMalloc/cudaFree of ~65 B per item would cost more than the kernels)
     size_t temp_bytes = 0;
@@ -1125,7 +1129,7 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
         KernelScope ks(K_ITEM_PREP);
         item_prepare_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, R.stream>>>(
             src, n_poses, lig->n, nf, lig->fx.p, lig->fy.p, lig->fz.p, lig->forder.p, lig->fparam.p, rec->origin[0], rec->origin[1],
-            rec->origin[2], lo[0], lo[1], lo[2], 1.0f / cell, nd[0], nd[1], nd[2], pos, keys, vals, d_far);
+            rec->origin[2], lo[0], lo[1], lo[2], 1.0f / cell, nd[0], nd[1], nd[2], far_key, pos, keys, vals, d_far);
         MMO_LAUNCH_CHECK();
         MMO_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys2, vals, perm, (int64_t)n_items, 0, end_bit, R.stream));
         count_launch(3);
