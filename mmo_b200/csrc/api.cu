@@ -30,6 +30,41 @@ int d2h_sync(void *host, const void *dev, size_t bytes) {
     return MMO_OK;
 }
 
+// Host arrays of one call -> ONE device buffer (dev[i] = start of array i), and no host synchronisation in between: the
+// call's closing d2h_sync orders everything.  Small inputs (single-pose calls: the reference's closures are
+// Mol.t -> float) are packed into a pinned staging buffer and travel as one copy.
+constexpr size_t kStageBytes = 64 * 1024;
+int upload_parts(DevBuf<double> &buf, int n, const double *const *host, const size_t *count, const double **dev) {
+    Runtime &R = rt();
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += count[i];
+    MMO_TRY(buf.alloc(total));
+    size_t off = 0;
+    for (int i = 0; i < n; i++) { dev[i] = buf.p + off; off += count[i]; }
+    if (total * sizeof(double) <= kStageBytes) {
+        if (!R.stage) MMO_CUDA(cudaHostAlloc(&R.stage, kStageBytes, cudaHostAllocDefault));
+        // the previous call that used the staging buffer ended with a stream synchronisation
+        off = 0;
+        for (int i = 0; i < n; i++) { memcpy((double *)R.stage + off, host[i], count[i] * sizeof(double)); off += count[i]; }
+        if (total) MMO_CUDA(cudaMemcpyAsync(buf.p, R.stage, total * sizeof(double), cudaMemcpyHostToDevice, R.stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            if (count[i]) MMO_CUDA(cudaMemcpyAsync((double *)dev[i], host[i], count[i] * sizeof(double), cudaMemcpyHostToDevice, R.stream));
+        MMO_CUDA(cudaStreamSynchronize(R.stream));      // pageable sources: the caller may reuse them after we return
+    }
+    return MMO_OK;
+}
+int upload_xyz(DevBuf<double> &buf, const double *xs, const double *ys, const double *zs, size_t m, const double **dev) {
+    const double *h[3] = {xs, ys, zs};
+    const size_t c[3] = {m, m, m};
+    return upload_parts(buf, 3, h, c, dev);
+}
+int upload_rt(DevBuf<double> &buf, const double *rot9, const double *trans3, size_t n_poses, const double **dev) {
+    const double *h[2] = {rot9, trans3};
+    const size_t c[2] = {n_poses * 9, n_poses * 3};
+    return upload_parts(buf, 2, h, c, dev);
+}
+
 PoseSrc coords_src(const double *x, const double *y, const double *z) {
     PoseSrc s = {};
     s.kind = 1;
@@ -57,10 +92,11 @@ int mmo_score_coords(const mmo_receptor *rec, const mmo_ligand *lig, int variant
     if (n_poses == 0) return MMO_OK;
     MMO_REQUIRE(xs && ys && zs && out_E, "mmo_score_coords: null buffer");
     const size_t m = (size_t)n_poses * lig->n;
-    DevBuf<double> dx, dy, dz, dE;
-    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    DevBuf<double> dxyz, dE;
+    const double *d[3];
+    MMO_TRY(upload_xyz(dxyz, xs, ys, zs, m, d));
     MMO_TRY(dE.alloc((size_t)n_poses));
-    MMO_TRY(run_direct(rec, lig, variant, prec, coords_src(dx.p, dy.p, dz.p), n_poses, dE.p));
+    MMO_TRY(run_direct(rec, lig, variant, prec, coords_src(d[0], d[1], d[2]), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
 } MMO_CATCH_ALL
 
@@ -72,11 +108,11 @@ int mmo_score_poses(const mmo_receptor *rec, const mmo_ligand *lig, int variant,
     MMO_REQUIRE(n_poses >= 0, "mmo_score_poses: negative pose count");
     if (n_poses == 0) return MMO_OK;
     MMO_REQUIRE(rot9 && trans3 && out_E, "mmo_score_poses: null buffer");
-    DevBuf<double> dr, dt, dE;
-    MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
-    MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
+    DevBuf<double> drt, dE;
+    const double *d[2];
+    MMO_TRY(upload_rt(drt, rot9, trans3, (size_t)n_poses, d));
     MMO_TRY(dE.alloc((size_t)n_poses));
-    MMO_TRY(run_direct(rec, lig, variant, prec, rt_src(dr.p, dt.p), n_poses, dE.p));
+    MMO_TRY(run_direct(rec, lig, variant, prec, rt_src(d[0], d[1]), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
 } MMO_CATCH_ALL
 
@@ -130,10 +166,11 @@ int mmo_intra_nb(const mmo_ligand *lig, int64_t n_confs, const double *xs, const
     if (n_confs == 0) return MMO_OK;
     MMO_REQUIRE(xs && ys && zs && out_E, "mmo_intra_nb: null buffer");
     const size_t m = (size_t)n_confs * lig->n;
-    DevBuf<double> dx, dy, dz, dE;
-    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    DevBuf<double> dxyz, dE;
+    const double *d[3];
+    MMO_TRY(upload_xyz(dxyz, xs, ys, zs, m, d));
     MMO_TRY(dE.alloc((size_t)n_confs));
-    MMO_TRY(launch_intra_fp64(lig, n_confs, dx.p, dy.p, dz.p, dE.p));
+    MMO_TRY(launch_intra_fp64(lig, n_confs, d[0], d[1], d[2], dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_confs * sizeof(double));
 } MMO_CATCH_ALL
 
@@ -335,10 +372,11 @@ int mmo_score_interp_coords(const mmo_grid *grid, const mmo_ligand *lig, int64_t
     if (n_poses == 0) return MMO_OK;
     MMO_REQUIRE(xs && ys && zs && out_E, "mmo_score_interp_coords: null buffer");
     const size_t m = (size_t)n_poses * lig->n;
-    DevBuf<double> dx, dy, dz, dE;
-    MMO_TRY(dx.upload(xs, m)); MMO_TRY(dy.upload(ys, m)); MMO_TRY(dz.upload(zs, m));
+    DevBuf<double> dxyz, dE;
+    const double *d[3];
+    MMO_TRY(upload_xyz(dxyz, xs, ys, zs, m, d));
     MMO_TRY(dE.alloc((size_t)n_poses));
-    MMO_TRY(launch_interp(grid, lig, coords_src(dx.p, dy.p, dz.p), n_poses, dE.p));
+    MMO_TRY(launch_interp(grid, lig, coords_src(d[0], d[1], d[2]), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
 } MMO_CATCH_ALL
 
@@ -349,11 +387,11 @@ int mmo_score_interp_poses(const mmo_grid *grid, const mmo_ligand *lig, int64_t 
     MMO_REQUIRE(n_poses >= 0, "mmo_score_interp_poses: negative pose count");
     if (n_poses == 0) return MMO_OK;
     MMO_REQUIRE(rot9 && trans3 && out_E, "mmo_score_interp_poses: null buffer");
-    DevBuf<double> dr, dt, dE;
-    MMO_TRY(dr.upload(rot9, (size_t)n_poses * 9));
-    MMO_TRY(dt.upload(trans3, (size_t)n_poses * 3));
+    DevBuf<double> drt, dE;
+    const double *d[2];
+    MMO_TRY(upload_rt(drt, rot9, trans3, (size_t)n_poses, d));
     MMO_TRY(dE.alloc((size_t)n_poses));
-    MMO_TRY(launch_interp(grid, lig, rt_src(dr.p, dt.p), n_poses, dE.p));
+    MMO_TRY(launch_interp(grid, lig, rt_src(d[0], d[1]), n_poses, dE.p));
     return d2h_sync(out_E, dE.p, (size_t)n_poses * sizeof(double));
 } MMO_CATCH_ALL
 

@@ -42,6 +42,7 @@ struct Runtime {
     int64_t launches = 0;
     int64_t stat_pairs = 0, stat_inside = 0, stat_fp64 = 0, stat_flagged = 0;
     bool collect_stats = false;
+    void *stage = nullptr;           // pinned staging buffer of the small host->device copies (api.cu)
     int epoch = 0;                   // bumped by every mmo_init: device-resident caches of an older epoch are stale
 };
 Runtime &rt();

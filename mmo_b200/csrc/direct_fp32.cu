@@ -189,15 +189,16 @@ __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const 
 // TILED: the (ROI) receptor fits one shared-memory tile (<= 2048 atoms: C2).  Otherwise the groups are read through L1
 // (read-only path) and culled in two stages over super-groups of 32, as in the item kernel: ONE launch for a receptor of
 // any size instead of one per tile, each of which decoded the poses and re-derived the ligand coordinates again.
-template <int VARIANT, bool STATS, bool TILED>
+template <int VARIANT, bool STATS, bool TILED, bool SLICED>
 __global__ void __launch_bounds__(TPB, kBlocksPerSM)
-direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int tile_groups, int n_split, int near_cap,
-                   unsigned long long *__restrict__ work, double *__restrict__ out, uint8_t *__restrict__ flags) {
-    // Persistent blocks (2 per SM), one launch per receptor tile [b0, b0 + nb) of groups.  A work unit is
-    // (64 consecutive poses, chunk split y): the warp that draws it sums the ligand chunks c = y, y + n_split, ...
-    // of those poses into out[y * n_poses + p]; units are handed out through one atomic counter, so warps never
-    // wait for each other and the tail of the launch is one unit long.  The splits (and tiles) are added in a
-    // fixed order by hard_fix_kernel.
+direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int tile_groups, int n_split, int n_slices,
+                   int near_cap, unsigned long long *__restrict__ work, double *__restrict__ out, uint8_t *__restrict__ flags) {
+    // Persistent blocks (1 per SM), one launch for the receptor groups [b0, b0 + nb).  A work unit is
+    // (64 consecutive poses, chunk split y, receptor slice sl): the warp that draws it sums the ligand chunks c = y,
+    // y + n_split, ... of those poses against the groups of slice sl into out[(sl * n_split + y) * n_poses + p]; units are
+    // handed out through one atomic counter, so warps never wait for each other and the tail of the launch is one unit
+    // long.  The parts are added in a fixed order by the fix kernel.  n_slices > 1 only for small batches (a single
+    // pose is 12 chunks x 8 slices = 96 warps instead of 12): the slices are what the fix kernels call tiles.
     extern __shared__ float4 smem4[];
     const int tile_atoms = tile_groups * kBlob;
     float4 *s_atom = smem4;                                   // tile_atoms + kBlob (a dummy group of far-away atoms)
@@ -230,7 +231,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
     __syncthreads();
     const int n_chunks = a.n_fast / LJ;
     const unsigned long long n_groups = (unsigned long long)((n_poses + 32 * PPT - 1) / (32 * PPT));
-    const unsigned long long n_units = n_groups * (unsigned long long)n_split;
+    const unsigned long long n_units = n_groups * (unsigned long long)n_split * (unsigned long long)n_slices;
     unsigned long long n_eval = 0, n_in_tot = 0;
 #ifdef MMO_EXPERIMENT_NOCULL
     bool exp_have_list = false;
@@ -241,8 +242,12 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
         if (lane == 0) u = atomicAdd(work, 1ull);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
-        const int y = (int)(u / n_groups);
-        const int64_t p0 = (int64_t)(u - (unsigned long long)y * n_groups) * (32 * PPT) + lane;
+        const int yz = (int)(u / n_groups);
+        // SLICED is a template parameter so that the throughput path (one slice) keeps its code: measured, the run-time
+        // form cost direct_fp32_kernel 2 % on C2
+        const int sl = SLICED ? yz / n_split : 0, y = yz - sl * n_split;
+        const int g_lo = SLICED ? nb * sl / n_slices : 0, g_hi = SLICED ? nb * (sl + 1) / n_slices : nb;    // this unit's groups
+        const int64_t p0 = (int64_t)(u - (unsigned long long)yz * n_groups) * (32 * PPT) + lane;
         int64_t pp[PPT];
         bool valid[PPT];
         double acc[PPT];
@@ -343,7 +348,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
 #pragma unroll
                     for (int r = 0; r < MAX_TILE_GROUPS / 32; r++) {
                         const int g = r * 32 + lane;
-                        bool near = g < nb;
+                        bool near = g >= g_lo && g < g_hi;
                         if (VARIANT == MMO_VARIANT_SHIFTED && near) {
                             const float4 blo = s_box[g * 2], bhi = s_box[g * 2 + 1];
                             const float gx = fmaxf(0.f, fmaxf(blo.x - cx, cx - bhi.x));
@@ -371,7 +376,7 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
                         while (sm) {
                             const int g = (s0 + __ffs(sm) - 1) * 32 + lane;
                             sm &= sm - 1u;
-                            bool near = g < nb;
+                            bool near = g >= g_lo && g < g_hi;
                             if (VARIANT == MMO_VARIANT_SHIFTED && near) near = box_near(__ldg(a.blob_box + 2 * g), __ldg(a.blob_box + 2 * g + 1));
                             const unsigned gm = __ballot_sync(0xffffffffu, near);
                             if (near) s_near[ng + __popc(gm & lt_mask)] = (uint16_t)g;
@@ -439,17 +444,17 @@ direct_fp32_kernel(FastArgs a, PoseSrc src, int64_t n_poses, int b0, int nb, int
 #pragma unroll
                 for (int h = 0; h < PPT; h++) cbits[h] |= (rmin[h] < Hj * 1.001f + 0.01f ? 1u : 0u) << jj;
             }
-            // close-contact flags of this (tile, chunk): one byte per pose, read by hard_fix_kernel
+            // close-contact flags of this (slice, chunk): one byte per pose, read by the fix kernel
 #pragma unroll
             for (int h = 0; h < PPT; h++) {
                 if (valid[h])
-                    flags[(int64_t)c * n_poses + p0 + 32 * h] = (uint8_t)cbits[h];
+                    flags[((int64_t)sl * n_chunks + c) * n_poses + p0 + 32 * h] = (uint8_t)cbits[h];
             }
             __syncwarp();    // the warp's s_c columns are rewritten by the next chunk
         }
 #pragma unroll
         for (int h = 0; h < PPT; h++) {
-            if (valid[h]) out[(int64_t)y * n_poses + p0 + 32 * h] = acc[h];
+            if (valid[h]) out[(int64_t)yz * n_poses + p0 + 32 * h] = acc[h];
             if (STATS && valid[h]) n_in_tot += n_in[h];
         }
     }
@@ -968,6 +973,48 @@ hard_fix_kernel(FixArgs a, PoseSrc src, int64_t n_poses, const double *part, int
     if (STATS) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, n_flag); }
 }
 
+// Small batches (single-pose calls, the reference's closure shape): block = pose, thread = ligand atom.  One thread per
+// pose walking its 48 flagged atoms one after the other is ~70 us of dependent loads; here every flagged atom has its own
+// thread, the corrections meet in shared memory and thread 0 adds the parts and then the corrections in atom order -- the
+// same additions in the same order as hard_fix_kernel (an unflagged atom adds 0.0), hence the same bits.
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(64)
+pose_fix_block_kernel(FixArgs a, PoseSrc src, int64_t n_poses, int n_fast, const double *part, int n_parts,
+                      const uint8_t *__restrict__ flags, int n_tiles, int n_chunks, double *out) {   // part may alias out
+    extern __shared__ double s_corr[];       // n_fast
+    const int64_t p = blockIdx.x;
+    unsigned long long n_fix = 0, n_flag = 0;
+    for (int k = threadIdx.x; k < n_fast; k += blockDim.x) {
+        const int c = k / kFixLJ, jj = k - c * kFixLJ;
+        unsigned bits = 0u;
+        for (int t = 0; t < n_tiles; t++) bits |= flags[((int64_t)t * n_chunks + c) * n_poses + p];
+        double corr = 0.0;
+        if ((bits >> jj) & 1u) {
+            const int j = __ldg(a.forder + k);
+            double x, y, z;
+            if (src.kind == 1) {
+                x = src.xs[p * a.L + j]; y = src.ys[p * a.L + j]; z = src.zs[p * a.L + j];
+            } else {
+                PoseRT P;
+                load_pose_rt(src, p, P);
+                pose_atom_rt(P, __ldg(a.lx + j), __ldg(a.ly + j), __ldg(a.lz + j), x, y, z);
+            }
+            corr = close_contact_corr<VARIANT, STATS>(a, x, y, z, j, n_fix);
+            if (STATS) n_flag++;
+        }
+        s_corr[k] = corr;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int k = 0; k < n_parts; k++) e += part[(int64_t)k * n_poses + p];
+        double corr = 0.0;
+        for (int k = 0; k < n_fast; k++) corr += s_corr[k];
+        out[p] = e + corr;
+    }
+    if (STATS && (n_fix | n_flag)) { atomicAdd(a.stats + 2, n_fix); atomicAdd(a.stats + 3, n_flag); }
+}
+
 // Item mode: the same correction with thread = ITEM in cell-sorted order (the order direct_items_kernel works in).  The
 // lanes of a warp then sit in neighbouring voxels: their candidate lists are the same few cache lines and about equally
 // long, which a warp of unrelated conformers (thread = pose) has neither of.  Everything read per item is either
@@ -1000,6 +1047,7 @@ item_fix_kernel(FixArgs a, double ox, double oy, double oz, int n_fast, const ui
 static DevBuf<double4> &g_fixtab = *new DevBuf<double4>();                   // FixArgs::tab
 static DevBuf<unsigned long long> &g_stats = *new DevBuf<unsigned long long>(), &g_work = *new DevBuf<unsigned long long>();
 static DevBuf<uint8_t> &g_item_scratch = *new DevBuf<uint8_t>();             // item mode scratch arena
+constexpr int64_t kPoseFixBlockMax = 4096;       // poses up to which the fp64 pass runs block = pose (latency), thread = pose beyond
 constexpr int64_t kItemModeMin = 32768;          // items (poses x ligand atoms) from which item mode pays
 constexpr int64_t kItemBatch = (int64_t)64 << 20;  // items per batch: ~65 B of scratch each (4.4 GB)
 constexpr int64_t kGlobalFp32MaxPairs = 120000;   // receptor x ligand atoms up to which GLOBAL stays on the fp32 path
@@ -1047,14 +1095,22 @@ static int set_fast_smem(size_t smem) {
     static int done_epoch = -1;
     if (done_epoch != rt().epoch) { done = 0; done_epoch = rt().epoch; }      // function attributes are per context
     if (smem <= done) return MMO_OK;
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_SHIFTED, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMO_CUDA(cudaFuncSetAttribute(direct_fp32_kernel<MMO_VARIANT_GLOBAL, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = smem;
     return MMO_OK;
 }
@@ -1246,9 +1302,11 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
     const int64_t n_groups = (n_poses + 32 * PPT - 1) / (32 * PPT);
     const int64_t resident_warps = (int64_t)kBlocksPerSM * R.sm_count * (TPB / 32);
     const int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (20 * resident_warps + n_groups - 1) / n_groups));
-    const int64_t n_units = n_groups * n_split;
+    // small batches (single-pose calls: the reference's closure shape) also split the receptor, so that one pose is
+    // ~100 warps of work and not 12
+    const int n_tiles = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, std::max(1, rec->n_blobs / 8)), resident_warps / (2 * n_groups * n_split)));
+    const int64_t n_units = n_groups * n_split * n_tiles;
     const unsigned blocks = (unsigned)std::min<int64_t>((int64_t)kBlocksPerSM * R.sm_count, (n_units + TPB / 32 - 1) / (TPB / 32));
-    const int n_tiles = 1;
     const int n_parts = n_tiles * n_split;
     DevBuf<double> part;
     if (n_parts > 1) MMO_TRY(part.alloc((size_t)n_parts * (size_t)n_poses));
@@ -1267,7 +1325,11 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
             double *o = d_part;
             uint8_t *f = flags.p;
             unsigned long long *w = g_work.p;
-#define MMO_LAUNCH_K1(V, S_, T_) direct_fp32_kernel<V, S_, T_><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, near_cap, w, o, f)
+#define MMO_LAUNCH_K1(V, S_, T_)                                                                                                   \
+    do {                                                                                                                           \
+        if (n_tiles > 1) direct_fp32_kernel<V, S_, T_, true><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, n_tiles, near_cap, w, o, f); \
+        else direct_fp32_kernel<V, S_, T_, false><<<blocks, TPB, smem, R.stream>>>(fa, src, n_poses, b0, nb, tile_blobs, n_split, 1, near_cap, w, o, f); \
+    } while (0)
             if (tiled) {
                 if (shifted && collect_stats) MMO_LAUNCH_K1(MMO_VARIANT_SHIFTED, true, true);
                 else if (shifted) MMO_LAUNCH_K1(MMO_VARIANT_SHIFTED, false, true);
@@ -1285,6 +1347,15 @@ int launch_direct_fp32(const mmo_receptor *rec, const mmo_ligand *lig, int varia
         }
         KernelScope ks2(K_HARD_FIX);
         const unsigned fblocks = (unsigned)((n_poses + 127) / 128);
+        if (n_poses <= kPoseFixBlockMax) {
+            const unsigned pb = (unsigned)n_poses;
+            const size_t sm = (size_t)lig->n_fast * sizeof(double);
+            MMO_REQUIRE(sm <= 48 * 1024, "ligand too large for the direct kernel (%d atoms)", lig->n);
+            if (shifted && collect_stats) pose_fix_block_kernel<MMO_VARIANT_SHIFTED, true><<<pb, 64, sm, R.stream>>>(xa, src, n_poses, lig->n_fast, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+            else if (shifted) pose_fix_block_kernel<MMO_VARIANT_SHIFTED, false><<<pb, 64, sm, R.stream>>>(xa, src, n_poses, lig->n_fast, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+            else if (collect_stats) pose_fix_block_kernel<MMO_VARIANT_GLOBAL, true><<<pb, 64, sm, R.stream>>>(xa, src, n_poses, lig->n_fast, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+            else pose_fix_block_kernel<MMO_VARIANT_GLOBAL, false><<<pb, 64, sm, R.stream>>>(xa, src, n_poses, lig->n_fast, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
+        } else
         if (shifted && collect_stats) hard_fix_kernel<MMO_VARIANT_SHIFTED, true, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
         else if (shifted) hard_fix_kernel<MMO_VARIANT_SHIFTED, false, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);
         else if (collect_stats) hard_fix_kernel<MMO_VARIANT_GLOBAL, true, false><<<fblocks, 128, 0, R.stream>>>(xa, src, n_poses, d_part, n_parts, flags.p, n_tiles, n_chunks, d_out);

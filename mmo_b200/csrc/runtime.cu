@@ -271,6 +271,8 @@ int mmo_shutdown(void) try {
     mc_drop_caches();
     pool_trim();
     if (R.l2_scratch) cudaFree(R.l2_scratch);
+    if (R.stage) cudaFreeHost(R.stage);
+    R.stage = nullptr;
     R.l2_scratch = nullptr;
     R.l2_scratch_bytes = 0;
     cudaEventDestroy(R.ev0);

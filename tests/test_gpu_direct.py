@@ -102,6 +102,28 @@ def test_fp32_coherent_warps_within_tolerance(gpu, orc, c2, c2_roi_rec, handles,
         assert (ratio <= 1.0).all(), f"worst ratio {ratio.max()} at E={want[ratio.argmax()]}"
 
 
+@pytest.mark.parametrize("n", [1, 2, 63, 65, 700, 4096, 4097])
+def test_fp32_small_batches_receptor_slices_and_block_fix(gpu, orc, c2, c2_roi_rec, handles, n):
+    """single-pose calls (the reference's closure shape) and other small batches split the receptor into slices and run
+    the fp64 pass with block = pose: same contract on both sides of the two thresholds, coordinates and rot/trans input,
+    and the result of a pose does not depend on where in the batch it sits (the parts are added in a fixed order)"""
+    rec, lig = handles
+    m = c2["lig"]
+    R, t = _poses(c2, n, seed=100 + n)
+    X, Y, Z = orc.pose_coords(lig.xs, lig.ys, lig.zs, R, t)
+    for shifted, variant in ((True, gpu.VARIANT_SHIFTED), (False, gpu.VARIANT_GLOBAL)):
+        want = orc.ene_inter(c2_roi_rec, m.q, m.anum, X, Y, Z, shifted=shifted)
+        got = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP32)
+        ratio = np.abs(got - want) / np.maximum(1e-6 * np.abs(want), 1e-4)
+        assert (ratio <= 1.0).all(), f"n={n} shifted={shifted}: worst ratio {ratio.max()} at E={want[ratio.argmax()]}"
+        got_c = gpu.Mol._score(rec, lig, variant, gpu.PREC_FP32, X, Y, Z)
+        assert tol_ok(got_c, want).all()
+        again = gpu.Mol.score_poses(rec, lig, R, t, variant=variant, prec=gpu.PREC_FP32)
+        assert np.array_equal(got, again)                       # deterministic
+    one = np.atleast_1d(gpu.Mol.ene_inter_UFF_shifted_brute(rec, lig, X[0], Y[0], Z[0]))
+    assert tol_ok(one, orc.ene_inter(c2_roi_rec, m.q, m.anum, X[:1], Y[:1], Z[:1], shifted=True)).all()
+
+
 def test_fp32_far_away_pose_is_exactly_zero(gpu, c2, handles, direct_mode):
     rec, lig = handles
     t = np.array([[c2["roi"][0] + 80.0, c2["roi"][1], c2["roi"][2]]])
