@@ -21,8 +21,11 @@ lig = mmo_b200.Ligand.from_mol(c2["lig"], centered=True)
 R, t = workloads.random_poses_in_sphere(600, c2["roi"][:3], 6.0, seed=3)
 if "direct" in which:        # pose kernel + hard_fix (close contacts), both variants
     mmo_b200.lib().mmo_direct_set_mode(1)
-    mmo_b200.Mol.score_poses(rec, lig, R, t)
+    mmo_b200.Mol.score_poses(rec, lig, R, t)                     # receptor slices + fp64 pass with block = pose
     mmo_b200.Mol.score_poses(rec, lig, R[:100], t[:100], variant=mmo_b200.VARIANT_GLOBAL)
+    mmo_b200.Mol.score_poses(rec, lig, R[:1], t[:1])             # the single-pose call (pinned staging upload)
+    R5, t5 = workloads.random_poses_in_sphere(4200, c2["roi"][:3], 6.0, seed=6)
+    mmo_b200.Mol.score_poses(rec, lig, R5, t5)                   # one slice + fp64 pass with thread = pose
     mmo_b200.lib().mmo_direct_set_mode(0)
 if "items" in which:         # item kernel: prepare, sort, direct_items_kernel, item_fix, per-pose sum; 10 000-atom receptor
     rec5_m = workloads.synthetic_receptor(3000, "sphere", 22.0, seed=5, origin=(40.0, 40.0, 40.0))
