@@ -11,3 +11,6 @@ for tool in memcheck racecheck synccheck initcheck; do
   timeout 900 compute-sanitizer --tool $tool $extra --print-limit 20 python tools/sanitize_driver.py > $out 2>&1
   echo "== $tool: exit $? =="; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_driver done|Error:|Race reported|hazard" $out | sort | uniq -c | head -12
 done
+# which kernels those invocations launch (the driver under the ncu launch list)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_sanitizer_driver_launches.csv python tools/sanitize_driver.py > /dev/null 2>&1
+echo "== driver launch list: $(wc -l < gpurun_out/${tag}_sanitizer_driver_launches.csv) lines =="
