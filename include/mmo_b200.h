@@ -81,6 +81,9 @@ int mmo_measure_hbm_copy(double *gbs);
 /* the gather roof of the interpolated lookup (K4): 8-corner reads of pseudo-random cells of T type-major f32 maps of
  * the given dims (L2 resident when they fit), no arithmetic; lookups/s (x 32 B = gathered bytes/s) */
 int mmo_measure_l2_gather(const int32_t dims[3], int32_t T, double *lookups_per_s);
+/* the same for the layout the lookup kernel actually reads: the z-pair copy of the maps ({v[k], v[k+1]} as one 8-byte
+ * element), four 8-byte reads in two rows of x per lookup */
+int mmo_measure_l2_gather_zpair(const int32_t dims[3], int32_t T, double *lookups_per_s);
 /* raw device buffers, so that a caller can keep pose batches resident in HBM */
 int mmo_dev_alloc(size_t bytes, void **dptr);
 int mmo_dev_free(void *dptr);

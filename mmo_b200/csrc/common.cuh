@@ -189,6 +189,11 @@ struct mmo_grid {
     int T = 0;
     size_t nvox = 0;
     mmo::DevBuf<float> maps;   // type-major: map t at maps + t*nvox
+    // look-up copy, built on the first look-up (strict_fp64.cu: grid_zpairs): zpair[t][k][j][i] = {map[k][j][i], map[k+1][j][i]}
+    // for k < z_dim - 1.  The eight corners of a trilinear cell are then four 8-byte loads in two rows of x instead of
+    // eight 4-byte loads in four: half the L2 sectors per look-up, same floats, same arithmetic.
+    mutable mmo::DevBuf<float2> zpair;
+    mutable bool zpair_ready = false;
 };
 
 struct mmo_mask {
@@ -233,6 +238,7 @@ int launch_intra_fp64(const mmo_ligand *lig, int64_t n_confs, const double *d_xs
 int launch_grid_build(const mmo_receptor *rec, const mmo_grid *g, const uint32_t *d_mask_words,
                       const int32_t *d_type_elt, const double *d_type_q, const int32_t *d_type_idx);
 int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, double *d_out);
+int grid_zpairs(const mmo_grid *g, const float2 **out);
 int launch_trilin(const mmo_grid *g, int type, int64_t n, const double *d_x, const double *d_y,
                   const double *d_z, double *d_out);
 int launch_vdw_mask(int n, const double *d_x, const double *d_y, const double *d_z, const double *d_r,

@@ -73,6 +73,29 @@ __device__ __forceinline__ double d_trilin(const GridGeom &g, const float *__res
             (double)__ldg(arr + (i0 + j1x + k1xy)) * (whx * wly * wlz));
 }
 
+// the same interpolation from the z-pair copy of the map (mmo_grid::zpair): the same eight floats, products and order of
+// additions as d_trilin, hence the same double
+__device__ __forceinline__ double d_trilin_zp(const GridGeom &g, const float2 *__restrict__ zp,
+                                              double px, double py, double pz) {
+    const int i0 = (int)(px * g.inv), j0 = (int)(py * g.inv), k0 = (int)(pz * g.inv);
+    const int i1 = i0 + 1, j1 = j0 + 1, k1 = k0 + 1;
+    if (i0 < 0 || j0 < 0 || k0 < 0 || i1 >= g.dims[0] || j1 >= g.dims[1] || k1 >= g.dims[2]) return 0.0;
+    const int j0x = j0 * g.x_dim, j1x = j1 * g.x_dim, k0xy = k0 * g.xy_dim;
+    const double lx = (double)i0 * g.q[0], ly = (double)j0 * g.q[1], lz = (double)k0 * g.q[2];
+    const double wlx = (px - lx) * g.inv, wly = (py - ly) * g.inv, wlz = (pz - lz) * g.inv;
+    const double whx = 1.0 - wlx, why = 1.0 - wly, whz = 1.0 - wlz;
+    const float2 a = __ldg(zp + (i0 + j0x + k0xy)), b = __ldg(zp + (i1 + j0x + k0xy));
+    const float2 c = __ldg(zp + (i1 + j1x + k0xy)), d = __ldg(zp + (i0 + j1x + k0xy));
+    return ((double)a.x * (whx * why * whz) +
+            (double)b.x * (wlx * why * whz) +
+            (double)c.x * (wlx * wly * whz) +
+            (double)d.x * (whx * wly * whz) +
+            (double)a.y * (whx * why * wlz) +
+            (double)b.y * (wlx * why * wlz) +
+            (double)c.y * (wlx * wly * wlz) +
+            (double)d.y * (whx * wly * wlz));
+}
+
 static inline GridGeom geom_of(const mmo_grid *g) {
     GridGeom G;
     G.inv = 1.0 / g->step;                  // grid.ml:41

@@ -423,8 +423,13 @@ __global__ void strict_trilin_kernel(GridGeom g, const float *__restrict__ arr, 
 #endif
 constexpr int kInterpUnroll = MMO_INTERP_UNROLL;
 // Mol.ene_inter_UFF_interp (mol.ml:1012-1020): res := !res +. trilin ... for j = 0 .. l-1
-__global__ void __launch_bounds__(128)
-strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
+// ZP: read the z-pair copy of the maps (maps = float2 [T][z_dim - 1][y_dim][x_dim], zvox elements per type)
+#ifndef MMO_INTERP_MINB
+#define MMO_INTERP_MINB 8
+#endif
+template <bool ZP>
+__global__ void __launch_bounds__(128, MMO_INTERP_MINB)
+strict_interp_kernel(GridGeom g, const void *__restrict__ maps_, size_t zvox, int L,
                      const double *__restrict__ lx, const double *__restrict__ ly,
                      const double *__restrict__ lz, const int32_t *__restrict__ ltyp,
                      PoseSrc src, int64_t n_poses, double *__restrict__ out) {
@@ -436,11 +441,16 @@ strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_poses) return;
     double res = 0.0;
+    const float *maps = (const float *)maps_;
+    const float2 *zmaps = (const float2 *)maps_;
+    auto look = [&](int t, double x, double y, double z) {
+        return ZP ? d_trilin_zp(g, zmaps + (size_t)t * zvox, x, y, z) : d_trilin(g, maps + (size_t)t * g.nvox, x, y, z);
+    };
     // unrolled by kInterpUnroll: the gathers of several atoms are in flight together (the kernel waits on L2), the sum keeps its order
     if (src.kind == 1) {
 #pragma unroll kInterpUnroll
         for (int j = 0; j < L; j++)
-            res = res + d_trilin(g, maps + (size_t)st[j] * g.nvox, src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
+            res = res + look(st[j], src.xs[p * L + j], src.ys[p * L + j], src.zs[p * L + j]);
     } else {
         PoseRT P;
         load_pose_rt(src, p, P);
@@ -448,10 +458,20 @@ strict_interp_kernel(GridGeom g, const float *__restrict__ maps, int L,
         for (int j = 0; j < L; j++) {
             double x, y, z;
             pose_atom_rt(P, sx[j], sy[j], sz[j], x, y, z);
-            res = res + d_trilin(g, maps + (size_t)st[j] * g.nvox, x, y, z);
+            res = res + look(st[j], x, y, z);
         }
     }
     out[p] = res;
+}
+
+// zpair[t][k][j][i] = {map[t][k][j][i], map[t][k + 1][j][i]}, k < z_dim - 1
+__global__ void __launch_bounds__(256)
+zpair_build_kernel(const float *__restrict__ maps, size_t nvox, size_t zvox, int T, float2 *__restrict__ zp, size_t xy) {
+    const size_t n = zvox * (size_t)T;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = e / zvox, v = e - t * zvox;
+        zp[e] = make_float2(__ldg(maps + t * nvox + v), __ldg(maps + t * nvox + v + xy));
+    }
 }
 
 // ---- self-test of div_by against the IEEE division (tests/test_gpu_direct.py) --------------------------------
@@ -585,15 +605,38 @@ int launch_trilin(const mmo_grid *g, int type, int64_t n, const double *d_x, con
     return MMO_OK;
 }
 
+// the z-pair look-up copy of a grid's maps, built on first use (the maps of a grid handle never change after its creation)
+int grid_zpairs(const mmo_grid *g, const float2 **out) {
+    if (!g->zpair_ready) {
+        const size_t xy = (size_t)g->dims[0] * g->dims[1], zvox = xy * (size_t)(g->dims[2] - 1);
+        MMO_TRY(g->zpair.alloc(zvox * (size_t)g->T));
+        zpair_build_kernel<<<rt().sm_count * 8, 256, 0, rt().stream>>>(g->maps.p, g->nvox, zvox, g->T, g->zpair.p, xy);
+        MMO_LAUNCH_CHECK();
+        g->zpair_ready = true;
+    }
+    *out = g->zpair.p;
+    return MMO_OK;
+}
+
 int launch_interp(const mmo_grid *g, const mmo_ligand *lig, const PoseSrc &src, int64_t n_poses, double *d_out) {
     if (n_poses == 0) return MMO_OK;
     int L = lig->n;
     size_t smem = (size_t)3 * L * sizeof(double) + (size_t)L * sizeof(int32_t) + 16;
     MMO_REQUIRE(smem <= 220 * 1024, "ligand with %d atoms is too large for the interpolation kernel", L);
-    if (smem > 48 * 1024) MMO_CUDA(cudaFuncSetAttribute(strict_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // look-ups read the z-pair copy of the maps (half the L2 sectors per look-up); MMO_INTERP_ZPAIR=0 keeps the plain maps
+    static const bool want_zp = [] { const char *e = getenv("MMO_INTERP_ZPAIR"); return !(e && e[0] == '0'); }();
+    const float2 *zp = nullptr;
+    if (want_zp) MMO_TRY(grid_zpairs(g, &zp));
+    const size_t zvox = (size_t)g->dims[0] * g->dims[1] * (g->dims[2] - 1);
+    if (smem > 48 * 1024) {
+        MMO_CUDA(cudaFuncSetAttribute(strict_interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MMO_CUDA(cudaFuncSetAttribute(strict_interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     KernelScope ks(K_INTERP);
-    strict_interp_kernel<<<(unsigned)((n_poses + 127) / 128), 128, smem, rt().stream>>>(
-        geom_of(g), g->maps.p, L, lig->x.p, lig->y.p, lig->z.p, lig->typ.p, src, n_poses, d_out);
+    if (zp) strict_interp_kernel<true><<<(unsigned)((n_poses + 127) / 128), 128, smem, rt().stream>>>(
+            geom_of(g), zp, zvox, L, lig->x.p, lig->y.p, lig->z.p, lig->typ.p, src, n_poses, d_out);
+    else strict_interp_kernel<false><<<(unsigned)((n_poses + 127) / 128), 128, smem, rt().stream>>>(
+            geom_of(g), g->maps.p, zvox, L, lig->x.p, lig->y.p, lig->z.p, lig->typ.p, src, n_poses, d_out);
     MMO_LAUNCH_CHECK();
     return MMO_OK;
 }

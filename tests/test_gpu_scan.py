@@ -309,6 +309,9 @@ def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
     lps = C.c_double()
     assert L.mmo_measure_l2_gather((C.c_int32 * 3)(81, 81, 81), C.c_int32(22), C.byref(lps)) == 0
     assert lps.value > 1e9
+    lz = C.c_double()
+    assert L.mmo_measure_l2_gather_zpair((C.c_int32 * 3)(81, 81, 81), C.c_int32(22), C.byref(lz)) == 0
+    assert lz.value > lps.value          # four 8-byte reads in two rows against eight 4-byte reads in four
 
 
 def test_scan_against_a_receptor_larger_than_one_tile(gpu, orc, c2):

@@ -117,10 +117,14 @@ def peaks(ctx, dims=(81, 81, 81), T=22):
     ctx.ck(L.mmo_measure_hbm_copy(C.byref(hbm)))
     d = (C.c_int32 * 3)(*dims)
     ctx.ck(L.mmo_measure_l2_gather(d, C.c_int32(T), C.byref(gat)))
+    gzp = C.c_double()
+    ctx.ck(L.mmo_measure_l2_gather_zpair(d, C.c_int32(T), C.byref(gzp)))
     return {"fp32_fma_tflops": fp32.value, "fp64_fma_tflops": fp64.value, "hbm_copy_gbs": hbm.value,
             "l2_gather_lookups_per_s": gat.value, "l2_gather_gbs": gat.value * 32 / 1e9,
+            "l2_gather_zpair_lookups_per_s": gzp.value, "l2_gather_zpair_gbs": gzp.value * 32 / 1e9,
             "how": "FMA chains (8 per thread, full occupancy), 1 GiB float4 copy, 8-corner gathers of random cells of 22 "
-                   "L2-resident 81^3 f32 maps (32 B per lookup); all measured in this run on this GPU"}
+                   "L2-resident 81^3 f32 maps (32 B per lookup) in the plain layout (8 x 4 B in four rows) and in the z-pair "
+                   "layout the lookup kernel reads (4 x 8 B in two rows); all measured in this run on this GPU"}
 
 
 def sphere_mask_bits(step, dims, c, r):
@@ -204,10 +208,14 @@ def leg_c3(ctx, pk, quick=False):
               "ms": out["l2_warm"], "ms_l2_flushed_before_launch": out["l2_flushed"], "poses_per_s": ctx.world * n_poses / (out["l2_warm"] * 1e-3),
               "atom_lookups_per_s": ctx.world * lps, "scaling": "weak (poses sharded, maps replicated)",
               "maps_mb": nvox * T * 4 / 1e6, "pose_stream_mb": n_poses * 104 / 1e6,
-              "roofline": {"bound": "l2_gather", "kernel": "strict_interp_kernel", "achieved": lps * 32 / 1e9, "peak": pk["l2_gather_gbs"],
-                           "unit": "GB/s", "frac": lps / pk["l2_gather_lookups_per_s"],
+              "maps_zpair_mb": nvox * T * 8 / 1e6 * (dims[2] - 1) / dims[2],
+              "roofline": {"bound": "l2_gather", "kernel": "strict_interp_kernel<zpair>", "achieved": lps * 32 / 1e9, "peak": pk["l2_gather_zpair_gbs"],
+                           "unit": "GB/s", "frac": lps / pk["l2_gather_zpair_lookups_per_s"],
+                           "frac_of_plain_layout_roof": lps / pk["l2_gather_lookups_per_s"],
                            "bytes_model": "32 B gathered per atom lookup (8 f32 corners); SURVEY 8(d)'s 48 B figure (+16 B atom record) gives "
-                                          f"{lps * 48 / 1e9:.0f} GB/s", "peak_source": "mmo_measure_l2_gather, this run"},
+                                          f"{lps * 48 / 1e9:.0f} GB/s",
+                           "peak_source": "mmo_measure_l2_gather_zpair, this run: random cells of the same maps in the layout the kernel reads "
+                                          "(frac_of_plain_layout_roof: against the 8 x 4 B gather of the reference's G3D layout)"},
               "clocks": ck.summary()}
     return build, lookup
 
