@@ -580,32 +580,51 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
     return v;
 }
 
-// position (double, then fp32 relative to the receptor origin) and lattice cell of every item; thread = item, so that
-// the 40 bytes written per item (and the coordinates read, for explicit conformers) are coalesced
+// position (double, then fp32 relative to the receptor origin) and lattice cell of every item; consecutive threads take
+// consecutive items, so that the 40 bytes written per item (and the coordinates read, for explicit conformers) are
+// coalesced, and every thread takes kPrepIPT items a block-width apart with all their coordinate loads issued before the
+// first use: the kernel waits on DRAM (three dependent-address loads per item), not on arithmetic
+constexpr int kPrepIPT = 4;
 __global__ void __launch_bounds__(256)
 item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const double *__restrict__ lx, const double *__restrict__ ly,
                     const double *__restrict__ lz, const int32_t *__restrict__ forder, const float4 *__restrict__ lparam,
                     double ox, double oy, double oz, float cell_lo_x, float cell_lo_y, float cell_lo_z, float cell_inv,
                     int nx, int ny, int nz, uint32_t far_key, float4 *__restrict__ pos, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                     unsigned long long *__restrict__ n_far) {
-    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_items = n_poses * n_fast;
-    uint32_t key = far_key;
-    if (it < n_items) {
-        const int64_t p = it / n_fast;
-        const int k = (int)(it - p * n_fast);
-        float4 v = make_float4(kFarAway, kFarAway, kFarAway, 0.f), vlo = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (__ldg(&lparam[k].w) != 0.f) {
-            double x, y, z;
-            if (src.kind == 1) {
-                const int j = __ldg(forder + k);
-                x = src.xs[p * L + j]; y = src.ys[p * L + j]; z = src.zs[p * L + j];
-            } else {
-                PoseRT P;
-                load_pose_rt(src, p, P);
-                pose_atom_rt(P, __ldg(lx + k), __ldg(ly + k), __ldg(lz + k), x, y, z);
+    const int64_t base = (int64_t)blockIdx.x * (256 * kPrepIPT) + threadIdx.x;
+    double X[kPrepIPT], Y[kPrepIPT], Z[kPrepIPT];
+    bool real[kPrepIPT];
+#pragma unroll
+    for (int r = 0; r < kPrepIPT; r++) {
+        const int64_t it = base + r * 256;
+        real[r] = false;
+        X[r] = Y[r] = Z[r] = 0.0;
+        if (it < n_items) {
+            const uint32_t p = (uint32_t)it / (uint32_t)n_fast;         // a batch holds fewer than 2^32 items
+            const int k = (int)((uint32_t)it - p * (uint32_t)n_fast);
+            real[r] = __ldg(&lparam[k].w) != 0.f;
+            if (real[r]) {
+                if (src.kind == 1) {
+                    const int64_t a = (int64_t)p * L + __ldg(forder + k);
+                    X[r] = __ldg(src.xs + a); Y[r] = __ldg(src.ys + a); Z[r] = __ldg(src.zs + a);
+                } else {
+                    PoseRT P;
+                    load_pose_rt(src, (int64_t)p, P);
+                    pose_atom_rt(P, __ldg(lx + k), __ldg(ly + k), __ldg(lz + k), X[r], Y[r], Z[r]);
+                }
             }
-            const double Dx = x - ox, Dy = y - oy, Dz = z - oz;
+        }
+    }
+    unsigned n_far_lane = 0;
+#pragma unroll
+    for (int r = 0; r < kPrepIPT; r++) {
+        const int64_t it = base + r * 256;
+        if (it >= n_items) continue;
+        uint32_t key = far_key;
+        float4 v = make_float4(kFarAway, kFarAway, kFarAway, 0.f), vlo = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (real[r]) {
+            const double Dx = X[r] - ox, Dy = Y[r] - oy, Dz = Z[r] - oz;
             v.x = (float)Dx; v.y = (float)Dy; v.z = (float)Dz;
             // hi + lo carries 48 bits of the double (< 2e-13 A at 50 A): what the fp64 close-contact pass works with
             vlo.x = (float)(Dx - (double)v.x); vlo.y = (float)(Dy - (double)v.y); vlo.z = (float)(Dz - (double)v.z);
@@ -617,10 +636,11 @@ item_prepare_kernel(PoseSrc src, int64_t n_poses, int L, int n_fast, const doubl
         pos[2 * it + 1] = vlo;
         keys[it] = key;
         vals[it] = (uint32_t)it;
+        n_far_lane += key == far_key;
     }
     // one atomic per warp
-    const unsigned far = __ballot_sync(0xffffffffu, it < n_items && key == far_key);
-    if ((threadIdx.x & 31) == 0 && far) atomicAdd(n_far, (unsigned long long)__popc(far));
+    for (int o = 16; o > 0; o >>= 1) n_far_lane += __shfl_xor_sync(0xffffffffu, n_far_lane, o);
+    if ((threadIdx.x & 31) == 0 && n_far_lane) atomicAdd(n_far, (unsigned long long)n_far_lane);
 }
 
 // One launch for the whole receptor.  The receptor is NOT staged in shared memory: 64 cell-sorted items only touch the
@@ -1183,7 +1203,7 @@ static int launch_items_batch(const mmo_receptor *rec, const mmo_ligand *lig, in
     unsigned long long *d_far = g_work.p + 63;
     {
         KernelScope ks(K_ITEM_PREP);
-        item_prepare_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, R.stream>>>(
+        item_prepare_kernel<<<(unsigned)((n_items + 256 * kPrepIPT - 1) / (256 * kPrepIPT)), 256, 0, R.stream>>>(
             src, n_poses, lig->n, nf, lig->fx.p, lig->fy.p, lig->fz.p, lig->forder.p, lig->fparam.p, rec->origin[0], rec->origin[1],
             rec->origin[2], lo[0], lo[1], lo[2], 1.0f / cell, nd[0], nd[1], nd[2], far_key, pos, keys, vals, d_far);
         MMO_LAUNCH_CHECK();
