@@ -356,7 +356,11 @@ def leg_fp64_scan(ctx, job_params, n_active, pps, n_rot, quick=False):
     P = job_params
     P.prec = mmo_b200.PREC_FP64
     job = C.c_void_p()
-    ctx.ck(L.mmo_scan_create(C.byref(P), 0, C.byref(job)))
+    try:
+        ctx.ck(L.mmo_scan_create(C.byref(P), 0, C.byref(job)))
+    except Exception:
+        P.prec = mmo_b200.PREC_FP32
+        raise
     n_slabs = n_active // pps
     steps = 3 if quick else 8
     sl = [int((s * ctx.world + ctx.rank + 0.5) * n_slabs / ((steps + 1) * ctx.world)) for s in range(steps + 1)]
@@ -396,7 +400,11 @@ def leg_grid_scan(ctx, job_params, n_active, pps, n_rot, quick=False):
     old_rec, old_grid = P.rec, P.grid
     P.rec, P.grid = None, grid.h
     job = C.c_void_p()
-    ctx.ck(L.mmo_scan_create(C.byref(P), 0, C.byref(job)))
+    try:
+        ctx.ck(L.mmo_scan_create(C.byref(P), 0, C.byref(job)))
+    except Exception:
+        P.rec, P.grid = old_rec, old_grid
+        raise
     n_slabs = n_active // pps
     steps = 4 if quick else 16
     sl = [int((s * ctx.world + ctx.rank + 0.5) * n_slabs / ((steps + 1) * ctx.world)) for s in range(steps + 1)]
@@ -488,22 +496,32 @@ def run_all(ctx, quick=False, scan_params=None, n_active=0, pps=8, n_rot=0, only
     t0 = time.perf_counter()
     pk = peaks(ctx)
     out["peaks"] = pk
-    if only in (None, "c3"):
-        out["c3_grid_build"], out["c3_lookup"] = leg_c3(ctx, pk, quick)
-    if only in (None, "c4"):
-        out["c4_mc"] = leg_c4(ctx, quick)
-    if only in (None, "c5"):
-        out["c5_screen"] = leg_c5(ctx, pk, quick)
-    if only == "n4":
-        out["n4_desolvation"] = leg_n4(ctx, quick)
-    if only in (None, "closure") and ctx.rank == 0:
-        out["single_pose_calls"] = leg_closure(ctx, quick)
-    if scan_params is not None:
-        out["c2_fp64_scan"] = leg_fp64_scan(ctx, scan_params, n_active, pps, n_rot, quick)
+
+    def leg(names, fn):
+        # a leg that fails must not take the headline line (or the other legs) with it: its error is reported in its place
         try:
-            out["c2_grid_scan"] = leg_grid_scan(ctx, scan_params, n_active, pps, n_rot, quick)
-        except Exception as e:      # an optional leg must not take the headline line with it
-            out["c2_grid_scan"] = {"error": repr(e)}
+            res = fn()
+        except Exception as e:
+            res = tuple({"error": repr(e)} for _ in names) if len(names) > 1 else {"error": repr(e)}
+        if len(names) > 1:
+            for n, r in zip(names, res):
+                out[n] = r
+        else:
+            out[names[0]] = res
+
+    if only in (None, "c3"):
+        leg(("c3_grid_build", "c3_lookup"), lambda: leg_c3(ctx, pk, quick))
+    if only in (None, "c4"):
+        leg(("c4_mc",), lambda: leg_c4(ctx, quick))
+    if only in (None, "c5"):
+        leg(("c5_screen",), lambda: leg_c5(ctx, pk, quick))
+    if only == "n4":
+        leg(("n4_desolvation",), lambda: leg_n4(ctx, quick))
+    if only in (None, "closure") and ctx.rank == 0:
+        leg(("single_pose_calls",), lambda: leg_closure(ctx, quick))
+    if scan_params is not None:
+        leg(("c2_fp64_scan",), lambda: leg_fp64_scan(ctx, scan_params, n_active, pps, n_rot, quick))
+        leg(("c2_grid_scan",), lambda: leg_grid_scan(ctx, scan_params, n_active, pps, n_rot, quick))
     ctx.ck(ctx.L.mmo_kernel_timing(0))
     out["wall_s"] = time.perf_counter() - t0
     return out
