@@ -57,6 +57,10 @@ constexpr int MAX_TILE_GROUPS = 128;
 #ifndef MMO_SUM_EVERY
 #define MMO_SUM_EVERY 32
 #endif
+#ifndef MMO_K1_UNROLL
+#define MMO_K1_UNROLL 1
+#endif
+constexpr int kK1Unroll = MMO_K1_UNROLL;    // pair-loop steps per iteration (tuning)
 constexpr int kSumEvery = MMO_SUM_EVERY;    // list steps (of 4 atoms) summed in fp32 before the fp64 accumulation
 constexpr float kRhoExpand2 = 20.25f;  // the expanded form of r^2 is used while rho <= 4.5 A
 static_assert(kBlob == 16, "two receptor groups per warp-wide test");
@@ -154,7 +158,7 @@ __device__ __forceinline__ void run_list(const float *s_l, int n, int n4, const 
         float2 f[PPT][2];
 #pragma unroll
         for (int h = 0; h < PPT; h++) f[h][0] = f[h][1] = make_float2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll kK1Unroll
         for (int k = k0; k < kend; k += 4) {
             const float4 X = *(const float4 *)(s_l + 0 * LIST_CAP + k), Y = *(const float4 *)(s_l + 1 * LIST_CAP + k);
             const float4 Z = *(const float4 *)(s_l + 2 * LIST_CAP + k), S = *(const float4 *)(s_l + 3 * LIST_CAP + k);
