@@ -33,7 +33,7 @@ int d2h_sync(void *host, const void *dev, size_t bytes) {
 // Host arrays of one call -> ONE device buffer (dev[i] = start of array i), and no host synchronisation in between: the
 // call's closing d2h_sync orders everything.  Small inputs (single-pose calls: the reference's closures are
 // Mol.t -> float) are packed into a pinned staging buffer and travel as one copy.
-constexpr size_t kStageBytes = 64 * 1024;
+constexpr size_t kStageBytes = kStageHalf;
 int upload_parts(DevBuf<double> &buf, int n, const double *const *host, const size_t *count, const double **dev) {
     Runtime &R = rt();
     size_t total = 0;
@@ -42,7 +42,8 @@ int upload_parts(DevBuf<double> &buf, int n, const double *const *host, const si
     size_t off = 0;
     for (int i = 0; i < n; i++) { dev[i] = buf.p + off; off += count[i]; }
     if (total * sizeof(double) <= kStageBytes) {
-        if (!R.stage) MMO_CUDA(cudaHostAlloc(&R.stage, kStageBytes, cudaHostAllocDefault));
+        void *stage = nullptr;
+        MMO_TRY(stage_buffer(&stage));
         // the previous call that used the staging buffer ended with a stream synchronisation
         off = 0;
         for (int i = 0; i < n; i++) { memcpy((double *)R.stage + off, host[i], count[i] * sizeof(double)); off += count[i]; }

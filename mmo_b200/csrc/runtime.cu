@@ -29,6 +29,12 @@ Runtime &rt() {
     static Runtime r;
     return r;
 }
+int stage_buffer(void **p) {
+    Runtime &R = rt();
+    if (!R.stage) MMO_CUDA(cudaHostAlloc(&R.stage, 2 * kStageHalf, cudaHostAllocDefault));
+    *p = R.stage;
+    return MMO_OK;
+}
 // ---- per-kernel timing ---------------------------------------------------------------------------
 struct KTimer {
     bool enabled = false;

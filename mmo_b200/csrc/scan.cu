@@ -64,6 +64,34 @@ scan_reduce_kernel(const double *__restrict__ energies, const int64_t *__restric
     }
 }
 
+// argmin over the per-block minima of scan_reduce_kernel (ties to the smaller frame): one ScoreFrame travels to the host
+__global__ void __launch_bounds__(1024)
+scan_best_kernel(const ScoreFrame *__restrict__ block_best, unsigned n, ScoreFrame *__restrict__ out) {
+    __shared__ double sh_s[32];
+    __shared__ long long sh_f[32];
+    double s = INFINITY;
+    long long f = 0x7fffffffffffffffLL;
+    for (unsigned b = threadIdx.x; b < n; b += blockDim.x) {
+        const double s2 = block_best[b].s;
+        const long long f2 = block_best[b].f;
+        if (sf_less(s2, f2, s, f)) { s = s2; f = f2; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        long long f2 = __shfl_xor_sync(0xffffffffu, f, o);
+        if (sf_less(s2, f2, s, f)) { s = s2; f = f2; }
+    }
+    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_f[threadIdx.x >> 5] = f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; w++)
+            if (sf_less(sh_s[w], sh_f[w], s, f)) { s = sh_s[w]; f = sh_f[w]; }
+        out->s = s;
+        out->f = f;
+    }
+}
+
 struct RotSet {
     DevBuf<double> rot;
     DevBuf<int32_t> perm;
@@ -259,7 +287,7 @@ static int scan_setup(ScanJob &J) {
         MMO_TRY(J.d_cand_s.alloc((size_t)J.slab_cap));
         MMO_TRY(J.d_cand_f.alloc((size_t)J.slab_cap));
     }
-    MMO_TRY(J.d_block_best.alloc((size_t)(J.slab_cap + 255) / 256));
+    MMO_TRY(J.d_block_best.alloc((size_t)(J.slab_cap + 255) / 256 + 1));     // + the slab's best (scan_best_kernel)
     J.top.clear();
     return MMO_OK;
 }
@@ -277,6 +305,15 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
     std::vector<ScoreFrame> hbest;
     std::vector<double> hs;
     std::vector<long long> hf;
+    // pinned read-back area (second half of the library's staging buffer): counters, the slab's best, candidate prefix
+    constexpr int64_t kCandPrefix = 2048;
+    void *stage = nullptr;
+    MMO_TRY(stage_buffer(&stage));
+    unsigned long long *pin_u64 = (unsigned long long *)((char *)stage + kStageHalf);
+    ScoreFrame *pin_best = (ScoreFrame *)(pin_u64 + 2);
+    double *pin_cs = (double *)(pin_u64 + 8);
+    long long *pin_cf = (long long *)(pin_cs + kCandPrefix);
+    static_assert(64 + 2 * kCandPrefix * 8 <= (int64_t)kStageHalf, "read-back area exceeds the staging buffer");
     for (int64_t s0 = a0; s0 < a1; s0 += pts_per_slab) {
         const int64_t npts = std::min(pts_per_slab, a1 - s0);
         const int64_t n_cand = npts * P.n_rot;
@@ -287,9 +324,13 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         MMO_CUDA(cudaMemsetAsync(J.d_counters.p, 0, 2 * sizeof(unsigned long long), R.stream));
         MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &thr, sizeof(double), cudaMemcpyHostToDevice, R.stream));
         MMO_TRY(launch_scan_prefilter(P.vdw_mask, P.lig, src, J.d_points.p + s0, J.rs->perm.p, n_cand, J.d_frames.p, J.d_counters.p));
-        unsigned long long n_surv = 0;
-        MMO_CUDA(cudaMemcpyAsync(&n_surv, J.d_counters.p, sizeof n_surv, cudaMemcpyDeviceToHost, R.stream));
-        MMO_CUDA(cudaStreamSynchronize(R.stream));
+        // without a mask the prefilter only writes the frames, in order: nothing to wait for
+        unsigned long long n_surv = (unsigned long long)n_cand;
+        if (P.vdw_mask) {
+            MMO_CUDA(cudaMemcpyAsync(pin_u64, J.d_counters.p, sizeof n_surv, cudaMemcpyDeviceToHost, R.stream));
+            MMO_CUDA(cudaStreamSynchronize(R.stream));
+            n_surv = pin_u64[0];
+        }
         J.n_scored += (int64_t)n_surv;
         if (n_surv == 0) continue;
         if (P.grid) {
@@ -326,16 +367,34 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
             MMO_CUDA(cudaMemcpyAsync(J.d_thr.p, &est, sizeof(double), cudaMemcpyHostToDevice, R.stream));
         }
         MMO_TRY(reduce_pass(J.k_eff > 0));
-        MMO_CUDA(cudaMemcpyAsync(hbest.data(), J.d_block_best.p, blocks * sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
-        MMO_CUDA(cudaMemcpyAsync(&n_cnd, J.d_counters.p + 1, sizeof n_cnd, cudaMemcpyDeviceToHost, R.stream));
+        // ONE synchronisation per slab: the slab's best (reduced on the device), the candidate count and the first
+        // kCandPrefix candidates travel together into pinned memory; only a slab with more candidates (the first ones
+        // of a scan, before the running threshold bites) pays a second round trip
+        scan_best_kernel<<<1, 1024, 0, R.stream>>>(J.d_block_best.p, blocks, J.d_block_best.p + blocks);
+        MMO_LAUNCH_CHECK();
+        MMO_CUDA(cudaMemcpyAsync(pin_best, J.d_block_best.p + blocks, sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
+        MMO_CUDA(cudaMemcpyAsync(pin_u64 + 1, J.d_counters.p + 1, sizeof n_cnd, cudaMemcpyDeviceToHost, R.stream));
+        if (J.k_eff > 0) {
+            const size_t pre = (size_t)std::min<int64_t>(kCandPrefix, J.slab_cap);
+            MMO_CUDA(cudaMemcpyAsync(pin_cs, J.d_cand_s.p, pre * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
+            MMO_CUDA(cudaMemcpyAsync(pin_cf, J.d_cand_f.p, pre * sizeof(long long), cudaMemcpyDeviceToHost, R.stream));
+        }
         MMO_CUDA(cudaStreamSynchronize(R.stream));
-        for (const ScoreFrame &b : hbest)
+        n_cnd = pin_u64[1];
+        {
+            const ScoreFrame b = *pin_best;
             if (b.s < J.best_s || (b.s == J.best_s && b.f < J.best_f && b.s != INFINITY)) { J.best_s = b.s; J.best_f = b.f; }
+        }
         if (J.k_eff > 0 && n_cnd > 0) {
             hs.resize(n_cnd); hf.resize(n_cnd);
-            MMO_CUDA(cudaMemcpyAsync(hs.data(), J.d_cand_s.p, n_cnd * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
-            MMO_CUDA(cudaMemcpyAsync(hf.data(), J.d_cand_f.p, n_cnd * sizeof(long long), cudaMemcpyDeviceToHost, R.stream));
-            MMO_CUDA(cudaStreamSynchronize(R.stream));
+            const size_t pre = (size_t)std::min<unsigned long long>(n_cnd, (unsigned long long)kCandPrefix);
+            memcpy(hs.data(), pin_cs, pre * sizeof(double));
+            memcpy(hf.data(), pin_cf, pre * sizeof(long long));
+            if (n_cnd > pre) {
+                MMO_CUDA(cudaMemcpyAsync(hs.data() + pre, J.d_cand_s.p + pre, (n_cnd - pre) * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
+                MMO_CUDA(cudaMemcpyAsync(hf.data() + pre, J.d_cand_f.p + pre, (n_cnd - pre) * sizeof(long long), cudaMemcpyDeviceToHost, R.stream));
+                MMO_CUDA(cudaStreamSynchronize(R.stream));
+            }
             size_t old = J.top.size();
             J.top.resize(old + n_cnd);
             for (size_t i = 0; i < n_cnd; i++) { J.top[old + i].s = hs[i]; J.top[old + i].f = hf[i]; }
