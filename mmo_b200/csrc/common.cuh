@@ -36,6 +36,7 @@ struct Runtime {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // one-shot scans check the caller's rotation set behind the kernels (scan.cu)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void *l2_scratch = nullptr;
     size_t l2_scratch_bytes = 0;
@@ -43,13 +44,14 @@ struct Runtime {
     int64_t stat_pairs = 0, stat_inside = 0, stat_fp64 = 0, stat_flagged = 0;
     bool collect_stats = false;
     void *stage = nullptr;           // pinned staging buffer (stage_buffer()): [0, 64 KB) small host->device copies of api.cu,
-                                     // [64 KB, 128 KB) per-slab read-backs of the scan driver
+                                     // [64 KB, 256 KB) per-slab read-backs of the scan driver
     int epoch = 0;                   // bumped by every mmo_init: device-resident caches of an older epoch are stale
 };
 Runtime &rt();
 int require_ready();
-constexpr size_t kStageHalf = 64 * 1024;
-int stage_buffer(void **p);          // the pinned staging buffer (2 x kStageHalf), allocated on first use
+constexpr size_t kStageHalf = 64 * 1024;        // uploads: [0, kStageHalf)
+constexpr size_t kStageReadback = 192 * 1024;   // read-backs: [kStageHalf, kStageHalf + kStageReadback)
+int stage_buffer(void **p);          // the pinned staging buffer, allocated on first use
 
 // per-kernel device timing (CUDA events on the library stream), off unless mmo_kernel_timing(1)
 enum KernelId { K_DIRECT_FP32 = 0, K_HARD_FIX, K_DIRECT_FP64, K_INTRA, K_GRID_BUILD, K_INTERP, K_PREFILTER,

@@ -31,7 +31,7 @@ Runtime &rt() {
 }
 int stage_buffer(void **p) {
     Runtime &R = rt();
-    if (!R.stage) MMO_CUDA(cudaHostAlloc(&R.stage, 2 * kStageHalf, cudaHostAllocDefault));
+    if (!R.stage) MMO_CUDA(cudaHostAlloc(&R.stage, kStageHalf + kStageReadback, cudaHostAllocDefault));
     *p = R.stage;
     return MMO_OK;
 }
@@ -283,6 +283,7 @@ int mmo_init(int device) try {
     R.device = device;
     R.sm_count = prop.multiProcessorCount;
     MMO_CUDA(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+    MMO_CUDA(cudaStreamCreateWithFlags(&R.copy_stream, cudaStreamNonBlocking));
     MMO_CUDA(cudaEventCreate(&R.ev0));
     MMO_CUDA(cudaEventCreate(&R.ev1));
     R.launches = 0;
@@ -308,6 +309,8 @@ int mmo_shutdown(void) try {
     cudaEventDestroy(R.ev1);
     cudaStreamDestroy(R.stream);
     R.stream = nullptr;
+    if (R.copy_stream) { cudaStreamSynchronize(R.copy_stream); cudaStreamDestroy(R.copy_stream); }
+    R.copy_stream = nullptr;
     R.ready = false;
     return MMO_OK;
 } MMO_CATCH_ALL

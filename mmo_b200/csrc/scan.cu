@@ -92,6 +92,30 @@ scan_best_kernel(const ScoreFrame *__restrict__ block_best, unsigned n, ScoreFra
     }
 }
 
+// k-th smallest of the per-block minima (n <= 4096), written to *thr as the first slab's candidate threshold: it bounds
+// the k-th best score from above.  One block, bitonic sort in shared memory; two_stage adds the fp32 sweep's 2 delta.
+__global__ void __launch_bounds__(1024)
+scan_kth_kernel(const ScoreFrame *__restrict__ block_best, unsigned n, unsigned k, int two_stage, double *__restrict__ thr) {
+    __shared__ double v[4096];
+    for (unsigned i = threadIdx.x; i < 4096; i += 1024) v[i] = i < n ? block_best[i].s : INFINITY;
+    __syncthreads();
+    for (unsigned size = 2; size <= 4096; size <<= 1)
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = threadIdx.x; t < 2048; t += 1024) {
+                const unsigned lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const double a = v[lo], b = v[hi];
+                if ((a > b) == up) { v[lo] = b; v[hi] = a; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        double est = v[k - 1];
+        if (two_stage && est < INFINITY) est = __dadd_rn(est, __dmul_rn(2.0, __dmul_rn(8.0, fmax(__dmul_rn(1e-6, fabs(est)), 1e-4))));
+        *thr = est;
+    }
+}
+
 struct RotSet {
     DevBuf<double> rot;
     DevBuf<int32_t> perm;
@@ -126,6 +150,13 @@ struct ScanJob {
     double exact_best_s = INFINITY;
     long long exact_best_f = -1;
     bool exact_ready = false;
+    // one-shot scans (mmo_scan): the caller's rotation bytes are uploaded and compared with the resident set on the copy
+    // stream WHILE the scan runs on the resident set; the verdict is read when the scan is done (a different set: redo)
+    bool speculative = false;
+    bool rot_check_pending = false;
+    DevBuf<double> rot_fresh;
+    DevBuf<int> rot_flag;
+    ~ScanJob() { if (rot_check_pending && rt().copy_stream) cudaStreamSynchronize(rt().copy_stream); }
 };
 
 // bound used for |E_fp32 - E_ref|: 8x the accuracy contract of MMO_PREC_FP32 (which the parity tests
@@ -199,7 +230,25 @@ rot_compare_kernel(const unsigned long long *__restrict__ a, const unsigned long
     if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) atomicOr(differ, 1);
 }
 
-static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out) {
+constexpr int kPinRotFlag = 6;       // slot of the rotation-set verdict in the pinned read-back area (as unsigned long long)
+static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out, ScanJob *spec) {
+    if (spec && g_rot_cache_mode == 1 && g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch) {
+        Runtime &R = rt();
+        const size_t nw = (size_t)n_rot * 9;
+        void *stage = nullptr;
+        MMO_TRY(stage_buffer(&stage));
+        int *pin_flag = (int *)((unsigned long long *)((char *)stage + kStageHalf) + kPinRotFlag);
+        MMO_TRY(spec->rot_fresh.alloc(nw));
+        MMO_TRY(spec->rot_flag.alloc(1));
+        MMO_CUDA(cudaMemsetAsync(spec->rot_flag.p, 0, sizeof(int), R.copy_stream));
+        MMO_CUDA(cudaMemcpyAsync(spec->rot_fresh.p, rot9, nw * sizeof(double), cudaMemcpyHostToDevice, R.copy_stream));
+        rot_compare_kernel<<<R.sm_count * 4, 256, 0, R.copy_stream>>>((const unsigned long long *)spec->rot_fresh.p, (const unsigned long long *)g_rotset->rot.p, nw, spec->rot_flag.p);
+        MMO_LAUNCH_CHECK();
+        MMO_CUDA(cudaMemcpyAsync(pin_flag, spec->rot_flag.p, sizeof(int), cudaMemcpyDeviceToHost, R.copy_stream));
+        spec->rot_check_pending = true;
+        out = g_rotset;
+        return MMO_OK;
+    }
     if (g_rot_cache_mode == 1 && g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch) {
         Runtime &R = rt();
         const size_t nw = (size_t)n_rot * 9;
@@ -271,7 +320,7 @@ static int scan_setup(ScanJob &J) {
         if (center_filter && host_clash_and(P.vdw_mask, pos[0], pos[1], pos[2])) continue;
         J.points.push_back(p);
     }
-    MMO_TRY(get_rotset(P.n_rot, P.rot9, J.rs));
+    MMO_TRY(get_rotset(P.n_rot, P.rot9, J.rs, J.speculative ? &J : nullptr));
     MMO_TRY(J.d_points.upload(J.points));
     // slab: as many lattice points as fit ~4M candidate poses
     int64_t pts_per_slab = std::max<int64_t>(1, (int64_t)(4 << 20) / std::max(1, P.n_rot));
@@ -306,14 +355,14 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
     std::vector<double> hs;
     std::vector<long long> hf;
     // pinned read-back area (second half of the library's staging buffer): counters, the slab's best, candidate prefix
-    constexpr int64_t kCandPrefix = 2048;
+    constexpr int64_t kCandPrefix = 8192;
     void *stage = nullptr;
     MMO_TRY(stage_buffer(&stage));
     unsigned long long *pin_u64 = (unsigned long long *)((char *)stage + kStageHalf);
     ScoreFrame *pin_best = (ScoreFrame *)(pin_u64 + 2);
     double *pin_cs = (double *)(pin_u64 + 8);
     long long *pin_cf = (long long *)(pin_cs + kCandPrefix);
-    static_assert(64 + 2 * kCandPrefix * 8 <= (int64_t)kStageHalf, "read-back area exceeds the staging buffer");
+    static_assert(64 + 2 * kCandPrefix * 8 <= (int64_t)kStageReadback, "read-back area exceeds the staging buffer");
     for (int64_t s0 = a0; s0 < a1; s0 += pts_per_slab) {
         const int64_t npts = std::min(pts_per_slab, a1 - s0);
         const int64_t n_cand = npts * P.n_rot;
@@ -353,9 +402,14 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         };
         hbest.resize(blocks);
         unsigned long long n_cnd = 0;
-        if (J.k_eff > 0 && thr == INFINITY && blocks >= (unsigned)J.k_eff) {
-            // No running threshold yet (first slab of a scan): the k-th smallest per-block minimum bounds
-            // the k-th best score from above, so only the few poses below it travel to the host.
+        if (J.k_eff > 0 && thr == INFINITY && blocks >= (unsigned)J.k_eff && blocks <= 4096u) {
+            // No running threshold yet (first slab of a scan -- every call of a one-shot scan): the k-th smallest
+            // per-block minimum bounds the k-th best score from above, so only the few poses below it travel to the
+            // host.  Selected on the device: no round trip before the candidate pass.
+            MMO_TRY(reduce_pass(false));
+            scan_kth_kernel<<<1, 1024, 0, R.stream>>>(J.d_block_best.p, blocks, (unsigned)J.k_eff, J.two_stage ? 1 : 0, J.d_thr.p);
+            MMO_LAUNCH_CHECK();
+        } else if (J.k_eff > 0 && thr == INFINITY && blocks >= (unsigned)J.k_eff) {
             MMO_TRY(reduce_pass(false));
             MMO_CUDA(cudaMemcpyAsync(hbest.data(), J.d_block_best.p, blocks * sizeof(ScoreFrame), cudaMemcpyDeviceToHost, R.stream));
             MMO_CUDA(cudaStreamSynchronize(R.stream));
@@ -381,6 +435,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
         }
         MMO_CUDA(cudaStreamSynchronize(R.stream));
         n_cnd = pin_u64[1];
+        if (getenv("MMO_DEBUG_TIMING")) fprintf(stderr, "[scan slab] %lld poses, %llu candidates (threshold %s)\n", (long long)n_surv, n_cnd, thr == INFINITY ? "estimated" : "running");
         {
             const ScoreFrame b = *pin_best;
             if (b.s < J.best_s || (b.s == J.best_s && b.f < J.best_f && b.s != INFINITY)) { J.best_s = b.s; J.best_f = b.f; }
@@ -406,7 +461,9 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
             };
             size_t keep = std::min<size_t>(J.top.size(), (size_t)J.k_eff);
             if (!J.two_stage) {
-                std::partial_sort(J.top.begin(), J.top.begin() + keep, J.top.end(), less);
+                // select, then sort the k kept: O(n + k log k) -- a one-shot call sees ~1e4 candidates (estimated threshold)
+                if (keep < J.top.size()) std::nth_element(J.top.begin(), J.top.begin() + keep, J.top.end(), less);
+                std::sort(J.top.begin(), J.top.begin() + keep, less);
                 J.top.resize(keep);
             } else {
                 // keep everything within 2*delta of the k-th best fp32 score: a superset of the exact top-k
@@ -519,9 +576,8 @@ using namespace mmo;
 
 struct mmo_scan_job { ScanJob J; };
 
-extern "C" {
-
-int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **out) try {
+// speculative: only for a call that holds the caller's rotation buffer until it returns (mmo_scan)
+static int scan_create(const mmo_scan_params *p, int collect_stats, bool speculative, mmo_scan_job **out) {
     MMO_TRY(require_ready());
     MMO_REQUIRE(out != nullptr, "mmo_scan_create: null output pointer");
     *out = nullptr;
@@ -529,10 +585,17 @@ int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **
     mmo_scan_job *h = new mmo_scan_job();
     h->J.P = *p;
     h->J.collect_stats = collect_stats != 0;
+    h->J.speculative = speculative;
     int rc = scan_setup(h->J);
     if (rc != MMO_OK) { delete h; return rc; }
     *out = h;
     return MMO_OK;
+}
+
+extern "C" {
+
+int mmo_scan_create(const mmo_scan_params *p, int collect_stats, mmo_scan_job **out) try {
+    return scan_create(p, collect_stats, false, out);
 } MMO_CATCH_ALL
 
 int mmo_scan_num_points(const mmo_scan_job *job, int64_t *n_active_points) try {
@@ -582,9 +645,25 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now();
     mmo_scan_job *job = nullptr;
-    MMO_TRY(mmo_scan_create(p, rt().collect_stats ? 1 : 0, &job));
+    MMO_TRY(scan_create(p, rt().collect_stats ? 1 : 0, true, &job));
     double t1 = now();
     int rc = mmo_scan_run(job, 0, -1);
+    if (job->J.rot_check_pending) {
+        // the verdict on the caller's rotation bytes, uploaded and compared behind the kernels
+        cudaError_t e = cudaStreamSynchronize(rt().copy_stream);
+        job->J.rot_check_pending = false;
+        void *stage = nullptr;
+        if (e != cudaSuccess) rc = cuda_fail(e, "rotation set check", __FILE__, __LINE__);
+        else if (rc == MMO_OK) rc = stage_buffer(&stage);
+        if (rc == MMO_OK && *(const int *)((const unsigned long long *)((const char *)stage + kStageHalf) + kPinRotFlag) != 0) {
+            // not the resident set after all: drop it and scan again with the caller's rotations
+            mmo_scan_destroy(job);
+            job = nullptr;
+            g_rotset.reset();
+            MMO_TRY(scan_create(p, rt().collect_stats ? 1 : 0, false, &job));
+            rc = mmo_scan_run(job, 0, -1);
+        }
+    }
     double t2 = now();
     if (rc == MMO_OK) rc = scan_finalize(job->J);
     if (rc == MMO_OK) scan_fill_result(job->J, top_scores, top_frames, res);
