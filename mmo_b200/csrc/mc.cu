@@ -55,6 +55,8 @@ struct McArgs {
     // interpolated scorer (maps != nullptr) ...
     GridGeom g;
     const float *maps;
+    const float2 *zp;                   // the z-pair copy of the maps (mmo_grid::zpair) the look-ups read, zvox elements per type
+    size_t zvox;
     // ... or direct shifted scorer over the receptor atoms
     int P;
     const double4 *pxyzq;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void mc_produce(const McArgs &a, const McShared &S, c
     }
     if (c.do_inter && h < n_lw * 32) {
         for (int j = h; j < a.L; j += n_lw * 32)
-            S.iterms[j] = d_trilin(a.g, a.maps + (size_t)S.ltyp[j] * a.g.nvox, x[j], y[j], z[j]);
+            S.iterms[j] = d_trilin_zp(a.g, a.zp + (size_t)S.ltyp[j] * a.zvox, x[j], y[j], z[j]);
         __threadfence_block();
         __syncwarp();
         bar_arrive(kBarLookups, n_lw * 32 + 32);
@@ -698,7 +700,7 @@ __device__ double w_interp_energy(const McArgs &a, const double *x, const double
     for (int base = 0; base < a.L; base += 32) {
         const int j = base + lane;
         double t = 0.0;
-        if (j < a.L) t = d_trilin(a.g, a.maps + (size_t)__ldg(a.ltyp + j) * a.g.nvox, x[j], y[j], z[j]);
+        if (j < a.L) t = d_trilin_zp(a.g, a.zp + (size_t)__ldg(a.ltyp + j) * a.zvox, x[j], y[j], z[j]);
         __syncwarp();
         terms[lane].x = t;
         __syncwarp();
@@ -1033,7 +1035,12 @@ extern "C" int mmo_mc_run(const mmo_receptor *rec, const mmo_grid *grid, const m
     a.pair_tab = lig->mc_pair_tab.p;
     a.n_rbonds = lig->n_rbonds; a.rb_left = lig->d_rb_left.p; a.rb_right = lig->d_rb_right.p;
     a.rg_off = lig->d_rg_off.p; a.rg_idx = lig->d_rg_idx.p;
-    if (grid) { a.g = geom_of(grid); a.maps = grid->maps.p; } else { memset(&a.g, 0, sizeof a.g); a.maps = nullptr; }
+    a.zp = nullptr; a.zvox = 0;
+    if (grid) {
+        a.g = geom_of(grid); a.maps = grid->maps.p;
+        MMO_TRY(grid_zpairs(grid, &a.zp));
+        a.zvox = (size_t)grid->dims[0] * grid->dims[1] * (grid->dims[2] - 1);
+    } else { memset(&a.g, 0, sizeof a.g); a.maps = nullptr; }
     a.P = rec ? rec->n : 0; a.pxyzq = rec ? rec->xyzq64.p : nullptr; a.pelt = rec ? rec->elt.p : nullptr;
     a.xij = g_mc_xij.p; a.dij = g_mc_dij.p;
     for (int d = 0; d < 3; d++) a.roi_c[d] = p->roi_c[d];
