@@ -4,9 +4,10 @@
 // for many poses per launch.  Layout of the computation (no tensor cores: non-linear pair sum):
 //
 //   thread  = two poses (p and p + 32), warp = 64 consecutive poses, one persistent block of 16 warps per SM that
-//             draws (64 poses, chunk split) work units from an atomic counter; the receptor
+//             draws (64 poses, chunk split, receptor slice) work units from an atomic counter; the receptor
 //             (k-d groups of 16 atoms, fp32, relative to the receptor origin) is staged in shared
-//             memory, the whole ROI receptor at once when it fits
+//             memory when it fits (<= 2048 atoms), else read through L1 with a two-stage level 1 (one launch
+//             either way); small batches (single-pose calls) also split the receptor into slices
 //   cull    = per (warp, ligand atom): centre c and radius rho of the atom's positions over the warp's 64
 //             poses (CREDUX); level 1: lane g tests the box of group g against the sphere (c, 12 + rho),
 //             one ballot per 32 groups; level 2: the atoms of four near groups per step are tested two
@@ -22,8 +23,12 @@
 //
 // Accuracy contract (MMO_PREC_FP32): |E - E_ref| <= max(1e-6 |E_ref|, 1e-4 kcal/mol).  fp32 cannot
 // deliver that for close contacts (r^-12), so the fast path clamps r^2 per ligand atom at H_j = x_j*x_max_rec/kTau
-// and a second, sparse kernel (hard_fix_kernel) adds  w(r) e64(r) - w(sqrt H) e64(sqrt H)  in the
-// reference's own double arithmetic for the few pairs with r^2 < H, found through the receptor's voxel lists.
+// and a second, sparse kernel (hard_fix_kernel: thread = pose; pose_fix_block_kernel: block = pose, for small batches)
+// adds  w(r) e64(r) - w(sqrt H) e64(sqrt H)  in double for the few pairs with r^2 < H, found through the receptor's
+// voxel lists.
+//
+// Item mode (further down): incoherent pose lists (conformer screens) are cut into (pose, ligand atom) items, sorted by
+// Morton cell, and run through the same cull -> list -> packed pair loop with 64 spatially neighbouring items per warp.
 #include "common.cuh"
 #include "pose.cuh"
 #include <math.h>
