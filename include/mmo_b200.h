@@ -314,8 +314,12 @@ int mmo_scan_destroy(mmo_scan_job *job);
  * handed: mode 1 (default) copies the caller's rotations to the device and compares them there with the resident copy
  * (7.2 MB for 1e5 rotations: 0.2 ms from pinned memory; every byte of the call's input moves); mode 0 compares them on
  * the host (one memcmp, 0.4 ms for the same set) and skips the upload -- for hosts with a slow link.  Either way the
- * visiting order is rebuilt only when the bytes differ. */
+ * visiting order is rebuilt only when the bytes differ.  In mode 1 the one-shot mmo_scan does not wait for the verdict:
+ * it scans on the resident set at once, uploads and compares the caller's bytes on a second stream behind the first
+ * slab's kernels (so a pageable source costs the same as a pinned one), and scans again only if the set turns out to be
+ * another one; mmo_scan_rot_rescans counts those second scans since the library was loaded. */
 int mmo_scan_set_rot_cache(int mode);
+int mmo_scan_rot_rescans(int64_t *count);
 /* k smallest of n device-resident energies (a conformer screen's top-k, src/lds.ml:1055-1064 semantics: ascending,
  * NaN last, ties to the smaller id); id of entry p = id_base + p.  out arrays hold k entries. */
 int mmo_topk_select_dev(const double *d_E, int64_t n, int32_t k, int64_t id_base, double *out_scores,

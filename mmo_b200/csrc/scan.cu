@@ -153,6 +153,7 @@ struct ScanJob {
     // one-shot scans (mmo_scan): the caller's rotation bytes are uploaded and compared with the resident set on the copy
     // stream WHILE the scan runs on the resident set; the verdict is read when the scan is done (a different set: redo)
     bool speculative = false;
+    bool rot_check_wanted = false;           // issue_rot_check still to be called (after the first slab's kernels are queued)
     bool rot_check_pending = false;
     DevBuf<double> rot_fresh;
     DevBuf<int> rot_flag;
@@ -217,6 +218,7 @@ static void rotation_visit_order(int n_rot, const double *rot9, std::vector<int3
 // (same count, same bytes: one memcmp against the host copy) skips the 72 n_rot bytes upload and the k-d sort.
 // leaked on purpose: must not run a destructor after the CUDA context / the allocator are gone
 static std::shared_ptr<RotSet> &g_rotset = *new std::shared_ptr<RotSet>();
+static long long g_rot_rescans = 0;    // one-shot scans that had to be redone because the rotation set was not the resident one
 static int g_rot_cache_mode = 1;      // mmo_scan_set_rot_cache: 1 = upload + compare on the device (default), 0 = memcmp on the host
 void scan_drop_caches() { g_rotset.reset(); }
 // device-side comparison of a freshly uploaded rotation set with the resident one (mode 1: the bytes move on every call,
@@ -231,21 +233,33 @@ rot_compare_kernel(const unsigned long long *__restrict__ a, const unsigned long
 }
 
 constexpr int kPinRotFlag = 6;       // slot of the rotation-set verdict in the pinned read-back area (as unsigned long long)
+// The check of a one-shot scan, issued by scan_run_points once the first slab's kernels are queued: upload + compare on the
+// copy stream.  Behind the kernels on purpose -- a pageable source (an OCaml float array) is staged by the driver while
+// this call blocks the host (~1 ms for 7.2 MB), and by then the GPU has 10 ms of work.
+static int issue_rot_check(ScanJob &J) {
+    Runtime &R = rt();
+    const size_t nw = (size_t)J.P.n_rot * 9;
+    void *stage = nullptr;
+    MMO_TRY(stage_buffer(&stage));
+    int *pin_flag = (int *)((unsigned long long *)((char *)stage + kStageHalf) + kPinRotFlag);
+    // (the two buffers were taken from the pool in scan_setup, before any kernel of this call was queued: the pool hands
+    //  blocks out in stream order of the LIBRARY stream, so a block freed by a launcher a moment ago may still be in use
+    //  there and must not be written from the copy stream)
+    J.rot_check_pending = true;          // from here on the job waits for the copy stream before it frees anything
+    J.rot_check_wanted = false;
+    MMO_CUDA(cudaMemsetAsync(J.rot_flag.p, 0, sizeof(int), R.copy_stream));
+    MMO_CUDA(cudaMemcpyAsync(J.rot_fresh.p, J.P.rot9, nw * sizeof(double), cudaMemcpyHostToDevice, R.copy_stream));
+    rot_compare_kernel<<<R.sm_count * 4, 256, 0, R.copy_stream>>>((const unsigned long long *)J.rot_fresh.p, (const unsigned long long *)J.rs->rot.p, nw, J.rot_flag.p);
+    MMO_LAUNCH_CHECK();
+    MMO_CUDA(cudaMemcpyAsync(pin_flag, J.rot_flag.p, sizeof(int), cudaMemcpyDeviceToHost, R.copy_stream));
+    return MMO_OK;
+}
+
 static int get_rotset(int n_rot, const double *rot9, std::shared_ptr<RotSet> &out, ScanJob *spec) {
     if (spec && g_rot_cache_mode == 1 && g_rotset && g_rotset->n == n_rot && g_rotset->epoch == rt().epoch) {
-        Runtime &R = rt();
-        const size_t nw = (size_t)n_rot * 9;
-        void *stage = nullptr;
-        MMO_TRY(stage_buffer(&stage));
-        int *pin_flag = (int *)((unsigned long long *)((char *)stage + kStageHalf) + kPinRotFlag);
-        MMO_TRY(spec->rot_fresh.alloc(nw));
+        MMO_TRY(spec->rot_fresh.alloc((size_t)n_rot * 9));
         MMO_TRY(spec->rot_flag.alloc(1));
-        MMO_CUDA(cudaMemsetAsync(spec->rot_flag.p, 0, sizeof(int), R.copy_stream));
-        MMO_CUDA(cudaMemcpyAsync(spec->rot_fresh.p, rot9, nw * sizeof(double), cudaMemcpyHostToDevice, R.copy_stream));
-        rot_compare_kernel<<<R.sm_count * 4, 256, 0, R.copy_stream>>>((const unsigned long long *)spec->rot_fresh.p, (const unsigned long long *)g_rotset->rot.p, nw, spec->rot_flag.p);
-        MMO_LAUNCH_CHECK();
-        MMO_CUDA(cudaMemcpyAsync(pin_flag, spec->rot_flag.p, sizeof(int), cudaMemcpyDeviceToHost, R.copy_stream));
-        spec->rot_check_pending = true;
+        spec->rot_check_wanted = true;       // scan on the resident set now, verdict on the caller's bytes when the scan is done
         out = g_rotset;
         return MMO_OK;
     }
@@ -390,6 +404,7 @@ static int scan_run_points(ScanJob &J, int64_t a0, int64_t a1) {
             MMO_TRY(launch_direct_fp32(P.rec, P.lig, P.variant, src, (int64_t)n_surv, J.d_E.p, J.collect_stats));
             if (J.collect_stats) { J.pairs_eval += R.stat_pairs; J.pairs_in += R.stat_inside; }
         }
+        if (J.rot_check_wanted) MMO_TRY(issue_rot_check(J));
         const unsigned blocks = (unsigned)((n_surv + 255) / 256);
         auto reduce_pass = [&](bool with_candidates) -> int {
             KernelScope ks(K_REDUCE);
@@ -648,6 +663,7 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
     MMO_TRY(scan_create(p, rt().collect_stats ? 1 : 0, true, &job));
     double t1 = now();
     int rc = mmo_scan_run(job, 0, -1);
+    if (rc == MMO_OK && job->J.rot_check_wanted) rc = issue_rot_check(job->J);      // nothing was scored: check all the same
     if (job->J.rot_check_pending) {
         // the verdict on the caller's rotation bytes, uploaded and compared behind the kernels
         cudaError_t e = cudaStreamSynchronize(rt().copy_stream);
@@ -657,6 +673,8 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
         else if (rc == MMO_OK) rc = stage_buffer(&stage);
         if (rc == MMO_OK && *(const int *)((const unsigned long long *)((const char *)stage + kStageHalf) + kPinRotFlag) != 0) {
             // not the resident set after all: drop it and scan again with the caller's rotations
+            if (dbg) fprintf(stderr, "[mmo_scan] the rotation set is not the resident one: scanning again\n");
+            g_rot_rescans++;
             mmo_scan_destroy(job);
             job = nullptr;
             g_rotset.reset();
@@ -671,6 +689,12 @@ int mmo_scan(const mmo_scan_params *p, double *top_scores, int64_t *top_frames, 
     mmo_scan_destroy(job);
     if (dbg) fprintf(stderr, "[mmo_scan] create %.1f ms, run %.1f ms, finalize %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
+} MMO_CATCH_ALL
+
+int mmo_scan_rot_rescans(int64_t *count) try {
+    MMO_REQUIRE(count != nullptr, "mmo_scan_rot_rescans: null pointer");
+    *count = (int64_t)g_rot_rescans;
+    return MMO_OK;
 } MMO_CATCH_ALL
 
 int mmo_scan_set_rot_cache(int mode) try {

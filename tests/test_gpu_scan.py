@@ -289,7 +289,13 @@ def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
     roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 2.0)
     a = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
     assert L.mmo_scan_set_rot_cache(1) == 0
+    n0, n1 = C.c_int64(), C.c_int64()
+    assert L.mmo_scan_rot_rescans(C.byref(n0)) == 0
     b = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
+    b2 = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, np.array(rot, copy=True), lig, rec=rec)     # same bytes, another buffer
+    assert L.mmo_scan_rot_rescans(C.byref(n1)) == 0
+    assert n1.value == n0.value          # the same set again: checked behind the kernels, never scanned twice
+    assert np.array_equal(b2["top_scores"], b["top_scores"]) and np.array_equal(b2["top_frames"], b["top_frames"])
     assert L.mmo_scan_set_rot_cache(7) != 0 and L.mmo_scan_set_rot_cache(0) == 0
     c = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot, lig, rec=rec)
     assert L.mmo_scan_set_rot_cache(1) == 0
@@ -297,7 +303,10 @@ def test_rot_cache_mode_and_gather_microbenchmark(gpu, c2, c2_roi_rec):
     assert np.array_equal(a["top_scores"], b["top_scores"]) and np.array_equal(a["top_frames"], b["top_frames"])
     # another set of the same size: the device-side comparison must notice and rebuild the visiting order
     rot2 = np.ascontiguousarray(rot[::-1])
+    assert L.mmo_scan_rot_rescans(C.byref(n0)) == 0
     d1 = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot2, lig, rec=rec)
+    assert L.mmo_scan_rot_rescans(C.byref(n1)) == 0
+    assert n1.value == n0.value + 1      # scanned on the resident set, found to be another one, scanned again
     assert L.mmo_scan_set_rot_cache(0) == 0
     d0 = gpu.Lds.exhaustive_rigid_ligand_docking(10, roi, 1.0, rot2, lig, rec=rec)
     assert L.mmo_scan_set_rot_cache(1) == 0
