@@ -632,3 +632,96 @@ def det_exp(x):
     k = int(kf)
     scale = struct.unpack("d", struct.pack("Q", (k + 1023) << 52))[0]
     return p * scale
+
+
+# ---------------------------------------------------------------------------------------------- SO3.ml, quat.ml
+def libm_cos_sin(theta):            # math.ml:9-11 with the platform's libm (host-side code: SO3.rotations runs once per lds run)
+    return math.cos(theta), math.sin(theta)
+
+
+MATH_PI = 4.0 * math.atan(1.0)      # math.ml:13
+MATH_TWO_PI = 2.0 * MATH_PI         # math.ml:15
+SO3_PHI = math.sqrt(2.0)            # SO3.ml:13
+SO3_PSI = 1.533751168755204288118041     # SO3.ml:14
+
+
+def super_fibonacci(n, i):          # SO3.ml:18-30, n already a float; returns the quaternion (w, x, y, z)
+    s = float(i) + 0.5
+    t = s / n
+    d = MATH_TWO_PI * s
+    c_r = math.sqrt(t)
+    c_R = math.sqrt(1.0 - t)
+    alpha = d / SO3_PHI
+    beta = d / SO3_PSI
+    return (c_r * math.sin(alpha), c_r * math.cos(alpha), c_R * math.sin(beta), c_R * math.cos(beta))
+
+
+def quat_to_axis_angle(q):          # quat.ml:33-37
+    w, x, y, z = q
+    mag = math.sqrt(x * x + y * y + z * z)
+    axis = (x / mag, y / mag, z / mag)
+    theta = 2.0 * math.atan2(mag, w)
+    return axis, theta
+
+
+def so3_rotations(n):               # SO3.ml:32-39
+    out = []
+    for i in range(n):
+        axis, angle = quat_to_axis_angle(super_fibonacci(float(n), i))
+        out.append(rot_of_axis_angle(axis, angle, libm_cos_sin))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- lds.ml bitmasks, G3D.ml clash test
+R_H2O = 1.4                         # const.ml:10
+
+
+def coord_of_point(grid, p):        # grid.ml:87-90; int_of_float truncates toward zero
+    return (int((p[0] - grid.xs[0]) / grid.step), int((p[1] - grid.ys[0]) / grid.step), int((p[2] - grid.zs[0]) / grid.step))
+
+
+def atom_bitmask_set(grid, mask, xyz, radius, b):       # lds.ml:148-169; mask: a Python list of bools, Bitv index order
+    i0, j0, k0 = coord_of_point(grid, xyz)
+    r_steps = int(math.ceil(radius / grid.step))
+    r2 = radius * radius
+    for i in range(i0 - r_steps, i0 + r_steps + 1):
+        x = grid.xs[i]              # OCaml raises Invalid_argument outside the array; the fixtures keep atoms inside
+        for j in range(j0 - r_steps, j0 + r_steps + 1):
+            y = grid.ys[j]
+            for k in range(k0 - r_steps, k0 + r_steps + 1):
+                if dist2(xyz, (x, y, grid.zs[k])) < r2:
+                    mask[i + j * grid.x_dim + k * grid.xy_dim] = b
+
+
+def vdW_volume(grid, atoms, radii):             # lds.ml:187-196
+    mask = [False] * (grid.x_dim * grid.y_dim * grid.z_dim)
+    for xyz, r in zip(atoms, radii):
+        atom_bitmask_set(grid, mask, xyz, r, True)
+    return mask
+
+
+def first_solvent_shell(grid, atoms, radii):    # lds.ml:172-184
+    mask = [False] * (grid.x_dim * grid.y_dim * grid.z_dim)
+    for xyz, r in zip(atoms, radii):
+        atom_bitmask_set(grid, mask, xyz, r + R_H2O, True)
+    for xyz, r in zip(atoms, radii):
+        atom_bitmask_set(grid, mask, xyz, r, False)
+    return mask
+
+
+def vdW_clash_OR(grid, bitmask, p):             # G3D.ml:162-186
+    i0 = int(p[0] * grid.one_div_step)
+    j0 = int(p[1] * grid.one_div_step)
+    k0 = int(p[2] * grid.one_div_step)
+    i1, j1, k1 = i0 + 1, j0 + 1, k0 + 1
+    j0x, j1x = j0 * grid.x_dim, j1 * grid.x_dim
+    k0xy, k1xy = k0 * grid.xy_dim, k1 * grid.xy_dim
+    return (bitmask[i0 + j0x + k0xy] or bitmask[i1 + j0x + k0xy] or bitmask[i1 + j1x + k0xy] or bitmask[i0 + j1x + k0xy] or
+            bitmask[i0 + j0x + k1xy] or bitmask[i1 + j0x + k1xy] or bitmask[i1 + j1x + k1xy] or bitmask[i0 + j1x + k1xy])
+
+
+def protein_ligand_clash(grid, bitmask, lig_atoms):     # mol.ml:1195-1203
+    for p in lig_atoms:
+        if vdW_clash_OR(grid, bitmask, p):
+            return True
+    return False

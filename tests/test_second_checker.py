@@ -1,6 +1,7 @@
 """The C oracle (oracle/mmo_oracle*.c) against a second restatement written independently from the OCaml text in pure
 Python (oracle/pycheck/mmo_ref.py): whole-pose energies on C2- and C5-shaped inputs, one map voxel and one trilinear
-cell on a C3-shaped input, intra-ligand energies, and 200 Monte-Carlo frames -- all BIT FOR BIT.  Plus a 40-digit mpmath
+cell on a C3-shaped input, intra-ligand energies, 200 Monte-Carlo frames, SO3.rotations, the vdW / solvent-shell bitmasks
+and the clash test -- all BIT FOR BIT.  Plus a 40-digit mpmath
 evaluation of the same whole-pose sums, which bounds the rounding error of either.  CPU only.
 
 VERDICT r1 'weak #1': the oracle and the kernels came from one reading of the source; this removes the transcription
@@ -178,3 +179,62 @@ def test_200_monte_carlo_frames_bit_for_bit(orc, c2, c2_roi_rec, c2lig, flags):
         (want["n_accept_rigid"], want["n_reject_rigid"], want["n_accept_conf"], want["n_reject_conf"], want["n_ooroi"], want["n_ezero"])
     if not flags:
         assert cnt["acc_rigid"] > 0 and cnt["rej_rigid"] > 0 and cnt["acc_conf"] + cnt["rej_conf"] > 0
+
+
+def test_so3_rotations_bit_for_bit(orc):
+    """SO3.rotations (SO3.ml:18-39, quat.ml:33-37, rot.ml:136-146) with the platform's libm on both sides"""
+    for n in (1, 7, 64):
+        want = orc.so3_rotations(n)
+        got = ref.so3_rotations(n)
+        assert len(got) == n
+        for i in range(n):
+            assert tuple(want[i]) == got[i], (n, i)
+    q = ref.super_fibonacci(10.0, 3)
+    assert q == orc.so3_quat(10, 3)
+
+
+def _bits(mask_bytes, nvox):
+    """Bitv order of the C oracle's byte masks: bit idx = (byte[idx >> 3] >> (idx & 7)) & 1"""
+    b = np.unpackbits(np.asarray(mask_bytes, np.uint8), bitorder="little")[:nvox]
+    return [bool(x) for x in b]
+
+
+def test_vdw_volume_solvent_shell_and_clash_bit_for_bit(orc, c2):
+    """Lds.vdW_volume / first_solvent_shell (lds.ml:148-196) and G3D.vdW_clash_OR / Mol.protein_ligand_clash
+    (G3D.ml:162-186, mol.ml:1195-1203) on a 1.0 A grid over a slice of the receptor"""
+    m = c2["rec"]
+    c = np.array(c2["roi"][:3])
+    near = np.where((m.xs - c[0]) ** 2 + (m.ys - c[1]) ** 2 + (m.zs - c[2]) ** 2 < 9.0 ** 2)[0][:160]
+    lo = np.array([m.xs[near].min(), m.ys[near].min(), m.zs[near].min()]) - 5.0
+    xs, ys, zs, rr = m.xs[near] - lo[0], m.ys[near] - lo[1], m.zs[near] - lo[2], m.r[near]
+    box = (float(xs.max() + 5.0), float(ys.max() + 5.0), float(zs.max() + 5.0))
+    step = 1.0
+    dims = orc.grid_from_box(step, *box)
+    g = ref.Grid(step, *box)
+    assert (g.x_dim, g.y_dim, g.z_dim) == tuple(dims)
+    nvox = dims[0] * dims[1] * dims[2]
+    atoms = list(zip(xs.tolist(), ys.tolist(), zs.tolist()))
+    vol = ref.vdW_volume(g, atoms, rr.tolist())
+    assert vol == _bits(orc.vdw_volume(xs, ys, zs, rr, step, dims), nvox)
+    assert 0 < sum(vol) < nvox
+    shell = ref.first_solvent_shell(g, atoms, rr.tolist())
+    assert shell == _bits(orc.first_solvent_shell(xs, ys, zs, rr, step, dims), nvox)
+    assert sum(shell) > 0 and not any(a and b for a, b in zip(vol, shell))      # the shell excludes the vdW volume
+    # clash test of ligand poses: some inside the protein slice, some in the empty margin
+    lig = c2["lig"]
+    cx, cy, cz = c2["centered"]
+    rng = np.random.default_rng(5)
+    mask_bytes = orc.vdw_volume(xs, ys, zs, rr, step, dims)
+    seen = set()
+    for trial in range(14):
+        t = np.array([rng.uniform(6.0, box[0] - 6.0), rng.uniform(6.0, box[1] - 6.0), rng.uniform(6.0, box[2] - 6.0)])
+        s = 0.3                                              # shrink the ligand so that every atom stays inside the box
+        if trial >= 12:                                      # two poses in the empty margin at the box corner
+            t, s = np.array([1.5, 1.5, 1.5]) + 0.2 * (trial - 12), 0.08
+        px, py, pz = cx * s + t[0], cy * s + t[1], cz * s + t[2]
+        assert px.min() > 0 and px.max() < box[0] - 1 and py.min() > 0 and py.max() < box[1] - 1 and pz.min() > 0 and pz.max() < box[2] - 1
+        want = orc.protein_ligand_clash(step, dims, mask_bytes, px, py, pz)
+        got = ref.protein_ligand_clash(g, vol, list(zip(px.tolist(), py.tolist(), pz.tolist())))
+        assert got == want
+        seen.add(got)
+    assert seen == {True, False}
