@@ -725,3 +725,60 @@ def protein_ligand_clash(grid, bitmask, lig_atoms):     # mol.ml:1195-1203
         if vdW_clash_OR(grid, bitmask, p):
             return True
     return False
+
+
+# ---------------------------------------------------------------------------------------------- lds.ml exhaustive scan
+def centered_rotate_copy(lig, r):               # mol.ml:664-667
+    m = lig.copy()
+    m.centered_rotate(r)
+    return m
+
+
+def translate_copy_to(m, p):                    # mol.ml:689-696
+    c = m.copy()
+    c.translate_by(v_diff(p, c.center))
+    c.center = p
+    return c
+
+
+def roi_is_inside(roi, p):                      # ROI.ml:65-66: V3.dist2 s.c p < s.out_r2, out_r2 = out_r * out_r
+    return dist2(roi[:3], p) < roi[3] * roi[3]
+
+
+def exhaustive_rigid_ligand_docking(topk, roi, trans_step, rotations, centered_lig, score, clash=None):
+    """lds.ml:1040-1114 without the two vdW prefilters unless `clash` (Mol.protein_ligand_clash on the pose) is given:
+    returns (top scores, best score, best frame, poses scored).  TopK keeps the k highest of -score (Cpm.TopKeeper,
+    not vendored: only the kept scores are output, lds.ml:1110-1113); the best pose is the FIRST one with the lowest
+    score in loop order z, y, x, rotation (strict <, lds.ml:1099)."""
+    x0, x1 = roi[0] - roi[3], roi[0] + roi[3]   # ROI.get_bounds (ROI.ml:76-82)
+    y0, y1 = roi[1] - roi[3], roi[1] + roi[3]
+    z0, z1 = roi[2] - roi[3], roi[2] + roi[3]
+    g = Grid(trans_step, x1 - x0, y1 - y0, z1 - z0)           # Bbox.create_6f: dims = high - low; Grid.from_box
+    xs = [x0 + v for v in g.xs]                 # A.map ((+.) x_min) g.xs
+    ys = [y0 + v for v in g.ys]
+    zs = [z0 + v for v in g.zs]
+    n_rot = len(rotations)
+    best_score, best_frame = float("inf"), -1
+    kept = []
+    n_scored = 0
+    rotated = [centered_rotate_copy(centered_lig, r) for r in rotations]
+    for k, z in enumerate(zs):
+        z_dim = k * g.xy_dim
+        for j, y in enumerate(ys):
+            jz_dim = j * g.x_dim + z_dim
+            for i, x in enumerate(xs):
+                pos = (x, y, z)
+                if not roi_is_inside(roi, pos):
+                    continue
+                for rot_i, rot_lig in enumerate(rotated):
+                    lig2 = translate_copy_to(rot_lig, pos)
+                    if clash is not None and clash(lig2):
+                        continue
+                    curr = score(lig2)
+                    n_scored += 1
+                    kept.append(curr)
+                    if curr < best_score:
+                        best_score = curr
+                        best_frame = rot_i + n_rot * (i + jz_dim)
+    kept.sort()
+    return kept[:topk] if topk > 0 else [], best_score, best_frame, n_scored

@@ -238,3 +238,21 @@ def test_vdw_volume_solvent_shell_and_clash_bit_for_bit(orc, c2):
         assert got == want
         seen.add(got)
     assert seen == {True, False}
+
+
+def test_exhaustive_scan_bit_for_bit(orc, c2, c2_roi_rec, c2lig):
+    """Lds.exhaustive_rigid_ligand_docking (lds.ml:1040-1114) on a small lattice and rotation set: the lattice of
+    Grid.from_box over ROI.get_bounds, the strict in-ROI test, score = E_intra + E_inter per pose, first-pose-wins argmin
+    and its frame number, the k best scores -- the C oracle's scan against the Python restatement, bit for bit"""
+    cx, cy, cz = c2["centered"]
+    roi = (c2["roi"][0], c2["roi"][1], c2["roi"][2], 2.2)
+    rot9 = orc.so3_rotations(5)
+    e_intra = 1.25
+    want = orc.scan(c2_roi_rec, c2lig, cx, cy, cz, roi, 1.5, rot9, 12, scorer=0, e_intra_const=e_intra)
+    prot = _ref_prot(c2_roi_rec)
+    lig0 = _ref_lig(c2lig, cx, cy, cz, center=(0.0, 0.0, 0.0))
+    top, best, frame, n_scored = ref.exhaustive_rigid_ligand_docking(
+        12, roi, 1.5, [tuple(r) for r in rot9], lig0, lambda m: e_intra + ref.ene_inter_UFF_shifted_brute(prot, m))
+    assert n_scored == want["n_scored"] and n_scored >= 5 * 7
+    assert best == want["best_score"] and frame == want["best_frame"]
+    assert top == list(want["top_scores"])
