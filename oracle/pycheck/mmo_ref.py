@@ -782,3 +782,56 @@ def exhaustive_rigid_ligand_docking(topk, roi, trans_step, rotations, centered_l
                         best_frame = rot_i + n_rot * (i + jz_dim)
     kept.sort()
     return kept[:topk] if topk > 0 else [], best_score, best_frame, n_scored
+
+
+# ---------------------------------------------------------------------------------------------- lds.ml desolvation (N4)
+CHARGED_CUTOFF = 12.0                                               # const.ml:12
+CHARGED_CUTOFF_SQUARED = CHARGED_CUTOFF * CHARGED_CUTOFF            # const.ml:14
+DESOLVATION = (1.0 / 4.0 - 1.0 / 78.5) / (8.0 * MATH_PI)            # const.ml:18-31
+
+
+def ijk_of_idx(grid, idx):          # grid.ml:101-105
+    k = idx // grid.xy_dim
+    j = (idx - k * grid.xy_dim) // grid.x_dim
+    i = idx - (k * grid.xy_dim + j * grid.x_dim)
+    return i, j, k
+
+
+def protein_desolv(roi, grid, shell, prot):     # lds.ml:204-236; BST.neighbors restated as index order with dist <= cutoff
+    voxel_vol = grid.step * grid.step * grid.step
+    n = grid.x_dim * grid.y_dim * grid.z_dim
+    assert n == len(shell)
+    res = [0.0] * n
+    for idx in range(n):                        # Bitv.iteri_true: ascending index
+        if not shell[idx]:
+            continue
+        i, j, k = ijk_of_idx(grid, idx)
+        x_p = (grid.xs[i], grid.ys[j], grid.zs[k])
+        if roi_is_inside(roi, x_p):
+            for a in range(prot.n):
+                x_j = prot.get_xyz(a)
+                if dist(x_p, x_j) <= CHARGED_CUTOFF:
+                    d2 = dist2(x_p, x_j)
+                    x = prot.q_a[a] / d2
+                    res[idx] = res[idx] + (x * x)
+            res[idx] = DESOLVATION * (voxel_vol * res[idx])
+    return res
+
+
+def desolvation_penalty(grid, contribs, prot_shell, lig_atoms, lig_charges, lig_radii):     # lds.ml:239-267
+    voxel_vol = grid.step * grid.step * grid.step
+    lig_shell = first_solvent_shell(grid, lig_atoms, lig_radii)
+    lig_desolv = 0.0
+    prot_desolv = 0.0
+    for idx in range(len(prot_shell)):
+        if not (prot_shell[idx] and lig_shell[idx]):        # Bitv.bw_and, then iteri_true
+            continue
+        i, j, k = ijk_of_idx(grid, idx)
+        x_p = (grid.xs[i], grid.ys[j], grid.zs[k])
+        for x_j, q_j in zip(lig_atoms, lig_charges):
+            d2 = dist2(x_p, x_j)
+            if d2 < CHARGED_CUTOFF_SQUARED:
+                x = q_j / d2
+                lig_desolv = lig_desolv + (x * x)
+        prot_desolv = prot_desolv + contribs[idx]
+    return prot_desolv, DESOLVATION * (voxel_vol * lig_desolv)

@@ -256,3 +256,44 @@ def test_exhaustive_scan_bit_for_bit(orc, c2, c2_roi_rec, c2lig):
     assert n_scored == want["n_scored"] and n_scored >= 5 * 7
     assert best == want["best_score"] and frame == want["best_frame"]
     assert top == list(want["top_scores"])
+
+
+def test_desolvation_sums_bit_for_bit(orc, c2):
+    """Lds.protein_desolv and Lds.desolvation_penalty (lds.ml:204-267) on a 1 A grid over a slice of the receptor"""
+    m = c2["rec"]
+    c = np.array(c2["roi"][:3])
+    near = np.where((m.xs - c[0]) ** 2 + (m.ys - c[1]) ** 2 + (m.zs - c[2]) ** 2 < 8.0 ** 2)[0][:120]
+    lo = np.array([m.xs[near].min(), m.ys[near].min(), m.zs[near].min()]) - 6.0
+    xs, ys, zs, rr, qq = m.xs[near] - lo[0], m.ys[near] - lo[1], m.zs[near] - lo[2], m.r[near], m.q[near]
+    box = (float(xs.max() + 6.0), float(ys.max() + 6.0), float(zs.max() + 6.0))
+    step = 1.0
+    dims = orc.grid_from_box(step, *box)
+    g = ref.Grid(step, *box)
+    nvox = dims[0] * dims[1] * dims[2]
+    atoms = list(zip(xs.tolist(), ys.tolist(), zs.tolist()))
+    shell_bytes = orc.first_solvent_shell(xs, ys, zs, rr, step, dims)
+    shell = _bits(shell_bytes, nvox)
+
+    class _R:
+        pass
+    rec = _R(); rec.xs, rec.ys, rec.zs, rec.q, rec.n = xs, ys, zs, qq, len(xs)
+    roi = (float(c[0] - lo[0]), float(c[1] - lo[1]), float(c[2] - lo[2]), 6.5)
+    want = orc.protein_desolv(rec, step, dims, shell_bytes, roi)
+    prot = ref.Mol(xs, ys, zs, qq, m.anum[near])
+    got = ref.protein_desolv(roi, g, shell, prot)
+    assert got == list(want)
+    assert np.count_nonzero(want) > 50
+    # a shrunken ligand pose next to the protein surface: both terms of the penalty
+    lig = c2["lig"]
+    cx, cy, cz = c2["centered"]
+    nonzero = 0
+    for t, s in ((np.array(roi[:3]) + np.array([0.0, 0.0, 3.0]), 0.35), (np.array(roi[:3]) + np.array([2.0, -1.0, 0.0]), 0.25),
+                 (np.array([4.5, 4.5, 4.5]), 0.05)):
+        px, py, pz = cx * s + t[0], cy * s + t[1], cz * s + t[2]
+        assert min(px.min(), py.min(), pz.min()) > 4.0          # every atom's shell cube stays inside the grid (OCaml would raise)
+        assert px.max() < box[0] - 4.0 and py.max() < box[1] - 4.0 and pz.max() < box[2] - 4.0
+        wp, wl = orc.desolvation_penalty(step, dims, shell_bytes, want, px, py, pz, lig.q, lig.r)
+        gp, gl = ref.desolvation_penalty(g, got, shell, list(zip(px.tolist(), py.tolist(), pz.tolist())), lig.q.tolist(), lig.r.tolist())
+        assert (gp, gl) == (wp, wl), (t, gp, wp, gl, wl)
+        nonzero += (wp != 0.0) + (wl != 0.0)
+    assert nonzero >= 2
