@@ -835,3 +835,33 @@ def desolvation_penalty(grid, contribs, prot_shell, lig_atoms, lig_charges, lig_
                 lig_desolv = lig_desolv + (x * x)
         prot_desolv = prot_desolv + contribs[idx]
     return prot_desolv, DESOLVATION * (voxel_vol * lig_desolv)
+
+
+# ---------------------------------------------------------------------------------------------- lds.ml N3 bitmasks
+def bitmask_whole_protein(grid, atoms):         # lds.ml:97-145: nearest protein atom closer than Const.charged_cutoff
+    mask = [False] * (grid.x_dim * grid.y_dim * grid.z_dim)
+    for i in range(grid.x_dim):
+        x = grid.xs[i]
+        for j in range(grid.y_dim):
+            y = grid.ys[j]
+            for k in range(grid.z_dim):
+                p = (x, y, grid.zs[k])
+                # BST.nearest_neighbor returns the distance to the closest atom: min over atoms of V3.dist
+                if min(dist(p, a) for a in atoms) < CHARGED_CUTOFF:
+                    mask[i + j * grid.x_dim + k * grid.xy_dim] = True
+    return mask
+
+
+def bitmask_ROI_only(roi, grid):                # lds.ml:269-305
+    c = roi[:3]
+    r = roi[3] + (CHARGED_CUTOFF * 2.0)
+    r2 = r * r
+    mask = [False] * (grid.x_dim * grid.y_dim * grid.z_dim)
+    for i in range(grid.x_dim):
+        x = grid.xs[i]
+        for j in range(grid.y_dim):
+            y = grid.ys[j]
+            for k in range(grid.z_dim):
+                if dist2(c, (x, y, grid.zs[k])) < r2:
+                    mask[i + j * grid.x_dim + k * grid.xy_dim] = True
+    return mask

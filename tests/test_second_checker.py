@@ -297,3 +297,24 @@ def test_desolvation_sums_bit_for_bit(orc, c2):
         assert (gp, gl) == (wp, wl), (t, gp, wp, gl, wl)
         nonzero += (wp != 0.0) + (wl != 0.0)
     assert nonzero >= 2
+
+
+def test_n3_bitmasks_bit_for_bit(orc, c2):
+    """Lds.bitmask_whole_protein (lds.ml:97-145) and Lds.bitmask_ROI_only (lds.ml:269-305) on a coarse grid"""
+    m = c2["rec"]
+    c = np.array(c2["roi"][:3])
+    near = np.where((m.xs - c[0]) ** 2 + (m.ys - c[1]) ** 2 + (m.zs - c[2]) ** 2 < 7.0 ** 2)[0][:60]
+    lo = np.array([m.xs[near].min(), m.ys[near].min(), m.zs[near].min()]) - 16.0
+    xs, ys, zs = m.xs[near] - lo[0], m.ys[near] - lo[1], m.zs[near] - lo[2]
+    box = (float(xs.max() + 16.0), float(ys.max() + 16.0), float(zs.max() + 16.0))
+    step = 2.0
+    dims = orc.grid_from_box(step, *box)
+    g = ref.Grid(step, *box)
+    nvox = dims[0] * dims[1] * dims[2]
+    whole = ref.bitmask_whole_protein(g, list(zip(xs.tolist(), ys.tolist(), zs.tolist())))
+    assert whole == _bits(orc.bitmask_whole_protein(xs, ys, zs, step, dims), nvox)
+    assert 0 < sum(whole) < nvox
+    roi = (float(c[0] - lo[0]), float(c[1] - lo[1]), float(c[2] - lo[2]), 3.0)
+    only = ref.bitmask_ROI_only((roi[0], roi[1], roi[2], 3.0 - 24.0 + 9.0), g)        # out radius chosen so that the sphere cuts the grid
+    want = _bits(orc.bitmask_sphere(step, dims, roi[:3], (3.0 - 24.0 + 9.0) + 12.0 * 2.0), nvox)
+    assert only == want and 0 < sum(only) < nvox
